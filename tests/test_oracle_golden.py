@@ -1,0 +1,149 @@
+"""Pin oracle/openobj_oracle.py against the golden vectors frozen from the unmodified
+reference by oracle/make_golden.py (CPU, no GPU needed)."""
+import json
+import os
+
+import numpy as np
+import pytest
+import torch
+
+import openobj_oracle as oc
+
+GOLDEN = os.path.join(os.path.dirname(__file__), "golden")
+
+
+def load(name):
+    d = np.load(os.path.join(GOLDEN, name))
+    return {k: torch.from_numpy(d[k]) for k in d.files}
+
+
+def params(d):
+    return [d["fc%02d" % i] for i in range(18)], d["peB"]
+
+
+def close(a, b, rtol=1e-4, atol=1e-6):
+    torch.testing.assert_close(a, b, rtol=rtol, atol=atol)
+
+
+# parameters after k AdamW steps: SURVEY 8(d) asks rel 1e-3.  Adam's normalised update
+# lr*m/(sqrt(v)+eps) turns round-off in a near-zero gradient (|g| ~ eps) into an O(lr) step, so a
+# handful of elements fed by almost-dead ReLU units move by a fraction of lr=1e-3: atol 2e-4.
+PTOL = dict(rtol=1e-3, atol=2e-4)
+
+
+@pytest.fixture(scope="module")
+def ms():
+    return load("model_step.npz")
+
+
+def test_pe_and_mlp_forward(ms):
+    fc, B = params(ms)
+    emb = oc.pe_forward(ms["pcs"], B, 2.0)
+    close(emb, ms["emb"], rtol=1e-5, atol=2e-5)
+    a, c, f = oc.mlp_forward(fc, ms["emb"])
+    close(a, ms["alpha"], rtol=1e-5, atol=1e-5)
+    close(c, ms["color"], rtol=1e-5, atol=1e-6)
+    close(f, ms["clip"], rtol=1e-5, atol=1e-5)
+
+
+@pytest.mark.parametrize("mode", ["on", "off", "zm"])
+def test_loss_and_grads(ms, mode):
+    fc, B = params(ms)
+    rgb = ms["gt_rgb8"] / 255.
+    labels = ms["labels_zm"] if mode == "zm" else ms["labels"]
+    gt_feat = None if mode == "off" else ms["gt_feat"]
+    terms, grads = oc.train_step_grads(fc, B, ms["pcs"], ms["z"], ms["gt_depth"], rgb, labels, gt_feat)
+    close(terms.total, ms["loss_" + mode], rtol=1e-5, atol=1e-6)
+    if mode == "zm":
+        assert terms.flags & 2
+        assert float(terms.depth.abs().sum() + terms.color.abs().sum() + terms.feat.abs().sum()) == 0.0
+    none_idx = set(ms["g_off_none"].tolist()) if mode == "off" else set()
+    for i, g in enumerate(grads):
+        if i in none_idx:
+            assert g is None
+            continue
+        ref = ms["g_%s%02d" % (mode, i)]
+        got = g if g is not None else torch.zeros_like(ref)
+        close(got, ref, rtol=1e-4, atol=1e-7)
+    if mode == "off":
+        assert none_idx == {14, 15, 16, 17}
+
+
+def test_adamw_three_plus_two_steps(ms):
+    fc, B = params(ms)
+    P = [p.clone() for p in fc] + [B.clone()]
+    M = [torch.zeros_like(p) for p in P]
+    V = [torch.zeros_like(p) for p in P]
+    rgb = ms["gt_rgb8"] / 255.
+    losses = []
+    steps = [0] * len(P)
+    for it in range(5):
+        gt_feat = ms["gt_feat"] if it < 3 else None
+        terms, grads = oc.train_step_grads(P[:18], P[18], ms["pcs"], ms["z"], ms["gt_depth"], rgb,
+                                           ms["labels"], gt_feat)
+        losses.append(terms.total)
+        for i, g in enumerate(grads):
+            if g is None:          # AdamW skips tensors without grad entirely (no decay)
+                continue
+            steps[i] += 1
+            oc.adamw_step(P[i], g, M[i], V[i], steps[i])
+        if it == 2:
+            close(torch.stack(losses), ms["losses_3"], rtol=1e-5, atol=1e-6)
+            for i in range(19):
+                close(P[i], ms["p3_%02d" % i], **PTOL)
+    for i in range(19):
+        close(P[i], ms["p5_%02d" % i], **PTOL)
+
+
+@pytest.mark.parametrize("name", ["sample_obj.npz", "sample_bg.npz"])
+def test_sampling_bit_exact(name):
+    d = load(name)
+    tape = oc.SampleTape(d["kf_ids"], d["u_w"], d["u_h"], d["r_invalid"], d["r_valid"],
+                         d["r_normal"], d["r_other"])
+    out = oc.sample_object(d["rgbs_batch"], d["depth_batch"], d["t_wc_batch"], d["bbox"], d["rays_dir"],
+                           tape, n_c2s=int(d["n_c2s"]), n_bins=int(d["n_bins"]),
+                           use_frame=d["use_frame"], stride=int(d["stride"]), part_down=int(d["part_down"]))
+    assert torch.equal(out["rgb"], d["gt_rgb"])
+    assert torch.equal(out["depth"], d["gt_depth"])
+    assert torch.equal(out["valid"], d["valid"])
+    assert torch.equal(out["labels"], d["labels"])
+    assert torch.equal(out["z"], d["z"])
+    assert torch.equal(out["pcs"], d["pcs"])
+    pf = d["global_partfeat"][out["pf"], out["pw"], out["ph"]]
+    assert torch.equal(pf, d["partfeat"])
+
+
+def test_render_object():
+    d = load("render_obj.npz")
+    fc, B = params(d)
+    r = oc.render_object(fc, B, d["T_wc"].float(), d["rays_dir"], d["obb_R"].float(), d["obb_center"].float(),
+                         d["obb_extent"].float(), d["jitter"], scale=2.0)
+    assert torch.equal(r["mask"], d["mask"])
+    m = r["mask"]
+    close(r["depth"][m], d["depth"], rtol=1e-5, atol=1e-6)
+    diff = (r["rgb"][m].int() - d["color"].int()).abs()
+    assert int(diff.max()) <= 1            # u8 truncation: +-1 LSB
+    assert float((diff > 0).float().mean()) < 0.01
+    close(r["feat"][m], d["feat"], rtol=1e-4, atol=1e-5)
+
+
+def test_zmerge_rule():
+    W, H = 4, 3
+    m0 = torch.ones(W, H, dtype=torch.bool)
+    d0 = torch.full((W, H), 2.0)
+    m1 = torch.zeros(W, H, dtype=torch.bool); m1[:2] = True
+    d1 = torch.full((W, H), 1.0)
+    m2 = torch.ones(W, H, dtype=torch.bool)
+    d2 = torch.full((W, H), 1.5)
+    c = [torch.full((W, H, 3), v, dtype=torch.uint8) for v in (10, 20, 30)]
+    # object 0 is a "bg id": paints but does not write depth
+    dbuf, cbuf, win, _ = oc.zmerge([m0, m1, m2], [d0, d1, d2], c, [True, False, False])
+    assert win[:2].eq(1).all() and win[2:].eq(2).all()
+    assert dbuf[:2].eq(1.0).all() and dbuf[2:].eq(1.5).all()
+    assert cbuf[0, 0, 0] == 20 and cbuf[3, 0, 0] == 30
+
+
+def test_keyframe_policy_fixture_sane():
+    t = json.load(open(os.path.join(GOLDEN, "keyframe_policy.json")))
+    assert t["keyframe_step"] == 2.5 and t["buffer"] == 20
+    assert t["trace"][-1]["n_keyframes"] == 19
