@@ -1,0 +1,202 @@
+/*
+ * openobj_b200 -- C ABI of the B200-native (sm_100a) replacement for OpenObj's
+ * vectorised per-object NeRF training hot path (reference: BIT-DYN/OpenObj, objnerf/).
+ *
+ * The reference has no FFI layer: its boundary is the Python call surface used by
+ * objnerf/train.py.  The Python modules under openobj_b200/ keep those names and
+ * signatures and call the entry points below through ctypes.
+ *
+ * Conventions
+ *   - every pointer is a DEVICE pointer unless the name ends in _host;
+ *   - the library borrows pointers for the duration of a call and allocates nothing
+ *     the caller can see; all launches are asynchronous on `stream` (a cudaStream_t
+ *     passed as void*);
+ *   - return value: 0 = OK, negative = error (message via oo_last_error());
+ *     no C++ exception or abort() crosses this boundary;
+ *   - "theta" is the stacked parameter block [n_obj][OO_PSTRIDE] (float32); tensor i of
+ *     the reference's named_parameters() order lives at oo_param_offset(i) inside an
+ *     object's block, row-major exactly as the reference stores it, so the Python side
+ *     exposes the 19 stacked tensors of utils.update_vmap (objnerf/utils.py:55-62) as
+ *     strided views of one buffer.
+ *   - frames are [W][H]-major like the reference (objnerf/dataset.py:100-106).
+ */
+#ifndef OPENOBJ_B200_H
+#define OPENOBJ_B200_H
+
+#include <stdint.h>
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+#define OO_ABI_VERSION 1
+#define OO_N_TENSORS 19        /* 18 OccupancyMap tensors (model.py:31-56) + UniDirsEmbed.B_layer.weight (embedding.py:39) */
+#define OO_PCOUNT 30659        /* trainable floats per object */
+#define OO_PSTRIDE 30720       /* floats between consecutive objects' blocks (16-byte aligned tensors, 128-byte aligned blocks) */
+#define OO_HIDDEN 32           /* hidden_feature_size (configs/Replica/room_0.json:53) */
+#define OO_CLIP 512            /* clip_point_feature_size (room_0.json:55) */
+#define OO_EMB 129             /* 3 + 21*6 (embedding.py:47-53) */
+#define OO_EMB1 87             /* trainer.py:20 */
+#define OO_NSAMP 10            /* n_bins_cam2surface + n_bins (room_0.json:31-32) */
+#define OO_TILE_RAYS 10        /* rays one CTA tile processes */
+
+/* flags written by oo_label_counts / oo_loss_* (reference: render_rays.py:89-94,109-111) */
+#define OO_FLAG_EXPLODE 1      /* some per-object loss term > 1e5: the reference prints and exit(-1)s */
+#define OO_FLAG_NO_OBJ 2       /* some object has no label==1 ray: depth/colour/feature terms are 0 for ALL objects */
+#define OO_FLAG_NO_SEM 4       /* some object has no label!=2 ray: opacity term is 0 for ALL objects */
+
+int oo_version(void);
+const char* oo_last_error(void);
+
+/* offset (floats) and element count of tensor i (0..18) inside an object's block. */
+int oo_param_offset(int i);
+int oo_param_size(int i);
+
+/* ---- a2+a3: vmap(pe_model) -> vmap(fc_model) forward (objnerf/train.py:424-425,
+ *      embedding.py:46-55, model.py:61-103).  pcs [n_obj][n_pts][3]; outputs alpha [n_obj][n_pts]
+ *      (already x10), color [n_obj][n_pts][3] (after sigmoid), clip [n_obj][n_pts][512] or NULL.
+ *      emb_out [n_obj][n_pts][129] or NULL. n_pts must be a multiple of 4. */
+int oo_forward(const float* theta, int n_obj, const float* pcs, int n_pts, float scale,
+               float* alpha, float* color, float* clip, float* emb_out, void* stream);
+
+/* ---- a4-a9: loss.step_batch_loss forward and backward as one pair of HBM-bound kernels
+ *      (objnerf/loss.py:5-103, render_rays.py:6-117).  alpha [N][R][S], color [N][R][S][3],
+ *      z [N][R][S], gt_depth [N][R], gt_color [N][R][3] float in [0,1], labels [N][R] u8,
+ *      pred_feat [N][R][S][C] / gt_feat [N][R][C] or both NULL.
+ *      terms_out [N][4] = per-object depth, colour, opacity, feature terms (after the zero-mask rule);
+ *      loss_out [1] = sum_obj (d + cs*c + os*o + fs*f); flags_out [1] int.
+ *      Backward writes d_alpha, d_color, d_pred_feat (same shapes; d_pred_feat NULL iff pred_feat NULL)
+ *      for upstream gradient grad_loss (host scalar). */
+int oo_loss_fwd(const float* alpha, const float* color, const float* z, const float* gt_depth,
+                const float* gt_color, const uint8_t* labels, const float* pred_feat, const float* gt_feat,
+                int n_obj, int n_rays, int n_samp, int n_feat,
+                float color_scaling, float opacity_scaling, float feat_scaling,
+                float* terms_out, float* loss_out, int* flags_out, float* ray_ws, void* stream);
+int oo_loss_bwd(const float* alpha, const float* color, const float* z, const float* gt_depth,
+                const float* gt_color, const uint8_t* labels, const float* pred_feat, const float* gt_feat,
+                int n_obj, int n_rays, int n_samp, int n_feat,
+                float color_scaling, float opacity_scaling, float feat_scaling, float grad_loss,
+                const int* flags, const float* ray_ws,
+                float* d_alpha, float* d_color, float* d_pred_feat, void* stream);
+/* floats of workspace per (object, ray) that oo_loss_fwd leaves for oo_loss_bwd */
+int oo_loss_ws_per_ray(void);
+
+/* ---- fused training path (a1-a11 in one step: train.py:394-474) ------------------------- */
+
+typedef struct oo_batch {
+    const float*   pcs;        /* [n_obj][rays_per_obj][S][3]  sampled points        (train.py:371) */
+    const float*   z;          /* [n_obj][rays_per_obj][S]     sampled depths        (train.py:376) */
+    const float*   gt_depth;   /* [n_obj][rays_per_obj]                               (train.py:372) */
+    const uint8_t* gt_rgb;     /* [n_obj][rays_per_obj][3] u8; /255 happens in-kernel (train.py:373) */
+    const uint8_t* labels;     /* [n_obj][rays_per_obj] 0 other / 1 this / 2 unknown  (train.py:375) */
+    const int32_t* feat_row;   /* [n_obj][rays_per_obj] row of `feat_table` holding the ray's gt part feature, or NULL = part_mode off */
+    const float*   feat_table; /* [rows][512] (global_partfeat flattened, train.py:183-188; or the materialised Batch_N_gt_partfeat) */
+    int rays_per_obj;          /* iters_per_frame * n_per_optim = 12000 */
+} oo_batch;
+
+typedef struct oo_train_ws {   /* caller-allocated scratch; sizes from oo_train_ws_sizes() */
+    float* slab;               /* [n_slots][OO_PSTRIDE] per-(CTA,object) gradient partials */
+    float* slot_loss;          /* [n_slots][4] */
+    float* wocl_t;             /* [n_obj][32][512] transposed copy of out_clip.weight kept in sync by oo_adamw_step */
+    int*   sched;              /* device copy of the static schedule */
+    int*   counts;             /* [iters][n_obj][2] label==1 / label!=2 ray counts per step */
+    int*   flags;              /* [iters] OO_FLAG_* per step (OR over objects; all-reduce across ranks when sharded) */
+    float* adam_scal;          /* [iters][3][4]: per step and parameter group {active, lr/bc1, 1/sqrt(bc2), 0} */
+    int*   adam_t;             /* [3] persistent Adam step counters per group (trunk+alpha+PE, colour head, clip head) */
+} oo_train_ws;
+
+/* number of CTAs the fused step launches and the scratch sizes (in elements) it needs. */
+int oo_train_ws_sizes(int n_obj, int rays_per_step, int iters, int n_sm,
+                      int* n_cta, int* n_slots, int64_t* slab_floats, int64_t* sched_ints);
+/* build the static ray-range schedule on the host and copy it to ws->sched (synchronous, once per ensemble rebuild). */
+int oo_train_schedule(int n_obj, int rays_per_step, int n_sm, oo_train_ws* ws, void* stream);
+/* refresh ws->wocl_t from theta (after the caller wrote parameters, e.g. utils.update_vmap). */
+int oo_sync_wocl_t(const float* theta, int n_obj, oo_train_ws* ws, void* stream);
+
+/* per frame: ray counts + zero-mask flags for every step (render_rays.py:88-94 evaluated up front),
+ * then the Adam step/bias-correction schedule (torch.optim.AdamW bookkeeping, train.py:473).
+ * Sharded runs all-reduce(OR) ws->flags between the two calls. */
+int oo_label_counts(const uint8_t* labels, int n_obj, int rays_per_obj, int rays_per_step, int iters,
+                    int* counts, int* flags, void* stream);
+int oo_adam_schedule(const int* flags, int iters, int part_on, float lr, float beta1, float beta2,
+                     int* adam_t, float* adam_scal, void* stream);
+
+/* one optimisation step `it` of the whole ensemble: encode + MLP + compositing + loss + backward (K1),
+ * then fused multi-tensor AdamW over the stacked blocks (K4).  loss_terms [n_obj][4] (this step) or NULL. */
+int oo_train_step(float* theta, float* adam_m, float* adam_v, int n_obj, const oo_batch* batch, int it,
+                  int rays_per_step, float scale, float lr, float weight_decay, float beta1, float beta2, float eps,
+                  oo_train_ws* ws, float* loss_terms, int n_sm, void* stream);
+/* gradients only (no parameter update): grads_out [n_obj][OO_PSTRIDE] in theta layout. For parity tests and
+ * for the autograd-facing Python surface. */
+int oo_train_grads(const float* theta, int n_obj, const oo_batch* batch, int it, int rays_per_step, float scale,
+                   oo_train_ws* ws, float* grads_out, float* loss_terms, int n_sm, void* stream);
+/* `iters` consecutive steps (train.py:394 loop); loss_terms [iters][n_obj][4] or NULL. */
+int oo_train_frame(float* theta, float* adam_m, float* adam_v, int n_obj, const oo_batch* batch, int iters,
+                   int rays_per_step, float scale, float lr, float weight_decay, float beta1, float beta2, float eps,
+                   oo_train_ws* ws, float* loss_terms, int n_sm, void* stream);
+
+/* a11 standalone: torch.optim.AdamW over a flat float buffer. step is 1-based. */
+int oo_adamw_flat(float* p, const float* g, float* m, float* v, int64_t n, int step,
+                  float lr, float weight_decay, float beta1, float beta2, float eps, void* stream);
+
+/* ---- a13-a15: sceneObject.get_training_samples + sample_3d_points for ALL objects in one launch
+ *      (objnerf/vmap.py:386-554, utils.py:324-397).  Keyframe rings stay in the reference's layout and
+ *      are addressed through per-object pointer tables. */
+typedef struct oo_sample_args {
+    int n_obj, n_frames, n_samples;      /* per object: n_frames keyframe draws x n_samples pixels (500 x 24) */
+    int W, H, n_c2s, n_bins;             /* frame size; 1 + 9 samples per ray */
+    float eps, other_eps, min_bound;     /* surface_eps 0.1, other_eps 0.05, min_depth 0 */
+    int part_down;                       /* 5; 0 = part_mode off */
+    int pw, ph;                          /* part map size (W/part_down, H/part_down) */
+    const uint8_t* const* rgbs;          /* [n_obj] -> u8 [KF][W][H][4]  (vmap.py:97-102) */
+    const float* const*   depth;         /* [n_obj] -> f32 [KF][W][H]    (vmap.py:131-135) */
+    const float* const*   t_wc;          /* [n_obj] -> f32 [KF][4][4]    (vmap.py:139-142) */
+    const float* const*   bbox;          /* [n_obj] -> f32 [KF][4] = w_lo,w_hi,h_lo,h_hi (vmap.py:84-89) */
+    const int32_t*        part_frame;    /* [n_obj][KF_MAX=20] (use_frame/stride).long()  (vmap.py:438-440) */
+    const float*          rays_dir;      /* [W][H][3] cameraInfo.rays_dir_cache (vmap.py:701-720) */
+    /* RNG tape; rows of the class tapes are consumed by rank within the class */
+    const int64_t* kf_ids;               /* [n_obj][n_frames] */
+    const float* u_w;                    /* [n_obj][n_frames*n_samples] */
+    const float* u_h;
+    const float* r_invalid;              /* [n_obj][n_rays][S]      */
+    const float* r_valid;                /* [n_obj][n_rays][n_c2s]  */
+    const float* r_normal;               /* [n_obj][n_rays][n_bins] normal_(0, eps/3) draws, unsorted */
+    const float* r_other;                /* [n_obj][n_rays][n_bins] */
+    int tape_by_rank;                    /* 1: reference order (row j -> j-th ray of the class); 0: row = ray index */
+    /* outputs, all [n_obj][n_rays...] */
+    uint8_t* gt_rgb; float* gt_depth; uint8_t* valid; uint8_t* labels;
+    float* pcs; float* z; int32_t* feat_row; int64_t* pix;   /* pix [n_obj][n_rays][3] = kf, w, h */
+    int* oob_count;                      /* [1] rays whose pixel index had to be clamped (quirk 11) */
+} oo_sample_args;
+int oo_sample_rays(const oo_sample_args* a, void* stream);
+/* counter-based uniform / normal tapes keyed by (seed, frame, object id, element) -- shard independent. */
+int oo_rng_fill(uint64_t seed, uint32_t frame, const int32_t* obj_ids, int n_obj, int64_t per_obj,
+                int kind /*0 uniform [0,1), 1 normal(0,std)*/, float std, float* out, void* stream);
+
+/* ---- a19: render_2D_syn for one object over all W*H pixels (vmap.py:604-685, trainer.py:130-198)
+ *      and the sequential depth-test merge (train.py:577-594). */
+typedef struct oo_render_args {
+    int W, H, n_bins;                    /* 150 bins -> 149 midpoints */
+    float scale;
+    const float* theta1;                 /* this object's parameter block */
+    const float* T_wc;                   /* [4][4] f32 */
+    const float* T_oc;                   /* [4][4] f32 = inv(T_WO) @ T_WC (trainer.py:157-160, computed by the caller) */
+    const float* half_extent;            /* [3] */
+    const float* rays_dir;               /* [W][H][3] */
+    const float* jitter;                 /* [W*H][n_bins] uniform draws */
+    int jitter_by_rank;                  /* 1: row j -> j-th hit ray (reference order) */
+    uint8_t* mask; float* depth; uint8_t* rgb; float* feat;  /* [W][H], [W][H], [W][H][3], [W][H][512] or NULL */
+    float* opacity;                      /* [W][H] or NULL */
+    int* n_hit;                          /* [1] */
+} oo_render_args;
+int oo_render_object(const oo_render_args* a, void* stream);
+int oo_zmerge(const uint8_t* masks, const float* depths, const uint8_t* rgbs, const uint8_t* is_bg, int n_obj,
+              int64_t n_pix, float* depth_out, uint8_t* rgb_out, int32_t* winner_out, void* stream);
+
+/* FP32 FFMA-pipe peak probe used as the roofline denominator of the fused step. */
+int oo_fma_peak(int n_sm, int iters, float* sink, void* stream);
+
+#ifdef __cplusplus
+}
+#endif
+#endif

@@ -1,0 +1,834 @@
+// One fused tile of the per-object NeRF training step: 10 rays x 10 samples of ONE object.
+//
+//   encode (UniDirsEmbed, embedding.py:46-55) -> OccupancyMap MLP (model.py:61-103)
+//   -> occupancy/termination compositing (render_rays.py:6-63) -> losses (loss.py:5-103)
+//   -> hand-derived backward of all of it, weight gradients accumulated in registers.
+//
+// The tile is written as a list of PHASES; inside a phase every thread works on private outputs and the
+// only communication is through shared memory, with a block barrier between phases.  That makes the
+// same source compilable for the device (oo_train.cu: phase<k>(threadIdx.x); __syncthreads();) and for
+// the host-side tile emulator the CPU tests use to check the index algebra (tests/emu: for every tid:
+// phase<k>(tid)).  The emulator is test infrastructure; the product path is the CUDA kernel only.
+//
+// Data layout (see oo_layout.h): activations feature-major  A[row][p]  (p = 10*ray + sample),
+// weights row-major [out][in] with padded row strides so that 8 consecutive rows hit 8 distinct
+// 16-byte bank groups; all inner loops are 4x4 register tiles fed by 128-bit shared loads
+// (8 FFMA per LDS.128).  The 512-wide out_clip layer is linear and only ever consumed through the
+// compositing sum, so it is applied once per RAY to S = sum_i T_i hp_i instead of once per sample
+// (SURVEY 8d "legal algebraic restructure"): feat = W S + b*opacity.
+#pragma once
+#include <math.h>
+#include <stdint.h>
+
+#include "oo_layout.h"
+
+#ifdef __CUDACC__
+#define OO_DEV __device__ __forceinline__
+#define OO_LDG(p) __ldg(p)
+#else
+#define OO_DEV inline
+#define OO_LDG(p) (*(p))
+struct alignas(16) float4 {
+    float x, y, z, w;
+};
+#endif
+
+namespace oo {
+
+OO_DEV float4 ld4(const float* p) { return *reinterpret_cast<const float4*>(p); }
+OO_DEV void st4(float* p, const float4& v) { *reinterpret_cast<float4*>(p) = v; }
+OO_DEV float sigmoidf_(float x) { return 1.0f / (1.0f + expf(-x)); }
+OO_DEV float sgnf_(float x) { return x > 0.f ? 1.f : (x < 0.f ? -1.f : 0.f); }
+
+// register-resident weight-gradient accumulators of one thread (live across all tiles of an object)
+struct TileAcc {
+    float in[16];    // in_layer   : rows ji+8jj, cols ki+22kk          (tid < 176)
+    float cat[16];   // cat_layer  : rows ji+8jj, cols ki+30kk          (tid < 240)
+    float m1[16];    // mid1       : rows ji+8jj, cols ki+8kk, point group tid>>6
+    float m2[16];    // mid2
+    float hd[32];    // [color_linear ; clip_linear] : rows ji+8jj (jj<8), cols ki+19kk (tid < 152)
+    float s0;        // out_color.weight (tid<96), out_alpha.weight (96<=tid<128)
+    float s1;        // biases of the six hidden layers (tid<192), out_color.bias (192..194), out_alpha.bias (195)
+    float s2;        // B_layer.weight (tid<63)
+    float loss[4];   // per-ray loss partials (tid<10): depth, colour, opacity, feature
+};
+
+OO_DEV void acc_zero(TileAcc& a) {
+#pragma unroll
+    for (int i = 0; i < 16; ++i) a.in[i] = a.cat[i] = a.m1[i] = a.m2[i] = 0.f;
+#pragma unroll
+    for (int i = 0; i < 32; ++i) a.hd[i] = 0.f;
+    a.s0 = a.s1 = a.s2 = 0.f;
+    a.loss[0] = a.loss[1] = a.loss[2] = a.loss[3] = 0.f;
+}
+
+// everything a tile needs that is uniform across the block
+struct TileCtx {
+    const float* pcs;          // first ray of the tile: [nrays][S][3]
+    const float* z;            // [nrays][S]
+    const float* gt_depth;     // [nrays]
+    const uint8_t* gt_rgb;     // [nrays][3]
+    const uint8_t* labels;     // [nrays]
+    const int32_t* feat_row;   // [nrays] or nullptr
+    const float* feat_table;   // [rows][512]
+    const float* theta;        // this object's parameter block
+    const float* wocl_t;       // this object's out_clip.weight transposed [32][512]
+    float* slab;               // gradient slab of the current (CTA, object) slot
+    int nrays;                 // <= RT
+    int first_tile;            // first tile of this slot: out_clip gradient is stored, not accumulated
+    int flags;                 // OO_FLAG_NO_OBJ (2) / OO_FLAG_NO_SEM (4) for this step
+    float scale;               // UniDirsEmbed scale
+    float inv1, invs;          // 1/(n(label==1)+1e-10), 1/(n(label!=2)+1e-10) of this object in this step
+    float cs, os, fs;          // colour / opacity / feature scaling (loss.py:6)
+};
+
+// ------------------------------------------------------------------------------------------------
+// register-tiled building blocks
+// ------------------------------------------------------------------------------------------------
+
+// Y[j][p] = act(b[j] + sum_k W[j][k] X[k][p]), 32 output rows, P points.  200 threads: rows ji+8jj, points 4pi..4pi+3
+template <int K, int WS, bool RELU>
+OO_DEV void gemm_fwd(int tid, const float* __restrict__ W, const float* __restrict__ bias,
+                     const float* __restrict__ X, float* __restrict__ Y) {
+    if (tid >= 8 * (P / 4)) return;
+    const int ji = tid & 7, pi = tid >> 3;
+    float acc[4][4];
+#pragma unroll
+    for (int jj = 0; jj < 4; ++jj) {
+        const float b = bias[ji + 8 * jj];
+        acc[jj][0] = acc[jj][1] = acc[jj][2] = acc[jj][3] = b;
+    }
+    const float* wp = W + ji * WS;
+    const float* xp = X + 4 * pi;
+#pragma unroll 2
+    for (int k0 = 0; k0 < K; k0 += 4) {
+        float4 w[4], x[4];
+#pragma unroll
+        for (int jj = 0; jj < 4; ++jj) w[jj] = ld4(wp + jj * 8 * WS + k0);
+#pragma unroll
+        for (int kk = 0; kk < 4; ++kk) x[kk] = ld4(xp + (k0 + kk) * PS);
+#pragma unroll
+        for (int jj = 0; jj < 4; ++jj) {
+            acc[jj][0] += w[jj].x * x[0].x + w[jj].y * x[1].x + w[jj].z * x[2].x + w[jj].w * x[3].x;
+            acc[jj][1] += w[jj].x * x[0].y + w[jj].y * x[1].y + w[jj].z * x[2].y + w[jj].w * x[3].y;
+            acc[jj][2] += w[jj].x * x[0].z + w[jj].y * x[1].z + w[jj].z * x[2].z + w[jj].w * x[3].z;
+            acc[jj][3] += w[jj].x * x[0].w + w[jj].y * x[1].w + w[jj].z * x[2].w + w[jj].w * x[3].w;
+        }
+    }
+#pragma unroll
+    for (int jj = 0; jj < 4; ++jj) {
+        float4 y;
+        y.x = acc[jj][0]; y.y = acc[jj][1]; y.z = acc[jj][2]; y.w = acc[jj][3];
+        if (RELU) {
+            y.x = fmaxf(y.x, 0.f); y.y = fmaxf(y.y, 0.f); y.z = fmaxf(y.z, 0.f); y.w = fmaxf(y.w, 0.f);
+        }
+        st4(Y + (ji + 8 * jj) * PS + 4 * pi, y);
+    }
+}
+
+// DX[k][p] = [k < relu_rows ? (X[k][p] > 0) : 1] * ( sum_{j<J0} W0[j][k] DY0[j][p] + sum_{j<J1} W1[j][k] DY1[j][p]
+//            + [k < 32 && wa] wa[k] * draw[p] ),  written IN PLACE over X (rows 0..K-1).  K % 4 == 0.
+template <int K, int WS0, int J0, int WS1, int J1>
+OO_DEV void gemm_bwd_data(int tid, const float* __restrict__ W0, const float* __restrict__ DY0,
+                          const float* __restrict__ W1, const float* __restrict__ DY1,
+                          float* X, int relu_rows, const float* wa, const float* draw) {
+#pragma unroll
+    for (int kb = 0; kb < K; kb += 32) {
+        const int nk = ((K - kb) >= 32 ? 32 : (K - kb)) / 4;   // k-groups in this block of rows
+        if (tid < nk * (P / 4)) {
+            const int ki = tid % nk, pi = tid / nk;
+            const int k0 = kb + 4 * ki;
+            float acc[4][4];
+#pragma unroll
+            for (int kk = 0; kk < 4; ++kk) acc[kk][0] = acc[kk][1] = acc[kk][2] = acc[kk][3] = 0.f;
+#pragma unroll 4
+            for (int j = 0; j < J0; ++j) {
+                const float4 w = ld4(W0 + j * WS0 + k0);
+                const float4 d = ld4(DY0 + j * PS + 4 * pi);
+                acc[0][0] += w.x * d.x; acc[0][1] += w.x * d.y; acc[0][2] += w.x * d.z; acc[0][3] += w.x * d.w;
+                acc[1][0] += w.y * d.x; acc[1][1] += w.y * d.y; acc[1][2] += w.y * d.z; acc[1][3] += w.y * d.w;
+                acc[2][0] += w.z * d.x; acc[2][1] += w.z * d.y; acc[2][2] += w.z * d.z; acc[2][3] += w.z * d.w;
+                acc[3][0] += w.w * d.x; acc[3][1] += w.w * d.y; acc[3][2] += w.w * d.z; acc[3][3] += w.w * d.w;
+            }
+            if (J1 > 0) {
+#pragma unroll 4
+                for (int j = 0; j < J1; ++j) {
+                    const float4 w = ld4(W1 + j * WS1 + k0);
+                    const float4 d = ld4(DY1 + j * PS + 4 * pi);
+                    acc[0][0] += w.x * d.x; acc[0][1] += w.x * d.y; acc[0][2] += w.x * d.z; acc[0][3] += w.x * d.w;
+                    acc[1][0] += w.y * d.x; acc[1][1] += w.y * d.y; acc[1][2] += w.y * d.z; acc[1][3] += w.y * d.w;
+                    acc[2][0] += w.z * d.x; acc[2][1] += w.z * d.y; acc[2][2] += w.z * d.z; acc[2][3] += w.z * d.w;
+                    acc[3][0] += w.w * d.x; acc[3][1] += w.w * d.y; acc[3][2] += w.w * d.z; acc[3][3] += w.w * d.w;
+                }
+            }
+            if (wa != nullptr && kb == 0) {
+                const float4 dr = ld4(draw + 4 * pi);
+#pragma unroll
+                for (int kk = 0; kk < 4; ++kk) {
+                    const float a = wa[k0 + kk];
+                    acc[kk][0] += a * dr.x; acc[kk][1] += a * dr.y; acc[kk][2] += a * dr.z; acc[kk][3] += a * dr.w;
+                }
+            }
+#pragma unroll
+            for (int kk = 0; kk < 4; ++kk) {
+                float* xp = X + (k0 + kk) * PS + 4 * pi;
+                float4 o;
+                o.x = acc[kk][0]; o.y = acc[kk][1]; o.z = acc[kk][2]; o.w = acc[kk][3];
+                if (k0 + kk < relu_rows) {
+                    const float4 h = ld4(xp);
+                    o.x = h.x > 0.f ? o.x : 0.f; o.y = h.y > 0.f ? o.y : 0.f;
+                    o.z = h.z > 0.f ? o.z : 0.f; o.w = h.w > 0.f ? o.w : 0.f;
+                }
+                st4(xp, o);
+            }
+        }
+    }
+}
+
+// acc[jj*4+kk] += sum_{p in [pa,pb)} DY[ji+8jj][p] * X[ki+KQ*kk][p]
+template <int NJJ, int KQ>
+OO_DEV void gemm_bwd_w(float* acc, int ji, int ki, const float* __restrict__ DY, const float* __restrict__ X,
+                       int pa, int pb) {
+    const float* dp = DY + ji * PS;
+    const float* xp = X + ki * PS;
+    for (int p0 = pa; p0 < pb; p0 += 4) {
+        float4 d[NJJ], x[4];
+#pragma unroll
+        for (int jj = 0; jj < NJJ; ++jj) d[jj] = ld4(dp + jj * 8 * PS + p0);
+#pragma unroll
+        for (int kk = 0; kk < 4; ++kk) x[kk] = ld4(xp + kk * KQ * PS + p0);
+#pragma unroll
+        for (int jj = 0; jj < NJJ; ++jj)
+#pragma unroll
+            for (int kk = 0; kk < 4; ++kk)
+                acc[jj * 4 + kk] += d[jj].x * x[kk].x + d[jj].y * x[kk].y + d[jj].z * x[kk].z + d[jj].w * x[kk].w;
+    }
+}
+
+// ------------------------------------------------------------------------------------------------
+// staging an object's weights into shared memory (padded rows, zero pad columns)
+// ------------------------------------------------------------------------------------------------
+OO_DEV void copy_rows(int tid, float* dst, int ws, const float* __restrict__ src, int rows, int cols, int colsp) {
+    for (int i = tid; i < rows * colsp; i += NTHREADS) {
+        const int r = i / colsp, c = i - r * colsp;
+        dst[r * ws + c] = c < cols ? OO_LDG(src + r * cols + c) : 0.f;
+    }
+}
+
+OO_DEV void stage_weights(int tid, float* sm, const float* __restrict__ th) {
+    float* w = sm + SM_W;
+    copy_rows(tid, w + W_IN, WS_IN, th + OFF_IN_W, H, E1, KP_IN);
+    copy_rows(tid, w + W_M1, WS_H, th + OFF_M1_W, H, H, H);
+    copy_rows(tid, w + W_CAT, WS_CAT, th + OFF_CAT_W, H, H + E1, KP_CAT);
+    copy_rows(tid, w + W_M2, WS_H, th + OFF_M2_W, H, H, H);
+    copy_rows(tid, w + W_CL, WS_HD, th + OFF_CL_W, H, H + E2, KP_HD);
+    copy_rows(tid, w + W_CP, WS_HD, th + OFF_CP_W, H, H + E2, KP_HD);
+    for (int i = tid; i < H; i += NTHREADS) {
+        w[W_A + i] = OO_LDG(th + OFF_A_W + i);
+        w[B_IN + i] = OO_LDG(th + OFF_IN_B + i);
+        w[B_M1 + i] = OO_LDG(th + OFF_M1_B + i);
+        w[B_CAT + i] = OO_LDG(th + OFF_CAT_B + i);
+        w[B_M2 + i] = OO_LDG(th + OFF_M2_B + i);
+        w[B_CL + i] = OO_LDG(th + OFF_CL_B + i);
+        w[B_CP + i] = OO_LDG(th + OFF_CP_B + i);
+    }
+    for (int i = tid; i < 3 * H; i += NTHREADS) w[W_OC + i] = OO_LDG(th + OFF_OC_W + i);
+    for (int i = tid; i < 64; i += NTHREADS) w[W_PE + i] = i < NDIR * 3 ? OO_LDG(th + OFF_PE_B + i) : 0.f;
+    if (tid < 4) {
+        w[B_A + tid] = tid < 1 ? OO_LDG(th + OFF_A_B) : 0.f;
+        w[B_OC + tid] = tid < 3 ? OO_LDG(th + OFF_OC_B + tid) : 0.f;
+    }
+}
+
+// zero the pad rows of e1 / e2 and the spare rows once per kernel
+OO_DEV void zero_pad_rows(int tid, float* sm) {
+    for (int i = tid; i < PS; i += NTHREADS) {
+        sm[(R_E1 + E1) * PS + i] = 0.f;
+        sm[(R_E2 + E2) * PS + i] = 0.f;
+        sm[(R_E2 + E2 + 1) * PS + i] = 0.f;
+        sm[(R_T + 3) * PS + i] = 0.f;
+        sm[(R_MISC + M_HU) * PS + i] = 0.f;
+        sm[(R_MISC + M_HU + 1) * PS + i] = 0.f;
+    }
+    for (int i = tid; i < 2 * H * RP + NRV * RP; i += NTHREADS) sm[SM_ST + i] = 0.f;
+}
+
+// ------------------------------------------------------------------------------------------------
+// phases
+// ------------------------------------------------------------------------------------------------
+constexpr int N_TRAIN_PHASES = 32;
+constexpr int N_FWD_PHASES = 8;    // phases 0..7 are shared with the standalone forward kernel
+
+template <int PH, bool PART>
+OO_DEV void tile_phase(int tid, float* __restrict__ sm, const TileCtx& c, TileAcc& a) {
+    float* act = sm + SM_ACT;
+    float* w = sm + SM_W;
+    float* misc = act + R_MISC * PS;
+    float* rv = sm + SM_RV;
+
+    if constexpr (PH == 0) {
+        // scaled coordinates t = x / scale (embedding.py:47) -> T rows and e1[0:3]
+        const int n = c.nrays * S * 3;
+        for (int i = tid; i < P * 3; i += NTHREADS) {
+            const float x = i < n ? OO_LDG(c.pcs + i) : 0.f;
+            const int p = i / 3, ch = i - 3 * p;
+            const float t = x / c.scale;
+            act[(R_T + ch) * PS + p] = t;
+            act[(R_E1 + ch) * PS + p] = t;
+        }
+    } else if constexpr (PH == 1) {
+        // proj = B t ; e[3 + 21 k + d] = sin(pi * 2^k * proj) (embedding.py:48-53)
+        for (int i = tid; i < NDIR * P; i += NTHREADS) {
+            const int d = i / P, p = i - d * P;
+            const float t0 = act[(R_T + 0) * PS + p], t1 = act[(R_T + 1) * PS + p], t2 = act[(R_T + 2) * PS + p];
+            const float proj = w[W_PE + 3 * d] * t0 + w[W_PE + 3 * d + 1] * t1 + w[W_PE + 3 * d + 2] * t2;
+            float band = 1.f;
+#pragma unroll
+            for (int k = 0; k < NBAND; ++k) {
+                const float s = sinf((proj * band) * PI_F);
+                const int row = 3 + NDIR * k + d;
+                if (row < E1) act[(R_E1 + row) * PS + p] = s;
+                else act[(R_E2 + row - E1) * PS + p] = s;
+                band *= 2.f;
+            }
+        }
+    } else if constexpr (PH == 2) {
+        gemm_fwd<KP_IN, WS_IN, true>(tid, w + W_IN, w + B_IN, act + R_E1 * PS, act + R_H1 * PS);
+    } else if constexpr (PH == 3) {
+        gemm_fwd<H, WS_H, true>(tid, w + W_M1, w + B_M1, act + R_H1 * PS, act + R_H2 * PS);
+    } else if constexpr (PH == 4) {
+        gemm_fwd<KP_CAT, WS_CAT, true>(tid, w + W_CAT, w + B_CAT, act + R_H2 * PS, act + R_H3 * PS);
+    } else if constexpr (PH == 5) {
+        gemm_fwd<H, WS_H, true>(tid, w + W_M2, w + B_M2, act + R_H3 * PS, act + R_H4 * PS);
+    } else if constexpr (PH == 6) {
+        gemm_fwd<KP_HD, WS_HD, true>(tid, w + W_CL, w + B_CL, act + R_H4 * PS, act + R_HC * PS);
+        if (PART) gemm_fwd<KP_HD, WS_HD, true>(tid, w + W_CP, w + B_CP, act + R_H4 * PS, act + R_HP * PS);
+    } else if constexpr (PH == 7) {
+        // out_alpha (x10, model.py:88) -> occupancy = sigmoid (render_rays.py:13); out_color -> sigmoid (model.py:96)
+        for (int i = tid; i < 4 * P; i += NTHREADS) {
+            const int o = i / P, p = i - o * P;
+            if (o == 0) {
+                float r = w[B_A];
+#pragma unroll 8
+                for (int j = 0; j < H; ++j) r += w[W_A + j] * act[(R_H4 + j) * PS + p];
+                misc[M_DRAW * PS + p] = r * 10.f;                  // alpha (kept for the forward-only kernel)
+                misc[M_OCC * PS + p] = sigmoidf_(r * 10.f);
+            } else {
+                const int ch = o - 1;
+                float r = w[B_OC + ch];
+#pragma unroll 8
+                for (int j = 0; j < H; ++j) r += w[W_OC + ch * H + j] * act[(R_HC + j) * PS + p];
+                misc[(M_COL + ch) * PS + p] = sigmoidf_(r);
+            }
+        }
+    } else if constexpr (PH == 8) {
+        // per ray: termination, rendered depth / variance / colour / opacity, loss terms and their
+        // derivatives w.r.t. the rendered quantities (render_rays.py:32-63, loss.py:27-75)
+        if (tid < RT) {
+            const int r = tid;
+            float gd = 0.f, go = 0.f, gc0 = 0.f, gc1 = 0.f, gc2 = 0.f, cf = 0.f;
+            float depth = 0.f, opac = 0.f, c0 = 0.f, c1 = 0.f, c2 = 0.f;
+            if (r < c.nrays) {
+                float zv[S], tv[S];
+                float freep = 1.f;
+#pragma unroll
+                for (int i = 0; i < S; ++i) {
+                    const int p = r * S + i;
+                    const float o = misc[M_OCC * PS + p];
+                    const float t = o * freep;
+                    misc[M_TERM * PS + p] = t;
+                    misc[M_FREE * PS + p] = freep;
+                    zv[i] = OO_LDG(c.z + p);
+                    tv[i] = t;
+                    depth += t * zv[i];
+                    opac += t;
+                    c0 += t * misc[(M_COL + 0) * PS + p];
+                    c1 += t * misc[(M_COL + 1) * PS + p];
+                    c2 += t * misc[(M_COL + 2) * PS + p];
+                    freep *= (1.f - o + 1e-10f);
+                }
+                float var = 0.f;
+#pragma unroll
+                for (int i = 0; i < S; ++i) {
+                    const float dz = zv[i] - depth;
+                    var += tv[i] * (dz * dz);
+                }
+                const int lab = c.labels[r];
+                const bool is1 = lab == 1, sem = lab != 2;
+                const float tgt = lab != 0 ? 1.f : 0.f;
+                if (is1 && !(c.flags & 2)) {
+                    const float wgt = 1.f / (sqrtf(var) + 1e-4f);           // render_rays.py:95-100, var detached
+                    const float dd = depth - OO_LDG(c.gt_depth + r);
+                    a.loss[0] += fabsf(dd) * wgt;
+                    gd = sgnf_(dd) * wgt * c.inv1;
+                    const float e0 = c0 - (float)c.gt_rgb[3 * r + 0] / 255.f;   // train.py:373 `/ 255.`
+                    const float e1 = c1 - (float)c.gt_rgb[3 * r + 1] / 255.f;
+                    const float e2 = c2 - (float)c.gt_rgb[3 * r + 2] / 255.f;
+                    a.loss[1] += fabsf(e0) + fabsf(e1) + fabsf(e2);              // loss.py:61 sum over channels
+                    gc0 = sgnf_(e0) * c.cs * c.inv1;
+                    gc1 = sgnf_(e1) * c.cs * c.inv1;
+                    gc2 = sgnf_(e2) * c.cs * c.inv1;
+                    cf = PART ? c.fs * c.inv1 : 0.f;
+                }
+                if (sem && !(c.flags & 4)) {
+                    const float eo = opac - tgt;                                 // loss.py:71
+                    a.loss[2] += fabsf(eo);
+                    go = sgnf_(eo) * c.os * c.invs;
+                }
+            } else {
+#pragma unroll
+                for (int i = 0; i < S; ++i) {
+                    misc[M_TERM * PS + r * S + i] = 0.f;
+                    misc[M_FREE * PS + r * S + i] = 0.f;
+                }
+            }
+            rv[V_DEPTH * RP + r] = depth;
+            rv[V_OPAC * RP + r] = opac;
+            rv[(V_COL + 0) * RP + r] = c0; rv[(V_COL + 1) * RP + r] = c1; rv[(V_COL + 2) * RP + r] = c2;
+            rv[V_GD * RP + r] = gd; rv[V_GO * RP + r] = go;
+            rv[(V_GC + 0) * RP + r] = gc0; rv[(V_GC + 1) * RP + r] = gc1; rv[(V_GC + 2) * RP + r] = gc2;
+            rv[V_CF * RP + r] = cf;
+            rv[V_BG * RP + r] = 0.f;
+        }
+    } else if constexpr (PH == 9) {
+        // S[j][r] = sum_i T_i hp_i[j]   (render of the clip-head hidden activations)
+        if (PART) {
+            for (int i = tid; i < H * RT; i += NTHREADS) {
+                const int j = i / RT, r = i - j * RT;
+                float s = 0.f;
+#pragma unroll
+                for (int q = 0; q < S; ++q) s += misc[M_TERM * PS + r * S + q] * act[(R_HP + j) * PS + r * S + q];
+                sm[SM_ST + j * RP + r] = s;
+            }
+        }
+    } else if constexpr (PH == 10) {
+        // feat[r][c] = sum_j W_ocl[c][j] S[j][r] + b_ocl[c] * opacity_r   (== render(T, out_clip(hp)), loss.py:82)
+        if (PART) {
+            float f[2][RT];
+            const int c0 = tid, c1 = tid + NTHREADS;
+            const float b0 = OO_LDG(c.theta + OFF_OCL_B + c0), b1 = OO_LDG(c.theta + OFF_OCL_B + c1);
+#pragma unroll
+            for (int r = 0; r < RT; ++r) {
+                const float op = rv[V_OPAC * RP + r];
+                f[0][r] = b0 * op;
+                f[1][r] = b1 * op;
+            }
+#pragma unroll 4
+            for (int j = 0; j < H; ++j) {
+                const float w0 = OO_LDG(c.wocl_t + j * C + c0), w1 = OO_LDG(c.wocl_t + j * C + c1);
+                const float4 sa = ld4(sm + SM_ST + j * RP), sb = ld4(sm + SM_ST + j * RP + 4),
+                             sc = ld4(sm + SM_ST + j * RP + 8);
+                const float sv[RT] = {sa.x, sa.y, sa.z, sa.w, sb.x, sb.y, sb.z, sb.w, sc.x, sc.y};
+#pragma unroll
+                for (int r = 0; r < RT; ++r) {
+                    f[0][r] += w0 * sv[r];
+                    f[1][r] += w1 * sv[r];
+                }
+            }
+#pragma unroll
+            for (int r = 0; r < RT; ++r) {
+                sm[SM_FEAT + r * C + c0] = f[0][r];
+                sm[SM_FEAT + r * C + c1] = f[1][r];
+            }
+        }
+    } else if constexpr (PH == 11) {
+        // partial dot products for the cosine loss (render_rays.py:75) and for b_ocl . g
+        if (PART) {
+            if (tid < RT * 16) {
+                const int r = tid >> 4, ch = tid & 15;
+                const int rr = r < c.nrays ? r : 0;
+                const float* y = c.feat_table + (size_t)OO_LDG(c.feat_row + rr) * C;
+                float xy = 0.f, xx = 0.f, yy = 0.f, xb = 0.f, yb = 0.f;
+#pragma unroll 4
+                for (int i = 0; i < C / 16; ++i) {
+                    const int cc = i * 16 + ch;
+                    const float xv = sm[SM_FEAT + r * C + cc], yv = OO_LDG(y + cc), bv = OO_LDG(c.theta + OFF_OCL_B + cc);
+                    xy += xv * yv; xx += xv * xv; yy += yv * yv; xb += xv * bv; yb += yv * bv;
+                }
+                float* o = sm + SM_COSP + (r * 16 + ch) * 5;
+                o[0] = xy; o[1] = xx; o[2] = yy; o[3] = xb; o[4] = yb;
+            }
+        }
+    } else if constexpr (PH == 12) {
+        if (PART) {
+            if (tid < RT) {
+                const int r = tid;
+                float xy = 0.f, xx = 0.f, yy = 0.f, xb = 0.f, yb = 0.f;
+                for (int ch = 0; ch < 16; ++ch) {
+                    const float* o = sm + SM_COSP + (r * 16 + ch) * 5;
+                    xy += o[0]; xx += o[1]; yy += o[2]; xb += o[3]; yb += o[4];
+                }
+                const float cf = rv[V_CF * RP + r];
+                const float nxr = sqrtf(xx), nyr = sqrtf(yy);
+                const float nx = fmaxf(nxr, 1e-8f), ny = fmaxf(nyr, 1e-8f);   // F.cosine_similarity eps clamp
+                const float cosv = xy / (nx * ny);
+                float A = 0.f, B = 0.f;
+                if (cf != 0.f) {
+                    a.loss[3] += 1.f - cosv;
+                    // d(1-cos)/dx = -y/(nx ny) + [|x|>eps] cos * x / nx^2
+                    A = -cf / (nx * ny);
+                    B = nxr > 1e-8f ? cf * cosv / (nx * nx) : 0.f;
+                }
+                rv[V_A * RP + r] = A;
+                rv[V_B * RP + r] = B;
+                rv[V_BG * RP + r] = A * yb + B * xb;       // b_ocl . g_r
+            }
+        }
+    } else if constexpr (PH == 13) {
+        // g[r][c] = dL/dfeat, in place over feat
+        if (PART) {
+            const int c0 = tid, c1 = tid + NTHREADS;
+#pragma unroll
+            for (int r = 0; r < RT; ++r) {
+                const float A = rv[V_A * RP + r], B = rv[V_B * RP + r];
+                float y0 = 0.f, y1 = 0.f;
+                if (A != 0.f) {
+                    const float* y = c.feat_table + (size_t)OO_LDG(c.feat_row + r) * C;
+                    y0 = OO_LDG(y + c0);
+                    y1 = OO_LDG(y + c1);
+                }
+                sm[SM_FEAT + r * C + c0] = A * y0 + B * sm[SM_FEAT + r * C + c0];
+                sm[SM_FEAT + r * C + c1] = A * y1 + B * sm[SM_FEAT + r * C + c1];
+            }
+        }
+    } else if constexpr (PH == 14) {
+        if (PART) {
+            // (a) U partials: warp wv owns features [64 wv, 64 wv + 64); lane = hidden unit j
+            {
+                const int wv = tid >> 5, j = tid & 31;
+                float u[RT];
+#pragma unroll
+                for (int r = 0; r < RT; ++r) u[r] = 0.f;
+                const float* wocl = c.theta + OFF_OCL_W;
+                for (int cc = wv * 64; cc < wv * 64 + 64; cc += 4) {
+                    const float w0 = OO_LDG(wocl + (cc + 0) * H + j), w1 = OO_LDG(wocl + (cc + 1) * H + j),
+                                w2 = OO_LDG(wocl + (cc + 2) * H + j), w3 = OO_LDG(wocl + (cc + 3) * H + j);
+#pragma unroll
+                    for (int r = 0; r < RT; ++r) {
+                        const float4 g = ld4(sm + SM_FEAT + r * C + cc);
+                        u[r] += g.x * w0 + g.y * w1 + g.z * w2 + g.w * w3;
+                    }
+                }
+#pragma unroll
+                for (int r = 0; r < RT; ++r) sm[SM_UPART + (wv * RT + r) * H + j] = u[r];
+            }
+            // (b) out_clip weight/bias gradient, accumulated in this slot's slab (transposed [j][c] like wocl_t)
+            {
+                const int c0 = tid, c1 = tid + NTHREADS;
+                float g0[RT], g1[RT];
+                float db0 = 0.f, db1 = 0.f;
+#pragma unroll
+                for (int r = 0; r < RT; ++r) {
+                    g0[r] = sm[SM_FEAT + r * C + c0];
+                    g1[r] = sm[SM_FEAT + r * C + c1];
+                    const float op = rv[V_OPAC * RP + r];
+                    db0 += g0[r] * op;
+                    db1 += g1[r] * op;
+                }
+                float* sw = c.slab + OFF_OCL_W;
+                float* sb = c.slab + OFF_OCL_B;
+                if (!c.first_tile) {
+                    db0 += sb[c0];
+                    db1 += sb[c1];
+                }
+                sb[c0] = db0;
+                sb[c1] = db1;
+#pragma unroll 4
+                for (int j = 0; j < H; ++j) {
+                    const float4 sa = ld4(sm + SM_ST + j * RP), sb4 = ld4(sm + SM_ST + j * RP + 4),
+                                 sc = ld4(sm + SM_ST + j * RP + 8);
+                    const float sv[RT] = {sa.x, sa.y, sa.z, sa.w, sb4.x, sb4.y, sb4.z, sb4.w, sc.x, sc.y};
+                    float d0 = 0.f, d1 = 0.f;
+                    if (!c.first_tile) {
+                        d0 = sw[j * C + c0];
+                        d1 = sw[j * C + c1];
+                    }
+#pragma unroll
+                    for (int r = 0; r < RT; ++r) {
+                        d0 += g0[r] * sv[r];
+                        d1 += g1[r] * sv[r];
+                    }
+                    sw[j * C + c0] = d0;
+                    sw[j * C + c1] = d1;
+                }
+            }
+        }
+    } else if constexpr (PH == 15) {
+        if (PART) {
+            for (int i = tid; i < H * RT; i += NTHREADS) {
+                const int r = i / H, j = i - r * H;
+                float u = 0.f;
+#pragma unroll
+                for (int wv = 0; wv < 8; ++wv) u += sm[SM_UPART + (wv * RT + r) * H + j];
+                sm[SM_UT + j * RP + r] = u;
+            }
+        }
+    } else if constexpr (PH == 16) {
+        // hu[p] = hp_p . U_r + b_ocl . g_r  : what one unit of termination weight at p adds to the feature loss
+        if (PART) {
+            for (int p = tid; p < P; p += NTHREADS) {
+                const int r = p / S;
+                float hu = rv[V_BG * RP + r];
+#pragma unroll 8
+                for (int j = 0; j < H; ++j) hu += act[(R_HP + j) * PS + p] * sm[SM_UT + j * RP + r];
+                misc[M_HU * PS + p] = hu;
+            }
+        }
+    } else if constexpr (PH == 17) {
+        // back through the compositing sums and the exclusive product:
+        //   g_i = dL/dT_i ; dL/do_i = g_i P_i - (sum_{k>i} g_k T_k) / (1 - o_i + 1e-10) ; alpha = 10 raw
+        if (tid < RT) {
+            const int r = tid;
+            const float gd = rv[V_GD * RP + r], go = rv[V_GO * RP + r];
+            const float gc0 = rv[(V_GC + 0) * RP + r], gc1 = rv[(V_GC + 1) * RP + r], gc2 = rv[(V_GC + 2) * RP + r];
+            float suffix = 0.f;
+#pragma unroll
+            for (int i = S - 1; i >= 0; --i) {
+                const int p = r * S + i;
+                float draw = 0.f, d0 = 0.f, d1 = 0.f, d2 = 0.f;
+                if (r < c.nrays) {
+                    const float t = misc[M_TERM * PS + p], o = misc[M_OCC * PS + p], fp = misc[M_FREE * PS + p];
+                    const float k0 = misc[(M_COL + 0) * PS + p], k1 = misc[(M_COL + 1) * PS + p],
+                                k2 = misc[(M_COL + 2) * PS + p];
+                    float g = OO_LDG(c.z + p) * gd + go + k0 * gc0 + k1 * gc1 + k2 * gc2;
+                    if (PART) g += misc[M_HU * PS + p];
+                    const float docc = g * fp - suffix / (1.f - o + 1e-10f);
+                    suffix += g * t;
+                    draw = docc * o * (1.f - o) * 10.f;
+                    d0 = t * gc0 * k0 * (1.f - k0);
+                    d1 = t * gc1 * k1 * (1.f - k1);
+                    d2 = t * gc2 * k2 * (1.f - k2);
+                }
+                misc[M_DRAW * PS + p] = draw;
+                misc[(M_DCOL + 0) * PS + p] = d0;
+                misc[(M_DCOL + 1) * PS + p] = d1;
+                misc[(M_DCOL + 2) * PS + p] = d2;
+            }
+        }
+    } else if constexpr (PH == 18) {
+        // out_color / out_alpha weight gradients (reduce over points) ...
+        if (tid < 4 * H) {
+            const int o = tid >> 5, j = tid & 31;
+            const float* dy = misc + (o < 3 ? (M_DCOL + o) : M_DRAW) * PS;
+            const float* x = act + ((o < 3 ? R_HC : R_H4) + j) * PS;
+            float s = 0.f;
+#pragma unroll 5
+            for (int p0 = 0; p0 < P; p0 += 4) {
+                const float4 d = ld4(dy + p0), h = ld4(x + p0);
+                s += d.x * h.x + d.y * h.y + d.z * h.z + d.w * h.w;
+            }
+            a.s0 += s;
+        }
+        // ... and d(hp_pre) = T_p * U_r * [hp > 0] in place
+        if (PART) {
+            for (int i = tid; i < H * (P / 4); i += NTHREADS) {
+                const int j = i / (P / 4), p0 = 4 * (i - j * (P / 4));
+                float* hp = act + (R_HP + j) * PS + p0;
+                const float4 h = ld4(hp), t = ld4(misc + M_TERM * PS + p0);
+                const float* ut = sm + SM_UT + j * RP;
+                float4 o;
+                o.x = h.x > 0.f ? t.x * ut[(p0 + 0) / S] : 0.f;
+                o.y = h.y > 0.f ? t.y * ut[(p0 + 1) / S] : 0.f;
+                o.z = h.z > 0.f ? t.z * ut[(p0 + 2) / S] : 0.f;
+                o.w = h.w > 0.f ? t.w * ut[(p0 + 3) / S] : 0.f;
+                st4(hp, o);
+            }
+        }
+    } else if constexpr (PH == 19) {
+        // d(hc_pre) = (W_oc^T dcol_pre) * [hc > 0] in place
+        for (int i = tid; i < H * (P / 4); i += NTHREADS) {
+            const int j = i / (P / 4), p0 = 4 * (i - j * (P / 4));
+            float* hc = act + (R_HC + j) * PS + p0;
+            const float4 h = ld4(hc);
+            const float4 d0 = ld4(misc + (M_DCOL + 0) * PS + p0), d1 = ld4(misc + (M_DCOL + 1) * PS + p0),
+                         d2 = ld4(misc + (M_DCOL + 2) * PS + p0);
+            const float w0 = w[W_OC + j], w1 = w[W_OC + H + j], w2 = w[W_OC + 2 * H + j];
+            float4 o;
+            o.x = h.x > 0.f ? w0 * d0.x + w1 * d1.x + w2 * d2.x : 0.f;
+            o.y = h.y > 0.f ? w0 * d0.y + w1 * d1.y + w2 * d2.y : 0.f;
+            o.z = h.z > 0.f ? w0 * d0.z + w1 * d1.z + w2 * d2.z : 0.f;
+            o.w = h.w > 0.f ? w0 * d0.w + w1 * d1.w + w2 * d2.w : 0.f;
+            st4(hc, o);
+        }
+    } else if constexpr (PH == 20) {
+        // [color_linear ; clip_linear] weight gradient: rows = [d_hc ; d_hp], cols = [h4 ; e2]
+        if (tid < 8 * (KP_HD / 4)) {
+            if (PART) gemm_bwd_w<8, KP_HD / 4>(a.hd, tid & 7, tid >> 3, act + R_HC * PS, act + R_H4 * PS, 0, P);
+            else gemm_bwd_w<4, KP_HD / 4>(a.hd, tid & 7, tid >> 3, act + R_HC * PS, act + R_H4 * PS, 0, P);
+        }
+    } else if constexpr (PH == 21) {
+        // d[h4 ; e2] = W_cl^T d_hc + W_cp^T d_hp (+ W_a draw on the h4 rows), ReLU mask on the h4 rows; in place
+        if (PART)
+            gemm_bwd_data<KP_HD, WS_HD, 2 * H, 1, 0>(tid, w + W_CL, act + R_HC * PS, nullptr, nullptr,
+                                                     act + R_H4 * PS, H, w + W_A, misc + M_DRAW * PS);
+        else
+            gemm_bwd_data<KP_HD, WS_HD, H, 1, 0>(tid, w + W_CL, act + R_HC * PS, nullptr, nullptr,
+                                                 act + R_H4 * PS, H, w + W_A, misc + M_DRAW * PS);
+    } else if constexpr (PH == 22) {
+        const int g = tid >> 6, t = tid & 63;
+        gemm_bwd_w<4, H / 4>(a.m2, t & 7, t >> 3, act + R_H4 * PS, act + R_H3 * PS, pgroup_begin(g), pgroup_end(g));
+    } else if constexpr (PH == 23) {
+        gemm_bwd_data<H, WS_H, H, 1, 0>(tid, w + W_M2, act + R_H4 * PS, nullptr, nullptr, act + R_H3 * PS, H,
+                                        nullptr, nullptr);
+    } else if constexpr (PH == 24) {
+        if (tid < 8 * (KP_CAT / 4))
+            gemm_bwd_w<4, KP_CAT / 4>(a.cat, tid & 7, tid >> 3, act + R_H3 * PS, act + R_H2 * PS, 0, P);
+    } else if constexpr (PH == 25) {
+        gemm_bwd_data<H, WS_CAT, H, 1, 0>(tid, w + W_CAT, act + R_H3 * PS, nullptr, nullptr, act + R_H2 * PS, H,
+                                          nullptr, nullptr);
+    } else if constexpr (PH == 26) {
+        const int g = tid >> 6, t = tid & 63;
+        gemm_bwd_w<4, H / 4>(a.m1, t & 7, t >> 3, act + R_H2 * PS, act + R_H1 * PS, pgroup_begin(g), pgroup_end(g));
+    } else if constexpr (PH == 27) {
+        gemm_bwd_data<H, WS_H, H, 1, 0>(tid, w + W_M1, act + R_H2 * PS, nullptr, nullptr, act + R_H1 * PS, H,
+                                        nullptr, nullptr);
+    } else if constexpr (PH == 28) {
+        if (tid < 8 * (KP_IN / 4))
+            gemm_bwd_w<4, KP_IN / 4>(a.in, tid & 7, tid >> 3, act + R_H1 * PS, act + R_E1 * PS, 0, P);
+    } else if constexpr (PH == 29) {
+        // d e1 = W_cat[:, 32:]^T d_h3 + W_in^T d_h1, in place over e1 (no mask)
+        gemm_bwd_data<KP_IN, WS_CAT, H, WS_IN, H>(tid, w + W_CAT + H, act + R_H3 * PS, w + W_IN, act + R_H1 * PS,
+                                                  act + R_E1 * PS, 0, nullptr, nullptr);
+    } else if constexpr (PH == 30) {
+        // d proj[d][p] = sum_k d e[3+21k+d][p] * pi 2^k cos(pi 2^k proj); stored over e1 row 3+d
+        for (int i = tid; i < NDIR * P; i += NTHREADS) {
+            const int d = i / P, p = i - d * P;
+            const float t0 = act[(R_T + 0) * PS + p], t1 = act[(R_T + 1) * PS + p], t2 = act[(R_T + 2) * PS + p];
+            const float proj = w[W_PE + 3 * d] * t0 + w[W_PE + 3 * d + 1] * t1 + w[W_PE + 3 * d + 2] * t2;
+            float band = 1.f, dp = 0.f;
+#pragma unroll
+            for (int k = 0; k < NBAND; ++k) {
+                const int row = 3 + NDIR * k + d;
+                const float de = row < E1 ? act[(R_E1 + row) * PS + p] : act[(R_E2 + row - E1) * PS + p];
+                dp += de * (cosf((proj * band) * PI_F) * PI_F * band);
+                band *= 2.f;
+            }
+            act[(R_E1 + 3 + d) * PS + p] = dp;
+        }
+    } else if constexpr (PH == 31) {
+        if (tid < NDIR * 3) {
+            const int d = tid / 3, ch = tid - 3 * d;
+            const float* dp = act + (R_E1 + 3 + d) * PS;
+            const float* tt = act + (R_T + ch) * PS;
+            float s = 0.f;
+#pragma unroll 5
+            for (int p0 = 0; p0 < P; p0 += 4) {
+                const float4 x = ld4(dp + p0), y = ld4(tt + p0);
+                s += x.x * y.x + x.y * y.y + x.z * y.z + x.w * y.w;
+            }
+            a.s2 += s;
+        }
+        if (tid < 6 * H + 4) {
+            const float* row;
+            if (tid < 6 * H) {
+                const int l = tid >> 5, j = tid & 31;
+                const int base = l == 0 ? R_H1 : l == 1 ? R_H2 : l == 2 ? R_H3 : l == 3 ? R_H4 : l == 4 ? R_HC : R_HP;
+                row = act + (base + j) * PS;
+            } else {
+                const int o = tid - 6 * H;
+                row = misc + (o < 3 ? (M_DCOL + o) : M_DRAW) * PS;
+            }
+            float s = 0.f;
+#pragma unroll 5
+            for (int p0 = 0; p0 < P; p0 += 4) {
+                const float4 x = ld4(row + p0);
+                s += (x.x + x.y) + (x.z + x.w);
+            }
+            if (PART || tid < 5 * H || tid >= 6 * H) a.s1 += s;
+        }
+    }
+}
+
+// ------------------------------------------------------------------------------------------------
+// flush one (CTA, object) slot: registers -> slab in the reference's tensor layouts
+// (the out_clip gradient is already in the slab, transposed; see phase 14)
+// ------------------------------------------------------------------------------------------------
+// step 0: in/cat/heads/small from registers -> slab, mid1 point-group partials -> scratch;
+// step 1: mid1 sum -> slab; step 2: mid2 partials -> scratch, ray loss partials -> smem;
+// step 3: mid2 sum -> slab, loss sum -> slot_loss.  A block barrier follows every step.
+OO_DEV void flush_partials32(int tid, float* scratch, const float* acc) {
+    const int g = tid >> 6, t = tid & 63, ji = t & 7, ki = t >> 3;
+#pragma unroll
+    for (int jj = 0; jj < 4; ++jj)
+#pragma unroll
+        for (int kk = 0; kk < 4; ++kk) scratch[g * 1024 + (ji + 8 * jj) * H + ki + 8 * kk] = acc[jj * 4 + kk];
+}
+
+template <int STEP, bool PART>
+OO_DEV void tile_flush(int tid, float* __restrict__ sm, float* __restrict__ slab, float* __restrict__ slot_loss,
+                       const TileAcc& a) {
+    float* scratch = sm + SM_FEAT;   // [4][1024]
+    if constexpr (STEP == 0) {
+        if (tid < 8 * (KP_IN / 4)) {
+            const int ji = tid & 7, ki = tid >> 3;
+#pragma unroll
+            for (int jj = 0; jj < 4; ++jj)
+#pragma unroll
+                for (int kk = 0; kk < 4; ++kk) {
+                    const int k = ki + (KP_IN / 4) * kk;
+                    if (k < E1) slab[OFF_IN_W + (ji + 8 * jj) * E1 + k] = a.in[jj * 4 + kk];
+                }
+        }
+        if (tid < 8 * (KP_CAT / 4)) {
+            const int ji = tid & 7, ki = tid >> 3;
+#pragma unroll
+            for (int jj = 0; jj < 4; ++jj)
+#pragma unroll
+                for (int kk = 0; kk < 4; ++kk) {
+                    const int k = ki + (KP_CAT / 4) * kk;
+                    if (k < H + E1) slab[OFF_CAT_W + (ji + 8 * jj) * (H + E1) + k] = a.cat[jj * 4 + kk];
+                }
+        }
+        if (tid < 8 * (KP_HD / 4)) {
+            const int ji = tid & 7, ki = tid >> 3;
+#pragma unroll
+            for (int jj = 0; jj < (PART ? 8 : 4); ++jj)
+#pragma unroll
+                for (int kk = 0; kk < 4; ++kk) {
+                    const int k = ki + (KP_HD / 4) * kk;
+                    const int j = ji + 8 * jj;
+                    if (k < H + E2)
+                        slab[(j < H ? OFF_CL_W + j * (H + E2) : OFF_CP_W + (j - H) * (H + E2)) + k] = a.hd[jj * 4 + kk];
+                }
+        }
+        if (tid < 3 * H) slab[OFF_OC_W + tid] = a.s0;
+        else if (tid < 4 * H) slab[OFF_A_W + tid - 3 * H] = a.s0;
+        if (tid < 6 * H) {
+            const int l = tid >> 5, j = tid & 31;
+            const int off = l == 0 ? OFF_IN_B : l == 1 ? OFF_M1_B : l == 2 ? OFF_CAT_B : l == 3 ? OFF_M2_B
+                                                                      : l == 4 ? OFF_CL_B : OFF_CP_B;
+            if (PART || l < 5) slab[off + j] = a.s1;
+        } else if (tid < 6 * H + 3) {
+            slab[OFF_OC_B + tid - 6 * H] = a.s1;
+        } else if (tid == 6 * H + 3) {
+            slab[OFF_A_B] = a.s1;
+        }
+        if (tid < NDIR * 3) slab[OFF_PE_B + tid] = a.s2;
+        flush_partials32(tid, scratch, a.m1);
+    } else if constexpr (STEP == 1) {
+        for (int i = tid; i < H * H; i += NTHREADS)
+            slab[OFF_M1_W + i] = (scratch[i] + scratch[1024 + i]) + (scratch[2048 + i] + scratch[3072 + i]);
+    } else if constexpr (STEP == 2) {
+        flush_partials32(tid, scratch, a.m2);
+        if (tid < RT) {
+            float* rvl = sm + SM_RV;
+            rvl[V_LD * RP + tid] = a.loss[0];
+            rvl[V_LC * RP + tid] = a.loss[1];
+            rvl[V_LO * RP + tid] = a.loss[2];
+            rvl[V_LF * RP + tid] = a.loss[3];
+        }
+    } else {
+        for (int i = tid; i < H * H; i += NTHREADS)
+            slab[OFF_M2_W + i] = (scratch[i] + scratch[1024 + i]) + (scratch[2048 + i] + scratch[3072 + i]);
+        if (tid < 4) {
+            const float* rvl = sm + SM_RV + (V_LD + tid) * RP;
+            float sum = 0.f;
+            for (int r = 0; r < RT; ++r) sum += rvl[r];
+            slot_loss[tid] = sum;
+        }
+    }
+}
+
+constexpr int N_FLUSH_STEPS = 4;   // barrier after each
+
+}  // namespace oo

@@ -1,0 +1,398 @@
+// K1 fused per-object encode + MLP + compositing + loss + backward (one persistent CTA per SM),
+// K4 fused multi-tensor AdamW over the stacked parameter blocks, and the per-frame bookkeeping kernels.
+// Reference path replaced: objnerf/train.py:394-474 (vmap(pe), vmap(fc), loss.step_batch_loss,
+// backward, AdamW.step), utils.py:55-62 (combine_state_for_ensemble).
+#include "../../include/openobj_b200.h"
+#include "oo_common.cuh"
+#include "oo_sched.h"
+#include "oo_tile.h"
+
+using namespace oo;
+
+namespace {
+
+struct TrainParams {
+    const float* theta;
+    const float* wocl_t;
+    oo_batch b;
+    int ray0;              // first ray of this step inside each object's batch (it * rays_per_step)
+    int R;                 // rays per object per step
+    int tiles_per_obj;
+    int n_obj;
+    const int* sched;      // cta_tile_begin[n_cta+1], cta_slot_begin[n_cta], ...
+    const int* counts;     // [n_obj][2] for this step
+    const int* flags;      // [1] for this step
+    float* slab;
+    float* slot_loss;
+    float scale, cs, os, fs;
+};
+
+template <int PH, int END, bool PART>
+struct Phases {
+    static __device__ __forceinline__ void run(int tid, float* sm, const TileCtx& c, TileAcc& a) {
+        tile_phase<PH, PART>(tid, sm, c, a);
+        __syncthreads();
+        Phases<PH + 1, END, PART>::run(tid, sm, c, a);
+    }
+};
+template <int END, bool PART>
+struct Phases<END, END, PART> {
+    static __device__ __forceinline__ void run(int, float*, const TileCtx&, TileAcc&) {}
+};
+
+template <bool PART>
+__global__ void __launch_bounds__(NTHREADS, 1) k_train(const TrainParams prm) {
+    extern __shared__ __align__(16) float sm[];
+    const int tid = threadIdx.x;
+    const int n_cta = gridDim.x;
+    const int t_begin = prm.sched[blockIdx.x], t_end = prm.sched[blockIdx.x + 1];
+    if (t_begin >= t_end) return;
+    int slot = prm.sched[n_cta + 1 + blockIdx.x];
+    const int flags = prm.flags[0];
+
+    zero_pad_rows(tid, sm);
+    TileAcc acc;
+    acc_zero(acc);
+    TileCtx c;
+    c.flags = flags;
+    c.scale = prm.scale;
+    c.cs = prm.cs; c.os = prm.os; c.fs = prm.fs;
+    c.feat_table = prm.b.feat_table;
+
+    int cur_obj = -1;
+    for (int t = t_begin; t < t_end; ++t) {
+        const int obj = t / prm.tiles_per_obj;
+        const int r0 = (t - obj * prm.tiles_per_obj) * RT;
+        if (obj != cur_obj) {
+            cur_obj = obj;
+            c.theta = prm.theta + (size_t)obj * PSTRIDE;
+            c.wocl_t = prm.wocl_t + (size_t)obj * (H * C);
+            c.slab = prm.slab + (size_t)slot * PSTRIDE;
+            c.inv1 = 1.f / ((float)prm.counts[2 * obj] + 1e-10f);
+            c.invs = 1.f / ((float)prm.counts[2 * obj + 1] + 1e-10f);
+            c.first_tile = 1;
+            stage_weights(tid, sm, c.theta);
+            __syncthreads();
+        }
+        const size_t ray = (size_t)obj * prm.b.rays_per_obj + prm.ray0 + r0;
+        c.nrays = min(RT, prm.R - r0);
+        c.pcs = prm.b.pcs + ray * (S * 3);
+        c.z = prm.b.z + ray * S;
+        c.gt_depth = prm.b.gt_depth + ray;
+        c.gt_rgb = prm.b.gt_rgb + ray * 3;
+        c.labels = prm.b.labels + ray;
+        c.feat_row = PART ? prm.b.feat_row + ray : nullptr;
+
+        Phases<0, N_TRAIN_PHASES, PART>::run(tid, sm, c, acc);
+        c.first_tile = 0;
+
+        const bool last_of_obj = (t + 1 == t_end) || ((t + 1) / prm.tiles_per_obj != obj);
+        if (last_of_obj) {
+            float* sl = prm.slot_loss + 4 * slot;
+            tile_flush<0, PART>(tid, sm, c.slab, sl, acc); __syncthreads();
+            tile_flush<1, PART>(tid, sm, c.slab, sl, acc); __syncthreads();
+            tile_flush<2, PART>(tid, sm, c.slab, sl, acc); __syncthreads();
+            tile_flush<3, PART>(tid, sm, c.slab, sl, acc); __syncthreads();
+            acc_zero(acc);
+            ++slot;
+            cur_obj = -1;
+        }
+    }
+}
+
+// ---- per-frame: ray counts per (step, object) and the cross-object zero-mask flags (render_rays.py:88-94)
+__global__ void k_label_counts(const uint8_t* __restrict__ labels, int n_obj, int rays_per_obj, int R,
+                               int* __restrict__ counts, int* __restrict__ flags) {
+    const int it = blockIdx.x;
+    int f = 0;
+    for (int o = 0; o < n_obj; ++o) {
+        int n1 = 0, ns = 0;
+        for (int r0 = 0; r0 < R; r0 += blockDim.x) {
+            const int r = r0 + threadIdx.x;
+            int lab = 2;
+            bool in = r < R;
+            if (in) lab = labels[(size_t)o * rays_per_obj + (size_t)it * R + r];
+            n1 += __syncthreads_count(in && lab == 1);
+            ns += __syncthreads_count(in && lab != 2);
+        }
+        if (threadIdx.x == 0) {
+            counts[((size_t)it * n_obj + o) * 2 + 0] = n1;
+            counts[((size_t)it * n_obj + o) * 2 + 1] = ns;
+        }
+        if (n1 == 0) f |= OO_FLAG_NO_OBJ;
+        if (ns == 0) f |= OO_FLAG_NO_SEM;
+    }
+    if (threadIdx.x == 0) flags[it] = f;
+}
+
+// ---- per-frame: which parameter groups autograd reaches in each step, their Adam step numbers and bias
+// corrections (torch.optim.AdamW: tensors whose grad is None are skipped entirely)
+__global__ void k_adam_schedule(const int* __restrict__ flags, int iters, int part_on, double lr, double b1, double b2,
+                                int* __restrict__ adam_t, float* __restrict__ scal) {
+    if (threadIdx.x != 0 || blockIdx.x != 0) return;
+    int t[3] = {adam_t[0], adam_t[1], adam_t[2]};
+    for (int it = 0; it < iters; ++it) {
+        const int f = flags[it];
+        const bool obj_terms = !(f & OO_FLAG_NO_OBJ), op_term = !(f & OO_FLAG_NO_SEM);
+        const bool active[3] = {obj_terms || op_term, obj_terms, obj_terms && part_on != 0};
+        for (int g = 0; g < 3; ++g) {
+            float* s = scal + ((size_t)it * 3 + g) * 4;
+            if (active[g]) {
+                t[g] += 1;
+                const double bc1 = 1.0 - pow(b1, (double)t[g]);
+                const double bc2 = 1.0 - pow(b2, (double)t[g]);
+                s[0] = 1.f;
+                s[1] = (float)(lr / bc1);
+                s[2] = (float)sqrt(bc2);
+                s[3] = (float)t[g];
+            } else {
+                s[0] = s[1] = s[2] = s[3] = 0.f;
+            }
+        }
+    }
+    adam_t[0] = t[0]; adam_t[1] = t[1]; adam_t[2] = t[2];
+}
+
+// ---- K4: sum the gradient slots of each object (fixed order) and apply AdamW in place; HBM-bound.
+// grid = (PSTRIDE/4/256, n_obj); thread = 4 consecutive parameters of one object.
+template <bool UPDATE>
+__global__ void __launch_bounds__(256) k_adamw(float* __restrict__ theta, float* __restrict__ am, float* __restrict__ av,
+                                               const float* __restrict__ slab, const int* __restrict__ obj_slot,
+                                               const float* __restrict__ scal, float decay, float b1, float b2, float eps,
+                                               float* __restrict__ wocl_t, const float* __restrict__ slot_loss,
+                                               const int* __restrict__ counts, float* __restrict__ loss_terms,
+                                               float* __restrict__ grads_out) {
+    const int o = blockIdx.y;
+    const int i = 4 * (blockIdx.x * 256 + threadIdx.x);
+    const int s0 = obj_slot[o], s1 = obj_slot[o + 1];
+    if (blockIdx.x == 0 && threadIdx.x < 4 && loss_terms != nullptr) {
+        // per-object loss terms: masked mean = sum / (count + 1e-10)  (render_rays.py:108)
+        float s = 0.f;
+        for (int q = s0; q < s1; ++q) s += slot_loss[4 * q + threadIdx.x];
+        const int n = counts[2 * o + (threadIdx.x == 2 ? 1 : 0)];
+        loss_terms[4 * o + threadIdx.x] = s / ((float)n + 1e-10f);
+    }
+    if (i >= PEND) return;
+    const int grp = group_of_offset(i);
+    const bool active = scal[grp * 4] != 0.f;
+    float4 g = {0.f, 0.f, 0.f, 0.f};
+    const bool tr = i >= OFF_OCL_W && i < OFF_OCL_B;
+    const int cc = (i - OFF_OCL_W) / H, j0 = (i - OFF_OCL_W) % H;   // valid when tr
+    if (active) {
+        for (int q = s0; q < s1; ++q) {
+            const float* sp = slab + (size_t)q * PSTRIDE;
+            if (tr) {
+                const float* t = sp + OFF_OCL_W + j0 * C + cc;
+                g.x += t[0]; g.y += t[C]; g.z += t[2 * C]; g.w += t[3 * C];
+            } else {
+                const float4 v = *reinterpret_cast<const float4*>(sp + i);
+                g.x += v.x; g.y += v.y; g.z += v.z; g.w += v.w;
+            }
+        }
+    }
+    const size_t idx = (size_t)o * PSTRIDE + i;
+    if (!UPDATE) {
+        *reinterpret_cast<float4*>(grads_out + idx) = g;
+        return;
+    }
+    if (!active) return;
+    const float step = scal[grp * 4 + 1], bc2s = scal[grp * 4 + 2];
+    float4 p = *reinterpret_cast<float4*>(theta + idx);
+    float4 m = *reinterpret_cast<float4*>(am + idx);
+    float4 v = *reinterpret_cast<float4*>(av + idx);
+#define OO_ADAM1(P, M, V, G)                               \
+    {                                                      \
+        P = P * decay;                                     \
+        M = M + (G - M) * (1.f - b1);                      \
+        V = V * b2 + ((1.f - b2) * G) * G;                 \
+        const float den = sqrtf(V) / bc2s + eps;           \
+        P = P - step * (M / den);                          \
+    }
+    OO_ADAM1(p.x, m.x, v.x, g.x)
+    OO_ADAM1(p.y, m.y, v.y, g.y)
+    OO_ADAM1(p.z, m.z, v.z, g.z)
+    OO_ADAM1(p.w, m.w, v.w, g.w)
+#undef OO_ADAM1
+    *reinterpret_cast<float4*>(theta + idx) = p;
+    *reinterpret_cast<float4*>(am + idx) = m;
+    *reinterpret_cast<float4*>(av + idx) = v;
+    if (tr) {
+        float* t = wocl_t + (size_t)o * (H * C) + j0 * C + cc;
+        t[0] = p.x; t[C] = p.y; t[2 * C] = p.z; t[3 * C] = p.w;
+    }
+}
+
+__global__ void k_wocl_t(const float* __restrict__ theta, float* __restrict__ wocl_t) {
+    const int o = blockIdx.y;
+    const int i = blockIdx.x * blockDim.x + threadIdx.x;     // index into [32][512]
+    if (i >= H * C) return;
+    const int j = i / C, cc = i - j * C;
+    wocl_t[(size_t)o * (H * C) + i] = theta[(size_t)o * PSTRIDE + OFF_OCL_W + cc * H + j];
+}
+
+__global__ void k_adamw_flat(float* __restrict__ p, const float* __restrict__ g, float* __restrict__ m,
+                             float* __restrict__ v, int64_t n, float decay, float b1, float b2, float eps,
+                             float step, float bc2s) {
+    for (int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; i < n; i += (int64_t)gridDim.x * blockDim.x) {
+        float P = p[i] * decay, G = g[i];
+        const float M = m[i] + (G - m[i]) * (1.f - b1);
+        const float V = v[i] * b2 + ((1.f - b2) * G) * G;
+        P = P - step * (M / (sqrtf(V) / bc2s + eps));
+        p[i] = P; m[i] = M; v[i] = V;
+    }
+}
+
+int check_train_args(int n_obj, const oo_batch* b, int rays_per_step, const oo_train_ws* ws) {
+    OO_REQUIRE(n_obj > 0 && b && ws, "oo_train: null argument / n_obj <= 0");
+    OO_REQUIRE(rays_per_step > 0 && b->rays_per_obj >= rays_per_step, "oo_train: bad rays_per_step");
+    OO_REQUIRE(ws->slab && ws->slot_loss && ws->sched && ws->counts && ws->flags && ws->adam_scal,
+               "oo_train: workspace not allocated");
+    return 0;
+}
+
+int launch_k1(const float* theta, int n_obj, const oo_batch* b, int it, int R, float scale, const oo_train_ws* ws,
+              int n_sm, cudaStream_t st) {
+    Schedule s;                      // only the counts are needed here; the tables are already on the device
+    s.tiles_per_obj = tiles_per_object(R);
+    const long long T = (long long)n_obj * s.tiles_per_obj;
+    const int n_cta = (int)(T < n_sm ? T : n_sm);
+    TrainParams prm;
+    prm.theta = theta;
+    prm.wocl_t = ws->wocl_t;
+    prm.b = *b;
+    prm.ray0 = it * R;
+    prm.R = R;
+    prm.tiles_per_obj = s.tiles_per_obj;
+    prm.n_obj = n_obj;
+    prm.sched = ws->sched;
+    prm.counts = ws->counts + (size_t)it * n_obj * 2;
+    prm.flags = ws->flags + it;
+    prm.slab = ws->slab;
+    prm.slot_loss = ws->slot_loss;
+    prm.scale = scale;
+    prm.cs = 5.f; prm.os = 10.f; prm.fs = 5.f;   // loss.py:6 defaults (the JSON values are never read)
+    const size_t smem = (size_t)SM_TOTAL * sizeof(float);
+    static bool attr_set = false;
+    if (!attr_set) {
+        OO_CUDA(cudaFuncSetAttribute(k_train<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+        OO_CUDA(cudaFuncSetAttribute(k_train<false>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+        attr_set = true;
+    }
+    if (b->feat_row != nullptr) k_train<true><<<n_cta, NTHREADS, smem, st>>>(prm);
+    else k_train<false><<<n_cta, NTHREADS, smem, st>>>(prm);
+    OO_LAUNCH_CHECK();
+    return 0;
+}
+
+}  // namespace
+
+extern "C" int oo_train_ws_sizes(int n_obj, int rays_per_step, int iters, int n_sm, int* n_cta, int* n_slots,
+                                 int64_t* slab_floats, int64_t* sched_ints_out) {
+    OO_REQUIRE(n_obj > 0 && rays_per_step > 0 && n_sm > 0 && iters > 0, "oo_train_ws_sizes: bad argument");
+    const Schedule s = build_schedule(n_obj, rays_per_step, n_sm);
+    if (n_cta) *n_cta = s.n_cta;
+    if (n_slots) *n_slots = s.n_slots;
+    if (slab_floats) *slab_floats = (int64_t)s.n_slots * PSTRIDE;
+    if (sched_ints_out) *sched_ints_out = (int64_t)s.data.size();
+    return 0;
+}
+
+extern "C" int oo_train_schedule(int n_obj, int rays_per_step, int n_sm, oo_train_ws* ws, void* stream) {
+    OO_REQUIRE(ws && ws->sched, "oo_train_schedule: workspace not allocated");
+    const Schedule s = build_schedule(n_obj, rays_per_step, n_sm);
+    OO_CUDA(cudaMemcpyAsync(ws->sched, s.data.data(), s.data.size() * sizeof(int), cudaMemcpyHostToDevice,
+                            (cudaStream_t)stream));
+    OO_CUDA(cudaStreamSynchronize((cudaStream_t)stream));   // `s` dies at return
+    return 0;
+}
+
+extern "C" int oo_sync_wocl_t(const float* theta, int n_obj, oo_train_ws* ws, void* stream) {
+    OO_REQUIRE(theta && ws && ws->wocl_t, "oo_sync_wocl_t: null argument");
+    k_wocl_t<<<dim3((H * C + 255) / 256, n_obj), 256, 0, (cudaStream_t)stream>>>(theta, ws->wocl_t);
+    OO_LAUNCH_CHECK();
+    return 0;
+}
+
+extern "C" int oo_label_counts(const uint8_t* labels, int n_obj, int rays_per_obj, int rays_per_step, int iters,
+                               int* counts, int* flags, void* stream) {
+    OO_REQUIRE(labels && counts && flags && iters > 0, "oo_label_counts: null argument");
+    OO_REQUIRE((long long)iters * rays_per_step <= rays_per_obj, "oo_label_counts: iters*rays_per_step > rays_per_obj");
+    k_label_counts<<<iters, 128, 0, (cudaStream_t)stream>>>(labels, n_obj, rays_per_obj, rays_per_step, counts, flags);
+    OO_LAUNCH_CHECK();
+    return 0;
+}
+
+extern "C" int oo_adam_schedule(const int* flags, int iters, int part_on, float lr, float beta1, float beta2,
+                                int* adam_t, float* adam_scal, void* stream) {
+    OO_REQUIRE(flags && adam_t && adam_scal, "oo_adam_schedule: null argument");
+    k_adam_schedule<<<1, 32, 0, (cudaStream_t)stream>>>(flags, iters, part_on, (double)lr, (double)beta1, (double)beta2,
+                                                        adam_t, adam_scal);
+    OO_LAUNCH_CHECK();
+    return 0;
+}
+
+static int train_step_impl(float* theta, float* am, float* av, int n_obj, const oo_batch* b, int it, int R, float scale,
+                           float lr, float wd, float b1, float b2, float eps, oo_train_ws* ws, float* loss_terms,
+                           float* grads_out, int n_sm, cudaStream_t st) {
+    if (int rc = check_train_args(n_obj, b, R, ws)) return rc;
+    OO_REQUIRE((long long)(it + 1) * R <= b->rays_per_obj, "oo_train: step %d exceeds the pre-sampled batch", it);
+    if (int rc = launch_k1(theta, n_obj, b, it, R, scale, ws, n_sm, st)) return rc;
+    const Schedule s0;   // layout helper only
+    (void)s0;
+    const long long T = (long long)n_obj * tiles_per_object(R);
+    const int n_cta = (int)(T < n_sm ? T : n_sm);
+    const int* obj_slot = ws->sched + 2 * n_cta + 1;
+    const dim3 grid(PSTRIDE / 4 / 256, n_obj);
+    const float* scal = ws->adam_scal + (size_t)it * 12;
+    const int* counts = ws->counts + (size_t)it * n_obj * 2;
+    if (grads_out) {
+        k_adamw<false><<<grid, 256, 0, st>>>(nullptr, nullptr, nullptr, ws->slab, obj_slot, scal, 0.f, 0.f, 0.f, 0.f,
+                                             nullptr, ws->slot_loss, counts, loss_terms, grads_out);
+    } else {
+        const float decay = (float)(1.0 - (double)lr * (double)wd);
+        k_adamw<true><<<grid, 256, 0, st>>>(theta, am, av, ws->slab, obj_slot, scal, decay, b1, b2, eps, ws->wocl_t,
+                                            ws->slot_loss, counts, loss_terms, nullptr);
+    }
+    OO_LAUNCH_CHECK();
+    return 0;
+}
+
+extern "C" int oo_train_step(float* theta, float* adam_m, float* adam_v, int n_obj, const oo_batch* batch, int it,
+                             int rays_per_step, float scale, float lr, float weight_decay, float beta1, float beta2,
+                             float eps, oo_train_ws* ws, float* loss_terms, int n_sm, void* stream) {
+    OO_REQUIRE(theta && adam_m && adam_v, "oo_train_step: null parameter buffers");
+    return train_step_impl(theta, adam_m, adam_v, n_obj, batch, it, rays_per_step, scale, lr, weight_decay, beta1, beta2,
+                           eps, ws, loss_terms, nullptr, n_sm, (cudaStream_t)stream);
+}
+
+extern "C" int oo_train_grads(const float* theta, int n_obj, const oo_batch* batch, int it, int rays_per_step, float scale,
+                              oo_train_ws* ws, float* grads_out, float* loss_terms, int n_sm, void* stream) {
+    OO_REQUIRE(theta && grads_out, "oo_train_grads: null argument");
+    return train_step_impl(const_cast<float*>(theta), nullptr, nullptr, n_obj, batch, it, rays_per_step, scale, 0.f, 0.f,
+                           0.f, 0.f, 0.f, ws, loss_terms, grads_out, n_sm, (cudaStream_t)stream);
+}
+
+extern "C" int oo_train_frame(float* theta, float* adam_m, float* adam_v, int n_obj, const oo_batch* batch, int iters,
+                              int rays_per_step, float scale, float lr, float weight_decay, float beta1, float beta2,
+                              float eps, oo_train_ws* ws, float* loss_terms, int n_sm, void* stream) {
+    OO_REQUIRE(theta && adam_m && adam_v, "oo_train_frame: null parameter buffers");
+    for (int it = 0; it < iters; ++it) {
+        float* lt = loss_terms ? loss_terms + (size_t)it * n_obj * 4 : nullptr;
+        if (int rc = train_step_impl(theta, adam_m, adam_v, n_obj, batch, it, rays_per_step, scale, lr, weight_decay,
+                                     beta1, beta2, eps, ws, lt, nullptr, n_sm, (cudaStream_t)stream))
+            return rc;
+    }
+    return 0;
+}
+
+extern "C" int oo_adamw_flat(float* p, const float* g, float* m, float* v, int64_t n, int step, float lr,
+                             float weight_decay, float beta1, float beta2, float eps, void* stream) {
+    OO_REQUIRE(p && g && m && v && n >= 0 && step >= 1, "oo_adamw_flat: bad argument");
+    if (n == 0) return 0;
+    const double bc1 = 1.0 - pow((double)beta1, (double)step), bc2 = 1.0 - pow((double)beta2, (double)step);
+    const int blocks = (int)((n + 255) / 256 < 148 * 8 ? (n + 255) / 256 : 148 * 8);
+    k_adamw_flat<<<blocks, 256, 0, (cudaStream_t)stream>>>(p, g, m, v, n, (float)(1.0 - (double)lr * weight_decay), beta1,
+                                                           beta2, eps, (float)(lr / bc1), (float)sqrt(bc2));
+    OO_LAUNCH_CHECK();
+    return 0;
+}
