@@ -1,0 +1,164 @@
+"""Stacked per-object ensemble living in one device buffer + the fused training step.
+
+Replaces, for the vmap training strategy of the reference (objnerf/train.py):
+  * utils.update_vmap / functorch.combine_state_for_ensemble (utils.py:55-62): `Ensemble.load_stacked`
+    and `Ensemble.stacked()` -- the 19 stacked tensors are strided views of ONE buffer theta[N, PSTRIDE];
+  * the per-iteration body train.py:394-474 (vmap(pe), vmap(fc), loss.step_batch_loss, backward,
+    AdamW.step, zero_grad): `Ensemble.train_frame` / `train_step`, two kernel launches per iteration.
+All arithmetic happens in libopenobj_b200.so; this file only owns buffers and bookkeeping.
+"""
+import ctypes
+from dataclasses import dataclass
+from typing import Optional
+
+import torch
+
+from . import _lib, layout
+from ._lib import Batch, TrainWs, check, lib, ptr, stream
+
+
+@dataclass
+class FrameBatch:
+    """Pre-sampled training data of one frame for all objects (train.py:371-388).
+
+    pcs [N,RAYS,S,3] f32, z [N,RAYS,S] f32, gt_depth [N,RAYS] f32, gt_rgb [N,RAYS,3] u8,
+    labels [N,RAYS] u8 (0 other / 1 this / 2 unknown), and for part_mode either
+    feat_row [N,RAYS] int32 rows of feat_table [rows,512], or None (part features off)."""
+    pcs: torch.Tensor
+    z: torch.Tensor
+    gt_depth: torch.Tensor
+    gt_rgb: torch.Tensor
+    labels: torch.Tensor
+    feat_row: Optional[torch.Tensor] = None
+    feat_table: Optional[torch.Tensor] = None
+
+    @staticmethod
+    def from_dense(pcs, z, gt_depth, gt_rgb_u8, labels, gt_feat=None):
+        """The reference materialises Batch_N_gt_partfeat [N,RAYS,512] (train.py:378): use it as the table."""
+        rows = table = None
+        if gt_feat is not None:
+            n, r = labels.shape
+            table = gt_feat.reshape(n * r, gt_feat.shape[-1]).contiguous()
+            rows = torch.arange(n * r, dtype=torch.int32, device=labels.device).reshape(n, r)
+        return FrameBatch(pcs.contiguous(), z.contiguous(), gt_depth.contiguous(), gt_rgb_u8.contiguous(),
+                          labels.contiguous(), rows, table)
+
+    @property
+    def rays_per_obj(self):
+        return self.labels.shape[1]
+
+    def to_c(self):
+        assert self.gt_rgb.dtype == torch.uint8 and self.labels.dtype == torch.uint8
+        assert self.pcs.dtype == torch.float32 and self.z.dtype == torch.float32
+        if self.feat_row is not None:
+            assert self.feat_row.dtype == torch.int32 and self.feat_table.dtype == torch.float32
+            assert self.feat_table.shape[-1] == layout.CLIP
+        b = Batch(ptr(self.pcs), ptr(self.z), ptr(self.gt_depth), ptr(self.gt_rgb), ptr(self.labels),
+                  ptr(self.feat_row), ptr(self.feat_table), int(self.rays_per_obj))
+        return b
+
+
+class Ensemble:
+    def __init__(self, n_obj, device="cuda:0", rays_per_step=120, iters_per_frame=100, lr=1e-3, weight_decay=0.013,
+                 betas=(0.9, 0.999), eps=1e-8, scale=2.0, n_sm=None):
+        self.device = torch.device(device)
+        if self.device.type != "cuda":
+            raise _lib.OOError("Ensemble needs a CUDA device (no CPU fallback)")
+        self.L = lib()
+        self.n_obj, self.R, self.iters = int(n_obj), int(rays_per_step), int(iters_per_frame)
+        self.lr, self.wd, self.betas, self.eps, self.scale = lr, weight_decay, betas, eps, scale
+        self.n_sm = int(n_sm or _lib.n_sm(self.device))
+        with torch.cuda.device(self.device):
+            f32 = dict(dtype=torch.float32, device=self.device)
+            i32 = dict(dtype=torch.int32, device=self.device)
+            self.theta = torch.zeros(self.n_obj, layout.PSTRIDE, **f32)
+            self.m = torch.zeros_like(self.theta)
+            self.v = torch.zeros_like(self.theta)
+            n_cta, n_slots = ctypes.c_int(), ctypes.c_int()
+            slab_f, sched_i = ctypes.c_int64(), ctypes.c_int64()
+            check(self.L.oo_train_ws_sizes(self.n_obj, self.R, self.iters, self.n_sm, ctypes.byref(n_cta),
+                                           ctypes.byref(n_slots), ctypes.byref(slab_f), ctypes.byref(sched_i)),
+                  "oo_train_ws_sizes")
+            self.n_cta, self.n_slots = n_cta.value, n_slots.value
+            self._slab = torch.zeros(slab_f.value, **f32)
+            self._slot_loss = torch.zeros(self.n_slots * 4, **f32)
+            self._wocl_t = torch.zeros(self.n_obj, layout.HIDDEN, layout.CLIP, **f32)
+            self._sched = torch.zeros(sched_i.value, **i32)
+            self.counts = torch.zeros(self.iters, self.n_obj, 2, **i32)
+            self.flags = torch.zeros(self.iters, **i32)
+            self._adam_scal = torch.zeros(self.iters, 3, 4, **f32)
+            self.adam_t = torch.zeros(3, **i32)
+            self.ws = TrainWs(ptr(self._slab), ptr(self._slot_loss), ptr(self._wocl_t), ptr(self._sched),
+                              ptr(self.counts), ptr(self.flags), ptr(self._adam_scal), ptr(self.adam_t))
+            check(self.L.oo_train_schedule(self.n_obj, self.R, self.n_sm, ctypes.byref(self.ws), stream()),
+                  "oo_train_schedule")
+
+    # ---- parameters -------------------------------------------------------------------------
+    def stacked(self):
+        """The 19 stacked tensors [N,...] of utils.update_vmap, as views of theta."""
+        return layout.views(self.theta)
+
+    def load_stacked(self, tensors):
+        for v, t in zip(self.stacked(), tensors):
+            v.copy_(t.to(self.device))
+        self.params_changed()
+
+    def params_changed(self):
+        """Call after writing theta from outside (keeps the transposed out_clip copy in sync)."""
+        with torch.cuda.device(self.device):
+            check(self.L.oo_sync_wocl_t(ptr(self.theta), self.n_obj, ctypes.byref(self.ws), stream()), "oo_sync_wocl_t")
+
+    def reset_optimizer(self):
+        """Adam moments and step counters restart whenever the ensemble is rebuilt."""
+        self.m.zero_()
+        self.v.zero_()
+        self.adam_t.zero_()
+
+    # ---- per frame --------------------------------------------------------------------------
+    def prepare_frame(self, batch: FrameBatch, iters=None, flag_allreduce=None):
+        """Ray counts + zero-mask flags for every step, then the Adam schedule.  `flag_allreduce(flags)` lets a
+        sharded run OR the flags across ranks (the one cross-object coupling, render_rays.py:89-94)."""
+        iters = iters or self.iters
+        part_on = batch.feat_row is not None
+        with torch.cuda.device(self.device):
+            check(self.L.oo_label_counts(ptr(batch.labels), self.n_obj, batch.rays_per_obj, self.R, iters,
+                                         ptr(self.counts), ptr(self.flags), stream()), "oo_label_counts")
+            if flag_allreduce is not None:
+                flag_allreduce(self.flags[:iters])
+            check(self.L.oo_adam_schedule(ptr(self.flags), iters, int(part_on), self.lr, self.betas[0], self.betas[1],
+                                          ptr(self.adam_t), ptr(self._adam_scal), stream()), "oo_adam_schedule")
+
+    def grads(self, batch: FrameBatch, it=0):
+        """Gradients of the step loss w.r.t. theta (no update) + per-object loss terms [N,4]."""
+        g = torch.empty_like(self.theta)
+        terms = torch.empty(self.n_obj, 4, dtype=torch.float32, device=self.device)
+        b = batch.to_c()
+        with torch.cuda.device(self.device):
+            check(self.L.oo_train_grads(ptr(self.theta), self.n_obj, ctypes.byref(b), it, self.R, self.scale,
+                                        ctypes.byref(self.ws), ptr(g), ptr(terms), self.n_sm, stream()), "oo_train_grads")
+        return g, terms
+
+    def train_step(self, batch: FrameBatch, it, loss_terms=None):
+        b = batch.to_c()
+        with torch.cuda.device(self.device):
+            check(self.L.oo_train_step(ptr(self.theta), ptr(self.m), ptr(self.v), self.n_obj, ctypes.byref(b), it, self.R,
+                                       self.scale, self.lr, self.wd, self.betas[0], self.betas[1], self.eps,
+                                       ctypes.byref(self.ws), ptr(loss_terms), self.n_sm, stream()), "oo_train_step")
+
+    def train_frame(self, batch: FrameBatch, iters=None, loss_terms=None, prepare=True, flag_allreduce=None):
+        """`iters` optimisation steps over the pre-sampled batch (train.py:394-474).
+        loss_terms: optional [iters,N,4] output (depth, colour, opacity, feature per object)."""
+        iters = iters or self.iters
+        if prepare:
+            self.prepare_frame(batch, iters, flag_allreduce)
+        b = batch.to_c()
+        with torch.cuda.device(self.device):
+            check(self.L.oo_train_frame(ptr(self.theta), ptr(self.m), ptr(self.v), self.n_obj, ctypes.byref(b), iters,
+                                        self.R, self.scale, self.lr, self.wd, self.betas[0], self.betas[1], self.eps,
+                                        ctypes.byref(self.ws), ptr(loss_terms), self.n_sm, stream()), "oo_train_frame")
+
+    @staticmethod
+    def total_loss(terms, color_scaling=5.0, opacity_scaling=10.0, feat_scaling=5.0):
+        """loss.py:79,99,101: sum over objects of d + 5 c + 10 o + 5 f."""
+        return (terms[..., 0] + color_scaling * terms[..., 1] + opacity_scaling * terms[..., 2]
+                + feat_scaling * terms[..., 3]).sum(-1)
