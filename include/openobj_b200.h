@@ -55,8 +55,9 @@ int oo_param_size(int i);
 /* ---- a2+a3: vmap(pe_model) -> vmap(fc_model) forward (objnerf/train.py:424-425,
  *      embedding.py:46-55, model.py:61-103).  pcs [n_obj][n_pts][3]; outputs alpha [n_obj][n_pts]
  *      (already x10), color [n_obj][n_pts][3] (after sigmoid), clip [n_obj][n_pts][512] or NULL.
- *      emb_out [n_obj][n_pts][129] or NULL. n_pts must be a multiple of 4. */
-int oo_forward(const float* theta, int n_obj, const float* pcs, int n_pts, float scale,
+ *      emb_out [n_obj][n_pts][129] or NULL.  Exactly one of pcs / emb_in is non-NULL: with emb_in
+ *      [n_obj][n_pts][129] the encoder is skipped (OccupancyMap.forward on a given embedding). */
+int oo_forward(const float* theta, int n_obj, const float* pcs, const float* emb_in, int n_pts, float scale,
                float* alpha, float* color, float* clip, float* emb_out, void* stream);
 
 /* ---- a4-a9: loss.step_batch_loss forward and backward as one pair of HBM-bound kernels
@@ -78,7 +79,8 @@ int oo_loss_bwd(const float* alpha, const float* color, const float* z, const fl
                 float color_scaling, float opacity_scaling, float feat_scaling, float grad_loss,
                 const int* flags, const float* ray_ws,
                 float* d_alpha, float* d_color, float* d_pred_feat, void* stream);
-/* floats of workspace per (object, ray) that oo_loss_fwd leaves for oo_loss_bwd */
+/* floats of workspace per (object, ray) that oo_loss_fwd leaves for oo_loss_bwd;
+ * ray_ws must hold n_obj*n_rays*oo_loss_ws_per_ray() + 8*n_obj floats */
 int oo_loss_ws_per_ray(void);
 
 /* ---- fused training path (a1-a11 in one step: train.py:394-474) ------------------------- */
@@ -163,6 +165,9 @@ typedef struct oo_sample_args {
     const float* r_normal;               /* [n_obj][n_rays][n_bins] normal_(0, eps/3) draws, unsorted */
     const float* r_other;                /* [n_obj][n_rays][n_bins] */
     int tape_by_rank;                    /* 1: reference order (row j -> j-th ray of the class); 0: row = ray index */
+    /* torch.linspace(0,1,n+1) tables used by utils.stratified_bins (utils.py:349) for n = S, n_c2s, n_bins.
+     * HOST pointers: ATen's vectorised linspace is not a closed formula, so the caller supplies what torch gives. */
+    const float* lin_s_host; const float* lin_c2s_host; const float* lin_bins_host;
     /* outputs, all [n_obj][n_rays...] */
     uint8_t* gt_rgb; float* gt_depth; uint8_t* valid; uint8_t* labels;
     float* pcs; float* z; int32_t* feat_row; int64_t* pix;   /* pix [n_obj][n_rays][3] = kf, w, h */
@@ -185,6 +190,7 @@ typedef struct oo_render_args {
     const float* rays_dir;               /* [W][H][3] */
     const float* jitter;                 /* [W*H][n_bins] uniform draws */
     int jitter_by_rank;                  /* 1: row j -> j-th hit ray (reference order) */
+    const float* lin_host;               /* HOST: torch.linspace(0,1,n_bins+1) (utils.py:349) */
     uint8_t* mask; float* depth; uint8_t* rgb; float* feat;  /* [W][H], [W][H], [W][H][3], [W][H][512] or NULL */
     float* opacity;                      /* [W][H] or NULL */
     int* n_hit;                          /* [1] */

@@ -37,6 +37,7 @@ class SampleArgs(Structure):
                 ("kf_ids", c_void_p), ("u_w", c_void_p), ("u_h", c_void_p),
                 ("r_invalid", c_void_p), ("r_valid", c_void_p), ("r_normal", c_void_p), ("r_other", c_void_p),
                 ("tape_by_rank", c_int),
+                ("lin_s_host", c_void_p), ("lin_c2s_host", c_void_p), ("lin_bins_host", c_void_p),
                 ("gt_rgb", c_void_p), ("gt_depth", c_void_p), ("valid", c_void_p), ("labels", c_void_p),
                 ("pcs", c_void_p), ("z", c_void_p), ("feat_row", c_void_p), ("pix", c_void_p),
                 ("oob_count", c_void_p)]
@@ -45,7 +46,7 @@ class SampleArgs(Structure):
 class RenderArgs(Structure):
     _fields_ = [("W", c_int), ("H", c_int), ("n_bins", c_int), ("scale", c_float),
                 ("theta1", c_void_p), ("T_wc", c_void_p), ("T_oc", c_void_p), ("half_extent", c_void_p),
-                ("rays_dir", c_void_p), ("jitter", c_void_p), ("jitter_by_rank", c_int),
+                ("rays_dir", c_void_p), ("jitter", c_void_p), ("jitter_by_rank", c_int), ("lin_host", c_void_p),
                 ("mask", c_void_p), ("depth", c_void_p), ("rgb", c_void_p), ("feat", c_void_p),
                 ("opacity", c_void_p), ("n_hit", c_void_p)]
 
@@ -55,7 +56,7 @@ _SIGS = {
     "oo_last_error": ([], c_char_p),
     "oo_param_offset": ([c_int], c_int),
     "oo_param_size": ([c_int], c_int),
-    "oo_forward": ([c_void_p, c_int, c_void_p, c_int, c_float, c_void_p, c_void_p, c_void_p, c_void_p, c_void_p], c_int),
+    "oo_forward": ([c_void_p, c_int, c_void_p, c_void_p, c_int, c_float, c_void_p, c_void_p, c_void_p, c_void_p, c_void_p], c_int),
     "oo_loss_fwd": ([c_void_p] * 8 + [c_int] * 4 + [c_float] * 3 + [c_void_p] * 5, c_int),
     "oo_loss_bwd": ([c_void_p] * 8 + [c_int] * 4 + [c_float] * 4 + [c_void_p] * 6, c_int),
     "oo_loss_ws_per_ray": ([], c_int),

@@ -1,0 +1,124 @@
+// Standalone ensemble forward: vmap(pe_model) -> vmap(fc_model) (objnerf/train.py:424-425, embedding.py:46-55,
+// model.py:61-103).  Same tile phases 0..7 as the fused training step; the 512-wide out_clip layer is applied
+// per point here because this entry point returns the reference's per-point `clip` tensor.
+#include "../../include/openobj_b200.h"
+#include "oo_common.cuh"
+#include "oo_tile.h"
+
+using namespace oo;
+
+namespace {
+
+template <int PH, int END>
+struct FwdPhases {
+    static __device__ __forceinline__ void run(int tid, float* sm, const TileCtx& c, TileAcc& a) {
+        tile_phase<PH, true>(tid, sm, c, a);
+        __syncthreads();
+        FwdPhases<PH + 1, END>::run(tid, sm, c, a);
+    }
+};
+template <int END>
+struct FwdPhases<END, END> {
+    static __device__ __forceinline__ void run(int, float*, const TileCtx&, TileAcc&) {}
+};
+
+// grid = (tile groups, n_obj); each CTA stages its object's weights once and loops over 100-point tiles
+__global__ void __launch_bounds__(NTHREADS, 1) k_forward(const float* __restrict__ theta, const float* __restrict__ pcs,
+                                                         const float* __restrict__ emb_in, int n_pts, float scale,
+                                                         float* __restrict__ alpha,
+                                                         float* __restrict__ color, float* __restrict__ clip,
+                                                         float* __restrict__ emb) {
+    extern __shared__ __align__(16) float sm[];
+    const int tid = threadIdx.x, obj = blockIdx.y;
+    const float* th = theta + (size_t)obj * PSTRIDE;
+    zero_pad_rows(tid, sm);
+    stage_weights(tid, sm, th);
+    __syncthreads();
+    TileAcc acc;        // unused by phases 0..7
+    TileCtx c;
+    c.scale = scale;
+    c.theta = th;
+    float* act = sm + SM_ACT;
+    float* misc = act + R_MISC * PS;
+    // out_clip rows of this thread (2 of 512) stay in registers for the whole CTA
+    float w0[H], w1[H], b0 = 0.f, b1 = 0.f;
+    if (clip != nullptr) {
+#pragma unroll
+        for (int j = 0; j < H; j += 4) {
+            const float4 a = *reinterpret_cast<const float4*>(th + OFF_OCL_W + tid * H + j);
+            const float4 b = *reinterpret_cast<const float4*>(th + OFF_OCL_W + (tid + NTHREADS) * H + j);
+            w0[j] = a.x; w0[j + 1] = a.y; w0[j + 2] = a.z; w0[j + 3] = a.w;
+            w1[j] = b.x; w1[j + 1] = b.y; w1[j + 2] = b.z; w1[j + 3] = b.w;
+        }
+        b0 = th[OFF_OCL_B + tid];
+        b1 = th[OFF_OCL_B + tid + NTHREADS];
+    }
+    const int n_tiles = (n_pts + P - 1) / P;
+    for (int t = blockIdx.x; t < n_tiles; t += gridDim.x) {
+        const int p0 = t * P;
+        c.npts = min(P, n_pts - p0);
+        c.nrays = 0;
+        const size_t base = (size_t)obj * n_pts + p0;
+        if (emb_in != nullptr) {
+            // OccupancyMap.forward on a caller-supplied embedding: fill e1 / e2 rows directly
+            for (int i = tid; i < P * EMB; i += NTHREADS) {
+                const int p = i / EMB, e = i - p * EMB;
+                const float v = p < c.npts ? emb_in[base * EMB + i] : 0.f;
+                if (e < E1) act[(R_E1 + e) * PS + p] = v;
+                else act[(R_E2 + e - E1) * PS + p] = v;
+            }
+            __syncthreads();
+            FwdPhases<2, N_FWD_PHASES>::run(tid, sm, c, acc);
+        } else {
+            c.pcs = pcs + base * 3;
+            FwdPhases<0, N_FWD_PHASES>::run(tid, sm, c, acc);
+        }
+        for (int i = tid; i < c.npts; i += NTHREADS) alpha[base + i] = misc[M_DRAW * PS + i];
+        for (int i = tid; i < c.npts * 3; i += NTHREADS) {
+            const int p = i / 3, ch = i - 3 * p;
+            color[base * 3 + i] = misc[(M_COL + ch) * PS + p];
+        }
+        if (emb != nullptr) {
+            for (int i = tid; i < c.npts * EMB; i += NTHREADS) {
+                const int p = i / EMB, e = i - p * EMB;
+                emb[base * EMB + i] = e < E1 ? act[(R_E1 + e) * PS + p] : act[(R_E2 + e - E1) * PS + p];
+            }
+        }
+        if (clip != nullptr) {
+            for (int p = 0; p < c.npts; ++p) {
+                float f0 = b0, f1 = b1;
+#pragma unroll
+                for (int j = 0; j < H; ++j) {
+                    const float h = act[(R_HP + j) * PS + p];
+                    f0 += w0[j] * h;
+                    f1 += w1[j] * h;
+                }
+                clip[(base + p) * C + tid] = f0;
+                clip[(base + p) * C + tid + NTHREADS] = f1;
+            }
+        }
+        __syncthreads();
+    }
+}
+
+}  // namespace
+
+extern "C" int oo_forward(const float* theta, int n_obj, const float* pcs, const float* emb_in, int n_pts, float scale,
+                          float* alpha, float* color, float* clip, float* emb_out, void* stream) {
+    OO_REQUIRE(theta && alpha && color, "oo_forward: null argument");
+    OO_REQUIRE((pcs != nullptr) != (emb_in != nullptr), "oo_forward: give exactly one of pcs / emb_in");
+    OO_REQUIRE(n_obj > 0 && n_pts > 0, "oo_forward: empty input");
+    const size_t smem = (size_t)SM_TOTAL * sizeof(float);
+    static bool attr_set = false;
+    if (!attr_set) {
+        OO_CUDA(cudaFuncSetAttribute(k_forward, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+        attr_set = true;
+    }
+    const int n_tiles = (n_pts + P - 1) / P;
+    int gx = (4 * 148 + n_obj - 1) / n_obj;
+    if (gx > n_tiles) gx = n_tiles;
+    if (gx < 1) gx = 1;
+    k_forward<<<dim3(gx, n_obj), NTHREADS, smem, (cudaStream_t)stream>>>(theta, pcs, emb_in, n_pts, scale, alpha, color, clip, emb_out);
+    OO_LAUNCH_CHECK();
+    return 0;
+}

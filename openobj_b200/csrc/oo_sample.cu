@@ -1,0 +1,269 @@
+// K2: keyframe / pixel draw, gathers, ray transform and depth-guided sample placement for ALL objects in one
+// launch (objnerf/vmap.py:386-554, utils.py:324-397), plus the counter-based RNG used for throughput runs.
+// One 1024-thread CTA per object: pass A gathers and classifies the object's rays, a block scan gives every ray
+// its rank inside its class (the reference consumes its random rows by rank) and the batch-max depth
+// (quirk 6), pass B places the samples.  HBM-bound: ~180 B per ray.
+#include "../../include/openobj_b200.h"
+#include "oo_common.cuh"
+
+namespace {
+
+constexpr int NTH = 1024;
+constexpr int MAXB = 33;
+
+struct SampleK {
+    oo_sample_args a;
+    float lin_s[MAXB], lin_c[MAXB], lin_b[MAXB];
+};
+
+__device__ __forceinline__ void sort_small(float* v, int n) {   // insertion sort, n <= 32 (n_bins = 9)
+    for (int i = 1; i < n; ++i) {
+        const float x = v[i];
+        int j = i - 1;
+        while (j >= 0 && v[j] > x) {
+            v[j + 1] = v[j];
+            --j;
+        }
+        v[j + 1] = x;
+    }
+}
+
+struct RayPix {
+    int kf, iw, ih;
+    float iwf, ihf;
+    bool oob;
+};
+
+__device__ __forceinline__ RayPix ray_pixel(const oo_sample_args& a, int obj, int ray) {
+    RayPix r;
+    const int f = ray / a.n_samples;
+    r.kf = (int)a.kf_ids[(size_t)obj * a.n_frames + f];
+    const float* bb = a.bbox[obj] + 4 * r.kf;
+    const size_t ui = (size_t)obj * a.n_frames * a.n_samples + ray;
+    // separate fp32 mul and add, then truncation -- vmap.py:418-422
+    r.iwf = __fadd_rn(__fmul_rn(a.u_w[ui], __fsub_rn(bb[1], bb[0])), bb[0]);
+    r.ihf = __fadd_rn(__fmul_rn(a.u_h[ui], __fsub_rn(bb[3], bb[2])), bb[2]);
+    int iw = (int)r.iwf, ih = (int)r.ihf;
+    r.oob = iw < 0 || iw >= a.W || ih < 0 || ih >= a.H;   // quirk 11: the reference would raise an index error
+    r.iw = min(max(iw, 0), a.W - 1);
+    r.ih = min(max(ih, 0), a.H - 1);
+    return r;
+}
+
+__global__ void __launch_bounds__(NTH, 1) k_sample(const SampleK k) {
+    const oo_sample_args& a = k.a;
+    const int obj = blockIdx.x, tid = threadIdx.x, lane = tid & 31, wv = tid >> 5;
+    const int n_rays = a.n_frames * a.n_samples;
+    const int S = a.n_c2s + a.n_bins;
+    const int cpt = (n_rays + NTH - 1) / NTH;
+    const int r_begin = min(tid * cpt, n_rays), r_end = min(r_begin + cpt, n_rays);
+    const uint8_t* rgbs = a.rgbs[obj];
+    const float* depth = a.depth[obj];
+    __shared__ int sh_cnt[32][3];
+    __shared__ float sh_max[32];
+    __shared__ int sh_oob;
+    if (tid == 0) sh_oob = 0;
+
+    // ---- pass A: gather + classify -------------------------------------------------------------------
+    int n_inv = 0, n_obj = 0, n_oth = 0, oob = 0;
+    float dmax = -INFINITY;
+    for (int ray = r_begin; ray < r_end; ++ray) {
+        const RayPix p = ray_pixel(a, obj, ray);
+        oob += p.oob;
+        const size_t pix = ((size_t)p.kf * a.W + p.iw) * a.H + p.ih;
+        const uchar4 c = *reinterpret_cast<const uchar4*>(rgbs + pix * 4);        // vmap.py:424
+        const float d = depth[pix];                                                // vmap.py:425
+        const size_t o = (size_t)obj * n_rays + ray;
+        a.gt_rgb[o * 3 + 0] = c.x; a.gt_rgb[o * 3 + 1] = c.y; a.gt_rgb[o * 3 + 2] = c.z;
+        a.gt_depth[o] = d;
+        a.labels[o] = c.w;
+        const bool invalid = d <= a.min_bound;                                     // vmap.py:485
+        a.valid[o] = invalid ? 0 : 1;
+        if (a.pix) {
+            a.pix[o * 3 + 0] = p.kf; a.pix[o * 3 + 1] = p.iw; a.pix[o * 3 + 2] = p.ih;
+        }
+        if (a.feat_row) {                                                          // vmap.py:437-452
+            const int pw = min(max((int)floorf(__fdiv_rn(p.iwf, (float)a.part_down)), 0), a.pw - 1);
+            const int ph = min(max((int)floorf(__fdiv_rn(p.ihf, (float)a.part_down)), 0), a.ph - 1);
+            a.feat_row[o] = (a.part_frame[obj * 20 + p.kf] * a.pw + pw) * a.ph + ph;
+        }
+        dmax = fmaxf(dmax, d);
+        if (invalid) ++n_inv;
+        else if (c.w == 1) ++n_obj;
+        else ++n_oth;
+    }
+    // ---- block exclusive scan of the three class counters, block max of the sampled depths ----------------
+    int s_inv = n_inv, s_obj = n_obj, s_oth = n_oth;
+#pragma unroll
+    for (int o = 1; o < 32; o <<= 1) {
+        const int t0 = __shfl_up_sync(0xffffffffu, s_inv, o), t1 = __shfl_up_sync(0xffffffffu, s_obj, o),
+                  t2 = __shfl_up_sync(0xffffffffu, s_oth, o);
+        if (lane >= o) { s_inv += t0; s_obj += t1; s_oth += t2; }
+    }
+#pragma unroll
+    for (int o = 16; o > 0; o >>= 1) dmax = fmaxf(dmax, __shfl_xor_sync(0xffffffffu, dmax, o));
+    if (lane == 31) { sh_cnt[wv][0] = s_inv; sh_cnt[wv][1] = s_obj; sh_cnt[wv][2] = s_oth; }
+    if (lane == 0) sh_max[wv] = dmax;
+    if (oob) atomicAdd(&sh_oob, oob);
+    __syncthreads();
+    if (wv == 0) {
+        int c0 = sh_cnt[lane][0], c1 = sh_cnt[lane][1], c2 = sh_cnt[lane][2];
+        float m = sh_max[lane];
+#pragma unroll
+        for (int o = 1; o < 32; o <<= 1) {
+            const int t0 = __shfl_up_sync(0xffffffffu, c0, o), t1 = __shfl_up_sync(0xffffffffu, c1, o),
+                      t2 = __shfl_up_sync(0xffffffffu, c2, o);
+            if (lane >= o) { c0 += t0; c1 += t1; c2 += t2; }
+        }
+#pragma unroll
+        for (int o = 16; o > 0; o >>= 1) m = fmaxf(m, __shfl_xor_sync(0xffffffffu, m, o));
+        sh_cnt[lane][0] = c0 - sh_cnt[lane][0];   // exclusive warp offsets
+        sh_cnt[lane][1] = c1 - sh_cnt[lane][1];
+        sh_cnt[lane][2] = c2 - sh_cnt[lane][2];
+        sh_max[lane] = m;
+    }
+    __syncthreads();
+    int rk_inv = sh_cnt[wv][0] + s_inv - n_inv, rk_obj = sh_cnt[wv][1] + s_obj - n_obj,
+        rk_oth = sh_cnt[wv][2] + s_oth - n_oth;
+    const float max_bound = sh_max[0];                                             // vmap.py:489
+    if (tid == 0 && a.oob_count && sh_oob) atomicAdd(a.oob_count, sh_oob);
+
+    // ---- pass B: sample placement ----------------------------------------------------------------------
+    const float eps = a.eps;
+    for (int ray = r_begin; ray < r_end; ++ray) {
+        const RayPix p = ray_pixel(a, obj, ray);
+        const size_t o = (size_t)obj * n_rays + ray;
+        const float d = a.gt_depth[o];
+        const int state = a.labels[o];
+        const bool invalid = d <= a.min_bound;
+        float zs[MAXB];
+        if (invalid) {
+            // stratified_bins(min_bound, max(sampled_depth), S) -- vmap.py:493-498, utils.py:342-379
+            const size_t row = ((size_t)obj * n_rays + (a.tape_by_rank ? rk_inv : ray)) * S;
+            const float range = __fsub_rn(max_bound, a.min_bound);
+            const float blen = __fdiv_rn(range, (float)S);
+            for (int i = 0; i < S; ++i)
+                zs[i] = __fadd_rn(__fadd_rn(__fmul_rn(range, k.lin_s[i]), a.min_bound), __fmul_rn(a.r_invalid[row + i], blen));
+            ++rk_inv;
+        } else {
+            const int rk_val = a.tape_by_rank ? (ray - rk_inv) : ray;              // rank among valid rays
+            {   // cam -> surface: stratified_bins(min_bound, d - eps, n_c2s) -- vmap.py:506-509
+                const size_t row = ((size_t)obj * n_rays + rk_val) * a.n_c2s;
+                const float range = __fsub_rn(__fsub_rn(d, eps), a.min_bound);
+                const float blen = __fdiv_rn(range, (float)a.n_c2s);
+                for (int i = 0; i < a.n_c2s; ++i)
+                    zs[i] = __fadd_rn(__fadd_rn(__fmul_rn(range, k.lin_c[i]), a.min_bound), __fmul_rn(a.r_valid[row + i], blen));
+            }
+            if (state == 1) {
+                // normal_bins_sampling: N(0, eps/3) draws sorted ascending, clipped to +-eps, + d -- utils.py:382-397
+                const size_t row = ((size_t)obj * n_rays + (a.tape_by_rank ? rk_obj : ray)) * a.n_bins;
+                float b[MAXB];
+                for (int i = 0; i < a.n_bins; ++i) b[i] = a.r_normal[row + i];
+                sort_small(b, a.n_bins);
+                for (int i = 0; i < a.n_bins; ++i) zs[a.n_c2s + i] = __fadd_rn(d, fminf(fmaxf(b[i], -eps), eps));
+                ++rk_obj;
+            } else {
+                // stratified_bins(d - eps, d + other_eps, n_bins) -- vmap.py:538-542
+                const size_t row = ((size_t)obj * n_rays + (a.tape_by_rank ? rk_oth : ray)) * a.n_bins;
+                const float lo = __fsub_rn(d, eps), hi = __fadd_rn(d, a.other_eps);
+                const float range = __fsub_rn(hi, lo);
+                const float blen = __fdiv_rn(range, (float)a.n_bins);
+                for (int i = 0; i < a.n_bins; ++i)
+                    zs[a.n_c2s + i] = __fadd_rn(__fadd_rn(__fmul_rn(range, k.lin_b[i]), lo), __fmul_rn(a.r_other[row + i], blen));
+                ++rk_oth;
+            }
+        }
+        // rays: dir_W = R dir_C, origin = T[:3,3] (utils.py:324-336); points = o + d*z (vmap.py:548-549)
+        const float* T = a.t_wc[obj] + 16 * p.kf;
+        const float* dc = a.rays_dir + ((size_t)p.iw * a.H + p.ih) * 3;
+        const float dx = dc[0], dy = dc[1], dz = dc[2];
+        const float wx = T[0] * dx + T[1] * dy + T[2] * dz;
+        const float wy = T[4] * dx + T[5] * dy + T[6] * dz;
+        const float wz = T[8] * dx + T[9] * dy + T[10] * dz;
+        const float ox = T[3], oy = T[7], oz = T[11];
+        float* zo = a.z + o * S;
+        float* po = a.pcs + o * S * 3;
+        for (int i = 0; i < S; ++i) {
+            zo[i] = zs[i];
+            po[3 * i + 0] = __fadd_rn(ox, __fmul_rn(wx, zs[i]));
+            po[3 * i + 1] = __fadd_rn(oy, __fmul_rn(wy, zs[i]));
+            po[3 * i + 2] = __fadd_rn(oz, __fmul_rn(wz, zs[i]));
+        }
+    }
+}
+
+// ---- Philox4x32-10 counter RNG: value i of object id `oid` in frame `frame` depends only on (seed, frame, oid, i)
+__device__ __forceinline__ uint4 philox4x32_10(uint4 ctr, uint2 key) {
+#pragma unroll
+    for (int r = 0; r < 10; ++r) {
+        const uint32_t hi0 = __umulhi(0xD2511F53u, ctr.x), lo0 = 0xD2511F53u * ctr.x;
+        const uint32_t hi1 = __umulhi(0xCD9E8D57u, ctr.z), lo1 = 0xCD9E8D57u * ctr.z;
+        ctr = make_uint4(hi1 ^ ctr.y ^ key.x, lo1, hi0 ^ ctr.w ^ key.y, lo0);
+        key.x += 0x9E3779B9u;
+        key.y += 0xBB67AE85u;
+    }
+    return ctr;
+}
+
+__global__ void k_rng_fill(uint64_t seed, uint32_t frame, const int32_t* __restrict__ obj_ids, int64_t per_obj, int kind,
+                           float std, float* __restrict__ out) {
+    const int o = blockIdx.y;
+    const uint32_t oid = (uint32_t)obj_ids[o];
+    const int64_t n4 = (per_obj + 3) / 4;
+    for (int64_t q = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; q < n4; q += (int64_t)gridDim.x * blockDim.x) {
+        const uint4 r = philox4x32_10(make_uint4((uint32_t)q, (uint32_t)(q >> 32), oid, frame),
+                                      make_uint2((uint32_t)seed, (uint32_t)(seed >> 32)));
+        float v[4];
+        if (kind == 0) {
+            v[0] = (float)(r.x >> 8) * 5.9604644775390625e-8f; v[1] = (float)(r.y >> 8) * 5.9604644775390625e-8f;
+            v[2] = (float)(r.z >> 8) * 5.9604644775390625e-8f; v[3] = (float)(r.w >> 8) * 5.9604644775390625e-8f;
+        } else {
+            const float u0 = ((float)(r.x >> 8) + 1.f) * 5.9604644775390625e-8f, u1 = (float)(r.y >> 8) * 5.9604644775390625e-8f;
+            const float u2 = ((float)(r.z >> 8) + 1.f) * 5.9604644775390625e-8f, u3 = (float)(r.w >> 8) * 5.9604644775390625e-8f;
+            const float ra = sqrtf(-2.f * logf(u0)) * std, rb = sqrtf(-2.f * logf(u2)) * std;
+            float s, c;
+            sincospif(2.f * u1, &s, &c);
+            v[0] = ra * c; v[1] = ra * s;
+            sincospif(2.f * u3, &s, &c);
+            v[2] = rb * c; v[3] = rb * s;
+        }
+        float* dst = out + (size_t)o * per_obj + 4 * q;
+        for (int i = 0; i < 4; ++i)
+            if (4 * q + i < per_obj) dst[i] = v[i];
+    }
+}
+
+}  // namespace
+
+extern "C" int oo_sample_rays(const oo_sample_args* a, void* stream) {
+    OO_REQUIRE(a, "oo_sample_rays: null args");
+    OO_REQUIRE(a->n_obj > 0 && a->n_frames > 0 && a->n_samples > 0, "oo_sample_rays: empty request");
+    const int S = a->n_c2s + a->n_bins;
+    OO_REQUIRE(a->n_c2s >= 1 && a->n_bins >= 1 && S + 1 <= MAXB, "oo_sample_rays: need 1 <= n_c2s, n_bins and S <= 32");
+    OO_REQUIRE(a->rgbs && a->depth && a->t_wc && a->bbox && a->rays_dir && a->kf_ids && a->u_w && a->u_h,
+               "oo_sample_rays: null input");
+    OO_REQUIRE(a->r_invalid && a->r_valid && a->r_normal && a->r_other, "oo_sample_rays: null RNG tape");
+    OO_REQUIRE(a->gt_rgb && a->gt_depth && a->valid && a->labels && a->pcs && a->z, "oo_sample_rays: null output");
+    OO_REQUIRE(a->lin_s_host && a->lin_c2s_host && a->lin_bins_host, "oo_sample_rays: null linspace table");
+    OO_REQUIRE(!a->feat_row || (a->part_frame && a->part_down > 0 && a->pw > 0 && a->ph > 0),
+               "oo_sample_rays: part features requested without part_frame / part map size");
+    SampleK k;
+    k.a = *a;
+    for (int i = 0; i <= S; ++i) k.lin_s[i] = a->lin_s_host[i];
+    for (int i = 0; i <= a->n_c2s; ++i) k.lin_c[i] = a->lin_c2s_host[i];
+    for (int i = 0; i <= a->n_bins; ++i) k.lin_b[i] = a->lin_bins_host[i];
+    k_sample<<<a->n_obj, NTH, 0, (cudaStream_t)stream>>>(k);
+    OO_LAUNCH_CHECK();
+    return 0;
+}
+
+extern "C" int oo_rng_fill(uint64_t seed, uint32_t frame, const int32_t* obj_ids, int n_obj, int64_t per_obj, int kind,
+                           float std, float* out, void* stream) {
+    OO_REQUIRE(obj_ids && out && n_obj > 0 && per_obj > 0 && (kind == 0 || kind == 1), "oo_rng_fill: bad argument");
+    const int64_t n4 = (per_obj + 3) / 4;
+    int gx = (int)((n4 + 255) / 256);
+    if (gx > 148 * 8) gx = 148 * 8;
+    k_rng_fill<<<dim3(gx, n_obj), 256, 0, (cudaStream_t)stream>>>(seed, frame, obj_ids, per_obj, kind, std, out);
+    OO_LAUNCH_CHECK();
+    return 0;
+}

@@ -75,6 +75,7 @@ struct TileCtx {
     const float* wocl_t;       // this object's out_clip.weight transposed [32][512]
     float* slab;               // gradient slab of the current (CTA, object) slot
     int nrays;                 // <= RT
+    int npts;                  // valid points in the tile (nrays * S when training)
     int first_tile;            // first tile of this slot: out_clip gradient is stored, not accumulated
     int flags;                 // OO_FLAG_NO_OBJ (2) / OO_FLAG_NO_SEM (4) for this step
     float scale;               // UniDirsEmbed scale
@@ -268,7 +269,7 @@ OO_DEV void tile_phase(int tid, float* __restrict__ sm, const TileCtx& c, TileAc
 
     if constexpr (PH == 0) {
         // scaled coordinates t = x / scale (embedding.py:47) -> T rows and e1[0:3]
-        const int n = c.nrays * S * 3;
+        const int n = c.npts * 3;
         for (int i = tid; i < P * 3; i += NTHREADS) {
             const float x = i < n ? OO_LDG(c.pcs + i) : 0.f;
             const int p = i / 3, ch = i - 3 * p;

@@ -76,6 +76,7 @@ __global__ void __launch_bounds__(NTHREADS, 1) k_train(const TrainParams prm) {
         }
         const size_t ray = (size_t)obj * prm.b.rays_per_obj + prm.ray0 + r0;
         c.nrays = min(RT, prm.R - r0);
+        c.npts = c.nrays * S;
         c.pcs = prm.b.pcs + ray * (S * 3);
         c.z = prm.b.z + ray * S;
         c.gt_depth = prm.b.gt_depth + ray;

@@ -1,0 +1,141 @@
+"""Thin functional wrappers over the C ABI (tensors in, tensors out).  Everything here launches CUDA kernels
+from libopenobj_b200.so; nothing falls back to PyTorch arithmetic."""
+import ctypes
+
+import torch
+
+from . import _lib, layout
+from ._lib import check, lib, ptr, stream
+
+
+def _dev(t):
+    if not t.is_cuda:
+        raise _lib.OOError("openobj_b200 kernels need CUDA tensors; got a %s tensor (no CPU fallback)" % t.device)
+    return torch.cuda.device(t.device)
+
+
+def forward(theta, pcs=None, emb=None, scale=2.0, want_clip=True, want_emb=False):
+    """vmap(pe) -> vmap(fc) forward.  theta [N,PSTRIDE]; pcs [N,...,3] or emb [N,...,129].
+    Returns alpha [N,...,1] (x10 applied), color [N,...,3], clip [N,...,512] or None, emb or None."""
+    src = pcs if pcs is not None else emb
+    _dev(theta)
+    n = theta.shape[0]
+    lead = list(src.shape[:-1])
+    m = 1
+    for s in lead[1:]:
+        m *= s
+    src = src.contiguous().float()
+    f32 = dict(dtype=torch.float32, device=theta.device)
+    alpha = torch.empty(n, m, **f32)
+    color = torch.empty(n, m, 3, **f32)
+    clip = torch.empty(n, m, layout.CLIP, **f32) if want_clip else None
+    emb_o = torch.empty(n, m, 129, **f32) if want_emb else None
+    with _dev(theta):
+        check(lib().oo_forward(ptr(theta), n, ptr(src) if pcs is not None else None,
+                               ptr(src) if pcs is None else None, m, float(scale), ptr(alpha), ptr(color), ptr(clip),
+                               ptr(emb_o), stream()), "oo_forward")
+    return (alpha.view(lead + [1]), color.view(lead + [3]),
+            None if clip is None else clip.view(lead + [layout.CLIP]),
+            None if emb_o is None else emb_o.view(lead + [129]))
+
+
+class _StepLoss(torch.autograd.Function):
+    """loss.step_batch_loss as one fused forward / backward kernel pair (K3)."""
+
+    @staticmethod
+    def forward(ctx, alpha, color, gt_depth, gt_color, labels, z, pred_feat, gt_feat, cs, os_, fs):
+        n, r, s = z.shape
+        dev = z.device
+        alpha_c = alpha.reshape(n, r, s).contiguous().float()
+        color_c = color.reshape(n, r, s, 3).contiguous().float()
+        gt_depth, gt_color, z = gt_depth.contiguous().float(), gt_color.contiguous().float(), z.contiguous().float()
+        labels = labels.contiguous().to(torch.uint8)
+        cf = 0
+        if pred_feat is not None:
+            pred_feat, gt_feat = pred_feat.contiguous().float(), gt_feat.contiguous().float()
+            cf = pred_feat.shape[-1]
+        L = lib()
+        ws = torch.empty(n * r * L.oo_loss_ws_per_ray() + 8 * n, dtype=torch.float32, device=dev)
+        terms = torch.empty(n, 4, dtype=torch.float32, device=dev)
+        loss = torch.empty(1, dtype=torch.float32, device=dev)
+        flags = torch.zeros(1, dtype=torch.int32, device=dev)
+        with _dev(z):
+            check(L.oo_loss_fwd(ptr(alpha_c), ptr(color_c), ptr(z), ptr(gt_depth), ptr(gt_color), ptr(labels),
+                                ptr(pred_feat), ptr(gt_feat), n, r, s, cf, cs, os_, fs, ptr(terms), ptr(loss), ptr(flags),
+                                ptr(ws), stream()), "oo_loss_fwd")
+        ctx.save_for_backward(alpha_c, color_c, z, gt_depth, gt_color, labels, pred_feat, gt_feat, flags, ws)
+        ctx.dims = (n, r, s, cf, cs, os_, fs, alpha.shape, color.shape)
+        ctx.mark_non_differentiable(terms, flags)
+        return loss.reshape(()), terms, flags
+
+    @staticmethod
+    def backward(ctx, g_loss, _g_terms, _g_flags):
+        alpha_c, color_c, z, gt_depth, gt_color, labels, pred_feat, gt_feat, flags, ws = ctx.saved_tensors
+        n, r, s, cf, cs, os_, fs, a_shape, c_shape = ctx.dims
+        d_alpha = torch.empty_like(alpha_c)
+        d_color = torch.empty_like(color_c)
+        d_pred = torch.empty_like(pred_feat) if pred_feat is not None else None
+        with _dev(z):
+            check(lib().oo_loss_bwd(ptr(alpha_c), ptr(color_c), ptr(z), ptr(gt_depth), ptr(gt_color), ptr(labels),
+                                    ptr(pred_feat), ptr(gt_feat), n, r, s, cf, cs, os_, fs, float(g_loss), ptr(flags),
+                                    ptr(ws), ptr(d_alpha), ptr(d_color), ptr(d_pred), stream()), "oo_loss_bwd")
+        return (d_alpha.view(a_shape), d_color.view(c_shape), None, None, None, None, d_pred, None, None, None, None)
+
+
+def step_loss(alpha, color, gt_depth, gt_color, labels, z, pred_feat=None, gt_feat=None,
+              color_scaling=5.0, opacity_scaling=10.0, feat_scaling=5.0):
+    """Returns (loss scalar with autograd, per-object terms [N,4], flags int32[1])."""
+    return _StepLoss.apply(alpha, color, gt_depth, gt_color, labels, z, pred_feat, gt_feat,
+                           float(color_scaling), float(opacity_scaling), float(feat_scaling))
+
+
+def adamw_flat(p, g, m, v, step, lr=1e-3, weight_decay=0.013, betas=(0.9, 0.999), eps=1e-8):
+    with _dev(p):
+        check(lib().oo_adamw_flat(ptr(p), ptr(g), ptr(m), ptr(v), p.numel(), int(step), lr, weight_decay, betas[0], betas[1],
+                                  eps, stream()), "oo_adamw_flat")
+
+
+def rng_fill(out, seed, frame, obj_ids, kind="uniform", std=1.0):
+    """out [n_obj, per_obj] f32 <- Philox4x32-10 keyed by (seed, frame, object id, element)."""
+    n, per = out.shape
+    with _dev(out):
+        check(lib().oo_rng_fill(int(seed), int(frame), ptr(obj_ids), n, per, 0 if kind == "uniform" else 1, float(std),
+                                ptr(out), stream()), "oo_rng_fill")
+    return out
+
+
+def zmerge(masks, depths, rgbs, is_bg):
+    """Sequential strict depth test across objects in order (train.py:577-594).
+    masks [K,W,H] u8/bool, depths [K,W,H] f32, rgbs [K,W,H,3] u8, is_bg [K]."""
+    k = masks.shape[0]
+    shp = masks.shape[1:]
+    npix = masks[0].numel()
+    dev = masks.device
+    masks = masks.contiguous().to(torch.uint8)
+    depth_out = torch.empty(shp, dtype=torch.float32, device=dev)
+    rgb_out = torch.empty(tuple(shp) + (3,), dtype=torch.uint8, device=dev)
+    win = torch.empty(shp, dtype=torch.int32, device=dev)
+    bg = torch.as_tensor(is_bg, dtype=torch.uint8).to(dev).contiguous()
+    with _dev(masks):
+        check(lib().oo_zmerge(ptr(masks), ptr(depths.contiguous()), ptr(rgbs.contiguous()), ptr(bg), k, npix,
+                              ptr(depth_out), ptr(rgb_out), ptr(win), stream()), "oo_zmerge")
+    return depth_out, rgb_out, win
+
+
+def fma_peak_tflops(iters=4000):
+    """Measured FP32 FFMA throughput of this GPU (roofline denominator of the fused step)."""
+    L = lib()
+    sink = torch.zeros(4, device="cuda")
+    n_sm = _lib.n_sm()
+    check(L.oo_fma_peak(n_sm, 200, ptr(sink), stream()))
+    torch.cuda.synchronize()
+    e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    best = 0.0
+    for _ in range(3):
+        e0.record()
+        check(L.oo_fma_peak(n_sm, iters, ptr(sink), stream()))
+        e1.record()
+        torch.cuda.synchronize()
+        flops = n_sm * 4 * 256 * iters * 16 * 8 * 2
+        best = max(best, flops / (e0.elapsed_time(e1) * 1e-3) / 1e12)
+    return best

@@ -1,0 +1,119 @@
+"""Host side of K2: batches sceneObject.get_training_samples + sample_3d_points of MANY objects into one launch
+(reference loop: objnerf/train.py:317-332 calling vmap.py:386-554 per object)."""
+import ctypes
+from dataclasses import dataclass
+from typing import Optional
+
+import torch
+
+from . import ops
+from ._lib import SampleArgs, check, lib, ptr, stream
+
+KF_MAX = 20
+
+
+def torch_linspace01(n):
+    """torch.linspace(0, 1, n+1) on the CPU -- what utils.stratified_bins uses (utils.py:349)."""
+    return torch.linspace(0, 1, n + 1, dtype=torch.float32).contiguous()
+
+
+@dataclass
+class SampleTapes:
+    """RNG tape for n_obj objects.  by_rank=True: class-tape row j belongs to the j-th ray of that
+    class (the reference's consumption order); False: row = ray index (shard-independent counter RNG)."""
+    kf_ids: torch.Tensor       # int64 [n_obj, n_frames]
+    u_w: torch.Tensor          # f32 [n_obj, n_rays]
+    u_h: torch.Tensor
+    r_invalid: torch.Tensor    # f32 [n_obj, n_rays, S]
+    r_valid: torch.Tensor      # f32 [n_obj, n_rays, n_c2s]
+    r_normal: torch.Tensor     # f32 [n_obj, n_rays, n_bins]
+    r_other: torch.Tensor      # f32 [n_obj, n_rays, n_bins]
+    by_rank: bool = False
+
+
+@dataclass
+class SampleOut:
+    gt_rgb: torch.Tensor       # u8 [n_obj, n_rays, 3]
+    gt_depth: torch.Tensor     # f32 [n_obj, n_rays]
+    valid: torch.Tensor        # u8 [n_obj, n_rays]
+    labels: torch.Tensor       # u8 [n_obj, n_rays]
+    pcs: torch.Tensor          # f32 [n_obj, n_rays, S, 3]
+    z: torch.Tensor            # f32 [n_obj, n_rays, S]
+    feat_row: Optional[torch.Tensor]   # int32 [n_obj, n_rays] rows of global_partfeat.view(-1, C)
+    pix: Optional[torch.Tensor]        # int64 [n_obj, n_rays, 3] (kf, w, h)
+    oob: torch.Tensor          # int32 [1]
+
+
+def _ptr_table(tensors, device):
+    return torch.tensor([t.data_ptr() for t in tensors], dtype=torch.int64, device=device)
+
+
+def latest_kf_ids(draws, n_keyframes, latest):
+    """vmap.py:390-410: the last two of the n_frames keyframe ids are forced to the two latest keyframes."""
+    if n_keyframes > 2:
+        return torch.cat([draws, torch.as_tensor(latest[-2:], dtype=torch.int64, device=draws.device)])
+    return draws
+
+
+def device_tapes(objects, n_frames, n_samples, n_c2s, n_bins, eps, seed, frame, device):
+    """Counter-based tapes (Philox keyed by seed/frame/object id) for a list of sceneObject."""
+    n = len(objects)
+    n_rays = n_frames * n_samples
+    S = n_c2s + n_bins
+    ids = torch.tensor([o.obj_id for o in objects], dtype=torch.int32, device=device)
+    f32 = dict(dtype=torch.float32, device=device)
+    u_kf = ops.rng_fill(torch.empty(n, n_frames, **f32), seed, 8 * frame + 0, ids)
+    nkf = torch.tensor([o.n_keyframes for o in objects], dtype=torch.float32, device=device)[:, None]
+    kf = torch.minimum((u_kf * nkf).long(), (nkf - 1).long())
+    for i, o in enumerate(objects):              # forced latest two keyframes (host bookkeeping, vmap.py:398-400)
+        if o.n_keyframes > 2:
+            kf[i, -2:] = torch.as_tensor(o.lastest_kf_queue[-2:], device=device)
+    return SampleTapes(
+        kf_ids=kf.contiguous(),
+        u_w=ops.rng_fill(torch.empty(n, n_rays, **f32), seed, 8 * frame + 1, ids),
+        u_h=ops.rng_fill(torch.empty(n, n_rays, **f32), seed, 8 * frame + 2, ids),
+        r_invalid=ops.rng_fill(torch.empty(n, n_rays * S, **f32), seed, 8 * frame + 3, ids).view(n, n_rays, S),
+        r_valid=ops.rng_fill(torch.empty(n, n_rays * n_c2s, **f32), seed, 8 * frame + 4, ids).view(n, n_rays, n_c2s),
+        r_normal=ops.rng_fill(torch.empty(n, n_rays * n_bins, **f32), seed, 8 * frame + 5, ids, "normal", eps / 3.).view(
+            n, n_rays, n_bins),
+        r_other=ops.rng_fill(torch.empty(n, n_rays * n_bins, **f32), seed, 8 * frame + 6, ids).view(n, n_rays, n_bins),
+        by_rank=False)
+
+
+def sample(rgbs, depth, t_wc, bbox, part_frame, rays_dir, tapes: SampleTapes, n_frames, n_samples, n_c2s=1, n_bins=9,
+           eps=0.1, other_eps=0.05, min_bound=0.0, part_down=0, part_hw=(0, 0), want_pix=False, out: SampleOut = None):
+    """rgbs/depth/t_wc/bbox: lists (one per object) of the keyframe ring tensors in the reference layout
+    (u8 [KF,W,H,4], f32 [KF,W,H], f32 [KF,4,4], f32 [KF,4]); part_frame int32 [n_obj,20] or None."""
+    n = len(rgbs)
+    dev = rays_dir.device
+    W, H = rays_dir.shape[:2]
+    n_rays = n_frames * n_samples
+    S = n_c2s + n_bins
+    if out is None:
+        u8 = dict(dtype=torch.uint8, device=dev)
+        f32 = dict(dtype=torch.float32, device=dev)
+        out = SampleOut(torch.empty(n, n_rays, 3, **u8), torch.empty(n, n_rays, **f32), torch.empty(n, n_rays, **u8),
+                        torch.empty(n, n_rays, **u8), torch.empty(n, n_rays, S, 3, **f32), torch.empty(n, n_rays, S, **f32),
+                        torch.empty(n, n_rays, dtype=torch.int32, device=dev) if part_frame is not None else None,
+                        torch.empty(n, n_rays, 3, dtype=torch.int64, device=dev) if want_pix else None,
+                        torch.zeros(1, dtype=torch.int32, device=dev))
+    tabs = [_ptr_table(x, dev) for x in (rgbs, depth, t_wc, bbox)]
+    lin = [torch_linspace01(S), torch_linspace01(n_c2s), torch_linspace01(n_bins)]
+    a = SampleArgs()
+    a.n_obj, a.n_frames, a.n_samples = n, n_frames, n_samples
+    a.W, a.H, a.n_c2s, a.n_bins = W, H, n_c2s, n_bins
+    a.eps, a.other_eps, a.min_bound = eps, other_eps, min_bound
+    a.part_down, a.pw, a.ph = int(part_down), int(part_hw[0]), int(part_hw[1])
+    a.rgbs, a.depth, a.t_wc, a.bbox = [ptr(t) for t in tabs]
+    a.part_frame = ptr(part_frame)
+    a.rays_dir = ptr(rays_dir)
+    a.kf_ids, a.u_w, a.u_h = ptr(tapes.kf_ids), ptr(tapes.u_w), ptr(tapes.u_h)
+    a.r_invalid, a.r_valid, a.r_normal, a.r_other = (ptr(tapes.r_invalid), ptr(tapes.r_valid), ptr(tapes.r_normal),
+                                                     ptr(tapes.r_other))
+    a.tape_by_rank = int(tapes.by_rank)
+    a.lin_s_host, a.lin_c2s_host, a.lin_bins_host = [ctypes.c_void_p(t.data_ptr()) for t in lin]
+    a.gt_rgb, a.gt_depth, a.valid, a.labels = ptr(out.gt_rgb), ptr(out.gt_depth), ptr(out.valid), ptr(out.labels)
+    a.pcs, a.z, a.feat_row, a.pix, a.oob_count = ptr(out.pcs), ptr(out.z), ptr(out.feat_row), ptr(out.pix), ptr(out.oob)
+    with torch.cuda.device(dev):
+        check(lib().oo_sample_rays(ctypes.byref(a), stream()), "oo_sample_rays")
+    return out

@@ -1,0 +1,253 @@
+"""Mirror of objnerf/vmap.py: `sceneObject` (keyframe rings + sampling + eval render + checkpoints) and
+`cameraInfo`, with the reference's constructor / method signatures.  Sampling and rendering run in the CUDA
+kernels K2 / K5; the keyframe bookkeeping (vmap.py:166-257) is host logic restated here."""
+import copy
+import ctypes
+import os
+import random
+
+import numpy as np
+import torch
+
+from . import layout, sampler, trainer
+from ._lib import RenderArgs, check, lib, ptr, stream
+
+
+class KeyframeRing:
+    """Which ring slot a new frame lands in, and which keyframes survive (vmap.py:166-257).
+
+    Keyframe every `keyframe_step` appended frames (float step, e.g. 2.5 -> every 5th), otherwise the newest slot
+    is overwritten; once buffer_size-1 keyframes exist the frame goes to `kf_pointer`, and when that frame is a
+    keyframe a random non-latest entry is pruned with Python's `random.choice` (vmap.py:256)."""
+
+    def __init__(self, first_frame_id, buffer_size, keyframe_step):
+        self.buffer_size, self.keyframe_step = buffer_size, keyframe_step
+        self.n_keyframes = 1
+        self.kf_pointer = None
+        self.kf_buffer_full = False
+        self.frame_cnt = 0
+        self.latest = []
+        self.slot_of = {first_frame_id: 0}        # insertion-ordered frame id -> slot (the reference's bidict)
+
+    def _rekey(self, slot, frame_id):
+        for k in [k for k, v in self.slot_of.items() if v == slot]:
+            del self.slot_of[k]
+        self.slot_of[frame_id] = slot
+
+    def push(self, frame_id):
+        """Returns the slot to write the frame into."""
+        is_kf = (self.frame_cnt % self.keyframe_step == 0) or self.n_keyframes == 1
+        if self.n_keyframes == self.buffer_size - 1:
+            self.kf_buffer_full = True
+            if self.kf_pointer is None:
+                self.kf_pointer = self.n_keyframes
+            slot = self.kf_pointer
+            self._rekey(slot, frame_id)
+            if is_kf:
+                self.latest.append(slot)
+                _, self.kf_pointer = random.choice(list(self.slot_of.items())[:-2])
+        elif not is_kf:
+            slot = self.n_keyframes - 1
+            self._rekey(slot, frame_id)
+        else:
+            slot = self.n_keyframes
+            self.slot_of[frame_id] = slot
+            self.latest.append(slot)
+            self.n_keyframes += 1
+        self.frame_cnt += 1
+        self.latest = self.latest[-2:]
+        return slot
+
+
+class sceneObject:
+    def __init__(self, cfg, obj_id, rgb, depth, mask, bbox_2d, t_wc, live_frame_id, clip_feat=None, caption_feat=None):
+        assert rgb.shape[:2] == depth.shape == mask.shape and bbox_2d.shape == (4,) and t_wc.shape == (4, 4)
+        self.do_bg, self.obj_id = cfg.do_bg, obj_id
+        self.data_device, self.training_device = cfg.data_device, cfg.training_device
+        self.part_mode, self.stride = cfg.part_mode, cfg.stride
+        bg = self.do_bg and obj_id == 0
+        self.obj_scale = cfg.bg_scale if bg else cfg.obj_scale
+        self.hidden_feature_size = cfg.hidden_feature_size_bg if bg else cfg.hidden_feature_size
+        self.n_bins_cam2surface = cfg.n_bins_cam2surface_bg if bg else cfg.n_bins_cam2surface
+        self.keyframe_step = cfg.keyframe_step_bg if bg else cfg.keyframe_step
+        self.frames_width, self.frames_height = rgb.shape[0], rgb.shape[1]
+        self.min_bound, self.max_bound = cfg.min_depth, cfg.max_depth
+        self.n_bins, self.n_unidir_funcs = cfg.n_bins, cfg.n_unidir_funcs
+        self.surface_eps, self.stop_eps = cfg.surface_eps, cfg.stop_eps
+        self.keyframe_buffer_size = cfg.keyframe_buffer_size
+        self.ring = KeyframeRing(live_frame_id, self.keyframe_buffer_size, self.keyframe_step)
+        self.feat_cnt, self.clip_feat, self.caption_feat = 1, clip_feat, caption_feat
+        self.eps_fine_vis, self.n_bins_fine_vis = cfg.eps_fine_vis, cfg.n_bins_fine_vis
+        dev, K, W, H = self.data_device, self.keyframe_buffer_size, self.frames_width, self.frames_height
+        self.bbox = torch.empty(K, 4, device=dev)                       # [w_lo, w_hi, h_lo, h_hi] per slot
+        self.rgb_idx, self.state_idx = slice(0, 3), slice(3, 4)
+        self.rgbs_batch = torch.empty(K, W, H, 4, dtype=torch.uint8, device=dev)   # rgb + pixel state
+        self.depth_batch = torch.empty(K, W, H, dtype=torch.float32, device=dev)
+        self.t_wc_batch = torch.empty(K, 4, 4, dtype=torch.float32, device=dev)
+        if self.part_mode:
+            self.part_down = cfg.part_down
+            self.use_frame = np.zeros(K)
+        self.other_obj, self.this_obj, self.unknown_obj = 0, 1, 2
+        self.semantic_id = None
+        self._write_slot(0, rgb, depth, mask, bbox_2d, t_wc, live_frame_id)
+        tcfg = copy.deepcopy(cfg)
+        tcfg.obj_id, tcfg.hidden_feature_size, tcfg.obj_scale = obj_id, self.hidden_feature_size, self.obj_scale
+        self.trainer = trainer.Trainer(tcfg)
+        self.bbox_final, self.serialized_bbox, self.bbox3d, self.bbox3dour, self.pc = False, None, None, None, []
+        self.obj_center = torch.tensor(0.0)
+
+    # reference attribute names, backed by the ring
+    n_keyframes = property(lambda self: self.ring.n_keyframes)
+    kf_pointer = property(lambda self: self.ring.kf_pointer)
+    kf_buffer_full = property(lambda self: self.ring.kf_buffer_full)
+    frame_cnt = property(lambda self: self.ring.frame_cnt)
+    lastest_kf_queue = property(lambda self: self.ring.latest)
+    kf_id_dict = property(lambda self: self.ring.slot_of)
+
+    def _write_slot(self, s, rgb, depth, mask, bbox_2d, t_wc, frame_id):
+        self.rgbs_batch[s, :, :, self.rgb_idx] = rgb
+        self.rgbs_batch[s, :, :, self.state_idx] = mask[..., None]
+        self.depth_batch[s] = depth
+        self.t_wc_batch[s] = t_wc
+        self.bbox[s] = bbox_2d
+        if self.part_mode:
+            self.use_frame[s] = frame_id
+
+    def append_keyframe(self, rgb, depth, mask, bbox_2d, t_wc, frame_id=1, clip_feat=None, caption_feat=None):
+        assert rgb.dtype == torch.uint8 and mask.dtype == torch.uint8 and depth.dtype == torch.float32
+        assert self.n_keyframes <= self.keyframe_buffer_size - 1
+        self._write_slot(self.ring.push(frame_id), rgb, depth, mask, bbox_2d, t_wc, frame_id)
+        if clip_feat is not None:
+            self.clip_feat = np.vstack((self.clip_feat, clip_feat))
+            self.caption_feat = np.vstack((self.caption_feat, caption_feat))
+            self.feat_cnt += 1
+
+    def prune_keyframe(self):
+        return random.choice(list(self.ring.slot_of.items())[:-2])
+
+    def part_frame_row(self):
+        """(use_frame / stride).long() per slot (vmap.py:438-440, float64 on the host)."""
+        return torch.from_numpy((self.use_frame / self.stride).astype(np.int64)).to(torch.int32)
+
+    def get_training_samples(self, n_frames, n_samples, cached_rays_dir, global_partfeat, tapes=None):
+        """vmap.py:386-454 -> (gt_rgb, gt_depth, valid_mask, labels, pcs, z, partfeat), one launch of K2.
+        Random draws come from torch's generator on the data device in the reference's order unless `tapes`
+        (a sampler.SampleTapes with n_obj = 1) is given."""
+        dev = self.rgbs_batch.device
+        n_rays, S = n_frames * n_samples, self.n_bins_cam2surface + self.n_bins
+        if tapes is None:
+            nk = self.n_keyframes
+            draws = torch.randint(0, nk, (n_frames - 2 if nk > 2 else n_frames,), dtype=torch.long, device=dev)
+            kf = sampler.latest_kf_ids(draws, nk, self.lastest_kf_queue)
+            u_w = torch.rand(n_frames, n_samples, device=dev)
+            u_h = torch.rand(n_frames, n_samples, device=dev)
+            tapes = sampler.SampleTapes(kf[None].contiguous(), u_w.view(1, -1), u_h.view(1, -1),
+                                        torch.rand(1, n_rays, S, device=dev),
+                                        torch.rand(1, n_rays, self.n_bins_cam2surface, device=dev),
+                                        torch.empty(1, n_rays, self.n_bins, device=dev).normal_(0., self.surface_eps / 3.),
+                                        torch.rand(1, n_rays, self.n_bins, device=dev), by_rank=True)
+        part = self.part_mode and global_partfeat is not None
+        out = sampler.sample([self.rgbs_batch], [self.depth_batch], [self.t_wc_batch], [self.bbox],
+                             self.part_frame_row()[None].to(dev).contiguous() if part else None, cached_rays_dir, tapes,
+                             n_frames, n_samples, self.n_bins_cam2surface, self.n_bins, self.surface_eps, self.stop_eps,
+                             self.min_bound, self.part_down if part else 0,
+                             tuple(global_partfeat.shape[1:3]) if part else (0, 0))
+        pf = None
+        if part:
+            pf = global_partfeat.reshape(-1, global_partfeat.shape[-1])[out.feat_row[0].long()].view(n_frames, n_samples, -1)
+        return (out.gt_rgb[0].view(n_frames, n_samples, 3), out.gt_depth[0].view(n_frames, n_samples),
+                out.valid[0].bool(), out.labels[0], out.pcs[0].view(n_frames, n_samples, S, 3),
+                out.z[0].view(n_frames, n_samples, S), pf)
+
+    def get_bound(self, intrinsic_open3d=None, final=False):
+        if self.bbox_final or self.bbox3dour is not None:
+            return self.bbox3d, self.bbox3dour
+        raise NotImplementedError("3-D bounds come from open3d/trimesh in the reference (vmap.py:285-379); outside the "
+                                  "accelerated path -- set .bbox3dour (center, R, extent) from the host pipeline")
+
+    def render_2D_syn(self, T_WC, intrinsic_open3d, cached_rays_dir, T_WO=None, chunk_size=1000, do_fine=True,
+                      obj_mask=None, render_part=False, jitter=None, dense=False):
+        """vmap.py:604-685 over every pixel, as one K5 launch.  Returns (obj_mask [W,H] bool, depth[n], rgb[n,3] u8,
+        feat[n,512] or None) compressed by the mask like the reference; `dense=True` returns device maps instead."""
+        _, bb = self.get_bound(intrinsic_open3d, final=True)
+        dev = torch.device(self.training_device)
+        W, H = cached_rays_dir.shape[:2]
+        T_wc = torch.as_tensor(np.asarray(T_WC), dtype=torch.float32)
+        T_wo = torch.eye(4)
+        T_wo[:3, :3] = torch.as_tensor(np.asarray(bb.R), dtype=torch.float32)
+        T_wo[:3, 3] = torch.as_tensor(np.asarray(bb.center), dtype=torch.float32)
+        T_oc = torch.inverse(T_wo) @ T_wc                                  # trainer.py:157-160 (4x4 host algebra)
+        half = torch.as_tensor(np.asarray(bb.extent), dtype=torch.float32) / 2.0
+        n_bins = 150
+        by_rank = jitter is not None
+        if jitter is None:
+            jitter = torch.rand(W * H, n_bins, device=dev)
+        lin = sampler.torch_linspace01(n_bins)
+        theta = self.trainer.packed(dev)
+        f32 = dict(dtype=torch.float32, device=dev)
+        mask = torch.empty(W, H, dtype=torch.uint8, device=dev)
+        depth = torch.empty(W, H, **f32)
+        rgb = torch.empty(W, H, 3, dtype=torch.uint8, device=dev)
+        feat = torch.empty(W, H, layout.CLIP, **f32) if render_part else None
+        n_hit = torch.zeros(1, dtype=torch.int32, device=dev)
+        keep = [T_wc.to(dev), T_oc.to(dev).contiguous(), half.to(dev), cached_rays_dir.to(dev).contiguous(),
+                jitter.to(dev).contiguous()]
+        a = RenderArgs()
+        a.W, a.H, a.n_bins, a.scale = W, H, n_bins, float(self.trainer.obj_scale)
+        a.theta1, a.T_wc, a.T_oc, a.half_extent, a.rays_dir, a.jitter = [ptr(t) for t in [theta] + keep]
+        a.jitter_by_rank = int(by_rank)
+        a.lin_host = ctypes.c_void_p(lin.data_ptr())
+        a.mask, a.depth, a.rgb, a.feat, a.opacity, a.n_hit = ptr(mask), ptr(depth), ptr(rgb), ptr(feat), None, ptr(n_hit)
+        with torch.cuda.device(dev):
+            check(lib().oo_render_object(ctypes.byref(a), stream()), "oo_render_object")
+        if dense:
+            return mask.bool(), depth, rgb, feat
+        if int(n_hit.item()) <= 1:
+            return None, None, None
+        m = mask.bool()
+        if obj_mask is not None:
+            m = m & torch.as_tensor(obj_mask, device=dev)
+        return (m.cpu().numpy(), depth[m].cpu().numpy(), rgb[m].cpu().numpy(),
+                feat[m].cpu().numpy() if render_part else None)
+
+    def save_checkpoints(self, path, epoch):
+        """Same dict keys as vmap.py:556-576 (the viewer, visualization/gen_map_vis.py, reads these)."""
+        torch.save({"epoch": epoch, "FC_state_dict": self.trainer.fc_occ_map.state_dict(),
+                    "PE_state_dict": self.trainer.pe.state_dict(), "obj_id": self.obj_id, "bbox": self.bbox3dour,
+                    "obj_scale": self.trainer.obj_scale, "clip_feat": self.clip_feat, "caption_feat": self.caption_feat,
+                    "semantic_id": self.semantic_id}, os.path.join(path, "obj_" + str(self.obj_id) + ".pth"))
+
+    def load_checkpoints(self, ckpt_file):
+        if not os.path.exists(ckpt_file):
+            print("ckpt not exist ", ckpt_file)
+            return
+        ck = torch.load(ckpt_file, weights_only=False)
+        self.trainer.fc_occ_map.load_state_dict(ck["FC_state_dict"])
+        self.trainer.pe.load_state_dict(ck["PE_state_dict"])
+        self.obj_id, self.bbox3dour, self.trainer.obj_scale = ck["obj_id"], ck["bbox"], ck["obj_scale"]
+        self.trainer.fc_occ_map.to(self.training_device)
+        self.trainer.pe.to(self.training_device)
+        if "clip_feat" not in ck:
+            return False
+        self.clip_feat, self.caption_feat, self.semantic_id = ck["clip_feat"], ck["caption_feat"], ck["semantic_id"]
+        self.bbox_final = True
+        return True
+
+
+class cameraInfo:
+    """vmap.py:687-720.  Ray directions are built on the CPU (true division) and then moved, so that they equal the
+    reference's CPU values bit for bit (a CUDA build of the reference multiplies by 1/fx instead)."""
+
+    def __init__(self, cfg):
+        self.device = cfg.data_device
+        self.width, self.height = cfg.W, cfg.H
+        self.fx, self.fy, self.cx, self.cy = cfg.fx, cfg.fy, cfg.cx, cfg.cy
+        self.rays_dir_cache = self.get_rays_dirs()
+
+    def get_rays_dirs(self, depth_type="z"):
+        if depth_type != "z":
+            raise Exception("Get camera rays directions with euclidean depth not yet implemented")
+        dirs = torch.ones((self.width, self.height, 3))
+        dirs[:, :, 0] = ((torch.arange(end=self.width) - self.cx) / self.fx)[:, None]
+        dirs[:, :, 1] = ((torch.arange(end=self.height) - self.cy) / self.fy)
+        return dirs.to(self.device)

@@ -64,6 +64,7 @@ void emulate(const float* theta, const float* wocl_t, int n_obj, const float* pc
             }
             const size_t ray = (size_t)obj * rays_per_obj + (size_t)it * R + r0;
             c.nrays = (R - r0) < RT ? (R - r0) : RT;
+            c.npts = c.nrays * S;
             c.pcs = pcs + ray * (S * 3);
             c.z = z + ray * S;
             c.gt_depth = gt_depth + ray;

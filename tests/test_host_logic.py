@@ -1,0 +1,79 @@
+"""CPU tests of host-side logic: keyframe ring policy vs the reference trace, C-ABI exports, layout."""
+import ctypes
+import json
+import os
+import random
+import re
+
+import pytest
+import torch
+
+from openobj_b200 import layout
+
+ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+
+
+def test_keyframe_ring_matches_reference_trace():
+    from openobj_b200.vmap import KeyframeRing
+    t = json.load(open(os.path.join(ROOT, "tests", "golden", "keyframe_policy.json")))
+    random.seed(t["seed"])
+    ring = KeyframeRing(0, t["buffer"], t["keyframe_step"])
+    slots = {0: 0}
+    for rec in t["trace"][1:]:
+        s = ring.push(rec["frame"])
+        slots[s] = rec["frame"] // 10 % 250
+        assert ring.n_keyframes == rec["n_keyframes"] and ring.kf_pointer == rec["kf_pointer"]
+        assert ring.latest == rec["latest"] and ring.frame_cnt == rec["frame_cnt"]
+        assert [[k, v] for k, v in ring.slot_of.items()] == rec["kf_id_dict"]
+        for slot, mark in slots.items():
+            assert rec["slot_mark"][slot] == mark
+
+
+def test_library_exports_every_declared_symbol():
+    hdr = open(os.path.join(ROOT, "include", "openobj_b200.h")).read()
+    declared = set(re.findall(r"\b(oo_[a-z0-9_]+)\s*\(", hdr))
+    from openobj_b200 import _lib
+    assert declared == set(_lib.EXPORTS), declared ^ set(_lib.EXPORTS)
+    so = _lib.LIB_PATH
+    if not os.path.exists(so):
+        from openobj_b200 import build
+        build.build()
+    L = ctypes.CDLL(so)
+    for name in declared:
+        assert hasattr(L, name), name
+    L.oo_version.restype = ctypes.c_int
+    assert L.oo_version() == 1
+    L.oo_param_offset.restype = ctypes.c_int
+    L.oo_param_size.restype = ctypes.c_int
+    for i, (off, shp) in enumerate(zip(layout.OFFSETS, layout.SHAPES)):
+        assert L.oo_param_offset(i) == off and L.oo_param_size(i) == layout.numel(shp)
+    assert L.oo_param_offset(19) == -1
+
+
+def test_layout_views_roundtrip_and_reference_shapes():
+    import openobj_oracle as oc
+    fc, B = oc.init_params(4, generator=torch.Generator().manual_seed(0))
+    theta = layout.pack(fc + [B])
+    for v, t, (name, shp) in zip(layout.views(theta), fc + [B], oc.fc_shapes() + [("B_layer.weight", (21, 3))]):
+        assert tuple(v.shape[1:]) == tuple(shp) and torch.equal(v, t)
+    assert sum(layout.numel(s) for s in layout.SHAPES) == layout.PCOUNT
+
+
+def test_no_gpu_means_loud_failure():
+    if torch.cuda.is_available():
+        pytest.skip("GPU present")
+    from openobj_b200 import _lib, ops
+    from openobj_b200.ensemble import Ensemble
+    with pytest.raises(_lib.OOError):
+        Ensemble(2, device="cpu")
+    with pytest.raises(_lib.OOError):
+        ops.forward(torch.zeros(1, layout.PSTRIDE), pcs=torch.zeros(1, 4, 3))
+
+
+def test_product_never_imports_oracle():
+    pkg = os.path.join(ROOT, "openobj_b200")
+    for dirpath, _, files in os.walk(pkg):
+        for f in files:
+            if f.endswith((".py", ".cu", ".h", ".cuh")):
+                src = open(os.path.join(dirpath, f)).read()
+                assert "openobj_oracle" not in src and "ref_harness" not in src and "import philox" not in src, f

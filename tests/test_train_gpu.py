@@ -25,11 +25,19 @@ def make_batch(ms, labels=None, feat=True, dev="cuda:0"):
                                  lab.to(dev), ms["gt_feat"].to(dev) if feat else None)
 
 
-def check_grads(got_theta_grads, ref_grads, tol=2e-4):
+def check_grads(got_theta_grads, ref_grads, tol=1e-4):
+    """max |error| <= tol * max |reference| per tensor.  The reference gradients come from the oracle evaluated in
+    float64: its float32 autograd is itself ~5e-4 (up to 5e-2 on clip_linear) away from float64 on these sums, which
+    is noisier than the kernel (profiles/r1a diag: kernel vs f64 ~2e-6)."""
     for name, g, r in zip(layout.NAMES, layout.views(got_theta_grads.cpu()), ref_grads):
-        r = torch.zeros_like(g) if r is None else r
+        r = torch.zeros_like(g) if r is None else r.float()
         err, scale = float((g - r).abs().max()), float(r.abs().max())
         assert err <= tol * scale + 1e-7, (name, err, scale)
+
+
+def grads64(fc, B, pcs, z, gt_depth, rgb01, labels, gt_feat):
+    d = lambda t: None if t is None else t.double()
+    return oc.train_step_grads([d(p) for p in fc], d(B), d(pcs), d(z), d(gt_depth), d(rgb01), labels, d(gt_feat))
 
 
 @pytest.mark.parametrize("mode", ["on", "off", "zm"])
@@ -48,7 +56,10 @@ def test_golden_step_grads_and_loss(mode, n_sm):
     total = float(ens.total_loss(terms.cpu()))
     assert abs(total - float(ms["loss_" + mode])) <= 1e-4 * abs(float(ms["loss_" + mode])) + 1e-6   # rel 1e-4 on losses
     ref = [ms["g_%s%02d" % (mode, i)] if ("g_%s%02d" % (mode, i)) in ms else None for i in range(19)]
-    check_grads(g, ref)
+    check_grads(g, ref, tol=2e-4)     # reference's own fp32 autograd (frozen golden)
+    rt, rg = grads64(fc, ms["peB"], ms["pcs"], ms["z"], ms["gt_depth"], ms["gt_rgb8"] / 255., labels,
+                     ms["gt_feat"] if mode != "off" else None)
+    check_grads(g, rg)                # same algorithm in float64
     assert int(ens.flags[0]) == (2 if mode == "zm" else 0)
 
 
@@ -97,6 +108,11 @@ def test_room0_shape_steps_match_oracle(N, feat):
     R, I = 120, 3
     pcs, z, gt_depth, rgb8, labels, gt_feat = synth_batch(N, R * I, seed=N, feat=feat)
     fc, B = oc.init_params(N, generator=torch.Generator().manual_seed(100 + N))
+    # keep sigmoid(alpha) away from saturation: the reference forms the free probability as 1 - occ in fp32
+    # (render_rays.py:38), so with |alpha| ~ 15 one ulp of occ moves T, var and the depth weight by ~10 % and no two
+    # fp32 implementations (nor the reference on CPU vs CUDA) agree to 1e-4; see DESIGN.md "conditioning".
+    fc[8] *= 0.3
+    fc[9] *= 0.3
     ens = Ensemble(N, rays_per_step=R, iters_per_frame=I)
     ens.load_stacked(fc + [B])
     dev = "cuda:0"
@@ -106,9 +122,9 @@ def test_room0_shape_steps_match_oracle(N, feat):
     ens.prepare_frame(batch)
     g, terms = ens.grads(batch, 1)
     sl = slice(R, 2 * R)
-    rt, rg = oc.train_step_grads(fc, B, pcs[:, sl], z[:, sl], gt_depth[:, sl], rgb8[:, sl] / 255., labels[:, sl],
-                                 gt_feat[:, sl] if feat else None)
-    ref_t = torch.stack([rt.depth, rt.color, rt.opacity, rt.feat], 1)
+    rt, rg = grads64(fc, B, pcs[:, sl], z[:, sl], gt_depth[:, sl], rgb8[:, sl] / 255., labels[:, sl],
+                     gt_feat[:, sl] if feat else None)
+    ref_t = torch.stack([rt.depth, rt.color, rt.opacity, rt.feat], 1).float()
     torch.testing.assert_close(terms.cpu(), ref_t, rtol=1e-4, atol=1e-6)
     check_grads(g, rg)
     # three optimisation steps
@@ -124,7 +140,7 @@ def test_room0_shape_steps_match_oracle(N, feat):
         rt, rg = oc.train_step_grads(P[:18], P[18], pcs[:, sl], z[:, sl], gt_depth[:, sl], rgb8[:, sl] / 255.,
                                      labels[:, sl], gt_feat[:, sl] if feat else None)
         got = float(ens.total_loss(lt[it].cpu()))
-        assert abs(got - float(rt.total)) <= 1e-4 * abs(float(rt.total)) + 1e-6, (it, got, float(rt.total))
+        assert abs(got - float(rt.total.detach())) <= 1e-4 * abs(float(rt.total)) + 1e-6, (it, got, float(rt.total.detach()))
         for i, gr in enumerate(rg):
             if gr is None:
                 continue
