@@ -1,0 +1,329 @@
+#!/usr/bin/env python
+"""Benchmark of the accelerated OpenObj hot path (contract: see the task statement / DESIGN.md "Measurement").
+
+    python bench.py [--gpus N] [--steps K] [--warmup W] [--impl ours|reference] [--objects 60] [--part 1]
+
+A *step* is one optimisation iteration of the whole ensemble (N objects x 120 rays x 10 samples: encode, MLP,
+compositing, losses, backward, AdamW -- objnerf/train.py:394-474).  Every 100 steps a new synthetic RGB-D + mask
+(+ part-feature) frame of Replica shape (1200x680) is appended to the keyframe rings and all objects are re-sampled
+(train.py:164-388); that per-frame work is inside the timed region (sampling amortised per frame, as BASELINE.json's
+metric says).  Workload = BASELINE.json configs[1]: "Replica room_0 shape, ~60 objects, 1 B200"; with --gpus G each
+rank holds 60 objects (weak scaling, objects sharded by ensemble index, no gradient collectives).
+"""
+import argparse
+import json
+import os
+import subprocess
+import sys
+import threading
+import time
+
+ROOT = os.path.dirname(os.path.abspath(__file__))
+sys.path.insert(0, ROOT)
+
+ITERS = 100           # iters_per_frame (room_0.json:34)
+R = 120               # n_per_optim (room_0.json:35)
+S = 10
+MAC_PER_POINT = 63 + 2784 + 1024 + 3808 + 1024 + 32 + 2368 + 96      # PE, in, mid1, cat, mid2, alpha, color_linear, out_color
+MAC_CLIP_POINT = 2368                                                   # clip_linear (per point)
+MAC_CLIP_RAY = 16384                                                    # out_clip applied once per ray
+
+
+def flop_per_ray(part):
+    mac = S * (MAC_PER_POINT + (MAC_CLIP_POINT if part else 0)) + (MAC_CLIP_RAY if part else 0)
+    return 2 * 3 * mac        # FLOP = 2 MAC; forward + dX + dW
+
+
+class ClockSampler:
+    """nvidia-smi clocks / throttle reasons during the timed region (B200_PROFILING.md recipe)."""
+
+    def __init__(self, index=0):
+        self.index, self.rows, self.proc = index, [], None
+
+    def __enter__(self):
+        q = ("clocks.sm,clocks.max.sm,power.draw,clocks_event_reasons.hw_slowdown,clocks_event_reasons.hw_thermal_slowdown,"
+             "clocks_event_reasons.sw_thermal_slowdown,clocks_event_reasons.sw_power_cap")
+        try:
+            self.proc = subprocess.Popen(["nvidia-smi", "-i", str(self.index), "--query-gpu=" + q,
+                                          "--format=csv,noheader,nounits", "-lms", "100"], stdout=subprocess.PIPE, text=True)
+            self.thread = threading.Thread(target=self._read, daemon=True)
+            self.thread.start()
+        except OSError:
+            self.proc = None
+        return self
+
+    def _read(self):
+        for line in self.proc.stdout:
+            self.rows.append([x.strip() for x in line.split(",")])
+
+    def __exit__(self, *exc):
+        if self.proc:
+            time.sleep(0.15)
+            self.proc.terminate()
+            self.thread.join(timeout=2)
+
+    def summary(self):
+        sm = sorted(int(r[0]) for r in self.rows if r and r[0].isdigit())
+        if not sm:
+            return {"sm_mhz": None, "sm_max_mhz": None, "reasons": ["nvidia-smi unavailable"]}
+        reasons = []
+        for name, col in (("hw_slowdown", 3), ("hw_thermal_slowdown", 4), ("sw_thermal_slowdown", 5), ("sw_power_cap", 6)):
+            if any(len(r) > col and r[col].lower().startswith("active") for r in self.rows):
+                reasons.append(name)
+        busy = [v for v in sm if v >= 0.6 * sm[-1]] or sm
+        return {"sm_mhz": busy[len(busy) // 2], "sm_max_mhz": int(self.rows[0][1]), "reasons": reasons,
+                "samples": len(sm)}
+
+
+def cuda_timer():
+    import torch
+    return torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+
+
+# ------------------------------------------------------------------------------------------------------------
+# CPU arm: the oracle port (oracle/openobj_oracle.py == the reference's algorithm in torch-CPU) on the host cores
+# ------------------------------------------------------------------------------------------------------------
+def cpu_reference_run(n_obj, part, steps, warmup, time_budget_s):
+    import torch
+    sys.path.insert(0, os.path.join(ROOT, "oracle"))
+    import openobj_oracle as oc
+    cores = os.cpu_count() or 1
+    torch.set_num_threads(cores)
+    g = torch.Generator().manual_seed(0)
+    fc, B = oc.init_params(n_obj, generator=g)
+    P = [p.clone() for p in fc] + [B.clone()]
+    M = [torch.zeros_like(p) for p in P]
+    V = [torch.zeros_like(p) for p in P]
+    z = torch.sort(0.5 + 3.0 * torch.rand(n_obj, R, S, generator=g), dim=-1).values
+    o = torch.randn(n_obj, R, 1, 3, generator=g) * 0.2
+    d = torch.nn.functional.normalize(torch.randn(n_obj, R, 1, 3, generator=g), dim=-1)
+    pcs = o + d * z[..., None]
+    gt_depth = z[..., 6].clone()
+    rgb = torch.rand(n_obj, R, 3, generator=g)
+    labels = torch.randint(0, 3, (n_obj, R), generator=g, dtype=torch.uint8)
+    labels[:, 0], labels[:, 1] = 1, 0
+    gt_feat = torch.randn(n_obj, R, 512, generator=g) if part else None
+
+    def one_step(t):
+        terms, grads = oc.train_step_grads(P[:18], P[18], pcs, z, gt_depth, rgb, labels, gt_feat)
+        for i, gr in enumerate(grads):
+            if gr is not None:
+                oc.adamw_step(P[i], gr, M[i], V[i], t)
+        return float(terms.total)
+
+    for w in range(warmup):
+        one_step(w + 1)
+    t0 = time.perf_counter()
+    done = 0
+    for s in range(steps):
+        one_step(warmup + s + 1)
+        done += 1
+        if time.perf_counter() - t0 > time_budget_s:
+            break
+    dt = time.perf_counter() - t0
+    return dict(rays_per_s=n_obj * R * done / dt, steps_done=done, seconds=dt, cores=cores, ms_per_step=1e3 * dt / done)
+
+
+def run_reference_arm(args):
+    rank = int(os.environ.get("RANK", "0"))
+    if rank != 0:
+        return 0
+    n_obj = 8     # bounded sample: 8 of the 60 objects per step (objects are independent; rays/s per core is the same)
+    r = cpu_reference_run(n_obj, bool(args.part), args.steps, min(args.warmup, 3), time_budget_s=150.0)
+    line = {
+        "metric": "training rays/sec for N-object ensemble", "value": r["rays_per_s"], "unit": "rays/s", "n_gpus": args.gpus,
+        "steps": r["steps_done"], "warmup": min(args.warmup, 3), "ms_per_step": r["ms_per_step"], "higher_is_better": True,
+        "scaling": "weak", "vs_baseline": None, "dtype": "f32", "data": "synthetic", "impl": "reference",
+        "config": {"workload": "Replica room_0 shape, %d objects x 120 rays x 10 samples per step, part_mode=%d"
+                               % (args.objects, args.part)},
+        "cpu_baseline": {"value": r["rays_per_s"], "unit": "rays/s", "cores": r["cores"], "kind": "port",
+                         "sample": "oracle port (torch-CPU restatement of the reference step: vmap forward, step_batch_loss, "
+                                   "autograd backward, AdamW) on %d of the %d objects per step, %d steps (time-bounded)"
+                                   % (n_obj, args.objects, r["steps_done"])},
+        "e2e": {"value": r["rays_per_s"], "unit": "rays/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
+        "gpu_launches": 0,
+    }
+    print(json.dumps(line))
+    return 0
+
+
+# ------------------------------------------------------------------------------------------------------------
+# our arm
+# ------------------------------------------------------------------------------------------------------------
+def run_ours(args):
+    import torch
+    from openobj_b200 import _lib, cfg as C, dist as D, ops
+    from openobj_b200.ensemble import Ensemble
+    from openobj_b200.scene import Scene
+    from openobj_b200.synthetic import SyntheticScene
+
+    rank, world, local = D.init_from_env()
+    if not torch.cuda.is_available():
+        raise _lib.OOError("bench.py needs a CUDA device: the product path has no CPU fallback")
+    torch.cuda.set_device(local)
+    dev = torch.device("cuda", local)
+    cfg = C.room0_config()
+    cfg.training_device = cfg.data_device = str(dev)
+    cfg.part_mode = bool(args.part)
+    cfg.do_bg = False
+    n_local = args.objects
+    steps, warmup = args.steps, max(args.warmup, 3)
+    frames_w = (warmup + ITERS - 1) // ITERS
+    frames_t = (steps + ITERS - 1) // ITERS
+    fill = args.fill_frames
+    n_frames_total = fill + 2 * (frames_w + frames_t) + 2
+    # every rank sees the same frames; object ids are spread so that rank r owns ids with (index % world == r)
+    synth = SyntheticScene(n_local * world, W=cfg.W, H=cfg.H, part_mode=cfg.part_mode, seed=0, pin=True, n_distinct=2)
+    scene = Scene(cfg, rank=rank, world=world, seed=1234, max_frames=n_frames_total, flag_allreduce=D.make_flag_allreduce())
+
+    def iters_of(frame_idx, n_frames, total):
+        return min(ITERS, total - frame_idx * ITERS)
+
+    # ---- fill the keyframe rings (untimed), then move frame payloads to the device for the device-resident pass
+    f = 0
+    for _ in range(fill):
+        scene.add_frame(synth.frame(f)); f += 1
+    scene.sample()
+    scene.train(iters=3)
+    torch.cuda.synchronize()
+
+    def to_dev(s):
+        return {k: (v.to(dev) if torch.is_tensor(v) and k != "T" else v) for k, v in s.items()}
+
+    n_obj = len(scene.obj_dict)
+    lt = torch.zeros(ITERS, n_obj, 4, device=dev)
+    launches = {"n": 0}
+
+    def run_frames(n_frames, total_steps, host):
+        nonlocal f
+        for j in range(n_frames):
+            s = synth.frame(f)
+            if not host:
+                s = to_dev(s)
+            it = iters_of(j, n_frames, total_steps)
+            scene.add_frame(s)
+            scene.sample()
+            scene.train(iters=it, loss_terms=lt)
+            if host:
+                _ = lt[it - 1].sum().item()        # D2H read of the step result inside the timed region
+            f += 1
+            launches["n"] += 2 * it + 2 + 8         # K1+K4 per step, label counts + adam schedule, sampler + 7 tape fills
+
+    # ---- device-resident pass: `value`
+    run_frames(frames_w, warmup, host=False)
+    torch.cuda.synchronize(); D.barrier()
+    e0, e1 = cuda_timer()
+    launches["n"] = 0
+    with ClockSampler(local) as clk:
+        e0.record()
+        run_frames(frames_t, steps, host=False)
+        e1.record()
+        torch.cuda.synchronize()
+    D.barrier()
+    ms = D.max_over_ranks(e0.elapsed_time(e1), dev)
+    n_launch = launches["n"]
+    # ---- end-to-end pass: host (pinned) frame -> H2D -> append -> sample -> train -> D2H loss
+    run_frames(1, min(warmup, ITERS), host=True)
+    torch.cuda.synchronize(); D.barrier()
+    e0.record()
+    run_frames(frames_t, steps, host=True)
+    e1.record()
+    torch.cuda.synchronize(); D.barrier()
+    ms_e2e = D.max_over_ranks(e0.elapsed_time(e1), dev)
+    rays = n_obj * world * R * steps
+    h2d_per_step = synth.frame_bytes() / ITERS
+    d2h_per_step = 4.0 / ITERS
+
+    out = None
+    if rank == 0:
+        # ---- roofline of the dominant kernel (K1): CUDA events around every K1 launch of one more frame
+        ens = scene.ens
+        bc = scene.batch.to_c()
+        ens.prepare_frame(scene.batch)
+        evs = [cuda_timer() for _ in range(ITERS)]
+        for it in range(ITERS):
+            evs[it][0].record()
+            ens.k1(bc, it)
+            evs[it][1].record()
+            ens.k4(it)
+        torch.cuda.synchronize()
+        k1_ms = sorted(a.elapsed_time(b) for a, b in evs)
+        k1_avg = sum(k1_ms) / len(k1_ms)
+        peak = ops.fma_peak_tflops()
+        flop_launch = flop_per_ray(cfg.part_mode) * n_obj * R
+        achieved = flop_launch / (k1_avg * 1e-3) / 1e12
+        peaks = {}
+        try:
+            peaks = json.load(open(os.path.join(ROOT, "MEASURED_PEAKS.json")))
+        except OSError:
+            pass
+        traffic = None
+        try:
+            traffic = json.load(open(os.path.join(ROOT, "profiles", "k1_traffic.json"))).get("dram_bytes_per_launch")
+        except (OSError, ValueError):
+            pass
+        # K4 (AdamW) is the HBM-bound kernel of the step: p, m, v read+write and the gradient slabs read
+        evs4 = [cuda_timer() for _ in range(ITERS)]
+        for it in range(ITERS):
+            ens.k1(bc, it)
+            evs4[it][0].record()
+            ens.k4(it)
+            evs4[it][1].record()
+        torch.cuda.synchronize()
+        k4_avg = sum(a.elapsed_time(b) for a, b in evs4) / ITERS
+        k4_bytes = n_obj * 30659 * 24 + ens.n_slots * 30659 * 4 + (n_obj * 16384 * 4 if cfg.part_mode else 0)
+        hbm_peak = peaks.get("hbm_gbs", 6650.0)
+        cpu = cpu_reference_run(8, cfg.part_mode, steps=10 ** 6, warmup=1, time_budget_s=15.0) if not args.no_cpu else None
+        out = {
+            "metric": "training rays/sec for N-object ensemble", "value": rays / (ms * 1e-3), "unit": "rays/s",
+            "n_gpus": world, "steps": steps, "warmup": warmup, "ms_per_step": ms / steps, "higher_is_better": True,
+            "scaling": "weak", "vs_baseline": None, "dtype": "f32", "data": "synthetic",
+            "config": {"workload": "BASELINE configs[1]: Replica room_0 shape (1200x680), %d objects per GPU x 120 rays x 10 "
+                                   "samples per step, part_mode=%d, 100 steps per frame; per-frame append + sampling of all "
+                                   "objects inside the timed region" % (n_obj, int(cfg.part_mode)),
+                       "objects_per_gpu": n_obj, "rays_per_step_per_object": R, "iters_per_frame": ITERS,
+                       "l2": "inputs larger than L2: %.0f MB sampled batch per frame + part-feature table" %
+                             (n_obj * ITERS * R * 181 / 1e6),
+                       "parallelism": "objects sharded by ensemble index, rank = k mod %d; no gradient collectives" % world},
+            "e2e": {"value": rays / (ms_e2e * 1e-3), "unit": "rays/s", "h2d_bytes_per_step": h2d_per_step,
+                    "d2h_bytes_per_step": d2h_per_step, "ms_per_step": ms_e2e / steps},
+            "gpu_launches": n_launch,
+            "clocks": clk.summary(),
+            "roofline": {"kernel": "k_train (K1 fused encode+MLP+composite+loss+backward)", "bound": "fma",
+                         "achieved": achieved, "peak": peak, "unit": "TFLOP/s", "frac": achieved / peak, "traffic": traffic,
+                         "peak_source": "FP32 FFMA throughput measured live by oo_fma_peak on this GPU (MEASURED_PEAKS.json "
+                                        "holds only HBM and bf16 tensor peaks; K1 is an FP32 FMA-pipe kernel)",
+                         "k1_ms_avg": k1_avg, "k1_ms_min": k1_ms[0], "flop_per_launch": flop_launch,
+                         "bf16_tensor_peak_for_context": peaks.get("bf16_tflops")},
+            "roofline_hbm": {"kernel": "k_adamw (K4 slab reduction + AdamW)", "bound": "hbm",
+                             "achieved": k4_bytes / (k4_avg * 1e-3) / 1e9, "peak": hbm_peak, "unit": "GB/s",
+                             "frac": k4_bytes / (k4_avg * 1e-3) / 1e9 / hbm_peak, "k4_ms_avg": k4_avg, "bytes_per_launch": k4_bytes,
+                             "peak_source": "MEASURED_PEAKS.json hbm_gbs" if "hbm_gbs" in peaks else "fallback 6.65 TB/s"},
+        }
+        if cpu is not None:
+            out["cpu_baseline"] = {"value": cpu["rays_per_s"], "unit": "rays/s", "cores": cpu["cores"], "kind": "port",
+                                   "sample": "oracle port (torch-CPU restatement of the reference step) on 8 of the %d objects, "
+                                             "%d steps in %.1f s" % (n_obj, cpu["steps_done"], cpu["seconds"])}
+        print(json.dumps(out))
+    D.barrier()
+    return 0
+
+
+def main():
+    ap = argparse.ArgumentParser()
+    ap.add_argument("--gpus", type=int, default=1)
+    ap.add_argument("--steps", type=int, default=1000)
+    ap.add_argument("--warmup", type=int, default=200)
+    ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
+    ap.add_argument("--objects", type=int, default=60, help="objects per GPU")
+    ap.add_argument("--part", type=int, default=1, help="part-level feature head on (room_0.json part_mode)")
+    ap.add_argument("--fill-frames", type=int, default=20, help="untimed frames that fill the keyframe rings (SURVEY 8d)")
+    ap.add_argument("--no-cpu", action="store_true", help="skip the CPU baseline leg")
+    args = ap.parse_args()
+    if args.impl == "reference":
+        return run_reference_arm(args)
+    return run_ours(args)
+
+
+if __name__ == "__main__":
+    sys.exit(main())

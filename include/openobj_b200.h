@@ -137,6 +137,14 @@ int oo_train_frame(float* theta, float* adam_m, float* adam_v, int n_obj, const 
                    int rays_per_step, float scale, float lr, float weight_decay, float beta1, float beta2, float eps,
                    oo_train_ws* ws, float* loss_terms, int n_sm, void* stream);
 
+/* the two halves of oo_train_step, separately launchable (bench.py brackets K1 with CUDA events for the roofline;
+ * ncu captures use them too): K1 = fused encode/MLP/composite/loss/backward into ws->slab, K4 = slab reduction + AdamW. */
+int oo_train_k1(const float* theta, int n_obj, const oo_batch* batch, int it, int rays_per_step, float scale,
+                oo_train_ws* ws, int n_sm, void* stream);
+int oo_train_k4(float* theta, float* adam_m, float* adam_v, int n_obj, int it, int rays_per_step,
+                float lr, float weight_decay, float beta1, float beta2, float eps,
+                oo_train_ws* ws, float* loss_terms, int n_sm, void* stream);
+
 /* a11 standalone: torch.optim.AdamW over a flat float buffer. step is 1-based. */
 int oo_adamw_flat(float* p, const float* g, float* m, float* v, int64_t n, int step,
                   float lr, float weight_decay, float beta1, float beta2, float eps, void* stream);

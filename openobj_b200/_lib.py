@@ -72,6 +72,9 @@ _SIGS = {
                         c_int, c_void_p], c_int),
     "oo_train_frame": ([c_void_p, c_void_p, c_void_p, c_int, POINTER(Batch), c_int, c_int, c_float, c_float, c_float,
                         c_float, c_float, c_float, POINTER(TrainWs), c_void_p, c_int, c_void_p], c_int),
+    "oo_train_k1": ([c_void_p, c_int, POINTER(Batch), c_int, c_int, c_float, POINTER(TrainWs), c_int, c_void_p], c_int),
+    "oo_train_k4": ([c_void_p, c_void_p, c_void_p, c_int, c_int, c_int, c_float, c_float, c_float, c_float, c_float,
+                     POINTER(TrainWs), c_void_p, c_int, c_void_p], c_int),
     "oo_adamw_flat": ([c_void_p, c_void_p, c_void_p, c_void_p, c_int64, c_int, c_float, c_float, c_float, c_float,
                        c_float, c_void_p], c_int),
     "oo_sample_rays": ([POINTER(SampleArgs), c_void_p], c_int),

@@ -332,14 +332,8 @@ extern "C" int oo_adam_schedule(const int* flags, int iters, int part_on, float 
     return 0;
 }
 
-static int train_step_impl(float* theta, float* am, float* av, int n_obj, const oo_batch* b, int it, int R, float scale,
-                           float lr, float wd, float b1, float b2, float eps, oo_train_ws* ws, float* loss_terms,
-                           float* grads_out, int n_sm, cudaStream_t st) {
-    if (int rc = check_train_args(n_obj, b, R, ws)) return rc;
-    OO_REQUIRE((long long)(it + 1) * R <= b->rays_per_obj, "oo_train: step %d exceeds the pre-sampled batch", it);
-    if (int rc = launch_k1(theta, n_obj, b, it, R, scale, ws, n_sm, st)) return rc;
-    const Schedule s0;   // layout helper only
-    (void)s0;
+static int launch_k4(float* theta, float* am, float* av, int n_obj, int it, int R, float lr, float wd, float b1, float b2,
+                     float eps, oo_train_ws* ws, float* loss_terms, float* grads_out, int n_sm, cudaStream_t st) {
     const long long T = (long long)n_obj * tiles_per_object(R);
     const int n_cta = (int)(T < n_sm ? T : n_sm);
     const int* obj_slot = ws->sched + 2 * n_cta + 1;
@@ -356,6 +350,31 @@ static int train_step_impl(float* theta, float* am, float* av, int n_obj, const 
     }
     OO_LAUNCH_CHECK();
     return 0;
+}
+
+static int train_step_impl(float* theta, float* am, float* av, int n_obj, const oo_batch* b, int it, int R, float scale,
+                           float lr, float wd, float b1, float b2, float eps, oo_train_ws* ws, float* loss_terms,
+                           float* grads_out, int n_sm, cudaStream_t st) {
+    if (int rc = check_train_args(n_obj, b, R, ws)) return rc;
+    OO_REQUIRE((long long)(it + 1) * R <= b->rays_per_obj, "oo_train: step %d exceeds the pre-sampled batch", it);
+    if (int rc = launch_k1(theta, n_obj, b, it, R, scale, ws, n_sm, st)) return rc;
+    return launch_k4(theta, am, av, n_obj, it, R, lr, wd, b1, b2, eps, ws, loss_terms, grads_out, n_sm, st);
+}
+
+extern "C" int oo_train_k1(const float* theta, int n_obj, const oo_batch* batch, int it, int rays_per_step, float scale,
+                           oo_train_ws* ws, int n_sm, void* stream) {
+    OO_REQUIRE(theta, "oo_train_k1: null theta");
+    if (int rc = check_train_args(n_obj, batch, rays_per_step, ws)) return rc;
+    OO_REQUIRE((long long)(it + 1) * rays_per_step <= batch->rays_per_obj, "oo_train_k1: step %d exceeds the batch", it);
+    return launch_k1(theta, n_obj, batch, it, rays_per_step, scale, ws, n_sm, (cudaStream_t)stream);
+}
+
+extern "C" int oo_train_k4(float* theta, float* adam_m, float* adam_v, int n_obj, int it, int rays_per_step, float lr,
+                           float weight_decay, float beta1, float beta2, float eps, oo_train_ws* ws, float* loss_terms,
+                           int n_sm, void* stream) {
+    OO_REQUIRE(theta && adam_m && adam_v && ws && ws->slab, "oo_train_k4: null argument");
+    return launch_k4(theta, adam_m, adam_v, n_obj, it, rays_per_step, lr, weight_decay, beta1, beta2, eps, ws, loss_terms,
+                     nullptr, n_sm, (cudaStream_t)stream);
 }
 
 extern "C" int oo_train_step(float* theta, float* adam_m, float* adam_v, int n_obj, const oo_batch* batch, int it,

@@ -157,6 +157,17 @@ class Ensemble:
                                         self.R, self.scale, self.lr, self.wd, self.betas[0], self.betas[1], self.eps,
                                         ctypes.byref(self.ws), ptr(loss_terms), self.n_sm, stream()), "oo_train_frame")
 
+    def k1(self, batch_c, it):
+        """K1 alone (fused encode/MLP/composite/loss/backward into the slabs)."""
+        check(self.L.oo_train_k1(ptr(self.theta), self.n_obj, ctypes.byref(batch_c), it, self.R, self.scale,
+                                 ctypes.byref(self.ws), self.n_sm, stream()), "oo_train_k1")
+
+    def k4(self, it, loss_terms=None):
+        """K4 alone (slab reduction + AdamW)."""
+        check(self.L.oo_train_k4(ptr(self.theta), ptr(self.m), ptr(self.v), self.n_obj, it, self.R, self.lr, self.wd,
+                                 self.betas[0], self.betas[1], self.eps, ctypes.byref(self.ws), ptr(loss_terms), self.n_sm,
+                                 stream()), "oo_train_k4")
+
     @staticmethod
     def total_loss(terms, color_scaling=5.0, opacity_scaling=10.0, feat_scaling=5.0):
         """loss.py:79,99,101: sum over objects of d + 5 c + 10 o + 5 f."""

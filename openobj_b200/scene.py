@@ -1,0 +1,117 @@
+"""Per-frame driver of the accelerated path: the body of objnerf/train.py:158-485 for the vmap strategy, with the
+Python object loop replaced by three batched launches per frame (append is still per object in round 1):
+
+    add_frame   (train.py:164-256)  H2D, per-object pixel state, keyframe rings, new objects -> ensemble rebuild
+    sample      (train.py:300-388)  K2 for all local objects in one launch, no [N,12000,512] feature copy
+    train       (train.py:394-474)  100 x (K1 + K4)
+    write-back  (train.py:478-485)  not needed: every object's nn.Parameters are views of the ensemble buffer
+
+Objects are sharded by ensemble index k (order of first appearance): rank = k % world; ranks share
+nothing but the per-step zero-mask flags, OR-reduced once per frame."""
+import torch
+
+from . import layout, sampler, vmap
+from .ensemble import Ensemble, FrameBatch
+
+
+class Scene:
+    def __init__(self, cfg, rank=0, world=1, seed=0, max_frames=64, n_sm=None, flag_allreduce=None):
+        self.cfg, self.rank, self.world, self.seed = cfg, rank, world, seed
+        self.device = torch.device(cfg.training_device)
+        self.cam = vmap.cameraInfo(cfg)
+        self.obj_dict = {}            # local objects, insertion order == local ensemble index
+        self.global_index = {}        # obj id -> global ensemble index k (all ranks agree)
+        self.ens = None
+        self.n_sm = n_sm
+        self.flag_allreduce = flag_allreduce
+        self.frames_seen = 0
+        self.part_mode = cfg.part_mode
+        self.part_table = None
+        if self.part_mode:
+            self.pw, self.ph = cfg.W // cfg.part_down, cfg.H // cfg.part_down
+            self.part_table = torch.empty(max_frames, self.pw, self.ph, cfg.clip_point_feature_size,
+                                          dtype=torch.float32, device=self.device)
+        self._stale = False
+        self.batch = None
+
+    # ---- train.py:164-256 ---------------------------------------------------------------------------------
+    def add_frame(self, sample):
+        cfg, dev = self.cfg, self.device
+        nb = dict(non_blocking=True)
+        rgb, depth = sample["image"].to(dev, **nb), sample["depth"].to(dev, **nb)
+        inst = sample["obj"].to(dev, **nb)
+        twc = sample["T"].to(dev, **nb)
+        frame_id = sample.get("frame_id", self.frames_seen)
+        if self.part_mode:
+            if self.frames_seen >= self.part_table.shape[0]:
+                raise RuntimeError("part-feature table full: raise max_frames")
+            self.part_table[self.frames_seen].copy_(sample["part_feat"], non_blocking=True)   # train.py:183-188
+        unknown = (inst == -1).to(torch.uint8) * 2
+        for obj_id in sorted(int(k) for k in sample["bbox_dict"].keys()):                 # torch.unique order (train.py:191)
+            if obj_id == -1 or (cfg.do_bg and obj_id == 0):
+                continue               # the separate background model is not part of the vmap ensemble (train.py:236-242)
+            if obj_id not in self.global_index:
+                if len(self.global_index) >= cfg.max_n_models * self.world:
+                    continue           # "models full" (train.py:231-233)
+                self.global_index[obj_id] = len(self.global_index)
+            if self.global_index[obj_id] % self.world != self.rank:
+                continue
+            state = (inst == obj_id).to(torch.uint8) + unknown                             # train.py:203-205
+            bbox = sample["bbox_dict"][obj_id]
+            if obj_id in self.obj_dict:
+                self.obj_dict[obj_id].append_keyframe(rgb, depth, state, bbox, twc, frame_id)
+            else:
+                c = cfg
+                self.obj_dict[obj_id] = vmap.sceneObject(c, obj_id, rgb, depth, state, bbox, twc, frame_id)
+                self._stale = True
+        self.frames_seen += 1
+        if self._stale:
+            self._rebuild_ensemble()
+
+    # ---- utils.update_vmap (train.py:272-276): restack, Adam state restarts ---------------------------------
+    def _rebuild_ensemble(self):
+        objs = list(self.obj_dict.values())
+        new = Ensemble(len(objs), device=self.device, rays_per_step=self.cfg.n_per_optim,
+                       iters_per_frame=self.cfg.n_iter_per_frame, lr=self.cfg.learning_rate,
+                       weight_decay=self.cfg.weight_decay, scale=self.cfg.obj_scale, n_sm=self.n_sm)
+        views = new.stacked()
+        with torch.no_grad():
+            for k, o in enumerate(objs):
+                ps = list(o.trainer.fc_occ_map.parameters()) + [o.trainer.pe.B_layer.weight]
+                for v, p in zip(views, ps):
+                    v[k].copy_(p.detach())
+                    p.data = v[k]      # the module now aliases the ensemble buffer: write-back (train.py:478-485) is free
+        new.params_changed()
+        new.reset_optimizer()
+        self.ens = new
+        self._stale = False
+
+    # ---- train.py:300-388 -----------------------------------------------------------------------------------
+    def sample(self):
+        cfg = self.cfg
+        objs = list(self.obj_dict.values())
+        n_frames = cfg.n_iter_per_frame * cfg.win_size
+        n_samples = cfg.n_samples_per_frame
+        o0 = objs[0]
+        tapes = sampler.device_tapes(objs, n_frames, n_samples, o0.n_bins_cam2surface, o0.n_bins, o0.surface_eps,
+                                     self.seed, self.frames_seen, self.device)
+        part_frame = None
+        if self.part_mode:
+            part_frame = torch.stack([o.part_frame_row() for o in objs]).to(self.device).contiguous()
+        out = sampler.sample([o.rgbs_batch for o in objs], [o.depth_batch for o in objs], [o.t_wc_batch for o in objs],
+                             [o.bbox for o in objs], part_frame, self.cam.rays_dir_cache, tapes, n_frames, n_samples,
+                             o0.n_bins_cam2surface, o0.n_bins, o0.surface_eps, o0.stop_eps, o0.min_bound,
+                             cfg.part_down if self.part_mode else 0, (self.pw, self.ph) if self.part_mode else (0, 0))
+        table = self.part_table.view(-1, self.part_table.shape[-1]) if self.part_mode else None
+        self.batch = FrameBatch(out.pcs, out.z, out.gt_depth, out.gt_rgb, out.labels, out.feat_row, table)
+        self.sample_out = out
+        return self.batch
+
+    # ---- train.py:394-474 -----------------------------------------------------------------------------------
+    def train(self, iters=None, loss_terms=None):
+        self.ens.train_frame(self.batch, iters=iters, loss_terms=loss_terms, flag_allreduce=self.flag_allreduce)
+
+    def step_frame(self, sample, iters=None, loss_terms=None):
+        self.add_frame(sample)
+        self.sample()
+        self.train(iters, loss_terms)
