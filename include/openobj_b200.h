@@ -176,12 +176,40 @@ typedef struct oo_sample_args {
     /* torch.linspace(0,1,n+1) tables used by utils.stratified_bins (utils.py:349) for n = S, n_c2s, n_bins.
      * HOST pointers: ATen's vectorised linspace is not a closed formula, so the caller supplies what torch gives. */
     const float* lin_s_host; const float* lin_c2s_host; const float* lin_bins_host;
+    /* rng_mode 1: no tapes; every draw comes from the counter RNG of oo_rng_fill evaluated in-kernel, stream
+     * 8*frame + {0 keyframe, 1 u_w, 2 u_h, 3 r_invalid, 4 r_valid, 5 r_normal (std eps/3), 6 r_other}, element = the
+     * tape index (so the result equals tape mode with tapes produced by oo_rng_fill, row = ray index).
+     * keyframe id f: min(int(u * n_keyframes), n_keyframes-1), the last two forced to `latest` when n_keyframes > 2. */
+    int rng_mode; uint64_t seed; uint32_t frame;
+    const int32_t* obj_ids;              /* [n_obj] RNG key per object (its instance id: shard independent) */
+    const int32_t* n_keyframes;          /* [n_obj] */
+    const int32_t* latest;               /* [n_obj][2] lastest_kf_queue[-2:] (vmap.py:398) */
     /* outputs, all [n_obj][n_rays...] */
     uint8_t* gt_rgb; float* gt_depth; uint8_t* valid; uint8_t* labels;
     float* pcs; float* z; int32_t* feat_row; int64_t* pix;   /* pix [n_obj][n_rays][3] = kf, w, h */
     int* oob_count;                      /* [1] rays whose pixel index had to be clamped (quirk 11) */
 } oo_sample_args;
 int oo_sample_rays(const oo_sample_args* a, void* stream);
+/* ---- a12: write one new frame into the keyframe rings of every visible object in ONE launch
+ *      (sceneObject.__init__ / append_keyframe slot writes, vmap.py:125-147,186-240; pixel state from the instance
+ *      map as train.py:203-205: 1 where inst == id, 2 where inst == -1, else 0).  Slot choice (keyframe policy) stays
+ *      on the host.  Tables are device arrays of length n_obj. */
+typedef struct oo_append_args {
+    int W, H, n_obj;
+    const uint8_t* rgb;                  /* [W][H][3] */
+    const float*   depth;                /* [W][H] */
+    const int32_t* inst;                 /* [W][H] */
+    const float*   t_wc;                 /* [16] float32 camera-to-world of this frame */
+    const int32_t* obj_id;               /* instance id of each object to append */
+    const int32_t* slot;                 /* ring slot each object writes */
+    const float*   bbox;                 /* [n_obj][4] = w_lo,w_hi,h_lo,h_hi */
+    uint8_t* const* rgbs;                /* -> u8 [KF][W][H][4] */
+    float* const*   depth_ring;          /* -> f32 [KF][W][H] */
+    float* const*   t_wc_ring;           /* -> f32 [KF][4][4] */
+    float* const*   bbox_ring;           /* -> f32 [KF][4] */
+} oo_append_args;
+int oo_append_frame(const oo_append_args* a, void* stream);
+
 /* counter-based uniform / normal tapes keyed by (seed, frame, object id, element) -- shard independent. */
 int oo_rng_fill(uint64_t seed, uint32_t frame, const int32_t* obj_ids, int n_obj, int64_t per_obj,
                 int kind /*0 uniform [0,1), 1 normal(0,std)*/, float std, float* out, void* stream);

@@ -38,9 +38,17 @@ class SampleArgs(Structure):
                 ("r_invalid", c_void_p), ("r_valid", c_void_p), ("r_normal", c_void_p), ("r_other", c_void_p),
                 ("tape_by_rank", c_int),
                 ("lin_s_host", c_void_p), ("lin_c2s_host", c_void_p), ("lin_bins_host", c_void_p),
+                ("rng_mode", c_int), ("seed", c_uint64), ("frame", c_uint32),
+                ("obj_ids", c_void_p), ("n_keyframes", c_void_p), ("latest", c_void_p),
                 ("gt_rgb", c_void_p), ("gt_depth", c_void_p), ("valid", c_void_p), ("labels", c_void_p),
                 ("pcs", c_void_p), ("z", c_void_p), ("feat_row", c_void_p), ("pix", c_void_p),
                 ("oob_count", c_void_p)]
+
+
+class AppendArgs(Structure):
+    _fields_ = [("W", c_int), ("H", c_int), ("n_obj", c_int), ("rgb", c_void_p), ("depth", c_void_p), ("inst", c_void_p),
+                ("t_wc", c_void_p), ("obj_id", c_void_p), ("slot", c_void_p), ("bbox", c_void_p), ("rgbs", c_void_p),
+                ("depth_ring", c_void_p), ("t_wc_ring", c_void_p), ("bbox_ring", c_void_p)]
 
 
 class RenderArgs(Structure):
@@ -78,6 +86,7 @@ _SIGS = {
     "oo_adamw_flat": ([c_void_p, c_void_p, c_void_p, c_void_p, c_int64, c_int, c_float, c_float, c_float, c_float,
                        c_float, c_void_p], c_int),
     "oo_sample_rays": ([POINTER(SampleArgs), c_void_p], c_int),
+    "oo_append_frame": ([POINTER(AppendArgs), c_void_p], c_int),
     "oo_rng_fill": ([c_uint64, c_uint32, c_void_p, c_int, c_int64, c_int, c_float, c_void_p, c_void_p], c_int),
     "oo_render_object": ([POINTER(RenderArgs), c_void_p], c_int),
     "oo_zmerge": ([c_void_p, c_void_p, c_void_p, c_void_p, c_int, c_int64, c_void_p, c_void_p, c_void_p, c_void_p],

@@ -28,21 +28,70 @@ __device__ __forceinline__ void sort_small(float* v, int n) {   // insertion sor
     }
 }
 
+// ---- Philox4x32-10 counter RNG: value i of object id `oid` in frame `frame` depends only on (seed, frame, oid, i)
+__device__ __forceinline__ uint4 philox4x32_10(uint4 ctr, uint2 key) {
+#pragma unroll
+    for (int r = 0; r < 10; ++r) {
+        const uint32_t hi0 = __umulhi(0xD2511F53u, ctr.x), lo0 = 0xD2511F53u * ctr.x;
+        const uint32_t hi1 = __umulhi(0xCD9E8D57u, ctr.z), lo1 = 0xCD9E8D57u * ctr.z;
+        ctr = make_uint4(hi1 ^ ctr.y ^ key.x, lo1, hi0 ^ ctr.w ^ key.y, lo0);
+        key.x += 0x9E3779B9u;
+        key.y += 0xBB67AE85u;
+    }
+    return ctr;
+}
+
+
+constexpr float TWO_M24 = 5.9604644775390625e-8f;
+struct Rng {
+    uint2 key;
+    uint32_t oid, frame;
+    __device__ __forceinline__ uint32_t word(uint32_t stream, uint64_t e) const {
+        const uint64_t q = e >> 2;
+        const uint4 r = philox4x32_10(make_uint4((uint32_t)q, (uint32_t)(q >> 32), oid, 8u * frame + stream), key);
+        const uint32_t i = (uint32_t)(e & 3);
+        return i == 0 ? r.x : i == 1 ? r.y : i == 2 ? r.z : r.w;
+    }
+    __device__ __forceinline__ float uniform(uint32_t stream, uint64_t e) const { return (float)(word(stream, e) >> 8) * TWO_M24; }
+    __device__ __forceinline__ float normal(uint32_t stream, uint64_t e, float std) const {   // same pairing as k_rng_fill
+        const uint64_t q = e >> 2;
+        const uint4 r = philox4x32_10(make_uint4((uint32_t)q, (uint32_t)(q >> 32), oid, 8u * frame + stream), key);
+        const uint32_t i = (uint32_t)(e & 3);
+        const uint32_t a = i < 2 ? r.x : r.z, b = i < 2 ? r.y : r.w;
+        const float u0 = ((float)(a >> 8) + 1.f) * TWO_M24, u1 = (float)(b >> 8) * TWO_M24;
+        const float rad = sqrtf(-2.f * logf(u0)) * std;
+        float sn, cs;
+        sincospif(2.f * u1, &sn, &cs);
+        return (i & 1) ? rad * sn : rad * cs;
+    }
+};
+
 struct RayPix {
     int kf, iw, ih;
     float iwf, ihf;
     bool oob;
 };
 
-__device__ __forceinline__ RayPix ray_pixel(const oo_sample_args& a, int obj, int ray) {
+__device__ __forceinline__ RayPix ray_pixel(const oo_sample_args& a, const Rng& g, int obj, int ray) {
     RayPix r;
     const int f = ray / a.n_samples;
-    r.kf = (int)a.kf_ids[(size_t)obj * a.n_frames + f];
+    float uw, uh;
+    if (a.rng_mode) {
+        const int nk = a.n_keyframes[obj];
+        if (nk > 2 && f >= a.n_frames - 2) r.kf = a.latest[2 * obj + (f - (a.n_frames - 2))];       // vmap.py:398-400
+        else r.kf = min((int)(g.uniform(0, (uint64_t)f) * (float)nk), nk - 1);
+        uw = g.uniform(1, (uint64_t)ray);
+        uh = g.uniform(2, (uint64_t)ray);
+    } else {
+        r.kf = (int)a.kf_ids[(size_t)obj * a.n_frames + f];
+        const size_t ui = (size_t)obj * a.n_frames * a.n_samples + ray;
+        uw = a.u_w[ui];
+        uh = a.u_h[ui];
+    }
     const float* bb = a.bbox[obj] + 4 * r.kf;
-    const size_t ui = (size_t)obj * a.n_frames * a.n_samples + ray;
     // separate fp32 mul and add, then truncation -- vmap.py:418-422
-    r.iwf = __fadd_rn(__fmul_rn(a.u_w[ui], __fsub_rn(bb[1], bb[0])), bb[0]);
-    r.ihf = __fadd_rn(__fmul_rn(a.u_h[ui], __fsub_rn(bb[3], bb[2])), bb[2]);
+    r.iwf = __fadd_rn(__fmul_rn(uw, __fsub_rn(bb[1], bb[0])), bb[0]);
+    r.ihf = __fadd_rn(__fmul_rn(uh, __fsub_rn(bb[3], bb[2])), bb[2]);
     int iw = (int)r.iwf, ih = (int)r.ihf;
     r.oob = iw < 0 || iw >= a.W || ih < 0 || ih >= a.H;   // quirk 11: the reference would raise an index error
     r.iw = min(max(iw, 0), a.W - 1);
@@ -63,12 +112,17 @@ __global__ void __launch_bounds__(NTH, 1) k_sample(const SampleK k) {
     __shared__ float sh_max[32];
     __shared__ int sh_oob;
     if (tid == 0) sh_oob = 0;
+    Rng g;
+    g.key = make_uint2((uint32_t)a.seed, (uint32_t)(a.seed >> 32));
+    g.oid = a.rng_mode ? (uint32_t)a.obj_ids[obj] : 0u;
+    g.frame = a.frame;
+    const bool rng = a.rng_mode != 0;
 
     // ---- pass A: gather + classify -------------------------------------------------------------------
     int n_inv = 0, n_obj = 0, n_oth = 0, oob = 0;
     float dmax = -INFINITY;
     for (int ray = r_begin; ray < r_end; ++ray) {
-        const RayPix p = ray_pixel(a, obj, ray);
+        const RayPix p = ray_pixel(a, g, obj, ray);
         oob += p.oob;
         const size_t pix = ((size_t)p.kf * a.W + p.iw) * a.H + p.ih;
         const uchar4 c = *reinterpret_cast<const uchar4*>(rgbs + pix * 4);        // vmap.py:424
@@ -131,7 +185,7 @@ __global__ void __launch_bounds__(NTH, 1) k_sample(const SampleK k) {
     // ---- pass B: sample placement ----------------------------------------------------------------------
     const float eps = a.eps;
     for (int ray = r_begin; ray < r_end; ++ray) {
-        const RayPix p = ray_pixel(a, obj, ray);
+        const RayPix p = ray_pixel(a, g, obj, ray);
         const size_t o = (size_t)obj * n_rays + ray;
         const float d = a.gt_depth[o];
         const int state = a.labels[o];
@@ -143,7 +197,7 @@ __global__ void __launch_bounds__(NTH, 1) k_sample(const SampleK k) {
             const float range = __fsub_rn(max_bound, a.min_bound);
             const float blen = __fdiv_rn(range, (float)S);
             for (int i = 0; i < S; ++i)
-                zs[i] = __fadd_rn(__fadd_rn(__fmul_rn(range, k.lin_s[i]), a.min_bound), __fmul_rn(a.r_invalid[row + i], blen));
+                zs[i] = __fadd_rn(__fadd_rn(__fmul_rn(range, k.lin_s[i]), a.min_bound), __fmul_rn(rng ? g.uniform(3, (uint64_t)ray * S + i) : a.r_invalid[row + i], blen));
             ++rk_inv;
         } else {
             const int rk_val = a.tape_by_rank ? (ray - rk_inv) : ray;              // rank among valid rays
@@ -152,13 +206,14 @@ __global__ void __launch_bounds__(NTH, 1) k_sample(const SampleK k) {
                 const float range = __fsub_rn(__fsub_rn(d, eps), a.min_bound);
                 const float blen = __fdiv_rn(range, (float)a.n_c2s);
                 for (int i = 0; i < a.n_c2s; ++i)
-                    zs[i] = __fadd_rn(__fadd_rn(__fmul_rn(range, k.lin_c[i]), a.min_bound), __fmul_rn(a.r_valid[row + i], blen));
+                    zs[i] = __fadd_rn(__fadd_rn(__fmul_rn(range, k.lin_c[i]), a.min_bound), __fmul_rn(rng ? g.uniform(4, (uint64_t)ray * a.n_c2s + i) : a.r_valid[row + i], blen));
             }
             if (state == 1) {
                 // normal_bins_sampling: N(0, eps/3) draws sorted ascending, clipped to +-eps, + d -- utils.py:382-397
                 const size_t row = ((size_t)obj * n_rays + (a.tape_by_rank ? rk_obj : ray)) * a.n_bins;
                 float b[MAXB];
-                for (int i = 0; i < a.n_bins; ++i) b[i] = a.r_normal[row + i];
+                for (int i = 0; i < a.n_bins; ++i)
+                    b[i] = rng ? g.normal(5, (uint64_t)ray * a.n_bins + i, __fdiv_rn(eps, 3.f)) : a.r_normal[row + i];
                 sort_small(b, a.n_bins);
                 for (int i = 0; i < a.n_bins; ++i) zs[a.n_c2s + i] = __fadd_rn(d, fminf(fmaxf(b[i], -eps), eps));
                 ++rk_obj;
@@ -169,7 +224,7 @@ __global__ void __launch_bounds__(NTH, 1) k_sample(const SampleK k) {
                 const float range = __fsub_rn(hi, lo);
                 const float blen = __fdiv_rn(range, (float)a.n_bins);
                 for (int i = 0; i < a.n_bins; ++i)
-                    zs[a.n_c2s + i] = __fadd_rn(__fadd_rn(__fmul_rn(range, k.lin_b[i]), lo), __fmul_rn(a.r_other[row + i], blen));
+                    zs[a.n_c2s + i] = __fadd_rn(__fadd_rn(__fmul_rn(range, k.lin_b[i]), lo), __fmul_rn(rng ? g.uniform(6, (uint64_t)ray * a.n_bins + i) : a.r_other[row + i], blen));
                 ++rk_oth;
             }
         }
@@ -190,19 +245,6 @@ __global__ void __launch_bounds__(NTH, 1) k_sample(const SampleK k) {
             po[3 * i + 2] = __fadd_rn(oz, __fmul_rn(wz, zs[i]));
         }
     }
-}
-
-// ---- Philox4x32-10 counter RNG: value i of object id `oid` in frame `frame` depends only on (seed, frame, oid, i)
-__device__ __forceinline__ uint4 philox4x32_10(uint4 ctr, uint2 key) {
-#pragma unroll
-    for (int r = 0; r < 10; ++r) {
-        const uint32_t hi0 = __umulhi(0xD2511F53u, ctr.x), lo0 = 0xD2511F53u * ctr.x;
-        const uint32_t hi1 = __umulhi(0xCD9E8D57u, ctr.z), lo1 = 0xCD9E8D57u * ctr.z;
-        ctr = make_uint4(hi1 ^ ctr.y ^ key.x, lo1, hi0 ^ ctr.w ^ key.y, lo0);
-        key.x += 0x9E3779B9u;
-        key.y += 0xBB67AE85u;
-    }
-    return ctr;
 }
 
 __global__ void k_rng_fill(uint64_t seed, uint32_t frame, const int32_t* __restrict__ obj_ids, int64_t per_obj, int kind,
@@ -233,16 +275,72 @@ __global__ void k_rng_fill(uint64_t seed, uint32_t frame, const int32_t* __restr
     }
 }
 
+// ---- keyframe ring append for all visible objects: one thread per pixel, loop over objects -----------------
+constexpr int APPEND_MAX = 256;
+__global__ void __launch_bounds__(256) k_append(const oo_append_args a) {
+    __shared__ int s_id[APPEND_MAX];
+    __shared__ uint8_t* s_rgbs[APPEND_MAX];
+    __shared__ float* s_depth[APPEND_MAX];
+    const int n_pix = a.W * a.H;
+    for (int o0 = 0; o0 < a.n_obj; o0 += APPEND_MAX) {
+        const int n = min(APPEND_MAX, a.n_obj - o0);
+        __syncthreads();
+        for (int i = threadIdx.x; i < n; i += blockDim.x) {
+            const size_t off = (size_t)a.slot[o0 + i] * n_pix;
+            s_id[i] = a.obj_id[o0 + i];
+            s_rgbs[i] = a.rgbs[o0 + i] + off * 4;
+            s_depth[i] = a.depth_ring[o0 + i] + off;
+        }
+        __syncthreads();
+        for (int pix = blockIdx.x * blockDim.x + threadIdx.x; pix < n_pix; pix += gridDim.x * blockDim.x) {
+            const uint8_t r = a.rgb[3 * (size_t)pix], g = a.rgb[3 * (size_t)pix + 1], b = a.rgb[3 * (size_t)pix + 2];
+            const float d = a.depth[pix];
+            const int id = a.inst[pix];
+            const uint8_t unk = id == -1 ? 2 : 0;
+            for (int i = 0; i < n; ++i) {
+                const uchar4 v = make_uchar4(r, g, b, id == s_id[i] ? 1 : unk);          // train.py:203-205
+                reinterpret_cast<uchar4*>(s_rgbs[i])[pix] = v;
+                s_depth[i][pix] = d;
+            }
+        }
+    }
+    if (blockIdx.x == 0) {
+        for (int i = threadIdx.x; i < a.n_obj * 20; i += blockDim.x) {
+            const int o = i / 20, q = i - 20 * o;
+            if (q < 16) a.t_wc_ring[o][16 * a.slot[o] + q] = a.t_wc[q];
+            else a.bbox_ring[o][4 * a.slot[o] + q - 16] = a.bbox[4 * o + q - 16];
+        }
+    }
+}
+
 }  // namespace
+
+extern "C" int oo_append_frame(const oo_append_args* a, void* stream) {
+    OO_REQUIRE(a && a->rgb && a->depth && a->inst && a->t_wc, "oo_append_frame: null frame");
+    if (a->n_obj == 0) return 0;
+    OO_REQUIRE(a->n_obj > 0 && a->obj_id && a->slot && a->bbox && a->rgbs && a->depth_ring && a->t_wc_ring && a->bbox_ring,
+               "oo_append_frame: null table");
+    const int n_pix = a->W * a->H;
+    int blocks = (n_pix + 255) / 256;
+    if (blocks > 148 * 8) blocks = 148 * 8;
+    k_append<<<blocks, 256, 0, (cudaStream_t)stream>>>(*a);
+    OO_LAUNCH_CHECK();
+    return 0;
+}
 
 extern "C" int oo_sample_rays(const oo_sample_args* a, void* stream) {
     OO_REQUIRE(a, "oo_sample_rays: null args");
     OO_REQUIRE(a->n_obj > 0 && a->n_frames > 0 && a->n_samples > 0, "oo_sample_rays: empty request");
     const int S = a->n_c2s + a->n_bins;
     OO_REQUIRE(a->n_c2s >= 1 && a->n_bins >= 1 && S + 1 <= MAXB, "oo_sample_rays: need 1 <= n_c2s, n_bins and S <= 32");
-    OO_REQUIRE(a->rgbs && a->depth && a->t_wc && a->bbox && a->rays_dir && a->kf_ids && a->u_w && a->u_h,
-               "oo_sample_rays: null input");
-    OO_REQUIRE(a->r_invalid && a->r_valid && a->r_normal && a->r_other, "oo_sample_rays: null RNG tape");
+    OO_REQUIRE(a->rgbs && a->depth && a->t_wc && a->bbox && a->rays_dir, "oo_sample_rays: null input");
+    if (a->rng_mode) {
+        OO_REQUIRE(a->obj_ids && a->n_keyframes && a->latest, "oo_sample_rays: rng_mode needs obj_ids / n_keyframes / latest");
+        OO_REQUIRE(!a->tape_by_rank, "oo_sample_rays: the counter RNG is indexed by ray, not by rank");
+    } else {
+        OO_REQUIRE(a->kf_ids && a->u_w && a->u_h, "oo_sample_rays: null keyframe / pixel tape");
+        OO_REQUIRE(a->r_invalid && a->r_valid && a->r_normal && a->r_other, "oo_sample_rays: null RNG tape");
+    }
     OO_REQUIRE(a->gt_rgb && a->gt_depth && a->valid && a->labels && a->pcs && a->z, "oo_sample_rays: null output");
     OO_REQUIRE(a->lin_s_host && a->lin_c2s_host && a->lin_bins_host, "oo_sample_rays: null linspace table");
     OO_REQUIRE(!a->feat_row || (a->part_frame && a->part_down > 0 && a->pw > 0 && a->ph > 0),

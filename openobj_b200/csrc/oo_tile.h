@@ -129,60 +129,86 @@ OO_DEV void gemm_fwd(int tid, const float* __restrict__ W, const float* __restri
 
 // DX[k][p] = [k < relu_rows ? (X[k][p] > 0) : 1] * ( sum_{j<J0} W0[j][k] DY0[j][p] + sum_{j<J1} W1[j][k] DY1[j][p]
 //            + [k < 32 && wa] wa[k] * draw[p] ),  written IN PLACE over X (rows 0..K-1).  K % 4 == 0.
+// One 4(k) x 4(p) register tile: k-group ki of the row block starting at kb (NK k-groups wide), point group pi.
+template <int WS0, int J0, int WS1, int J1>
+OO_DEV void dgemm_tile(int k0, int pi, const float* __restrict__ W0, const float* __restrict__ DY0,
+                       const float* __restrict__ W1, const float* __restrict__ DY1, float* X, int relu_rows,
+                       const float* wa, const float* draw) {
+    float acc[4][4];
+#pragma unroll
+    for (int kk = 0; kk < 4; ++kk) acc[kk][0] = acc[kk][1] = acc[kk][2] = acc[kk][3] = 0.f;
+#pragma unroll 4
+    for (int j = 0; j < J0; ++j) {
+        const float4 w = ld4(W0 + j * WS0 + k0);
+        const float4 d = ld4(DY0 + j * PS + 4 * pi);
+        acc[0][0] += w.x * d.x; acc[0][1] += w.x * d.y; acc[0][2] += w.x * d.z; acc[0][3] += w.x * d.w;
+        acc[1][0] += w.y * d.x; acc[1][1] += w.y * d.y; acc[1][2] += w.y * d.z; acc[1][3] += w.y * d.w;
+        acc[2][0] += w.z * d.x; acc[2][1] += w.z * d.y; acc[2][2] += w.z * d.z; acc[2][3] += w.z * d.w;
+        acc[3][0] += w.w * d.x; acc[3][1] += w.w * d.y; acc[3][2] += w.w * d.z; acc[3][3] += w.w * d.w;
+    }
+    if (J1 > 0) {
+#pragma unroll 4
+        for (int j = 0; j < J1; ++j) {
+            const float4 w = ld4(W1 + j * WS1 + k0);
+            const float4 d = ld4(DY1 + j * PS + 4 * pi);
+            acc[0][0] += w.x * d.x; acc[0][1] += w.x * d.y; acc[0][2] += w.x * d.z; acc[0][3] += w.x * d.w;
+            acc[1][0] += w.y * d.x; acc[1][1] += w.y * d.y; acc[1][2] += w.y * d.z; acc[1][3] += w.y * d.w;
+            acc[2][0] += w.z * d.x; acc[2][1] += w.z * d.y; acc[2][2] += w.z * d.z; acc[2][3] += w.z * d.w;
+            acc[3][0] += w.w * d.x; acc[3][1] += w.w * d.y; acc[3][2] += w.w * d.z; acc[3][3] += w.w * d.w;
+        }
+    }
+    if (wa != nullptr && k0 < H) {
+        const float4 dr = ld4(draw + 4 * pi);
+#pragma unroll
+        for (int kk = 0; kk < 4; ++kk) {
+            const float a = wa[k0 + kk];
+            acc[kk][0] += a * dr.x; acc[kk][1] += a * dr.y; acc[kk][2] += a * dr.z; acc[kk][3] += a * dr.w;
+        }
+    }
+#pragma unroll
+    for (int kk = 0; kk < 4; ++kk) {
+        float* xp = X + (k0 + kk) * PS + 4 * pi;
+        float4 o;
+        o.x = acc[kk][0]; o.y = acc[kk][1]; o.z = acc[kk][2]; o.w = acc[kk][3];
+        if (k0 + kk < relu_rows) {
+            const float4 h = ld4(xp);
+            o.x = h.x > 0.f ? o.x : 0.f; o.y = h.y > 0.f ? o.y : 0.f;
+            o.z = h.z > 0.f ? o.z : 0.f; o.w = h.w > 0.f ? o.w : 0.f;
+        }
+        st4(xp, o);
+    }
+}
+
+// Work distribution: rows are cut into blocks of 32 (8 k-groups x 25 point groups = 200 tiles, lanes = 8 k-groups x 4
+// point groups: conflict-free 128-bit loads).  Threads 0..199 take one full block per pass; the 56 spare threads
+// of every pass work through the tiles of the last, partial block, so K = 76 needs 2 passes and K = 88 needs 2 + a
+// short third instead of 3 each.
 template <int K, int WS0, int J0, int WS1, int J1>
 OO_DEV void gemm_bwd_data(int tid, const float* __restrict__ W0, const float* __restrict__ DY0,
                           const float* __restrict__ W1, const float* __restrict__ DY1,
                           float* X, int relu_rows, const float* wa, const float* draw) {
+    constexpr int PG = P / 4;                    // 25 point groups
+    constexpr int NFULL = K / 32;                // full 32-row blocks
+    constexpr int REM = (K - 32 * NFULL) / 4;    // k-groups of the partial block
+    constexpr int NREM = REM * PG;               // its tiles
+    constexpr int SPARE = NTHREADS - 8 * PG;     // 56
+    int rem_done = 0;
 #pragma unroll
-    for (int kb = 0; kb < K; kb += 32) {
-        const int nk = ((K - kb) >= 32 ? 32 : (K - kb)) / 4;   // k-groups in this block of rows
-        if (tid < nk * (P / 4)) {
-            const int ki = tid % nk, pi = tid / nk;
-            const int k0 = kb + 4 * ki;
-            float acc[4][4];
-#pragma unroll
-            for (int kk = 0; kk < 4; ++kk) acc[kk][0] = acc[kk][1] = acc[kk][2] = acc[kk][3] = 0.f;
-#pragma unroll 4
-            for (int j = 0; j < J0; ++j) {
-                const float4 w = ld4(W0 + j * WS0 + k0);
-                const float4 d = ld4(DY0 + j * PS + 4 * pi);
-                acc[0][0] += w.x * d.x; acc[0][1] += w.x * d.y; acc[0][2] += w.x * d.z; acc[0][3] += w.x * d.w;
-                acc[1][0] += w.y * d.x; acc[1][1] += w.y * d.y; acc[1][2] += w.y * d.z; acc[1][3] += w.y * d.w;
-                acc[2][0] += w.z * d.x; acc[2][1] += w.z * d.y; acc[2][2] += w.z * d.z; acc[2][3] += w.z * d.w;
-                acc[3][0] += w.w * d.x; acc[3][1] += w.w * d.y; acc[3][2] += w.w * d.z; acc[3][3] += w.w * d.w;
-            }
-            if (J1 > 0) {
-#pragma unroll 4
-                for (int j = 0; j < J1; ++j) {
-                    const float4 w = ld4(W1 + j * WS1 + k0);
-                    const float4 d = ld4(DY1 + j * PS + 4 * pi);
-                    acc[0][0] += w.x * d.x; acc[0][1] += w.x * d.y; acc[0][2] += w.x * d.z; acc[0][3] += w.x * d.w;
-                    acc[1][0] += w.y * d.x; acc[1][1] += w.y * d.y; acc[1][2] += w.y * d.z; acc[1][3] += w.y * d.w;
-                    acc[2][0] += w.z * d.x; acc[2][1] += w.z * d.y; acc[2][2] += w.z * d.z; acc[2][3] += w.z * d.w;
-                    acc[3][0] += w.w * d.x; acc[3][1] += w.w * d.y; acc[3][2] += w.w * d.z; acc[3][3] += w.w * d.w;
-                }
-            }
-            if (wa != nullptr && kb == 0) {
-                const float4 dr = ld4(draw + 4 * pi);
-#pragma unroll
-                for (int kk = 0; kk < 4; ++kk) {
-                    const float a = wa[k0 + kk];
-                    acc[kk][0] += a * dr.x; acc[kk][1] += a * dr.y; acc[kk][2] += a * dr.z; acc[kk][3] += a * dr.w;
-                }
-            }
-#pragma unroll
-            for (int kk = 0; kk < 4; ++kk) {
-                float* xp = X + (k0 + kk) * PS + 4 * pi;
-                float4 o;
-                o.x = acc[kk][0]; o.y = acc[kk][1]; o.z = acc[kk][2]; o.w = acc[kk][3];
-                if (k0 + kk < relu_rows) {
-                    const float4 h = ld4(xp);
-                    o.x = h.x > 0.f ? o.x : 0.f; o.y = h.y > 0.f ? o.y : 0.f;
-                    o.z = h.z > 0.f ? o.z : 0.f; o.w = h.w > 0.f ? o.w : 0.f;
-                }
-                st4(xp, o);
-            }
+    for (int b = 0; b < NFULL; ++b) {
+        if (tid < 8 * PG) {
+            dgemm_tile<WS0, J0, WS1, J1>(32 * b + 4 * (tid & 7), tid >> 3, W0, DY0, W1, DY1, X, relu_rows, wa, draw);
+        } else if (REM > 0) {
+            const int t = rem_done + tid - 8 * PG;
+            if (t < NREM)
+                dgemm_tile<WS0, J0, WS1, J1>(32 * NFULL + 4 * (t % (REM > 0 ? REM : 1)), t / (REM > 0 ? REM : 1), W0, DY0, W1,
+                                             DY1, X, relu_rows, wa, draw);
         }
+        rem_done += SPARE;
+    }
+    if (REM > 0) {
+        for (int t = rem_done + tid; t < NREM; t += NTHREADS)
+            dgemm_tile<WS0, J0, WS1, J1>(32 * NFULL + 4 * (t % (REM > 0 ? REM : 1)), t / (REM > 0 ? REM : 1), W0, DY0, W1, DY1,
+                                         X, relu_rows, wa, draw);
     }
 }
 
@@ -257,8 +283,11 @@ OO_DEV void zero_pad_rows(int tid, float* sm) {
 // ------------------------------------------------------------------------------------------------
 // phases
 // ------------------------------------------------------------------------------------------------
-constexpr int N_TRAIN_PHASES = 32;
+constexpr int N_TRAIN_PHASES = 34;
 constexpr int N_FWD_PHASES = 8;    // phases 0..7 are shared with the standalone forward kernel
+// execution order of the training tile (phases 32..35 were split out of their neighbours later)
+constexpr int kTrainOrder[N_TRAIN_PHASES] = {0, 1, 2, 3, 4, 5, 6, 7, 33, 8, 9, 10, 11, 12, 32, 13, 14, 15, 16, 17, 18, 19,
+                                             20, 21, 22, 23, 24, 25, 26, 27, 28, 29, 30, 31};
 
 template <int PH, bool PART>
 OO_DEV void tile_phase(int tid, float* __restrict__ sm, const TileCtx& c, TileAcc& a) {
@@ -278,19 +307,23 @@ OO_DEV void tile_phase(int tid, float* __restrict__ sm, const TileCtx& c, TileAc
             act[(R_E1 + ch) * PS + p] = t;
         }
     } else if constexpr (PH == 1) {
-        // proj = B t ; e[3 + 21 k + d] = sin(pi * 2^k * proj) (embedding.py:48-53)
+        // proj = B t ; e[3 + 21 k + d] = sin(pi * 2^k * proj) (embedding.py:48-53).  The reference's argument for band k
+        // is fl(2^k proj * pi_f) = 2^k * fl(proj * pi_f) exactly (power-of-two scaling commutes with rounding), so all
+        // six bands follow from one sincosf by angle doubling: s' = 2 s c, c' = (c - s)(c + s)  (norm error only doubles).
         for (int i = tid; i < NDIR * P; i += NTHREADS) {
             const int d = i / P, p = i - d * P;
             const float t0 = act[(R_T + 0) * PS + p], t1 = act[(R_T + 1) * PS + p], t2 = act[(R_T + 2) * PS + p];
             const float proj = w[W_PE + 3 * d] * t0 + w[W_PE + 3 * d + 1] * t1 + w[W_PE + 3 * d + 2] * t2;
-            float band = 1.f;
+            float sn, cs;
+            sincosf(proj * PI_F, &sn, &cs);
 #pragma unroll
             for (int k = 0; k < NBAND; ++k) {
-                const float s = sinf((proj * band) * PI_F);
                 const int row = 3 + NDIR * k + d;
-                if (row < E1) act[(R_E1 + row) * PS + p] = s;
-                else act[(R_E2 + row - E1) * PS + p] = s;
-                band *= 2.f;
+                if (row < E1) act[(R_E1 + row) * PS + p] = sn;
+                else act[(R_E2 + row - E1) * PS + p] = sn;
+                const float s2 = 2.f * sn * cs, c2 = (cs - sn) * (cs + sn);
+                sn = s2;
+                cs = c2;
             }
         }
     } else if constexpr (PH == 2) {
@@ -322,23 +355,30 @@ OO_DEV void tile_phase(int tid, float* __restrict__ sm, const TileCtx& c, TileAc
                 misc[(M_COL + ch) * PS + p] = sigmoidf_(r);
             }
         }
+    } else if constexpr (PH == 33) {
+        // per point: exclusive product of the free probabilities in torch.cumprod's order, termination weight
+        // (render_rays.py:36-43)
+        for (int p = tid; p < P; p += NTHREADS) {
+            const int r = p / S, i = p - r * S;
+            float freep = 1.f;
+            for (int q = 0; q < i; ++q) freep *= (1.f - misc[M_OCC * PS + r * S + q] + 1e-10f);
+            const bool live = r < c.nrays;
+            misc[M_FREE * PS + p] = live ? freep : 0.f;
+            misc[M_TERM * PS + p] = live ? misc[M_OCC * PS + p] * freep : 0.f;
+        }
     } else if constexpr (PH == 8) {
-        // per ray: termination, rendered depth / variance / colour / opacity, loss terms and their
-        // derivatives w.r.t. the rendered quantities (render_rays.py:32-63, loss.py:27-75)
+        // per ray: rendered depth / variance / colour / opacity, loss terms and their derivatives w.r.t. the rendered
+        // quantities (render_rays.py:56-63, loss.py:27-75)
         if (tid < RT) {
             const int r = tid;
             float gd = 0.f, go = 0.f, gc0 = 0.f, gc1 = 0.f, gc2 = 0.f, cf = 0.f;
             float depth = 0.f, opac = 0.f, c0 = 0.f, c1 = 0.f, c2 = 0.f;
             if (r < c.nrays) {
                 float zv[S], tv[S];
-                float freep = 1.f;
 #pragma unroll
                 for (int i = 0; i < S; ++i) {
                     const int p = r * S + i;
-                    const float o = misc[M_OCC * PS + p];
-                    const float t = o * freep;
-                    misc[M_TERM * PS + p] = t;
-                    misc[M_FREE * PS + p] = freep;
+                    const float t = misc[M_TERM * PS + p];
                     zv[i] = OO_LDG(c.z + p);
                     tv[i] = t;
                     depth += t * zv[i];
@@ -346,7 +386,6 @@ OO_DEV void tile_phase(int tid, float* __restrict__ sm, const TileCtx& c, TileAc
                     c0 += t * misc[(M_COL + 0) * PS + p];
                     c1 += t * misc[(M_COL + 1) * PS + p];
                     c2 += t * misc[(M_COL + 2) * PS + p];
-                    freep *= (1.f - o + 1e-10f);
                 }
                 float var = 0.f;
 #pragma unroll
@@ -375,12 +414,6 @@ OO_DEV void tile_phase(int tid, float* __restrict__ sm, const TileCtx& c, TileAc
                     const float eo = opac - tgt;                                 // loss.py:71
                     a.loss[2] += fabsf(eo);
                     go = sgnf_(eo) * c.os * c.invs;
-                }
-            } else {
-#pragma unroll
-                for (int i = 0; i < S; ++i) {
-                    misc[M_TERM * PS + r * S + i] = 0.f;
-                    misc[M_FREE * PS + r * S + i] = 0.f;
                 }
             }
             rv[V_DEPTH * RP + r] = depth;
@@ -414,16 +447,21 @@ OO_DEV void tile_phase(int tid, float* __restrict__ sm, const TileCtx& c, TileAc
                 f[0][r] = b0 * op;
                 f[1][r] = b1 * op;
             }
-#pragma unroll 4
+            float w0[H], w1[H];      // all 64 global loads are issued before the first use
+#pragma unroll
             for (int j = 0; j < H; ++j) {
-                const float w0 = OO_LDG(c.wocl_t + j * C + c0), w1 = OO_LDG(c.wocl_t + j * C + c1);
+                w0[j] = OO_LDG(c.wocl_t + j * C + c0);
+                w1[j] = OO_LDG(c.wocl_t + j * C + c1);
+            }
+#pragma unroll
+            for (int j = 0; j < H; ++j) {
                 const float4 sa = ld4(sm + SM_ST + j * RP), sb = ld4(sm + SM_ST + j * RP + 4),
                              sc = ld4(sm + SM_ST + j * RP + 8);
                 const float sv[RT] = {sa.x, sa.y, sa.z, sa.w, sb.x, sb.y, sb.z, sb.w, sc.x, sc.y};
 #pragma unroll
                 for (int r = 0; r < RT; ++r) {
-                    f[0][r] += w0 * sv[r];
-                    f[1][r] += w1 * sv[r];
+                    f[0][r] += w0[j] * sv[r];
+                    f[1][r] += w1[j] * sv[r];
                 }
             }
 #pragma unroll
@@ -451,14 +489,27 @@ OO_DEV void tile_phase(int tid, float* __restrict__ sm, const TileCtx& c, TileAc
             }
         }
     } else if constexpr (PH == 12) {
+        // (a) 50 threads: total of the 16 partials per (ray, quantity)
+        if (PART) {
+            if (tid < RT * 5) {
+                const int r = tid / 5, q = tid - 5 * r;
+                const float* o = sm + SM_COSP + r * 80 + q;
+                float s0 = 0.f, s1 = 0.f;
+#pragma unroll
+                for (int ch = 0; ch < 16; ch += 2) {
+                    s0 += o[ch * 5];
+                    s1 += o[ch * 5 + 5];
+                }
+                sm[SM_COSP + 800 + tid] = s0 + s1;
+            }
+        }
+    } else if constexpr (PH == 32) {
+        // (b) 10 threads: cosine, loss partial, and the two coefficients of g = A*y + B*x
         if (PART) {
             if (tid < RT) {
                 const int r = tid;
-                float xy = 0.f, xx = 0.f, yy = 0.f, xb = 0.f, yb = 0.f;
-                for (int ch = 0; ch < 16; ++ch) {
-                    const float* o = sm + SM_COSP + (r * 16 + ch) * 5;
-                    xy += o[0]; xx += o[1]; yy += o[2]; xb += o[3]; yb += o[4];
-                }
+                const float* o = sm + SM_COSP + 800 + 5 * r;
+                const float xy = o[0], xx = o[1], yy = o[2], xb = o[3], yb = o[4];
                 const float cf = rv[V_CF * RP + r];
                 const float nxr = sqrtf(xx), nyr = sqrtf(yy);
                 const float nx = fmaxf(nxr, 1e-8f), ny = fmaxf(nyr, 1e-8f);   // F.cosine_similarity eps clamp
@@ -500,14 +551,16 @@ OO_DEV void tile_phase(int tid, float* __restrict__ sm, const TileCtx& c, TileAc
                 float u[RT];
 #pragma unroll
                 for (int r = 0; r < RT; ++r) u[r] = 0.f;
-                const float* wocl = c.theta + OFF_OCL_W;
-                for (int cc = wv * 64; cc < wv * 64 + 64; cc += 4) {
-                    const float w0 = OO_LDG(wocl + (cc + 0) * H + j), w1 = OO_LDG(wocl + (cc + 1) * H + j),
-                                w2 = OO_LDG(wocl + (cc + 2) * H + j), w3 = OO_LDG(wocl + (cc + 3) * H + j);
+                const float* wocl = c.theta + OFF_OCL_W + (size_t)(wv * 64) * H + j;
+                float wq[64];            // 64 coalesced global loads in flight before the first use
+#pragma unroll
+                for (int q = 0; q < 64; ++q) wq[q] = OO_LDG(wocl + q * H);
+#pragma unroll
+                for (int q = 0; q < 64; q += 4) {
 #pragma unroll
                     for (int r = 0; r < RT; ++r) {
-                        const float4 g = ld4(sm + SM_FEAT + r * C + cc);
-                        u[r] += g.x * w0 + g.y * w1 + g.z * w2 + g.w * w3;
+                        const float4 g = ld4(sm + SM_FEAT + r * C + wv * 64 + q);
+                        u[r] += g.x * wq[q] + g.y * wq[q + 1] + g.z * wq[q + 2] + g.w * wq[q + 3];
                     }
                 }
 #pragma unroll
@@ -534,23 +587,24 @@ OO_DEV void tile_phase(int tid, float* __restrict__ sm, const TileCtx& c, TileAc
                 }
                 sb[c0] = db0;
                 sb[c1] = db1;
-#pragma unroll 4
+                float d0[H], d1[H];
+#pragma unroll
+                for (int j = 0; j < H; ++j) {
+                    d0[j] = c.first_tile ? 0.f : sw[j * C + c0];
+                    d1[j] = c.first_tile ? 0.f : sw[j * C + c1];
+                }
+#pragma unroll
                 for (int j = 0; j < H; ++j) {
                     const float4 sa = ld4(sm + SM_ST + j * RP), sb4 = ld4(sm + SM_ST + j * RP + 4),
                                  sc = ld4(sm + SM_ST + j * RP + 8);
                     const float sv[RT] = {sa.x, sa.y, sa.z, sa.w, sb4.x, sb4.y, sb4.z, sb4.w, sc.x, sc.y};
-                    float d0 = 0.f, d1 = 0.f;
-                    if (!c.first_tile) {
-                        d0 = sw[j * C + c0];
-                        d1 = sw[j * C + c1];
-                    }
 #pragma unroll
                     for (int r = 0; r < RT; ++r) {
-                        d0 += g0[r] * sv[r];
-                        d1 += g1[r] * sv[r];
+                        d0[j] += g0[r] * sv[r];
+                        d1[j] += g1[r] * sv[r];
                     }
-                    sw[j * C + c0] = d0;
-                    sw[j * C + c1] = d1;
+                    sw[j * C + c0] = d0[j];
+                    sw[j * C + c1] = d1[j];
                 }
             }
         }
@@ -565,46 +619,49 @@ OO_DEV void tile_phase(int tid, float* __restrict__ sm, const TileCtx& c, TileAc
             }
         }
     } else if constexpr (PH == 16) {
-        // hu[p] = hp_p . U_r + b_ocl . g_r  : what one unit of termination weight at p adds to the feature loss
-        if (PART) {
-            for (int p = tid; p < P; p += NTHREADS) {
-                const int r = p / S;
-                float hu = rv[V_BG * RP + r];
+        // per point: g = dL/dT = z gd + go + col . gc (+ hp . U_r + b_ocl . g_r : what one unit of termination weight
+        // at this point adds to the feature loss).  g -> M_DRAW row, g*T -> M_HU row.
+        for (int p = tid; p < P; p += NTHREADS) {
+            const int r = p / S;
+            float g = 0.f;
+            if (r < c.nrays) {
+                g = OO_LDG(c.z + p) * rv[V_GD * RP + r] + rv[V_GO * RP + r] +
+                    misc[(M_COL + 0) * PS + p] * rv[(V_GC + 0) * RP + r] + misc[(M_COL + 1) * PS + p] * rv[(V_GC + 1) * RP + r] +
+                    misc[(M_COL + 2) * PS + p] * rv[(V_GC + 2) * RP + r];
+                if (PART) {
+                    float hu = rv[V_BG * RP + r];
 #pragma unroll 8
-                for (int j = 0; j < H; ++j) hu += act[(R_HP + j) * PS + p] * sm[SM_UT + j * RP + r];
-                misc[M_HU * PS + p] = hu;
+                    for (int j = 0; j < H; ++j) hu += act[(R_HP + j) * PS + p] * sm[SM_UT + j * RP + r];
+                    g += hu;
+                }
             }
+            misc[M_DRAW * PS + p] = g;
+            misc[M_HU * PS + p] = g * misc[M_TERM * PS + p];
         }
     } else if constexpr (PH == 17) {
-        // back through the compositing sums and the exclusive product:
+        // back through the compositing sums and the exclusive product, one thread per point:
         //   g_i = dL/dT_i ; dL/do_i = g_i P_i - (sum_{k>i} g_k T_k) / (1 - o_i + 1e-10) ; alpha = 10 raw
-        if (tid < RT) {
-            const int r = tid;
-            const float gd = rv[V_GD * RP + r], go = rv[V_GO * RP + r];
-            const float gc0 = rv[(V_GC + 0) * RP + r], gc1 = rv[(V_GC + 1) * RP + r], gc2 = rv[(V_GC + 2) * RP + r];
-            float suffix = 0.f;
-#pragma unroll
-            for (int i = S - 1; i >= 0; --i) {
-                const int p = r * S + i;
-                float draw = 0.f, d0 = 0.f, d1 = 0.f, d2 = 0.f;
-                if (r < c.nrays) {
-                    const float t = misc[M_TERM * PS + p], o = misc[M_OCC * PS + p], fp = misc[M_FREE * PS + p];
-                    const float k0 = misc[(M_COL + 0) * PS + p], k1 = misc[(M_COL + 1) * PS + p],
-                                k2 = misc[(M_COL + 2) * PS + p];
-                    float g = OO_LDG(c.z + p) * gd + go + k0 * gc0 + k1 * gc1 + k2 * gc2;
-                    if (PART) g += misc[M_HU * PS + p];
-                    const float docc = g * fp - suffix / (1.f - o + 1e-10f);
-                    suffix += g * t;
-                    draw = docc * o * (1.f - o) * 10.f;
-                    d0 = t * gc0 * k0 * (1.f - k0);
-                    d1 = t * gc1 * k1 * (1.f - k1);
-                    d2 = t * gc2 * k2 * (1.f - k2);
-                }
-                misc[M_DRAW * PS + p] = draw;
-                misc[(M_DCOL + 0) * PS + p] = d0;
-                misc[(M_DCOL + 1) * PS + p] = d1;
-                misc[(M_DCOL + 2) * PS + p] = d2;
+        // phase 34 stored g_i T_i in the M_HU row (after adding the feature term), g_i in M_DRAW.
+        for (int p = tid; p < P; p += NTHREADS) {
+            const int r = p / S, i = p - r * S;
+            float draw = 0.f, d0 = 0.f, d1 = 0.f, d2 = 0.f;
+            if (r < c.nrays) {
+                float suffix = 0.f;
+                for (int q = S - 1; q > i; --q) suffix += misc[M_HU * PS + r * S + q];
+                const float t = misc[M_TERM * PS + p], o = misc[M_OCC * PS + p], fp = misc[M_FREE * PS + p];
+                const float k0 = misc[(M_COL + 0) * PS + p], k1 = misc[(M_COL + 1) * PS + p], k2 = misc[(M_COL + 2) * PS + p];
+                const float g = misc[M_DRAW * PS + p];
+                const float docc = g * fp - suffix / (1.f - o + 1e-10f);
+                draw = docc * o * (1.f - o) * 10.f;
+                const float gc0 = rv[(V_GC + 0) * RP + r], gc1 = rv[(V_GC + 1) * RP + r], gc2 = rv[(V_GC + 2) * RP + r];
+                d0 = t * gc0 * k0 * (1.f - k0);
+                d1 = t * gc1 * k1 * (1.f - k1);
+                d2 = t * gc2 * k2 * (1.f - k2);
             }
+            misc[(M_DCOL + 0) * PS + p] = d0;
+            misc[(M_DCOL + 1) * PS + p] = d1;
+            misc[(M_DCOL + 2) * PS + p] = d2;
+            misc[M_DRAW * PS + p] = draw;      // only this thread read g from this element
         }
     } else if constexpr (PH == 18) {
         // out_color / out_alpha weight gradients (reduce over points) ...
@@ -612,13 +669,13 @@ OO_DEV void tile_phase(int tid, float* __restrict__ sm, const TileCtx& c, TileAc
             const int o = tid >> 5, j = tid & 31;
             const float* dy = misc + (o < 3 ? (M_DCOL + o) : M_DRAW) * PS;
             const float* x = act + ((o < 3 ? R_HC : R_H4) + j) * PS;
-            float s = 0.f;
-#pragma unroll 5
+            float s0 = 0.f, s1 = 0.f, s2 = 0.f, s3 = 0.f;      // four independent chains
+#pragma unroll
             for (int p0 = 0; p0 < P; p0 += 4) {
                 const float4 d = ld4(dy + p0), h = ld4(x + p0);
-                s += d.x * h.x + d.y * h.y + d.z * h.z + d.w * h.w;
+                s0 += d.x * h.x; s1 += d.y * h.y; s2 += d.z * h.z; s3 += d.w * h.w;
             }
-            a.s0 += s;
+            a.s0 += (s0 + s1) + (s2 + s3);
         }
         // ... and d(hp_pre) = T_p * U_r * [hp > 0] in place
         if (PART) {
@@ -696,12 +753,17 @@ OO_DEV void tile_phase(int tid, float* __restrict__ sm, const TileCtx& c, TileAc
             const int d = i / P, p = i - d * P;
             const float t0 = act[(R_T + 0) * PS + p], t1 = act[(R_T + 1) * PS + p], t2 = act[(R_T + 2) * PS + p];
             const float proj = w[W_PE + 3 * d] * t0 + w[W_PE + 3 * d + 1] * t1 + w[W_PE + 3 * d + 2] * t2;
-            float band = 1.f, dp = 0.f;
+            float sn, cs;
+            sincosf(proj * PI_F, &sn, &cs);
+            float band = PI_F, dp = 0.f;
 #pragma unroll
             for (int k = 0; k < NBAND; ++k) {
                 const int row = 3 + NDIR * k + d;
                 const float de = row < E1 ? act[(R_E1 + row) * PS + p] : act[(R_E2 + row - E1) * PS + p];
-                dp += de * (cosf((proj * band) * PI_F) * PI_F * band);
+                dp += de * (cs * band);
+                const float s2 = 2.f * sn * cs, c2 = (cs - sn) * (cs + sn);
+                sn = s2;
+                cs = c2;
                 band *= 2.f;
             }
             act[(R_E1 + 3 + d) * PS + p] = dp;
@@ -711,13 +773,13 @@ OO_DEV void tile_phase(int tid, float* __restrict__ sm, const TileCtx& c, TileAc
             const int d = tid / 3, ch = tid - 3 * d;
             const float* dp = act + (R_E1 + 3 + d) * PS;
             const float* tt = act + (R_T + ch) * PS;
-            float s = 0.f;
-#pragma unroll 5
+            float s0 = 0.f, s1 = 0.f, s2 = 0.f, s3 = 0.f;
+#pragma unroll
             for (int p0 = 0; p0 < P; p0 += 4) {
                 const float4 x = ld4(dp + p0), y = ld4(tt + p0);
-                s += x.x * y.x + x.y * y.y + x.z * y.z + x.w * y.w;
+                s0 += x.x * y.x; s1 += x.y * y.y; s2 += x.z * y.z; s3 += x.w * y.w;
             }
-            a.s2 += s;
+            a.s2 += (s0 + s1) + (s2 + s3);
         }
         if (tid < 6 * H + 4) {
             const float* row;
@@ -729,13 +791,13 @@ OO_DEV void tile_phase(int tid, float* __restrict__ sm, const TileCtx& c, TileAc
                 const int o = tid - 6 * H;
                 row = misc + (o < 3 ? (M_DCOL + o) : M_DRAW) * PS;
             }
-            float s = 0.f;
-#pragma unroll 5
+            float s0 = 0.f, s1 = 0.f, s2 = 0.f, s3 = 0.f;
+#pragma unroll
             for (int p0 = 0; p0 < P; p0 += 4) {
                 const float4 x = ld4(row + p0);
-                s += (x.x + x.y) + (x.z + x.w);
+                s0 += x.x; s1 += x.y; s2 += x.z; s3 += x.w;
             }
-            if (PART || tid < 5 * H || tid >= 6 * H) a.s1 += s;
+            if (PART || tid < 5 * H || tid >= 6 * H) a.s1 += (s0 + s1) + (s2 + s3);
         }
     }
 }

@@ -25,19 +25,25 @@ struct TrainParams {
     float* slab;
     float* slot_loss;
     float scale, cs, os, fs;
+    long long* phase_cycles;   // debug: [N_TRAIN_PHASES + 2] cycle totals of block 0 (nullptr = off)
 };
+
+long long* g_phase_cycles = nullptr;
 
 template <int PH, int END, bool PART>
 struct Phases {
-    static __device__ __forceinline__ void run(int tid, float* sm, const TileCtx& c, TileAcc& a) {
-        tile_phase<PH, PART>(tid, sm, c, a);
+    static __device__ __forceinline__ void run(int tid, float* sm, const TileCtx& c, TileAcc& a, long long* cyc) {
+        long long t0 = 0;
+        if (cyc) t0 = clock64();
+        tile_phase<kTrainOrder[PH], PART>(tid, sm, c, a);
         __syncthreads();
-        Phases<PH + 1, END, PART>::run(tid, sm, c, a);
+        if (cyc && tid == 0) cyc[PH] += clock64() - t0;
+        Phases<PH + 1, END, PART>::run(tid, sm, c, a, cyc);
     }
 };
 template <int END, bool PART>
 struct Phases<END, END, PART> {
-    static __device__ __forceinline__ void run(int, float*, const TileCtx&, TileAcc&) {}
+    static __device__ __forceinline__ void run(int, float*, const TileCtx&, TileAcc&, long long*) {}
 };
 
 template <bool PART>
@@ -50,6 +56,8 @@ __global__ void __launch_bounds__(NTHREADS, 1) k_train(const TrainParams prm) {
     int slot = prm.sched[n_cta + 1 + blockIdx.x];
     const int flags = prm.flags[0];
 
+    long long* cyc = (prm.phase_cycles != nullptr && blockIdx.x == 0) ? prm.phase_cycles : nullptr;
+    const long long t_start = cyc ? clock64() : 0;
     zero_pad_rows(tid, sm);
     TileAcc acc;
     acc_zero(acc);
@@ -84,7 +92,7 @@ __global__ void __launch_bounds__(NTHREADS, 1) k_train(const TrainParams prm) {
         c.labels = prm.b.labels + ray;
         c.feat_row = PART ? prm.b.feat_row + ray : nullptr;
 
-        Phases<0, N_TRAIN_PHASES, PART>::run(tid, sm, c, acc);
+        Phases<0, N_TRAIN_PHASES, PART>::run(tid, sm, c, acc, cyc);
         c.first_tile = 0;
 
         const bool last_of_obj = (t + 1 == t_end) || ((t + 1) / prm.tiles_per_obj != obj);
@@ -98,6 +106,10 @@ __global__ void __launch_bounds__(NTHREADS, 1) k_train(const TrainParams prm) {
             ++slot;
             cur_obj = -1;
         }
+    }
+    if (cyc && tid == 0) {
+        cyc[N_TRAIN_PHASES] += clock64() - t_start;     // whole block
+        cyc[N_TRAIN_PHASES + 1] += t_end - t_begin;     // tiles processed
     }
 }
 
@@ -130,28 +142,43 @@ __global__ void k_label_counts(const uint8_t* __restrict__ labels, int n_obj, in
 // corrections (torch.optim.AdamW: tensors whose grad is None are skipped entirely)
 __global__ void k_adam_schedule(const int* __restrict__ flags, int iters, int part_on, double lr, double b1, double b2,
                                 int* __restrict__ adam_t, float* __restrict__ scal) {
-    if (threadIdx.x != 0 || blockIdx.x != 0) return;
-    int t[3] = {adam_t[0], adam_t[1], adam_t[2]};
-    for (int it = 0; it < iters; ++it) {
+    // one thread per step; the step number of a group = its counter + number of active steps up to and including `it`
+    __shared__ int s_act[3][1024];
+    const int it = threadIdx.x;
+    bool active[3] = {false, false, false};
+    if (it < iters) {
         const int f = flags[it];
         const bool obj_terms = !(f & OO_FLAG_NO_OBJ), op_term = !(f & OO_FLAG_NO_SEM);
-        const bool active[3] = {obj_terms || op_term, obj_terms, obj_terms && part_on != 0};
+        active[0] = obj_terms || op_term;
+        active[1] = obj_terms;
+        active[2] = obj_terms && part_on != 0;
+    }
+    for (int g = 0; g < 3; ++g) s_act[g][it] = active[g] ? 1 : 0;
+    __syncthreads();
+    if (it < iters) {
         for (int g = 0; g < 3; ++g) {
+            int t = adam_t[g];
+            for (int q = 0; q <= it; ++q) t += s_act[g][q];
             float* s = scal + ((size_t)it * 3 + g) * 4;
             if (active[g]) {
-                t[g] += 1;
-                const double bc1 = 1.0 - pow(b1, (double)t[g]);
-                const double bc2 = 1.0 - pow(b2, (double)t[g]);
+                const double bc1 = 1.0 - pow(b1, (double)t), bc2 = 1.0 - pow(b2, (double)t);
                 s[0] = 1.f;
                 s[1] = (float)(lr / bc1);
                 s[2] = (float)sqrt(bc2);
-                s[3] = (float)t[g];
+                s[3] = (float)t;
             } else {
                 s[0] = s[1] = s[2] = s[3] = 0.f;
             }
         }
     }
-    adam_t[0] = t[0]; adam_t[1] = t[1]; adam_t[2] = t[2];
+    __syncthreads();
+    if (it == 0) {
+        for (int g = 0; g < 3; ++g) {
+            int t = adam_t[g];
+            for (int q = 0; q < iters; ++q) t += s_act[g][q];
+            adam_t[g] = t;
+        }
+    }
 }
 
 // ---- K4: sum the gradient slots of each object (fixed order) and apply AdamW in place; HBM-bound.
@@ -271,6 +298,7 @@ int launch_k1(const float* theta, int n_obj, const oo_batch* b, int it, int R, f
     prm.slab = ws->slab;
     prm.slot_loss = ws->slot_loss;
     prm.scale = scale;
+    prm.phase_cycles = g_phase_cycles;
     prm.cs = 5.f; prm.os = 10.f; prm.fs = 5.f;   // loss.py:6 defaults (the JSON values are never read)
     const size_t smem = (size_t)SM_TOTAL * sizeof(float);
     static bool attr_set = false;
@@ -286,6 +314,12 @@ int launch_k1(const float* theta, int n_obj, const oo_batch* b, int it, int R, f
 }
 
 }  // namespace
+
+// debug hook (not part of the ABI header): per-phase cycle counters of block 0
+extern "C" int oo_debug_phase_cycles(long long* dev_ptr) {
+    g_phase_cycles = dev_ptr;
+    return N_TRAIN_PHASES + 2;
+}
 
 extern "C" int oo_train_ws_sizes(int n_obj, int rays_per_step, int iters, int n_sm, int* n_cta, int* n_slots,
                                  int64_t* slab_floats, int64_t* sched_ints_out) {
@@ -326,7 +360,8 @@ extern "C" int oo_label_counts(const uint8_t* labels, int n_obj, int rays_per_ob
 extern "C" int oo_adam_schedule(const int* flags, int iters, int part_on, float lr, float beta1, float beta2,
                                 int* adam_t, float* adam_scal, void* stream) {
     OO_REQUIRE(flags && adam_t && adam_scal, "oo_adam_schedule: null argument");
-    k_adam_schedule<<<1, 32, 0, (cudaStream_t)stream>>>(flags, iters, part_on, (double)lr, (double)beta1, (double)beta2,
+    OO_REQUIRE(iters >= 1 && iters <= 1024, "oo_adam_schedule: iters must be in [1, 1024]");
+    k_adam_schedule<<<1, 1024, 0, (cudaStream_t)stream>>>(flags, iters, part_on, (double)lr, (double)beta1, (double)beta2,
                                                         adam_t, adam_scal);
     OO_LAUNCH_CHECK();
     return 0;

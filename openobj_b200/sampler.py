@@ -7,7 +7,7 @@ from typing import Optional
 import torch
 
 from . import ops
-from ._lib import SampleArgs, check, lib, ptr, stream
+from ._lib import AppendArgs, SampleArgs, check, lib, ptr, stream
 
 KF_MAX = 20
 
@@ -64,7 +64,7 @@ def device_tapes(objects, n_frames, n_samples, n_c2s, n_bins, eps, seed, frame, 
     f32 = dict(dtype=torch.float32, device=device)
     u_kf = ops.rng_fill(torch.empty(n, n_frames, **f32), seed, 8 * frame + 0, ids)
     nkf = torch.tensor([o.n_keyframes for o in objects], dtype=torch.float32, device=device)[:, None]
-    kf = torch.minimum((u_kf * nkf).long(), (nkf - 1).long())
+    kf = torch.minimum((u_kf * nkf).int().long(), (nkf - 1).long())
     for i, o in enumerate(objects):              # forced latest two keyframes (host bookkeeping, vmap.py:398-400)
         if o.n_keyframes > 2:
             kf[i, -2:] = torch.as_tensor(o.lastest_kf_queue[-2:], device=device)
@@ -80,11 +80,34 @@ def device_tapes(objects, n_frames, n_samples, n_c2s, n_bins, eps, seed, frame, 
         by_rank=False)
 
 
-def sample(rgbs, depth, t_wc, bbox, part_frame, rays_dir, tapes: SampleTapes, n_frames, n_samples, n_c2s=1, n_bins=9,
-           eps=0.1, other_eps=0.05, min_bound=0.0, part_down=0, part_hw=(0, 0), want_pix=False, out: SampleOut = None):
+@dataclass
+class CounterRng:
+    """In-kernel counter RNG (no tapes): same values as device_tapes() for the same (seed, frame, object ids)."""
+    seed: int
+    frame: int
+    obj_ids: torch.Tensor      # int32 [n_obj]
+    n_keyframes: torch.Tensor  # int32 [n_obj]
+    latest: torch.Tensor       # int32 [n_obj, 2]
+
+
+class RingTables:
+    """Device pointer tables of the objects' keyframe rings (rebuilt only when the object set changes)."""
+
+    def __init__(self, objects, device):
+        self.n = len(objects)
+        self.rgbs = _ptr_table([o.rgbs_batch for o in objects], device)
+        self.depth = _ptr_table([o.depth_batch for o in objects], device)
+        self.t_wc = _ptr_table([o.t_wc_batch for o in objects], device)
+        self.bbox = _ptr_table([o.bbox for o in objects], device)
+
+
+def sample(rgbs, depth, t_wc, bbox, part_frame, rays_dir, tapes, n_frames, n_samples, n_c2s=1, n_bins=9,
+           eps=0.1, other_eps=0.05, min_bound=0.0, part_down=0, part_hw=(0, 0), want_pix=False, out: SampleOut = None,
+           tables: RingTables = None):
     """rgbs/depth/t_wc/bbox: lists (one per object) of the keyframe ring tensors in the reference layout
-    (u8 [KF,W,H,4], f32 [KF,W,H], f32 [KF,4,4], f32 [KF,4]); part_frame int32 [n_obj,20] or None."""
-    n = len(rgbs)
+    (u8 [KF,W,H,4], f32 [KF,W,H], f32 [KF,4,4], f32 [KF,4]), or `tables`; part_frame int32 [n_obj,20] or None;
+    tapes: SampleTapes (explicit draws) or CounterRng (draws generated in the kernel)."""
+    n = tables.n if tables is not None else len(rgbs)
     dev = rays_dir.device
     W, H = rays_dir.shape[:2]
     n_rays = n_frames * n_samples
@@ -97,7 +120,8 @@ def sample(rgbs, depth, t_wc, bbox, part_frame, rays_dir, tapes: SampleTapes, n_
                         torch.empty(n, n_rays, dtype=torch.int32, device=dev) if part_frame is not None else None,
                         torch.empty(n, n_rays, 3, dtype=torch.int64, device=dev) if want_pix else None,
                         torch.zeros(1, dtype=torch.int32, device=dev))
-    tabs = [_ptr_table(x, dev) for x in (rgbs, depth, t_wc, bbox)]
+    tabs = ([tables.rgbs, tables.depth, tables.t_wc, tables.bbox] if tables is not None
+            else [_ptr_table(x, dev) for x in (rgbs, depth, t_wc, bbox)])
     lin = [torch_linspace01(S), torch_linspace01(n_c2s), torch_linspace01(n_bins)]
     a = SampleArgs()
     a.n_obj, a.n_frames, a.n_samples = n, n_frames, n_samples
@@ -107,13 +131,51 @@ def sample(rgbs, depth, t_wc, bbox, part_frame, rays_dir, tapes: SampleTapes, n_
     a.rgbs, a.depth, a.t_wc, a.bbox = [ptr(t) for t in tabs]
     a.part_frame = ptr(part_frame)
     a.rays_dir = ptr(rays_dir)
-    a.kf_ids, a.u_w, a.u_h = ptr(tapes.kf_ids), ptr(tapes.u_w), ptr(tapes.u_h)
-    a.r_invalid, a.r_valid, a.r_normal, a.r_other = (ptr(tapes.r_invalid), ptr(tapes.r_valid), ptr(tapes.r_normal),
-                                                     ptr(tapes.r_other))
-    a.tape_by_rank = int(tapes.by_rank)
+    if isinstance(tapes, CounterRng):
+        a.rng_mode, a.seed, a.frame = 1, int(tapes.seed), int(tapes.frame)
+        a.obj_ids, a.n_keyframes, a.latest = ptr(tapes.obj_ids), ptr(tapes.n_keyframes), ptr(tapes.latest)
+        a.tape_by_rank = 0
+    else:
+        a.rng_mode = 0
+        a.kf_ids, a.u_w, a.u_h = ptr(tapes.kf_ids), ptr(tapes.u_w), ptr(tapes.u_h)
+        a.r_invalid, a.r_valid, a.r_normal, a.r_other = (ptr(tapes.r_invalid), ptr(tapes.r_valid), ptr(tapes.r_normal),
+                                                         ptr(tapes.r_other))
+        a.tape_by_rank = int(tapes.by_rank)
     a.lin_s_host, a.lin_c2s_host, a.lin_bins_host = [ctypes.c_void_p(t.data_ptr()) for t in lin]
     a.gt_rgb, a.gt_depth, a.valid, a.labels = ptr(out.gt_rgb), ptr(out.gt_depth), ptr(out.valid), ptr(out.labels)
     a.pcs, a.z, a.feat_row, a.pix, a.oob_count = ptr(out.pcs), ptr(out.z), ptr(out.feat_row), ptr(out.pix), ptr(out.oob)
     with torch.cuda.device(dev):
         check(lib().oo_sample_rays(ctypes.byref(a), stream()), "oo_sample_rays")
     return out
+
+
+def counter_rng(objects, seed, frame, device):
+    ids = torch.tensor([o.obj_id for o in objects], dtype=torch.int32)
+    nkf = torch.tensor([o.n_keyframes for o in objects], dtype=torch.int32)
+    latest = torch.tensor([list(o.lastest_kf_queue)[-2:] if len(o.lastest_kf_queue) >= 2 else [0, 0]
+                           for o in objects], dtype=torch.int32)
+    pack = torch.cat([ids, nkf, latest.reshape(-1)]).to(device, non_blocking=True)     # one H2D copy
+    n = len(objects)
+    return CounterRng(seed, frame, pack[:n], pack[n:2 * n], pack[2 * n:].view(n, 2))
+
+
+def append_frame(rgb, depth, inst, t_wc, objects, slots, bboxes):
+    """One launch writes the new frame into ring slot slots[i] of objects[i] (rgb + per-object pixel state, depth,
+    pose, bbox).  rgb u8 [W,H,3], depth f32 [W,H], inst int32 [W,H], t_wc f32 [4,4] on the device; bboxes: list of
+    4-vectors (host)."""
+    dev = rgb.device
+    n = len(objects)
+    if n == 0:
+        return
+    W, H = depth.shape
+    ints = torch.tensor([[o.obj_id for o in objects], slots], dtype=torch.int32).to(dev, non_blocking=True)
+    bb = torch.stack([torch.as_tensor(b, dtype=torch.float32) for b in bboxes]).to(dev, non_blocking=True).contiguous()
+    tab = RingTables(objects, dev)
+    t = t_wc.to(torch.float32).contiguous()
+    a = AppendArgs()
+    a.W, a.H, a.n_obj = W, H, n
+    a.rgb, a.depth, a.inst, a.t_wc = ptr(rgb), ptr(depth), ptr(inst), ptr(t)
+    a.obj_id, a.slot, a.bbox = ptr(ints[0]), ptr(ints[1]), ptr(bb)
+    a.rgbs, a.depth_ring, a.t_wc_ring, a.bbox_ring = ptr(tab.rgbs), ptr(tab.depth), ptr(tab.t_wc), ptr(tab.bbox)
+    with torch.cuda.device(dev):
+        check(lib().oo_append_frame(ctypes.byref(a), stream()), "oo_append_frame")

@@ -46,7 +46,8 @@ class Scene:
             if self.frames_seen >= self.part_table.shape[0]:
                 raise RuntimeError("part-feature table full: raise max_frames")
             self.part_table[self.frames_seen].copy_(sample["part_feat"], non_blocking=True)   # train.py:183-188
-        unknown = (inst == -1).to(torch.uint8) * 2
+        twc32 = twc.to(torch.float32)
+        objs, slots, bboxes = [], [], []
         for obj_id in sorted(int(k) for k in sample["bbox_dict"].keys()):                 # torch.unique order (train.py:191)
             if obj_id == -1 or (cfg.do_bg and obj_id == 0):
                 continue               # the separate background model is not part of the vmap ensemble (train.py:236-242)
@@ -56,14 +57,18 @@ class Scene:
                 self.global_index[obj_id] = len(self.global_index)
             if self.global_index[obj_id] % self.world != self.rank:
                 continue
-            state = (inst == obj_id).to(torch.uint8) + unknown                             # train.py:203-205
             bbox = sample["bbox_dict"][obj_id]
             if obj_id in self.obj_dict:
-                self.obj_dict[obj_id].append_keyframe(rgb, depth, state, bbox, twc, frame_id)
+                o = self.obj_dict[obj_id]
+                slot = o.push_slot(frame_id)
             else:
-                c = cfg
-                self.obj_dict[obj_id] = vmap.sceneObject(c, obj_id, rgb, depth, state, bbox, twc, frame_id)
+                o = vmap.sceneObject(cfg, obj_id, rgb, depth, None, bbox, twc, frame_id, defer_write=True)
+                self.obj_dict[obj_id] = o
+                slot = 0
                 self._stale = True
+            objs.append(o); slots.append(slot); bboxes.append(bbox)
+        # pixel state (train.py:203-205) + ring writes of every visible object in ONE launch
+        sampler.append_frame(rgb, depth, inst, twc32, objs, slots, bboxes)
         self.frames_seen += 1
         if self._stale:
             self._rebuild_ensemble()
@@ -84,6 +89,7 @@ class Scene:
         new.params_changed()
         new.reset_optimizer()
         self.ens = new
+        self.tables = sampler.RingTables(objs, self.device)
         self._stale = False
 
     # ---- train.py:300-388 -----------------------------------------------------------------------------------
@@ -93,15 +99,18 @@ class Scene:
         n_frames = cfg.n_iter_per_frame * cfg.win_size
         n_samples = cfg.n_samples_per_frame
         o0 = objs[0]
-        tapes = sampler.device_tapes(objs, n_frames, n_samples, o0.n_bins_cam2surface, o0.n_bins, o0.surface_eps,
-                                     self.seed, self.frames_seen, self.device)
+        rng = sampler.counter_rng(objs, self.seed, self.frames_seen, self.device)
         part_frame = None
         if self.part_mode:
-            part_frame = torch.stack([o.part_frame_row() for o in objs]).to(self.device).contiguous()
-        out = sampler.sample([o.rgbs_batch for o in objs], [o.depth_batch for o in objs], [o.t_wc_batch for o in objs],
-                             [o.bbox for o in objs], part_frame, self.cam.rays_dir_cache, tapes, n_frames, n_samples,
+            import numpy as np
+            pf = np.stack([(o.use_frame / o.stride).astype(np.int64) for o in objs]).astype(np.int32)   # vmap.py:438-440
+            part_frame = torch.from_numpy(pf).to(self.device, non_blocking=True)
+        out = sampler.sample(None, None, None, None, part_frame, self.cam.rays_dir_cache, rng, n_frames, n_samples,
                              o0.n_bins_cam2surface, o0.n_bins, o0.surface_eps, o0.stop_eps, o0.min_bound,
-                             cfg.part_down if self.part_mode else 0, (self.pw, self.ph) if self.part_mode else (0, 0))
+                             cfg.part_down if self.part_mode else 0, (self.pw, self.ph) if self.part_mode else (0, 0),
+                             out=getattr(self, "sample_out", None) if getattr(self, "_out_n", -1) == len(objs) else None,
+                             tables=self.tables)
+        self._out_n = len(objs)
         table = self.part_table.view(-1, self.part_table.shape[-1]) if self.part_mode else None
         self.batch = FrameBatch(out.pcs, out.z, out.gt_depth, out.gt_rgb, out.labels, out.feat_row, table)
         self.sample_out = out

@@ -59,11 +59,12 @@ class SyntheticScene:
             if part_mode:
                 part = self.rng.standard_normal((W // part_down, H // part_down, clip), dtype=np.float32)
                 part[self.rng.random((W // part_down, H // part_down)) < 0.1] = 0.0
-            self._payload.append((image, depth, part))
+            self._payload.append(tuple(None if a is None else self._mk(a) for a in (image, depth, part)))
+        self.inst_t = self._mk(self.inst)
 
-    def _t(self, a):
+    def _mk(self, a):
         t = torch.from_numpy(a)
-        return t.pin_memory() if self.pin else t
+        return t.pin_memory() if self.pin else t       # pinned once, like a DataLoader with pin_memory=True
 
     def pose(self, f):
         ang = 0.02 * f
@@ -74,12 +75,13 @@ class SyntheticScene:
 
     def frame(self, f, stride=10):
         image, depth, part = self._payload[f % len(self._payload)]
-        s = {"image": self._t(image), "depth": self._t(depth), "T": self.pose(f), "obj": self._t(self.inst),
+        s = {"image": image, "depth": depth, "T": self.pose(f), "obj": self.inst_t,
              "bbox_dict": self.bbox, "frame_id": f * stride}
         if self.part_mode:
-            s["part_feat"] = self._t(part)
+            s["part_feat"] = part
         return s
 
     def frame_bytes(self):
         image, depth, part = self._payload[0]
-        return image.nbytes + depth.nbytes + self.inst.nbytes + 128 + (part.nbytes if part is not None else 0)
+        nb = lambda t: t.numel() * t.element_size()
+        return nb(image) + nb(depth) + self.inst.nbytes + 128 + (nb(part) if part is not None else 0)

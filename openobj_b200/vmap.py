@@ -60,8 +60,12 @@ class KeyframeRing:
 
 
 class sceneObject:
-    def __init__(self, cfg, obj_id, rgb, depth, mask, bbox_2d, t_wc, live_frame_id, clip_feat=None, caption_feat=None):
-        assert rgb.shape[:2] == depth.shape == mask.shape and bbox_2d.shape == (4,) and t_wc.shape == (4, 4)
+    def __init__(self, cfg, obj_id, rgb, depth, mask, bbox_2d, t_wc, live_frame_id, clip_feat=None, caption_feat=None,
+                 defer_write=False):
+        """`defer_write=True` (used by scene.Scene): allocate the rings but let the batched oo_append_frame launch write
+        slot 0 together with every other object's slot of this frame."""
+        assert rgb.shape[:2] == depth.shape and bbox_2d.shape == (4,) and t_wc.shape == (4, 4)
+        assert defer_write or rgb.shape[:2] == mask.shape
         self.do_bg, self.obj_id = cfg.do_bg, obj_id
         self.data_device, self.training_device = cfg.data_device, cfg.training_device
         self.part_mode, self.stride = cfg.part_mode, cfg.stride
@@ -89,7 +93,11 @@ class sceneObject:
             self.use_frame = np.zeros(K)
         self.other_obj, self.this_obj, self.unknown_obj = 0, 1, 2
         self.semantic_id = None
-        self._write_slot(0, rgb, depth, mask, bbox_2d, t_wc, live_frame_id)
+        if defer_write:
+            if self.part_mode:
+                self.use_frame[0] = live_frame_id
+        else:
+            self._write_slot(0, rgb, depth, mask, bbox_2d, t_wc, live_frame_id)
         tcfg = copy.deepcopy(cfg)
         tcfg.obj_id, tcfg.hidden_feature_size, tcfg.obj_scale = obj_id, self.hidden_feature_size, self.obj_scale
         self.trainer = trainer.Trainer(tcfg)
@@ -121,6 +129,14 @@ class sceneObject:
             self.clip_feat = np.vstack((self.clip_feat, clip_feat))
             self.caption_feat = np.vstack((self.caption_feat, caption_feat))
             self.feat_cnt += 1
+
+    def push_slot(self, frame_id):
+        """Keyframe policy only (vmap.py:166-257): returns the slot the caller must write (scene.Scene batches the
+        writes of all objects into one oo_append_frame launch)."""
+        s = self.ring.push(frame_id)
+        if self.part_mode:
+            self.use_frame[s] = frame_id
+        return s
 
     def prune_keyframe(self):
         return random.choice(list(self.ring.slot_of.items())[:-2])

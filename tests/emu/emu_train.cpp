@@ -19,7 +19,7 @@ namespace {
 template <int PH, int END, bool PART>
 struct Run {
     static void go(float* sm, const TileCtx& c, std::vector<TileAcc>& acc) {
-        for (int tid = 0; tid < NTHREADS; ++tid) tile_phase<PH, PART>(tid, sm, c, acc[tid]);
+        for (int tid = 0; tid < NTHREADS; ++tid) tile_phase<kTrainOrder[PH], PART>(tid, sm, c, acc[tid]);
         Run<PH + 1, END, PART>::go(sm, c, acc);
     }
 };

@@ -257,3 +257,88 @@ def test_reference_surface_modules():
     torch.testing.assert_close(e1, emb[1], rtol=0, atol=0)
     a1, c1, f1 = trs[1].fc_occ_map(e1)
     torch.testing.assert_close(a1, a[1], rtol=0, atol=0)
+
+
+def _small_scene(n_obj=5, W=100, H=60, frames=7):
+    from openobj_b200 import cfg as C
+    from openobj_b200.scene import Scene
+    from openobj_b200.synthetic import SyntheticScene
+    cfg = C.room0_config(w=W, h=H)
+    cfg.n_iter_per_frame = 4
+    cfg.do_bg = False
+    synth = SyntheticScene(n_obj, W=W, H=H, part_mode=True, seed=3, n_distinct=2)
+    sc = Scene(cfg, seed=77, max_frames=frames + 2)
+    return cfg, synth, sc
+
+
+def test_append_kernel_equals_reference_slot_writes():
+    """oo_append_frame (one launch, all objects) == sceneObject.__init__/append_keyframe's per-object slot writes."""
+    from openobj_b200 import vmap as V
+    cfg, synth, sc = _small_scene()
+    ref = {}
+    for f in range(7):
+        s = synth.frame(f)
+        sc.add_frame(s)
+        rgb, depth, inst = s["image"].to(DEV), s["depth"].to(DEV), s["obj"].to(DEV)
+        for oid, bbox in s["bbox_dict"].items():
+            state = (inst == oid).to(torch.uint8) + (inst == -1).to(torch.uint8) * 2
+            if oid not in ref:
+                ref[oid] = V.sceneObject(cfg, oid, rgb, depth, state, bbox, s["T"].to(DEV), s["frame_id"])
+            else:
+                ref[oid].append_keyframe(rgb, depth, state, bbox, s["T"].to(DEV), s["frame_id"])
+    torch.cuda.synchronize()
+    for oid, r in ref.items():
+        o = sc.obj_dict[oid]
+        n = r.n_keyframes
+        assert o.n_keyframes == n and o.lastest_kf_queue == r.lastest_kf_queue and dict(o.kf_id_dict) == dict(r.kf_id_dict)
+        assert torch.equal(o.rgbs_batch[:n], r.rgbs_batch[:n]) and torch.equal(o.depth_batch[:n], r.depth_batch[:n])
+        assert torch.equal(o.t_wc_batch[:n], r.t_wc_batch[:n]) and torch.equal(o.bbox[:n], r.bbox[:n])
+        assert (o.use_frame == r.use_frame).all()
+
+
+def test_in_kernel_rng_equals_tape_mode():
+    """rng_mode=1 (Philox evaluated inside K2) is bit-identical to tape mode fed by oo_rng_fill."""
+    from openobj_b200 import sampler
+    cfg, synth, sc = _small_scene()
+    for f in range(7):
+        sc.add_frame(synth.frame(f))
+    objs = list(sc.obj_dict.values())
+    n_frames, n_samples = 20, 24
+    o0 = objs[0]
+    tapes = sampler.device_tapes(objs, n_frames, n_samples, 1, 9, o0.surface_eps, 77, 5, DEV)
+    rng = sampler.counter_rng(objs, 77, 5, DEV)
+    args = ([o.rgbs_batch for o in objs], [o.depth_batch for o in objs], [o.t_wc_batch for o in objs], [o.bbox for o in objs])
+    pf = torch.stack([o.part_frame_row() for o in objs]).to(DEV).contiguous()
+    kw = dict(part_down=5, part_hw=(sc.pw, sc.ph), want_pix=True)
+    a = sampler.sample(*args, pf, sc.cam.rays_dir_cache, tapes, n_frames, n_samples, **kw)
+    b = sampler.sample(*args, pf, sc.cam.rays_dir_cache, rng, n_frames, n_samples, **kw)
+    for name in ("gt_rgb", "gt_depth", "valid", "labels", "pcs", "z", "feat_row", "pix"):
+        assert torch.equal(getattr(a, name), getattr(b, name)), name
+    # the forced latest two keyframes
+    for i, o in enumerate(objs):
+        if o.n_keyframes > 2:
+            assert b.pix[i, -2 * n_samples, 0].item() == o.lastest_kf_queue[-2] and b.pix[i, -1, 0].item() == o.lastest_kf_queue[-1]
+
+
+def test_scene_frames_train_and_alias_parameters():
+    """End-to-end frames through Scene (append -> sample -> 4 steps): losses finite and falling on a fixed batch, the
+    objects' nn.Parameters alias the ensemble buffer (write-back of train.py:478-485 is free), labels consistent."""
+    cfg, synth, sc = _small_scene()
+    n = 5
+    lt = torch.zeros(cfg.n_iter_per_frame, n, 4, device=DEV)
+    for f in range(6):
+        sc.step_frame(synth.frame(f), loss_terms=lt)
+    torch.cuda.synchronize()
+    assert torch.isfinite(lt).all()
+    o = list(sc.obj_dict.values())[2]
+    w = o.trainer.fc_occ_map.in_layer[0].weight
+    assert w.data_ptr() == sc.ens.stacked()[0][2].data_ptr()
+    before = w.detach().clone()
+    hist = []
+    for k in range(40):
+        sc.train(loss_terms=lt)
+        hist.append(float(sc.ens.total_loss(lt).mean().item()))
+    assert sum(hist[-3:]) < sum(hist[:3]) and not torch.equal(before, w.detach()), hist
+    lab = sc.batch.labels
+    assert int(lab.max()) <= 2 and int((lab == 1).sum()) > 0
+    assert int(sc.sample_out.oob.item()) == 0
