@@ -39,6 +39,8 @@ extern "C" {
 #define OO_EMB1 87             /* trainer.py:20 */
 #define OO_NSAMP 10            /* n_bins_cam2surface + n_bins (room_0.json:31-32) */
 #define OO_TILE_RAYS 10        /* rays one CTA tile processes */
+#define OO_DERIVED_FLOATS 1088
+#define OO_RAYREC_FLOATS 36
 
 /* flags written by oo_label_counts / oo_loss_* (reference: render_rays.py:89-94,109-111) */
 #define OO_FLAG_EXPLODE 1      /* some per-object loss term > 1e5: the reference prints and exit(-1)s */
@@ -99,7 +101,9 @@ typedef struct oo_batch {
 typedef struct oo_train_ws {   /* caller-allocated scratch; sizes from oo_train_ws_sizes() */
     float* slab;               /* [n_slots][OO_PSTRIDE] per-(CTA,object) gradient partials */
     float* slot_loss;          /* [n_slots][4] */
-    float* wocl_t;             /* [n_obj][32][512] transposed copy of out_clip.weight kept in sync by oo_adamw_step */
+    float* derived;            /* [n_cta][OO_DERIVED_FLOATS] per-CTA scratch: out_clip constants (W^T W, W^T b, b.b) of the object a CTA works on */
+    float* clip_grad;          /* [n_obj][512*32 + 512] out_clip.weight / .bias gradient assembled by K4a for K4b */
+    float* rayrec;             /* [n_obj][rays_per_step][OO_RAYREC_FLOATS] per-ray records K1 leaves for K4 (out_clip gradient) */
     int*   sched;              /* device copy of the static schedule */
     int*   counts;             /* [iters][n_obj][2] label==1 / label!=2 ray counts per step */
     int*   flags;              /* [iters] OO_FLAG_* per step (OR over objects; all-reduce across ranks when sharded) */
@@ -112,8 +116,6 @@ int oo_train_ws_sizes(int n_obj, int rays_per_step, int iters, int n_sm,
                       int* n_cta, int* n_slots, int64_t* slab_floats, int64_t* sched_ints);
 /* build the static ray-range schedule on the host and copy it to ws->sched (synchronous, once per ensemble rebuild). */
 int oo_train_schedule(int n_obj, int rays_per_step, int n_sm, oo_train_ws* ws, void* stream);
-/* refresh ws->wocl_t from theta (after the caller wrote parameters, e.g. utils.update_vmap). */
-int oo_sync_wocl_t(const float* theta, int n_obj, oo_train_ws* ws, void* stream);
 
 /* per frame: ray counts + zero-mask flags for every step (render_rays.py:88-94 evaluated up front),
  * then the Adam step/bias-correction schedule (torch.optim.AdamW bookkeeping, train.py:473).
@@ -141,7 +143,7 @@ int oo_train_frame(float* theta, float* adam_m, float* adam_v, int n_obj, const 
  * ncu captures use them too): K1 = fused encode/MLP/composite/loss/backward into ws->slab, K4 = slab reduction + AdamW. */
 int oo_train_k1(const float* theta, int n_obj, const oo_batch* batch, int it, int rays_per_step, float scale,
                 oo_train_ws* ws, int n_sm, void* stream);
-int oo_train_k4(float* theta, float* adam_m, float* adam_v, int n_obj, int it, int rays_per_step,
+int oo_train_k4(float* theta, float* adam_m, float* adam_v, int n_obj, const oo_batch* batch, int it, int rays_per_step,
                 float lr, float weight_decay, float beta1, float beta2, float eps,
                 oo_train_ws* ws, float* loss_terms, int n_sm, void* stream);
 

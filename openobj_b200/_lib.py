@@ -23,7 +23,7 @@ class Batch(Structure):
 
 
 class TrainWs(Structure):
-    _fields_ = [("slab", c_void_p), ("slot_loss", c_void_p), ("wocl_t", c_void_p), ("sched", c_void_p),
+    _fields_ = [("slab", c_void_p), ("slot_loss", c_void_p), ("derived", c_void_p), ("clip_grad", c_void_p), ("rayrec", c_void_p), ("sched", c_void_p),
                 ("counts", c_void_p), ("flags", c_void_p), ("adam_scal", c_void_p), ("adam_t", c_void_p)]
 
 
@@ -71,7 +71,6 @@ _SIGS = {
     "oo_train_ws_sizes": ([c_int, c_int, c_int, c_int, POINTER(c_int), POINTER(c_int), POINTER(c_int64),
                            POINTER(c_int64)], c_int),
     "oo_train_schedule": ([c_int, c_int, c_int, POINTER(TrainWs), c_void_p], c_int),
-    "oo_sync_wocl_t": ([c_void_p, c_int, POINTER(TrainWs), c_void_p], c_int),
     "oo_label_counts": ([c_void_p, c_int, c_int, c_int, c_int, c_void_p, c_void_p, c_void_p], c_int),
     "oo_adam_schedule": ([c_void_p, c_int, c_int, c_float, c_float, c_float, c_void_p, c_void_p, c_void_p], c_int),
     "oo_train_step": ([c_void_p, c_void_p, c_void_p, c_int, POINTER(Batch), c_int, c_int, c_float, c_float, c_float,
@@ -81,7 +80,7 @@ _SIGS = {
     "oo_train_frame": ([c_void_p, c_void_p, c_void_p, c_int, POINTER(Batch), c_int, c_int, c_float, c_float, c_float,
                         c_float, c_float, c_float, POINTER(TrainWs), c_void_p, c_int, c_void_p], c_int),
     "oo_train_k1": ([c_void_p, c_int, POINTER(Batch), c_int, c_int, c_float, POINTER(TrainWs), c_int, c_void_p], c_int),
-    "oo_train_k4": ([c_void_p, c_void_p, c_void_p, c_int, c_int, c_int, c_float, c_float, c_float, c_float, c_float,
+    "oo_train_k4": ([c_void_p, c_void_p, c_void_p, c_int, POINTER(Batch), c_int, c_int, c_float, c_float, c_float, c_float, c_float,
                      POINTER(TrainWs), c_void_p, c_int, c_void_p], c_int),
     "oo_adamw_flat": ([c_void_p, c_void_p, c_void_p, c_void_p, c_int64, c_int, c_float, c_float, c_float, c_float,
                        c_float, c_void_p], c_int),

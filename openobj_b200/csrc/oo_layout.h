@@ -107,14 +107,22 @@ constexpr int SM_RV = SM_UT + H * RP;                // ray values [24][12]
 constexpr int NRV = 24;
 constexpr int SM_UPART = SM_RV + NRV * RP;           // [8 warps][10][32] cross-warp partials of U
 constexpr int SM_COSP = SM_UPART;                    // cos partials [10][16][5] (dead before U is formed)
-constexpr int SM_FEAT = SM_UPART + 8 * RT * H;       // [10][512]
-constexpr int SM_TOTAL = SM_FEAT + RT * C;           // floats
+constexpr int SM_FEAT = SM_UPART + 8 * RT * H;       // Y [10][512]: gt part features of the tile's rays (cp.async in phase 0)
+constexpr int SM_YS = SM_FEAT + RT * C;              // gt-feature statistics: partials [10][16][2], totals [2][12]
+constexpr int SM_TOTAL = SM_YS + 352;                // floats
 // ray-value rows
 constexpr int V_DEPTH = 0, V_OPAC = 1, V_COL = 2, V_GD = 5, V_GO = 6, V_GC = 7, V_CF = 10, V_BG = 11,
               V_LD = 12, V_LC = 13, V_LO = 14, V_LF = 15, V_A = 16, V_B = 17, V_ZSRC = 18;
 
 static_assert(SM_TOTAL * 4 <= 232448, "tile does not fit in 227 KB of shared memory");
 static_assert(PS % 4 == 0 && SM_W % 4 == 0 && SM_RAY % 4 == 0 && SM_FEAT % 4 == 0, "float4 alignment");
+
+// per-object constants derived from the out_clip layer (k_gram): G = W^T W [32][32], wb = W^T b [32], bb = b.b
+constexpr int DER_G = 0, DER_WB = 1024, DER_BB = 1056, DERIVED = 1088;
+// per-ray record K1 leaves for K4 (out_clip gradient): A, opacity, S[32]
+constexpr int REC_A = 0, REC_OPAC = 1, REC_S = 4, RAYREC = 36;   // S 16-byte aligned
+// out_clip region of a gradient slab holds M = sum_r B_r S_r S_r^T [32][32], m = sum_r B_r opac_r S_r [32], beta = sum_r B_r opac_r^2
+constexpr int SLAB_M = OFF_OCL_W, SLAB_MV = OFF_OCL_W + 1024, SLAB_BETA = OFF_OCL_W + 1056;
 
 constexpr float PI_F = 3.14159274101257324f;         // float32(np.pi): embedding.py:52 multiplies in fp32
 

@@ -25,9 +25,16 @@
 #ifdef __CUDACC__
 #define OO_DEV __device__ __forceinline__
 #define OO_LDG(p) __ldg(p)
+// 16-byte asynchronous global -> shared copy (LDGSTS); completion awaited with OO_CP_ASYNC_WAIT before a barrier
+#define OO_CP_ASYNC16(dst, src)                                                                          \
+    asm volatile("cp.async.cg.shared.global [%0], [%1], 16;" ::"r"((unsigned)__cvta_generic_to_shared(dst)), "l"(src))
+#define OO_CP_ASYNC_WAIT() asm volatile("cp.async.wait_all;" ::: "memory")
 #else
 #define OO_DEV inline
 #define OO_LDG(p) (*(p))
+#define OO_CP_ASYNC16(dst, src) memcpy((dst), (src), 16)
+#define OO_CP_ASYNC_WAIT() ((void)0)
+#include <string.h>
 struct alignas(16) float4 {
     float x, y, z, w;
 };
@@ -50,6 +57,8 @@ struct TileAcc {
     float s0;        // out_color.weight (tid<96), out_alpha.weight (96<=tid<128)
     float s1;        // biases of the six hidden layers (tid<192), out_color.bias (192..194), out_alpha.bias (195)
     float s2;        // B_layer.weight (tid<63)
+    float gm[4];     // M = sum_r B_r S_r S_r^T, row tid/8, cols 4(tid%8)..+3   (out_clip gradient, see phase 13)
+    float s3;        // m = sum_r B_r opac_r S_r (tid<32), beta = sum_r B_r opac_r^2 (tid 32)
     float loss[4];   // per-ray loss partials (tid<10): depth, colour, opacity, feature
 };
 
@@ -58,7 +67,8 @@ OO_DEV void acc_zero(TileAcc& a) {
     for (int i = 0; i < 16; ++i) a.in[i] = a.cat[i] = a.m1[i] = a.m2[i] = 0.f;
 #pragma unroll
     for (int i = 0; i < 32; ++i) a.hd[i] = 0.f;
-    a.s0 = a.s1 = a.s2 = 0.f;
+    a.s0 = a.s1 = a.s2 = a.s3 = 0.f;
+    a.gm[0] = a.gm[1] = a.gm[2] = a.gm[3] = 0.f;
     a.loss[0] = a.loss[1] = a.loss[2] = a.loss[3] = 0.f;
 }
 
@@ -72,11 +82,11 @@ struct TileCtx {
     const int32_t* feat_row;   // [nrays] or nullptr
     const float* feat_table;   // [rows][512]
     const float* theta;        // this object's parameter block
-    const float* wocl_t;       // this object's out_clip.weight transposed [32][512]
+    const float* derived;      // this CTA's scratch holding the current object's G = W^T W, wb = W^T b, bb (gram_stage)
+    float* rayrec;             // [nrays][RAYREC] per-ray record for K4, first ray of the tile
     float* slab;               // gradient slab of the current (CTA, object) slot
     int nrays;                 // <= RT
     int npts;                  // valid points in the tile (nrays * S when training)
-    int first_tile;            // first tile of this slot: out_clip gradient is stored, not accumulated
     int flags;                 // OO_FLAG_NO_OBJ (2) / OO_FLAG_NO_SEM (4) for this step
     float scale;               // UniDirsEmbed scale
     float inv1, invs;          // 1/(n(label==1)+1e-10), 1/(n(label!=2)+1e-10) of this object in this step
@@ -267,6 +277,61 @@ OO_DEV void stage_weights(int tid, float* sm, const float* __restrict__ th) {
     }
 }
 
+// Per-object constants of the out_clip layer, computed by the CTA when it starts an object (no tile is in flight, so the
+// activation area is free): [W | b] (512 x 33, rows padded to 36 floats) is staged there with 16-byte async copies, then
+// G' = [W | b]^T [W | b] (33 x 33; G = W^T W, wb = W^T b, bb = b.b) is formed with 4x4 register tiles, the 512 rows split
+// over four thread groups whose partials are summed through shared memory.  Result -> this CTA's scratch `der` (global).
+constexpr int GS = 36;                       // row stride of the staged [W | b]
+constexpr int SM_GPART = 512 * GS;           // [4 groups][36 x 36] partial products (floats, inside the activation area)
+static_assert(SM_GPART + 4 * 36 * 36 <= SM_W, "gram staging must fit in the activation area");
+
+template <int STEP>
+OO_DEV void gram_stage(int tid, float* __restrict__ sm, const float* __restrict__ th, float* __restrict__ der) {
+    float* wst = sm + SM_ACT;
+    float* part = sm + SM_ACT + SM_GPART;
+    if constexpr (STEP == 0) {
+        for (int q = tid; q < C * (H / 4); q += NTHREADS) {                       // 4096 x 16 B
+            const int row = q >> 3, v4 = q & 7;
+            OO_CP_ASYNC16(wst + row * GS + 4 * v4, th + OFF_OCL_W + row * H + 4 * v4);
+        }
+        for (int row = tid; row < C; row += NTHREADS) {
+            wst[row * GS + H] = OO_LDG(th + OFF_OCL_B + row);
+            wst[row * GS + H + 1] = wst[row * GS + H + 2] = wst[row * GS + H + 3] = 0.f;
+        }
+        OO_CP_ASYNC_WAIT();
+    } else if constexpr (STEP == 1) {
+        // thread (group g = tid>>6, tile t = tid&63): 9 x 9 tiles of 4x4 cover 36 x 36; tiles 64..80 are taken by the
+        // first 17 threads of each group in a second pass
+        const int g = tid >> 6;
+        for (int t = tid & 63; t < 81; t += 64) {
+            const int k4 = 4 * (t / 9), j4 = 4 * (t % 9);
+            float acc[4][4];
+#pragma unroll
+            for (int x = 0; x < 4; ++x) acc[x][0] = acc[x][1] = acc[x][2] = acc[x][3] = 0.f;
+            const float* base = wst + (size_t)(128 * g) * GS;
+#pragma unroll 4
+            for (int cc = 0; cc < 128; ++cc) {
+                const float4 a4 = ld4(base + cc * GS + k4), b4 = ld4(base + cc * GS + j4);
+                acc[0][0] += a4.x * b4.x; acc[0][1] += a4.x * b4.y; acc[0][2] += a4.x * b4.z; acc[0][3] += a4.x * b4.w;
+                acc[1][0] += a4.y * b4.x; acc[1][1] += a4.y * b4.y; acc[1][2] += a4.y * b4.z; acc[1][3] += a4.y * b4.w;
+                acc[2][0] += a4.z * b4.x; acc[2][1] += a4.z * b4.y; acc[2][2] += a4.z * b4.z; acc[2][3] += a4.z * b4.w;
+                acc[3][0] += a4.w * b4.x; acc[3][1] += a4.w * b4.y; acc[3][2] += a4.w * b4.z; acc[3][3] += a4.w * b4.w;
+            }
+#pragma unroll
+            for (int x = 0; x < 4; ++x)
+                st4(part + g * 1296 + (k4 + x) * 36 + j4, float4{acc[x][0], acc[x][1], acc[x][2], acc[x][3]});
+        }
+    } else {
+        for (int q = tid; q < 33 * 33; q += NTHREADS) {
+            const int k = q / 33, j = q - 33 * k;
+            const float v = (part[k * 36 + j] + part[1296 + k * 36 + j]) + (part[2592 + k * 36 + j] + part[3888 + k * 36 + j]);
+            if (k < H && j < H) der[DER_G + k * H + j] = v;
+            else if (k < H) der[DER_WB + k] = v;            // column 32: W^T b
+            else if (j == H) der[DER_BB] = v;               // b . b
+        }
+    }
+}
+
 // zero the pad rows of e1 / e2 and the spare rows once per kernel
 OO_DEV void zero_pad_rows(int tid, float* sm) {
     for (int i = tid; i < PS; i += NTHREADS) {
@@ -283,10 +348,10 @@ OO_DEV void zero_pad_rows(int tid, float* sm) {
 // ------------------------------------------------------------------------------------------------
 // phases
 // ------------------------------------------------------------------------------------------------
-constexpr int N_TRAIN_PHASES = 34;
+constexpr int N_TRAIN_PHASES = 32;
 constexpr int N_FWD_PHASES = 8;    // phases 0..7 are shared with the standalone forward kernel
 // execution order of the training tile (phases 32..35 were split out of their neighbours later)
-constexpr int kTrainOrder[N_TRAIN_PHASES] = {0, 1, 2, 3, 4, 5, 6, 7, 33, 8, 9, 10, 11, 12, 32, 13, 14, 15, 16, 17, 18, 19,
+constexpr int kTrainOrder[N_TRAIN_PHASES] = {0, 1, 2, 3, 4, 5, 6, 7, 33, 8, 9, 10, 11, 12, 32, 13, 16, 17, 18, 19,
                                              20, 21, 22, 23, 24, 25, 26, 27, 28, 29, 30, 31};
 
 template <int PH, bool PART>
@@ -305,6 +370,18 @@ OO_DEV void tile_phase(int tid, float* __restrict__ sm, const TileCtx& c, TileAc
             const float t = x / c.scale;
             act[(R_T + ch) * PS + p] = t;
             act[(R_E1 + ch) * PS + p] = t;
+        }
+        if (PART) {
+            // gt part features of the tile's rays -> Y [10][512]; asynchronous, awaited at the end of phase 8
+            for (int i = tid; i < RT * (C / 4); i += NTHREADS) {
+                const int r = i / (C / 4), q = i - r * (C / 4);
+                float* dst = sm + SM_FEAT + r * C + 4 * q;
+                if (r < c.nrays) {
+                    OO_CP_ASYNC16(dst, c.feat_table + (size_t)OO_LDG(c.feat_row + r) * C + 4 * q);
+                } else {
+                    dst[0] = dst[1] = dst[2] = dst[3] = 0.f;
+                }
+            }
         }
     } else if constexpr (PH == 1) {
         // proj = B t ; e[3 + 21 k + d] = sin(pi * 2^k * proj) (embedding.py:48-53).  The reference's argument for band k
@@ -424,6 +501,7 @@ OO_DEV void tile_phase(int tid, float* __restrict__ sm, const TileCtx& c, TileAc
             rv[V_CF * RP + r] = cf;
             rv[V_BG * RP + r] = 0.f;
         }
+        if (PART) OO_CP_ASYNC_WAIT();      // Y rows issued in phase 0 are complete for this thread; the barrier publishes them
     } else if constexpr (PH == 9) {
         // S[j][r] = sum_i T_i hp_i[j]   (render of the clip-head hidden activations)
         if (PART) {
@@ -436,82 +514,101 @@ OO_DEV void tile_phase(int tid, float* __restrict__ sm, const TileCtx& c, TileAc
             }
         }
     } else if constexpr (PH == 10) {
-        // feat[r][c] = sum_j W_ocl[c][j] S[j][r] + b_ocl[c] * opacity_r   (== render(T, out_clip(hp)), loss.py:82)
+        // The rendered feature x_r = W S_r + b opac_r is never formed.  With per-object constants G = W^T W,
+        // wb = W^T b, bb = b.b (k_gram) the cosine loss and its gradient need only
+        //     v_r = W^T y_r,  yb_r = b.y_r,  yy_r = y_r.y_r        (y_r = gt feature row, staged in Y)
+        //   x.y = S.v + opac yb ;  x.x = S.(G S + opac wb) + opac (S.wb + opac bb) ;  dL/dS = A v + B (G S + opac wb).
         if (PART) {
-            float f[2][RT];
-            const int c0 = tid, c1 = tid + NTHREADS;
-            const float b0 = OO_LDG(c.theta + OFF_OCL_B + c0), b1 = OO_LDG(c.theta + OFF_OCL_B + c1);
+            {   // (a) v partials: warp wv owns features [64 wv, 64 wv + 64); lane = hidden unit j
+                const int wv = tid >> 5, j = tid & 31;
+                float v[RT];
 #pragma unroll
-            for (int r = 0; r < RT; ++r) {
-                const float op = rv[V_OPAC * RP + r];
-                f[0][r] = b0 * op;
-                f[1][r] = b1 * op;
-            }
-            float w0[H], w1[H];      // all 64 global loads are issued before the first use
+                for (int r = 0; r < RT; ++r) v[r] = 0.f;
+                const float* wocl = c.theta + OFF_OCL_W + (size_t)(wv * 64) * H + j;
+                float wq[64];            // 64 coalesced global loads in flight before the first use
 #pragma unroll
-            for (int j = 0; j < H; ++j) {
-                w0[j] = OO_LDG(c.wocl_t + j * C + c0);
-                w1[j] = OO_LDG(c.wocl_t + j * C + c1);
-            }
+                for (int q = 0; q < 64; ++q) wq[q] = OO_LDG(wocl + q * H);
 #pragma unroll
-            for (int j = 0; j < H; ++j) {
-                const float4 sa = ld4(sm + SM_ST + j * RP), sb = ld4(sm + SM_ST + j * RP + 4),
-                             sc = ld4(sm + SM_ST + j * RP + 8);
-                const float sv[RT] = {sa.x, sa.y, sa.z, sa.w, sb.x, sb.y, sb.z, sb.w, sc.x, sc.y};
+                for (int q = 0; q < 64; q += 4) {
 #pragma unroll
-                for (int r = 0; r < RT; ++r) {
-                    f[0][r] += w0[j] * sv[r];
-                    f[1][r] += w1[j] * sv[r];
+                    for (int r = 0; r < RT; ++r) {
+                        const float4 y = ld4(sm + SM_FEAT + r * C + wv * 64 + q);
+                        v[r] += y.x * wq[q] + y.y * wq[q + 1] + y.z * wq[q + 2] + y.w * wq[q + 3];
+                    }
                 }
-            }
 #pragma unroll
-            for (int r = 0; r < RT; ++r) {
-                sm[SM_FEAT + r * C + c0] = f[0][r];
-                sm[SM_FEAT + r * C + c1] = f[1][r];
+                for (int r = 0; r < RT; ++r) sm[SM_UPART + (wv * RT + r) * H + j] = v[r];
+            }
+            if (tid < RT * 16) {   // (b) partial y.b and y.y
+                const int r = tid >> 4, ch = tid & 15;
+                float bq[C / 16];
+#pragma unroll
+                for (int i = 0; i < C / 16; ++i) bq[i] = OO_LDG(c.theta + OFF_OCL_B + i * 16 + ch);
+                float yb = 0.f, yy = 0.f;
+#pragma unroll
+                for (int i = 0; i < C / 16; ++i) {
+                    const float yv = sm[SM_FEAT + r * C + i * 16 + ch];
+                    yb += yv * bq[i];
+                    yy += yv * yv;
+                }
+                sm[SM_YS + (r * 16 + ch) * 2] = yb;
+                sm[SM_YS + (r * 16 + ch) * 2 + 1] = yy;
             }
         }
     } else if constexpr (PH == 11) {
-        // partial dot products for the cosine loss (render_rays.py:75) and for b_ocl . g
         if (PART) {
-            if (tid < RT * 16) {
-                const int r = tid >> 4, ch = tid & 15;
-                const int rr = r < c.nrays ? r : 0;
-                const float* y = c.feat_table + (size_t)OO_LDG(c.feat_row + rr) * C;
-                float xy = 0.f, xx = 0.f, yy = 0.f, xb = 0.f, yb = 0.f;
-#pragma unroll 4
-                for (int i = 0; i < C / 16; ++i) {
-                    const int cc = i * 16 + ch;
-                    const float xv = sm[SM_FEAT + r * C + cc], yv = OO_LDG(y + cc), bv = OO_LDG(c.theta + OFF_OCL_B + cc);
-                    xy += xv * yv; xx += xv * xv; yy += yv * yv; xb += xv * bv; yb += yv * bv;
-                }
-                float* o = sm + SM_COSP + (r * 16 + ch) * 5;
-                o[0] = xy; o[1] = xx; o[2] = yy; o[3] = xb; o[4] = yb;
+            for (int i = tid; i < H * RT; i += NTHREADS) {      // v[j][r] -> SM_UT
+                const int r = i / H, j = i - r * H;
+                float v = 0.f;
+#pragma unroll
+                for (int wv = 0; wv < 8; ++wv) v += sm[SM_UPART + (wv * RT + r) * H + j];
+                sm[SM_UT + j * RP + r] = v;
             }
-        }
-    } else if constexpr (PH == 12) {
-        // (a) 50 threads: total of the 16 partials per (ray, quantity)
-        if (PART) {
-            if (tid < RT * 5) {
-                const int r = tid / 5, q = tid - 5 * r;
-                const float* o = sm + SM_COSP + r * 80 + q;
+            if (tid >= 128 && tid < 128 + 2 * RT) {             // totals of y.b and y.y
+                const int q = (tid - 128) / RT, r = (tid - 128) - q * RT;
                 float s0 = 0.f, s1 = 0.f;
 #pragma unroll
                 for (int ch = 0; ch < 16; ch += 2) {
-                    s0 += o[ch * 5];
-                    s1 += o[ch * 5 + 5];
+                    s0 += sm[SM_YS + (r * 16 + ch) * 2 + q];
+                    s1 += sm[SM_YS + (r * 16 + ch + 1) * 2 + q];
                 }
-                sm[SM_COSP + 800 + tid] = s0 + s1;
+                sm[SM_YS + 320 + q * RP + r] = s0 + s1;
+            }
+        }
+    } else if constexpr (PH == 12) {
+        // gs[j][r] = sum_k G[j][k] S[k][r] + opac_r wb[j]   (stored in the now free UPART area)
+        if (PART) {
+            for (int i = tid; i < H * RT; i += NTHREADS) {
+                const int r = i / H, j = i - r * H;
+                float g[H];
+#pragma unroll
+                for (int k = 0; k < H; ++k) g[k] = c.derived[DER_G + k * H + j];      // G is symmetric: coalesced over j
+                float acc = rv[V_OPAC * RP + r] * c.derived[DER_WB + j];
+#pragma unroll
+                for (int k = 0; k < H; ++k) acc += g[k] * sm[SM_ST + k * RP + r];
+                sm[SM_UPART + j * RP + r] = acc;
             }
         }
     } else if constexpr (PH == 32) {
-        // (b) 10 threads: cosine, loss partial, and the two coefficients of g = A*y + B*x
+        // per ray: cosine, loss partial, and the two coefficients of dL/dx = A y + B x
         if (PART) {
             if (tid < RT) {
                 const int r = tid;
-                const float* o = sm + SM_COSP + 800 + 5 * r;
-                const float xy = o[0], xx = o[1], yy = o[2], xb = o[3], yb = o[4];
+                const float opac = rv[V_OPAC * RP + r];
+                float sv = 0.f, swb = 0.f, sgs = 0.f;
+#pragma unroll 8
+                for (int j = 0; j < H; ++j) {
+                    const float sj = sm[SM_ST + j * RP + r];
+                    sv += sj * sm[SM_UT + j * RP + r];
+                    swb += sj * c.derived[DER_WB + j];
+                    sgs += sj * sm[SM_UPART + j * RP + r];
+                }
+                const float bb = c.derived[DER_BB];
+                const float yb = sm[SM_YS + 320 + r], yy = sm[SM_YS + 320 + RP + r];
+                const float xb = swb + opac * bb;                     // b . x
+                const float xy = sv + opac * yb, xx = sgs + opac * xb;
                 const float cf = rv[V_CF * RP + r];
-                const float nxr = sqrtf(xx), nyr = sqrtf(yy);
+                const float nxr = sqrtf(fmaxf(xx, 0.f)), nyr = sqrtf(yy);
                 const float nx = fmaxf(nxr, 1e-8f), ny = fmaxf(nyr, 1e-8f);   // F.cosine_similarity eps clamp
                 const float cosv = xy / (nx * ny);
                 float A = 0.f, B = 0.f;
@@ -523,99 +620,39 @@ OO_DEV void tile_phase(int tid, float* __restrict__ sm, const TileCtx& c, TileAc
                 }
                 rv[V_A * RP + r] = A;
                 rv[V_B * RP + r] = B;
-                rv[V_BG * RP + r] = A * yb + B * xb;       // b_ocl . g_r
+                rv[V_BG * RP + r] = A * yb + B * xb;       // b_ocl . dL/dx
             }
         }
     } else if constexpr (PH == 13) {
-        // g[r][c] = dL/dfeat, in place over feat
         if (PART) {
-            const int c0 = tid, c1 = tid + NTHREADS;
-#pragma unroll
-            for (int r = 0; r < RT; ++r) {
-                const float A = rv[V_A * RP + r], B = rv[V_B * RP + r];
-                float y0 = 0.f, y1 = 0.f;
-                if (A != 0.f) {
-                    const float* y = c.feat_table + (size_t)OO_LDG(c.feat_row + r) * C;
-                    y0 = OO_LDG(y + c0);
-                    y1 = OO_LDG(y + c1);
-                }
-                sm[SM_FEAT + r * C + c0] = A * y0 + B * sm[SM_FEAT + r * C + c0];
-                sm[SM_FEAT + r * C + c1] = A * y1 + B * sm[SM_FEAT + r * C + c1];
-            }
-        }
-    } else if constexpr (PH == 14) {
-        if (PART) {
-            // (a) U partials: warp wv owns features [64 wv, 64 wv + 64); lane = hidden unit j
-            {
-                const int wv = tid >> 5, j = tid & 31;
-                float u[RT];
-#pragma unroll
-                for (int r = 0; r < RT; ++r) u[r] = 0.f;
-                const float* wocl = c.theta + OFF_OCL_W + (size_t)(wv * 64) * H + j;
-                float wq[64];            // 64 coalesced global loads in flight before the first use
-#pragma unroll
-                for (int q = 0; q < 64; ++q) wq[q] = OO_LDG(wocl + q * H);
-#pragma unroll
-                for (int q = 0; q < 64; q += 4) {
-#pragma unroll
-                    for (int r = 0; r < RT; ++r) {
-                        const float4 g = ld4(sm + SM_FEAT + r * C + wv * 64 + q);
-                        u[r] += g.x * wq[q] + g.y * wq[q + 1] + g.z * wq[q + 2] + g.w * wq[q + 3];
-                    }
-                }
-#pragma unroll
-                for (int r = 0; r < RT; ++r) sm[SM_UPART + (wv * RT + r) * H + j] = u[r];
-            }
-            // (b) out_clip weight/bias gradient, accumulated in this slot's slab (transposed [j][c] like wocl_t)
-            {
-                const int c0 = tid, c1 = tid + NTHREADS;
-                float g0[RT], g1[RT];
-                float db0 = 0.f, db1 = 0.f;
-#pragma unroll
-                for (int r = 0; r < RT; ++r) {
-                    g0[r] = sm[SM_FEAT + r * C + c0];
-                    g1[r] = sm[SM_FEAT + r * C + c1];
-                    const float op = rv[V_OPAC * RP + r];
-                    db0 += g0[r] * op;
-                    db1 += g1[r] * op;
-                }
-                float* sw = c.slab + OFF_OCL_W;
-                float* sb = c.slab + OFF_OCL_B;
-                if (!c.first_tile) {
-                    db0 += sb[c0];
-                    db1 += sb[c1];
-                }
-                sb[c0] = db0;
-                sb[c1] = db1;
-                float d0[H], d1[H];
-#pragma unroll
-                for (int j = 0; j < H; ++j) {
-                    d0[j] = c.first_tile ? 0.f : sw[j * C + c0];
-                    d1[j] = c.first_tile ? 0.f : sw[j * C + c1];
-                }
-#pragma unroll
-                for (int j = 0; j < H; ++j) {
-                    const float4 sa = ld4(sm + SM_ST + j * RP), sb4 = ld4(sm + SM_ST + j * RP + 4),
-                                 sc = ld4(sm + SM_ST + j * RP + 8);
-                    const float sv[RT] = {sa.x, sa.y, sa.z, sa.w, sb4.x, sb4.y, sb4.z, sb4.w, sc.x, sc.y};
-#pragma unroll
-                    for (int r = 0; r < RT; ++r) {
-                        d0[j] += g0[r] * sv[r];
-                        d1[j] += g1[r] * sv[r];
-                    }
-                    sw[j * C + c0] = d0[j];
-                    sw[j * C + c1] = d1[j];
-                }
-            }
-        }
-    } else if constexpr (PH == 15) {
-        if (PART) {
+            // dL/dS -> SM_UT (in place over v); per-ray record for K4; M, m, beta accumulators of the out_clip gradient:
+            //   dW = sum_r (A_r y_r + B_r x_r) S_r^T = sum_r A_r y_r S_r^T + W M + b m^T,  M = sum_r B_r S_r S_r^T, m = sum_r B_r opac_r S_r
             for (int i = tid; i < H * RT; i += NTHREADS) {
                 const int r = i / H, j = i - r * H;
-                float u = 0.f;
+                sm[SM_UT + j * RP + r] = rv[V_A * RP + r] * sm[SM_UT + j * RP + r] + rv[V_B * RP + r] * sm[SM_UPART + j * RP + r];
+            }
+            for (int i = tid; i < c.nrays * (H + 2); i += NTHREADS) {
+                const int r = i / (H + 2), q = i - r * (H + 2);
+                if (q < 2) c.rayrec[r * RAYREC + q] = q == REC_A ? rv[V_A * RP + r] : rv[V_OPAC * RP + r];
+                else c.rayrec[r * RAYREC + REC_S + q - 2] = sm[SM_ST + (q - 2) * RP + r];
+            }
+            {
+                const int k = tid >> 3, j4 = 4 * (tid & 7);
 #pragma unroll
-                for (int wv = 0; wv < 8; ++wv) u += sm[SM_UPART + (wv * RT + r) * H + j];
-                sm[SM_UT + j * RP + r] = u;
+                for (int r = 0; r < RT; ++r) {
+                    const float bs = rv[V_B * RP + r] * sm[SM_ST + k * RP + r];
+                    a.gm[0] += bs * sm[SM_ST + (j4 + 0) * RP + r];
+                    a.gm[1] += bs * sm[SM_ST + (j4 + 1) * RP + r];
+                    a.gm[2] += bs * sm[SM_ST + (j4 + 2) * RP + r];
+                    a.gm[3] += bs * sm[SM_ST + (j4 + 3) * RP + r];
+                }
+            }
+            if (tid <= H) {
+#pragma unroll
+                for (int r = 0; r < RT; ++r) {
+                    const float bo = rv[V_B * RP + r] * rv[V_OPAC * RP + r];
+                    a.s3 += bo * (tid < H ? sm[SM_ST + tid * RP + r] : rv[V_OPAC * RP + r]);
+                }
             }
         }
     } else if constexpr (PH == 16) {
@@ -867,6 +904,10 @@ OO_DEV void tile_flush(int tid, float* __restrict__ sm, float* __restrict__ slab
             slab[OFF_A_B] = a.s1;
         }
         if (tid < NDIR * 3) slab[OFF_PE_B + tid] = a.s2;
+        if (PART) {
+            st4(slab + SLAB_M + 4 * tid, float4{a.gm[0], a.gm[1], a.gm[2], a.gm[3]});
+            if (tid <= H) slab[SLAB_MV + tid] = a.s3;     // m[0..31], beta at SLAB_MV + 32 == SLAB_BETA
+        }
         flush_partials32(tid, scratch, a.m1);
     } else if constexpr (STEP == 1) {
         for (int i = tid; i < H * H; i += NTHREADS)

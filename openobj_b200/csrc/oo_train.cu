@@ -13,7 +13,8 @@ namespace {
 
 struct TrainParams {
     const float* theta;
-    const float* wocl_t;
+    float* derived;        // [n_cta][DERIVED] per-CTA scratch
+    float* rayrec;         // [n_obj][R][RAYREC] (this step)
     oo_batch b;
     int ray0;              // first ray of this step inside each object's batch (it * rays_per_step)
     int R;                 // rays per object per step
@@ -74,12 +75,18 @@ __global__ void __launch_bounds__(NTHREADS, 1) k_train(const TrainParams prm) {
         if (obj != cur_obj) {
             cur_obj = obj;
             c.theta = prm.theta + (size_t)obj * PSTRIDE;
-            c.wocl_t = prm.wocl_t + (size_t)obj * (H * C);
+            c.derived = prm.derived + (size_t)blockIdx.x * DERIVED;
             c.slab = prm.slab + (size_t)slot * PSTRIDE;
             c.inv1 = 1.f / ((float)prm.counts[2 * obj] + 1e-10f);
             c.invs = 1.f / ((float)prm.counts[2 * obj + 1] + 1e-10f);
-            c.first_tile = 1;
             stage_weights(tid, sm, c.theta);
+            if (PART) {
+                float* der = prm.derived + (size_t)blockIdx.x * DERIVED;
+                gram_stage<0>(tid, sm, c.theta, der); __syncthreads();
+                gram_stage<1>(tid, sm, c.theta, der); __syncthreads();
+                gram_stage<2>(tid, sm, c.theta, der); __syncthreads();
+                zero_pad_rows(tid, sm);          // the staging used the activation area
+            }
             __syncthreads();
         }
         const size_t ray = (size_t)obj * prm.b.rays_per_obj + prm.ray0 + r0;
@@ -91,9 +98,9 @@ __global__ void __launch_bounds__(NTHREADS, 1) k_train(const TrainParams prm) {
         c.gt_rgb = prm.b.gt_rgb + ray * 3;
         c.labels = prm.b.labels + ray;
         c.feat_row = PART ? prm.b.feat_row + ray : nullptr;
+        c.rayrec = prm.rayrec + ((size_t)obj * prm.R + r0) * RAYREC;
 
         Phases<0, N_TRAIN_PHASES, PART>::run(tid, sm, c, acc, cyc);
-        c.first_tile = 0;
 
         const bool last_of_obj = (t + 1 == t_end) || ((t + 1) / prm.tiles_per_obj != obj);
         if (last_of_obj) {
@@ -181,13 +188,121 @@ __global__ void k_adam_schedule(const int* __restrict__ flags, int iters, int pa
     }
 }
 
-// ---- K4: sum the gradient slots of each object (fixed order) and apply AdamW in place; HBM-bound.
+// ---- K4a: out_clip gradient of each object from what K1 left:
+//   dW[c][j] = sum_r A_r y_r[c] S_r[j] + sum_k W[c][k] M[k][j] + b[c] m[j],   db[c] = sum_r A_r opac_r y_r[c] + W[c].m + b[c] beta
+struct ClipGrad {
+    const float* rayrec;       // [n_obj][R][RAYREC]
+    const int32_t* feat_row;   // batch feat_row + ray0 (this step), stride rays_per_obj per object
+    const float* feat_table;
+    int rays_per_obj, R;
+};
+
+__global__ void __launch_bounds__(512) k_clipgrad(const float* __restrict__ theta, const float* __restrict__ slab,
+                                                  const int* __restrict__ obj_slot, const ClipGrad cg,
+                                                  float* __restrict__ clip_grad) {
+    // grid = (4 chunks of 128 feature rows, n_obj).  Rays whose coefficient A_r is zero (label != 1, or the zero-mask rule)
+    // are compacted away first; then a [128 x n_act] x [n_act x 32] product with A_r y_r staged in shared memory.
+    extern __shared__ float sh[];          // [1088] M, m, beta ; [R] active list ; [R][RAYREC] records ; [R][128] y_r[c]
+    __shared__ int s_warp[33];
+    const int o = blockIdx.y, c_lo = 128 * blockIdx.x, tid = threadIdx.x, lane = tid & 31, wv = tid >> 5;
+    const int s0 = obj_slot[o], s1 = obj_slot[o + 1];
+    const int Rp = (cg.R + 3) & ~3;
+    int* act = reinterpret_cast<int*>(sh + DERIVED);
+    float* rec = sh + DERIVED + Rp;
+    float* ys = rec + (size_t)cg.R * RAYREC;
+    const float* src = cg.rayrec + (size_t)o * cg.R * RAYREC;
+    // this thread's out_clip row and bias: issued first, consumed last
+    const float* th = theta + (size_t)o * PSTRIDE;
+    const int cl = tid >> 2, j0 = 8 * (tid & 3), cc = c_lo + cl;
+    float wr[H];
+#pragma unroll
+    for (int k = 0; k < H; k += 4) {
+        const float4 w4 = __ldg(reinterpret_cast<const float4*>(th + OFF_OCL_W + cc * H + k));
+        wr[k] = w4.x; wr[k + 1] = w4.y; wr[k + 2] = w4.z; wr[k + 3] = w4.w;
+    }
+    const float bc = __ldg(th + OFF_OCL_B + cc);
+    for (int q = tid; q < 1057; q += 512) {            // slot totals, 4 independent loads per round trip
+        float t = 0.f;
+        for (int sl = s0; sl < s1; sl += 4) {
+            const float* p0 = slab + (size_t)sl * PSTRIDE + SLAB_M + q;
+            const float v0 = p0[0];
+            const float v1 = sl + 1 < s1 ? p0[PSTRIDE] : 0.f;
+            const float v2 = sl + 2 < s1 ? p0[2 * (size_t)PSTRIDE] : 0.f;
+            const float v3 = sl + 3 < s1 ? p0[3 * (size_t)PSTRIDE] : 0.f;
+            t += v0; t += v1; t += v2; t += v3;
+        }
+        sh[q] = t;
+    }
+    // ---- compaction of the active rays (order preserved: deterministic summation order)
+    int n_act = 0;
+    for (int base = 0; base < cg.R; base += 512) {
+        const int r = base + tid;
+        const bool a = r < cg.R && src[(size_t)r * RAYREC + REC_A] != 0.f;
+        const unsigned m = __ballot_sync(0xffffffffu, a);
+        if (lane == 0) s_warp[wv] = __popc(m);
+        __syncthreads();
+        int off = n_act;
+        for (int w = 0; w < wv; ++w) off += s_warp[w];
+        if (a) act[off + __popc(m & ((1u << lane) - 1u))] = r;
+        int tot = 0;
+        for (int w = 0; w < 16; ++w) tot += s_warp[w];
+        n_act += tot;
+        __syncthreads();
+    }
+    // ---- records and gt feature rows of the active rays
+    for (int q = tid; q < n_act * RAYREC; q += 512) {
+        const int i = q / RAYREC, e = q - i * RAYREC;
+        rec[q] = src[(size_t)act[i] * RAYREC + e];
+    }
+    {
+        const int cc = tid & 127, n_it = (n_act * 128 + 511) / 512;
+        for (int i0 = 0; i0 < n_it; i0 += 6) {
+            float v[6];
+#pragma unroll
+            for (int u = 0; u < 6; ++u) {
+                const int i = ((i0 + u) * 512 + tid) >> 7;
+                v[u] = i < n_act ? __ldg(cg.feat_table + (size_t)cg.feat_row[(size_t)o * cg.rays_per_obj + act[i]] * C + c_lo + cc) : 0.f;
+            }
+#pragma unroll
+            for (int u = 0; u < 6; ++u) {
+                const int i = ((i0 + u) * 512 + tid) >> 7;
+                if (i < n_act) ys[i * 128 + cc] = v[u];
+            }
+        }
+    }
+    __syncthreads();
+    float g[8] = {0.f, 0.f, 0.f, 0.f, 0.f, 0.f, 0.f, 0.f};
+    float gb = 0.f;
+#pragma unroll 4
+    for (int i = 0; i < n_act; ++i) {
+        const float ay = rec[i * RAYREC + REC_A] * ys[i * 128 + cl];
+        const float4 Sa = *reinterpret_cast<const float4*>(rec + i * RAYREC + REC_S + j0);
+        const float4 Sb = *reinterpret_cast<const float4*>(rec + i * RAYREC + REC_S + j0 + 4);
+        g[0] += ay * Sa.x; g[1] += ay * Sa.y; g[2] += ay * Sa.z; g[3] += ay * Sa.w;
+        g[4] += ay * Sb.x; g[5] += ay * Sb.y; g[6] += ay * Sb.z; g[7] += ay * Sb.w;
+        gb += ay * rec[i * RAYREC + REC_OPAC];
+    }
+    float wm = 0.f;
+#pragma unroll
+    for (int k = 0; k < H; ++k) {
+        const float* M = sh + k * H + j0;
+#pragma unroll
+        for (int q = 0; q < 8; ++q) g[q] += wr[k] * M[q];
+        wm += wr[k] * sh[1024 + k];
+    }
+    float* out = clip_grad + (size_t)o * (C * H + C);
+#pragma unroll
+    for (int q = 0; q < 8; ++q) out[cc * H + j0 + q] = g[q] + bc * sh[1024 + j0 + q];
+    if ((tid & 3) == 0) out[C * H + cc] = gb + wm + bc * sh[1056];
+}
+
+// ---- K4b: sum the gradient slots of each object (fixed order) and apply AdamW in place; HBM-bound.
 // grid = (PSTRIDE/4/256, n_obj); thread = 4 consecutive parameters of one object.
 template <bool UPDATE>
 __global__ void __launch_bounds__(256) k_adamw(float* __restrict__ theta, float* __restrict__ am, float* __restrict__ av,
                                                const float* __restrict__ slab, const int* __restrict__ obj_slot,
                                                const float* __restrict__ scal, float decay, float b1, float b2, float eps,
-                                               float* __restrict__ wocl_t, const float* __restrict__ slot_loss,
+                                               const float* __restrict__ clip_grad, const float* __restrict__ slot_loss,
                                                const int* __restrict__ counts, float* __restrict__ loss_terms,
                                                float* __restrict__ grads_out) {
     const int o = blockIdx.y;
@@ -204,30 +319,37 @@ __global__ void __launch_bounds__(256) k_adamw(float* __restrict__ theta, float*
     const int grp = group_of_offset(i);
     const bool active = scal[grp * 4] != 0.f;
     float4 g = {0.f, 0.f, 0.f, 0.f};
-    const bool tr = i >= OFF_OCL_W && i < OFF_OCL_B;
-    const int cc = (i - OFF_OCL_W) / H, j0 = (i - OFF_OCL_W) % H;   // valid when tr
+    const size_t idx = (size_t)o * PSTRIDE + i;
+    float4 p = {0.f, 0.f, 0.f, 0.f}, m = p, v = p;
+    if (UPDATE && active) {                       // issued before the gradient loads: all independent
+        p = *reinterpret_cast<const float4*>(theta + idx);
+        m = *reinterpret_cast<const float4*>(am + idx);
+        v = *reinterpret_cast<const float4*>(av + idx);
+    }
     if (active) {
-        for (int q = s0; q < s1; ++q) {
-            const float* sp = slab + (size_t)q * PSTRIDE;
-            if (tr) {
-                const float* t = sp + OFF_OCL_W + j0 * C + cc;
-                g.x += t[0]; g.y += t[C]; g.z += t[2 * C]; g.w += t[3 * C];
-            } else {
-                const float4 v = *reinterpret_cast<const float4*>(sp + i);
-                g.x += v.x; g.y += v.y; g.z += v.z; g.w += v.w;
+        if (i >= OFF_OCL_W && i < OFF_OCL_B + C) {
+            if (clip_grad != nullptr) g = *reinterpret_cast<const float4*>(clip_grad + (size_t)o * (C * H + C) + (i - OFF_OCL_W));
+        } else {
+            const float4 z4 = {0.f, 0.f, 0.f, 0.f};
+            for (int q = s0; q < s1; q += 4) {    // slots summed in order, 4 loads per round trip
+                const float* sp = slab + (size_t)q * PSTRIDE + i;
+                const float4 v0 = *reinterpret_cast<const float4*>(sp);
+                const float4 v1 = q + 1 < s1 ? *reinterpret_cast<const float4*>(sp + PSTRIDE) : z4;
+                const float4 v2 = q + 2 < s1 ? *reinterpret_cast<const float4*>(sp + 2 * (size_t)PSTRIDE) : z4;
+                const float4 v3 = q + 3 < s1 ? *reinterpret_cast<const float4*>(sp + 3 * (size_t)PSTRIDE) : z4;
+                g.x += v0.x; g.y += v0.y; g.z += v0.z; g.w += v0.w;
+                g.x += v1.x; g.y += v1.y; g.z += v1.z; g.w += v1.w;
+                g.x += v2.x; g.y += v2.y; g.z += v2.z; g.w += v2.w;
+                g.x += v3.x; g.y += v3.y; g.z += v3.z; g.w += v3.w;
             }
         }
     }
-    const size_t idx = (size_t)o * PSTRIDE + i;
     if (!UPDATE) {
         *reinterpret_cast<float4*>(grads_out + idx) = g;
         return;
     }
     if (!active) return;
     const float step = scal[grp * 4 + 1], bc2s = scal[grp * 4 + 2];
-    float4 p = *reinterpret_cast<float4*>(theta + idx);
-    float4 m = *reinterpret_cast<float4*>(am + idx);
-    float4 v = *reinterpret_cast<float4*>(av + idx);
 #define OO_ADAM1(P, M, V, G)                               \
     {                                                      \
         P = P * decay;                                     \
@@ -244,18 +366,6 @@ __global__ void __launch_bounds__(256) k_adamw(float* __restrict__ theta, float*
     *reinterpret_cast<float4*>(theta + idx) = p;
     *reinterpret_cast<float4*>(am + idx) = m;
     *reinterpret_cast<float4*>(av + idx) = v;
-    if (tr) {
-        float* t = wocl_t + (size_t)o * (H * C) + j0 * C + cc;
-        t[0] = p.x; t[C] = p.y; t[2 * C] = p.z; t[3 * C] = p.w;
-    }
-}
-
-__global__ void k_wocl_t(const float* __restrict__ theta, float* __restrict__ wocl_t) {
-    const int o = blockIdx.y;
-    const int i = blockIdx.x * blockDim.x + threadIdx.x;     // index into [32][512]
-    if (i >= H * C) return;
-    const int j = i / C, cc = i - j * C;
-    wocl_t[(size_t)o * (H * C) + i] = theta[(size_t)o * PSTRIDE + OFF_OCL_W + cc * H + j];
 }
 
 __global__ void k_adamw_flat(float* __restrict__ p, const float* __restrict__ g, float* __restrict__ m,
@@ -273,7 +383,7 @@ __global__ void k_adamw_flat(float* __restrict__ p, const float* __restrict__ g,
 int check_train_args(int n_obj, const oo_batch* b, int rays_per_step, const oo_train_ws* ws) {
     OO_REQUIRE(n_obj > 0 && b && ws, "oo_train: null argument / n_obj <= 0");
     OO_REQUIRE(rays_per_step > 0 && b->rays_per_obj >= rays_per_step, "oo_train: bad rays_per_step");
-    OO_REQUIRE(ws->slab && ws->slot_loss && ws->sched && ws->counts && ws->flags && ws->adam_scal,
+    OO_REQUIRE(ws->slab && ws->slot_loss && ws->sched && ws->counts && ws->flags && ws->adam_scal && ws->derived && ws->rayrec && ws->clip_grad,
                "oo_train: workspace not allocated");
     return 0;
 }
@@ -286,7 +396,8 @@ int launch_k1(const float* theta, int n_obj, const oo_batch* b, int it, int R, f
     const int n_cta = (int)(T < n_sm ? T : n_sm);
     TrainParams prm;
     prm.theta = theta;
-    prm.wocl_t = ws->wocl_t;
+    prm.derived = ws->derived;
+    prm.rayrec = ws->rayrec;
     prm.b = *b;
     prm.ray0 = it * R;
     prm.R = R;
@@ -341,13 +452,6 @@ extern "C" int oo_train_schedule(int n_obj, int rays_per_step, int n_sm, oo_trai
     return 0;
 }
 
-extern "C" int oo_sync_wocl_t(const float* theta, int n_obj, oo_train_ws* ws, void* stream) {
-    OO_REQUIRE(theta && ws && ws->wocl_t, "oo_sync_wocl_t: null argument");
-    k_wocl_t<<<dim3((H * C + 255) / 256, n_obj), 256, 0, (cudaStream_t)stream>>>(theta, ws->wocl_t);
-    OO_LAUNCH_CHECK();
-    return 0;
-}
-
 extern "C" int oo_label_counts(const uint8_t* labels, int n_obj, int rays_per_obj, int rays_per_step, int iters,
                                int* counts, int* flags, void* stream) {
     OO_REQUIRE(labels && counts && flags && iters > 0, "oo_label_counts: null argument");
@@ -367,21 +471,41 @@ extern "C" int oo_adam_schedule(const int* flags, int iters, int part_on, float 
     return 0;
 }
 
-static int launch_k4(float* theta, float* am, float* av, int n_obj, int it, int R, float lr, float wd, float b1, float b2,
-                     float eps, oo_train_ws* ws, float* loss_terms, float* grads_out, int n_sm, cudaStream_t st) {
+static int launch_k4(float* theta, float* am, float* av, int n_obj, const oo_batch* b, int it, int R, float lr, float wd,
+                     float b1, float b2, float eps, oo_train_ws* ws, float* loss_terms, float* grads_out, int n_sm,
+                     cudaStream_t st) {
     const long long T = (long long)n_obj * tiles_per_object(R);
     const int n_cta = (int)(T < n_sm ? T : n_sm);
     const int* obj_slot = ws->sched + 2 * n_cta + 1;
     const dim3 grid(PSTRIDE / 4 / 256, n_obj);
     const float* scal = ws->adam_scal + (size_t)it * 12;
     const int* counts = ws->counts + (size_t)it * n_obj * 2;
+    const bool part = b && b->feat_row;
+    if (part) {
+        ClipGrad cg;
+        cg.rayrec = ws->rayrec;
+        cg.feat_row = b->feat_row + (size_t)it * R;
+        cg.feat_table = b->feat_table;
+        cg.rays_per_obj = b->rays_per_obj;
+        cg.R = R;
+        const size_t smem = (size_t)(DERIVED + ((R + 3) & ~3) + (size_t)R * RAYREC + (size_t)R * 128) * sizeof(float);
+        OO_REQUIRE(smem <= 200 * 1024, "oo_train: rays_per_step too large for the out_clip gradient kernel's staging buffer");
+        static size_t attr_smem = 0;
+        if (smem > attr_smem) {
+            OO_CUDA(cudaFuncSetAttribute(k_clipgrad, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+            attr_smem = smem;
+        }
+        k_clipgrad<<<dim3(C / 128, n_obj), 512, smem, st>>>(theta, ws->slab, obj_slot, cg, ws->clip_grad);
+        OO_LAUNCH_CHECK();
+    }
+    const float* cgrad = part ? ws->clip_grad : nullptr;
     if (grads_out) {
-        k_adamw<false><<<grid, 256, 0, st>>>(nullptr, nullptr, nullptr, ws->slab, obj_slot, scal, 0.f, 0.f, 0.f, 0.f,
-                                             nullptr, ws->slot_loss, counts, loss_terms, grads_out);
+        k_adamw<false><<<grid, 256, 0, st>>>(theta, nullptr, nullptr, ws->slab, obj_slot, scal, 0.f, 0.f, 0.f, 0.f, cgrad,
+                                             ws->slot_loss, counts, loss_terms, grads_out);
     } else {
         const float decay = (float)(1.0 - (double)lr * (double)wd);
-        k_adamw<true><<<grid, 256, 0, st>>>(theta, am, av, ws->slab, obj_slot, scal, decay, b1, b2, eps, ws->wocl_t,
-                                            ws->slot_loss, counts, loss_terms, nullptr);
+        k_adamw<true><<<grid, 256, 0, st>>>(theta, am, av, ws->slab, obj_slot, scal, decay, b1, b2, eps, cgrad, ws->slot_loss,
+                                            counts, loss_terms, nullptr);
     }
     OO_LAUNCH_CHECK();
     return 0;
@@ -393,7 +517,7 @@ static int train_step_impl(float* theta, float* am, float* av, int n_obj, const 
     if (int rc = check_train_args(n_obj, b, R, ws)) return rc;
     OO_REQUIRE((long long)(it + 1) * R <= b->rays_per_obj, "oo_train: step %d exceeds the pre-sampled batch", it);
     if (int rc = launch_k1(theta, n_obj, b, it, R, scale, ws, n_sm, st)) return rc;
-    return launch_k4(theta, am, av, n_obj, it, R, lr, wd, b1, b2, eps, ws, loss_terms, grads_out, n_sm, st);
+    return launch_k4(theta, am, av, n_obj, b, it, R, lr, wd, b1, b2, eps, ws, loss_terms, grads_out, n_sm, st);
 }
 
 extern "C" int oo_train_k1(const float* theta, int n_obj, const oo_batch* batch, int it, int rays_per_step, float scale,
@@ -404,12 +528,12 @@ extern "C" int oo_train_k1(const float* theta, int n_obj, const oo_batch* batch,
     return launch_k1(theta, n_obj, batch, it, rays_per_step, scale, ws, n_sm, (cudaStream_t)stream);
 }
 
-extern "C" int oo_train_k4(float* theta, float* adam_m, float* adam_v, int n_obj, int it, int rays_per_step, float lr,
-                           float weight_decay, float beta1, float beta2, float eps, oo_train_ws* ws, float* loss_terms,
-                           int n_sm, void* stream) {
-    OO_REQUIRE(theta && adam_m && adam_v && ws && ws->slab, "oo_train_k4: null argument");
-    return launch_k4(theta, adam_m, adam_v, n_obj, it, rays_per_step, lr, weight_decay, beta1, beta2, eps, ws, loss_terms,
-                     nullptr, n_sm, (cudaStream_t)stream);
+extern "C" int oo_train_k4(float* theta, float* adam_m, float* adam_v, int n_obj, const oo_batch* batch, int it,
+                           int rays_per_step, float lr, float weight_decay, float beta1, float beta2, float eps,
+                           oo_train_ws* ws, float* loss_terms, int n_sm, void* stream) {
+    OO_REQUIRE(theta && adam_m && adam_v && batch && ws && ws->slab, "oo_train_k4: null argument");
+    return launch_k4(theta, adam_m, adam_v, n_obj, batch, it, rays_per_step, lr, weight_decay, beta1, beta2, eps, ws,
+                     loss_terms, nullptr, n_sm, (cudaStream_t)stream);
 }
 
 extern "C" int oo_train_step(float* theta, float* adam_m, float* adam_v, int n_obj, const oo_batch* batch, int it,

@@ -82,13 +82,15 @@ class Ensemble:
             self.n_cta, self.n_slots = n_cta.value, n_slots.value
             self._slab = torch.zeros(slab_f.value, **f32)
             self._slot_loss = torch.zeros(self.n_slots * 4, **f32)
-            self._wocl_t = torch.zeros(self.n_obj, layout.HIDDEN, layout.CLIP, **f32)
+            self._derived = torch.zeros(self.n_cta, 1088, **f32)          # OO_DERIVED_FLOATS per CTA
+            self._clip_grad = torch.zeros(self.n_obj, 512 * 32 + 512, **f32)
+            self._rayrec = torch.zeros(self.n_obj, self.R, 36, **f32)      # OO_RAYREC_FLOATS
             self._sched = torch.zeros(sched_i.value, **i32)
             self.counts = torch.zeros(self.iters, self.n_obj, 2, **i32)
             self.flags = torch.zeros(self.iters, **i32)
             self._adam_scal = torch.zeros(self.iters, 3, 4, **f32)
             self.adam_t = torch.zeros(3, **i32)
-            self.ws = TrainWs(ptr(self._slab), ptr(self._slot_loss), ptr(self._wocl_t), ptr(self._sched),
+            self.ws = TrainWs(ptr(self._slab), ptr(self._slot_loss), ptr(self._derived), ptr(self._clip_grad), ptr(self._rayrec), ptr(self._sched),
                               ptr(self.counts), ptr(self.flags), ptr(self._adam_scal), ptr(self.adam_t))
             check(self.L.oo_train_schedule(self.n_obj, self.R, self.n_sm, ctypes.byref(self.ws), stream()),
                   "oo_train_schedule")
@@ -104,9 +106,9 @@ class Ensemble:
         self.params_changed()
 
     def params_changed(self):
-        """Call after writing theta from outside (keeps the transposed out_clip copy in sync)."""
-        with torch.cuda.device(self.device):
-            check(self.L.oo_sync_wocl_t(ptr(self.theta), self.n_obj, ctypes.byref(self.ws), stream()), "oo_sync_wocl_t")
+        """Kept for callers that write theta from outside: nothing derived from the parameters is cached any more
+        (K1 recomputes the out_clip constants when it starts an object)."""
+        return None
 
     def reset_optimizer(self):
         """Adam moments and step counters restart whenever the ensemble is rebuilt."""
@@ -162,9 +164,10 @@ class Ensemble:
         check(self.L.oo_train_k1(ptr(self.theta), self.n_obj, ctypes.byref(batch_c), it, self.R, self.scale,
                                  ctypes.byref(self.ws), self.n_sm, stream()), "oo_train_k1")
 
-    def k4(self, it, loss_terms=None):
-        """K4 alone (slab reduction + AdamW)."""
-        check(self.L.oo_train_k4(ptr(self.theta), ptr(self.m), ptr(self.v), self.n_obj, it, self.R, self.lr, self.wd,
+    def k4(self, batch_c, it, loss_terms=None):
+        """K4 alone (slab reduction + out_clip gradient assembly + AdamW + derived-constant refresh)."""
+        check(self.L.oo_train_k4(ptr(self.theta), ptr(self.m), ptr(self.v), self.n_obj, ctypes.byref(batch_c), it, self.R,
+                                 self.lr, self.wd,
                                  self.betas[0], self.betas[1], self.eps, ctypes.byref(self.ws), ptr(loss_terms), self.n_sm,
                                  stream()), "oo_train_k4")
 

@@ -8,6 +8,8 @@ from test_train_gpu import synth_batch
 N, R, I = 8, 120, 3
 pcs, z, gt_depth, rgb8, labels, gt_feat = synth_batch(N, R * I, seed=N, feat=True)
 fc, B = oc.init_params(N, generator=torch.Generator().manual_seed(100 + N))
+fc[8] *= 0.3
+fc[9] *= 0.3
 ens = Ensemble(N, rays_per_step=R, iters_per_frame=I)
 ens.load_stacked(fc + [B])
 dev = "cuda:0"
