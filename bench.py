@@ -171,7 +171,7 @@ def run_ours(args):
     frames_w = (warmup + ITERS - 1) // ITERS
     frames_t = (steps + ITERS - 1) // ITERS
     fill = args.fill_frames
-    n_frames_total = fill + 2 * (frames_w + frames_t) + 2
+    n_frames_total = fill + 2 * (frames_w + frames_t) + 12
     # every rank sees the same frames; object ids are spread so that rank r owns ids with (index % world == r)
     synth = SyntheticScene(n_local * world, W=cfg.W, H=cfg.H, part_mode=cfg.part_mode, seed=0, pin=True, n_distinct=2)
     scene = Scene(cfg, rank=rank, world=world, seed=1234, max_frames=n_frames_total, flag_allreduce=D.make_flag_allreduce())
@@ -273,6 +273,20 @@ def run_ours(args):
         k4_avg = sum(a.elapsed_time(b) for a, b in evs4) / ITERS
         k4_bytes = n_obj * 30659 * 24 + ens.n_slots * 30659 * 4 + (n_obj * 16384 * 4 if cfg.part_mode else 0)
         hbm_peak = peaks.get("hbm_gbs", 6650.0)
+        # per-frame HBM kernels: K2 sampling (all objects, one launch) and the keyframe append
+        ev_s = [cuda_timer() for _ in range(5)]
+        ev_a = [cuda_timer() for _ in range(5)]
+        for j in range(5):
+            s_dev = to_dev(synth.frame(f + j))
+            torch.cuda.synchronize()
+            ev_a[j][0].record(); scene.add_frame(s_dev); ev_a[j][1].record()
+            ev_s[j][0].record(); scene.sample(); ev_s[j][1].record()
+        torch.cuda.synchronize()
+        t_append = sorted(a.elapsed_time(b) for a, b in ev_a)[2]
+        t_sample = sorted(a.elapsed_time(b) for a, b in ev_s)[2]
+        rays_frame = n_obj * ITERS * R
+        sample_bytes = rays_frame * (180 + 4)
+        append_bytes = n_obj * cfg.W * cfg.H * 8 + cfg.W * cfg.H * 11 + (synth.frame_bytes() - cfg.W * cfg.H * 11) * 2
         cpu = cpu_reference_run(8, cfg.part_mode, steps=10 ** 6, warmup=1, time_budget_s=15.0) if not args.no_cpu else None
         out = {
             "metric": "training rays/sec for N-object ensemble", "value": rays / (ms * 1e-3), "unit": "rays/s",
@@ -295,7 +309,14 @@ def run_ours(args):
                                         "holds only HBM and bf16 tensor peaks; K1 is an FP32 FMA-pipe kernel)",
                          "k1_ms_avg": k1_avg, "k1_ms_min": k1_ms[0], "flop_per_launch": flop_launch,
                          "bf16_tensor_peak_for_context": peaks.get("bf16_tflops")},
-            "roofline_hbm": {"kernel": "k_adamw (K4 slab reduction + AdamW)", "bound": "hbm",
+            "roofline_sampling": {"kernel": "k_sample (K2, all objects in one launch; median of 5 frames incl. host-side table upload)",
+                                  "bound": "hbm", "achieved": sample_bytes / (t_sample * 1e-3) / 1e9, "peak": hbm_peak,
+                                  "unit": "GB/s", "frac": sample_bytes / (t_sample * 1e-3) / 1e9 / hbm_peak, "ms": t_sample,
+                                  "bytes_per_launch": sample_bytes, "rays_per_s": rays_frame / (t_sample * 1e-3)},
+            "roofline_append": {"kernel": "k_append + part-feature copy (per frame)", "bound": "hbm",
+                                "achieved": append_bytes / (t_append * 1e-3) / 1e9, "peak": hbm_peak, "unit": "GB/s",
+                                "frac": append_bytes / (t_append * 1e-3) / 1e9 / hbm_peak, "ms": t_append},
+            "roofline_hbm": {"kernel": "K4 = k_clipgrad (out_clip gradient assembly) + k_adamw (slab reduction + AdamW)", "bound": "hbm",
                              "achieved": k4_bytes / (k4_avg * 1e-3) / 1e9, "peak": hbm_peak, "unit": "GB/s",
                              "frac": k4_bytes / (k4_avg * 1e-3) / 1e9 / hbm_peak, "k4_ms_avg": k4_avg, "bytes_per_launch": k4_bytes,
                              "peak_source": "MEASURED_PEAKS.json hbm_gbs" if "hbm_gbs" in peaks else "fallback 6.65 TB/s"},
@@ -306,6 +327,8 @@ def run_ours(args):
                                              "%d steps in %.1f s" % (n_obj, cpu["steps_done"], cpu["seconds"])}
         print(json.dumps(out))
     D.barrier()
+    if world > 1:
+        torch.distributed.destroy_process_group()
     return 0
 
 
