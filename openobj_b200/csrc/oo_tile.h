@@ -289,11 +289,13 @@ template <int STEP>
 OO_DEV void gram_stage(int tid, float* __restrict__ sm, const float* __restrict__ th, float* __restrict__ der) {
     float* wst = sm + SM_ACT;
     float* part = sm + SM_ACT + SM_GPART;
-    if constexpr (STEP == 0) {
+    if constexpr (STEP == -1) {
+        // issue only: the 64 KB fetch overlaps the (synchronous) staging of the other weights
         for (int q = tid; q < C * (H / 4); q += NTHREADS) {                       // 4096 x 16 B
             const int row = q >> 3, v4 = q & 7;
             OO_CP_ASYNC16(wst + row * GS + 4 * v4, th + OFF_OCL_W + row * H + 4 * v4);
         }
+    } else if constexpr (STEP == 0) {
         for (int row = tid; row < C; row += NTHREADS) {
             wst[row * GS + H] = OO_LDG(th + OFF_OCL_B + row);
             wst[row * GS + H + 1] = wst[row * GS + H + 2] = wst[row * GS + H + 3] = 0.f;

@@ -79,6 +79,7 @@ __global__ void __launch_bounds__(NTHREADS, 1) k_train(const TrainParams prm) {
             c.slab = prm.slab + (size_t)slot * PSTRIDE;
             c.inv1 = 1.f / ((float)prm.counts[2 * obj] + 1e-10f);
             c.invs = 1.f / ((float)prm.counts[2 * obj + 1] + 1e-10f);
+            if (PART) gram_stage<-1>(tid, sm, c.theta, nullptr);
             stage_weights(tid, sm, c.theta);
             if (PART) {
                 float* der = prm.derived + (size_t)blockIdx.x * DERIVED;

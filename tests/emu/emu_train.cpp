@@ -61,6 +61,8 @@ void emulate(const float* theta, const float* derived, int n_obj, const float* p
                 c.slab = slab.data() + (size_t)slot * PSTRIDE;
                 c.inv1 = 1.f / ((float)counts[2 * obj] + 1e-10f);
                 c.invs = 1.f / ((float)counts[2 * obj + 1] + 1e-10f);
+                if (PART)
+                    for (int tid = 0; tid < NTHREADS; ++tid) gram_stage<-1>(tid, sm, c.theta, nullptr);
                 for (int tid = 0; tid < NTHREADS; ++tid) stage_weights(tid, sm, c.theta);
                 if (PART) {
                     for (int tid = 0; tid < NTHREADS; ++tid) gram_stage<0>(tid, sm, c.theta, der.data());
