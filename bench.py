@@ -109,7 +109,7 @@ def cpu_reference_run(n_obj, part, steps, warmup, time_budget_s):
         for i, gr in enumerate(grads):
             if gr is not None:
                 oc.adamw_step(P[i], gr, M[i], V[i], t)
-        return float(terms.total)
+        return float(terms.total.detach())
 
     for w in range(warmup):
         one_step(w + 1)

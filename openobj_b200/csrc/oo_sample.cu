@@ -99,54 +99,129 @@ __device__ __forceinline__ RayPix ray_pixel(const oo_sample_args& a, const Rng& 
     return r;
 }
 
-__global__ void __launch_bounds__(NTH, 1) k_sample(const SampleK k) {
+// ---- pass A for one ray: pixel draw, gathers, per-ray outputs, class (0 invalid depth / 1 this object / 2 other)
+__device__ __forceinline__ int sample_ray_a(const oo_sample_args& a, const Rng& g, int obj, int ray, int n_rays, float& d_out,
+                                            int& oob) {
+    const RayPix p = ray_pixel(a, g, obj, ray);
+    oob += p.oob;
+    const size_t pix = ((size_t)p.kf * a.W + p.iw) * a.H + p.ih;
+    const uchar4 c = *reinterpret_cast<const uchar4*>(a.rgbs[obj] + pix * 4);    // vmap.py:424
+    const float d = a.depth[obj][pix];                                          // vmap.py:425
+    const size_t o = (size_t)obj * n_rays + ray;
+    a.gt_rgb[o * 3 + 0] = c.x; a.gt_rgb[o * 3 + 1] = c.y; a.gt_rgb[o * 3 + 2] = c.z;
+    a.gt_depth[o] = d;
+    a.labels[o] = c.w;
+    const bool invalid = d <= a.min_bound;                                      // vmap.py:485
+    a.valid[o] = invalid ? 0 : 1;
+    if (a.pix) {
+        a.pix[o * 3 + 0] = p.kf; a.pix[o * 3 + 1] = p.iw; a.pix[o * 3 + 2] = p.ih;
+    }
+    if (a.feat_row) {                                                           // vmap.py:437-452
+        const int pw = min(max((int)floorf(__fdiv_rn(p.iwf, (float)a.part_down)), 0), a.pw - 1);
+        const int ph = min(max((int)floorf(__fdiv_rn(p.ihf, (float)a.part_down)), 0), a.ph - 1);
+        a.feat_row[o] = (a.part_frame[obj * 20 + p.kf] * a.pw + pw) * a.ph + ph;
+    }
+    d_out = d;
+    return invalid ? 0 : (c.w == 1 ? 1 : 2);
+}
+
+// ---- pass B for one ray: depth placement along the ray and the sample points.  rk_* = rank of the ray inside its class
+// (tape rows in tape_by_rank mode); max_bound = max sampled depth of the object's batch (vmap.py:489, quirk 6)
+__device__ __forceinline__ void sample_ray_b(const SampleK& k, const Rng& g, int obj, int ray, int n_rays, int rk_inv, int rk_val,
+                                             int rk_obj, int rk_oth, float max_bound) {
     const oo_sample_args& a = k.a;
-    const int obj = blockIdx.x, tid = threadIdx.x, lane = tid & 31, wv = tid >> 5;
-    const int n_rays = a.n_frames * a.n_samples;
+    const bool rng = a.rng_mode != 0;
     const int S = a.n_c2s + a.n_bins;
-    const int cpt = (n_rays + NTH - 1) / NTH;
-    const int r_begin = min(tid * cpt, n_rays), r_end = min(r_begin + cpt, n_rays);
-    const uint8_t* rgbs = a.rgbs[obj];
-    const float* depth = a.depth[obj];
-    __shared__ int sh_cnt[32][3];
-    __shared__ float sh_max[32];
-    __shared__ int sh_oob;
-    if (tid == 0) sh_oob = 0;
+    const float eps = a.eps;
+    const RayPix p = ray_pixel(a, g, obj, ray);
+    const size_t o = (size_t)obj * n_rays + ray;
+    const float d = a.gt_depth[o];
+    const int state = a.labels[o];
+    const bool invalid = d <= a.min_bound;
+    float zs[MAXB];
+    if (invalid) {
+        // stratified_bins(min_bound, max(sampled_depth), S) -- vmap.py:493-498, utils.py:342-379
+        const size_t row = ((size_t)obj * n_rays + (a.tape_by_rank ? rk_inv : ray)) * S;
+        const float range = __fsub_rn(max_bound, a.min_bound);
+        const float blen = __fdiv_rn(range, (float)S);
+        for (int i = 0; i < S; ++i)
+            zs[i] = __fadd_rn(__fadd_rn(__fmul_rn(range, k.lin_s[i]), a.min_bound),
+                              __fmul_rn(rng ? g.uniform(3, (uint64_t)ray * S + i) : a.r_invalid[row + i], blen));
+    } else {
+        {   // cam -> surface: stratified_bins(min_bound, d - eps, n_c2s) -- vmap.py:506-509
+            const size_t row = ((size_t)obj * n_rays + (a.tape_by_rank ? rk_val : ray)) * a.n_c2s;
+            const float range = __fsub_rn(__fsub_rn(d, eps), a.min_bound);
+            const float blen = __fdiv_rn(range, (float)a.n_c2s);
+            for (int i = 0; i < a.n_c2s; ++i)
+                zs[i] = __fadd_rn(__fadd_rn(__fmul_rn(range, k.lin_c[i]), a.min_bound),
+                                  __fmul_rn(rng ? g.uniform(4, (uint64_t)ray * a.n_c2s + i) : a.r_valid[row + i], blen));
+        }
+        if (state == 1) {
+            // normal_bins_sampling: N(0, eps/3) draws sorted ascending, clipped to +-eps, + d -- utils.py:382-397
+            const size_t row = ((size_t)obj * n_rays + (a.tape_by_rank ? rk_obj : ray)) * a.n_bins;
+            float b[MAXB];
+            for (int i = 0; i < a.n_bins; ++i)
+                b[i] = rng ? g.normal(5, (uint64_t)ray * a.n_bins + i, __fdiv_rn(eps, 3.f)) : a.r_normal[row + i];
+            sort_small(b, a.n_bins);
+            for (int i = 0; i < a.n_bins; ++i) zs[a.n_c2s + i] = __fadd_rn(d, fminf(fmaxf(b[i], -eps), eps));
+        } else {
+            // stratified_bins(d - eps, d + other_eps, n_bins) -- vmap.py:538-542
+            const size_t row = ((size_t)obj * n_rays + (a.tape_by_rank ? rk_oth : ray)) * a.n_bins;
+            const float lo = __fsub_rn(d, eps), hi = __fadd_rn(d, a.other_eps);
+            const float range = __fsub_rn(hi, lo);
+            const float blen = __fdiv_rn(range, (float)a.n_bins);
+            for (int i = 0; i < a.n_bins; ++i)
+                zs[a.n_c2s + i] = __fadd_rn(__fadd_rn(__fmul_rn(range, k.lin_b[i]), lo),
+                                            __fmul_rn(rng ? g.uniform(6, (uint64_t)ray * a.n_bins + i) : a.r_other[row + i], blen));
+        }
+    }
+    // rays: dir_W = R dir_C, origin = T[:3,3] (utils.py:324-336); points = o + d*z (vmap.py:548-549)
+    const float* T = a.t_wc[obj] + 16 * p.kf;
+    const float* dc = a.rays_dir + ((size_t)p.iw * a.H + p.ih) * 3;
+    const float dx = dc[0], dy = dc[1], dz = dc[2];
+    const float wx = T[0] * dx + T[1] * dy + T[2] * dz;
+    const float wy = T[4] * dx + T[5] * dy + T[6] * dz;
+    const float wz = T[8] * dx + T[9] * dy + T[10] * dz;
+    const float ox = T[3], oy = T[7], oz = T[11];
+    float* zo = a.z + o * S;
+    float* po = a.pcs + o * S * 3;
+    for (int i = 0; i < S; ++i) {
+        zo[i] = zs[i];
+        po[3 * i + 0] = __fadd_rn(ox, __fmul_rn(wx, zs[i]));
+        po[3 * i + 1] = __fadd_rn(oy, __fmul_rn(wy, zs[i]));
+        po[3 * i + 2] = __fadd_rn(oz, __fmul_rn(wz, zs[i]));
+    }
+}
+
+__device__ __forceinline__ Rng make_rng(const oo_sample_args& a, int obj) {
     Rng g;
     g.key = make_uint2((uint32_t)a.seed, (uint32_t)(a.seed >> 32));
     g.oid = a.rng_mode ? (uint32_t)a.obj_ids[obj] : 0u;
     g.frame = a.frame;
-    const bool rng = a.rng_mode != 0;
+    return g;
+}
 
-    // ---- pass A: gather + classify -------------------------------------------------------------------
+// ---- tape mode (and the general path): one 1024-thread CTA per object, ranks by block scan -------------------------
+__global__ void __launch_bounds__(NTH, 1) k_sample(const SampleK k) {
+    const oo_sample_args& a = k.a;
+    const int obj = blockIdx.x, tid = threadIdx.x, lane = tid & 31, wv = tid >> 5;
+    const int n_rays = a.n_frames * a.n_samples;
+    const int cpt = (n_rays + NTH - 1) / NTH;
+    const int r_begin = min(tid * cpt, n_rays), r_end = min(r_begin + cpt, n_rays);
+    __shared__ int sh_cnt[32][3];
+    __shared__ float sh_max[32];
+    __shared__ int sh_oob;
+    if (tid == 0) sh_oob = 0;
+    const Rng g = make_rng(a, obj);
     int n_inv = 0, n_obj = 0, n_oth = 0, oob = 0;
     float dmax = -INFINITY;
     for (int ray = r_begin; ray < r_end; ++ray) {
-        const RayPix p = ray_pixel(a, g, obj, ray);
-        oob += p.oob;
-        const size_t pix = ((size_t)p.kf * a.W + p.iw) * a.H + p.ih;
-        const uchar4 c = *reinterpret_cast<const uchar4*>(rgbs + pix * 4);        // vmap.py:424
-        const float d = depth[pix];                                                // vmap.py:425
-        const size_t o = (size_t)obj * n_rays + ray;
-        a.gt_rgb[o * 3 + 0] = c.x; a.gt_rgb[o * 3 + 1] = c.y; a.gt_rgb[o * 3 + 2] = c.z;
-        a.gt_depth[o] = d;
-        a.labels[o] = c.w;
-        const bool invalid = d <= a.min_bound;                                     // vmap.py:485
-        a.valid[o] = invalid ? 0 : 1;
-        if (a.pix) {
-            a.pix[o * 3 + 0] = p.kf; a.pix[o * 3 + 1] = p.iw; a.pix[o * 3 + 2] = p.ih;
-        }
-        if (a.feat_row) {                                                          // vmap.py:437-452
-            const int pw = min(max((int)floorf(__fdiv_rn(p.iwf, (float)a.part_down)), 0), a.pw - 1);
-            const int ph = min(max((int)floorf(__fdiv_rn(p.ihf, (float)a.part_down)), 0), a.ph - 1);
-            a.feat_row[o] = (a.part_frame[obj * 20 + p.kf] * a.pw + pw) * a.ph + ph;
-        }
+        float d;
+        const int cls = sample_ray_a(a, g, obj, ray, n_rays, d, oob);
         dmax = fmaxf(dmax, d);
-        if (invalid) ++n_inv;
-        else if (c.w == 1) ++n_obj;
-        else ++n_oth;
+        n_inv += cls == 0; n_obj += cls == 1; n_oth += cls == 2;
     }
-    // ---- block exclusive scan of the three class counters, block max of the sampled depths ----------------
+    // block exclusive scan of the three class counters, block max of the sampled depths
     int s_inv = n_inv, s_obj = n_obj, s_oth = n_oth;
 #pragma unroll
     for (int o = 1; o < 32; o <<= 1) {
@@ -181,70 +256,40 @@ __global__ void __launch_bounds__(NTH, 1) k_sample(const SampleK k) {
         rk_oth = sh_cnt[wv][2] + s_oth - n_oth;
     const float max_bound = sh_max[0];                                             // vmap.py:489
     if (tid == 0 && a.oob_count && sh_oob) atomicAdd(a.oob_count, sh_oob);
-
-    // ---- pass B: sample placement ----------------------------------------------------------------------
-    const float eps = a.eps;
     for (int ray = r_begin; ray < r_end; ++ray) {
-        const RayPix p = ray_pixel(a, g, obj, ray);
-        const size_t o = (size_t)obj * n_rays + ray;
-        const float d = a.gt_depth[o];
-        const int state = a.labels[o];
-        const bool invalid = d <= a.min_bound;
-        float zs[MAXB];
-        if (invalid) {
-            // stratified_bins(min_bound, max(sampled_depth), S) -- vmap.py:493-498, utils.py:342-379
-            const size_t row = ((size_t)obj * n_rays + (a.tape_by_rank ? rk_inv : ray)) * S;
-            const float range = __fsub_rn(max_bound, a.min_bound);
-            const float blen = __fdiv_rn(range, (float)S);
-            for (int i = 0; i < S; ++i)
-                zs[i] = __fadd_rn(__fadd_rn(__fmul_rn(range, k.lin_s[i]), a.min_bound), __fmul_rn(rng ? g.uniform(3, (uint64_t)ray * S + i) : a.r_invalid[row + i], blen));
-            ++rk_inv;
-        } else {
-            const int rk_val = a.tape_by_rank ? (ray - rk_inv) : ray;              // rank among valid rays
-            {   // cam -> surface: stratified_bins(min_bound, d - eps, n_c2s) -- vmap.py:506-509
-                const size_t row = ((size_t)obj * n_rays + rk_val) * a.n_c2s;
-                const float range = __fsub_rn(__fsub_rn(d, eps), a.min_bound);
-                const float blen = __fdiv_rn(range, (float)a.n_c2s);
-                for (int i = 0; i < a.n_c2s; ++i)
-                    zs[i] = __fadd_rn(__fadd_rn(__fmul_rn(range, k.lin_c[i]), a.min_bound), __fmul_rn(rng ? g.uniform(4, (uint64_t)ray * a.n_c2s + i) : a.r_valid[row + i], blen));
-            }
-            if (state == 1) {
-                // normal_bins_sampling: N(0, eps/3) draws sorted ascending, clipped to +-eps, + d -- utils.py:382-397
-                const size_t row = ((size_t)obj * n_rays + (a.tape_by_rank ? rk_obj : ray)) * a.n_bins;
-                float b[MAXB];
-                for (int i = 0; i < a.n_bins; ++i)
-                    b[i] = rng ? g.normal(5, (uint64_t)ray * a.n_bins + i, __fdiv_rn(eps, 3.f)) : a.r_normal[row + i];
-                sort_small(b, a.n_bins);
-                for (int i = 0; i < a.n_bins; ++i) zs[a.n_c2s + i] = __fadd_rn(d, fminf(fmaxf(b[i], -eps), eps));
-                ++rk_obj;
-            } else {
-                // stratified_bins(d - eps, d + other_eps, n_bins) -- vmap.py:538-542
-                const size_t row = ((size_t)obj * n_rays + (a.tape_by_rank ? rk_oth : ray)) * a.n_bins;
-                const float lo = __fsub_rn(d, eps), hi = __fadd_rn(d, a.other_eps);
-                const float range = __fsub_rn(hi, lo);
-                const float blen = __fdiv_rn(range, (float)a.n_bins);
-                for (int i = 0; i < a.n_bins; ++i)
-                    zs[a.n_c2s + i] = __fadd_rn(__fadd_rn(__fmul_rn(range, k.lin_b[i]), lo), __fmul_rn(rng ? g.uniform(6, (uint64_t)ray * a.n_bins + i) : a.r_other[row + i], blen));
-                ++rk_oth;
-            }
-        }
-        // rays: dir_W = R dir_C, origin = T[:3,3] (utils.py:324-336); points = o + d*z (vmap.py:548-549)
-        const float* T = a.t_wc[obj] + 16 * p.kf;
-        const float* dc = a.rays_dir + ((size_t)p.iw * a.H + p.ih) * 3;
-        const float dx = dc[0], dy = dc[1], dz = dc[2];
-        const float wx = T[0] * dx + T[1] * dy + T[2] * dz;
-        const float wy = T[4] * dx + T[5] * dy + T[6] * dz;
-        const float wz = T[8] * dx + T[9] * dy + T[10] * dz;
-        const float ox = T[3], oy = T[7], oz = T[11];
-        float* zo = a.z + o * S;
-        float* po = a.pcs + o * S * 3;
-        for (int i = 0; i < S; ++i) {
-            zo[i] = zs[i];
-            po[3 * i + 0] = __fadd_rn(ox, __fmul_rn(wx, zs[i]));
-            po[3 * i + 1] = __fadd_rn(oy, __fmul_rn(wy, zs[i]));
-            po[3 * i + 2] = __fadd_rn(oz, __fmul_rn(wz, zs[i]));
-        }
+        sample_ray_b(k, g, obj, ray, n_rays, rk_inv, ray - rk_inv, rk_obj, rk_oth, max_bound);
+        const float d = a.gt_depth[(size_t)obj * n_rays + ray];
+        const int state = a.labels[(size_t)obj * n_rays + ray];
+        if (d <= a.min_bound) ++rk_inv;
+        else if (state == 1) ++rk_obj;
+        else ++rk_oth;
     }
+}
+
+// ---- counter-RNG mode: no ranks are needed, so every ray is independent: two fully parallel launches with the batch
+// max depth of each object (non-negative floats order like their bit patterns) exchanged through a tiny global array
+__global__ void __launch_bounds__(256) k_sample_a(const SampleK k, int* __restrict__ max_bits) {
+    const oo_sample_args& a = k.a;
+    const int obj = blockIdx.y, n_rays = a.n_frames * a.n_samples;
+    const int ray = blockIdx.x * blockDim.x + threadIdx.x;
+    const Rng g = make_rng(a, obj);
+    float d = 0.f;
+    int oob = 0;
+    if (ray < n_rays) sample_ray_a(a, g, obj, ray, n_rays, d, oob);
+    d = fmaxf(d, 0.f);
+#pragma unroll
+    for (int o = 16; o > 0; o >>= 1) d = fmaxf(d, __shfl_xor_sync(0xffffffffu, d, o));
+    if ((threadIdx.x & 31) == 0) atomicMax(max_bits + obj, __float_as_int(d));
+    if (oob && a.oob_count) atomicAdd(a.oob_count, oob);
+}
+
+__global__ void __launch_bounds__(256) k_sample_b(const SampleK k, const int* __restrict__ max_bits) {
+    const oo_sample_args& a = k.a;
+    const int obj = blockIdx.y, n_rays = a.n_frames * a.n_samples;
+    const int ray = blockIdx.x * blockDim.x + threadIdx.x;
+    if (ray >= n_rays) return;
+    const Rng g = make_rng(a, obj);
+    sample_ray_b(k, g, obj, ray, n_rays, 0, 0, 0, 0, __int_as_float(max_bits[obj]));
 }
 
 __global__ void k_rng_fill(uint64_t seed, uint32_t frame, const int32_t* __restrict__ obj_ids, int64_t per_obj, int kind,
@@ -350,6 +395,25 @@ extern "C" int oo_sample_rays(const oo_sample_args* a, void* stream) {
     for (int i = 0; i <= S; ++i) k.lin_s[i] = a->lin_s_host[i];
     for (int i = 0; i <= a->n_c2s; ++i) k.lin_c[i] = a->lin_c2s_host[i];
     for (int i = 0; i <= a->n_bins; ++i) k.lin_b[i] = a->lin_bins_host[i];
+    if (a->rng_mode) {
+        OO_REQUIRE(a->min_bound >= 0.f, "oo_sample_rays: the parallel path assumes min_bound >= 0");
+        // per-object batch-max scratch: one small allocation per process, grown on demand (calls are not re-entrant)
+        static int* max_bits = nullptr;
+        static int max_cap = 0;
+        if (a->n_obj > max_cap) {
+            if (max_bits) OO_CUDA(cudaFree(max_bits));
+            max_cap = a->n_obj < 1024 ? 1024 : 2 * a->n_obj;
+            OO_CUDA(cudaMalloc((void**)&max_bits, max_cap * sizeof(int)));
+        }
+        OO_CUDA(cudaMemsetAsync(max_bits, 0, a->n_obj * sizeof(int), (cudaStream_t)stream));
+        const int n_rays = a->n_frames * a->n_samples;
+        const dim3 grid((n_rays + 255) / 256, a->n_obj);
+        k_sample_a<<<grid, 256, 0, (cudaStream_t)stream>>>(k, max_bits);
+        OO_LAUNCH_CHECK();
+        k_sample_b<<<grid, 256, 0, (cudaStream_t)stream>>>(k, max_bits);
+        OO_LAUNCH_CHECK();
+        return 0;
+    }
     k_sample<<<a->n_obj, NTH, 0, (cudaStream_t)stream>>>(k);
     OO_LAUNCH_CHECK();
     return 0;

@@ -26,7 +26,7 @@ struct TrainParams {
     float* slab;
     float* slot_loss;
     float scale, cs, os, fs;
-    long long* phase_cycles;   // debug: [N_TRAIN_PHASES + 2] cycle totals of block 0 (nullptr = off)
+    long long* phase_cycles;   // debug: [N_TRAIN_PHASES + 4] cycle totals of block 0: phases, block, tiles, staging, flush
 };
 
 long long* g_phase_cycles = nullptr;
@@ -73,6 +73,7 @@ __global__ void __launch_bounds__(NTHREADS, 1) k_train(const TrainParams prm) {
         const int obj = t / prm.tiles_per_obj;
         const int r0 = (t - obj * prm.tiles_per_obj) * RT;
         if (obj != cur_obj) {
+            const long long ts0 = cyc ? clock64() : 0;
             cur_obj = obj;
             c.theta = prm.theta + (size_t)obj * PSTRIDE;
             c.derived = prm.derived + (size_t)blockIdx.x * DERIVED;
@@ -89,6 +90,7 @@ __global__ void __launch_bounds__(NTHREADS, 1) k_train(const TrainParams prm) {
                 zero_pad_rows(tid, sm);          // the staging used the activation area
             }
             __syncthreads();
+            if (cyc && tid == 0) cyc[N_TRAIN_PHASES + 2] += clock64() - ts0;
         }
         const size_t ray = (size_t)obj * prm.b.rays_per_obj + prm.ray0 + r0;
         c.nrays = min(RT, prm.R - r0);
@@ -105,6 +107,7 @@ __global__ void __launch_bounds__(NTHREADS, 1) k_train(const TrainParams prm) {
 
         const bool last_of_obj = (t + 1 == t_end) || ((t + 1) / prm.tiles_per_obj != obj);
         if (last_of_obj) {
+            const long long tf0 = cyc ? clock64() : 0;
             float* sl = prm.slot_loss + 4 * slot;
             tile_flush<0, PART>(tid, sm, c.slab, sl, acc); __syncthreads();
             tile_flush<1, PART>(tid, sm, c.slab, sl, acc); __syncthreads();
@@ -113,6 +116,7 @@ __global__ void __launch_bounds__(NTHREADS, 1) k_train(const TrainParams prm) {
             acc_zero(acc);
             ++slot;
             cur_obj = -1;
+            if (cyc && tid == 0) cyc[N_TRAIN_PHASES + 3] += clock64() - tf0;
         }
     }
     if (cyc && tid == 0) {
@@ -430,7 +434,7 @@ int launch_k1(const float* theta, int n_obj, const oo_batch* b, int it, int R, f
 // debug hook (not part of the ABI header): per-phase cycle counters of block 0
 extern "C" int oo_debug_phase_cycles(long long* dev_ptr) {
     g_phase_cycles = dev_ptr;
-    return N_TRAIN_PHASES + 2;
+    return N_TRAIN_PHASES + 4;
 }
 
 extern "C" int oo_train_ws_sizes(int n_obj, int rays_per_step, int iters, int n_sm, int* n_cta, int* n_slots,

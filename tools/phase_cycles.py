@@ -31,7 +31,7 @@ ens.train_frame(batch)
 torch.cuda.synchronize()
 L.oo_debug_phase_cycles(None)
 c = cyc.cpu().tolist()
-NP = n - 2
+NP = n - 4
 tiles = c[NP + 1]
 label = {0: "load", 1: "PE fwd", 2: "in", 3: "mid1", 4: "cat", 5: "mid2", 6: "heads", 7: "out", 33: "termination", 8: "ray sums+loss",
          9: "S", 10: "v=W^T y part", 11: "v reduce", 12: "G S", 32: "cos/A/B", 13: "U+rec+M", 16: "g per point",
@@ -42,6 +42,6 @@ if len(sys.argv) > 3:
     order = [int(x) for x in sys.argv[3].split(",")]
 names = ["%d %s" % (o, label.get(o, "?")) for o in order][:NP]
 tot = sum(c[:NP])
-print("tiles", tiles, "block cycles/tile %.0f, phases sum/tile %.0f" % (c[NP] / tiles, tot / tiles))
+print("tiles", tiles, "block cycles/tile %.0f, phases sum/tile %.0f, staging/tile %.0f, flush/tile %.0f" % (c[NP] / tiles, tot / tiles, c[NP + 2] / tiles, c[NP + 3] / tiles))
 for nme, v in zip(names, c[:NP]):
     print("%-14s %8.0f cyc/tile  %5.1f%%" % (nme, v / tiles, 100.0 * v / tot))
