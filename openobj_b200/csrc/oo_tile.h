@@ -202,23 +202,31 @@ OO_DEV void gemm_bwd_data(int tid, const float* __restrict__ W0, const float* __
     constexpr int REM = (K - 32 * NFULL) / 4;    // k-groups of the partial block
     constexpr int NREM = REM * PG;               // its tiles
     constexpr int SPARE = NTHREADS - 8 * PG;     // 56
-    int rem_done = 0;
+    constexpr int RDIV = REM > 0 ? REM : 1;
+    // every pass: ONE call site, so a warp that holds both block tiles and remainder tiles does not diverge
+    constexpr int NPASS = NFULL + (NREM > NFULL * SPARE ? (NREM - NFULL * SPARE + NTHREADS - 1) / NTHREADS : 0);
 #pragma unroll
-    for (int b = 0; b < NFULL; ++b) {
-        if (tid < 8 * PG) {
-            dgemm_tile<WS0, J0, WS1, J1>(32 * b + 4 * (tid & 7), tid >> 3, W0, DY0, W1, DY1, X, relu_rows, wa, draw);
-        } else if (REM > 0) {
-            const int t = rem_done + tid - 8 * PG;
-            if (t < NREM)
-                dgemm_tile<WS0, J0, WS1, J1>(32 * NFULL + 4 * (t % (REM > 0 ? REM : 1)), t / (REM > 0 ? REM : 1), W0, DY0, W1,
-                                             DY1, X, relu_rows, wa, draw);
+    for (int pass = 0; pass < NPASS; ++pass) {
+        int k0 = 0, pi = 0;
+        bool valid;
+        if (pass < NFULL) {
+            if (tid < 8 * PG) {
+                k0 = 32 * pass + 4 * (tid & 7);
+                pi = tid >> 3;
+                valid = true;
+            } else {
+                const int t = pass * SPARE + tid - 8 * PG;
+                valid = t < NREM;
+                k0 = 32 * NFULL + 4 * (t % RDIV);
+                pi = t / RDIV;
+            }
+        } else {
+            const int t = NFULL * SPARE + (pass - NFULL) * NTHREADS + tid;
+            valid = t < NREM;
+            k0 = 32 * NFULL + 4 * (t % RDIV);
+            pi = t / RDIV;
         }
-        rem_done += SPARE;
-    }
-    if (REM > 0) {
-        for (int t = rem_done + tid; t < NREM; t += NTHREADS)
-            dgemm_tile<WS0, J0, WS1, J1>(32 * NFULL + 4 * (t % (REM > 0 ? REM : 1)), t / (REM > 0 ? REM : 1), W0, DY0, W1, DY1,
-                                         X, relu_rows, wa, draw);
+        if (valid) dgemm_tile<WS0, J0, WS1, J1>(k0, pi, W0, DY0, W1, DY1, X, relu_rows, wa, draw);
     }
 }
 

@@ -1,0 +1,139 @@
+"""Edge cases and size-independent properties on the GPU: ragged ray counts, a single object, many
+objects (ScanNet-shape config 4: part features off), both zero-mask flags, sampler invariants at full frame size."""
+import numpy as np
+import pytest
+import torch
+
+import openobj_oracle as oc
+from openobj_b200 import layout
+
+pytestmark = pytest.mark.gpu
+DEV = "cuda:0"
+
+
+def _batch(N, RAYS, seed, feat):
+    from test_train_gpu import synth_batch
+    return synth_batch(N, RAYS, seed=seed, feat=feat)
+
+
+def _ensemble(N, R, I, seed):
+    from openobj_b200.ensemble import Ensemble
+    fc, B = oc.init_params(N, generator=torch.Generator().manual_seed(seed))
+    fc[8] *= 0.3
+    fc[9] *= 0.3
+    ens = Ensemble(N, rays_per_step=R, iters_per_frame=I)
+    ens.load_stacked(fc + [B])
+    return ens, fc, B
+
+
+@pytest.mark.parametrize("N,R,feat", [(1, 120, True), (3, 7, True), (2, 33, False), (5, 101, True), (200, 120, False)])
+def test_ragged_and_extreme_shapes(N, R, feat):
+    """rays per step not a multiple of the 10-ray tile, one object, 200 objects (more tiles than CTAs): losses rel 1e-4
+    against the oracle; gradients against its float64 / float32 evaluations."""
+    from openobj_b200.ensemble import FrameBatch
+    from test_train_gpu import check_grads, grads64
+    pcs, z, gt_depth, rgb8, labels, gt_feat = _batch(N, R, seed=N * 1000 + R, feat=feat)
+    labels[:, 0], labels[:, -1] = 1, 0
+    ens, fc, B = _ensemble(N, R, 1, seed=N + R)
+    batch = FrameBatch.from_dense(pcs.to(DEV), z.to(DEV), gt_depth.to(DEV), rgb8.to(DEV), labels.to(DEV),
+                                  gt_feat.to(DEV) if feat else None)
+    ens.prepare_frame(batch)
+    g, terms = ens.grads(batch, 0)
+    rt, rg = grads64(fc, B, pcs, z, gt_depth, rgb8 / 255., labels, gt_feat)
+    ref_t = torch.stack([rt.depth, rt.color, rt.opacity, rt.feat], 1).float()
+    torch.testing.assert_close(terms.cpu(), ref_t, rtol=1e-4, atol=1e-6)
+    if N <= 5:
+        _, rg32 = oc.train_step_grads(fc, B, pcs, z, gt_depth, rgb8 / 255., labels, gt_feat)
+        check_grads(g, rg, ref_grads_alt=rg32)
+    else:
+        check_grads(g, rg)
+    if not feat:       # clip head: no gradient at all (quirk 8)
+        for i in (14, 15, 16, 17):
+            assert float(layout.views(g)[i].abs().max()) == 0.0
+
+
+def test_both_zero_mask_flags_skip_every_group():
+    """Some object without label==1 rays AND some object without label!=2 rays: every loss term is zero for all objects
+    (render_rays.py:89-94) and no parameter moves (no gradient reaches any tensor)."""
+    from openobj_b200.ensemble import FrameBatch
+    N, R = 3, 20
+    pcs, z, gt_depth, rgb8, labels, gt_feat = _batch(N, R, seed=5, feat=True)
+    labels[0] = 2            # object 0: only unknown pixels
+    labels[1] = 0
+    ens, fc, B = _ensemble(N, R, 1, seed=9)
+    batch = FrameBatch.from_dense(pcs.to(DEV), z.to(DEV), gt_depth.to(DEV), rgb8.to(DEV), labels.to(DEV), gt_feat.to(DEV))
+    before = ens.theta.clone()
+    lt = torch.ones(1, N, 4, device=DEV)
+    ens.train_frame(batch, loss_terms=lt)
+    torch.cuda.synchronize()
+    assert int(ens.flags[0]) == 6 and float(lt.abs().max()) == 0.0
+    assert torch.equal(before, ens.theta) and ens.adam_t.cpu().tolist() == [0, 0, 0]
+    terms = oc.step_loss(*oc.ensemble_forward(fc, B, pcs)[:2], gt_depth, rgb8 / 255., labels, z, gt_feat,
+                         oc.ensemble_forward(fc, B, pcs)[2])
+    assert terms.flags & 6 == 6 and float(terms.total) == 0.0
+
+
+def test_partial_frame_and_step_offsets():
+    """train_frame(iters < iters_per_frame) consumes exactly the first slices; Adam step counters advance by iters."""
+    from openobj_b200.ensemble import FrameBatch
+    N, R, I = 4, 30, 5
+    pcs, z, gt_depth, rgb8, labels, gt_feat = _batch(N, R * I, seed=11, feat=True)
+    ens, fc, B = _ensemble(N, R, I, seed=12)
+    batch = FrameBatch.from_dense(pcs.to(DEV), z.to(DEV), gt_depth.to(DEV), rgb8.to(DEV), labels.to(DEV), gt_feat.to(DEV))
+    lt = torch.zeros(I, N, 4, device=DEV)
+    ens.train_frame(batch, iters=2, loss_terms=lt)
+    assert ens.adam_t.cpu().tolist() == [2, 2, 2]
+    assert float(lt[2:].abs().max()) == 0.0 and float(lt[:2].abs().min()) > 0.0
+    sl = slice(0, R)
+    rt, _ = oc.train_step_grads(fc, B, pcs[:, sl], z[:, sl], gt_depth[:, sl], rgb8[:, sl] / 255., labels[:, sl], gt_feat[:, sl])
+    got = float(ens.total_loss(lt[0].cpu()))
+    assert abs(got - float(rt.total.detach())) <= 1e-4 * abs(float(rt.total.detach()))
+    with pytest.raises(Exception):
+        ens.train_frame(batch, iters=I + 1)        # more steps than the pre-sampled batch holds
+
+
+def test_sampler_invariants_full_frame_size():
+    """Replica frame size, 60 objects, counter RNG: pixel indices inside each object's bbox, labels match the ring's state
+    plane, z inside its class interval, normal bins sorted and within +-eps of the depth, pcs = o + d z."""
+    from openobj_b200 import cfg as C
+    from openobj_b200.scene import Scene
+    from openobj_b200.synthetic import SyntheticScene
+    cfg = C.room0_config()
+    cfg.do_bg = False
+    n_obj = 60
+    synth = SyntheticScene(n_obj, W=cfg.W, H=cfg.H, part_mode=True, seed=2, n_distinct=1)
+    sc = Scene(cfg, seed=5, max_frames=4)
+    for f in range(3):
+        sc.add_frame(synth.frame(f))
+    b = sc.sample()
+    out = sc.sample_out
+    torch.cuda.synchronize()
+    assert int(out.oob.item()) == 0
+    objs = list(sc.obj_dict.values())
+    n_rays = out.labels.shape[1]
+    assert n_rays == cfg.n_iter_per_frame * cfg.n_per_optim == 12000
+    eps, oeps = cfg.surface_eps, cfg.stop_eps
+    z, d, lab = out.z, out.gt_depth, out.labels
+    valid = out.valid.bool()
+    assert torch.equal(valid, d > 0)
+    zmax = d.max(dim=1, keepdim=True).values
+    inv = ~valid
+    assert bool((z[inv] >= 0).all()) and bool((z[inv] <= zmax.expand_as(d)[inv][:, None] + 1e-6).all())
+    assert bool((z[valid][:, 0] >= 0).all()) and bool((z[valid][:, 0] <= (d[valid] - eps) + 1e-6).all())
+    is_obj = valid & (lab == 1)
+    zo = z[is_obj][:, 1:]
+    assert bool((zo[:, 1:] >= zo[:, :-1]).all())                      # sorted normal bins (utils.py:391)
+    assert bool(((zo - d[is_obj][:, None]).abs() <= eps + 1e-6).all())
+    oth = valid & (lab != 1)
+    zt = z[oth][:, 1:]
+    assert bool((zt >= (d[oth] - eps)[:, None] - 1e-6).all()) and bool((zt <= (d[oth] + oeps)[:, None] + 1e-6).all())
+    assert int((lab == 1).sum()) > 0 and int((lab == 2).sum()) > 0 and int(lab.max()) <= 2
+    # part-feature rows inside the table; every object samples its two latest keyframes in the last two frame draws
+    assert int(out.feat_row.min()) >= 0 and int(out.feat_row.max()) < sc.part_table.shape[0] * sc.pw * sc.ph
+    # linearity of the points in z: pcs = origin + dir * z  =>  second differences along the ray vanish relative to |dz|
+    p = out.pcs
+    dz = (z[..., 1:] - z[..., :-1])[..., None]
+    dirs = (p[..., 1:, :] - p[..., :-1, :]) / dz.clamp_min(1e-6)
+    ok = dz[..., 0] > 1e-3
+    spread = (dirs - dirs[..., :1, :]).abs().amax(-1)
+    assert float(spread[ok].max()) < 2e-3
