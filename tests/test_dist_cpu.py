@@ -60,3 +60,12 @@ def test_single_process_helpers_are_noops():
     assert D.max_over_ranks(3.5, torch.device("cpu")) == 3.5
     D.barrier()
     assert [D.owner_rank(k, 8) for k in range(10)] == [0, 1, 2, 3, 4, 5, 6, 7, 0, 1]
+
+
+def test_eval_gather_order_is_global_insertion_order():
+    from openobj_b200.eval import global_order
+    ks, order = global_order([3, 2, 2], 3)            # 7 objects over 3 ranks: rank r holds k = r, r+3, ...
+    assert ks == [0, 3, 6, 1, 4, 2, 5]
+    assert [ks[q] for q in order] == list(range(7))
+    ks, order = global_order([4], 1)
+    assert ks == [0, 1, 2, 3] and order == [0, 1, 2, 3]
