@@ -61,7 +61,8 @@ OO_HOSTDEV inline constexpr int group_of_offset(int off) {
 // ---- one tile: RT rays x S samples = P points, activations feature-major [row][P] -----------
 constexpr int RT = 10;
 constexpr int P = RT * S;      // 100
-constexpr int PS = 100;        // row stride (floats); PS % 32 == 4 keeps 8 consecutive rows on distinct banks
+constexpr int PS = 100;        // row stride (floats); PS % 32 == 4: the tensor-core fragment loads (8 rows x 4 points, or
+                               // 4 row pairs x 8 points) touch 32 distinct banks
 constexpr int NTHREADS = 256;
 
 // activation rows
@@ -69,28 +70,28 @@ constexpr int R_H2 = 0;        // fc2            } contiguous = cat_layer input 
 constexpr int R_E1 = 32;       // e1 (87) + 1 zero row
 constexpr int E1P = 88;
 constexpr int R_H4 = 120;      // fc4            } contiguous = head input [h4 ; e2]
-constexpr int R_E2 = 152;      // e2 (42) + 2 zero rows
-constexpr int E2P = 44;
-constexpr int R_H1 = 196;
-constexpr int R_H3 = 228;
-constexpr int R_HC = 260;      // color_linear out } contiguous = [hc ; hp]
-constexpr int R_HP = 292;      // clip_linear out
-constexpr int R_T = 324;       // scaled coords t (3) + 1 spare
-constexpr int R_MISC = 328;    // 12 rows, see M_*
-constexpr int NROWS = 340;
+constexpr int R_E2 = 152;      // e2 (42) + 6 zero rows (head input padded to 80 = ten 8-wide k-steps)
+constexpr int E2P = 48;
+constexpr int R_H1 = 200;
+constexpr int R_H3 = 232;
+constexpr int R_HC = 264;      // color_linear out } contiguous = [hc ; hp]
+constexpr int R_HP = 296;      // clip_linear out
+constexpr int R_T = 328;       // scaled coords t (3) + 1 spare
+constexpr int R_MISC = 332;    // 12 rows, see M_*
+constexpr int NROWS = 344;
 constexpr int M_OCC = 0, M_TERM = 1, M_DRAW = 2, M_COL = 3, M_DCOL = 6, M_FREE = 9, M_HU = 10;
 
 constexpr int SM_ACT = 0;
-constexpr int SM_W = NROWS * PS;                     // 34000
-// padded weight copies: row stride WS with WS % 32 in {4,12,20,28}
-constexpr int WS_IN = 92, WS_H = 36, WS_CAT = 124, WS_HD = 76;
-constexpr int KP_IN = 88, KP_CAT = 120, KP_HD = 76;  // padded K (multiples of 4)
+constexpr int SM_W = NROWS * PS;                     // 34400
+// padded weight copies (zero pad columns); K padded to multiples of 8 = one m16n8k8 k-step
+constexpr int WS_IN = 88, WS_H = 36, WS_CAT = 120, WS_HD = 80;
+constexpr int KP_IN = 88, KP_CAT = 120, KP_HD = 80;
 constexpr int W_IN = 0;
-constexpr int W_M1 = W_IN + H * WS_IN;               // 2944
-constexpr int W_CAT = W_M1 + H * WS_H;               // 4096
-constexpr int W_M2 = W_CAT + H * WS_CAT;             // 8064
-constexpr int W_CL = W_M2 + H * WS_H;                // 9216   } contiguous [64][76]
-constexpr int W_CP = W_CL + H * WS_HD;               // 11648
+constexpr int W_M1 = W_IN + H * WS_IN;               // 2816
+constexpr int W_CAT = W_M1 + H * WS_H;               // 3968
+constexpr int W_M2 = W_CAT + H * WS_CAT;             // 7808
+constexpr int W_CL = W_M2 + H * WS_H;                // 8960   } contiguous [64][80]
+constexpr int W_CP = W_CL + H * WS_HD;               // 11520
 constexpr int W_A = W_CP + H * WS_HD;                // 14080
 constexpr int W_OC = W_A + H;                        // 14112
 constexpr int B_IN = W_OC + 3 * H;                   // 14208
@@ -99,7 +100,7 @@ constexpr int B_A = B_CP + H;                        // 14400
 constexpr int B_OC = B_A + 4;
 constexpr int W_PE = B_OC + 4;                       // 14408, [21][3]
 constexpr int W_TOTAL = W_PE + 64;                   // 14472
-constexpr int SM_RAY = SM_W + W_TOTAL;               // 48472
+constexpr int SM_RAY = SM_W + W_TOTAL;               // 48872
 constexpr int RP = 12;                               // padded rays per row
 constexpr int SM_ST = SM_RAY;                        // S^T [32][12]   sum_i T_i hp_i
 constexpr int SM_UT = SM_ST + H * RP;                // U^T [32][12]   dL/dS

@@ -47,13 +47,16 @@ OO_DEV void st4(float* p, const float4& v) { *reinterpret_cast<float4*>(p) = v; 
 OO_DEV float sigmoidf_(float x) { return 1.0f / (1.0f + expf(-x)); }
 OO_DEV float sgnf_(float x) { return x > 0.f ? 1.f : (x < 0.f ? -1.f : 0.f); }
 
-// register-resident weight-gradient accumulators of one thread (live across all tiles of an object)
+// register-resident weight-gradient accumulators of one thread (live across all tiles of an object).  The five weight
+// matrices are accumulated as m16n8k8 C fragments: output tile u = warp + 8 i of a GEMM with MT row tiles (16 output
+// rows j each) is (m = u % MT, n = u / MT); register r of fragment i holds row j = 16 m + lane/4 + 8 (r >> 1) and
+// input column k = 8 n + 2 (lane % 4) + (r & 1)   (see wfrag_row / wfrag_col).
 struct TileAcc {
-    float in[16];    // in_layer   : rows ji+8jj, cols ki+22kk          (tid < 176)
-    float cat[16];   // cat_layer  : rows ji+8jj, cols ki+30kk          (tid < 240)
-    float m1[16];    // mid1       : rows ji+8jj, cols ki+8kk, point group tid>>6
-    float m2[16];    // mid2
-    float hd[32];    // [color_linear ; clip_linear] : rows ji+8jj (jj<8), cols ki+19kk (tid < 152)
+    float in[12];    // in_layer   : 2 x 11 tiles -> 3 fragments
+    float cat[16];   // cat_layer  : 2 x 15 tiles -> 4 fragments
+    float m1[4];     // mid1       : 2 x 4 tiles  -> 1 fragment
+    float m2[4];     // mid2
+    float hd[20];    // [color_linear ; clip_linear] : 4 x 10 tiles -> 5 fragments (part features off: 2 x 10 -> 3)
     float s0;        // out_color.weight (tid<96), out_alpha.weight (96<=tid<128)
     float s1;        // biases of the six hidden layers (tid<192), out_color.bias (192..194), out_alpha.bias (195)
     float s2;        // B_layer.weight (tid<63)
@@ -64,9 +67,13 @@ struct TileAcc {
 
 OO_DEV void acc_zero(TileAcc& a) {
 #pragma unroll
-    for (int i = 0; i < 16; ++i) a.in[i] = a.cat[i] = a.m1[i] = a.m2[i] = 0.f;
+    for (int i = 0; i < 12; ++i) a.in[i] = 0.f;
 #pragma unroll
-    for (int i = 0; i < 32; ++i) a.hd[i] = 0.f;
+    for (int i = 0; i < 16; ++i) a.cat[i] = 0.f;
+#pragma unroll
+    for (int i = 0; i < 4; ++i) a.m1[i] = a.m2[i] = 0.f;
+#pragma unroll
+    for (int i = 0; i < 20; ++i) a.hd[i] = 0.f;
     a.s0 = a.s1 = a.s2 = a.s3 = 0.f;
     a.gm[0] = a.gm[1] = a.gm[2] = a.gm[3] = 0.f;
     a.loss[0] = a.loss[1] = a.loss[2] = a.loss[3] = 0.f;
@@ -94,160 +101,238 @@ struct TileCtx {
 };
 
 // ------------------------------------------------------------------------------------------------
-// register-tiled building blocks
+// tensor-core building blocks
+//
+// Every contraction of the tile runs on the tensor pipe as mma.sync m16n8k8 TF32 with three-term error compensation
+// (x = hi + lo, hi = x with the low 13 mantissa bits cleared, lo = x - hi exactly; a.b ~ lo_a hi_b + hi_a lo_b +
+// hi_a hi_b, fp32 accumulate): the result agrees with an fp32 FMA chain to ~1e-6, which the parity tolerance
+// (rel 1e-4 on losses) needs and plain TF32 does not give.  Fragment element maps (g = lane / 4, t = lane % 4):
+//   A 16x8: a0 (g, t) a1 (g+8, t) a2 (g, t+4) a3 (g+8, t+4);  B 8x8: b0 (t, g) b1 (t+4, g);
+//   C 16x8: c0 (g, 2t) c1 (g, 2t+1) c2 (g+8, 2t) c3 (g+8, 2t+1).
+// The k index inside a k-step is a dummy, so a fragment "slot" may hold any k as long as A and B agree: the forward
+// GEMM puts k0+2t in slot t and k0+2t+1 in slot t+4, which makes the weight fragment one 64-bit load and the activation
+// fragment bank-conflict free with the row stride PS = 100.
+// Work split: a GEMM with MT row tiles and NT column tiles has MT*NT output tiles; warp w owns tiles u = w + 8 i
+// (m = u % MT, n = u / MT).  The host build (CPU tile emulator, tests only) replaces the fragment code by plain loops
+// with the same thread -> element ownership.
 // ------------------------------------------------------------------------------------------------
+constexpr int NT_P = (P + 7) / 8;      // 13 point tiles of 8 (the last one is half empty)
 
-// Y[j][p] = act(b[j] + sum_k W[j][k] X[k][p]), 32 output rows, P points.  200 threads: rows ji+8jj, points 4pi..4pi+3
-template <int K, int WS, bool RELU>
+OO_HOSTDEV inline constexpr int wfrag_units(int MT, int NT) { return (MT * NT + 7) / 8; }
+// which weight-gradient element register r of fragment i of thread tid holds (MT row tiles, NT column tiles)
+OO_HOSTDEV inline int wfrag_row(int tid, int i, int r, int MT) { return 16 * (((tid >> 5) + 8 * i) % MT) + ((tid & 31) >> 2) + 8 * (r >> 1); }
+OO_HOSTDEV inline int wfrag_col(int tid, int i, int r, int MT) { return 8 * (((tid >> 5) + 8 * i) / MT) + 2 * (tid & 3) + (r & 1); }
+
+#ifdef __CUDACC__
+struct FragA { uint32_t hi[4], lo[4]; };
+struct FragB { uint32_t hi[2], lo[2]; };
+
+OO_DEV void tf32_split(float x, uint32_t& hi, uint32_t& lo) {
+    hi = __float_as_uint(x) & 0xffffe000u;
+    lo = __float_as_uint(x - __uint_as_float(hi));
+}
+OO_DEV void mma_tf32(float (&c)[4], const uint32_t (&a)[4], const uint32_t (&b)[2]) {
+    asm("mma.sync.aligned.m16n8k8.row.col.f32.tf32.tf32.f32 {%0,%1,%2,%3}, {%4,%5,%6,%7}, {%8,%9}, {%0,%1,%2,%3};"
+        : "+f"(c[0]), "+f"(c[1]), "+f"(c[2]), "+f"(c[3])
+        : "r"(a[0]), "r"(a[1]), "r"(a[2]), "r"(a[3]), "r"(b[0]), "r"(b[1]));
+}
+OO_DEV void mma3(float (&c)[4], const FragA& a, const FragB& b) {
+    mma_tf32(c, a.lo, b.hi);      // small terms first
+    mma_tf32(c, a.hi, b.lo);
+    mma_tf32(c, a.hi, b.hi);
+}
+OO_DEV void frag_a(FragA& f, float a0, float a1, float a2, float a3) {
+    tf32_split(a0, f.hi[0], f.lo[0]); tf32_split(a1, f.hi[1], f.lo[1]);
+    tf32_split(a2, f.hi[2], f.lo[2]); tf32_split(a3, f.hi[3], f.lo[3]);
+}
+OO_DEV void frag_b(FragB& f, float b0, float b1) {
+    tf32_split(b0, f.hi[0], f.lo[0]); tf32_split(b1, f.hi[1], f.lo[1]);
+}
+#endif
+
+// Y[j][p] = act(b[j] + sum_k W[j][k] X[k][p]), 16*MT output rows, P points, K % 8 == 0.  M = j, N = p.
+template <int K, int WS, int MT, bool RELU>
 OO_DEV void gemm_fwd(int tid, const float* __restrict__ W, const float* __restrict__ bias,
                      const float* __restrict__ X, float* __restrict__ Y) {
-    if (tid >= 8 * (P / 4)) return;
-    const int ji = tid & 7, pi = tid >> 3;
-    float acc[4][4];
+#ifdef __CUDACC__
+    static_assert(8 % MT == 0 && K % 8 == 0 && WS % 2 == 0, "gemm_fwd tiling");
+    constexpr int NU = wfrag_units(MT, NT_P), NSTEP = 8 / MT;
+    const int warp = tid >> 5, lane = tid & 31, g = lane >> 2, t = lane & 3;
+    const int m = warp % MT, n0 = warp / MT;
+    float acc[NU][4];
+    {
+        const float b_lo = bias[16 * m + g], b_hi = bias[16 * m + g + 8];
 #pragma unroll
-    for (int jj = 0; jj < 4; ++jj) {
-        const float b = bias[ji + 8 * jj];
-        acc[jj][0] = acc[jj][1] = acc[jj][2] = acc[jj][3] = b;
+        for (int i = 0; i < NU; ++i) { acc[i][0] = acc[i][1] = b_lo; acc[i][2] = acc[i][3] = b_hi; }
     }
-    const float* wp = W + ji * WS;
-    const float* xp = X + 4 * pi;
+    const float* wp = W + (16 * m + g) * WS + 2 * t;
+    const float* xp = X + 2 * t * PS + 8 * n0 + g;
 #pragma unroll 2
-    for (int k0 = 0; k0 < K; k0 += 4) {
-        float4 w[4], x[4];
+    for (int k0 = 0; k0 < K; k0 += 8) {
+        const float2 w_lo = *reinterpret_cast<const float2*>(wp + k0);
+        const float2 w_hi = *reinterpret_cast<const float2*>(wp + 8 * WS + k0);
+        FragA a;
+        frag_a(a, w_lo.x, w_hi.x, w_lo.y, w_hi.y);
 #pragma unroll
-        for (int jj = 0; jj < 4; ++jj) w[jj] = ld4(wp + jj * 8 * WS + k0);
-#pragma unroll
-        for (int kk = 0; kk < 4; ++kk) x[kk] = ld4(xp + (k0 + kk) * PS);
-#pragma unroll
-        for (int jj = 0; jj < 4; ++jj) {
-            acc[jj][0] += w[jj].x * x[0].x + w[jj].y * x[1].x + w[jj].z * x[2].x + w[jj].w * x[3].x;
-            acc[jj][1] += w[jj].x * x[0].y + w[jj].y * x[1].y + w[jj].z * x[2].y + w[jj].w * x[3].y;
-            acc[jj][2] += w[jj].x * x[0].z + w[jj].y * x[1].z + w[jj].z * x[2].z + w[jj].w * x[3].z;
-            acc[jj][3] += w[jj].x * x[0].w + w[jj].y * x[1].w + w[jj].z * x[2].w + w[jj].w * x[3].w;
+        for (int i = 0; i < NU; ++i) {
+            if (n0 + NSTEP * i < NT_P) {              // warp-uniform
+                FragB b;
+                frag_b(b, xp[k0 * PS + 8 * NSTEP * i], xp[(k0 + 1) * PS + 8 * NSTEP * i]);
+                mma3(acc[i], a, b);
+            }
         }
     }
 #pragma unroll
-    for (int jj = 0; jj < 4; ++jj) {
-        float4 y;
-        y.x = acc[jj][0]; y.y = acc[jj][1]; y.z = acc[jj][2]; y.w = acc[jj][3];
-        if (RELU) {
-            y.x = fmaxf(y.x, 0.f); y.y = fmaxf(y.y, 0.f); y.z = fmaxf(y.z, 0.f); y.w = fmaxf(y.w, 0.f);
+    for (int i = 0; i < NU; ++i) {
+        const int p = 8 * (n0 + NSTEP * i) + 2 * t;
+        if (n0 + NSTEP * i < NT_P && p < P) {
+            float2 y0 = {acc[i][0], acc[i][1]}, y1 = {acc[i][2], acc[i][3]};
+            if (RELU) {
+                y0.x = fmaxf(y0.x, 0.f); y0.y = fmaxf(y0.y, 0.f); y1.x = fmaxf(y1.x, 0.f); y1.y = fmaxf(y1.y, 0.f);
+            }
+            *reinterpret_cast<float2*>(Y + (16 * m + g) * PS + p) = y0;
+            *reinterpret_cast<float2*>(Y + (16 * m + g + 8) * PS + p) = y1;
         }
-        st4(Y + (ji + 8 * jj) * PS + 4 * pi, y);
     }
+#else
+    if (tid != 0) return;
+    for (int j = 0; j < 16 * MT; ++j)
+        for (int p = 0; p < P; ++p) {
+            float acc = bias[j];
+            for (int k = 0; k < K; ++k) acc += W[j * WS + k] * X[k * PS + p];
+            Y[j * PS + p] = RELU ? (acc > 0.f ? acc : 0.f) : acc;
+        }
+#endif
 }
 
 // DX[k][p] = [k < relu_rows ? (X[k][p] > 0) : 1] * ( sum_{j<J0} W0[j][k] DY0[j][p] + sum_{j<J1} W1[j][k] DY1[j][p]
-//            + [k < 32 && wa] wa[k] * draw[p] ),  written IN PLACE over X (rows 0..K-1).  K % 4 == 0.
-// One 4(k) x 4(p) register tile: k-group ki of the row block starting at kb (NK k-groups wide), point group pi.
-template <int WS0, int J0, int WS1, int J1>
-OO_DEV void dgemm_tile(int k0, int pi, const float* __restrict__ W0, const float* __restrict__ DY0,
-                       const float* __restrict__ W1, const float* __restrict__ DY1, float* X, int relu_rows,
-                       const float* wa, const float* draw) {
-    float acc[4][4];
-#pragma unroll
-    for (int kk = 0; kk < 4; ++kk) acc[kk][0] = acc[kk][1] = acc[kk][2] = acc[kk][3] = 0.f;
-#pragma unroll 4
-    for (int j = 0; j < J0; ++j) {
-        const float4 w = ld4(W0 + j * WS0 + k0);
-        const float4 d = ld4(DY0 + j * PS + 4 * pi);
-        acc[0][0] += w.x * d.x; acc[0][1] += w.x * d.y; acc[0][2] += w.x * d.z; acc[0][3] += w.x * d.w;
-        acc[1][0] += w.y * d.x; acc[1][1] += w.y * d.y; acc[1][2] += w.y * d.z; acc[1][3] += w.y * d.w;
-        acc[2][0] += w.z * d.x; acc[2][1] += w.z * d.y; acc[2][2] += w.z * d.z; acc[2][3] += w.z * d.w;
-        acc[3][0] += w.w * d.x; acc[3][1] += w.w * d.y; acc[3][2] += w.w * d.z; acc[3][3] += w.w * d.w;
-    }
-    if (J1 > 0) {
-#pragma unroll 4
-        for (int j = 0; j < J1; ++j) {
-            const float4 w = ld4(W1 + j * WS1 + k0);
-            const float4 d = ld4(DY1 + j * PS + 4 * pi);
-            acc[0][0] += w.x * d.x; acc[0][1] += w.x * d.y; acc[0][2] += w.x * d.z; acc[0][3] += w.x * d.w;
-            acc[1][0] += w.y * d.x; acc[1][1] += w.y * d.y; acc[1][2] += w.y * d.z; acc[1][3] += w.y * d.w;
-            acc[2][0] += w.z * d.x; acc[2][1] += w.z * d.y; acc[2][2] += w.z * d.z; acc[2][3] += w.z * d.w;
-            acc[3][0] += w.w * d.x; acc[3][1] += w.w * d.y; acc[3][2] += w.w * d.z; acc[3][3] += w.w * d.w;
-        }
-    }
-    if (wa != nullptr && k0 < H) {
-        const float4 dr = ld4(draw + 4 * pi);
-#pragma unroll
-        for (int kk = 0; kk < 4; ++kk) {
-            const float a = wa[k0 + kk];
-            acc[kk][0] += a * dr.x; acc[kk][1] += a * dr.y; acc[kk][2] += a * dr.z; acc[kk][3] += a * dr.w;
-        }
-    }
-#pragma unroll
-    for (int kk = 0; kk < 4; ++kk) {
-        float* xp = X + (k0 + kk) * PS + 4 * pi;
-        float4 o;
-        o.x = acc[kk][0]; o.y = acc[kk][1]; o.z = acc[kk][2]; o.w = acc[kk][3];
-        if (k0 + kk < relu_rows) {
-            const float4 h = ld4(xp);
-            o.x = h.x > 0.f ? o.x : 0.f; o.y = h.y > 0.f ? o.y : 0.f;
-            o.z = h.z > 0.f ? o.z : 0.f; o.w = h.w > 0.f ? o.w : 0.f;
-        }
-        st4(xp, o);
-    }
-}
-
-// Work distribution: rows are cut into blocks of 32 (8 k-groups x 25 point groups = 200 tiles, lanes = 8 k-groups x 4
-// point groups: conflict-free 128-bit loads).  Threads 0..199 take one full block per pass; the 56 spare threads
-// of every pass work through the tiles of the last, partial block, so K = 76 needs 2 passes and K = 88 needs 2 + a
-// short third instead of 3 each.
+//            + [k < 32 && wa] wa[k] * draw[p] ),  written IN PLACE over X (rows 0..K-1).  M = k (MT = ceil(K/16) row
+// tiles; rows >= K are computed from whatever follows the weights and never stored), N = p, contraction over j.
+// An output tile reads and writes only its own 16 x 8 block of X, so in-place is safe across warps.
+// Work split: warp w owns point tile w with all row tiles (job 0); warps 0..3 also own point tile w + 8, and the row
+// tiles of the 13th point tile are shared out between warps 5..7 (job 1), so the four schedulers carry 3, 3.4, 3.4, 3.4
+// point tiles.  Each DY fragment is split once per k-step and reused for every row tile, each weight fragment serves both
+// jobs.
 template <int K, int WS0, int J0, int WS1, int J1>
 OO_DEV void gemm_bwd_data(int tid, const float* __restrict__ W0, const float* __restrict__ DY0,
                           const float* __restrict__ W1, const float* __restrict__ DY1,
                           float* X, int relu_rows, const float* wa, const float* draw) {
-    constexpr int PG = P / 4;                    // 25 point groups
-    constexpr int NFULL = K / 32;                // full 32-row blocks
-    constexpr int REM = (K - 32 * NFULL) / 4;    // k-groups of the partial block
-    constexpr int NREM = REM * PG;               // its tiles
-    constexpr int SPARE = NTHREADS - 8 * PG;     // 56
-    constexpr int RDIV = REM > 0 ? REM : 1;
-    // every pass: ONE call site, so a warp that holds both block tiles and remainder tiles does not diverge
-    constexpr int NPASS = NFULL + (NREM > NFULL * SPARE ? (NREM - NFULL * SPARE + NTHREADS - 1) / NTHREADS : 0);
+#ifdef __CUDACC__
+    static_assert(J0 % 8 == 0 && J1 % 8 == 0, "gemm_bwd_data tiling");
+    constexpr int MT = (K + 15) / 16, MSPLIT = (MT + 2) / 3;
+    const int warp = tid >> 5, lane = tid & 31, g = lane >> 2, t = lane & 3;
+    const int n1 = warp < 4 ? warp + 8 : NT_P - 1;
+    const int mb1 = warp < 4 ? 0 : warp == 4 ? MT : (warp - 5) * MSPLIT;
+    const int me1 = warp < 4 ? MT : warp == 4 ? MT : (mb1 + MSPLIT < MT ? mb1 + MSPLIT : MT);
+    const bool job1 = mb1 < me1;
+    float acc[MT][2][4];
 #pragma unroll
-    for (int pass = 0; pass < NPASS; ++pass) {
-        int k0 = 0, pi = 0;
-        bool valid;
-        if (pass < NFULL) {
-            if (tid < 8 * PG) {
-                k0 = 32 * pass + 4 * (tid & 7);
-                pi = tid >> 3;
-                valid = true;
-            } else {
-                const int t = pass * SPARE + tid - 8 * PG;
-                valid = t < NREM;
-                k0 = 32 * NFULL + 4 * (t % RDIV);
-                pi = t / RDIV;
+    for (int m = 0; m < MT; ++m)
+#pragma unroll
+        for (int q = 0; q < 2; ++q) acc[m][q][0] = acc[m][q][1] = acc[m][q][2] = acc[m][q][3] = 0.f;
+#pragma unroll
+    for (int term = 0; term < (J1 > 0 ? 2 : 1); ++term) {
+        const float* W = term == 0 ? W0 : W1;
+        const float* DY = term == 0 ? DY0 : DY1;
+        const int WS = term == 0 ? WS0 : WS1, J = term == 0 ? J0 : J1;
+        const float* wp = W + t * WS + g;
+        const float* dp = DY + t * PS + g;
+#pragma unroll 1
+        for (int j0 = 0; j0 < J; j0 += 8) {
+            FragB b0, b1;
+            frag_b(b0, dp[j0 * PS + 8 * warp], dp[(j0 + 4) * PS + 8 * warp]);
+            if (job1) frag_b(b1, dp[j0 * PS + 8 * n1], dp[(j0 + 4) * PS + 8 * n1]);
+#pragma unroll
+            for (int m = 0; m < MT; ++m) {
+                FragA a;
+                frag_a(a, wp[j0 * WS + 16 * m], wp[j0 * WS + 16 * m + 8], wp[(j0 + 4) * WS + 16 * m], wp[(j0 + 4) * WS + 16 * m + 8]);
+                mma3(acc[m][0], a, b0);
+                if (m >= mb1 && m < me1) mma3(acc[m][1], a, b1);      // warp-uniform
             }
-        } else {
-            const int t = NFULL * SPARE + (pass - NFULL) * NTHREADS + tid;
-            valid = t < NREM;
-            k0 = 32 * NFULL + 4 * (t % RDIV);
-            pi = t / RDIV;
         }
-        if (valid) dgemm_tile<WS0, J0, WS1, J1>(k0, pi, W0, DY0, W1, DY1, X, relu_rows, wa, draw);
     }
+#pragma unroll
+    for (int q = 0; q < 2; ++q) {
+        const int p = 8 * (q == 0 ? warp : n1) + 2 * t;
+        if (p >= P) continue;
+        float2 dr = {0.f, 0.f};
+        if (wa != nullptr) dr = *reinterpret_cast<const float2*>(draw + p);
+#pragma unroll
+        for (int m = 0; m < MT; ++m) {
+            if (q == 1 && !(m >= mb1 && m < me1)) continue;
+#pragma unroll
+            for (int h = 0; h < 2; ++h) {
+                const int k = 16 * m + g + 8 * h;
+                if (k < K) {
+                    float2 o = {acc[m][q][2 * h], acc[m][q][2 * h + 1]};
+                    if (wa != nullptr && k < H) {
+                        o.x += wa[k] * dr.x; o.y += wa[k] * dr.y;
+                    }
+                    float2* xp = reinterpret_cast<float2*>(X + k * PS + p);
+                    if (k < relu_rows) {
+                        const float2 hv = *xp;
+                        o.x = hv.x > 0.f ? o.x : 0.f; o.y = hv.y > 0.f ? o.y : 0.f;
+                    }
+                    *xp = o;
+                }
+            }
+        }
+    }
+#else
+    if (tid != 0) return;
+    for (int k = 0; k < K; ++k)
+        for (int p = 0; p < P; ++p) {
+            float acc = 0.f;
+            for (int j = 0; j < J0; ++j) acc += W0[j * WS0 + k] * DY0[j * PS + p];
+            for (int j = 0; j < J1; ++j) acc += W1[j * WS1 + k] * DY1[j * PS + p];
+            if (wa != nullptr && k < H) acc += wa[k] * draw[p];
+            if (k < relu_rows && !(X[k * PS + p] > 0.f)) acc = 0.f;
+            X[k * PS + p] = acc;
+        }
+#endif
 }
 
-// acc[jj*4+kk] += sum_{p in [pa,pb)} DY[ji+8jj][p] * X[ki+KQ*kk][p]
-template <int NJJ, int KQ>
-OO_DEV void gemm_bwd_w(float* acc, int ji, int ki, const float* __restrict__ DY, const float* __restrict__ X,
-                       int pa, int pb) {
-    const float* dp = DY + ji * PS;
-    const float* xp = X + ki * PS;
-    for (int p0 = pa; p0 < pb; p0 += 4) {
-        float4 d[NJJ], x[4];
+// acc fragment i (+)= sum_p DY[j][p] X[k][p] over the tile's points, for this thread's elements of output tiles
+// u = warp + 8 i of the [16 MT] x [8 NT] weight gradient.  M = j, N = k, contraction over points (the four points
+// of the last k-step that lie beyond P contribute zero).
+template <int MT, int NT>
+OO_DEV void gemm_bwd_w(float* acc, int tid, const float* __restrict__ DY, const float* __restrict__ X) {
+#ifdef __CUDACC__
+    static_assert(8 % MT == 0, "gemm_bwd_w tiling");
+    constexpr int NU = wfrag_units(MT, NT), NSTEP = 8 / MT;
+    const int warp = tid >> 5, lane = tid & 31, g = lane >> 2, t = lane & 3;
+    const int m = warp % MT, n0 = warp / MT;
+    float c[NU][4];
 #pragma unroll
-        for (int jj = 0; jj < NJJ; ++jj) d[jj] = ld4(dp + jj * 8 * PS + p0);
+    for (int i = 0; i < NU; ++i) { c[i][0] = acc[4 * i]; c[i][1] = acc[4 * i + 1]; c[i][2] = acc[4 * i + 2]; c[i][3] = acc[4 * i + 3]; }
+    const float* dp = DY + (16 * m + g) * PS + t;
+    const float* xp = X + (8 * n0 + g) * PS + t;
+#pragma unroll 2
+    for (int p0 = 0; p0 < 8 * NT_P; p0 += 8) {
+        const bool tail = p0 + t + 4 >= P;               // only in the last k-step
+        FragA a;
+        frag_a(a, dp[p0], dp[8 * PS + p0], tail ? 0.f : dp[p0 + 4], tail ? 0.f : dp[8 * PS + p0 + 4]);
 #pragma unroll
-        for (int kk = 0; kk < 4; ++kk) x[kk] = ld4(xp + kk * KQ * PS + p0);
-#pragma unroll
-        for (int jj = 0; jj < NJJ; ++jj)
-#pragma unroll
-            for (int kk = 0; kk < 4; ++kk)
-                acc[jj * 4 + kk] += d[jj].x * x[kk].x + d[jj].y * x[kk].y + d[jj].z * x[kk].z + d[jj].w * x[kk].w;
+        for (int i = 0; i < NU; ++i) {
+            if (n0 + NSTEP * i < NT) {                    // warp-uniform
+                FragB b;
+                frag_b(b, xp[8 * NSTEP * i * PS + p0], tail ? 0.f : xp[8 * NSTEP * i * PS + p0 + 4]);
+                mma3(c[i], a, b);
+            }
+        }
     }
+#pragma unroll
+    for (int i = 0; i < NU; ++i) { acc[4 * i] = c[i][0]; acc[4 * i + 1] = c[i][1]; acc[4 * i + 2] = c[i][2]; acc[4 * i + 3] = c[i][3]; }
+#else
+    for (int i = 0; i < wfrag_units(MT, NT); ++i)
+        for (int r = 0; r < 4; ++r) {
+            const int j = wfrag_row(tid, i, r, MT), k = wfrag_col(tid, i, r, MT);
+            if (k >= 8 * NT) continue;
+            float s = 0.f;
+            for (int p = 0; p < P; ++p) s += DY[j * PS + p] * X[k * PS + p];
+            acc[4 * i + r] += s;
+        }
+#endif
 }
 
 // ------------------------------------------------------------------------------------------------
@@ -346,8 +431,8 @@ OO_DEV void gram_stage(int tid, float* __restrict__ sm, const float* __restrict_
 OO_DEV void zero_pad_rows(int tid, float* sm) {
     for (int i = tid; i < PS; i += NTHREADS) {
         sm[(R_E1 + E1) * PS + i] = 0.f;
-        sm[(R_E2 + E2) * PS + i] = 0.f;
-        sm[(R_E2 + E2 + 1) * PS + i] = 0.f;
+#pragma unroll
+        for (int q = E2; q < E2P; ++q) sm[(R_E2 + q) * PS + i] = 0.f;
         sm[(R_T + 3) * PS + i] = 0.f;
         sm[(R_MISC + M_HU) * PS + i] = 0.f;
         sm[(R_MISC + M_HU + 1) * PS + i] = 0.f;
@@ -414,16 +499,17 @@ OO_DEV void tile_phase(int tid, float* __restrict__ sm, const TileCtx& c, TileAc
             }
         }
     } else if constexpr (PH == 2) {
-        gemm_fwd<KP_IN, WS_IN, true>(tid, w + W_IN, w + B_IN, act + R_E1 * PS, act + R_H1 * PS);
+        gemm_fwd<KP_IN, WS_IN, 2, true>(tid, w + W_IN, w + B_IN, act + R_E1 * PS, act + R_H1 * PS);
     } else if constexpr (PH == 3) {
-        gemm_fwd<H, WS_H, true>(tid, w + W_M1, w + B_M1, act + R_H1 * PS, act + R_H2 * PS);
+        gemm_fwd<H, WS_H, 2, true>(tid, w + W_M1, w + B_M1, act + R_H1 * PS, act + R_H2 * PS);
     } else if constexpr (PH == 4) {
-        gemm_fwd<KP_CAT, WS_CAT, true>(tid, w + W_CAT, w + B_CAT, act + R_H2 * PS, act + R_H3 * PS);
+        gemm_fwd<KP_CAT, WS_CAT, 2, true>(tid, w + W_CAT, w + B_CAT, act + R_H2 * PS, act + R_H3 * PS);
     } else if constexpr (PH == 5) {
-        gemm_fwd<H, WS_H, true>(tid, w + W_M2, w + B_M2, act + R_H3 * PS, act + R_H4 * PS);
+        gemm_fwd<H, WS_H, 2, true>(tid, w + W_M2, w + B_M2, act + R_H3 * PS, act + R_H4 * PS);
     } else if constexpr (PH == 6) {
-        gemm_fwd<KP_HD, WS_HD, true>(tid, w + W_CL, w + B_CL, act + R_H4 * PS, act + R_HC * PS);
-        if (PART) gemm_fwd<KP_HD, WS_HD, true>(tid, w + W_CP, w + B_CP, act + R_H4 * PS, act + R_HP * PS);
+        // [color_linear ; clip_linear] share their input: one GEMM with 64 output rows when the clip head is live
+        if (PART) gemm_fwd<KP_HD, WS_HD, 4, true>(tid, w + W_CL, w + B_CL, act + R_H4 * PS, act + R_HC * PS);
+        else gemm_fwd<KP_HD, WS_HD, 2, true>(tid, w + W_CL, w + B_CL, act + R_H4 * PS, act + R_HC * PS);
     } else if constexpr (PH == 7) {
         // out_alpha (x10, model.py:88) -> occupancy = sigmoid (render_rays.py:13); out_color -> sigmoid (model.py:96)
         for (int i = tid; i < 4 * P; i += NTHREADS) {
@@ -757,39 +843,33 @@ OO_DEV void tile_phase(int tid, float* __restrict__ sm, const TileCtx& c, TileAc
         }
     } else if constexpr (PH == 20) {
         // [color_linear ; clip_linear] weight gradient: rows = [d_hc ; d_hp], cols = [h4 ; e2]
-        if (tid < 8 * (KP_HD / 4)) {
-            if (PART) gemm_bwd_w<8, KP_HD / 4>(a.hd, tid & 7, tid >> 3, act + R_HC * PS, act + R_H4 * PS, 0, P);
-            else gemm_bwd_w<4, KP_HD / 4>(a.hd, tid & 7, tid >> 3, act + R_HC * PS, act + R_H4 * PS, 0, P);
-        }
+        if (PART) gemm_bwd_w<4, KP_HD / 8>(a.hd, tid, act + R_HC * PS, act + R_H4 * PS);
+        else gemm_bwd_w<2, KP_HD / 8>(a.hd, tid, act + R_HC * PS, act + R_H4 * PS);
     } else if constexpr (PH == 21) {
         // d[h4 ; e2] = W_cl^T d_hc + W_cp^T d_hp (+ W_a draw on the h4 rows), ReLU mask on the h4 rows; in place
         if (PART)
-            gemm_bwd_data<KP_HD, WS_HD, 2 * H, 1, 0>(tid, w + W_CL, act + R_HC * PS, nullptr, nullptr,
+            gemm_bwd_data<KP_HD, WS_HD, 2 * H, 8, 0>(tid, w + W_CL, act + R_HC * PS, nullptr, nullptr,
                                                      act + R_H4 * PS, H, w + W_A, misc + M_DRAW * PS);
         else
-            gemm_bwd_data<KP_HD, WS_HD, H, 1, 0>(tid, w + W_CL, act + R_HC * PS, nullptr, nullptr,
+            gemm_bwd_data<KP_HD, WS_HD, H, 8, 0>(tid, w + W_CL, act + R_HC * PS, nullptr, nullptr,
                                                  act + R_H4 * PS, H, w + W_A, misc + M_DRAW * PS);
     } else if constexpr (PH == 22) {
-        const int g = tid >> 6, t = tid & 63;
-        gemm_bwd_w<4, H / 4>(a.m2, t & 7, t >> 3, act + R_H4 * PS, act + R_H3 * PS, pgroup_begin(g), pgroup_end(g));
+        gemm_bwd_w<2, H / 8>(a.m2, tid, act + R_H4 * PS, act + R_H3 * PS);
     } else if constexpr (PH == 23) {
-        gemm_bwd_data<H, WS_H, H, 1, 0>(tid, w + W_M2, act + R_H4 * PS, nullptr, nullptr, act + R_H3 * PS, H,
+        gemm_bwd_data<H, WS_H, H, 8, 0>(tid, w + W_M2, act + R_H4 * PS, nullptr, nullptr, act + R_H3 * PS, H,
                                         nullptr, nullptr);
     } else if constexpr (PH == 24) {
-        if (tid < 8 * (KP_CAT / 4))
-            gemm_bwd_w<4, KP_CAT / 4>(a.cat, tid & 7, tid >> 3, act + R_H3 * PS, act + R_H2 * PS, 0, P);
+        gemm_bwd_w<2, KP_CAT / 8>(a.cat, tid, act + R_H3 * PS, act + R_H2 * PS);
     } else if constexpr (PH == 25) {
-        gemm_bwd_data<H, WS_CAT, H, 1, 0>(tid, w + W_CAT, act + R_H3 * PS, nullptr, nullptr, act + R_H2 * PS, H,
+        gemm_bwd_data<H, WS_CAT, H, 8, 0>(tid, w + W_CAT, act + R_H3 * PS, nullptr, nullptr, act + R_H2 * PS, H,
                                           nullptr, nullptr);
     } else if constexpr (PH == 26) {
-        const int g = tid >> 6, t = tid & 63;
-        gemm_bwd_w<4, H / 4>(a.m1, t & 7, t >> 3, act + R_H2 * PS, act + R_H1 * PS, pgroup_begin(g), pgroup_end(g));
+        gemm_bwd_w<2, H / 8>(a.m1, tid, act + R_H2 * PS, act + R_H1 * PS);
     } else if constexpr (PH == 27) {
-        gemm_bwd_data<H, WS_H, H, 1, 0>(tid, w + W_M1, act + R_H2 * PS, nullptr, nullptr, act + R_H1 * PS, H,
+        gemm_bwd_data<H, WS_H, H, 8, 0>(tid, w + W_M1, act + R_H2 * PS, nullptr, nullptr, act + R_H1 * PS, H,
                                         nullptr, nullptr);
     } else if constexpr (PH == 28) {
-        if (tid < 8 * (KP_IN / 4))
-            gemm_bwd_w<4, KP_IN / 4>(a.in, tid & 7, tid >> 3, act + R_H1 * PS, act + R_E1 * PS, 0, P);
+        gemm_bwd_w<2, KP_IN / 8>(a.in, tid, act + R_H1 * PS, act + R_E1 * PS);
     } else if constexpr (PH == 29) {
         // d e1 = W_cat[:, 32:]^T d_h3 + W_in^T d_h1, in place over e1 (no mask)
         gemm_bwd_data<KP_IN, WS_CAT, H, WS_IN, H>(tid, w + W_CAT + H, act + R_H3 * PS, w + W_IN, act + R_H1 * PS,
@@ -851,56 +931,31 @@ OO_DEV void tile_phase(int tid, float* __restrict__ sm, const TileCtx& c, TileAc
 
 // ------------------------------------------------------------------------------------------------
 // flush one (CTA, object) slot: registers -> slab in the reference's tensor layouts
-// (the out_clip gradient is already in the slab, transposed; see phase 14)
 // ------------------------------------------------------------------------------------------------
-// step 0: in/cat/heads/small from registers -> slab, mid1 point-group partials -> scratch;
-// step 1: mid1 sum -> slab; step 2: mid2 partials -> scratch, ray loss partials -> smem;
-// step 3: mid2 sum -> slab, loss sum -> slot_loss.  A block barrier follows every step.
-OO_DEV void flush_partials32(int tid, float* scratch, const float* acc) {
-    const int g = tid >> 6, t = tid & 63, ji = t & 7, ki = t >> 3;
+// step 0: every register accumulator -> slab, ray loss partials -> smem; step 1: loss sum -> slot_loss.
+// A block barrier follows every step.
+template <int MT, int NT>
+OO_DEV void flush_wfrags(int tid, float* __restrict__ slab, const float* acc, int off_lo, int off_hi, int cols) {
+    // rows j < 32 go to the tensor at off_lo, rows 32..63 (clip_linear) to off_hi; both [32][cols] row-major
 #pragma unroll
-    for (int jj = 0; jj < 4; ++jj)
+    for (int i = 0; i < wfrag_units(MT, NT); ++i)
 #pragma unroll
-        for (int kk = 0; kk < 4; ++kk) scratch[g * 1024 + (ji + 8 * jj) * H + ki + 8 * kk] = acc[jj * 4 + kk];
+        for (int r = 0; r < 4; ++r) {
+            const int j = wfrag_row(tid, i, r, MT), k = wfrag_col(tid, i, r, MT);
+            if (k < cols && k < 8 * NT) slab[(j < H ? off_lo + j * cols : off_hi + (j - H) * cols) + k] = acc[4 * i + r];
+        }
 }
 
 template <int STEP, bool PART>
 OO_DEV void tile_flush(int tid, float* __restrict__ sm, float* __restrict__ slab, float* __restrict__ slot_loss,
                        const TileAcc& a) {
-    float* scratch = sm + SM_FEAT;   // [4][1024]
     if constexpr (STEP == 0) {
-        if (tid < 8 * (KP_IN / 4)) {
-            const int ji = tid & 7, ki = tid >> 3;
-#pragma unroll
-            for (int jj = 0; jj < 4; ++jj)
-#pragma unroll
-                for (int kk = 0; kk < 4; ++kk) {
-                    const int k = ki + (KP_IN / 4) * kk;
-                    if (k < E1) slab[OFF_IN_W + (ji + 8 * jj) * E1 + k] = a.in[jj * 4 + kk];
-                }
-        }
-        if (tid < 8 * (KP_CAT / 4)) {
-            const int ji = tid & 7, ki = tid >> 3;
-#pragma unroll
-            for (int jj = 0; jj < 4; ++jj)
-#pragma unroll
-                for (int kk = 0; kk < 4; ++kk) {
-                    const int k = ki + (KP_CAT / 4) * kk;
-                    if (k < H + E1) slab[OFF_CAT_W + (ji + 8 * jj) * (H + E1) + k] = a.cat[jj * 4 + kk];
-                }
-        }
-        if (tid < 8 * (KP_HD / 4)) {
-            const int ji = tid & 7, ki = tid >> 3;
-#pragma unroll
-            for (int jj = 0; jj < (PART ? 8 : 4); ++jj)
-#pragma unroll
-                for (int kk = 0; kk < 4; ++kk) {
-                    const int k = ki + (KP_HD / 4) * kk;
-                    const int j = ji + 8 * jj;
-                    if (k < H + E2)
-                        slab[(j < H ? OFF_CL_W + j * (H + E2) : OFF_CP_W + (j - H) * (H + E2)) + k] = a.hd[jj * 4 + kk];
-                }
-        }
+        flush_wfrags<2, KP_IN / 8>(tid, slab, a.in, OFF_IN_W, 0, E1);
+        flush_wfrags<2, KP_CAT / 8>(tid, slab, a.cat, OFF_CAT_W, 0, H + E1);
+        flush_wfrags<2, H / 8>(tid, slab, a.m1, OFF_M1_W, 0, H);
+        flush_wfrags<2, H / 8>(tid, slab, a.m2, OFF_M2_W, 0, H);
+        if (PART) flush_wfrags<4, KP_HD / 8>(tid, slab, a.hd, OFF_CL_W, OFF_CP_W, H + E2);
+        else flush_wfrags<2, KP_HD / 8>(tid, slab, a.hd, OFF_CL_W, 0, H + E2);
         if (tid < 3 * H) slab[OFF_OC_W + tid] = a.s0;
         else if (tid < 4 * H) slab[OFF_A_W + tid - 3 * H] = a.s0;
         if (tid < 6 * H) {
@@ -918,12 +973,6 @@ OO_DEV void tile_flush(int tid, float* __restrict__ sm, float* __restrict__ slab
             st4(slab + SLAB_M + 4 * tid, float4{a.gm[0], a.gm[1], a.gm[2], a.gm[3]});
             if (tid <= H) slab[SLAB_MV + tid] = a.s3;     // m[0..31], beta at SLAB_MV + 32 == SLAB_BETA
         }
-        flush_partials32(tid, scratch, a.m1);
-    } else if constexpr (STEP == 1) {
-        for (int i = tid; i < H * H; i += NTHREADS)
-            slab[OFF_M1_W + i] = (scratch[i] + scratch[1024 + i]) + (scratch[2048 + i] + scratch[3072 + i]);
-    } else if constexpr (STEP == 2) {
-        flush_partials32(tid, scratch, a.m2);
         if (tid < RT) {
             float* rvl = sm + SM_RV;
             rvl[V_LD * RP + tid] = a.loss[0];
@@ -932,8 +981,6 @@ OO_DEV void tile_flush(int tid, float* __restrict__ sm, float* __restrict__ slab
             rvl[V_LF * RP + tid] = a.loss[3];
         }
     } else {
-        for (int i = tid; i < H * H; i += NTHREADS)
-            slab[OFF_M2_W + i] = (scratch[i] + scratch[1024 + i]) + (scratch[2048 + i] + scratch[3072 + i]);
         if (tid < 4) {
             const float* rvl = sm + SM_RV + (V_LD + tid) * RP;
             float sum = 0.f;
@@ -943,6 +990,6 @@ OO_DEV void tile_flush(int tid, float* __restrict__ sm, float* __restrict__ slab
     }
 }
 
-constexpr int N_FLUSH_STEPS = 4;   // barrier after each
+constexpr int N_FLUSH_STEPS = 2;   // barrier after each
 
 }  // namespace oo

@@ -111,8 +111,6 @@ __global__ void __launch_bounds__(NTHREADS, 1) k_train(const TrainParams prm) {
             float* sl = prm.slot_loss + 4 * slot;
             tile_flush<0, PART>(tid, sm, c.slab, sl, acc); __syncthreads();
             tile_flush<1, PART>(tid, sm, c.slab, sl, acc); __syncthreads();
-            tile_flush<2, PART>(tid, sm, c.slab, sl, acc); __syncthreads();
-            tile_flush<3, PART>(tid, sm, c.slab, sl, acc); __syncthreads();
             acc_zero(acc);
             ++slot;
             cur_obj = -1;

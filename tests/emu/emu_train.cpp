@@ -87,8 +87,6 @@ void emulate(const float* theta, const float* derived, int n_obj, const float* p
                 float* sl = slot_loss.data() + 4 * slot;
                 for (int tid = 0; tid < NTHREADS; ++tid) tile_flush<0, PART>(tid, sm, c.slab, sl, acc[tid]);
                 for (int tid = 0; tid < NTHREADS; ++tid) tile_flush<1, PART>(tid, sm, c.slab, sl, acc[tid]);
-                for (int tid = 0; tid < NTHREADS; ++tid) tile_flush<2, PART>(tid, sm, c.slab, sl, acc[tid]);
-                for (int tid = 0; tid < NTHREADS; ++tid) tile_flush<3, PART>(tid, sm, c.slab, sl, acc[tid]);
                 for (auto& a : acc) acc_zero(a);
                 ++slot;
                 cur_obj = -1;
