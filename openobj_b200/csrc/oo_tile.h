@@ -151,13 +151,14 @@ OO_DEV void frag_b(FragB& f, float b0, float b1) {
 #endif
 
 // Y[j][p] = act(b[j] + sum_k W[j][k] X[k][p]), 16*MT output rows, P points, K % 8 == 0.  M = j, N = p.
-template <int K, int WS, int MT, bool RELU>
-OO_DEV void gemm_fwd(int tid, const float* __restrict__ W, const float* __restrict__ bias,
-                     const float* __restrict__ X, float* __restrict__ Y) {
+// A warp owns NU or NU-1 output tiles; the body is instantiated for both counts so that it has no branches and the
+// independent accumulator chains interleave.
 #ifdef __CUDACC__
-    static_assert(8 % MT == 0 && K % 8 == 0 && WS % 2 == 0, "gemm_fwd tiling");
-    constexpr int NU = wfrag_units(MT, NT_P), NSTEP = 8 / MT;
-    const int warp = tid >> 5, lane = tid & 31, g = lane >> 2, t = lane & 3;
+template <int K, int WS, int MT, bool RELU, int NU>
+OO_DEV void gemm_fwd_body(int warp, int lane, const float* __restrict__ W, const float* __restrict__ bias,
+                          const float* __restrict__ X, float* __restrict__ Y) {
+    constexpr int NSTEP = 8 / MT;
+    const int g = lane >> 2, t = lane & 3;
     const int m = warp % MT, n0 = warp / MT;
     float acc[NU][4];
     {
@@ -173,19 +174,20 @@ OO_DEV void gemm_fwd(int tid, const float* __restrict__ W, const float* __restri
         const float2 w_hi = *reinterpret_cast<const float2*>(wp + 8 * WS + k0);
         FragA a;
         frag_a(a, w_lo.x, w_hi.x, w_lo.y, w_hi.y);
+        FragB b[NU];
 #pragma unroll
-        for (int i = 0; i < NU; ++i) {
-            if (n0 + NSTEP * i < NT_P) {              // warp-uniform
-                FragB b;
-                frag_b(b, xp[k0 * PS + 8 * NSTEP * i], xp[(k0 + 1) * PS + 8 * NSTEP * i]);
-                mma3(acc[i], a, b);
-            }
-        }
+        for (int i = 0; i < NU; ++i) frag_b(b[i], xp[k0 * PS + 8 * NSTEP * i], xp[(k0 + 1) * PS + 8 * NSTEP * i]);
+#pragma unroll
+        for (int i = 0; i < NU; ++i) mma_tf32(acc[i], a.lo, b[i].hi);
+#pragma unroll
+        for (int i = 0; i < NU; ++i) mma_tf32(acc[i], a.hi, b[i].lo);
+#pragma unroll
+        for (int i = 0; i < NU; ++i) mma_tf32(acc[i], a.hi, b[i].hi);
     }
 #pragma unroll
     for (int i = 0; i < NU; ++i) {
         const int p = 8 * (n0 + NSTEP * i) + 2 * t;
-        if (n0 + NSTEP * i < NT_P && p < P) {
+        if (p < P) {
             float2 y0 = {acc[i][0], acc[i][1]}, y1 = {acc[i][2], acc[i][3]};
             if (RELU) {
                 y0.x = fmaxf(y0.x, 0.f); y0.y = fmaxf(y0.y, 0.f); y1.x = fmaxf(y1.x, 0.f); y1.y = fmaxf(y1.y, 0.f);
@@ -194,6 +196,18 @@ OO_DEV void gemm_fwd(int tid, const float* __restrict__ W, const float* __restri
             *reinterpret_cast<float2*>(Y + (16 * m + g + 8) * PS + p) = y1;
         }
     }
+}
+#endif
+
+template <int K, int WS, int MT, bool RELU>
+OO_DEV void gemm_fwd(int tid, const float* __restrict__ W, const float* __restrict__ bias,
+                     const float* __restrict__ X, float* __restrict__ Y) {
+#ifdef __CUDACC__
+    static_assert(8 % MT == 0 && K % 8 == 0 && WS % 2 == 0, "gemm_fwd tiling");
+    constexpr int NU = wfrag_units(MT, NT_P), NSTEP = 8 / MT;
+    const int warp = tid >> 5, lane = tid & 31;
+    if (warp / MT + NSTEP * (NU - 1) < NT_P) gemm_fwd_body<K, WS, MT, RELU, NU>(warp, lane, W, bias, X, Y);
+    else gemm_fwd_body<K, WS, MT, RELU, NU - 1>(warp, lane, W, bias, X, Y);
 #else
     if (tid != 0) return;
     for (int j = 0; j < 16 * MT; ++j)
@@ -209,10 +223,82 @@ OO_DEV void gemm_fwd(int tid, const float* __restrict__ W, const float* __restri
 //            + [k < 32 && wa] wa[k] * draw[p] ),  written IN PLACE over X (rows 0..K-1).  M = k (MT = ceil(K/16) row
 // tiles; rows >= K are computed from whatever follows the weights and never stored), N = p, contraction over j.
 // An output tile reads and writes only its own 16 x 8 block of X, so in-place is safe across warps.
-// Work split: warp w owns point tile w with all row tiles (job 0); warps 0..3 also own point tile w + 8, and the row
-// tiles of the 13th point tile are shared out between warps 5..7 (job 1), so the four schedulers carry 3, 3.4, 3.4, 3.4
-// point tiles.  Each DY fragment is split once per k-step and reused for every row tile, each weight fragment serves both
-// jobs.
+// Work split: warp w owns point tile w with all row tiles; warps 0..3 also own point tile w + 8 (NQ = 2: each weight
+// fragment serves both point tiles, each DY fragment every row tile); the row tiles of the 13th point tile are shared out
+// between warps 5..7 in a short second pass, so the four schedulers carry 3, 3.4, 3.4, 3.4 point tiles.
+#ifdef __CUDACC__
+struct BwdDataArgs {
+    const float *W0, *DY0, *W1, *DY1;
+    float* X;
+    int relu_rows;
+    const float *wa, *draw;
+};
+
+// row tiles [mb, mb + MTN) of NQ point tiles starting at tile n0 (stride 8 tiles)
+template <int K, int WS0, int J0, int WS1, int J1, int MTN, int NQ>
+OO_DEV void gemm_bwd_data_body(int lane, int mb, int n0, const BwdDataArgs& q) {
+    const int g = lane >> 2, t = lane & 3;
+    float acc[MTN][NQ][4];
+#pragma unroll
+    for (int m = 0; m < MTN; ++m)
+#pragma unroll
+        for (int i = 0; i < NQ; ++i) acc[m][i][0] = acc[m][i][1] = acc[m][i][2] = acc[m][i][3] = 0.f;
+#pragma unroll
+    for (int term = 0; term < (J1 > 0 ? 2 : 1); ++term) {
+        const int WS = term == 0 ? WS0 : WS1, J = term == 0 ? J0 : J1;
+        const float* wp = (term == 0 ? q.W0 : q.W1) + t * WS + 16 * mb + g;
+        const float* dp = (term == 0 ? q.DY0 : q.DY1) + t * PS + 8 * n0 + g;
+#pragma unroll 1
+        for (int j0 = 0; j0 < J; j0 += 8) {
+            FragB b[NQ];
+#pragma unroll
+            for (int i = 0; i < NQ; ++i) frag_b(b[i], dp[j0 * PS + 64 * i], dp[(j0 + 4) * PS + 64 * i]);
+            FragA a[MTN];
+#pragma unroll
+            for (int m = 0; m < MTN; ++m)
+                frag_a(a[m], wp[j0 * WS + 16 * m], wp[j0 * WS + 16 * m + 8], wp[(j0 + 4) * WS + 16 * m], wp[(j0 + 4) * WS + 16 * m + 8]);
+#pragma unroll
+            for (int m = 0; m < MTN; ++m)
+#pragma unroll
+                for (int i = 0; i < NQ; ++i) mma_tf32(acc[m][i], a[m].lo, b[i].hi);
+#pragma unroll
+            for (int m = 0; m < MTN; ++m)
+#pragma unroll
+                for (int i = 0; i < NQ; ++i) mma_tf32(acc[m][i], a[m].hi, b[i].lo);
+#pragma unroll
+            for (int m = 0; m < MTN; ++m)
+#pragma unroll
+                for (int i = 0; i < NQ; ++i) mma_tf32(acc[m][i], a[m].hi, b[i].hi);
+        }
+    }
+#pragma unroll
+    for (int i = 0; i < NQ; ++i) {
+        const int p = 8 * n0 + 64 * i + 2 * t;
+        if (p >= P) continue;
+        float2 dr = {0.f, 0.f};
+        if (q.wa != nullptr) dr = *reinterpret_cast<const float2*>(q.draw + p);
+#pragma unroll
+        for (int m = 0; m < MTN; ++m)
+#pragma unroll
+            for (int h = 0; h < 2; ++h) {
+                const int k = 16 * (mb + m) + g + 8 * h;
+                if (k < K) {
+                    float2 o = {acc[m][i][2 * h], acc[m][i][2 * h + 1]};
+                    if (q.wa != nullptr && k < H) {
+                        o.x += q.wa[k] * dr.x; o.y += q.wa[k] * dr.y;
+                    }
+                    float2* xp = reinterpret_cast<float2*>(q.X + k * PS + p);
+                    if (k < q.relu_rows) {
+                        const float2 hv = *xp;
+                        o.x = hv.x > 0.f ? o.x : 0.f; o.y = hv.y > 0.f ? o.y : 0.f;
+                    }
+                    *xp = o;
+                }
+            }
+    }
+}
+#endif
+
 template <int K, int WS0, int J0, int WS1, int J1>
 OO_DEV void gemm_bwd_data(int tid, const float* __restrict__ W0, const float* __restrict__ DY0,
                           const float* __restrict__ W1, const float* __restrict__ DY1,
@@ -220,62 +306,16 @@ OO_DEV void gemm_bwd_data(int tid, const float* __restrict__ W0, const float* __
 #ifdef __CUDACC__
     static_assert(J0 % 8 == 0 && J1 % 8 == 0, "gemm_bwd_data tiling");
     constexpr int MT = (K + 15) / 16, MSPLIT = (MT + 2) / 3;
-    const int warp = tid >> 5, lane = tid & 31, g = lane >> 2, t = lane & 3;
-    const int n1 = warp < 4 ? warp + 8 : NT_P - 1;
-    const int mb1 = warp < 4 ? 0 : warp == 4 ? MT : (warp - 5) * MSPLIT;
-    const int me1 = warp < 4 ? MT : warp == 4 ? MT : (mb1 + MSPLIT < MT ? mb1 + MSPLIT : MT);
-    const bool job1 = mb1 < me1;
-    float acc[MT][2][4];
-#pragma unroll
-    for (int m = 0; m < MT; ++m)
-#pragma unroll
-        for (int q = 0; q < 2; ++q) acc[m][q][0] = acc[m][q][1] = acc[m][q][2] = acc[m][q][3] = 0.f;
-#pragma unroll
-    for (int term = 0; term < (J1 > 0 ? 2 : 1); ++term) {
-        const float* W = term == 0 ? W0 : W1;
-        const float* DY = term == 0 ? DY0 : DY1;
-        const int WS = term == 0 ? WS0 : WS1, J = term == 0 ? J0 : J1;
-        const float* wp = W + t * WS + g;
-        const float* dp = DY + t * PS + g;
-#pragma unroll 1
-        for (int j0 = 0; j0 < J; j0 += 8) {
-            FragB b0, b1;
-            frag_b(b0, dp[j0 * PS + 8 * warp], dp[(j0 + 4) * PS + 8 * warp]);
-            if (job1) frag_b(b1, dp[j0 * PS + 8 * n1], dp[(j0 + 4) * PS + 8 * n1]);
-#pragma unroll
-            for (int m = 0; m < MT; ++m) {
-                FragA a;
-                frag_a(a, wp[j0 * WS + 16 * m], wp[j0 * WS + 16 * m + 8], wp[(j0 + 4) * WS + 16 * m], wp[(j0 + 4) * WS + 16 * m + 8]);
-                mma3(acc[m][0], a, b0);
-                if (m >= mb1 && m < me1) mma3(acc[m][1], a, b1);      // warp-uniform
-            }
-        }
-    }
-#pragma unroll
-    for (int q = 0; q < 2; ++q) {
-        const int p = 8 * (q == 0 ? warp : n1) + 2 * t;
-        if (p >= P) continue;
-        float2 dr = {0.f, 0.f};
-        if (wa != nullptr) dr = *reinterpret_cast<const float2*>(draw + p);
-#pragma unroll
-        for (int m = 0; m < MT; ++m) {
-            if (q == 1 && !(m >= mb1 && m < me1)) continue;
-#pragma unroll
-            for (int h = 0; h < 2; ++h) {
-                const int k = 16 * m + g + 8 * h;
-                if (k < K) {
-                    float2 o = {acc[m][q][2 * h], acc[m][q][2 * h + 1]};
-                    if (wa != nullptr && k < H) {
-                        o.x += wa[k] * dr.x; o.y += wa[k] * dr.y;
-                    }
-                    float2* xp = reinterpret_cast<float2*>(X + k * PS + p);
-                    if (k < relu_rows) {
-                        const float2 hv = *xp;
-                        o.x = hv.x > 0.f ? o.x : 0.f; o.y = hv.y > 0.f ? o.y : 0.f;
-                    }
-                    *xp = o;
-                }
-            }
+    const int warp = tid >> 5, lane = tid & 31;
+    const BwdDataArgs q = {W0, DY0, W1, DY1, X, relu_rows, wa, draw};
+    if (warp < 4) {
+        gemm_bwd_data_body<K, WS0, J0, WS1, J1, MT, 2>(lane, 0, warp, q);
+    } else {
+        gemm_bwd_data_body<K, WS0, J0, WS1, J1, MT, 1>(lane, 0, warp, q);
+        if (warp >= 5) {                       // a third of the row tiles of the last point tile
+            const int mb = (warp - 5) * MSPLIT;
+            if (mb + MSPLIT <= MT) gemm_bwd_data_body<K, WS0, J0, WS1, J1, MSPLIT, 1>(lane, mb, NT_P - 1, q);
+            else if (mb < MT) gemm_bwd_data_body<K, WS0, J0, WS1, J1, (MT % MSPLIT ? MT % MSPLIT : 1), 1>(lane, mb, NT_P - 1, q);
         }
     }
 #else
@@ -294,35 +334,52 @@ OO_DEV void gemm_bwd_data(int tid, const float* __restrict__ W0, const float* __
 
 // acc fragment i (+)= sum_p DY[j][p] X[k][p] over the tile's points, for this thread's elements of output tiles
 // u = warp + 8 i of the [16 MT] x [8 NT] weight gradient.  M = j, N = k, contraction over points (the four points
-// of the last k-step that lie beyond P contribute zero).
+// of the last k-step that lie beyond P contribute zero).  Even and odd k-steps accumulate into separate fragments
+// (twice the independent chains for the scheduler), folded into the persistent accumulators at the end.
+#ifdef __CUDACC__
+template <int MT, int NT, int NU>
+OO_DEV void gemm_bwd_w_body(float* acc, int warp, int lane, const float* __restrict__ DY, const float* __restrict__ X) {
+    constexpr int NSTEP = 8 / MT;
+    const int g = lane >> 2, t = lane & 3;
+    const int m = warp % MT, n0 = warp / MT;
+    float c[2][NU][4];
+#pragma unroll
+    for (int i = 0; i < NU; ++i)
+#pragma unroll
+        for (int r = 0; r < 4; ++r) { c[0][i][r] = acc[4 * i + r]; c[1][i][r] = 0.f; }
+    const float* dp = DY + (16 * m + g) * PS + t;
+    const float* xp = X + (8 * n0 + g) * PS + t;
+#pragma unroll 2
+    for (int ks = 0; ks < NT_P; ++ks) {
+        const int p0 = 8 * ks;
+        const bool tail = p0 + t + 4 >= P;               // only in the last k-step
+        FragA a;
+        frag_a(a, dp[p0], dp[8 * PS + p0], tail ? 0.f : dp[p0 + 4], tail ? 0.f : dp[8 * PS + p0 + 4]);
+        FragB b[NU];
+#pragma unroll
+        for (int i = 0; i < NU; ++i) frag_b(b[i], xp[8 * NSTEP * i * PS + p0], tail ? 0.f : xp[8 * NSTEP * i * PS + p0 + 4]);
+#pragma unroll
+        for (int i = 0; i < NU; ++i) mma_tf32(c[ks & 1][i], a.lo, b[i].hi);
+#pragma unroll
+        for (int i = 0; i < NU; ++i) mma_tf32(c[ks & 1][i], a.hi, b[i].lo);
+#pragma unroll
+        for (int i = 0; i < NU; ++i) mma_tf32(c[ks & 1][i], a.hi, b[i].hi);
+    }
+#pragma unroll
+    for (int i = 0; i < NU; ++i)
+#pragma unroll
+        for (int r = 0; r < 4; ++r) acc[4 * i + r] = c[0][i][r] + c[1][i][r];
+}
+#endif
+
 template <int MT, int NT>
 OO_DEV void gemm_bwd_w(float* acc, int tid, const float* __restrict__ DY, const float* __restrict__ X) {
 #ifdef __CUDACC__
     static_assert(8 % MT == 0, "gemm_bwd_w tiling");
     constexpr int NU = wfrag_units(MT, NT), NSTEP = 8 / MT;
-    const int warp = tid >> 5, lane = tid & 31, g = lane >> 2, t = lane & 3;
-    const int m = warp % MT, n0 = warp / MT;
-    float c[NU][4];
-#pragma unroll
-    for (int i = 0; i < NU; ++i) { c[i][0] = acc[4 * i]; c[i][1] = acc[4 * i + 1]; c[i][2] = acc[4 * i + 2]; c[i][3] = acc[4 * i + 3]; }
-    const float* dp = DY + (16 * m + g) * PS + t;
-    const float* xp = X + (8 * n0 + g) * PS + t;
-#pragma unroll 2
-    for (int p0 = 0; p0 < 8 * NT_P; p0 += 8) {
-        const bool tail = p0 + t + 4 >= P;               // only in the last k-step
-        FragA a;
-        frag_a(a, dp[p0], dp[8 * PS + p0], tail ? 0.f : dp[p0 + 4], tail ? 0.f : dp[8 * PS + p0 + 4]);
-#pragma unroll
-        for (int i = 0; i < NU; ++i) {
-            if (n0 + NSTEP * i < NT) {                    // warp-uniform
-                FragB b;
-                frag_b(b, xp[8 * NSTEP * i * PS + p0], tail ? 0.f : xp[8 * NSTEP * i * PS + p0 + 4]);
-                mma3(c[i], a, b);
-            }
-        }
-    }
-#pragma unroll
-    for (int i = 0; i < NU; ++i) { acc[4 * i] = c[i][0]; acc[4 * i + 1] = c[i][1]; acc[4 * i + 2] = c[i][2]; acc[4 * i + 3] = c[i][3]; }
+    const int warp = tid >> 5, lane = tid & 31;
+    if (warp / MT + NSTEP * (NU - 1) < NT) gemm_bwd_w_body<MT, NT, NU>(acc, warp, lane, DY, X);
+    else if (NU > 1) gemm_bwd_w_body<MT, NT, (NU > 1 ? NU - 1 : 1)>(acc, warp, lane, DY, X);
 #else
     for (int i = 0; i < wfrag_units(MT, NT); ++i)
         for (int r = 0; r < 4; ++r) {
