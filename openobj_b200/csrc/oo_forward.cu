@@ -40,18 +40,16 @@ __global__ void __launch_bounds__(NTHREADS, 1) k_forward(const float* __restrict
     c.theta = th;
     float* act = sm + SM_ACT;
     float* misc = act + R_MISC * PS;
-    // out_clip rows of this thread (2 of 512) stay in registers for the whole CTA
-    float w0[H], w1[H], b0 = 0.f, b1 = 0.f;
+    // this thread's out_clip row (C == NTHREADS) stays in registers for the whole CTA
+    static_assert(C == NTHREADS, "k_forward maps one out_clip row to each thread");
+    float w0[H], b0 = 0.f;
     if (clip != nullptr) {
 #pragma unroll
         for (int j = 0; j < H; j += 4) {
             const float4 a = *reinterpret_cast<const float4*>(th + OFF_OCL_W + tid * H + j);
-            const float4 b = *reinterpret_cast<const float4*>(th + OFF_OCL_W + (tid + NTHREADS) * H + j);
             w0[j] = a.x; w0[j + 1] = a.y; w0[j + 2] = a.z; w0[j + 3] = a.w;
-            w1[j] = b.x; w1[j + 1] = b.y; w1[j + 2] = b.z; w1[j + 3] = b.w;
         }
         b0 = th[OFF_OCL_B + tid];
-        b1 = th[OFF_OCL_B + tid + NTHREADS];
     }
     const int n_tiles = (n_pts + P - 1) / P;
     for (int t = blockIdx.x; t < n_tiles; t += gridDim.x) {
@@ -86,15 +84,10 @@ __global__ void __launch_bounds__(NTHREADS, 1) k_forward(const float* __restrict
         }
         if (clip != nullptr) {
             for (int p = 0; p < c.npts; ++p) {
-                float f0 = b0, f1 = b1;
+                float f0 = b0;
 #pragma unroll
-                for (int j = 0; j < H; ++j) {
-                    const float h = act[(R_HP + j) * PS + p];
-                    f0 += w0[j] * h;
-                    f1 += w1[j] * h;
-                }
+                for (int j = 0; j < H; ++j) f0 += w0[j] * act[(R_HP + j) * PS + p];
                 clip[(base + p) * C + tid] = f0;
-                clip[(base + p) * C + tid + NTHREADS] = f1;
             }
         }
         __syncthreads();

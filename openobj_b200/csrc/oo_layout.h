@@ -63,7 +63,8 @@ constexpr int RT = 10;
 constexpr int P = RT * S;      // 100
 constexpr int PS = 100;        // row stride (floats); PS % 32 == 4: the tensor-core fragment loads (8 rows x 4 points, or
                                // 4 row pairs x 8 points) touch 32 distinct banks
-constexpr int NTHREADS = 256;
+constexpr int NTHREADS = 512;      // 16 warps: four per scheduler hide the tensor-pipe and shared-memory latencies
+constexpr int NWARPS = NTHREADS / 32;
 
 // activation rows
 constexpr int R_H2 = 0;        // fc2            } contiguous = cat_layer input [h2 ; e1]
@@ -79,7 +80,7 @@ constexpr int R_HP = 296;      // clip_linear out
 constexpr int R_T = 328;       // scaled coords t (3) + 1 spare
 constexpr int R_MISC = 332;    // 12 rows, see M_*
 constexpr int NROWS = 344;
-constexpr int M_OCC = 0, M_TERM = 1, M_DRAW = 2, M_COL = 3, M_DCOL = 6, M_FREE = 9, M_HU = 10;
+constexpr int M_OCC = 0, M_TERM = 1, M_DRAW = 2, M_COL = 3, M_DCOL = 6, M_FREE = 9, M_HU = 10, M_Z = 11;   // M_Z: z of the tile's points
 
 constexpr int SM_ACT = 0;
 constexpr int SM_W = NROWS * PS;                     // 34400
@@ -105,15 +106,19 @@ constexpr int RP = 12;                               // padded rays per row
 constexpr int SM_ST = SM_RAY;                        // S^T [32][12]   sum_i T_i hp_i
 constexpr int SM_UT = SM_ST + H * RP;                // U^T [32][12]   dL/dS
 constexpr int SM_RV = SM_UT + H * RP;                // ray values [24][12]
-constexpr int NRV = 24;
-constexpr int SM_UPART = SM_RV + NRV * RP;           // [8 warps][10][32] cross-warp partials of U
-constexpr int SM_COSP = SM_UPART;                    // cos partials [10][16][5] (dead before U is formed)
-constexpr int SM_FEAT = SM_UPART + 8 * RT * H;       // Y [10][512]: gt part features of the tile's rays (cp.async in phase 0)
-constexpr int SM_YS = SM_FEAT + RT * C;              // gt-feature statistics: partials [10][16][2], totals [2][12]
+constexpr int NRV = 27;                              // rows 0..23 per-ray values (zeroed with the tile), 24..26 per-object wb / bb
+constexpr int NRV_TILE = 24;
+constexpr int SM_UPART = SM_RV + NRV * RP;           // gs [32][12] = G S + opac wb (phase 12)
+constexpr int SM_FEAT = SM_UPART + H * RP;           // Y [10][512]: gt part features of the tile's rays (cp.async in phase 0);
+                                                     // phase 10 overwrites each warp's 32 columns with its partial W^T y
+constexpr int YSTR = C + 4;                          // row stride of Y: YSTR % 32 == 4 -> conflict-free A fragments in phase 10
+constexpr int SM_YS = SM_FEAT + RT * YSTR;              // gt-feature statistics: partials [10][16 warps][2], totals [2][12]
 constexpr int SM_TOTAL = SM_YS + 352;                // floats
 // ray-value rows
 constexpr int V_DEPTH = 0, V_OPAC = 1, V_COL = 2, V_GD = 5, V_GO = 6, V_GC = 7, V_CF = 10, V_BG = 11,
-              V_LD = 12, V_LC = 13, V_LO = 14, V_LF = 15, V_A = 16, V_B = 17, V_ZSRC = 18;
+              V_LD = 12, V_LC = 13, V_LO = 14, V_LF = 15, V_A = 16, V_B = 17, V_ZSRC = 18,
+              V_GTD = 19, V_LAB = 20, V_RGB = 21,      // gt depth, label, gt colour of the tile's rays (phase 0)
+              V_WB = 24;                               // W_ocl^T b_ocl [32] and b.b [1] of the current object (gram_stage)
 
 static_assert(SM_TOTAL * 4 <= 232448, "tile does not fit in 227 KB of shared memory");
 static_assert(PS % 4 == 0 && SM_W % 4 == 0 && SM_RAY % 4 == 0 && SM_FEAT % 4 == 0, "float4 alignment");

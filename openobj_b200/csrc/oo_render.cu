@@ -111,29 +111,22 @@ __device__ void emit_batch(int tid, float* sm, const RenderK& k, const float* th
     float* fin = sm + SM_FIN;
     const bool want_feat = k.a.feat != nullptr;
     if (want_feat) {
-        float f[2][RT];
-        const int c0 = tid, c1 = tid + NTHREADS;
-        const float b0 = th[OFF_OCL_B + c0], b1 = th[OFF_OCL_B + c1];
+        static_assert(C == NTHREADS, "emit_batch maps one out_clip row to each thread");
+        float f[RT];
+        const int c0 = tid;
+        const float b0 = th[OFF_OCL_B + c0];
 #pragma unroll
-        for (int r = 0; r < RT; ++r) {
-            const float op = fin[F_OPAC * RP + r];
-            f[0][r] = b0 * op;
-            f[1][r] = b1 * op;
-        }
+        for (int r = 0; r < RT; ++r) f[r] = b0 * fin[F_OPAC * RP + r];
         const float4* w0 = reinterpret_cast<const float4*>(th + OFF_OCL_W + c0 * H);
-        const float4* w1 = reinterpret_cast<const float4*>(th + OFF_OCL_W + c1 * H);
 #pragma unroll
         for (int j4 = 0; j4 < H / 4; ++j4) {
-            const float4 a = w0[j4], b = w1[j4];
-            const float wa[4] = {a.x, a.y, a.z, a.w}, wb[4] = {b.x, b.y, b.z, b.w};
+            const float4 a = w0[j4];
+            const float wa[4] = {a.x, a.y, a.z, a.w};
 #pragma unroll
             for (int q = 0; q < 4; ++q) {
                 const float* srow = sm + SM_ST + (4 * j4 + q) * RP;
 #pragma unroll
-                for (int r = 0; r < RT; ++r) {
-                    f[0][r] += wa[q] * srow[r];
-                    f[1][r] += wb[q] * srow[r];
-                }
+                for (int r = 0; r < RT; ++r) f[r] += wa[q] * srow[r];
             }
         }
 #pragma unroll
@@ -142,8 +135,7 @@ __device__ void emit_batch(int tid, float* sm, const RenderK& k, const float* th
                 const float d = fin[F_DEPTH * RP + r], op = fin[F_OPAC * RP + r];
                 const bool bad = d < fin[F_NEAR * RP + r] || d > fin[F_FAR * RP + r] || op < 0.9f;   // vmap.py:665,672
                 const size_t pix = (size_t)__float_as_int(fin[F_PIX * RP + r]);
-                k.a.feat[pix * C + c0] = bad ? 0.f : f[0][r];
-                k.a.feat[pix * C + c1] = bad ? 0.f : f[1][r];
+                k.a.feat[pix * C + c0] = bad ? 0.f : f[r];
             }
         }
     }

@@ -48,15 +48,15 @@ OO_DEV float sigmoidf_(float x) { return 1.0f / (1.0f + expf(-x)); }
 OO_DEV float sgnf_(float x) { return x > 0.f ? 1.f : (x < 0.f ? -1.f : 0.f); }
 
 // register-resident weight-gradient accumulators of one thread (live across all tiles of an object).  The five weight
-// matrices are accumulated as m16n8k8 C fragments: output tile u = warp + 8 i of a GEMM with MT row tiles (16 output
+// matrices are accumulated as m16n8k8 C fragments: output tile u = warp + NWARPS i of a GEMM with MT row tiles (16 output
 // rows j each) is (m = u % MT, n = u / MT); register r of fragment i holds row j = 16 m + lane/4 + 8 (r >> 1) and
 // input column k = 8 n + 2 (lane % 4) + (r & 1)   (see wfrag_row / wfrag_col).
 struct TileAcc {
-    float in[12];    // in_layer   : 2 x 11 tiles -> 3 fragments
-    float cat[16];   // cat_layer  : 2 x 15 tiles -> 4 fragments
-    float m1[4];     // mid1       : 2 x 4 tiles  -> 1 fragment
+    float in[8];     // in_layer   : 2 x 11 tiles -> 2 fragments
+    float cat[8];    // cat_layer  : 2 x 15 tiles -> 2 fragments
+    float m1[4];     // mid1       : 2 x 4 tiles  -> 1 fragment (warps 0..7)
     float m2[4];     // mid2
-    float hd[20];    // [color_linear ; clip_linear] : 4 x 10 tiles -> 5 fragments (part features off: 2 x 10 -> 3)
+    float hd[12];    // [color_linear ; clip_linear] : 4 x 10 tiles -> 3 fragments (part features off: 2 x 10 -> 2)
     float s0;        // out_color.weight (tid<96), out_alpha.weight (96<=tid<128)
     float s1;        // biases of the six hidden layers (tid<192), out_color.bias (192..194), out_alpha.bias (195)
     float s2;        // B_layer.weight (tid<63)
@@ -67,13 +67,11 @@ struct TileAcc {
 
 OO_DEV void acc_zero(TileAcc& a) {
 #pragma unroll
-    for (int i = 0; i < 12; ++i) a.in[i] = 0.f;
-#pragma unroll
-    for (int i = 0; i < 16; ++i) a.cat[i] = 0.f;
+    for (int i = 0; i < 8; ++i) a.in[i] = a.cat[i] = 0.f;
 #pragma unroll
     for (int i = 0; i < 4; ++i) a.m1[i] = a.m2[i] = 0.f;
 #pragma unroll
-    for (int i = 0; i < 20; ++i) a.hd[i] = 0.f;
+    for (int i = 0; i < 12; ++i) a.hd[i] = 0.f;
     a.s0 = a.s1 = a.s2 = a.s3 = 0.f;
     a.gm[0] = a.gm[1] = a.gm[2] = a.gm[3] = 0.f;
     a.loss[0] = a.loss[1] = a.loss[2] = a.loss[3] = 0.f;
@@ -112,16 +110,16 @@ struct TileCtx {
 // The k index inside a k-step is a dummy, so a fragment "slot" may hold any k as long as A and B agree: the forward
 // GEMM puts k0+2t in slot t and k0+2t+1 in slot t+4, which makes the weight fragment one 64-bit load and the activation
 // fragment bank-conflict free with the row stride PS = 100.
-// Work split: a GEMM with MT row tiles and NT column tiles has MT*NT output tiles; warp w owns tiles u = w + 8 i
+// Work split: a GEMM with MT row tiles and NT column tiles has MT*NT output tiles; warp w owns tiles u = w + NWARPS i
 // (m = u % MT, n = u / MT).  The host build (CPU tile emulator, tests only) replaces the fragment code by plain loops
 // with the same thread -> element ownership.
 // ------------------------------------------------------------------------------------------------
 constexpr int NT_P = (P + 7) / 8;      // 13 point tiles of 8 (the last one is half empty)
 
-OO_HOSTDEV inline constexpr int wfrag_units(int MT, int NT) { return (MT * NT + 7) / 8; }
+OO_HOSTDEV inline constexpr int wfrag_units(int MT, int NT) { return (MT * NT + NWARPS - 1) / NWARPS; }
 // which weight-gradient element register r of fragment i of thread tid holds (MT row tiles, NT column tiles)
-OO_HOSTDEV inline int wfrag_row(int tid, int i, int r, int MT) { return 16 * (((tid >> 5) + 8 * i) % MT) + ((tid & 31) >> 2) + 8 * (r >> 1); }
-OO_HOSTDEV inline int wfrag_col(int tid, int i, int r, int MT) { return 8 * (((tid >> 5) + 8 * i) / MT) + 2 * (tid & 3) + (r & 1); }
+OO_HOSTDEV inline int wfrag_row(int tid, int i, int r, int MT) { return 16 * (((tid >> 5) + NWARPS * i) % MT) + ((tid & 31) >> 2) + 8 * (r >> 1); }
+OO_HOSTDEV inline int wfrag_col(int tid, int i, int r, int MT) { return 8 * (((tid >> 5) + NWARPS * i) / MT) + 2 * (tid & 3) + (r & 1); }
 
 #ifdef __CUDACC__
 struct FragA { uint32_t hi[4], lo[4]; };
@@ -157,14 +155,19 @@ OO_DEV void frag_b(FragB& f, float b0, float b1) {
 template <int K, int WS, int MT, bool RELU, int NU>
 OO_DEV void gemm_fwd_body(int warp, int lane, const float* __restrict__ W, const float* __restrict__ bias,
                           const float* __restrict__ X, float* __restrict__ Y) {
-    constexpr int NSTEP = 8 / MT;
+    constexpr int NSTEP = NWARPS / MT;
     const int g = lane >> 2, t = lane & 3;
     const int m = warp % MT, n0 = warp / MT;
-    float acc[NU][4];
+    // three accumulator chains per output tile (lo*hi, hi*lo, hi*hi): the MMAs of one k-step are independent
+    float acc[NU][4], sm1[NU][4], sm2[NU][4];
     {
         const float b_lo = bias[16 * m + g], b_hi = bias[16 * m + g + 8];
 #pragma unroll
-        for (int i = 0; i < NU; ++i) { acc[i][0] = acc[i][1] = b_lo; acc[i][2] = acc[i][3] = b_hi; }
+        for (int i = 0; i < NU; ++i) {
+            acc[i][0] = acc[i][1] = b_lo; acc[i][2] = acc[i][3] = b_hi;
+            sm1[i][0] = sm1[i][1] = sm1[i][2] = sm1[i][3] = 0.f;
+            sm2[i][0] = sm2[i][1] = sm2[i][2] = sm2[i][3] = 0.f;
+        }
     }
     const float* wp = W + (16 * m + g) * WS + 2 * t;
     const float* xp = X + 2 * t * PS + 8 * n0 + g;
@@ -178,12 +181,16 @@ OO_DEV void gemm_fwd_body(int warp, int lane, const float* __restrict__ W, const
 #pragma unroll
         for (int i = 0; i < NU; ++i) frag_b(b[i], xp[k0 * PS + 8 * NSTEP * i], xp[(k0 + 1) * PS + 8 * NSTEP * i]);
 #pragma unroll
-        for (int i = 0; i < NU; ++i) mma_tf32(acc[i], a.lo, b[i].hi);
-#pragma unroll
-        for (int i = 0; i < NU; ++i) mma_tf32(acc[i], a.hi, b[i].lo);
-#pragma unroll
-        for (int i = 0; i < NU; ++i) mma_tf32(acc[i], a.hi, b[i].hi);
+        for (int i = 0; i < NU; ++i) {
+            mma_tf32(sm1[i], a.lo, b[i].hi);
+            mma_tf32(sm2[i], a.hi, b[i].lo);
+            mma_tf32(acc[i], a.hi, b[i].hi);
+        }
     }
+#pragma unroll
+    for (int i = 0; i < NU; ++i)
+#pragma unroll
+        for (int r = 0; r < 4; ++r) acc[i][r] += sm1[i][r] + sm2[i][r];
 #pragma unroll
     for (int i = 0; i < NU; ++i) {
         const int p = 8 * (n0 + NSTEP * i) + 2 * t;
@@ -203,11 +210,11 @@ template <int K, int WS, int MT, bool RELU>
 OO_DEV void gemm_fwd(int tid, const float* __restrict__ W, const float* __restrict__ bias,
                      const float* __restrict__ X, float* __restrict__ Y) {
 #ifdef __CUDACC__
-    static_assert(8 % MT == 0 && K % 8 == 0 && WS % 2 == 0, "gemm_fwd tiling");
-    constexpr int NU = wfrag_units(MT, NT_P), NSTEP = 8 / MT;
+    static_assert(NWARPS % MT == 0 && K % 8 == 0 && WS % 2 == 0, "gemm_fwd tiling");
+    constexpr int NU = wfrag_units(MT, NT_P), NSTEP = NWARPS / MT;
     const int warp = tid >> 5, lane = tid & 31;
     if (warp / MT + NSTEP * (NU - 1) < NT_P) gemm_fwd_body<K, WS, MT, RELU, NU>(warp, lane, W, bias, X, Y);
-    else gemm_fwd_body<K, WS, MT, RELU, NU - 1>(warp, lane, W, bias, X, Y);
+    else if (NU > 1) gemm_fwd_body<K, WS, MT, RELU, (NU > 1 ? NU - 1 : 1)>(warp, lane, W, bias, X, Y);
 #else
     if (tid != 0) return;
     for (int j = 0; j < 16 * MT; ++j)
@@ -223,9 +230,9 @@ OO_DEV void gemm_fwd(int tid, const float* __restrict__ W, const float* __restri
 //            + [k < 32 && wa] wa[k] * draw[p] ),  written IN PLACE over X (rows 0..K-1).  M = k (MT = ceil(K/16) row
 // tiles; rows >= K are computed from whatever follows the weights and never stored), N = p, contraction over j.
 // An output tile reads and writes only its own 16 x 8 block of X, so in-place is safe across warps.
-// Work split: warp w owns point tile w with all row tiles; warps 0..3 also own point tile w + 8 (NQ = 2: each weight
-// fragment serves both point tiles, each DY fragment every row tile); the row tiles of the 13th point tile are shared out
-// between warps 5..7 in a short second pass, so the four schedulers carry 3, 3.4, 3.4, 3.4 point tiles.
+// Work split: warps 0..11 own one point tile each with all row tiles (each DY fragment is split once per k-step and
+// reused for every row tile); the row tiles of the 13th point tile are shared out between warps 12..15, so every
+// scheduler carries 3.25 point tiles.
 #ifdef __CUDACC__
 struct BwdDataArgs {
     const float *W0, *DY0, *W1, *DY1;
@@ -234,68 +241,69 @@ struct BwdDataArgs {
     const float *wa, *draw;
 };
 
-// row tiles [mb, mb + MTN) of NQ point tiles starting at tile n0 (stride 8 tiles)
-template <int K, int WS0, int J0, int WS1, int J1, int MTN, int NQ>
+// row tiles [mb, mb + MTN) of point tile n0
+template <int K, int WS0, int J0, int WS1, int J1, int MTN>
 OO_DEV void gemm_bwd_data_body(int lane, int mb, int n0, const BwdDataArgs& q) {
+    constexpr int MG = MTN < 3 ? MTN : 3;            // row tiles whose weight fragments are live together
     const int g = lane >> 2, t = lane & 3;
-    float acc[MTN][NQ][4];
+    float acc[MTN][4], sml[MTN][4];          // hi*hi chain and the chain of the two small products
 #pragma unroll
-    for (int m = 0; m < MTN; ++m)
-#pragma unroll
-        for (int i = 0; i < NQ; ++i) acc[m][i][0] = acc[m][i][1] = acc[m][i][2] = acc[m][i][3] = 0.f;
+    for (int m = 0; m < MTN; ++m) {
+        acc[m][0] = acc[m][1] = acc[m][2] = acc[m][3] = 0.f;
+        sml[m][0] = sml[m][1] = sml[m][2] = sml[m][3] = 0.f;
+    }
 #pragma unroll
     for (int term = 0; term < (J1 > 0 ? 2 : 1); ++term) {
         const int WS = term == 0 ? WS0 : WS1, J = term == 0 ? J0 : J1;
         const float* wp = (term == 0 ? q.W0 : q.W1) + t * WS + 16 * mb + g;
         const float* dp = (term == 0 ? q.DY0 : q.DY1) + t * PS + 8 * n0 + g;
-#pragma unroll 1
+#pragma unroll 2
         for (int j0 = 0; j0 < J; j0 += 8) {
-            FragB b[NQ];
+            FragB b;
+            frag_b(b, dp[j0 * PS], dp[(j0 + 4) * PS]);
 #pragma unroll
-            for (int i = 0; i < NQ; ++i) frag_b(b[i], dp[j0 * PS + 64 * i], dp[(j0 + 4) * PS + 64 * i]);
-            FragA a[MTN];
+            for (int m0 = 0; m0 < MTN; m0 += MG) {
+                FragA a[MG];
 #pragma unroll
-            for (int m = 0; m < MTN; ++m)
-                frag_a(a[m], wp[j0 * WS + 16 * m], wp[j0 * WS + 16 * m + 8], wp[(j0 + 4) * WS + 16 * m], wp[(j0 + 4) * WS + 16 * m + 8]);
+                for (int m = 0; m < MG; ++m)
+                    if (m0 + m < MTN)
+                        frag_a(a[m], wp[j0 * WS + 16 * (m0 + m)], wp[j0 * WS + 16 * (m0 + m) + 8], wp[(j0 + 4) * WS + 16 * (m0 + m)],
+                               wp[(j0 + 4) * WS + 16 * (m0 + m) + 8]);
 #pragma unroll
-            for (int m = 0; m < MTN; ++m)
+                for (int m = 0; m < MG; ++m)
+                    if (m0 + m < MTN) { mma_tf32(sml[m0 + m], a[m].lo, b.hi); mma_tf32(acc[m0 + m], a[m].hi, b.hi); }
 #pragma unroll
-                for (int i = 0; i < NQ; ++i) mma_tf32(acc[m][i], a[m].lo, b[i].hi);
-#pragma unroll
-            for (int m = 0; m < MTN; ++m)
-#pragma unroll
-                for (int i = 0; i < NQ; ++i) mma_tf32(acc[m][i], a[m].hi, b[i].lo);
-#pragma unroll
-            for (int m = 0; m < MTN; ++m)
-#pragma unroll
-                for (int i = 0; i < NQ; ++i) mma_tf32(acc[m][i], a[m].hi, b[i].hi);
+                for (int m = 0; m < MG; ++m)
+                    if (m0 + m < MTN) mma_tf32(sml[m0 + m], a[m].hi, b.lo);
+            }
         }
     }
 #pragma unroll
-    for (int i = 0; i < NQ; ++i) {
-        const int p = 8 * n0 + 64 * i + 2 * t;
-        if (p >= P) continue;
-        float2 dr = {0.f, 0.f};
-        if (q.wa != nullptr) dr = *reinterpret_cast<const float2*>(q.draw + p);
+    for (int m = 0; m < MTN; ++m)
 #pragma unroll
-        for (int m = 0; m < MTN; ++m)
+        for (int r = 0; r < 4; ++r) acc[m][r] += sml[m][r];
+    const int p = 8 * n0 + 2 * t;
+    if (p >= P) return;
+    float2 dr = {0.f, 0.f};
+    if (q.wa != nullptr) dr = *reinterpret_cast<const float2*>(q.draw + p);
 #pragma unroll
-            for (int h = 0; h < 2; ++h) {
-                const int k = 16 * (mb + m) + g + 8 * h;
-                if (k < K) {
-                    float2 o = {acc[m][i][2 * h], acc[m][i][2 * h + 1]};
-                    if (q.wa != nullptr && k < H) {
-                        o.x += q.wa[k] * dr.x; o.y += q.wa[k] * dr.y;
-                    }
-                    float2* xp = reinterpret_cast<float2*>(q.X + k * PS + p);
-                    if (k < q.relu_rows) {
-                        const float2 hv = *xp;
-                        o.x = hv.x > 0.f ? o.x : 0.f; o.y = hv.y > 0.f ? o.y : 0.f;
-                    }
-                    *xp = o;
+    for (int m = 0; m < MTN; ++m)
+#pragma unroll
+        for (int h = 0; h < 2; ++h) {
+            const int k = 16 * (mb + m) + g + 8 * h;
+            if (k < K) {
+                float2 o = {acc[m][2 * h], acc[m][2 * h + 1]};
+                if (q.wa != nullptr && k < H) {
+                    o.x += q.wa[k] * dr.x; o.y += q.wa[k] * dr.y;
                 }
+                float2* xp = reinterpret_cast<float2*>(q.X + k * PS + p);
+                if (k < q.relu_rows) {
+                    const float2 hv = *xp;
+                    o.x = hv.x > 0.f ? o.x : 0.f; o.y = hv.y > 0.f ? o.y : 0.f;
+                }
+                *xp = o;
             }
-    }
+        }
 }
 #endif
 
@@ -304,19 +312,16 @@ OO_DEV void gemm_bwd_data(int tid, const float* __restrict__ W0, const float* __
                           const float* __restrict__ W1, const float* __restrict__ DY1,
                           float* X, int relu_rows, const float* wa, const float* draw) {
 #ifdef __CUDACC__
-    static_assert(J0 % 8 == 0 && J1 % 8 == 0, "gemm_bwd_data tiling");
-    constexpr int MT = (K + 15) / 16, MSPLIT = (MT + 2) / 3;
+    static_assert(J0 % 8 == 0 && J1 % 8 == 0 && NWARPS == 16 && NT_P == 13, "gemm_bwd_data tiling");
+    constexpr int MT = (K + 15) / 16, MSPLIT = (MT + 3) / 4, MREM = MT % MSPLIT ? MT % MSPLIT : MSPLIT;
     const int warp = tid >> 5, lane = tid & 31;
     const BwdDataArgs q = {W0, DY0, W1, DY1, X, relu_rows, wa, draw};
-    if (warp < 4) {
-        gemm_bwd_data_body<K, WS0, J0, WS1, J1, MT, 2>(lane, 0, warp, q);
-    } else {
-        gemm_bwd_data_body<K, WS0, J0, WS1, J1, MT, 1>(lane, 0, warp, q);
-        if (warp >= 5) {                       // a third of the row tiles of the last point tile
-            const int mb = (warp - 5) * MSPLIT;
-            if (mb + MSPLIT <= MT) gemm_bwd_data_body<K, WS0, J0, WS1, J1, MSPLIT, 1>(lane, mb, NT_P - 1, q);
-            else if (mb < MT) gemm_bwd_data_body<K, WS0, J0, WS1, J1, (MT % MSPLIT ? MT % MSPLIT : 1), 1>(lane, mb, NT_P - 1, q);
-        }
+    if (warp < NT_P - 1) {
+        gemm_bwd_data_body<K, WS0, J0, WS1, J1, MT>(lane, 0, warp, q);
+    } else {                                   // a quarter of the row tiles of the last point tile
+        const int mb = (warp - (NT_P - 1)) * MSPLIT;
+        if (mb + MSPLIT <= MT) gemm_bwd_data_body<K, WS0, J0, WS1, J1, MSPLIT>(lane, mb, NT_P - 1, q);
+        else if (mb < MT) gemm_bwd_data_body<K, WS0, J0, WS1, J1, MREM>(lane, mb, NT_P - 1, q);
     }
 #else
     if (tid != 0) return;
@@ -333,20 +338,20 @@ OO_DEV void gemm_bwd_data(int tid, const float* __restrict__ W0, const float* __
 }
 
 // acc fragment i (+)= sum_p DY[j][p] X[k][p] over the tile's points, for this thread's elements of output tiles
-// u = warp + 8 i of the [16 MT] x [8 NT] weight gradient.  M = j, N = k, contraction over points (the four points
-// of the last k-step that lie beyond P contribute zero).  Even and odd k-steps accumulate into separate fragments
-// (twice the independent chains for the scheduler), folded into the persistent accumulators at the end.
+// u = warp + NWARPS i of the [16 MT] x [8 NT] weight gradient.  M = j, N = k, contraction over points (the four points
+// of the last k-step that lie beyond P contribute zero).
 #ifdef __CUDACC__
 template <int MT, int NT, int NU>
 OO_DEV void gemm_bwd_w_body(float* acc, int warp, int lane, const float* __restrict__ DY, const float* __restrict__ X) {
-    constexpr int NSTEP = 8 / MT;
+    constexpr int NSTEP = NWARPS / MT;
     const int g = lane >> 2, t = lane & 3;
     const int m = warp % MT, n0 = warp / MT;
-    float c[2][NU][4];
+    // three accumulator chains per output tile (lo*hi, hi*lo, hi*hi): the MMAs of one k-step are independent
+    float c[3][NU][4];
 #pragma unroll
     for (int i = 0; i < NU; ++i)
 #pragma unroll
-        for (int r = 0; r < 4; ++r) { c[0][i][r] = acc[4 * i + r]; c[1][i][r] = 0.f; }
+        for (int r = 0; r < 4; ++r) { c[0][i][r] = acc[4 * i + r]; c[1][i][r] = 0.f; c[2][i][r] = 0.f; }
     const float* dp = DY + (16 * m + g) * PS + t;
     const float* xp = X + (8 * n0 + g) * PS + t;
 #pragma unroll 2
@@ -359,27 +364,27 @@ OO_DEV void gemm_bwd_w_body(float* acc, int warp, int lane, const float* __restr
 #pragma unroll
         for (int i = 0; i < NU; ++i) frag_b(b[i], xp[8 * NSTEP * i * PS + p0], tail ? 0.f : xp[8 * NSTEP * i * PS + p0 + 4]);
 #pragma unroll
-        for (int i = 0; i < NU; ++i) mma_tf32(c[ks & 1][i], a.lo, b[i].hi);
-#pragma unroll
-        for (int i = 0; i < NU; ++i) mma_tf32(c[ks & 1][i], a.hi, b[i].lo);
-#pragma unroll
-        for (int i = 0; i < NU; ++i) mma_tf32(c[ks & 1][i], a.hi, b[i].hi);
+        for (int i = 0; i < NU; ++i) {
+            mma_tf32(c[1][i], a.lo, b[i].hi);
+            mma_tf32(c[2][i], a.hi, b[i].lo);
+            mma_tf32(c[0][i], a.hi, b[i].hi);
+        }
     }
 #pragma unroll
     for (int i = 0; i < NU; ++i)
 #pragma unroll
-        for (int r = 0; r < 4; ++r) acc[4 * i + r] = c[0][i][r] + c[1][i][r];
+        for (int r = 0; r < 4; ++r) acc[4 * i + r] = c[0][i][r] + (c[1][i][r] + c[2][i][r]);
 }
 #endif
 
 template <int MT, int NT>
 OO_DEV void gemm_bwd_w(float* acc, int tid, const float* __restrict__ DY, const float* __restrict__ X) {
 #ifdef __CUDACC__
-    static_assert(8 % MT == 0, "gemm_bwd_w tiling");
-    constexpr int NU = wfrag_units(MT, NT), NSTEP = 8 / MT;
+    static_assert(NWARPS % MT == 0, "gemm_bwd_w tiling");
+    constexpr int NU = wfrag_units(MT, NT), NSTEP = NWARPS / MT;
     const int warp = tid >> 5, lane = tid & 31;
     if (warp / MT + NSTEP * (NU - 1) < NT) gemm_bwd_w_body<MT, NT, NU>(acc, warp, lane, DY, X);
-    else if (NU > 1) gemm_bwd_w_body<MT, NT, (NU > 1 ? NU - 1 : 1)>(acc, warp, lane, DY, X);
+    else if (NU > 1 && warp / MT < NT) gemm_bwd_w_body<MT, NT, (NU > 1 ? NU - 1 : 1)>(acc, warp, lane, DY, X);
 #else
     for (int i = 0; i < wfrag_units(MT, NT); ++i)
         for (int r = 0; r < 4; ++r) {
@@ -430,10 +435,11 @@ OO_DEV void stage_weights(int tid, float* sm, const float* __restrict__ th) {
 // Per-object constants of the out_clip layer, computed by the CTA when it starts an object (no tile is in flight, so the
 // activation area is free): [W | b] (512 x 33, rows padded to 36 floats) is staged there with 16-byte async copies, then
 // G' = [W | b]^T [W | b] (33 x 33; G = W^T W, wb = W^T b, bb = b.b) is formed with 4x4 register tiles, the 512 rows split
-// over four thread groups whose partials are summed through shared memory.  Result -> this CTA's scratch `der` (global).
+// over NGG thread groups whose partials are summed through shared memory.  Result -> this CTA's scratch `der` (global).
 constexpr int GS = 36;                       // row stride of the staged [W | b]
-constexpr int SM_GPART = 512 * GS;           // [4 groups][36 x 36] partial products (floats, inside the activation area)
-static_assert(SM_GPART + 4 * 36 * 36 <= SM_W, "gram staging must fit in the activation area");
+constexpr int SM_GPART = 512 * GS;           // [NGG groups][36 x 36] partial products (floats, inside the activation area)
+constexpr int NGG = NTHREADS / 64;           // thread groups of 64, each reduces C / NGG rows of [W | b]
+static_assert(SM_GPART + NGG * 36 * 36 <= SM_W, "gram staging must fit in the activation area");
 
 template <int STEP>
 OO_DEV void gram_stage(int tid, float* __restrict__ sm, const float* __restrict__ th, float* __restrict__ der) {
@@ -460,9 +466,9 @@ OO_DEV void gram_stage(int tid, float* __restrict__ sm, const float* __restrict_
             float acc[4][4];
 #pragma unroll
             for (int x = 0; x < 4; ++x) acc[x][0] = acc[x][1] = acc[x][2] = acc[x][3] = 0.f;
-            const float* base = wst + (size_t)(128 * g) * GS;
+            const float* base = wst + (size_t)((C / NGG) * g) * GS;
 #pragma unroll 4
-            for (int cc = 0; cc < 128; ++cc) {
+            for (int cc = 0; cc < C / NGG; ++cc) {
                 const float4 a4 = ld4(base + cc * GS + k4), b4 = ld4(base + cc * GS + j4);
                 acc[0][0] += a4.x * b4.x; acc[0][1] += a4.x * b4.y; acc[0][2] += a4.x * b4.z; acc[0][3] += a4.x * b4.w;
                 acc[1][0] += a4.y * b4.x; acc[1][1] += a4.y * b4.y; acc[1][2] += a4.y * b4.z; acc[1][3] += a4.y * b4.w;
@@ -476,10 +482,12 @@ OO_DEV void gram_stage(int tid, float* __restrict__ sm, const float* __restrict_
     } else {
         for (int q = tid; q < 33 * 33; q += NTHREADS) {
             const int k = q / 33, j = q - 33 * k;
-            const float v = (part[k * 36 + j] + part[1296 + k * 36 + j]) + (part[2592 + k * 36 + j] + part[3888 + k * 36 + j]);
+            float v = 0.f;
+#pragma unroll
+            for (int gg = 0; gg < NGG; gg += 2) v += part[gg * 1296 + k * 36 + j] + part[(gg + 1) * 1296 + k * 36 + j];
             if (k < H && j < H) der[DER_G + k * H + j] = v;
-            else if (k < H) der[DER_WB + k] = v;            // column 32: W^T b
-            else if (j == H) der[DER_BB] = v;               // b . b
+            else if (k < H) { der[DER_WB + k] = v; sm[SM_RV + V_WB * RP + k] = v; }            // column 32: W^T b
+            else if (j == H) { der[DER_BB] = v; sm[SM_RV + V_WB * RP + H] = v; }               // b . b
         }
     }
 }
@@ -494,16 +502,16 @@ OO_DEV void zero_pad_rows(int tid, float* sm) {
         sm[(R_MISC + M_HU) * PS + i] = 0.f;
         sm[(R_MISC + M_HU + 1) * PS + i] = 0.f;
     }
-    for (int i = tid; i < 2 * H * RP + NRV * RP; i += NTHREADS) sm[SM_ST + i] = 0.f;
+    for (int i = tid; i < 2 * H * RP + NRV_TILE * RP; i += NTHREADS) sm[SM_ST + i] = 0.f;
 }
 
 // ------------------------------------------------------------------------------------------------
 // phases
 // ------------------------------------------------------------------------------------------------
-constexpr int N_TRAIN_PHASES = 32;
+constexpr int N_TRAIN_PHASES = 30;
 constexpr int N_FWD_PHASES = 8;    // phases 0..7 are shared with the standalone forward kernel
 // execution order of the training tile (phases 32..35 were split out of their neighbours later)
-constexpr int kTrainOrder[N_TRAIN_PHASES] = {0, 1, 2, 3, 4, 5, 6, 7, 33, 8, 9, 10, 11, 12, 32, 13, 16, 17, 18, 19,
+constexpr int kTrainOrder[N_TRAIN_PHASES] = {0, 1, 2, 3, 4, 5, 6, 7, 33, 8, 10, 11, 32, 13, 16, 17, 18, 19,
                                              20, 21, 22, 23, 24, 25, 26, 27, 28, 29, 30, 31};
 
 template <int PH, bool PART>
@@ -523,11 +531,21 @@ OO_DEV void tile_phase(int tid, float* __restrict__ sm, const TileCtx& c, TileAc
             act[(R_T + ch) * PS + p] = t;
             act[(R_E1 + ch) * PS + p] = t;
         }
+        if (c.nrays > 0) {
+            // training tile: z of the points and the gt values of the rays, so that no later phase waits on HBM
+            for (int p = tid; p < P; p += NTHREADS) misc[M_Z * PS + p] = p < c.npts ? OO_LDG(c.z + p) : 0.f;
+            if (tid >= 128 && tid < 128 + 5 * RT) {
+                const int q = (tid - 128) / RT, r = (tid - 128) - q * RT;
+                float v = 0.f;
+                if (r < c.nrays) v = q == 0 ? OO_LDG(c.gt_depth + r) : q == 1 ? (float)c.labels[r] : (float)c.gt_rgb[3 * r + q - 2];
+                rv[(V_GTD + q) * RP + r] = v;
+            }
+        }
         if (PART) {
             // gt part features of the tile's rays -> Y [10][512]; asynchronous, awaited at the end of phase 8
             for (int i = tid; i < RT * (C / 4); i += NTHREADS) {
                 const int r = i / (C / 4), q = i - r * (C / 4);
-                float* dst = sm + SM_FEAT + r * C + 4 * q;
+                float* dst = sm + SM_FEAT + r * YSTR + 4 * q;
                 if (r < c.nrays) {
                     OO_CP_ASYNC16(dst, c.feat_table + (size_t)OO_LDG(c.feat_row + r) * C + 4 * q);
                 } else {
@@ -609,7 +627,7 @@ OO_DEV void tile_phase(int tid, float* __restrict__ sm, const TileCtx& c, TileAc
                 for (int i = 0; i < S; ++i) {
                     const int p = r * S + i;
                     const float t = misc[M_TERM * PS + p];
-                    zv[i] = OO_LDG(c.z + p);
+                    zv[i] = misc[M_Z * PS + p];
                     tv[i] = t;
                     depth += t * zv[i];
                     opac += t;
@@ -623,17 +641,17 @@ OO_DEV void tile_phase(int tid, float* __restrict__ sm, const TileCtx& c, TileAc
                     const float dz = zv[i] - depth;
                     var += tv[i] * (dz * dz);
                 }
-                const int lab = c.labels[r];
+                const int lab = (int)rv[V_LAB * RP + r];
                 const bool is1 = lab == 1, sem = lab != 2;
                 const float tgt = lab != 0 ? 1.f : 0.f;
                 if (is1 && !(c.flags & 2)) {
                     const float wgt = 1.f / (sqrtf(var) + 1e-4f);           // render_rays.py:95-100, var detached
-                    const float dd = depth - OO_LDG(c.gt_depth + r);
+                    const float dd = depth - rv[V_GTD * RP + r];
                     a.loss[0] += fabsf(dd) * wgt;
                     gd = sgnf_(dd) * wgt * c.inv1;
-                    const float e0 = c0 - (float)c.gt_rgb[3 * r + 0] / 255.f;   // train.py:373 `/ 255.`
-                    const float e1 = c1 - (float)c.gt_rgb[3 * r + 1] / 255.f;
-                    const float e2 = c2 - (float)c.gt_rgb[3 * r + 2] / 255.f;
+                    const float e0 = c0 - rv[(V_RGB + 0) * RP + r] / 255.f;   // train.py:373 `/ 255.`
+                    const float e1 = c1 - rv[(V_RGB + 1) * RP + r] / 255.f;
+                    const float e2 = c2 - rv[(V_RGB + 2) * RP + r] / 255.f;
                     a.loss[1] += fabsf(e0) + fabsf(e1) + fabsf(e2);              // loss.py:61 sum over channels
                     gc0 = sgnf_(e0) * c.cs * c.inv1;
                     gc1 = sgnf_(e1) * c.cs * c.inv1;
@@ -655,9 +673,13 @@ OO_DEV void tile_phase(int tid, float* __restrict__ sm, const TileCtx& c, TileAc
             rv[V_BG * RP + r] = 0.f;
         }
         if (PART) OO_CP_ASYNC_WAIT();      // Y rows issued in phase 0 are complete for this thread; the barrier publishes them
-    } else if constexpr (PH == 9) {
-        // S[j][r] = sum_i T_i hp_i[j]   (render of the clip-head hidden activations)
+    } else if constexpr (PH == 10) {
+        // The rendered feature x_r = W S_r + b opac_r is never formed.  With per-object constants G = W^T W,
+        // wb = W^T b, bb = b.b (k_gram) the cosine loss and its gradient need only
+        //     v_r = W^T y_r,  yb_r = b.y_r,  yy_r = y_r.y_r        (y_r = gt feature row, staged in Y)
+        //   x.y = S.v + opac yb ;  x.x = S.(G S + opac wb) + opac (S.wb + opac bb) ;  dL/dS = A v + B (G S + opac wb).
         if (PART) {
+            // S[j][r] = sum_i T_i hp_i[j]   (render of the clip-head hidden activations); independent of the rest of the phase
             for (int i = tid; i < H * RT; i += NTHREADS) {
                 const int j = i / RT, r = i - j * RT;
                 float s = 0.f;
@@ -665,48 +687,91 @@ OO_DEV void tile_phase(int tid, float* __restrict__ sm, const TileCtx& c, TileAc
                 for (int q = 0; q < S; ++q) s += misc[M_TERM * PS + r * S + q] * act[(R_HP + j) * PS + r * S + q];
                 sm[SM_ST + j * RP + r] = s;
             }
-        }
-    } else if constexpr (PH == 10) {
-        // The rendered feature x_r = W S_r + b opac_r is never formed.  With per-object constants G = W^T W,
-        // wb = W^T b, bb = b.b (k_gram) the cosine loss and its gradient need only
-        //     v_r = W^T y_r,  yb_r = b.y_r,  yy_r = y_r.y_r        (y_r = gt feature row, staged in Y)
-        //   x.y = S.v + opac yb ;  x.x = S.(G S + opac wb) + opac (S.wb + opac bb) ;  dL/dS = A v + B (G S + opac wb).
-        if (PART) {
-            {   // (a) v partials: warp wv owns features [64 wv, 64 wv + 64); lane = hidden unit j
-                const int wv = tid >> 5, j = tid & 31;
-                float v[RT];
+            // warp wv owns gt-feature columns [32 wv, 32 wv + 32): partial v_r[j] = sum_c y_r[c] W[c][j] as a 16 x 32 x 32
+            // tensor-core product (M = ray, N = hidden unit, K = column; W fragments straight from L2), y.b as a fifth
+            // column tile whose column 0 is b, y.y on the side.  The partial v replaces the warp's own columns of Y
+            // (nobody else reads them); phase 11 sums the 16 partials.
+            constexpr int CW = C / NWARPS;
+            static_assert(CW == 32, "phase 10 gives each warp four 8-wide k-steps of gt-feature columns");
+#ifdef __CUDACC__
+            const int wv = tid >> 5, lane = tid & 31, g = lane >> 2, t = lane & 3;
+            const float* wg = c.theta + OFF_OCL_W + (size_t)(wv * CW) * H;
+            const float* bg = c.theta + OFF_OCL_B + wv * CW;
+            float bw[4][4][2], bq[4][2];            // global loads in flight before the first use
 #pragma unroll
-                for (int r = 0; r < RT; ++r) v[r] = 0.f;
-                const float* wocl = c.theta + OFF_OCL_W + (size_t)(wv * 64) * H + j;
-                float wq[64];            // 64 coalesced global loads in flight before the first use
+            for (int ks = 0; ks < 4; ++ks) {
 #pragma unroll
-                for (int q = 0; q < 64; ++q) wq[q] = OO_LDG(wocl + q * H);
+                for (int nt = 0; nt < 4; ++nt) {
+                    bw[ks][nt][0] = OO_LDG(wg + (8 * ks + t) * H + 8 * nt + g);
+                    bw[ks][nt][1] = OO_LDG(wg + (8 * ks + t + 4) * H + 8 * nt + g);
+                }
+                bq[ks][0] = g == 0 ? OO_LDG(bg + 8 * ks + t) : 0.f;
+                bq[ks][1] = g == 0 ? OO_LDG(bg + 8 * ks + t + 4) : 0.f;
+            }
+            float* y = sm + SM_FEAT + wv * CW;
+            const bool hi_row = g + 8 < RT;
+            float vacc[5][4];
 #pragma unroll
-                for (int q = 0; q < 64; q += 4) {
+            for (int nt = 0; nt < 5; ++nt) vacc[nt][0] = vacc[nt][1] = vacc[nt][2] = vacc[nt][3] = 0.f;
+            float yy0 = 0.f, yy1 = 0.f;
 #pragma unroll
+            for (int ks = 0; ks < 4; ++ks) {
+                const float a0 = y[g * YSTR + 8 * ks + t], a2 = y[g * YSTR + 8 * ks + t + 4];
+                const float a1 = hi_row ? y[(g + 8) * YSTR + 8 * ks + t] : 0.f, a3 = hi_row ? y[(g + 8) * YSTR + 8 * ks + t + 4] : 0.f;
+                yy0 += a0 * a0 + a2 * a2;
+                yy1 += a1 * a1 + a3 * a3;
+                FragA fa;
+                frag_a(fa, a0, a1, a2, a3);
+#pragma unroll
+                for (int nt = 0; nt < 4; ++nt) {
+                    FragB fb;
+                    frag_b(fb, bw[ks][nt][0], bw[ks][nt][1]);
+                    mma3(vacc[nt], fa, fb);
+                }
+                FragB fq;
+                frag_b(fq, bq[ks][0], bq[ks][1]);
+                mma3(vacc[4], fa, fq);
+            }
+            yy0 += __shfl_xor_sync(0xffffffffu, yy0, 1); yy0 += __shfl_xor_sync(0xffffffffu, yy0, 2);
+            yy1 += __shfl_xor_sync(0xffffffffu, yy1, 1); yy1 += __shfl_xor_sync(0xffffffffu, yy1, 2);
+            if (t == 0) {
+                sm[SM_YS + (g * 16 + wv) * 2] = vacc[4][0];
+                sm[SM_YS + (g * 16 + wv) * 2 + 1] = yy0;
+                if (hi_row) {
+                    sm[SM_YS + ((g + 8) * 16 + wv) * 2] = vacc[4][2];
+                    sm[SM_YS + ((g + 8) * 16 + wv) * 2 + 1] = yy1;
+                }
+            }
+            __syncwarp();
+#pragma unroll
+            for (int nt = 0; nt < 4; ++nt) {
+                *reinterpret_cast<float2*>(y + g * YSTR + 8 * nt + 2 * t) = float2{vacc[nt][0], vacc[nt][1]};
+                if (hi_row) *reinterpret_cast<float2*>(y + (g + 8) * YSTR + 8 * nt + 2 * t) = float2{vacc[nt][2], vacc[nt][3]};
+            }
+#else
+            if (tid == 0) {      // host emulation: same partial sums, sequential order inside a warp's column block
+                for (int wv = 0; wv < NWARPS; ++wv) {
+                    float* y = sm + SM_FEAT + wv * CW;
+                    float vv[RT][CW];
                     for (int r = 0; r < RT; ++r) {
-                        const float4 y = ld4(sm + SM_FEAT + r * C + wv * 64 + q);
-                        v[r] += y.x * wq[q] + y.y * wq[q + 1] + y.z * wq[q + 2] + y.w * wq[q + 3];
+                        float yb = 0.f, yy = 0.f;
+                        for (int q = 0; q < CW; ++q) {
+                            yb += y[r * YSTR + q] * c.theta[OFF_OCL_B + wv * CW + q];
+                            yy += y[r * YSTR + q] * y[r * YSTR + q];
+                        }
+                        sm[SM_YS + (r * 16 + wv) * 2] = yb;
+                        sm[SM_YS + (r * 16 + wv) * 2 + 1] = yy;
+                        for (int j = 0; j < H; ++j) {
+                            float v = 0.f;
+                            for (int q = 0; q < CW; ++q) v += y[r * YSTR + q] * c.theta[OFF_OCL_W + (size_t)(wv * CW + q) * H + j];
+                            vv[r][j] = v;
+                        }
                     }
+                    for (int r = 0; r < RT; ++r)
+                        for (int j = 0; j < H; ++j) y[r * YSTR + j] = vv[r][j];
                 }
-#pragma unroll
-                for (int r = 0; r < RT; ++r) sm[SM_UPART + (wv * RT + r) * H + j] = v[r];
             }
-            if (tid < RT * 16) {   // (b) partial y.b and y.y
-                const int r = tid >> 4, ch = tid & 15;
-                float bq[C / 16];
-#pragma unroll
-                for (int i = 0; i < C / 16; ++i) bq[i] = OO_LDG(c.theta + OFF_OCL_B + i * 16 + ch);
-                float yb = 0.f, yy = 0.f;
-#pragma unroll
-                for (int i = 0; i < C / 16; ++i) {
-                    const float yv = sm[SM_FEAT + r * C + i * 16 + ch];
-                    yb += yv * bq[i];
-                    yy += yv * yv;
-                }
-                sm[SM_YS + (r * 16 + ch) * 2] = yb;
-                sm[SM_YS + (r * 16 + ch) * 2 + 1] = yy;
-            }
+#endif
         }
     } else if constexpr (PH == 11) {
         if (PART) {
@@ -714,7 +779,7 @@ OO_DEV void tile_phase(int tid, float* __restrict__ sm, const TileCtx& c, TileAc
                 const int r = i / H, j = i - r * H;
                 float v = 0.f;
 #pragma unroll
-                for (int wv = 0; wv < 8; ++wv) v += sm[SM_UPART + (wv * RT + r) * H + j];
+                for (int wv = 0; wv < NWARPS; ++wv) v += sm[SM_FEAT + r * YSTR + wv * (C / NWARPS) + j];
                 sm[SM_UT + j * RP + r] = v;
             }
             if (tid >= 128 && tid < 128 + 2 * RT) {             // totals of y.b and y.y
@@ -727,16 +792,13 @@ OO_DEV void tile_phase(int tid, float* __restrict__ sm, const TileCtx& c, TileAc
                 }
                 sm[SM_YS + 320 + q * RP + r] = s0 + s1;
             }
-        }
-    } else if constexpr (PH == 12) {
-        // gs[j][r] = sum_k G[j][k] S[k][r] + opac_r wb[j]   (stored in the now free UPART area)
-        if (PART) {
+            // gs[j][r] = sum_k G[j][k] S[k][r] + opac_r wb[j]   (S from phase 10)
             for (int i = tid; i < H * RT; i += NTHREADS) {
                 const int r = i / H, j = i - r * H;
                 float g[H];
 #pragma unroll
                 for (int k = 0; k < H; ++k) g[k] = c.derived[DER_G + k * H + j];      // G is symmetric: coalesced over j
-                float acc = rv[V_OPAC * RP + r] * c.derived[DER_WB + j];
+                float acc = rv[V_OPAC * RP + r] * rv[V_WB * RP + j];
 #pragma unroll
                 for (int k = 0; k < H; ++k) acc += g[k] * sm[SM_ST + k * RP + r];
                 sm[SM_UPART + j * RP + r] = acc;
@@ -749,14 +811,14 @@ OO_DEV void tile_phase(int tid, float* __restrict__ sm, const TileCtx& c, TileAc
                 const int r = tid;
                 const float opac = rv[V_OPAC * RP + r];
                 float sv = 0.f, swb = 0.f, sgs = 0.f;
-#pragma unroll 8
+#pragma unroll
                 for (int j = 0; j < H; ++j) {
                     const float sj = sm[SM_ST + j * RP + r];
                     sv += sj * sm[SM_UT + j * RP + r];
-                    swb += sj * c.derived[DER_WB + j];
+                    swb += sj * rv[V_WB * RP + j];
                     sgs += sj * sm[SM_UPART + j * RP + r];
                 }
-                const float bb = c.derived[DER_BB];
+                const float bb = rv[V_WB * RP + H];
                 const float yb = sm[SM_YS + 320 + r], yy = sm[SM_YS + 320 + RP + r];
                 const float xb = swb + opac * bb;                     // b . x
                 const float xy = sv + opac * yb, xx = sgs + opac * xb;
@@ -789,7 +851,7 @@ OO_DEV void tile_phase(int tid, float* __restrict__ sm, const TileCtx& c, TileAc
                 if (q < 2) c.rayrec[r * RAYREC + q] = q == REC_A ? rv[V_A * RP + r] : rv[V_OPAC * RP + r];
                 else c.rayrec[r * RAYREC + REC_S + q - 2] = sm[SM_ST + (q - 2) * RP + r];
             }
-            {
+            if (tid < 8 * H) {
                 const int k = tid >> 3, j4 = 4 * (tid & 7);
 #pragma unroll
                 for (int r = 0; r < RT; ++r) {
@@ -815,7 +877,7 @@ OO_DEV void tile_phase(int tid, float* __restrict__ sm, const TileCtx& c, TileAc
             const int r = p / S;
             float g = 0.f;
             if (r < c.nrays) {
-                g = OO_LDG(c.z + p) * rv[V_GD * RP + r] + rv[V_GO * RP + r] +
+                g = misc[M_Z * PS + p] * rv[V_GD * RP + r] + rv[V_GO * RP + r] +
                     misc[(M_COL + 0) * PS + p] * rv[(V_GC + 0) * RP + r] + misc[(M_COL + 1) * PS + p] * rv[(V_GC + 1) * RP + r] +
                     misc[(M_COL + 2) * PS + p] * rv[(V_GC + 2) * RP + r];
                 if (PART) {
@@ -1027,7 +1089,7 @@ OO_DEV void tile_flush(int tid, float* __restrict__ sm, float* __restrict__ slab
         }
         if (tid < NDIR * 3) slab[OFF_PE_B + tid] = a.s2;
         if (PART) {
-            st4(slab + SLAB_M + 4 * tid, float4{a.gm[0], a.gm[1], a.gm[2], a.gm[3]});
+            if (tid < 8 * H) st4(slab + SLAB_M + 4 * tid, float4{a.gm[0], a.gm[1], a.gm[2], a.gm[3]});
             if (tid <= H) slab[SLAB_MV + tid] = a.s3;     // m[0..31], beta at SLAB_MV + 32 == SLAB_BETA
         }
         if (tid < RT) {
