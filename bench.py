@@ -207,7 +207,9 @@ def run_ours(args):
             if host:
                 _ = lt[it - 1].sum().item()        # D2H read of the step result inside the timed region
             f += 1
-            launches["n"] += 2 * it + 2 + 8         # K1+K4 per step, label counts + adam schedule, sampler + 7 tape fills
+            # per step: k_gram + k_train + k_clipgrad + k_adamw (part features on), else k_train + k_adamw;
+            # per frame: label counts + adam schedule, append, sampler
+            launches["n"] += (4 if args.part else 2) * it + 2 + 2
 
     # ---- device-resident pass: `value`
     run_frames(frames_w, warmup, host=False)

@@ -101,7 +101,7 @@ typedef struct oo_batch {
 typedef struct oo_train_ws {   /* caller-allocated scratch; sizes from oo_train_ws_sizes() */
     float* slab;               /* [n_slots][OO_PSTRIDE] per-(CTA,object) gradient partials */
     float* slot_loss;          /* [n_slots][4] */
-    float* derived;            /* [n_cta][OO_DERIVED_FLOATS] per-CTA scratch: out_clip constants (W^T W, W^T b, b.b) of the object a CTA works on */
+    float* derived;            /* [n_obj][OO_DERIVED_FLOATS] out_clip constants (W^T W, W^T b, b.b) of every object, refreshed by every step */
     float* clip_grad;          /* [n_obj][512*32 + 512] out_clip.weight / .bias gradient assembled by K4a for K4b */
     float* rayrec;             /* [n_obj][rays_per_step][OO_RAYREC_FLOATS] per-ray records K1 leaves for K4 (out_clip gradient) */
     int*   sched;              /* device copy of the static schedule */

@@ -46,6 +46,13 @@ OO_DEV float4 ld4(const float* p) { return *reinterpret_cast<const float4*>(p); 
 OO_DEV void st4(float* p, const float4& v) { *reinterpret_cast<float4*>(p) = v; }
 OO_DEV float sigmoidf_(float x) { return 1.0f / (1.0f + expf(-x)); }
 OO_DEV float sgnf_(float x) { return x > 0.f ? 1.f : (x < 0.f ? -1.f : 0.f); }
+#ifdef __CUDACC__
+OO_DEV float warp_sum(float v) {
+#pragma unroll
+    for (int o = 16; o > 0; o >>= 1) v += __shfl_xor_sync(0xffffffffu, v, o);
+    return v;
+}
+#endif
 
 // register-resident weight-gradient accumulators of one thread (live across all tiles of an object).  The five weight
 // matrices are accumulated as m16n8k8 C fragments: output tile u = warp + NWARPS i of a GEMM with MT row tiles (16 output
@@ -54,7 +61,7 @@ OO_DEV float sgnf_(float x) { return x > 0.f ? 1.f : (x < 0.f ? -1.f : 0.f); }
 struct TileAcc {
     float in[8];     // in_layer   : 2 x 11 tiles -> 2 fragments
     float cat[8];    // cat_layer  : 2 x 15 tiles -> 2 fragments
-    float m1[4];     // mid1       : 2 x 4 tiles  -> 1 fragment (warps 0..7)
+    float m1[4];     // mid1       : 2 x 4 tiles, two warps per tile (k-split, see gemm_bwd_w32)
     float m2[4];     // mid2
     float hd[12];    // [color_linear ; clip_linear] : 4 x 10 tiles -> 3 fragments (part features off: 2 x 10 -> 2)
     float s0;        // out_color.weight (tid<96), out_alpha.weight (96<=tid<128)
@@ -62,7 +69,7 @@ struct TileAcc {
     float s2;        // B_layer.weight (tid<63)
     float gm[4];     // M = sum_r B_r S_r S_r^T, row tid/8, cols 4(tid%8)..+3   (out_clip gradient, see phase 13)
     float s3;        // m = sum_r B_r opac_r S_r (tid<32), beta = sum_r B_r opac_r^2 (tid 32)
-    float loss[4];   // per-ray loss partials (tid<10): depth, colour, opacity, feature
+    float loss[4];   // per-ray loss partials (thread 32 r, r < 10): depth, colour, opacity, feature
 };
 
 OO_DEV void acc_zero(TileAcc& a) {
@@ -342,7 +349,8 @@ OO_DEV void gemm_bwd_data(int tid, const float* __restrict__ W0, const float* __
 // of the last k-step that lie beyond P contribute zero).
 #ifdef __CUDACC__
 template <int MT, int NT, int NU>
-OO_DEV void gemm_bwd_w_body(float* acc, int warp, int lane, const float* __restrict__ DY, const float* __restrict__ X) {
+OO_DEV void gemm_bwd_w_body(float* acc, int warp, int lane, const float* __restrict__ DY, const float* __restrict__ X,
+                            int ks0 = 0, int ks1 = NT_P) {
     constexpr int NSTEP = NWARPS / MT;
     const int g = lane >> 2, t = lane & 3;
     const int m = warp % MT, n0 = warp / MT;
@@ -355,7 +363,7 @@ OO_DEV void gemm_bwd_w_body(float* acc, int warp, int lane, const float* __restr
     const float* dp = DY + (16 * m + g) * PS + t;
     const float* xp = X + (8 * n0 + g) * PS + t;
 #pragma unroll 2
-    for (int ks = 0; ks < NT_P; ++ks) {
+    for (int ks = ks0; ks < ks1; ++ks) {
         const int p0 = 8 * ks;
         const bool tail = p0 + t + 4 >= P;               // only in the last k-step
         FragA a;
@@ -397,6 +405,27 @@ OO_DEV void gemm_bwd_w(float* acc, int tid, const float* __restrict__ DY, const 
 #endif
 }
 
+// The two 32 x 32 weight gradients have only 8 output tiles: two warps share a tile, each contracting over half of the
+// point k-steps (warp w and w + 8 own tile w; the halves are added when the slot is flushed).
+constexpr int KS_SPLIT = 7;            // k-steps [0, 7) and [7, 13)
+OO_HOSTDEV inline int wfrag32_row(int tid, int r) { return 16 * (((tid >> 5) & 7) % 2) + ((tid & 31) >> 2) + 8 * (r >> 1); }
+OO_HOSTDEV inline int wfrag32_col(int tid, int r) { return 8 * (((tid >> 5) & 7) / 2) + 2 * (tid & 3) + (r & 1); }
+
+OO_DEV void gemm_bwd_w32(float* acc, int tid, const float* __restrict__ DY, const float* __restrict__ X) {
+    static_assert(NWARPS == 16 && H == 32, "gemm_bwd_w32 pairs warps w and w + 8");
+    const int half = tid >> 8;
+#ifdef __CUDACC__
+    gemm_bwd_w_body<2, H / 8, 1>(acc, (tid >> 5) & 7, tid & 31, DY, X, half ? KS_SPLIT : 0, half ? NT_P : KS_SPLIT);
+#else
+    for (int r = 0; r < 4; ++r) {
+        const int j = wfrag32_row(tid, r), k = wfrag32_col(tid, r);
+        float s = 0.f;
+        for (int p = half ? 8 * KS_SPLIT : 0; p < (half ? P : 8 * KS_SPLIT); ++p) s += DY[j * PS + p] * X[k * PS + p];
+        acc[r] += s;
+    }
+#endif
+}
+
 // ------------------------------------------------------------------------------------------------
 // staging an object's weights into shared memory (padded rows, zero pad columns)
 // ------------------------------------------------------------------------------------------------
@@ -432,10 +461,10 @@ OO_DEV void stage_weights(int tid, float* sm, const float* __restrict__ th) {
     }
 }
 
-// Per-object constants of the out_clip layer, computed by the CTA when it starts an object (no tile is in flight, so the
-// activation area is free): [W | b] (512 x 33, rows padded to 36 floats) is staged there with 16-byte async copies, then
+// Per-object constants of the out_clip layer, computed once per object and step by k_gram (one CTA per object, before
+// k_train): [W | b] (512 x 33, rows padded to 36 floats) is staged in shared memory with 16-byte async copies, then
 // G' = [W | b]^T [W | b] (33 x 33; G = W^T W, wb = W^T b, bb = b.b) is formed with 4x4 register tiles, the 512 rows split
-// over NGG thread groups whose partials are summed through shared memory.  Result -> this CTA's scratch `der` (global).
+// over NGG thread groups whose partials are summed through shared memory.  Result -> the object's row of `derived` (global).
 constexpr int GS = 36;                       // row stride of the staged [W | b]
 constexpr int SM_GPART = 512 * GS;           // [NGG groups][36 x 36] partial products (floats, inside the activation area)
 constexpr int NGG = NTHREADS / 64;           // thread groups of 64, each reduces C / NGG rows of [W | b]
@@ -486,10 +515,15 @@ OO_DEV void gram_stage(int tid, float* __restrict__ sm, const float* __restrict_
 #pragma unroll
             for (int gg = 0; gg < NGG; gg += 2) v += part[gg * 1296 + k * 36 + j] + part[(gg + 1) * 1296 + k * 36 + j];
             if (k < H && j < H) der[DER_G + k * H + j] = v;
-            else if (k < H) { der[DER_WB + k] = v; sm[SM_RV + V_WB * RP + k] = v; }            // column 32: W^T b
-            else if (j == H) { der[DER_BB] = v; sm[SM_RV + V_WB * RP + H] = v; }               // b . b
+            else if (k < H) der[DER_WB + k] = v;            // column 32: W^T b
+            else if (j == H) der[DER_BB] = v;               // b . b
         }
     }
+}
+
+// W_ocl^T b_ocl and b.b of the object a CTA starts working on: global (k_gram) -> the per-object rows of the ray-value area
+OO_DEV void stage_derived(int tid, float* __restrict__ sm, const float* __restrict__ der) {
+    if (tid <= H) sm[SM_RV + V_WB * RP + tid] = OO_LDG(der + DER_WB + tid);      // DER_BB == DER_WB + H
 }
 
 // zero the pad rows of e1 / e2 and the spare rows once per kernel
@@ -617,60 +651,75 @@ OO_DEV void tile_phase(int tid, float* __restrict__ sm, const TileCtx& c, TileAc
     } else if constexpr (PH == 8) {
         // per ray: rendered depth / variance / colour / opacity, loss terms and their derivatives w.r.t. the rendered
         // quantities (render_rays.py:56-63, loss.py:27-75)
-        if (tid < RT) {
-            const int r = tid;
+        // warp r renders ray r: lanes = samples, sums by shuffle; lane 0 (thread 32 r) owns the ray's loss partials
+        const int r = tid >> 5, li = tid & 31;
+        if (r < RT) {
             float gd = 0.f, go = 0.f, gc0 = 0.f, gc1 = 0.f, gc2 = 0.f, cf = 0.f;
-            float depth = 0.f, opac = 0.f, c0 = 0.f, c1 = 0.f, c2 = 0.f;
-            if (r < c.nrays) {
-                float zv[S], tv[S];
-#pragma unroll
+            float depth = 0.f, opac = 0.f, c0 = 0.f, c1 = 0.f, c2 = 0.f, var = 0.f;
+#ifdef __CUDACC__
+            {
+                const bool live = r < c.nrays && li < S;
+                const int p = r * S + (li < S ? li : 0);
+                const float t = live ? misc[M_TERM * PS + p] : 0.f;
+                const float zv = live ? misc[M_Z * PS + p] : 0.f;
+                depth = warp_sum(t * zv);
+                opac = warp_sum(t);
+                c0 = warp_sum(t * misc[(M_COL + 0) * PS + p]);
+                c1 = warp_sum(t * misc[(M_COL + 1) * PS + p]);
+                c2 = warp_sum(t * misc[(M_COL + 2) * PS + p]);
+                const float dz = zv - depth;
+                var = warp_sum(t * (dz * dz));
+            }
+#else
+            if (li == 0 && r < c.nrays) {
                 for (int i = 0; i < S; ++i) {
                     const int p = r * S + i;
                     const float t = misc[M_TERM * PS + p];
-                    zv[i] = misc[M_Z * PS + p];
-                    tv[i] = t;
-                    depth += t * zv[i];
+                    depth += t * misc[M_Z * PS + p];
                     opac += t;
                     c0 += t * misc[(M_COL + 0) * PS + p];
                     c1 += t * misc[(M_COL + 1) * PS + p];
                     c2 += t * misc[(M_COL + 2) * PS + p];
                 }
-                float var = 0.f;
-#pragma unroll
                 for (int i = 0; i < S; ++i) {
-                    const float dz = zv[i] - depth;
-                    var += tv[i] * (dz * dz);
-                }
-                const int lab = (int)rv[V_LAB * RP + r];
-                const bool is1 = lab == 1, sem = lab != 2;
-                const float tgt = lab != 0 ? 1.f : 0.f;
-                if (is1 && !(c.flags & 2)) {
-                    const float wgt = 1.f / (sqrtf(var) + 1e-4f);           // render_rays.py:95-100, var detached
-                    const float dd = depth - rv[V_GTD * RP + r];
-                    a.loss[0] += fabsf(dd) * wgt;
-                    gd = sgnf_(dd) * wgt * c.inv1;
-                    const float e0 = c0 - rv[(V_RGB + 0) * RP + r] / 255.f;   // train.py:373 `/ 255.`
-                    const float e1 = c1 - rv[(V_RGB + 1) * RP + r] / 255.f;
-                    const float e2 = c2 - rv[(V_RGB + 2) * RP + r] / 255.f;
-                    a.loss[1] += fabsf(e0) + fabsf(e1) + fabsf(e2);              // loss.py:61 sum over channels
-                    gc0 = sgnf_(e0) * c.cs * c.inv1;
-                    gc1 = sgnf_(e1) * c.cs * c.inv1;
-                    gc2 = sgnf_(e2) * c.cs * c.inv1;
-                    cf = PART ? c.fs * c.inv1 : 0.f;
-                }
-                if (sem && !(c.flags & 4)) {
-                    const float eo = opac - tgt;                                 // loss.py:71
-                    a.loss[2] += fabsf(eo);
-                    go = sgnf_(eo) * c.os * c.invs;
+                    const float dz = misc[M_Z * PS + r * S + i] - depth;
+                    var += misc[M_TERM * PS + r * S + i] * (dz * dz);
                 }
             }
-            rv[V_DEPTH * RP + r] = depth;
-            rv[V_OPAC * RP + r] = opac;
-            rv[(V_COL + 0) * RP + r] = c0; rv[(V_COL + 1) * RP + r] = c1; rv[(V_COL + 2) * RP + r] = c2;
-            rv[V_GD * RP + r] = gd; rv[V_GO * RP + r] = go;
-            rv[(V_GC + 0) * RP + r] = gc0; rv[(V_GC + 1) * RP + r] = gc1; rv[(V_GC + 2) * RP + r] = gc2;
-            rv[V_CF * RP + r] = cf;
-            rv[V_BG * RP + r] = 0.f;
+#endif
+            if (li == 0) {
+                if (r < c.nrays) {
+                    const int lab = (int)rv[V_LAB * RP + r];
+                    const bool is1 = lab == 1, sem = lab != 2;
+                    const float tgt = lab != 0 ? 1.f : 0.f;
+                    if (is1 && !(c.flags & 2)) {
+                        const float wgt = 1.f / (sqrtf(var) + 1e-4f);           // render_rays.py:95-100, var detached
+                        const float dd = depth - rv[V_GTD * RP + r];
+                        a.loss[0] += fabsf(dd) * wgt;
+                        gd = sgnf_(dd) * wgt * c.inv1;
+                        const float e0 = c0 - rv[(V_RGB + 0) * RP + r] / 255.f;   // train.py:373 `/ 255.`
+                        const float e1 = c1 - rv[(V_RGB + 1) * RP + r] / 255.f;
+                        const float e2 = c2 - rv[(V_RGB + 2) * RP + r] / 255.f;
+                        a.loss[1] += fabsf(e0) + fabsf(e1) + fabsf(e2);              // loss.py:61 sum over channels
+                        gc0 = sgnf_(e0) * c.cs * c.inv1;
+                        gc1 = sgnf_(e1) * c.cs * c.inv1;
+                        gc2 = sgnf_(e2) * c.cs * c.inv1;
+                        cf = PART ? c.fs * c.inv1 : 0.f;
+                    }
+                    if (sem && !(c.flags & 4)) {
+                        const float eo = opac - tgt;                                 // loss.py:71
+                        a.loss[2] += fabsf(eo);
+                        go = sgnf_(eo) * c.os * c.invs;
+                    }
+                }
+                rv[V_DEPTH * RP + r] = depth;
+                rv[V_OPAC * RP + r] = opac;
+                rv[(V_COL + 0) * RP + r] = c0; rv[(V_COL + 1) * RP + r] = c1; rv[(V_COL + 2) * RP + r] = c2;
+                rv[V_GD * RP + r] = gd; rv[V_GO * RP + r] = go;
+                rv[(V_GC + 0) * RP + r] = gc0; rv[(V_GC + 1) * RP + r] = gc1; rv[(V_GC + 2) * RP + r] = gc2;
+                rv[V_CF * RP + r] = cf;
+                rv[V_BG * RP + r] = 0.f;
+            }
         }
         if (PART) OO_CP_ASYNC_WAIT();      // Y rows issued in phase 0 are complete for this thread; the barrier publishes them
     } else if constexpr (PH == 10) {
@@ -807,17 +856,27 @@ OO_DEV void tile_phase(int tid, float* __restrict__ sm, const TileCtx& c, TileAc
     } else if constexpr (PH == 32) {
         // per ray: cosine, loss partial, and the two coefficients of dL/dx = A y + B x
         if (PART) {
-            if (tid < RT) {
-                const int r = tid;
-                const float opac = rv[V_OPAC * RP + r];
-                float sv = 0.f, swb = 0.f, sgs = 0.f;
-#pragma unroll
+            // warp r: lanes = hidden units, three dot products by shuffle; lane 0 (thread 32 r) owns the ray's loss partial
+            const int r = tid >> 5, lj = tid & 31;
+            float sv = 0.f, swb = 0.f, sgs = 0.f;
+#ifdef __CUDACC__
+            if (r < RT) {
+                const float sj = sm[SM_ST + lj * RP + r];
+                sv = warp_sum(sj * sm[SM_UT + lj * RP + r]);
+                swb = warp_sum(sj * rv[V_WB * RP + lj]);
+                sgs = warp_sum(sj * sm[SM_UPART + lj * RP + r]);
+            }
+#else
+            if (r < RT && lj == 0)
                 for (int j = 0; j < H; ++j) {
                     const float sj = sm[SM_ST + j * RP + r];
                     sv += sj * sm[SM_UT + j * RP + r];
                     swb += sj * rv[V_WB * RP + j];
                     sgs += sj * sm[SM_UPART + j * RP + r];
                 }
+#endif
+            if (r < RT && lj == 0) {
+                const float opac = rv[V_OPAC * RP + r];
                 const float bb = rv[V_WB * RP + H];
                 const float yb = sm[SM_YS + 320 + r], yy = sm[SM_YS + 320 + RP + r];
                 const float xb = swb + opac * bb;                     // b . x
@@ -973,7 +1032,7 @@ OO_DEV void tile_phase(int tid, float* __restrict__ sm, const TileCtx& c, TileAc
             gemm_bwd_data<KP_HD, WS_HD, H, 8, 0>(tid, w + W_CL, act + R_HC * PS, nullptr, nullptr,
                                                  act + R_H4 * PS, H, w + W_A, misc + M_DRAW * PS);
     } else if constexpr (PH == 22) {
-        gemm_bwd_w<2, H / 8>(a.m2, tid, act + R_H4 * PS, act + R_H3 * PS);
+        gemm_bwd_w32(a.m2, tid, act + R_H4 * PS, act + R_H3 * PS);
     } else if constexpr (PH == 23) {
         gemm_bwd_data<H, WS_H, H, 8, 0>(tid, w + W_M2, act + R_H4 * PS, nullptr, nullptr, act + R_H3 * PS, H,
                                         nullptr, nullptr);
@@ -983,7 +1042,7 @@ OO_DEV void tile_phase(int tid, float* __restrict__ sm, const TileCtx& c, TileAc
         gemm_bwd_data<H, WS_CAT, H, 8, 0>(tid, w + W_CAT, act + R_H3 * PS, nullptr, nullptr, act + R_H2 * PS, H,
                                           nullptr, nullptr);
     } else if constexpr (PH == 26) {
-        gemm_bwd_w<2, H / 8>(a.m1, tid, act + R_H2 * PS, act + R_H1 * PS);
+        gemm_bwd_w32(a.m1, tid, act + R_H2 * PS, act + R_H1 * PS);
     } else if constexpr (PH == 27) {
         gemm_bwd_data<H, WS_H, H, 8, 0>(tid, w + W_M1, act + R_H2 * PS, nullptr, nullptr, act + R_H1 * PS, H,
                                         nullptr, nullptr);
@@ -1071,8 +1130,14 @@ OO_DEV void tile_flush(int tid, float* __restrict__ sm, float* __restrict__ slab
     if constexpr (STEP == 0) {
         flush_wfrags<2, KP_IN / 8>(tid, slab, a.in, OFF_IN_W, 0, E1);
         flush_wfrags<2, KP_CAT / 8>(tid, slab, a.cat, OFF_CAT_W, 0, H + E1);
-        flush_wfrags<2, H / 8>(tid, slab, a.m1, OFF_M1_W, 0, H);
-        flush_wfrags<2, H / 8>(tid, slab, a.m2, OFF_M2_W, 0, H);
+        if (tid >= NTHREADS / 2) {                       // second k-half of the 32 x 32 gradients -> scratch (Y area, free here)
+#pragma unroll
+            for (int r = 0; r < 4; ++r) {
+                const int e = wfrag32_row(tid, r) * H + wfrag32_col(tid, r);
+                sm[SM_FEAT + e] = a.m1[r];
+                sm[SM_FEAT + H * H + e] = a.m2[r];
+            }
+        }
         if (PART) flush_wfrags<4, KP_HD / 8>(tid, slab, a.hd, OFF_CL_W, OFF_CP_W, H + E2);
         else flush_wfrags<2, KP_HD / 8>(tid, slab, a.hd, OFF_CL_W, 0, H + E2);
         if (tid < 3 * H) slab[OFF_OC_W + tid] = a.s0;
@@ -1092,14 +1157,23 @@ OO_DEV void tile_flush(int tid, float* __restrict__ sm, float* __restrict__ slab
             if (tid < 8 * H) st4(slab + SLAB_M + 4 * tid, float4{a.gm[0], a.gm[1], a.gm[2], a.gm[3]});
             if (tid <= H) slab[SLAB_MV + tid] = a.s3;     // m[0..31], beta at SLAB_MV + 32 == SLAB_BETA
         }
-        if (tid < RT) {
+        if ((tid & 31) == 0 && (tid >> 5) < RT) {       // thread 32 r owns ray slot r (phases 8 and 32)
             float* rvl = sm + SM_RV;
-            rvl[V_LD * RP + tid] = a.loss[0];
-            rvl[V_LC * RP + tid] = a.loss[1];
-            rvl[V_LO * RP + tid] = a.loss[2];
-            rvl[V_LF * RP + tid] = a.loss[3];
+            const int r = tid >> 5;
+            rvl[V_LD * RP + r] = a.loss[0];
+            rvl[V_LC * RP + r] = a.loss[1];
+            rvl[V_LO * RP + r] = a.loss[2];
+            rvl[V_LF * RP + r] = a.loss[3];
         }
     } else {
+        if (tid < NTHREADS / 2) {
+#pragma unroll
+            for (int r = 0; r < 4; ++r) {
+                const int e = wfrag32_row(tid, r) * H + wfrag32_col(tid, r);
+                slab[OFF_M1_W + e] = a.m1[r] + sm[SM_FEAT + e];
+                slab[OFF_M2_W + e] = a.m2[r] + sm[SM_FEAT + H * H + e];
+            }
+        }
         if (tid < 4) {
             const float* rvl = sm + SM_RV + (V_LD + tid) * RP;
             float sum = 0.f;

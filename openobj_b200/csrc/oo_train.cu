@@ -13,7 +13,7 @@ namespace {
 
 struct TrainParams {
     const float* theta;
-    float* derived;        // [n_cta][DERIVED] per-CTA scratch
+    float* derived;        // [n_obj][DERIVED] out_clip constants of every object (k_gram)
     float* rayrec;         // [n_obj][R][RAYREC] (this step)
     oo_batch b;
     int ray0;              // first ray of this step inside each object's batch (it * rays_per_step)
@@ -47,6 +47,18 @@ struct Phases<END, END, PART> {
     static __device__ __forceinline__ void run(int, float*, const TileCtx&, TileAcc&, long long*) {}
 };
 
+// G = W_ocl^T W_ocl, wb = W_ocl^T b_ocl, bb = b.b of every object (DESIGN.md "clip head inside K1"); one CTA per object
+__global__ void __launch_bounds__(NTHREADS, 1) k_gram(const float* __restrict__ theta, float* __restrict__ derived) {
+    extern __shared__ __align__(16) float sm[];
+    const int tid = threadIdx.x;
+    const float* th = theta + (size_t)blockIdx.x * PSTRIDE;
+    float* der = derived + (size_t)blockIdx.x * DERIVED;
+    gram_stage<-1>(tid, sm, th, der);
+    gram_stage<0>(tid, sm, th, der); __syncthreads();
+    gram_stage<1>(tid, sm, th, der); __syncthreads();
+    gram_stage<2>(tid, sm, th, der);
+}
+
 template <bool PART>
 __global__ void __launch_bounds__(NTHREADS, 1) k_train(const TrainParams prm) {
     extern __shared__ __align__(16) float sm[];
@@ -76,19 +88,12 @@ __global__ void __launch_bounds__(NTHREADS, 1) k_train(const TrainParams prm) {
             const long long ts0 = cyc ? clock64() : 0;
             cur_obj = obj;
             c.theta = prm.theta + (size_t)obj * PSTRIDE;
-            c.derived = prm.derived + (size_t)blockIdx.x * DERIVED;
+            c.derived = prm.derived + (size_t)obj * DERIVED;
             c.slab = prm.slab + (size_t)slot * PSTRIDE;
             c.inv1 = 1.f / ((float)prm.counts[2 * obj] + 1e-10f);
             c.invs = 1.f / ((float)prm.counts[2 * obj + 1] + 1e-10f);
-            if (PART) gram_stage<-1>(tid, sm, c.theta, nullptr);
             stage_weights(tid, sm, c.theta);
-            if (PART) {
-                float* der = prm.derived + (size_t)blockIdx.x * DERIVED;
-                gram_stage<0>(tid, sm, c.theta, der); __syncthreads();
-                gram_stage<1>(tid, sm, c.theta, der); __syncthreads();
-                gram_stage<2>(tid, sm, c.theta, der); __syncthreads();
-                zero_pad_rows(tid, sm);          // the staging used the activation area
-            }
+            if (PART) stage_derived(tid, sm, c.derived);
             __syncthreads();
             if (cyc && tid == 0) cyc[N_TRAIN_PHASES + 2] += clock64() - ts0;
         }
@@ -420,6 +425,16 @@ int launch_k1(const float* theta, int n_obj, const oo_batch* b, int it, int R, f
         OO_CUDA(cudaFuncSetAttribute(k_train<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
         OO_CUDA(cudaFuncSetAttribute(k_train<false>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
         attr_set = true;
+    }
+    if (b->feat_row != nullptr) {
+        const size_t gsmem = (size_t)(SM_GPART + NGG * 36 * 36) * sizeof(float);
+        static bool gattr = false;
+        if (!gattr) {
+            OO_CUDA(cudaFuncSetAttribute(k_gram, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)gsmem));
+            gattr = true;
+        }
+        k_gram<<<n_obj, NTHREADS, gsmem, st>>>(theta, ws->derived);
+        OO_LAUNCH_CHECK();
     }
     if (b->feat_row != nullptr) k_train<true><<<n_cta, NTHREADS, smem, st>>>(prm);
     else k_train<false><<<n_cta, NTHREADS, smem, st>>>(prm);

@@ -82,7 +82,7 @@ class Ensemble:
             self.n_cta, self.n_slots = n_cta.value, n_slots.value
             self._slab = torch.zeros(slab_f.value, **f32)
             self._slot_loss = torch.zeros(self.n_slots * 4, **f32)
-            self._derived = torch.zeros(self.n_cta, 1088, **f32)          # OO_DERIVED_FLOATS per CTA
+            self._derived = torch.zeros(self.n_obj, 1088, **f32)                   # OO_DERIVED_FLOATS per object (k_gram)
             self._clip_grad = torch.zeros(self.n_obj, 512 * 32 + 512, **f32)
             self._rayrec = torch.zeros(self.n_obj, self.R, 36, **f32)      # OO_RAYREC_FLOATS
             self._sched = torch.zeros(sched_i.value, **i32)

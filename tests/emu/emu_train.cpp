@@ -69,6 +69,7 @@ void emulate(const float* theta, const float* derived, int n_obj, const float* p
                     for (int tid = 0; tid < NTHREADS; ++tid) gram_stage<1>(tid, sm, c.theta, der.data());
                     for (int tid = 0; tid < NTHREADS; ++tid) gram_stage<2>(tid, sm, c.theta, der.data());
                     for (int tid = 0; tid < NTHREADS; ++tid) zero_pad_rows(tid, sm);
+                    for (int tid = 0; tid < NTHREADS; ++tid) stage_derived(tid, sm, der.data());
                 }
             }
             const size_t ray = (size_t)obj * rays_per_obj + (size_t)it * R + r0;
