@@ -35,44 +35,81 @@ def flop_per_ray(part):
 
 
 class ClockSampler:
-    """nvidia-smi clocks / throttle reasons during the timed region (B200_PROFILING.md recipe)."""
+    """SM clock and throttle reasons sampled DURING the timed region (B200_PROFILING.md recipe) through NVML from a
+    background thread (a 10 ms period: the timed region of a default run lasts well under a second, less than the
+    start-up time of an `nvidia-smi -lms` child process).  Falls back to one-shot nvidia-smi queries when NVML is
+    not importable."""
 
-    def __init__(self, index=0):
-        self.index, self.rows, self.proc = index, [], None
+    REASONS = (("hw_slowdown", 0x8), ("hw_thermal_slowdown", 0x40), ("sw_thermal_slowdown", 0x20), ("sw_power_cap", 0x4))
 
-    def __enter__(self):
+    def __init__(self, index=0, period_s=0.01):
+        self.index, self.period, self.rows, self.max_mhz = index, period_s, [], None
+        self.stop = threading.Event()
+        self.thread = None
+        self.err = None
+
+    def _visible_index(self):
+        vis = os.environ.get("CUDA_VISIBLE_DEVICES")
+        if vis:
+            ids = [v for v in vis.split(",") if v.strip() != ""]
+            if self.index < len(ids) and ids[self.index].strip().isdigit():
+                return int(ids[self.index])
+        return self.index
+
+    def _loop_nvml(self, nv, h):
+        while not self.stop.is_set():
+            try:
+                self.rows.append((nv.nvmlDeviceGetClockInfo(h, nv.NVML_CLOCK_SM), nv.nvmlDeviceGetCurrentClocksEventReasons(h),
+                                  nv.nvmlDeviceGetPowerUsage(h) / 1000.0))
+            except Exception as e:          # noqa: BLE001 -- keep sampling, remember why a sample was lost
+                self.err = repr(e)
+            self.stop.wait(self.period)
+
+    def _loop_smi(self):
         q = ("clocks.sm,clocks.max.sm,power.draw,clocks_event_reasons.hw_slowdown,clocks_event_reasons.hw_thermal_slowdown,"
              "clocks_event_reasons.sw_thermal_slowdown,clocks_event_reasons.sw_power_cap")
+        while not self.stop.is_set():
+            try:
+                out = subprocess.run(["nvidia-smi", "-i", str(self._visible_index()), "--query-gpu=" + q,
+                                      "--format=csv,noheader,nounits"], capture_output=True, text=True, timeout=5).stdout
+                r = [x.strip() for x in out.strip().split(",")]
+                mask = 0
+                for (name, bit), col in zip(self.REASONS, (3, 4, 5, 6)):
+                    if len(r) > col and r[col].lower().startswith("active"):
+                        mask |= bit
+                self.rows.append((int(r[0]), mask, float(r[2])))
+                self.max_mhz = int(r[1])
+            except Exception as e:          # noqa: BLE001
+                self.err = repr(e)
+
+    def __enter__(self):
         try:
-            self.proc = subprocess.Popen(["nvidia-smi", "-i", str(self.index), "--query-gpu=" + q,
-                                          "--format=csv,noheader,nounits", "-lms", "100"], stdout=subprocess.PIPE, text=True)
-            self.thread = threading.Thread(target=self._read, daemon=True)
-            self.thread.start()
-        except OSError:
-            self.proc = None
+            import pynvml as nv
+            nv.nvmlInit()
+            h = nv.nvmlDeviceGetHandleByIndex(self._visible_index())
+            self.max_mhz = nv.nvmlDeviceGetMaxClockInfo(h, nv.NVML_CLOCK_SM)
+            self.thread = threading.Thread(target=self._loop_nvml, args=(nv, h), daemon=True)
+        except Exception as e:              # noqa: BLE001
+            self.err = repr(e)
+            self.thread = threading.Thread(target=self._loop_smi, daemon=True)
+        self.thread.start()
         return self
 
-    def _read(self):
-        for line in self.proc.stdout:
-            self.rows.append([x.strip() for x in line.split(",")])
-
     def __exit__(self, *exc):
-        if self.proc:
-            time.sleep(0.15)
-            self.proc.terminate()
-            self.thread.join(timeout=2)
+        self.stop.set()
+        self.thread.join(timeout=6)
 
     def summary(self):
-        sm = sorted(int(r[0]) for r in self.rows if r and r[0].isdigit())
+        sm = sorted(r[0] for r in self.rows)
         if not sm:
-            return {"sm_mhz": None, "sm_max_mhz": None, "reasons": ["nvidia-smi unavailable"]}
-        reasons = []
-        for name, col in (("hw_slowdown", 3), ("hw_thermal_slowdown", 4), ("sw_thermal_slowdown", 5), ("sw_power_cap", 6)):
-            if any(len(r) > col and r[col].lower().startswith("active") for r in self.rows):
-                reasons.append(name)
+            return {"sm_mhz": None, "sm_max_mhz": self.max_mhz, "reasons": ["no clock samples: %s" % self.err]}
+        mask = 0
+        for r in self.rows:
+            mask |= r[1]
+        reasons = [name for name, bit in self.REASONS if mask & bit]
         busy = [v for v in sm if v >= 0.6 * sm[-1]] or sm
-        return {"sm_mhz": busy[len(busy) // 2], "sm_max_mhz": int(self.rows[0][1]), "reasons": reasons,
-                "samples": len(sm)}
+        return {"sm_mhz": busy[len(busy) // 2], "sm_max_mhz": self.max_mhz, "reasons": reasons, "samples": len(sm),
+                "power_w_max": max(r[2] for r in self.rows)}
 
 
 def cuda_timer():
