@@ -41,6 +41,7 @@ extern "C" {
 #define OO_TILE_RAYS 10        /* rays one CTA tile processes */
 #define OO_DERIVED_FLOATS 1088
 #define OO_RAYREC_FLOATS 36
+#define OO_GRAM_PART_FLOATS 1092
 
 /* flags written by oo_label_counts / oo_loss_* (reference: render_rays.py:89-94,109-111) */
 #define OO_FLAG_EXPLODE 1      /* some per-object loss term > 1e5: the reference prints and exit(-1)s */
@@ -109,6 +110,8 @@ typedef struct oo_train_ws {   /* caller-allocated scratch; sizes from oo_train_
     int*   flags;              /* [iters] OO_FLAG_* per step (OR over objects; all-reduce across ranks when sharded) */
     float* adam_scal;          /* [iters][3][4]: per step and parameter group {active, lr/bc1, 1/sqrt(bc2), 0} */
     int*   adam_t;             /* [3] persistent Adam step counters per group (trunk+alpha+PE, colour head, clip head) */
+    float* gram_part;          /* [n_obj][4][OO_GRAM_PART_FLOATS] partial out_clip Gram matrices of the fused update kernel */
+    int*   gram_cnt;           /* [n_obj] arrival counters of the update kernel, zero-initialised by the caller (self-resetting) */
 } oo_train_ws;
 
 /* number of CTAs the fused step launches and the scratch sizes (in elements) it needs. */
@@ -140,9 +143,11 @@ int oo_train_frame(float* theta, float* adam_m, float* adam_v, int n_obj, const 
                    oo_train_ws* ws, float* loss_terms, int n_sm, void* stream);
 
 /* the two halves of oo_train_step, separately launchable (bench.py brackets K1 with CUDA events for the roofline;
- * ncu captures use them too): K1 = fused encode/MLP/composite/loss/backward into ws->slab, K4 = slab reduction + AdamW. */
+ * ncu captures use them too): K1 = fused encode/MLP/composite/loss/backward into ws->slab; K4 = one fused launch:
+ * out_clip gradient assembly + slab reduction + AdamW + the out_clip constants (ws->derived) of the NEXT step.
+ * refresh_derived != 0 makes K1 recompute ws->derived from theta first (needed whenever theta was not last written by K4). */
 int oo_train_k1(const float* theta, int n_obj, const oo_batch* batch, int it, int rays_per_step, float scale,
-                oo_train_ws* ws, int n_sm, void* stream);
+                oo_train_ws* ws, int refresh_derived, int n_sm, void* stream);
 int oo_train_k4(float* theta, float* adam_m, float* adam_v, int n_obj, const oo_batch* batch, int it, int rays_per_step,
                 float lr, float weight_decay, float beta1, float beta2, float eps,
                 oo_train_ws* ws, float* loss_terms, int n_sm, void* stream);

@@ -24,7 +24,8 @@ class Batch(Structure):
 
 class TrainWs(Structure):
     _fields_ = [("slab", c_void_p), ("slot_loss", c_void_p), ("derived", c_void_p), ("clip_grad", c_void_p), ("rayrec", c_void_p), ("sched", c_void_p),
-                ("counts", c_void_p), ("flags", c_void_p), ("adam_scal", c_void_p), ("adam_t", c_void_p)]
+                ("counts", c_void_p), ("flags", c_void_p), ("adam_scal", c_void_p), ("adam_t", c_void_p),
+                ("gram_part", c_void_p), ("gram_cnt", c_void_p)]
 
 
 class SampleArgs(Structure):
@@ -79,7 +80,7 @@ _SIGS = {
                         c_int, c_void_p], c_int),
     "oo_train_frame": ([c_void_p, c_void_p, c_void_p, c_int, POINTER(Batch), c_int, c_int, c_float, c_float, c_float,
                         c_float, c_float, c_float, POINTER(TrainWs), c_void_p, c_int, c_void_p], c_int),
-    "oo_train_k1": ([c_void_p, c_int, POINTER(Batch), c_int, c_int, c_float, POINTER(TrainWs), c_int, c_void_p], c_int),
+    "oo_train_k1": ([c_void_p, c_int, POINTER(Batch), c_int, c_int, c_float, POINTER(TrainWs), c_int, c_int, c_void_p], c_int),
     "oo_train_k4": ([c_void_p, c_void_p, c_void_p, c_int, POINTER(Batch), c_int, c_int, c_float, c_float, c_float, c_float, c_float,
                      POINTER(TrainWs), c_void_p, c_int, c_void_p], c_int),
     "oo_adamw_flat": ([c_void_p, c_void_p, c_void_p, c_void_p, c_int64, c_int, c_float, c_float, c_float, c_float,

@@ -388,16 +388,321 @@ __global__ void k_adamw_flat(float* __restrict__ p, const float* __restrict__ g,
     }
 }
 
+// ---- K4 fused (the path oo_train_step / oo_train_frame take): ONE launch per step does
+//   (a) the out_clip gradient assembly of k_clipgrad, applied straight to out_clip.{weight,bias} with AdamW,
+//   (b) slab reduction + AdamW of every other tensor (k_adamw), a quarter of the block per CTA,
+//   (c) the out_clip constants K1 needs in the NEXT step (k_gram: G = W^T W, wb = W^T b, bb = b.b of the UPDATED layer):
+//       each CTA forms the partial product of its 128 rows, the last CTA of an object to arrive sums the four partials
+//       in a fixed order (deterministic).
+// grid = (4 chunks of 128 out_clip rows, n_obj), 256 threads: thread = (row tid / 2, 16 columns).
+constexpr int UPD_CHUNKS = 4, UPD_ROWS = C / UPD_CHUNKS, UPD_THREADS = 256;
+constexpr int GPART = 1092;                   // 33 x 33 partial Gram matrix, padded
+constexpr int UPD_WN = UPD_ROWS * GS;         // staged updated rows [128][36]
+constexpr int UPD_GT = 81, UPD_RG = 3;        // 9 x 9 tiles of 4 x 4 over 36 x 36; three row groups
+
+__device__ __forceinline__ void adam1(float& P, float& M, float& V, float G, float decay, float b1, float b2, float eps,
+                                      float step, float bc2s) {
+    P = P * decay;
+    M = M + (G - M) * (1.f - b1);
+    V = V * b2 + ((1.f - b2) * G) * G;
+    const float den = sqrtf(V) / bc2s + eps;
+    P = P - step * (M / den);
+}
+
+__device__ __forceinline__ void adam4(float* theta, float* am, float* av, size_t idx, const float4& g, float decay, float b1,
+                                      float b2, float eps, float step, float bc2s) {
+    float4 p = *reinterpret_cast<const float4*>(theta + idx);
+    float4 m = *reinterpret_cast<const float4*>(am + idx);
+    float4 v = *reinterpret_cast<const float4*>(av + idx);
+    adam1(p.x, m.x, v.x, g.x, decay, b1, b2, eps, step, bc2s);
+    adam1(p.y, m.y, v.y, g.y, decay, b1, b2, eps, step, bc2s);
+    adam1(p.z, m.z, v.z, g.z, decay, b1, b2, eps, step, bc2s);
+    adam1(p.w, m.w, v.w, g.w, decay, b1, b2, eps, step, bc2s);
+    *reinterpret_cast<float4*>(theta + idx) = p;
+    *reinterpret_cast<float4*>(am + idx) = m;
+    *reinterpret_cast<float4*>(av + idx) = v;
+}
+
+constexpr int UPD_YS_MIN = UPD_RG * 1296;   // the three Gram row-group partials alias the gt-feature staging area
+
+inline size_t update_smem_floats(int R, bool part) {
+    if (!part) return 0;
+    const size_t ys = (size_t)R * UPD_ROWS;
+    return DERIVED + 2 * (size_t)((R + 3) & ~3) + (size_t)R * RAYREC + UPD_WN + (ys > UPD_YS_MIN ? ys : UPD_YS_MIN);
+}
+
+// The kernel is a chain of dependent memory round trips, so every stage issues all of its loads before the first use:
+// stage 1 = parameters / moments / slab slots of this CTA's quarter, the M, m, beta slot sums, the out_clip rows (cp.async)
+// and the ray coefficients; stage 2 = feature-table rows of the active rays; stage 3 = the gt-feature gather and the ray
+// records (cp.async) together with the moments of the out_clip rows.
+template <bool PART>
+__global__ void __launch_bounds__(UPD_THREADS, 2) k_update(float* theta, float* am, float* av, const float* __restrict__ slab,
+                                                           const int* __restrict__ obj_slot, const float* __restrict__ scal,
+                                                           float decay, float b1, float b2, float eps, const ClipGrad cg,
+                                                           const float* __restrict__ slot_loss, const int* __restrict__ counts,
+                                                           float* __restrict__ loss_terms, float* __restrict__ derived,
+                                                           float* gram_part, int* gram_cnt) {
+    extern __shared__ __align__(16) float sh[];   // [1088] M, m, beta | act [Rp] | frow [Rp] | rec [R][36] | wn [128][36] | ys [R][128]
+    __shared__ int s_warp[UPD_THREADS / 32];
+    __shared__ int s_last;
+    const int o = blockIdx.y, chunk = blockIdx.x, tid = threadIdx.x, lane = tid & 31, wv = tid >> 5;
+    const int s0 = obj_slot[o], s1 = obj_slot[o + 1];
+    const int Rp = (cg.R + 3) & ~3;
+    int* act = reinterpret_cast<int*>(sh + DERIVED);
+    int* frow = act + Rp;
+    float* rec = sh + DERIVED + 2 * Rp;
+    float* wn = rec + (size_t)cg.R * RAYREC;
+    float* ys = wn + UPD_WN;
+    float* gp = ys;                         // reused once the gradient is formed
+    const int c_lo = UPD_ROWS * chunk, cl = tid >> 1, j0 = 16 * (tid & 1), cc = c_lo + cl;
+    float* th = theta + (size_t)o * PSTRIDE;
+    const bool clip_on = PART && scal[GROUP_CLIP * 4] != 0.f;
+    const float* src = PART ? cg.rayrec + (size_t)o * cg.R * RAYREC : nullptr;
+
+    if (PART) {
+        // out_clip rows of this chunk -> wn [128][36] (col 32 = bias, 33..35 = 0); awaited before the gradient loop
+        for (int q = tid; q < UPD_ROWS * (H / 4); q += UPD_THREADS) {
+            const int row = q >> 3, v4 = q & 7;
+            OO_CP_ASYNC16(wn + row * GS + 4 * v4, th + OFF_OCL_W + (c_lo + row) * H + 4 * v4);
+        }
+        if (tid < UPD_ROWS) *reinterpret_cast<float4*>(wn + tid * GS + H) = float4{th[OFF_OCL_B + c_lo + tid], 0.f, 0.f, 0.f};
+    }
+    if (chunk == 0 && tid < 4 && loss_terms != nullptr) {
+        // per-object loss terms: masked mean = sum / (count + 1e-10)  (render_rays.py:108)
+        float s = 0.f;
+        for (int q = s0; q < s1; ++q) s += slot_loss[4 * q + tid];
+        const int n = counts[2 * o + (tid == 2 ? 1 : 0)];
+        loss_terms[4 * o + tid] = s / ((float)n + 1e-10f);
+    }
+    // ---- (b) this CTA's quarter of the tensors whose gradient is the slot sum, and the slot sums of M, m, beta
+    {
+        constexpr int NV_LO = OFF_OCL_W / 4, NV = NV_LO + (PEND - OFF_PE_B) / 4, PER = (NV + UPD_CHUNKS - 1) / UPD_CHUNKS;
+        constexpr int NQ = (PER + UPD_THREADS - 1) / UPD_THREADS, NM = (1057 + UPD_THREADS - 1) / UPD_THREADS;
+        const int q1 = min(NV, (chunk + 1) * PER);
+        float4 p[NQ], m[NQ], v[NQ], g[NQ];
+        int off[NQ], grp[NQ];
+        bool on[NQ];
+        float tm[NM];
+#pragma unroll
+        for (int u = 0; u < NQ; ++u) {
+            const int q = chunk * PER + tid + UPD_THREADS * u;
+            off[u] = q < NV_LO ? 4 * q : OFF_PE_B + 4 * (q - NV_LO);
+            grp[u] = group_of_offset(off[u]);
+            on[u] = q < q1 && scal[grp[u] * 4] != 0.f;
+            g[u] = float4{0.f, 0.f, 0.f, 0.f};
+            if (on[u]) {
+                const size_t idx = (size_t)o * PSTRIDE + off[u];
+                p[u] = *reinterpret_cast<const float4*>(theta + idx);
+                m[u] = *reinterpret_cast<const float4*>(am + idx);
+                v[u] = *reinterpret_cast<const float4*>(av + idx);
+            }
+        }
+#pragma unroll
+        for (int u = 0; u < NM; ++u) tm[u] = 0.f;
+        for (int sl = s0; sl < s1; sl += 2) {            // slots summed in order, two per round trip
+            const float* sp = slab + (size_t)sl * PSTRIDE;
+            const bool two = sl + 1 < s1;
+            float4 x0[NQ], x1[NQ];
+            float y0[NM], y1[NM];
+#pragma unroll
+            for (int u = 0; u < NQ; ++u) {
+                x0[u] = x1[u] = float4{0.f, 0.f, 0.f, 0.f};
+                if (on[u]) {
+                    x0[u] = *reinterpret_cast<const float4*>(sp + off[u]);
+                    if (two) x1[u] = *reinterpret_cast<const float4*>(sp + PSTRIDE + off[u]);
+                }
+            }
+#pragma unroll
+            for (int u = 0; u < NM; ++u) {
+                const int q = tid + UPD_THREADS * u;
+                y0[u] = y1[u] = 0.f;
+                if (clip_on && q < 1057) {
+                    y0[u] = sp[SLAB_M + q];
+                    if (two) y1[u] = sp[PSTRIDE + SLAB_M + q];
+                }
+            }
+#pragma unroll
+            for (int u = 0; u < NQ; ++u) {
+                g[u].x += x0[u].x; g[u].y += x0[u].y; g[u].z += x0[u].z; g[u].w += x0[u].w;
+                g[u].x += x1[u].x; g[u].y += x1[u].y; g[u].z += x1[u].z; g[u].w += x1[u].w;
+            }
+#pragma unroll
+            for (int u = 0; u < NM; ++u) { tm[u] += y0[u]; tm[u] += y1[u]; }
+        }
+#pragma unroll
+        for (int u = 0; u < NQ; ++u) {
+            if (!on[u]) continue;
+            const float step = scal[grp[u] * 4 + 1], bc2s = scal[grp[u] * 4 + 2];
+            adam1(p[u].x, m[u].x, v[u].x, g[u].x, decay, b1, b2, eps, step, bc2s);
+            adam1(p[u].y, m[u].y, v[u].y, g[u].y, decay, b1, b2, eps, step, bc2s);
+            adam1(p[u].z, m[u].z, v[u].z, g[u].z, decay, b1, b2, eps, step, bc2s);
+            adam1(p[u].w, m[u].w, v[u].w, g[u].w, decay, b1, b2, eps, step, bc2s);
+            const size_t idx = (size_t)o * PSTRIDE + off[u];
+            *reinterpret_cast<float4*>(theta + idx) = p[u];
+            *reinterpret_cast<float4*>(am + idx) = m[u];
+            *reinterpret_cast<float4*>(av + idx) = v[u];
+        }
+        if (clip_on) {
+#pragma unroll
+            for (int u = 0; u < NM; ++u)
+                if (tid + UPD_THREADS * u < 1057) sh[tid + UPD_THREADS * u] = tm[u];
+        }
+    }
+    if (!PART) return;
+    // ---- (a) gradient of out_clip rows [128 chunk, 128 chunk + 128) and their AdamW update
+    if (clip_on) {
+        // compaction of the rays with a non-zero coefficient A_r (order preserved: deterministic summation order)
+        int n_act = 0;
+        for (int base = 0; base < cg.R; base += UPD_THREADS) {
+            const int r = base + tid;
+            const bool a = r < cg.R && src[(size_t)r * RAYREC + REC_A] != 0.f;
+            const unsigned mk = __ballot_sync(0xffffffffu, a);
+            if (lane == 0) s_warp[wv] = __popc(mk);
+            __syncthreads();
+            int o2 = n_act, tot = 0;
+#pragma unroll
+            for (int w = 0; w < UPD_THREADS / 32; ++w) {
+                if (w < wv) o2 += s_warp[w];
+                tot += s_warp[w];
+            }
+            if (a) act[o2 + __popc(mk & ((1u << lane) - 1u))] = r;
+            n_act += tot;
+            __syncthreads();
+        }
+        for (int i = tid; i < n_act; i += UPD_THREADS) frow[i] = cg.feat_row[(size_t)o * cg.rays_per_obj + act[i]];
+        __syncthreads();
+        // gt feature rows (this chunk's 128 columns) and records of the active rays: all copies in flight together
+        for (int q = tid; q < n_act * (UPD_ROWS / 4); q += UPD_THREADS) {
+            const int i = q >> 5, v4 = q & 31;
+            OO_CP_ASYNC16(ys + i * UPD_ROWS + 4 * v4, cg.feat_table + (size_t)frow[i] * C + c_lo + 4 * v4);
+        }
+        for (int q = tid; q < n_act * (RAYREC / 4); q += UPD_THREADS) {
+            const int i = q / (RAYREC / 4), e = q - i * (RAYREC / 4);
+            OO_CP_ASYNC16(rec + i * RAYREC + 4 * e, src + (size_t)act[i] * RAYREC + 4 * e);
+        }
+        // moments of this thread's 16 weights (and of the row's bias): in flight during the gather
+        const size_t idx = (size_t)o * PSTRIDE + OFF_OCL_W + cc * H + j0;
+        const size_t ib = (size_t)o * PSTRIDE + OFF_OCL_B + cc;
+        float4 m4[4], v4r[4];
+#pragma unroll
+        for (int q4 = 0; q4 < 4; ++q4) {
+            m4[q4] = *reinterpret_cast<const float4*>(am + idx + 4 * q4);
+            v4r[q4] = *reinterpret_cast<const float4*>(av + idx + 4 * q4);
+        }
+        float mb = 0.f, vb = 0.f;
+        if ((tid & 1) == 0) { mb = am[ib]; vb = av[ib]; }
+        OO_CP_ASYNC_WAIT();
+        __syncthreads();
+        float g[16], gb = 0.f;
+#pragma unroll
+        for (int q = 0; q < 16; ++q) g[q] = 0.f;
+#pragma unroll 2
+        for (int i = 0; i < n_act; ++i) {
+            const float ay = rec[i * RAYREC + REC_A] * ys[i * UPD_ROWS + cl];
+            const float* Sp = rec + i * RAYREC + REC_S + j0;
+#pragma unroll
+            for (int q4 = 0; q4 < 16; q4 += 4) {
+                const float4 S4 = *reinterpret_cast<const float4*>(Sp + q4);
+                g[q4] += ay * S4.x; g[q4 + 1] += ay * S4.y; g[q4 + 2] += ay * S4.z; g[q4 + 3] += ay * S4.w;
+            }
+            gb += ay * rec[i * RAYREC + REC_OPAC];
+        }
+        float wm = 0.f;
+        const float* wrow = wn + cl * GS;
+#pragma unroll 8
+        for (int k = 0; k < H; ++k) {
+            const float wk = wrow[k];
+            const float* M = sh + k * H + j0;
+#pragma unroll
+            for (int q4 = 0; q4 < 16; q4 += 4) {
+                const float4 M4 = *reinterpret_cast<const float4*>(M + q4);
+                g[q4] += wk * M4.x; g[q4 + 1] += wk * M4.y; g[q4 + 2] += wk * M4.z; g[q4 + 3] += wk * M4.w;
+            }
+            wm += wk * sh[1024 + k];
+        }
+        float bc = wrow[H];
+#pragma unroll
+        for (int q = 0; q < 16; ++q) g[q] += bc * sh[1024 + j0 + q];
+        gb += wm + bc * sh[1056];
+        __syncthreads();                     // every thread has read its row of wn (and ys) before anything is overwritten
+        const float step = scal[GROUP_CLIP * 4 + 1], bc2s = scal[GROUP_CLIP * 4 + 2];
+#pragma unroll
+        for (int q4 = 0; q4 < 4; ++q4) {
+            float4 pw = *reinterpret_cast<const float4*>(wrow + j0 + 4 * q4);
+            adam1(pw.x, m4[q4].x, v4r[q4].x, g[4 * q4], decay, b1, b2, eps, step, bc2s);
+            adam1(pw.y, m4[q4].y, v4r[q4].y, g[4 * q4 + 1], decay, b1, b2, eps, step, bc2s);
+            adam1(pw.z, m4[q4].z, v4r[q4].z, g[4 * q4 + 2], decay, b1, b2, eps, step, bc2s);
+            adam1(pw.w, m4[q4].w, v4r[q4].w, g[4 * q4 + 3], decay, b1, b2, eps, step, bc2s);
+            *reinterpret_cast<float4*>(wn + cl * GS + j0 + 4 * q4) = pw;
+            *reinterpret_cast<float4*>(theta + idx + 4 * q4) = pw;
+            *reinterpret_cast<float4*>(am + idx + 4 * q4) = m4[q4];
+            *reinterpret_cast<float4*>(av + idx + 4 * q4) = v4r[q4];
+        }
+        if ((tid & 1) == 0) {
+            adam1(bc, mb, vb, gb, decay, b1, b2, eps, step, bc2s);
+            wn[cl * GS + H] = bc;
+            theta[ib] = bc; am[ib] = mb; av[ib] = vb;
+        }
+    } else {
+        OO_CP_ASYNC_WAIT();
+    }
+    __syncthreads();
+    // ---- (c) partial [W | b]^T [W | b] of the (updated) rows of this chunk
+    if (tid < UPD_GT * UPD_RG) {
+        const int t = tid % UPD_GT, rg = tid / UPD_GT;
+        const int k4 = 4 * (t / 9), j4 = 4 * (t % 9);
+        constexpr int RPG = (UPD_ROWS + UPD_RG - 1) / UPD_RG;
+        const int r1 = min(UPD_ROWS, (rg + 1) * RPG);
+        float acc[4][4];
+#pragma unroll
+        for (int x = 0; x < 4; ++x) acc[x][0] = acc[x][1] = acc[x][2] = acc[x][3] = 0.f;
+#pragma unroll 4
+        for (int r = rg * RPG; r < r1; ++r) {
+            const float4 a4 = *reinterpret_cast<const float4*>(wn + r * GS + k4), b4 = *reinterpret_cast<const float4*>(wn + r * GS + j4);
+            acc[0][0] += a4.x * b4.x; acc[0][1] += a4.x * b4.y; acc[0][2] += a4.x * b4.z; acc[0][3] += a4.x * b4.w;
+            acc[1][0] += a4.y * b4.x; acc[1][1] += a4.y * b4.y; acc[1][2] += a4.y * b4.z; acc[1][3] += a4.y * b4.w;
+            acc[2][0] += a4.z * b4.x; acc[2][1] += a4.z * b4.y; acc[2][2] += a4.z * b4.z; acc[2][3] += a4.z * b4.w;
+            acc[3][0] += a4.w * b4.x; acc[3][1] += a4.w * b4.y; acc[3][2] += a4.w * b4.z; acc[3][3] += a4.w * b4.w;
+        }
+#pragma unroll
+        for (int x = 0; x < 4; ++x)
+            *reinterpret_cast<float4*>(gp + rg * 1296 + (k4 + x) * 36 + j4) = float4{acc[x][0], acc[x][1], acc[x][2], acc[x][3]};
+    }
+    __syncthreads();
+    float* mine = gram_part + ((size_t)o * UPD_CHUNKS + chunk) * GPART;
+    for (int q = tid; q < 33 * 33; q += UPD_THREADS) {
+        const int k = q / 33, j = q - 33 * k;
+        __stcg(mine + q, gp[k * 36 + j] + gp[1296 + k * 36 + j] + gp[2 * 1296 + k * 36 + j]);
+    }
+    __threadfence();
+    __syncthreads();
+    if (tid == 0) s_last = atomicAdd(gram_cnt + o, 1) == UPD_CHUNKS - 1 ? 1 : 0;
+    __syncthreads();
+    if (s_last) {
+        __threadfence();
+        const float* gp0 = gram_part + (size_t)o * UPD_CHUNKS * GPART;
+        float* der = derived + (size_t)o * DERIVED;
+        for (int q = tid; q < 33 * 33; q += UPD_THREADS) {
+            const int k = q / 33, j = q - 33 * k;
+            const float v = (__ldcg(gp0 + q) + __ldcg(gp0 + GPART + q)) + (__ldcg(gp0 + 2 * GPART + q) + __ldcg(gp0 + 3 * GPART + q));
+            if (k < H && j < H) der[DER_G + k * H + j] = v;
+            else if (k < H) der[DER_WB + k] = v;            // column 32: W^T b
+            else if (j == H) der[DER_BB] = v;               // b . b
+        }
+        if (tid == 0) gram_cnt[o] = 0;
+    }
+}
+
 int check_train_args(int n_obj, const oo_batch* b, int rays_per_step, const oo_train_ws* ws) {
     OO_REQUIRE(n_obj > 0 && b && ws, "oo_train: null argument / n_obj <= 0");
     OO_REQUIRE(rays_per_step > 0 && b->rays_per_obj >= rays_per_step, "oo_train: bad rays_per_step");
-    OO_REQUIRE(ws->slab && ws->slot_loss && ws->sched && ws->counts && ws->flags && ws->adam_scal && ws->derived && ws->rayrec && ws->clip_grad,
+    OO_REQUIRE(ws->slab && ws->slot_loss && ws->sched && ws->counts && ws->flags && ws->adam_scal && ws->derived && ws->rayrec && ws->clip_grad && ws->gram_part && ws->gram_cnt,
                "oo_train: workspace not allocated");
     return 0;
 }
 
 int launch_k1(const float* theta, int n_obj, const oo_batch* b, int it, int R, float scale, const oo_train_ws* ws,
-              int n_sm, cudaStream_t st) {
+              int n_sm, cudaStream_t st, bool gram = true) {
     Schedule s;                      // only the counts are needed here; the tables are already on the device
     s.tiles_per_obj = tiles_per_object(R);
     const long long T = (long long)n_obj * s.tiles_per_obj;
@@ -426,7 +731,7 @@ int launch_k1(const float* theta, int n_obj, const oo_batch* b, int it, int R, f
         OO_CUDA(cudaFuncSetAttribute(k_train<false>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
         attr_set = true;
     }
-    if (b->feat_row != nullptr) {
+    if (b->feat_row != nullptr && gram) {
         const size_t gsmem = (size_t)(SM_GPART + NGG * 36 * 36) * sizeof(float);
         static bool gattr = false;
         if (!gattr) {
@@ -499,6 +804,34 @@ static int launch_k4(float* theta, float* am, float* av, int n_obj, const oo_bat
     const float* scal = ws->adam_scal + (size_t)it * 12;
     const int* counts = ws->counts + (size_t)it * n_obj * 2;
     const bool part = b && b->feat_row;
+    if (!grads_out) {
+        // the training path: one fused launch (out_clip gradient + AdamW of everything + next step's out_clip constants)
+        ClipGrad cg = {};
+        cg.R = R;
+        if (part) {
+            cg.rayrec = ws->rayrec;
+            cg.feat_row = b->feat_row + (size_t)it * R;
+            cg.feat_table = b->feat_table;
+            cg.rays_per_obj = b->rays_per_obj;
+        }
+        const size_t smem = update_smem_floats(R, part) * sizeof(float);
+        OO_REQUIRE(smem <= 112 * 1024, "oo_train: rays_per_step too large for the update kernel's staging buffer");
+        static size_t attr_smem = 0;
+        if (smem > attr_smem) {
+            OO_CUDA(cudaFuncSetAttribute(k_update<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+            attr_smem = smem;
+        }
+        const float decay = (float)(1.0 - (double)lr * (double)wd);
+        const dim3 ugrid(UPD_CHUNKS, n_obj);
+        if (part)
+            k_update<true><<<ugrid, UPD_THREADS, smem, st>>>(theta, am, av, ws->slab, obj_slot, scal, decay, b1, b2, eps, cg,
+                                                             ws->slot_loss, counts, loss_terms, ws->derived, ws->gram_part, ws->gram_cnt);
+        else
+            k_update<false><<<ugrid, UPD_THREADS, 0, st>>>(theta, am, av, ws->slab, obj_slot, scal, decay, b1, b2, eps, cg,
+                                                            ws->slot_loss, counts, loss_terms, nullptr, nullptr, nullptr);
+        OO_LAUNCH_CHECK();
+        return 0;
+    }
     if (part) {
         ClipGrad cg;
         cg.rayrec = ws->rayrec;
@@ -531,19 +864,19 @@ static int launch_k4(float* theta, float* am, float* av, int n_obj, const oo_bat
 
 static int train_step_impl(float* theta, float* am, float* av, int n_obj, const oo_batch* b, int it, int R, float scale,
                            float lr, float wd, float b1, float b2, float eps, oo_train_ws* ws, float* loss_terms,
-                           float* grads_out, int n_sm, cudaStream_t st) {
+                           float* grads_out, int n_sm, cudaStream_t st, bool gram = true) {
     if (int rc = check_train_args(n_obj, b, R, ws)) return rc;
     OO_REQUIRE((long long)(it + 1) * R <= b->rays_per_obj, "oo_train: step %d exceeds the pre-sampled batch", it);
-    if (int rc = launch_k1(theta, n_obj, b, it, R, scale, ws, n_sm, st)) return rc;
+    if (int rc = launch_k1(theta, n_obj, b, it, R, scale, ws, n_sm, st, gram)) return rc;
     return launch_k4(theta, am, av, n_obj, b, it, R, lr, wd, b1, b2, eps, ws, loss_terms, grads_out, n_sm, st);
 }
 
 extern "C" int oo_train_k1(const float* theta, int n_obj, const oo_batch* batch, int it, int rays_per_step, float scale,
-                           oo_train_ws* ws, int n_sm, void* stream) {
+                           oo_train_ws* ws, int refresh_derived, int n_sm, void* stream) {
     OO_REQUIRE(theta, "oo_train_k1: null theta");
     if (int rc = check_train_args(n_obj, batch, rays_per_step, ws)) return rc;
     OO_REQUIRE((long long)(it + 1) * rays_per_step <= batch->rays_per_obj, "oo_train_k1: step %d exceeds the batch", it);
-    return launch_k1(theta, n_obj, batch, it, rays_per_step, scale, ws, n_sm, (cudaStream_t)stream);
+    return launch_k1(theta, n_obj, batch, it, rays_per_step, scale, ws, n_sm, (cudaStream_t)stream, refresh_derived != 0);
 }
 
 extern "C" int oo_train_k4(float* theta, float* adam_m, float* adam_v, int n_obj, const oo_batch* batch, int it,
@@ -575,8 +908,10 @@ extern "C" int oo_train_frame(float* theta, float* adam_m, float* adam_v, int n_
     OO_REQUIRE(theta && adam_m && adam_v, "oo_train_frame: null parameter buffers");
     for (int it = 0; it < iters; ++it) {
         float* lt = loss_terms ? loss_terms + (size_t)it * n_obj * 4 : nullptr;
+        // the out_clip constants are computed from theta at the first step (theta may have been written from outside
+        // between frames); afterwards every update kernel leaves them ready for the next step
         if (int rc = train_step_impl(theta, adam_m, adam_v, n_obj, batch, it, rays_per_step, scale, lr, weight_decay,
-                                     beta1, beta2, eps, ws, lt, nullptr, n_sm, (cudaStream_t)stream))
+                                     beta1, beta2, eps, ws, lt, nullptr, n_sm, (cudaStream_t)stream, it == 0))
             return rc;
     }
     return 0;

@@ -4,7 +4,8 @@ Replaces, for the vmap training strategy of the reference (objnerf/train.py):
   * utils.update_vmap / functorch.combine_state_for_ensemble (utils.py:55-62): `Ensemble.load_stacked`
     and `Ensemble.stacked()` -- the 19 stacked tensors are strided views of ONE buffer theta[N, PSTRIDE];
   * the per-iteration body train.py:394-474 (vmap(pe), vmap(fc), loss.step_batch_loss, backward,
-    AdamW.step, zero_grad): `Ensemble.train_frame` / `train_step`, two kernel launches per iteration.
+    AdamW.step, zero_grad): `Ensemble.train_frame` / `train_step`, two kernel launches per iteration
+    (K1 fused forward/backward, K4 fused out_clip-gradient assembly + AdamW + next-step constants).
 All arithmetic happens in libopenobj_b200.so; this file only owns buffers and bookkeeping.
 """
 import ctypes
@@ -90,8 +91,11 @@ class Ensemble:
             self.flags = torch.zeros(self.iters, **i32)
             self._adam_scal = torch.zeros(self.iters, 3, 4, **f32)
             self.adam_t = torch.zeros(3, **i32)
+            self._gram_part = torch.zeros(self.n_obj, 4, 1092, **f32)             # OO_GRAM_PART_FLOATS
+            self._gram_cnt = torch.zeros(self.n_obj, **i32)
             self.ws = TrainWs(ptr(self._slab), ptr(self._slot_loss), ptr(self._derived), ptr(self._clip_grad), ptr(self._rayrec), ptr(self._sched),
-                              ptr(self.counts), ptr(self.flags), ptr(self._adam_scal), ptr(self.adam_t))
+                              ptr(self.counts), ptr(self.flags), ptr(self._adam_scal), ptr(self.adam_t),
+                              ptr(self._gram_part), ptr(self._gram_cnt))
             check(self.L.oo_train_schedule(self.n_obj, self.R, self.n_sm, ctypes.byref(self.ws), stream()),
                   "oo_train_schedule")
 
@@ -159,10 +163,11 @@ class Ensemble:
                                         self.R, self.scale, self.lr, self.wd, self.betas[0], self.betas[1], self.eps,
                                         ctypes.byref(self.ws), ptr(loss_terms), self.n_sm, stream()), "oo_train_frame")
 
-    def k1(self, batch_c, it):
-        """K1 alone (fused encode/MLP/composite/loss/backward into the slabs)."""
+    def k1(self, batch_c, it, refresh_derived=True):
+        """K1 alone (fused encode/MLP/composite/loss/backward into the slabs).  refresh_derived=False skips the
+        per-object out_clip constants kernel: valid when the previous launch on theta was `k4` (which leaves them ready)."""
         check(self.L.oo_train_k1(ptr(self.theta), self.n_obj, ctypes.byref(batch_c), it, self.R, self.scale,
-                                 ctypes.byref(self.ws), self.n_sm, stream()), "oo_train_k1")
+                                 ctypes.byref(self.ws), int(bool(refresh_derived)), self.n_sm, stream()), "oo_train_k1")
 
     def k4(self, batch_c, it, loss_terms=None):
         """K4 alone (slab reduction + out_clip gradient assembly + AdamW + derived-constant refresh)."""
