@@ -127,8 +127,9 @@ __device__ __forceinline__ int sample_ray_a(const oo_sample_args& a, const Rng& 
 
 // ---- pass B for one ray: depth placement along the ray and the sample points.  rk_* = rank of the ray inside its class
 // (tape rows in tape_by_rank mode); max_bound = max sampled depth of the object's batch (vmap.py:489, quirk 6)
+// zo [S] / po [S][3]: where the ray's depths and points go (global rows, or the CTA's staging tile in the parallel path)
 __device__ __forceinline__ void sample_ray_b(const SampleK& k, const Rng& g, int obj, int ray, int n_rays, int rk_inv, int rk_val,
-                                             int rk_obj, int rk_oth, float max_bound) {
+                                             int rk_obj, int rk_oth, float max_bound, float* zo, float* po) {
     const oo_sample_args& a = k.a;
     const bool rng = a.rng_mode != 0;
     const int S = a.n_c2s + a.n_bins;
@@ -183,8 +184,6 @@ __device__ __forceinline__ void sample_ray_b(const SampleK& k, const Rng& g, int
     const float wy = T[4] * dx + T[5] * dy + T[6] * dz;
     const float wz = T[8] * dx + T[9] * dy + T[10] * dz;
     const float ox = T[3], oy = T[7], oz = T[11];
-    float* zo = a.z + o * S;
-    float* po = a.pcs + o * S * 3;
     for (int i = 0; i < S; ++i) {
         zo[i] = zs[i];
         po[3 * i + 0] = __fadd_rn(ox, __fmul_rn(wx, zs[i]));
@@ -257,7 +256,9 @@ __global__ void __launch_bounds__(NTH, 1) k_sample(const SampleK k) {
     const float max_bound = sh_max[0];                                             // vmap.py:489
     if (tid == 0 && a.oob_count && sh_oob) atomicAdd(a.oob_count, sh_oob);
     for (int ray = r_begin; ray < r_end; ++ray) {
-        sample_ray_b(k, g, obj, ray, n_rays, rk_inv, ray - rk_inv, rk_obj, rk_oth, max_bound);
+        const size_t orow = (size_t)obj * n_rays + ray;
+        const int S = a.n_c2s + a.n_bins;
+        sample_ray_b(k, g, obj, ray, n_rays, rk_inv, ray - rk_inv, rk_obj, rk_oth, max_bound, a.z + orow * S, a.pcs + orow * S * 3);
         const float d = a.gt_depth[(size_t)obj * n_rays + ray];
         const int state = a.labels[(size_t)obj * n_rays + ray];
         if (d <= a.min_bound) ++rk_inv;
@@ -283,13 +284,35 @@ __global__ void __launch_bounds__(256) k_sample_a(const SampleK k, int* __restri
     if (oob && a.oob_count) atomicAdd(a.oob_count, oob);
 }
 
+// One thread places the samples of one ray into the CTA's staging tile (z [256][S], points [256][S][3]); the tile is a
+// contiguous range of the outputs and leaves with 128-bit, fully coalesced stores (a thread writing its own 40 B / 120 B
+// rows directly costs one 32-byte sector per 4-byte store).
 __global__ void __launch_bounds__(256) k_sample_b(const SampleK k, const int* __restrict__ max_bits) {
+    extern __shared__ __align__(16) float tile[];
     const oo_sample_args& a = k.a;
-    const int obj = blockIdx.y, n_rays = a.n_frames * a.n_samples;
-    const int ray = blockIdx.x * blockDim.x + threadIdx.x;
-    if (ray >= n_rays) return;
-    const Rng g = make_rng(a, obj);
-    sample_ray_b(k, g, obj, ray, n_rays, 0, 0, 0, 0, __int_as_float(max_bits[obj]));
+    const int obj = blockIdx.y, n_rays = a.n_frames * a.n_samples, S = a.n_c2s + a.n_bins;
+    const int ray0 = blockIdx.x * blockDim.x, ray = ray0 + threadIdx.x;
+    const int n_here = min((int)blockDim.x, n_rays - ray0);
+    float* zt = tile;
+    float* pt = tile + (size_t)blockDim.x * S;
+    if (ray < n_rays) {
+        const Rng g = make_rng(a, obj);
+        sample_ray_b(k, g, obj, ray, n_rays, 0, 0, 0, 0, __int_as_float(max_bits[obj]), zt + threadIdx.x * S, pt + threadIdx.x * S * 3);
+    }
+    __syncthreads();
+    const size_t row0 = (size_t)obj * n_rays + ray0;
+    float* zg = a.z + row0 * S;
+    float* pg = a.pcs + row0 * S * 3;
+    const int nz = n_here * S, np = 3 * nz;
+    if (((reinterpret_cast<uintptr_t>(zg) | reinterpret_cast<uintptr_t>(pg)) & 15) == 0 && ((blockDim.x * S) & 3) == 0) {
+        for (int i = threadIdx.x; i < nz / 4; i += blockDim.x) reinterpret_cast<float4*>(zg)[i] = reinterpret_cast<const float4*>(zt)[i];
+        for (int i = 4 * (nz / 4) + threadIdx.x; i < nz; i += blockDim.x) zg[i] = zt[i];
+        for (int i = threadIdx.x; i < np / 4; i += blockDim.x) reinterpret_cast<float4*>(pg)[i] = reinterpret_cast<const float4*>(pt)[i];
+        for (int i = 4 * (np / 4) + threadIdx.x; i < np; i += blockDim.x) pg[i] = pt[i];
+    } else {
+        for (int i = threadIdx.x; i < nz; i += blockDim.x) zg[i] = zt[i];
+        for (int i = threadIdx.x; i < np; i += blockDim.x) pg[i] = pt[i];
+    }
 }
 
 __global__ void k_rng_fill(uint64_t seed, uint32_t frame, const int32_t* __restrict__ obj_ids, int64_t per_obj, int kind,
@@ -410,7 +433,13 @@ extern "C" int oo_sample_rays(const oo_sample_args* a, void* stream) {
         const dim3 grid((n_rays + 255) / 256, a->n_obj);
         k_sample_a<<<grid, 256, 0, (cudaStream_t)stream>>>(k, max_bits);
         OO_LAUNCH_CHECK();
-        k_sample_b<<<grid, 256, 0, (cudaStream_t)stream>>>(k, max_bits);
+        const size_t tile_bytes = (size_t)256 * S * 4 * sizeof(float);        // z [256][S] + points [256][S][3]; <= 128 KB (S <= 32)
+        static size_t tile_attr = 48 * 1024;
+        if (tile_bytes > tile_attr) {
+            OO_CUDA(cudaFuncSetAttribute(k_sample_b, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)tile_bytes));
+            tile_attr = tile_bytes;
+        }
+        k_sample_b<<<grid, 256, tile_bytes, (cudaStream_t)stream>>>(k, max_bits);
         OO_LAUNCH_CHECK();
         return 0;
     }
