@@ -113,7 +113,8 @@ constexpr int SM_FEAT = SM_UPART + H * RP;           // Y [10][512]: gt part fea
                                                      // phase 10 overwrites each warp's 32 columns with its partial W^T y
 constexpr int YSTR = C + 4;                          // row stride of Y: YSTR % 32 == 4 -> conflict-free A fragments in phase 10
 constexpr int SM_YS = SM_FEAT + RT * YSTR;              // gt-feature statistics: partials [10][16 warps][2], totals [2][12]
-constexpr int SM_TOTAL = SM_YS + 352;                // floats
+constexpr int SM_FROW = SM_YS + 352;                 // int [12]: feature-table rows of the tile's rays (phase 0 -> phase 1)
+constexpr int SM_TOTAL = SM_FROW + 12;               // floats
 // ray-value rows
 constexpr int V_DEPTH = 0, V_OPAC = 1, V_COL = 2, V_GD = 5, V_GO = 6, V_GC = 7, V_CF = 10, V_BG = 11,
               V_LD = 12, V_LC = 13, V_LO = 14, V_LF = 15, V_A = 16, V_B = 17, V_ZSRC = 18,

@@ -539,6 +539,47 @@ OO_DEV void zero_pad_rows(int tid, float* sm) {
     for (int i = tid; i < 2 * H * RP + NRV_TILE * RP; i += NTHREADS) sm[SM_ST + i] = 0.f;
 }
 
+#ifdef __CUDACC__
+// Phase 0 of a training tile with its global loads taken out: while a tile is being processed every thread holds ONE value
+// of the next tile in a register (issued before the tile starts, so the HBM round trip hides behind ~100k cycles of work):
+//   tid < 300: pcs, 300..399: z, 400..449: gt depth / label / r / g / b of the rays, 450..459: feature-table rows.
+static_assert(4 * P + 6 * RT <= NTHREADS, "one prefetched value per thread");
+template <bool PART>
+OO_DEV float tile_prefetch(int tid, const TileCtx& c) {
+    float v = 0.f;
+    if (tid < 3 * P) {
+        if (tid < c.npts * 3) v = OO_LDG(c.pcs + tid);
+    } else if (tid < 4 * P) {
+        if (tid - 3 * P < c.npts) v = OO_LDG(c.z + tid - 3 * P);
+    } else if (tid < 4 * P + 5 * RT) {
+        const int q = (tid - 4 * P) / RT, r = (tid - 4 * P) - q * RT;
+        if (r < c.nrays) v = q == 0 ? OO_LDG(c.gt_depth + r) : q == 1 ? (float)c.labels[r] : (float)c.gt_rgb[3 * r + q - 2];
+    } else if (PART && tid < 4 * P + 6 * RT) {
+        const int r = tid - (4 * P + 5 * RT);
+        if (r < c.nrays) v = __int_as_float(OO_LDG(c.feat_row + r));
+    }
+    return v;
+}
+
+template <bool PART>
+OO_DEV void tile_phase0_pre(int tid, float* __restrict__ sm, const TileCtx& c, float pre) {
+    float* act = sm + SM_ACT;
+    if (tid < 3 * P) {
+        const int p = tid / 3, ch = tid - 3 * p;
+        const float t = pre / c.scale;
+        act[(R_T + ch) * PS + p] = t;
+        act[(R_E1 + ch) * PS + p] = t;
+    } else if (tid < 4 * P) {
+        act[(R_MISC + M_Z) * PS + tid - 3 * P] = pre;
+    } else if (tid < 4 * P + 5 * RT) {
+        const int q = (tid - 4 * P) / RT, r = (tid - 4 * P) - q * RT;
+        sm[SM_RV + (V_GTD + q) * RP + r] = pre;
+    } else if (PART && tid < 4 * P + 6 * RT) {
+        reinterpret_cast<int*>(sm + SM_FROW)[tid - (4 * P + 5 * RT)] = __float_as_int(pre);
+    }
+}
+#endif
+
 // ------------------------------------------------------------------------------------------------
 // phases
 // ------------------------------------------------------------------------------------------------
@@ -575,19 +616,22 @@ OO_DEV void tile_phase(int tid, float* __restrict__ sm, const TileCtx& c, TileAc
                 rv[(V_GTD + q) * RP + r] = v;
             }
         }
+        if (PART && tid >= 256 && tid < 256 + RT)         // feature-table rows of the tile's rays (consumed by phase 1)
+            reinterpret_cast<int*>(sm + SM_FROW)[tid - 256] = tid - 256 < c.nrays ? OO_LDG(c.feat_row + tid - 256) : 0;
+    } else if constexpr (PH == 1) {
         if (PART) {
             // gt part features of the tile's rays -> Y [10][512]; asynchronous, awaited at the end of phase 8
+            const int* frow = reinterpret_cast<const int*>(sm + SM_FROW);
             for (int i = tid; i < RT * (C / 4); i += NTHREADS) {
                 const int r = i / (C / 4), q = i - r * (C / 4);
                 float* dst = sm + SM_FEAT + r * YSTR + 4 * q;
                 if (r < c.nrays) {
-                    OO_CP_ASYNC16(dst, c.feat_table + (size_t)OO_LDG(c.feat_row + r) * C + 4 * q);
+                    OO_CP_ASYNC16(dst, c.feat_table + (size_t)frow[r] * C + 4 * q);
                 } else {
                     dst[0] = dst[1] = dst[2] = dst[3] = 0.f;
                 }
             }
         }
-    } else if constexpr (PH == 1) {
         // proj = B t ; e[3 + 21 k + d] = sin(pi * 2^k * proj) (embedding.py:48-53).  The reference's argument for band k
         // is fl(2^k proj * pi_f) = 2^k * fl(proj * pi_f) exactly (power-of-two scaling commutes with rounding), so all
         // six bands follow from one sincosf by angle doubling: s' = 2 s c, c' = (c - s)(c + s)  (norm error only doubles).

@@ -80,10 +80,26 @@ __global__ void __launch_bounds__(NTHREADS, 1) k_train(const TrainParams prm) {
     c.cs = prm.cs; c.os = prm.os; c.fs = prm.fs;
     c.feat_table = prm.b.feat_table;
 
+    // per-tile pointers (everything that depends only on the tile index)
+    auto tile_ptrs = [&](int t, TileCtx& x) {
+        const int obj = t / prm.tiles_per_obj;
+        const int r0 = (t - obj * prm.tiles_per_obj) * RT;
+        const size_t ray = (size_t)obj * prm.b.rays_per_obj + prm.ray0 + r0;
+        x.nrays = min(RT, prm.R - r0);
+        x.npts = x.nrays * S;
+        x.pcs = prm.b.pcs + ray * (S * 3);
+        x.z = prm.b.z + ray * S;
+        x.gt_depth = prm.b.gt_depth + ray;
+        x.gt_rgb = prm.b.gt_rgb + ray * 3;
+        x.labels = prm.b.labels + ray;
+        x.feat_row = PART ? prm.b.feat_row + ray : nullptr;
+        x.rayrec = prm.rayrec + ((size_t)obj * prm.R + r0) * RAYREC;
+    };
+    tile_ptrs(t_begin, c);
+    float pre = tile_prefetch<PART>(tid, c);          // this thread's input value of the first tile
     int cur_obj = -1;
     for (int t = t_begin; t < t_end; ++t) {
         const int obj = t / prm.tiles_per_obj;
-        const int r0 = (t - obj * prm.tiles_per_obj) * RT;
         if (obj != cur_obj) {
             const long long ts0 = cyc ? clock64() : 0;
             cur_obj = obj;
@@ -97,18 +113,21 @@ __global__ void __launch_bounds__(NTHREADS, 1) k_train(const TrainParams prm) {
             __syncthreads();
             if (cyc && tid == 0) cyc[N_TRAIN_PHASES + 2] += clock64() - ts0;
         }
-        const size_t ray = (size_t)obj * prm.b.rays_per_obj + prm.ray0 + r0;
-        c.nrays = min(RT, prm.R - r0);
-        c.npts = c.nrays * S;
-        c.pcs = prm.b.pcs + ray * (S * 3);
-        c.z = prm.b.z + ray * S;
-        c.gt_depth = prm.b.gt_depth + ray;
-        c.gt_rgb = prm.b.gt_rgb + ray * 3;
-        c.labels = prm.b.labels + ray;
-        c.feat_row = PART ? prm.b.feat_row + ray : nullptr;
-        c.rayrec = prm.rayrec + ((size_t)obj * prm.R + r0) * RAYREC;
-
-        Phases<0, N_TRAIN_PHASES, PART>::run(tid, sm, c, acc, cyc);
+        float nxt = 0.f;
+        if (t + 1 < t_end) {                           // the next tile's inputs start their trip now
+            TileCtx nx;
+            tile_ptrs(t + 1, nx);
+            nxt = tile_prefetch<PART>(tid, nx);
+        }
+        tile_ptrs(t, c);
+        {
+            const long long t0 = cyc ? clock64() : 0;
+            tile_phase0_pre<PART>(tid, sm, c, pre);
+            __syncthreads();
+            if (cyc && tid == 0) cyc[0] += clock64() - t0;
+        }
+        Phases<1, N_TRAIN_PHASES, PART>::run(tid, sm, c, acc, cyc);
+        pre = nxt;
 
         const bool last_of_obj = (t + 1 == t_end) || ((t + 1) / prm.tiles_per_obj != obj);
         if (last_of_obj) {
