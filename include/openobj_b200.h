@@ -156,6 +156,31 @@ int oo_train_k4(float* theta, float* adam_m, float* adam_v, int n_obj, const oo_
 int oo_adamw_flat(float* p, const float* g, float* m, float* v, int64_t n, int step,
                   float lr, float weight_decay, float beta1, float beta2, float eps, void* stream);
 
+/* ---- a17: the background model (objnerf/train.py:300-315,379-388,447-463; vmap.py:43-47): ONE OccupancyMap of
+ *      hidden width `hidden` (128 in room_0.json) + UniDirsEmbed(scale = bg_scale 5), n_per_optim_bg = 1200 rays x
+ *      (n_bins_cam2surface_bg 5 + n_bins 9) = 14 samples per step.  M = 16 800 points with K <= 215 are plain GEMMs:
+ *      layer-by-layer FP32 kernels + the K3 compositing/loss pair.  Parameters live in ONE flat block in
+ *      named_parameters() order (18 fc tensors, then B_layer.weight), offsets rounded to 4 floats. */
+int oo_bg_param_count(int hidden);
+int oo_bg_param_offset(int hidden, int i);
+int oo_bg_param_size(int hidden, int i);
+/* floats of caller-allocated scratch for n_pts points / n_rays rays */
+int64_t oo_bg_ws_floats(int hidden, int n_pts, int n_rays);
+/* pe -> fc_occ_map forward (train.py:449-450): alpha [n_pts] (x10 applied), color [n_pts][3], clip [n_pts][512] or NULL,
+ * emb_out [n_pts][129] or NULL */
+int oo_bg_forward(const float* theta, int hidden, const float* pcs, int n_pts, float scale, float* alpha, float* color,
+                  float* clip, float* emb_out, float* ws, void* stream);
+/* one optimisation step on rays [n_rays] x samples [n_samp] (train.py:447-474 for the background): forward,
+ * step_batch_loss on [1,R,S], backward, AdamW (adam_step = 1-based step count).  feat_row/feat_table NULL = part features
+ * off (the clip head then has no gradient and is skipped by the optimiser).  grads_out != NULL: write the flat gradient
+ * (parameter layout) and do NOT update.  terms_out [4], loss_out [1], flags_out [1] as oo_loss_fwd. */
+int oo_bg_train_step(float* theta, float* adam_m, float* adam_v, int hidden, const float* pcs, const float* z,
+                     const float* gt_depth, const uint8_t* gt_rgb, const uint8_t* labels, const int32_t* feat_row,
+                     const float* feat_table, int n_rays, int n_samp, float scale, int adam_step, float lr,
+                     float weight_decay, float beta1, float beta2, float eps, float color_scaling, float opacity_scaling,
+                     float feat_scaling, float* ws, float* terms_out, float* loss_out, int* flags_out, float* grads_out,
+                     void* stream);
+
 /* ---- a13-a15: sceneObject.get_training_samples + sample_3d_points for ALL objects in one launch
  *      (objnerf/vmap.py:386-554, utils.py:324-397).  Keyframe rings stay in the reference's layout and
  *      are addressed through per-object pointer tables. */

@@ -92,6 +92,15 @@ _SIGS = {
     "oo_zmerge": ([c_void_p, c_void_p, c_void_p, c_void_p, c_int, c_int64, c_void_p, c_void_p, c_void_p, c_void_p],
                   c_int),
     "oo_fma_peak": ([c_int, c_int, c_void_p, c_void_p], c_int),
+    "oo_bg_param_count": ([c_int], c_int),
+    "oo_bg_param_offset": ([c_int, c_int], c_int),
+    "oo_bg_param_size": ([c_int, c_int], c_int),
+    "oo_bg_ws_floats": ([c_int, c_int, c_int], c_int64),
+    "oo_bg_forward": ([c_void_p, c_int, c_void_p, c_int, c_float, c_void_p, c_void_p, c_void_p, c_void_p, c_void_p,
+                       c_void_p], c_int),
+    "oo_bg_train_step": ([c_void_p, c_void_p, c_void_p, c_int, c_void_p, c_void_p, c_void_p, c_void_p, c_void_p, c_void_p,
+                          c_void_p, c_int, c_int, c_float, c_int, c_float, c_float, c_float, c_float, c_float, c_float,
+                          c_float, c_float, c_void_p, c_void_p, c_void_p, c_void_p, c_void_p, c_void_p], c_int),
 }
 
 EXPORTS = tuple(_SIGS)

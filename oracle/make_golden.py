@@ -345,6 +345,79 @@ def gen_render(m):
     return out
 
 
+def gen_bg_step(m):
+    """The background model's step (train.py:447-474 with scene_bg): Trainer with hidden_feature_size_bg / bg_scale
+    (vmap.py:43-47), non-vmap forward, step_batch_loss on [1, R, S = 5 + 9], backward, AdamW."""
+    torch.manual_seed(4321)
+    R, S = 24, 14
+    base = small_cfg()
+    c = small_cfg(hidden_feature_size=base.hidden_feature_size_bg, obj_scale=base.bg_scale)
+    c.obj_id = 0
+    tr = m["trainer"].Trainer(c)
+    tr.pe.B_layer.weight.data += 0.01 * torch.randn(21, 3)
+    params = list(tr.fc_occ_map.parameters()) + [tr.pe.B_layer.weight]
+    opt = torch.optim.AdamW(params, lr=1e-3, weight_decay=0.013)
+    g = torch.Generator().manual_seed(77)
+    z = torch.sort(0.5 + 5.0 * torch.rand(R, S, generator=g), dim=-1).values
+    o = torch.randn(R, 1, 3, generator=g) * 0.3
+    d = torch.randn(R, 1, 3, generator=g)
+    d = d / d.norm(dim=-1, keepdim=True)
+    pcs = (o + d * z[..., None]).float()
+    gt_depth = (z[..., 8] + 0.05 * torch.randn(R, generator=g)).float()
+    gt_depth[3] = 0.0
+    gt_rgb8 = torch.randint(0, 256, (R, 3), generator=g, dtype=torch.uint8)
+    labels = torch.randint(0, 3, (R,), generator=g, dtype=torch.uint8)
+    labels[0], labels[1], labels[2] = 1, 0, 2
+    gt_feat = torch.randint(-8, 9, (R, 512), generator=g).float() / 4.0
+    gt_feat[5] = 0.0
+    mask_depth = gt_depth > 0
+    gt_rgb = gt_rgb8 / 255.
+    out = dict(pcs=pcs, z=z, gt_depth=gt_depth, gt_rgb8=gt_rgb8, labels=labels, gt_feat=gt_feat,
+               hidden=torch.tensor(c.hidden_feature_size), scale=torch.tensor(float(c.obj_scale)))
+    for i, p in enumerate(params):
+        out["p%02d" % i] = p.detach().clone()
+
+    def step_loss(part):
+        emb = tr.pe(pcs)
+        a, col, f = tr.fc_occ_map(emb)
+        if part:
+            l, _ = m["loss"].step_batch_loss(a[None], col[None], gt_depth[None], gt_rgb[None], labels[None], mask_depth[None],
+                                             z[None], gt_partfeat=gt_feat[None], pred_partfeat=f[None])
+        else:
+            l, _ = m["loss"].step_batch_loss(a[None], col[None], gt_depth[None], gt_rgb[None], labels[None], mask_depth[None],
+                                             z[None])
+        return emb, a, col, f, l
+
+    emb, a, col, f, l = step_loss(True)
+    out.update(emb=emb.detach()[:4], alpha=a.detach(), color=col.detach(), clip=f.detach()[:2], loss_on=l.detach())
+    l.backward()
+    for i, p in enumerate(params):
+        out["g_on%02d" % i] = p.grad.detach().clone()
+    opt.zero_grad(set_to_none=True)
+    _, _, _, _, l = step_loss(False)
+    out["loss_off"] = l.detach()
+    l.backward()
+    none_idx = []
+    for i, p in enumerate(params):
+        if p.grad is None:
+            none_idx.append(i)
+        else:
+            out["g_off%02d" % i] = p.grad.detach().clone()
+    out["g_off_none"] = torch.tensor(none_idx)
+    opt.zero_grad(set_to_none=True)
+    losses = []
+    for it in range(3):                                  # 2 steps part ON, then 1 step part OFF (clip head untouched)
+        _, _, _, _, l = step_loss(it < 2)
+        l.backward()
+        opt.step()
+        opt.zero_grad(set_to_none=True)
+        losses.append(l.detach())
+    out["losses_3"] = torch.stack(losses)
+    for i, p in enumerate(params):
+        out["q3_%02d" % i] = p.detach().clone()
+    return out
+
+
 def save(name, d):
     arrs = {k: (v.numpy() if torch.is_tensor(v) else np.asarray(v)) for k, v in d.items()}
     path = os.path.join(OUT, name)
@@ -355,6 +428,10 @@ def save(name, d):
 def main():
     os.makedirs(OUT, exist_ok=True)
     m = rh.load()
+    if "--only-bg" in sys.argv:                 # added after the other files were frozen: do not touch them
+        save("bg_step.npz", gen_bg_step(m))
+        return
+    save("bg_step.npz", gen_bg_step(m))
     save("model_step.npz", gen_model_step(m))
     save("sample_obj.npz", gen_sampling(m, bg=False))
     save("sample_bg.npz", gen_sampling(m, bg=True))
