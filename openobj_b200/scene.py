@@ -11,6 +11,7 @@ nothing but the per-step zero-mask flags, OR-reduced once per frame."""
 import torch
 
 from . import layout, sampler, vmap
+from .background import BackgroundModel
 from .ensemble import Ensemble, FrameBatch
 
 
@@ -33,6 +34,10 @@ class Scene:
                                           dtype=torch.float32, device=self.device)
         self._stale = False
         self.batch = None
+        # the separate background model (train.py:236-242): one hidden-128 model, not part of the vmap ensemble; it lives
+        # on the last rank (the ensemble's round-robin starts at rank 0)
+        self.scene_bg, self.bg, self.bg_batch, self.bg_tables = None, None, None, None
+        self.bg_rank = world - 1
 
     # ---- train.py:164-256 ---------------------------------------------------------------------------------
     def add_frame(self, sample):
@@ -49,8 +54,26 @@ class Scene:
         twc32 = twc.to(torch.float32)
         objs, slots, bboxes = [], [], []
         for obj_id in sorted(int(k) for k in sample["bbox_dict"].keys()):                 # torch.unique order (train.py:191)
-            if obj_id == -1 or (cfg.do_bg and obj_id == 0):
-                continue               # the separate background model is not part of the vmap ensemble (train.py:236-242)
+            if obj_id == -1:
+                continue
+            if cfg.do_bg and obj_id == 0:
+                # the separate background model is not part of the vmap ensemble (train.py:236-242)
+                if self.rank != self.bg_rank:
+                    continue
+                bbox = sample["bbox_dict"][obj_id]
+                if self.scene_bg is None:
+                    self.scene_bg = vmap.sceneObject(cfg, 0, rgb, depth, None, bbox, twc, frame_id, defer_write=True)
+                    self.bg = BackgroundModel(hidden=cfg.hidden_feature_size_bg, device=self.device,
+                                              rays_per_step=cfg.n_per_optim_bg,
+                                              n_samp=self.scene_bg.n_bins_cam2surface + self.scene_bg.n_bins,
+                                              lr=cfg.learning_rate, weight_decay=cfg.weight_decay, scale=cfg.bg_scale)
+                    self.bg.adopt(self.scene_bg.trainer.fc_occ_map, self.scene_bg.trainer.pe)
+                    self.bg_tables = sampler.RingTables([self.scene_bg], self.device)
+                    slot = 0
+                else:
+                    slot = self.scene_bg.push_slot(frame_id)
+                objs.append(self.scene_bg); slots.append(slot); bboxes.append(bbox)
+                continue
             if obj_id not in self.global_index:
                 if len(self.global_index) >= cfg.max_n_models * self.world:
                     continue           # "models full" (train.py:231-233)
@@ -114,11 +137,32 @@ class Scene:
         table = self.part_table.view(-1, self.part_table.shape[-1]) if self.part_mode else None
         self.batch = FrameBatch(out.pcs, out.z, out.gt_depth, out.gt_rgb, out.labels, out.feat_row, table)
         self.sample_out = out
+        if self.scene_bg is not None:
+            # train.py:300-315: the background draws n_iter_per_frame * win_size_bg keyframes x n_samples_per_frame_bg
+            # pixels with 5 + 9 samples per ray
+            b = self.scene_bg
+            rng_bg = sampler.counter_rng([b], self.seed, self.frames_seen, self.device)
+            pf_bg = None
+            if self.part_mode:
+                import numpy as np
+                pf_bg = torch.from_numpy((b.use_frame / b.stride).astype(np.int64).astype(np.int32)[None]).to(self.device, non_blocking=True)
+            ob = sampler.sample(None, None, None, None, pf_bg, self.cam.rays_dir_cache, rng_bg,
+                                cfg.n_iter_per_frame * cfg.win_size_bg, cfg.n_samples_per_frame_bg, b.n_bins_cam2surface,
+                                b.n_bins, b.surface_eps, b.stop_eps, b.min_bound, cfg.part_down if self.part_mode else 0,
+                                (self.pw, self.ph) if self.part_mode else (0, 0), out=getattr(self, "bg_sample_out", None),
+                                tables=self.bg_tables)
+            self.bg_sample_out = ob
+            self.bg_batch = FrameBatch(ob.pcs, ob.z, ob.gt_depth, ob.gt_rgb, ob.labels, ob.feat_row, table)
         return self.batch
 
     # ---- train.py:394-474 -----------------------------------------------------------------------------------
-    def train(self, iters=None, loss_terms=None):
+    def train(self, iters=None, loss_terms=None, bg_loss=None):
+        """loss_terms [iters, N, 4] (optional) receives the ensemble's per-object terms; bg_loss [iters] the background's
+        scalar loss of each step (the reference adds it to the same scalar, train.py:463: the two problems share no
+        tensor, so they are trained as two independent launch sequences)."""
         self.ens.train_frame(self.batch, iters=iters, loss_terms=loss_terms, flag_allreduce=self.flag_allreduce)
+        if self.bg is not None and self.bg_batch is not None:
+            self.bg.train_frame(self.bg_batch, iters=iters or self.cfg.n_iter_per_frame, loss_out=bg_loss)
 
     def step_frame(self, sample, iters=None, loss_terms=None):
         self.add_frame(sample)

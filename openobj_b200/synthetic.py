@@ -30,7 +30,7 @@ class SyntheticScene:
     """Frame generator: the same N objects seen from a smoothly moving camera."""
 
     def __init__(self, n_obj, W=1200, H=680, part_mode=True, part_down=5, clip=512, seed=0, first_id=1, pin=False,
-                 n_distinct=4):
+                 n_distinct=4, with_bg=False):
         self.n_obj, self.W, self.H, self.part_mode, self.part_down, self.clip = n_obj, W, H, part_mode, part_down, clip
         self.rng = np.random.default_rng(seed)
         self.ids = list(range(first_id, first_id + n_obj))
@@ -46,6 +46,8 @@ class SyntheticScene:
         for oid, (x0, y0, x1, y1) in zip(self.ids, self.boxes):
             e = enlarge_bbox([x0, y0, x1 - 1, y1 - 1], 0.2, w=W, h=H)       # note the reference's (w=shape[1], h=shape[0]) order
             self.bbox[oid] = torch.tensor([e[0], e[2], e[1], e[3]], dtype=torch.int64)
+        if with_bg:
+            self.bbox[0] = torch.tensor([0, W - 1, 0, H - 1], dtype=torch.int64)   # id 0 = background: the whole frame
         # a few distinct payloads are cycled: content does not change the work per frame
         ww, hh = np.meshgrid(np.arange(W, dtype=np.float32), np.arange(H, dtype=np.float32), indexing="ij")
         self._payload = []
