@@ -53,13 +53,20 @@ struct GemmOp {
     int accumulate;             // C += result
     int split, chunk;           // contraction chunks (chunk is a multiple of BK)
     float* part;
+    float* ones_out;            // non-null: one more virtual column j == J with B(J, c) = 1, written to ones_out[i]
+                                // (the bias gradient = column sums rides along with the weight gradient)
 };
+
+__device__ __forceinline__ int gemm_je(const GemmOp& g) { return g.J + (g.ones_out != nullptr ? 1 : 0); }
+__device__ __forceinline__ float* gemm_dst(const GemmOp& g, int i, int j) {
+    return j == g.J ? g.ones_out + i : g.C + i * g.sci + j * g.scj;
+}
 
 constexpr int BI = 128, BJ = 64, BK = 16, LDA_S = BI + 4, LDB_S = BJ + 4;
 
 __device__ __forceinline__ float gemm_epilogue(const GemmOp& g, int i, int j, float v) {
     v *= g.mult;
-    if (g.bias) v += g.bias[j];
+    if (g.bias && j < g.J) v += g.bias[j];
     v *= g.post;
     if (g.act == 1) v = fmaxf(v, 0.f);
     else if (g.act == 2) v = 1.f / (1.f + expf(-v));
@@ -90,7 +97,7 @@ __global__ void __launch_bounds__(256, 2) k_gemm(const GemmOp g) {
             const int e = tid + 256 * u;
             const int jj = b_c_fast ? e / BK : e % BJ, cc = b_c_fast ? e % BK : e / BJ;
             const int j = j0 + jj, c = c0 + cc;
-            Bs[cc][jj] = (j < g.J && c < c_end) ? g.B[j * g.sbj + c * g.sbc] : 0.f;
+            Bs[cc][jj] = c < c_end ? (j < g.J ? g.B[j * g.sbj + c * g.sbc] : (j == g.J && g.ones_out != nullptr ? 1.f : 0.f)) : 0.f;
         }
         __syncthreads();
 #pragma unroll
@@ -116,11 +123,11 @@ __global__ void __launch_bounds__(256, 2) k_gemm(const GemmOp g) {
 #pragma unroll
         for (int q = 0; q < 4; ++q) {
             const int j = j0 + 4 * tx + q;
-            if (j >= g.J) continue;
+            if (j >= gemm_je(g)) continue;
             if (g.split > 1) {
-                g.part[((size_t)blockIdx.z * g.I + i) * g.J + j] = acc[a][q];
+                g.part[((size_t)blockIdx.z * g.I + i) * gemm_je(g) + j] = acc[a][q];
             } else {
-                float* dst = g.C + i * g.sci + j * g.scj;
+                float* dst = gemm_dst(g, i, j);
                 const float v = gemm_epilogue(g, i, j, acc[a][q]);
                 *dst = g.accumulate ? *dst + v : v;
             }
@@ -129,12 +136,13 @@ __global__ void __launch_bounds__(256, 2) k_gemm(const GemmOp g) {
 }
 
 __global__ void k_gemm_reduce(const GemmOp g) {
-    const int e = blockIdx.x * blockDim.x + threadIdx.x;
-    if (e >= g.I * g.J) return;
-    const int i = e / g.J, j = e - i * g.J;
+    const int e = blockIdx.x * blockDim.x + threadIdx.x, je = gemm_je(g);
+    if (e >= g.I * je) return;
+    const int i = e / je, j = e - i * je;
     float s = 0.f;
-    for (int z = 0; z < g.split; ++z) s += g.part[(size_t)z * g.I * g.J + e];       // fixed order: deterministic
-    float* dst = g.C + i * g.sci + j * g.scj;
+#pragma unroll 8
+    for (int z = 0; z < g.split; ++z) s += g.part[(size_t)z * g.I * je + e];        // fixed order: deterministic
+    float* dst = gemm_dst(g, i, j);
     const float v = gemm_epilogue(g, i, j, s);
     *dst = g.accumulate ? *dst + v : v;
 }
@@ -147,11 +155,12 @@ int run_gemm(GemmOp g, int split, float* part, cudaStream_t st) {
         g.chunk = ((g.K + g.split - 1) / g.split + BK - 1) / BK * BK;
         g.split = (g.K + g.chunk - 1) / g.chunk;
     }
-    const dim3 grid((g.I + BI - 1) / BI, (g.J + BJ - 1) / BJ, g.split);
+    const int je = g.J + (g.ones_out != nullptr ? 1 : 0);
+    const dim3 grid((g.I + BI - 1) / BI, (je + BJ - 1) / BJ, g.split);
     k_gemm<<<grid, 256, 0, st>>>(g);
     OO_LAUNCH_CHECK();
     if (g.split > 1) {
-        k_gemm_reduce<<<(g.I * g.J + 255) / 256, 256, 0, st>>>(g);
+        k_gemm_reduce<<<(g.I * je + 255) / 256, 256, 0, st>>>(g);
         OO_LAUNCH_CHECK();
     }
     return 0;
@@ -205,7 +214,7 @@ __global__ void k_embed_fwd(const float* __restrict__ pcs, const float* __restri
 
 // d B[d][ch] = sum_p t[p][ch] * sum_k de[3+21k+d][p] * pi 2^k cos(pi 2^k proj): per-block partials [nblk][63], then a
 // fixed-order reduction
-constexpr int EB_PTS = 128;       // points per block
+constexpr int EB_PTS = 32;        // points per block
 __global__ void __launch_bounds__(NDIR * 4) k_embed_bwd(const float* __restrict__ pcs, const float* __restrict__ Bm, float scale,
                                                          int n_pts, const EmbedBufs g, float* __restrict__ partial) {
     // thread = (direction d, point lane q of 4); each walks EB_PTS / 4 points
@@ -299,7 +308,7 @@ BgWs bg_ws_map(float* base, int h, int n_pts, int n_rays) {
     w.gt_rgb = take(3LL * n_rays); w.gt_feat = take((long long)C * n_rays);
     w.loss_ws = take((long long)n_rays * oo_loss_ws_per_ray() + 8);
     w.ones = take(4);
-    const long long maxij = (long long)C * h > (long long)h * (h + E1) ? (long long)C * h : (long long)h * (h + E1);
+    const long long maxij = (long long)C * (h + 1) > (long long)h * (h + E1 + 1) ? (long long)C * (h + 1) : (long long)h * (h + E1 + 1);
     w.part = take((BG_SPLIT + 1) * maxij);
     w.emb_part = take(((M + EB_PTS - 1) / EB_PTS) * (NDIR * 3));
     w.grads = take(bg_layout(h).total);
@@ -418,35 +427,30 @@ extern "C" int oo_bg_train_step(float* theta, float* adam_m, float* adam_v, int 
     if (part) {
         // d out_clip.weight [C][h] = d_clip^T hp ; bias = column sums ; d hp = (d_clip W_ocl) * [hp > 0]
         g = op(w.d_clip, 1, C, w.hp, 1, h, G + L.off[T_OCL_W], h, 1, C, h, M);
-        OO_TRY(run_gemm(g, BG_SPLIT, w.part, st));
-        g = op(w.d_clip, 1, C, w.ones, 0, 0, G + L.off[T_OCL_B], 1, 1, C, 1, M);
+        g.ones_out = G + L.off[T_OCL_B];
         OO_TRY(run_gemm(g, BG_SPLIT, w.part, st));
         g = op(w.d_clip, C, 1, th + L.off[T_OCL_W], 1, h, w.d_hp, h, 1, M, h, C);
         g.mask = w.hp; g.smi = h; g.smj = 1; g.mask_cols = h;
         OO_TRY(run_gemm(g, 1, nullptr, st));
         g = op(w.d_hp, 1, h, w.xh, 1, w.ldh, G + L.off[T_CP_W], h + E2, 1, h, h + E2, M);
-        OO_TRY(run_gemm(g, BG_SPLIT, w.part, st));
-        g = op(w.d_hp, 1, h, w.ones, 0, 0, G + L.off[T_CP_B], 1, 1, h, 1, M);
+        g.ones_out = G + L.off[T_CP_B];
         OO_TRY(run_gemm(g, BG_SPLIT, w.part, st));
     }
     // ---- colour head: sigmoid backward, out_color, color_linear
     k_sigmoid_bwd<<<(3 * M + 255) / 256, 256, 0, st>>>(w.d_color, w.color, w.d_colpre, 3 * M);
     OO_LAUNCH_CHECK();
     g = op(w.d_colpre, 1, 3, w.hc, 1, h, G + L.off[T_OC_W], h, 1, 3, h, M);
-    OO_TRY(run_gemm(g, BG_SPLIT, w.part, st));
-    g = op(w.d_colpre, 1, 3, w.ones, 0, 0, G + L.off[T_OC_B], 1, 1, 3, 1, M);
+    g.ones_out = G + L.off[T_OC_B];
     OO_TRY(run_gemm(g, BG_SPLIT, w.part, st));
     g = op(w.d_colpre, 3, 1, th + L.off[T_OC_W], 1, h, w.d_hc, h, 1, M, h, 3);
     g.mask = w.hc; g.smi = h; g.smj = 1; g.mask_cols = h;
     OO_TRY(run_gemm(g, 1, nullptr, st));
     g = op(w.d_hc, 1, h, w.xh, 1, w.ldh, G + L.off[T_CL_W], h + E2, 1, h, h + E2, M);
-    OO_TRY(run_gemm(g, BG_SPLIT, w.part, st));
-    g = op(w.d_hc, 1, h, w.ones, 0, 0, G + L.off[T_CL_B], 1, 1, h, 1, M);
+    g.ones_out = G + L.off[T_CL_B];
     OO_TRY(run_gemm(g, BG_SPLIT, w.part, st));
     // ---- alpha head: alpha = 10 * (W_a fc4 + b_a)
     g = op(w.d_alpha, 1, 1, w.xh, 1, w.ldh, G + L.off[T_A_W], h, 1, 1, h, M); g.mult = 10.f;
-    OO_TRY(run_gemm(g, BG_SPLIT, w.part, st));
-    g = op(w.d_alpha, 1, 1, w.ones, 0, 0, G + L.off[T_A_B], 1, 1, 1, 1, M); g.mult = 10.f;
+    g.ones_out = G + L.off[T_A_B];
     OO_TRY(run_gemm(g, BG_SPLIT, w.part, st));
     // ---- d [fc4, e2] = d_hc W_cl + d_hp W_cp + 10 d_alpha W_a (cols < h).  The ReLU mask of fc4 is a 0/1 factor, so it is
     // applied to every term as it is added: (a + b + c) m == a m + b m + c m exactly, in the same order
@@ -463,32 +467,28 @@ extern "C" int oo_bg_train_step(float* theta, float* adam_m, float* adam_v, int 
     OO_TRY(run_gemm(g, 1, nullptr, st));
     // ---- mid2: d W = d_fc4^T fc3, d fc3 = (d_fc4 W_m2) * [fc3 > 0]
     g = op(w.d_xh, 1, w.ldh, w.h3, 1, h, G + L.off[T_M2_W], h, 1, h, h, M);
-    OO_TRY(run_gemm(g, BG_SPLIT, w.part, st));
-    g = op(w.d_xh, 1, w.ldh, w.ones, 0, 0, G + L.off[T_M2_B], 1, 1, h, 1, M);
+    g.ones_out = G + L.off[T_M2_B];
     OO_TRY(run_gemm(g, BG_SPLIT, w.part, st));
     g = op(w.d_xh, w.ldh, 1, th + L.off[T_M2_W], 1, h, w.d_h3, h, 1, M, h, h);
     g.mask = w.h3; g.smi = h; g.smj = 1; g.mask_cols = h;
     OO_TRY(run_gemm(g, 1, nullptr, st));
     // ---- cat_layer: d W = d_fc3^T [fc2, e1], d [fc2, e1] = d_fc3 W_cat with the ReLU mask on the fc2 columns
     g = op(w.d_h3, 1, h, w.xc, 1, w.ldc, G + L.off[T_CAT_W], h + E1, 1, h, h + E1, M);
-    OO_TRY(run_gemm(g, BG_SPLIT, w.part, st));
-    g = op(w.d_h3, 1, h, w.ones, 0, 0, G + L.off[T_CAT_B], 1, 1, h, 1, M);
+    g.ones_out = G + L.off[T_CAT_B];
     OO_TRY(run_gemm(g, BG_SPLIT, w.part, st));
     g = op(w.d_h3, h, 1, th + L.off[T_CAT_W], 1, h + E1, w.d_xc, w.ldc, 1, M, h + E1, h);
     g.mask = w.xc; g.smi = w.ldc; g.smj = 1; g.mask_cols = h;
     OO_TRY(run_gemm(g, 1, nullptr, st));
     // ---- mid1
     g = op(w.d_xc, 1, w.ldc, w.h1, 1, h, G + L.off[T_M1_W], h, 1, h, h, M);
-    OO_TRY(run_gemm(g, BG_SPLIT, w.part, st));
-    g = op(w.d_xc, 1, w.ldc, w.ones, 0, 0, G + L.off[T_M1_B], 1, 1, h, 1, M);
+    g.ones_out = G + L.off[T_M1_B];
     OO_TRY(run_gemm(g, BG_SPLIT, w.part, st));
     g = op(w.d_xc, w.ldc, 1, th + L.off[T_M1_W], 1, h, w.d_h1, h, 1, M, h, h);
     g.mask = w.h1; g.smi = h; g.smj = 1; g.mask_cols = h;
     OO_TRY(run_gemm(g, 1, nullptr, st));
     // ---- in_layer
     g = op(w.d_h1, 1, h, w.x1, 1, w.ld1, G + L.off[T_IN_W], E1, 1, h, E1, M);
-    OO_TRY(run_gemm(g, BG_SPLIT, w.part, st));
-    g = op(w.d_h1, 1, h, w.ones, 0, 0, G + L.off[T_IN_B], 1, 1, h, 1, M);
+    g.ones_out = G + L.off[T_IN_B];
     OO_TRY(run_gemm(g, BG_SPLIT, w.part, st));
     g = op(w.d_h1, h, 1, th + L.off[T_IN_W], 1, E1, w.d_x1, w.ld1, 1, M, E1, h);
     OO_TRY(run_gemm(g, 1, nullptr, st));
