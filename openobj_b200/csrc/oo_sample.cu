@@ -125,55 +125,157 @@ __device__ __forceinline__ int sample_ray_a(const oo_sample_args& a, const Rng& 
     return invalid ? 0 : (c.w == 1 ? 1 : 2);
 }
 
+// n consecutive values of one stream starting at element e0, one Philox block per four elements (same values as
+// Rng::uniform / Rng::normal element by element, which recompute the block for every element)
+template <int N>
+__device__ __forceinline__ void uniform_run(const Rng& g, uint32_t stream, uint64_t e0, int n, float* out) {
+    int i = 0;
+#pragma unroll
+    for (int blk = 0; blk < (N + 3) / 4 + 1; ++blk) {
+        const uint64_t q = (e0 >> 2) + blk;
+        const uint4 r = philox4x32_10(make_uint4((uint32_t)q, (uint32_t)(q >> 32), g.oid, 8u * g.frame + stream), g.key);
+        const uint32_t w[4] = {r.x, r.y, r.z, r.w};
+#pragma unroll
+        for (int k = 0; k < 4; ++k) {
+            const long long e = (long long)(4 * q + k) - (long long)e0;
+            if (e >= 0 && e < n) {
+#pragma unroll
+                for (int j = 0; j < N; ++j)
+                    if (j == (int)e) out[j] = (float)(w[k] >> 8) * TWO_M24;
+            }
+        }
+        (void)i;
+    }
+}
+
+template <int N>
+__device__ __forceinline__ void normal_run(const Rng& g, uint32_t stream, uint64_t e0, int n, float std, float* out) {
+#pragma unroll
+    for (int blk = 0; blk < (N + 3) / 4 + 1; ++blk) {
+        const uint64_t q = (e0 >> 2) + blk;
+        if ((long long)(4 * q) - (long long)e0 >= n) break;
+        const uint4 r = philox4x32_10(make_uint4((uint32_t)q, (uint32_t)(q >> 32), g.oid, 8u * g.frame + stream), g.key);
+#pragma unroll
+        for (int half = 0; half < 2; ++half) {                    // elements 4q + 2 half (cos) and 4q + 2 half + 1 (sin)
+            const long long e = (long long)(4 * q + 2 * half) - (long long)e0;
+            if (e + 1 < 0 || e >= n) continue;
+            const uint32_t a = half == 0 ? r.x : r.z, b = half == 0 ? r.y : r.w;
+            const float u0 = ((float)(a >> 8) + 1.f) * TWO_M24, u1 = (float)(b >> 8) * TWO_M24;
+            const float rad = sqrtf(-2.f * logf(u0)) * std;
+            float sn, cs;
+            sincospif(2.f * u1, &sn, &cs);
+#pragma unroll
+            for (int j = 0; j < N; ++j) {
+                if (j == (int)e && e >= 0) out[j] = rad * cs;
+                if (j == (int)e + 1 && e + 1 < n) out[j] = rad * sn;
+            }
+        }
+    }
+}
+
+// ascending sort of n <= N values held in registers: odd-even transposition network (N rounds of compare-exchange)
+template <int N>
+__device__ __forceinline__ void sort_regs(float* v, int n) {
+#pragma unroll
+    for (int round = 0; round < N; ++round)
+#pragma unroll
+        for (int i = round & 1; i + 1 < N; i += 2)
+            if (i + 1 < n) {
+                const float lo = fminf(v[i], v[i + 1]), hi = fmaxf(v[i], v[i + 1]);
+                v[i] = lo; v[i + 1] = hi;
+            }
+}
+
 // ---- pass B for one ray: depth placement along the ray and the sample points.  rk_* = rank of the ray inside its class
-// (tape rows in tape_by_rank mode); max_bound = max sampled depth of the object's batch (vmap.py:489, quirk 6)
-// zo [S] / po [S][3]: where the ray's depths and points go (global rows, or the CTA's staging tile in the parallel path)
+// (tape rows in tape_by_rank mode); max_bound = max sampled depth of the object's batch (vmap.py:489, quirk 6).
+// NC / NB = compile-time upper bounds of n_c2s / n_bins (the shipped configurations 1 + 9 and 5 + 9 get exact
+// instantiations, so every per-ray array lives in registers); zo [S] / po [S][3]: where the ray's depths and points go
+// (global rows, or the CTA's staging tile in the parallel path)
+template <int NC, int NB>
 __device__ __forceinline__ void sample_ray_b(const SampleK& k, const Rng& g, int obj, int ray, int n_rays, int rk_inv, int rk_val,
                                              int rk_obj, int rk_oth, float max_bound, float* zo, float* po) {
     const oo_sample_args& a = k.a;
     const bool rng = a.rng_mode != 0;
-    const int S = a.n_c2s + a.n_bins;
+    const int nc = a.n_c2s, nb = a.n_bins, S = nc + nb;
     const float eps = a.eps;
     const RayPix p = ray_pixel(a, g, obj, ray);
     const size_t o = (size_t)obj * n_rays + ray;
     const float d = a.gt_depth[o];
     const int state = a.labels[o];
     const bool invalid = d <= a.min_bound;
-    float zs[MAXB];
+    float zs[NC + NB];
     if (invalid) {
         // stratified_bins(min_bound, max(sampled_depth), S) -- vmap.py:493-498, utils.py:342-379
-        const size_t row = ((size_t)obj * n_rays + (a.tape_by_rank ? rk_inv : ray)) * S;
+        float u[NC + NB];
+        if (rng) {
+            uniform_run<NC + NB>(g, 3, (uint64_t)ray * S, S, u);
+        } else {
+            const size_t row = ((size_t)obj * n_rays + (a.tape_by_rank ? rk_inv : ray)) * S;
+#pragma unroll
+            for (int i = 0; i < NC + NB; ++i)
+                if (i < S) u[i] = a.r_invalid[row + i];
+        }
         const float range = __fsub_rn(max_bound, a.min_bound);
         const float blen = __fdiv_rn(range, (float)S);
-        for (int i = 0; i < S; ++i)
-            zs[i] = __fadd_rn(__fadd_rn(__fmul_rn(range, k.lin_s[i]), a.min_bound),
-                              __fmul_rn(rng ? g.uniform(3, (uint64_t)ray * S + i) : a.r_invalid[row + i], blen));
+#pragma unroll
+        for (int i = 0; i < NC + NB; ++i)
+            if (i < S) zs[i] = __fadd_rn(__fadd_rn(__fmul_rn(range, k.lin_s[i]), a.min_bound), __fmul_rn(u[i], blen));
     } else {
+        float uc[NC], ub[NB];
         {   // cam -> surface: stratified_bins(min_bound, d - eps, n_c2s) -- vmap.py:506-509
-            const size_t row = ((size_t)obj * n_rays + (a.tape_by_rank ? rk_val : ray)) * a.n_c2s;
+            if (rng) {
+                uniform_run<NC>(g, 4, (uint64_t)ray * nc, nc, uc);
+            } else {
+                const size_t row = ((size_t)obj * n_rays + (a.tape_by_rank ? rk_val : ray)) * nc;
+#pragma unroll
+                for (int i = 0; i < NC; ++i)
+                    if (i < nc) uc[i] = a.r_valid[row + i];
+            }
             const float range = __fsub_rn(__fsub_rn(d, eps), a.min_bound);
-            const float blen = __fdiv_rn(range, (float)a.n_c2s);
-            for (int i = 0; i < a.n_c2s; ++i)
-                zs[i] = __fadd_rn(__fadd_rn(__fmul_rn(range, k.lin_c[i]), a.min_bound),
-                                  __fmul_rn(rng ? g.uniform(4, (uint64_t)ray * a.n_c2s + i) : a.r_valid[row + i], blen));
+            const float blen = __fdiv_rn(range, (float)nc);
+#pragma unroll
+            for (int i = 0; i < NC; ++i)
+                if (i < nc) zs[i] = __fadd_rn(__fadd_rn(__fmul_rn(range, k.lin_c[i]), a.min_bound), __fmul_rn(uc[i], blen));
         }
         if (state == 1) {
             // normal_bins_sampling: N(0, eps/3) draws sorted ascending, clipped to +-eps, + d -- utils.py:382-397
-            const size_t row = ((size_t)obj * n_rays + (a.tape_by_rank ? rk_obj : ray)) * a.n_bins;
-            float b[MAXB];
-            for (int i = 0; i < a.n_bins; ++i)
-                b[i] = rng ? g.normal(5, (uint64_t)ray * a.n_bins + i, __fdiv_rn(eps, 3.f)) : a.r_normal[row + i];
-            sort_small(b, a.n_bins);
-            for (int i = 0; i < a.n_bins; ++i) zs[a.n_c2s + i] = __fadd_rn(d, fminf(fmaxf(b[i], -eps), eps));
+            if (rng) {
+                normal_run<NB>(g, 5, (uint64_t)ray * nb, nb, __fdiv_rn(eps, 3.f), ub);
+            } else {
+                const size_t row = ((size_t)obj * n_rays + (a.tape_by_rank ? rk_obj : ray)) * nb;
+#pragma unroll
+                for (int i = 0; i < NB; ++i)
+                    if (i < nb) ub[i] = a.r_normal[row + i];
+            }
+            sort_regs<NB>(ub, nb);
+#pragma unroll
+            for (int i = 0; i < NB; ++i)
+                if (i < nb) ub[i] = __fadd_rn(d, fminf(fmaxf(ub[i], -eps), eps));
         } else {
             // stratified_bins(d - eps, d + other_eps, n_bins) -- vmap.py:538-542
-            const size_t row = ((size_t)obj * n_rays + (a.tape_by_rank ? rk_oth : ray)) * a.n_bins;
+            if (rng) {
+                uniform_run<NB>(g, 6, (uint64_t)ray * nb, nb, ub);
+            } else {
+                const size_t row = ((size_t)obj * n_rays + (a.tape_by_rank ? rk_oth : ray)) * nb;
+#pragma unroll
+                for (int i = 0; i < NB; ++i)
+                    if (i < nb) ub[i] = a.r_other[row + i];
+            }
             const float lo = __fsub_rn(d, eps), hi = __fadd_rn(d, a.other_eps);
             const float range = __fsub_rn(hi, lo);
-            const float blen = __fdiv_rn(range, (float)a.n_bins);
-            for (int i = 0; i < a.n_bins; ++i)
-                zs[a.n_c2s + i] = __fadd_rn(__fadd_rn(__fmul_rn(range, k.lin_b[i]), lo),
-                                            __fmul_rn(rng ? g.uniform(6, (uint64_t)ray * a.n_bins + i) : a.r_other[row + i], blen));
+            const float blen = __fdiv_rn(range, (float)nb);
+#pragma unroll
+            for (int i = 0; i < NB; ++i)
+                if (i < nb) ub[i] = __fadd_rn(__fadd_rn(__fmul_rn(range, k.lin_b[i]), lo), __fmul_rn(ub[i], blen));
+        }
+        // zs = [cam->surface bins, surface bins]: the split point nc is a run-time value only in the generic instantiation
+#pragma unroll
+        for (int i = 0; i < NC + NB; ++i) {
+            if (i >= nc && i < S) {
+#pragma unroll
+                for (int j = 0; j < NB; ++j)
+                    if (j == i - nc) zs[i] = ub[j];
+            }
         }
     }
     // rays: dir_W = R dir_C, origin = T[:3,3] (utils.py:324-336); points = o + d*z (vmap.py:548-549)
@@ -184,11 +286,14 @@ __device__ __forceinline__ void sample_ray_b(const SampleK& k, const Rng& g, int
     const float wy = T[4] * dx + T[5] * dy + T[6] * dz;
     const float wz = T[8] * dx + T[9] * dy + T[10] * dz;
     const float ox = T[3], oy = T[7], oz = T[11];
-    for (int i = 0; i < S; ++i) {
-        zo[i] = zs[i];
-        po[3 * i + 0] = __fadd_rn(ox, __fmul_rn(wx, zs[i]));
-        po[3 * i + 1] = __fadd_rn(oy, __fmul_rn(wy, zs[i]));
-        po[3 * i + 2] = __fadd_rn(oz, __fmul_rn(wz, zs[i]));
+#pragma unroll
+    for (int i = 0; i < NC + NB; ++i) {
+        if (i < S) {
+            zo[i] = zs[i];
+            po[3 * i + 0] = __fadd_rn(ox, __fmul_rn(wx, zs[i]));
+            po[3 * i + 1] = __fadd_rn(oy, __fmul_rn(wy, zs[i]));
+            po[3 * i + 2] = __fadd_rn(oz, __fmul_rn(wz, zs[i]));
+        }
     }
 }
 
@@ -201,6 +306,7 @@ __device__ __forceinline__ Rng make_rng(const oo_sample_args& a, int obj) {
 }
 
 // ---- tape mode (and the general path): one 1024-thread CTA per object, ranks by block scan -------------------------
+template <int NC, int NB>
 __global__ void __launch_bounds__(NTH, 1) k_sample(const SampleK k) {
     const oo_sample_args& a = k.a;
     const int obj = blockIdx.x, tid = threadIdx.x, lane = tid & 31, wv = tid >> 5;
@@ -258,7 +364,7 @@ __global__ void __launch_bounds__(NTH, 1) k_sample(const SampleK k) {
     for (int ray = r_begin; ray < r_end; ++ray) {
         const size_t orow = (size_t)obj * n_rays + ray;
         const int S = a.n_c2s + a.n_bins;
-        sample_ray_b(k, g, obj, ray, n_rays, rk_inv, ray - rk_inv, rk_obj, rk_oth, max_bound, a.z + orow * S, a.pcs + orow * S * 3);
+        sample_ray_b<NC, NB>(k, g, obj, ray, n_rays, rk_inv, ray - rk_inv, rk_obj, rk_oth, max_bound, a.z + orow * S, a.pcs + orow * S * 3);
         const float d = a.gt_depth[(size_t)obj * n_rays + ray];
         const int state = a.labels[(size_t)obj * n_rays + ray];
         if (d <= a.min_bound) ++rk_inv;
@@ -287,6 +393,7 @@ __global__ void __launch_bounds__(256) k_sample_a(const SampleK k, int* __restri
 // One thread places the samples of one ray into the CTA's staging tile (z [256][S], points [256][S][3]); the tile is a
 // contiguous range of the outputs and leaves with 128-bit, fully coalesced stores (a thread writing its own 40 B / 120 B
 // rows directly costs one 32-byte sector per 4-byte store).
+template <int NC, int NB>
 __global__ void __launch_bounds__(256) k_sample_b(const SampleK k, const int* __restrict__ max_bits) {
     extern __shared__ __align__(16) float tile[];
     const oo_sample_args& a = k.a;
@@ -297,7 +404,8 @@ __global__ void __launch_bounds__(256) k_sample_b(const SampleK k, const int* __
     float* pt = tile + (size_t)blockDim.x * S;
     if (ray < n_rays) {
         const Rng g = make_rng(a, obj);
-        sample_ray_b(k, g, obj, ray, n_rays, 0, 0, 0, 0, __int_as_float(max_bits[obj]), zt + threadIdx.x * S, pt + threadIdx.x * S * 3);
+        sample_ray_b<NC, NB>(k, g, obj, ray, n_rays, 0, 0, 0, 0, __int_as_float(max_bits[obj]), zt + threadIdx.x * S,
+                             pt + threadIdx.x * S * 3);
     }
     __syncthreads();
     const size_t row0 = (size_t)obj * n_rays + ray0;
@@ -400,7 +508,7 @@ extern "C" int oo_sample_rays(const oo_sample_args* a, void* stream) {
     OO_REQUIRE(a, "oo_sample_rays: null args");
     OO_REQUIRE(a->n_obj > 0 && a->n_frames > 0 && a->n_samples > 0, "oo_sample_rays: empty request");
     const int S = a->n_c2s + a->n_bins;
-    OO_REQUIRE(a->n_c2s >= 1 && a->n_bins >= 1 && S + 1 <= MAXB, "oo_sample_rays: need 1 <= n_c2s, n_bins and S <= 32");
+    OO_REQUIRE(a->n_c2s >= 1 && a->n_bins >= 1 && a->n_c2s <= 16 && a->n_bins <= 16, "oo_sample_rays: need 1 <= n_c2s, n_bins <= 16");
     OO_REQUIRE(a->rgbs && a->depth && a->t_wc && a->bbox && a->rays_dir, "oo_sample_rays: null input");
     if (a->rng_mode) {
         OO_REQUIRE(a->obj_ids && a->n_keyframes && a->latest, "oo_sample_rays: rng_mode needs obj_ids / n_keyframes / latest");
@@ -434,16 +542,25 @@ extern "C" int oo_sample_rays(const oo_sample_args* a, void* stream) {
         k_sample_a<<<grid, 256, 0, (cudaStream_t)stream>>>(k, max_bits);
         OO_LAUNCH_CHECK();
         const size_t tile_bytes = (size_t)256 * S * 4 * sizeof(float);        // z [256][S] + points [256][S][3]; <= 128 KB (S <= 32)
-        static size_t tile_attr = 48 * 1024;
-        if (tile_bytes > tile_attr) {
-            OO_CUDA(cudaFuncSetAttribute(k_sample_b, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)tile_bytes));
-            tile_attr = tile_bytes;
-        }
-        k_sample_b<<<grid, 256, tile_bytes, (cudaStream_t)stream>>>(k, max_bits);
+        // one instantiation per launch (exact for the shipped 1 + 9 and 5 + 9 bins, upper bounds otherwise): per-ray arrays in
+        // registers and a code size the instruction cache holds
+#define OO_LAUNCH_B(NC_, NB_)                                                                                               \
+        do {                                                                                                                \
+            OO_CUDA(cudaFuncSetAttribute(k_sample_b<NC_, NB_>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)tile_bytes)); \
+            k_sample_b<NC_, NB_><<<grid, 256, tile_bytes, (cudaStream_t)stream>>>(k, max_bits);                              \
+        } while (0)
+        if (a->n_c2s == 1 && a->n_bins == 9) OO_LAUNCH_B(1, 9);
+        else if (a->n_c2s == 5 && a->n_bins == 9) OO_LAUNCH_B(5, 9);
+        else if (a->n_c2s <= 8 && a->n_bins <= 12) OO_LAUNCH_B(8, 12);
+        else OO_LAUNCH_B(16, 16);
+#undef OO_LAUNCH_B
         OO_LAUNCH_CHECK();
         return 0;
     }
-    k_sample<<<a->n_obj, NTH, 0, (cudaStream_t)stream>>>(k);
+    if (a->n_c2s == 1 && a->n_bins == 9) k_sample<1, 9><<<a->n_obj, NTH, 0, (cudaStream_t)stream>>>(k);
+    else if (a->n_c2s == 5 && a->n_bins == 9) k_sample<5, 9><<<a->n_obj, NTH, 0, (cudaStream_t)stream>>>(k);
+    else if (a->n_c2s <= 8 && a->n_bins <= 12) k_sample<8, 12><<<a->n_obj, NTH, 0, (cudaStream_t)stream>>>(k);
+    else k_sample<16, 16><<<a->n_obj, NTH, 0, (cudaStream_t)stream>>>(k);
     OO_LAUNCH_CHECK();
     return 0;
 }
