@@ -334,6 +334,45 @@ def run_ours(args):
         rays_frame = n_obj * ITERS * R
         sample_bytes = rays_frame * (180 + 4)
         append_bytes = n_obj * cfg.W * cfg.H * 8 + cfg.W * cfg.H * 11 + (synth.frame_bytes() - cfg.W * cfg.H * 11) * 2
+        # ---- K3: standalone loss.step_batch_loss forward + backward at the ensemble's per-step shape [N,120,10(,512)]
+        gk = torch.Generator(device=dev).manual_seed(4)
+        k3_alpha = torch.randn(n_obj, R, S, generator=gk, device=dev)
+        k3_color = torch.rand(n_obj, R, S, 3, generator=gk, device=dev)
+        k3_z = torch.sort(0.5 + 3.0 * torch.rand(n_obj, R, S, generator=gk, device=dev), dim=-1).values
+        k3_feat = torch.randn(n_obj, R, S, 512, generator=gk, device=dev) if cfg.part_mode else None
+        k3_gtf = torch.randn(n_obj, R, 512, generator=gk, device=dev) if cfg.part_mode else None
+        k3_rgb = torch.rand(n_obj, R, 3, generator=gk, device=dev)
+        k3_lab = torch.randint(0, 3, (n_obj, R), generator=gk, device=dev, dtype=torch.uint8)
+        k3_lab[:, 0], k3_lab[:, 1] = 1, 0
+        Lk = _lib.lib()
+        k3_ws = torch.empty(n_obj * R * Lk.oo_loss_ws_per_ray() + 8 * n_obj, device=dev)
+        k3_terms, k3_loss = torch.empty(n_obj, 4, device=dev), torch.empty(1, device=dev)
+        k3_flags = torch.zeros(1, dtype=torch.int32, device=dev)
+        k3_da, k3_dc = torch.empty_like(k3_alpha), torch.empty_like(k3_color)
+        k3_df = torch.empty_like(k3_feat) if cfg.part_mode else None
+        P_ = _lib.ptr
+
+        def k3_once():
+            _lib.check(Lk.oo_loss_fwd(P_(k3_alpha), P_(k3_color), P_(k3_z), P_(k3_z[..., 5].contiguous()), P_(k3_rgb), P_(k3_lab),
+                                      P_(k3_feat), P_(k3_gtf), n_obj, R, S, 512 if cfg.part_mode else 0, 5.0, 10.0, 5.0,
+                                      P_(k3_terms), P_(k3_loss), P_(k3_flags), P_(k3_ws), _lib.stream()), "oo_loss_fwd")
+            _lib.check(Lk.oo_loss_bwd(P_(k3_alpha), P_(k3_color), P_(k3_z), P_(k3_z[..., 5].contiguous()), P_(k3_rgb), P_(k3_lab),
+                                      P_(k3_feat), P_(k3_gtf), n_obj, R, S, 512 if cfg.part_mode else 0, 5.0, 10.0, 5.0, 1.0,
+                                      P_(k3_flags), P_(k3_ws), P_(k3_da), P_(k3_dc), P_(k3_df), _lib.stream()), "oo_loss_bwd")
+
+        for _ in range(3):
+            k3_once()
+        ek0, ek1 = cuda_timer()
+        ek0.record()
+        for _ in range(10):
+            k3_once()
+        ek1.record()
+        torch.cuda.synchronize()
+        k3_ms = ek0.elapsed_time(ek1) / 10
+        # algorithmic bytes per ray: forward reads alpha 40 + colour 120 + z 40 + gt 21 (+ pred 20 480 + gt feature
+        # 2 048); backward re-reads the 221 B of saved inputs (+ the gt feature) and writes d_alpha 40 + d_colour 120 (+ d_pred
+        # 20 480).  The backward does NOT re-read pred_feat (the forward leaves x, pred.x, pred.y in the workspace).
+        k3_bytes = n_obj * R * (221 * 2 + S * 16 + ((S * 512 * 4) * 2 + 512 * 4 * 2 if cfg.part_mode else 0))
         # ---- the separate background model (outside the N-object metric): hidden 128, 1200 rays x 14 samples
         from openobj_b200.background import BackgroundModel
         gb = torch.Generator(device=dev).manual_seed(3)
@@ -402,6 +441,11 @@ def run_ours(args):
                              "frac": k4_bytes / (k4_avg * 1e-3) / 1e9 / hbm_peak, "k4_ms_avg": k4_avg, "bytes_per_launch": k4_bytes,
                              "peak_source": "MEASURED_PEAKS.json hbm_gbs" if "hbm_gbs" in peaks else "fallback 6.65 TB/s"},
         }
+        out["roofline_composite"] = {"kernel": "K3 = oo_loss_fwd + oo_loss_bwd (standalone step_batch_loss at [N=%d,120,10%s]; pred_feat "
+                                               "%.0f MB + its gradient > L2)" % (n_obj, ",512" if cfg.part_mode else "",
+                                                                               n_obj * R * S * 2048 / 1e6),
+                                     "bound": "hbm", "achieved": k3_bytes / (k3_ms * 1e-3) / 1e9, "peak": hbm_peak, "unit": "GB/s",
+                                     "frac": k3_bytes / (k3_ms * 1e-3) / 1e9 / hbm_peak, "ms": k3_ms, "bytes_per_launch": k3_bytes}
         out["background"] = {"what": "separate background model (train.py:447-463): hidden %d, %d rays x %d samples per step, "
                                      "layer-by-layer FP32 GEMM path; NOT part of `value`" % (hb, Rb, Sb),
                              "ms_per_step": bg_ms, "rays_per_s": Rb / (bg_ms * 1e-3), "flop_per_step": bg_flop,

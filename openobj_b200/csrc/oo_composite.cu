@@ -7,8 +7,13 @@
 
 namespace {
 
-constexpr int WSR = 16;   // floats of workspace per ray
-// ray_ws[ray] = {depth, var, opac, col0, col1, col2, xy, xx, yy, l_depth, l_col, l_opac, l_feat, -, -, -}
+constexpr int CMAX = 512;                    // widest feature the workspace row holds (clip_point_feature_size)
+constexpr int WS_PX = 16, WS_PY = 48, WS_X = 80;
+constexpr int WSR = WS_X + CMAX;             // floats of workspace per ray
+// ray_ws[ray] = {depth, var, opac, col0, col1, col2, xy, xx, yy, l_depth, l_col, l_opac, l_feat, -, -, -,
+//                px[32] = pred_feat[i] . x, py[32] = pred_feat[i] . y, x[512] = rendered feature}
+// The forward leaves px, py and x so that the backward never re-reads pred_feat (10 x the size of everything else):
+//   dL/dpred[i][c] = T_i (A y[c] + B x[c]),   dL/dT_i (feature part) = pred[i] . (A y + B x) = A py[i] + B px[i]
 // tail (after n_obj*n_rays*WSR): per object {sum_d, sum_c, sum_o, sum_f, n1, nsem, -, -}
 
 __device__ __forceinline__ float warp_sum(float v) {
@@ -47,10 +52,11 @@ struct RayIn {
     int n_rays_total, S, C;
 };
 
-__global__ void __launch_bounds__(256) k_loss_ray_fwd(RayIn in, float* __restrict__ ws) {
+template <int SMAX>
+__global__ void __launch_bounds__(256, SMAX <= 16 ? 2 : 1) k_loss_ray_fwd(RayIn in, float* __restrict__ ws) {
     const int lane = threadIdx.x & 31;
-    const int ray = blockIdx.x * (blockDim.x >> 5) + (threadIdx.x >> 5);
-    if (ray >= in.n_rays_total) return;
+    // persistent warps: the grid is sized to one resident wave and every warp strides over the rays (no partial last wave)
+    for (int ray = blockIdx.x * (blockDim.x >> 5) + (threadIdx.x >> 5); ray < in.n_rays_total; ray += gridDim.x * (blockDim.x >> 5)) {
     const int S = in.S;
     const bool act = lane < S;
     const size_t pi = (size_t)ray * S + lane;
@@ -72,17 +78,43 @@ __global__ void __launch_bounds__(256) k_loss_ray_fwd(RayIn in, float* __restric
     if (in.pred_feat != nullptr) {                                 // loss.py:82-87
         const float* pf = in.pred_feat + (size_t)ray * S * in.C;
         const float* gy = in.gt_feat + (size_t)ray * in.C;
+        float px[SMAX], py[SMAX];
+#pragma unroll
+        for (int i = 0; i < SMAX; ++i) px[i] = py[i] = 0.f;
         for (int c4 = lane * 4; c4 < in.C; c4 += 128) {
+            // all S rows of this column chunk are requested before the first is used (memory-level parallelism: one warp
+            // keeps S x 512 B in flight); accumulation stays in sample order
+            float4 p[SMAX];
+#pragma unroll
+            for (int i = 0; i < SMAX; ++i)
+                if (i < S) p[i] = *reinterpret_cast<const float4*>(pf + (size_t)i * in.C + c4);
             float4 x = {0.f, 0.f, 0.f, 0.f};
-            for (int i = 0; i < S; ++i) {
-                const float Ti = __shfl_sync(0xffffffffu, T, i);
-                const float4 p = *reinterpret_cast<const float4*>(pf + (size_t)i * in.C + c4);
-                x.x += Ti * p.x; x.y += Ti * p.y; x.z += Ti * p.z; x.w += Ti * p.w;
+#pragma unroll
+            for (int i = 0; i < SMAX; ++i) {
+                if (i < S) {
+                    const float Ti = __shfl_sync(0xffffffffu, T, i);
+                    x.x += Ti * p[i].x; x.y += Ti * p[i].y; x.z += Ti * p[i].z; x.w += Ti * p[i].w;
+                }
             }
             const float4 y = *reinterpret_cast<const float4*>(gy + c4);
             xy += x.x * y.x + x.y * y.y + x.z * y.z + x.w * y.w;
             xx += x.x * x.x + x.y * x.y + x.z * x.z + x.w * x.w;
             yy += y.x * y.x + y.y * y.y + y.z * y.z + y.w * y.w;
+#pragma unroll
+            for (int i = 0; i < SMAX; ++i) {
+                if (i < S) {
+                    px[i] += p[i].x * x.x + p[i].y * x.y + p[i].z * x.z + p[i].w * x.w;
+                    py[i] += p[i].x * y.x + p[i].y * y.y + p[i].z * y.z + p[i].w * y.w;
+                }
+            }
+            *reinterpret_cast<float4*>(ws + (size_t)ray * WSR + WS_X + c4) = x;
+        }
+#pragma unroll
+        for (int i = 0; i < SMAX; ++i) {
+            if (i < S) {
+                const float a_ = warp_sum(px[i]), b_ = warp_sum(py[i]);
+                if (lane == i) { ws[(size_t)ray * WSR + WS_PX + i] = a_; ws[(size_t)ray * WSR + WS_PY + i] = b_; }
+            }
         }
         xy = warp_sum(xy); xx = warp_sum(xx); yy = warp_sum(yy);
     }
@@ -104,6 +136,7 @@ __global__ void __launch_bounds__(256) k_loss_ray_fwd(RayIn in, float* __restric
         float* w = ws + (size_t)ray * WSR;
         w[0] = depth; w[1] = var; w[2] = opac; w[3] = r0; w[4] = r1; w[5] = r2; w[6] = xy; w[7] = xx; w[8] = yy;
         w[9] = ld; w[10] = lc; w[11] = lo; w[12] = lf;
+    }
     }
 }
 
@@ -169,13 +202,12 @@ __global__ void k_loss_finalize(const float* __restrict__ tail, int n_obj, int h
 }
 
 template <int SMAX>
-__global__ void __launch_bounds__(256) k_loss_ray_bwd(RayIn in, const float* __restrict__ ws, const float* __restrict__ tail,
+__global__ void __launch_bounds__(256, 4) k_loss_ray_bwd(RayIn in, const float* __restrict__ ws, const float* __restrict__ tail,
                                                       const int* __restrict__ flags, int n_rays, float cs, float os,
                                                       float fs, float gl, float* __restrict__ d_alpha,
                                                       float* __restrict__ d_color, float* __restrict__ d_pred) {
     const int lane = threadIdx.x & 31;
-    const int ray = blockIdx.x * (blockDim.x >> 5) + (threadIdx.x >> 5);
-    if (ray >= in.n_rays_total) return;
+    for (int ray = blockIdx.x * (blockDim.x >> 5) + (threadIdx.x >> 5); ray < in.n_rays_total; ray += gridDim.x * (blockDim.x >> 5)) {
     const int S = in.S, obj = ray / n_rays;
     const int fl = flags[0];
     const bool act = lane < S;
@@ -209,44 +241,25 @@ __global__ void __launch_bounds__(256) k_loss_ray_bwd(RayIn in, const float* __r
     if (act) {
         c0 = in.color[pi * 3 + 0]; c1 = in.color[pi * 3 + 1]; c2 = in.color[pi * 3 + 2];
     }
-    float hu = 0.f;                                                // lane i: sum_c pred_feat[i][c] * g[c]
+    float hu = 0.f;                                                // lane i: pred_feat[i] . dL/dx = A py[i] + B px[i]
     if (in.pred_feat != nullptr) {
-        const float* pf = in.pred_feat + (size_t)ray * S * in.C;
         const float* gy = in.gt_feat + (size_t)ray * in.C;
+        const float* xr = w + WS_X;
         float* dp = d_pred + (size_t)ray * S * in.C;
-        float hup[SMAX];
-#pragma unroll
-        for (int i = 0; i < SMAX; ++i) hup[i] = 0.f;
+        if (act) hu = A * w[WS_PY + lane] + B * w[WS_PX + lane];
         for (int c4 = lane * 4; c4 < in.C; c4 += 128) {
-            float4 p[SMAX];
-            float4 x = {0.f, 0.f, 0.f, 0.f};
-#pragma unroll
-            for (int i = 0; i < SMAX; ++i) {
-                if (i < S) {
-                    const float Ti = __shfl_sync(0xffffffffu, T, i);
-                    p[i] = *reinterpret_cast<const float4*>(pf + (size_t)i * in.C + c4);
-                    x.x += Ti * p[i].x; x.y += Ti * p[i].y; x.z += Ti * p[i].z; x.w += Ti * p[i].w;
-                }
-            }
             const float4 y = *reinterpret_cast<const float4*>(gy + c4);
+            const float4 x = *reinterpret_cast<const float4*>(xr + c4);
             float4 g;
             g.x = A * y.x + B * x.x; g.y = A * y.y + B * x.y; g.z = A * y.z + B * x.z; g.w = A * y.w + B * x.w;
 #pragma unroll
             for (int i = 0; i < SMAX; ++i) {
                 if (i < S) {
                     const float Ti = __shfl_sync(0xffffffffu, T, i);
-                    hup[i] += p[i].x * g.x + p[i].y * g.y + p[i].z * g.z + p[i].w * g.w;
                     float4 d;
                     d.x = Ti * g.x; d.y = Ti * g.y; d.z = Ti * g.z; d.w = Ti * g.w;
                     *reinterpret_cast<float4*>(dp + (size_t)i * in.C + c4) = d;
                 }
-            }
-        }
-#pragma unroll
-        for (int i = 0; i < SMAX; ++i) {
-            if (i < S) {
-                const float t = warp_sum(hup[i]);
-                if (lane == i) hu = t;
             }
         }
     }
@@ -259,6 +272,18 @@ __global__ void __launch_bounds__(256) k_loss_ray_bwd(RayIn in, const float* __r
         d_color[pi * 3 + 1] = T * gc1;
         d_color[pi * 3 + 2] = T * gc2;
     }
+    }
+}
+
+// grid of one resident wave (occupancy x SM count), capped by the work
+template <typename K>
+int wave_blocks(K kernel, int needed) {
+    int dev = 0, n_sm = 148, occ = 1;
+    cudaGetDevice(&dev);
+    cudaDeviceGetAttribute(&n_sm, cudaDevAttrMultiProcessorCount, dev);
+    cudaOccupancyMaxActiveBlocksPerMultiprocessor(&occ, kernel, 256, 0);
+    const int wave = n_sm * (occ < 1 ? 1 : occ);
+    return needed < wave ? needed : wave;
 }
 
 int check_loss_args(const void* a, const void* c, const void* z, const void* gd, const void* gc, const void* lab,
@@ -266,7 +291,7 @@ int check_loss_args(const void* a, const void* c, const void* z, const void* gd,
     OO_REQUIRE(a && c && z && gd && gc && lab, "oo_loss: null input");
     OO_REQUIRE((pf == nullptr) == (gf == nullptr), "oo_loss: pred_feat and gt_feat must both be given or both be NULL");
     OO_REQUIRE(n_obj > 0 && n_rays > 0 && S > 0 && S <= 32, "oo_loss: need 0 < n_samp <= 32");
-    OO_REQUIRE(pf == nullptr || (C > 0 && C % 4 == 0), "oo_loss: feature width must be a multiple of 4");
+    OO_REQUIRE(pf == nullptr || (C > 0 && C % 4 == 0 && C <= CMAX), "oo_loss: feature width must be a multiple of 4, at most 512");
     return 0;
 }
 
@@ -285,7 +310,10 @@ extern "C" int oo_loss_fwd(const float* alpha, const float* color, const float* 
     cudaStream_t st = (cudaStream_t)stream;
     RayIn in{alpha, color, z, gt_depth, gt_color, pred_feat, gt_feat, labels, n_obj * n_rays, n_samp, n_feat};
     float* tail = ray_ws + (size_t)n_obj * n_rays * WSR;
-    k_loss_ray_fwd<<<(in.n_rays_total + 7) / 8, 256, 0, st>>>(in, ray_ws);
+    const int fblocks = (in.n_rays_total + 7) / 8;
+    if (n_samp <= 10) k_loss_ray_fwd<10><<<wave_blocks(k_loss_ray_fwd<10>, fblocks), 256, 0, st>>>(in, ray_ws);
+    else if (n_samp <= 16) k_loss_ray_fwd<16><<<wave_blocks(k_loss_ray_fwd<16>, fblocks), 256, 0, st>>>(in, ray_ws);
+    else k_loss_ray_fwd<32><<<wave_blocks(k_loss_ray_fwd<32>, fblocks), 256, 0, st>>>(in, ray_ws);
     OO_LAUNCH_CHECK();
     k_loss_obj_reduce<<<n_obj, 256, 0, st>>>(ray_ws, labels, n_rays, tail);
     OO_LAUNCH_CHECK();
@@ -309,13 +337,13 @@ extern "C" int oo_loss_bwd(const float* alpha, const float* color, const float* 
     const float* tail = ray_ws + (size_t)n_obj * n_rays * WSR;
     const int blocks = (in.n_rays_total + 7) / 8;
     if (n_samp <= 10)
-        k_loss_ray_bwd<10><<<blocks, 256, 0, st>>>(in, ray_ws, tail, flags, n_rays, cs, os, fs, grad_loss, d_alpha, d_color,
+        k_loss_ray_bwd<10><<<wave_blocks(k_loss_ray_bwd<10>, blocks), 256, 0, st>>>(in, ray_ws, tail, flags, n_rays, cs, os, fs, grad_loss, d_alpha, d_color,
                                                    d_pred_feat);
     else if (n_samp <= 16)
-        k_loss_ray_bwd<16><<<blocks, 256, 0, st>>>(in, ray_ws, tail, flags, n_rays, cs, os, fs, grad_loss, d_alpha, d_color,
+        k_loss_ray_bwd<16><<<wave_blocks(k_loss_ray_bwd<16>, blocks), 256, 0, st>>>(in, ray_ws, tail, flags, n_rays, cs, os, fs, grad_loss, d_alpha, d_color,
                                                    d_pred_feat);
     else
-        k_loss_ray_bwd<32><<<blocks, 256, 0, st>>>(in, ray_ws, tail, flags, n_rays, cs, os, fs, grad_loss, d_alpha, d_color,
+        k_loss_ray_bwd<32><<<wave_blocks(k_loss_ray_bwd<32>, blocks), 256, 0, st>>>(in, ray_ws, tail, flags, n_rays, cs, os, fs, grad_loss, d_alpha, d_color,
                                                    d_pred_feat);
     OO_LAUNCH_CHECK();
     return 0;
