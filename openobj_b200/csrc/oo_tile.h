@@ -54,34 +54,93 @@ OO_DEV float warp_sum(float v) {
 }
 #endif
 
-// register-resident weight-gradient accumulators of one thread (live across all tiles of an object).  The five weight
-// matrices are accumulated as m16n8k8 C fragments: output tile u = warp + NWARPS i of a GEMM with MT row tiles (16 output
-// rows j each) is (m = u % MT, n = u / MT); register r of fragment i holds row j = 16 m + lane/4 + 8 (r >> 1) and
-// input column k = 8 n + 2 (lane % 4) + (r & 1)   (see wfrag_row / wfrag_col).
+// Weight-gradient accumulators of one thread, live across all tiles of an object.  The five weight matrices are
+// accumulated as m16n8k8 C fragments: output tile u = warp + NWARPS i of a GEMM with MT row tiles (16 output rows j each)
+// is (m = u % MT, n = u / MT); register r of fragment i holds row j = 16 m + lane/4 + 8 (r >> 1) and input column
+// k = 8 n + 2 (lane % 4) + (r & 1)   (see wfrag_row / wfrag_col).
+//
+// On the device they do NOT live in registers between phases: each warp owns 64 columns x 32 lanes of TENSOR MEMORY
+// (tcgen05.alloc, 256 columns per CTA: lane quarter = warp % 4, column block = warp / 4) and a phase that updates an
+// accumulator loads it with tcgen05.ld at its start and stores it back with tcgen05.st at its end (OO_ACC / OO_ACC_PUT).
+// That frees 52 registers per thread for the GEMM loops (128 registers x 512 threads is the whole register file).
+// The host build (CPU tile emulator, tests only) keeps plain arrays.
+constexpr int AC_IN = 0, AC_CAT = 8, AC_HD = 16, AC_M1 = 32, AC_M2 = 36, AC_GM = 40, AC_OC = 44, AC_B = 45, AC_PE = 46,
+              AC_MV = 47, AC_LOSS = 48, AC_COLS = 64;
 struct TileAcc {
-    float in[8];     // in_layer   : 2 x 11 tiles -> 2 fragments
-    float cat[8];    // cat_layer  : 2 x 15 tiles -> 2 fragments
-    float m1[4];     // mid1       : 2 x 4 tiles, two warps per tile (k-split, see gemm_bwd_w32)
-    float m2[4];     // mid2
-    float hd[12];    // [color_linear ; clip_linear] : 4 x 10 tiles -> 3 fragments (part features off: 2 x 10 -> 2)
-    float s0;        // out_color.weight (tid<96), out_alpha.weight (96<=tid<128)
-    float s1;        // biases of the six hidden layers (tid<192), out_color.bias (192..194), out_alpha.bias (195)
-    float s2;        // B_layer.weight (tid<63)
-    float gm[4];     // M = sum_r B_r S_r S_r^T, row tid/8, cols 4(tid%8)..+3   (out_clip gradient, see phase 13)
-    float s3;        // m = sum_r B_r opac_r S_r (tid<32), beta = sum_r B_r opac_r^2 (tid 32)
-    float loss[4];   // per-ray loss partials (thread 32 r, r < 10): depth, colour, opacity, feature
+#ifdef __CUDACC__
+    uint32_t tm;       // tensor-memory address of this warp's column block (lane field = 32 * (warp % 4))
+#else
+    float w_in[8];     // in_layer   : 2 x 11 tiles -> 2 fragments
+    float w_cat[8];    // cat_layer  : 2 x 15 tiles -> 2 fragments
+    float w_m1[4];     // mid1       : 2 x 4 tiles, two warps per tile (k-split, see gemm_bwd_w32)
+    float w_m2[4];     // mid2
+    float w_hd[12];    // [color_linear ; clip_linear] : 4 x 10 tiles -> 3 fragments (part features off: 2 x 10 -> 2)
+    float g_oc[1];     // out_color.weight (tid<96), out_alpha.weight (96<=tid<128)
+    float g_b[1];      // biases of the six hidden layers (tid<192), out_color.bias (192..194), out_alpha.bias (195)
+    float g_pe[1];     // B_layer.weight (tid<63)
+    float g_gm[4];     // M = sum_r B_r S_r S_r^T, row tid/8, cols 4(tid%8)..+3   (out_clip gradient, see phase 13)
+    float g_mv[1];     // m = sum_r B_r opac_r S_r (tid<32), beta = sum_r B_r opac_r^2 (tid 32)
+    float loss[4];     // per-ray loss partials (thread 32 r, r < 10): depth, colour, opacity, feature
+#endif
 };
 
+#ifdef __CUDACC__
+template <int N>
+OO_DEV void tm_ld(uint32_t addr, float* v) {
+    static_assert(N == 1 || N == 4 || N == 8 || N == 12, "tm_ld sizes");
+    uint32_t r[12];
+    if constexpr (N == 1) {
+        asm volatile("tcgen05.ld.sync.aligned.32x32b.x1.b32 {%0}, [%1];" : "=r"(r[0]) : "r"(addr));
+    } else if constexpr (N == 4) {
+        asm volatile("tcgen05.ld.sync.aligned.32x32b.x4.b32 {%0,%1,%2,%3}, [%4];"
+                     : "=r"(r[0]), "=r"(r[1]), "=r"(r[2]), "=r"(r[3]) : "r"(addr));
+    } else {
+        asm volatile("tcgen05.ld.sync.aligned.32x32b.x8.b32 {%0,%1,%2,%3,%4,%5,%6,%7}, [%8];"
+                     : "=r"(r[0]), "=r"(r[1]), "=r"(r[2]), "=r"(r[3]), "=r"(r[4]), "=r"(r[5]), "=r"(r[6]), "=r"(r[7]) : "r"(addr));
+        if constexpr (N == 12)
+            asm volatile("tcgen05.ld.sync.aligned.32x32b.x4.b32 {%0,%1,%2,%3}, [%4];"
+                         : "=r"(r[8]), "=r"(r[9]), "=r"(r[10]), "=r"(r[11]) : "r"(addr + 8));
+    }
+    asm volatile("tcgen05.wait::ld.sync.aligned;" ::: "memory");
+#pragma unroll
+    for (int i = 0; i < N; ++i) v[i] = __uint_as_float(r[i]);
+}
+template <int N>
+OO_DEV void tm_st(uint32_t addr, const float* v) {
+    static_assert(N == 1 || N == 4 || N == 8 || N == 12, "tm_st sizes");
+    uint32_t r[12];
+#pragma unroll
+    for (int i = 0; i < N; ++i) r[i] = __float_as_uint(v[i]);
+    if constexpr (N == 1) {
+        asm volatile("tcgen05.st.sync.aligned.32x32b.x1.b32 [%0], {%1};" ::"r"(addr), "r"(r[0]) : "memory");
+    } else if constexpr (N == 4) {
+        asm volatile("tcgen05.st.sync.aligned.32x32b.x4.b32 [%0], {%1,%2,%3,%4};" ::"r"(addr), "r"(r[0]), "r"(r[1]), "r"(r[2]),
+                     "r"(r[3]) : "memory");
+    } else {
+        asm volatile("tcgen05.st.sync.aligned.32x32b.x8.b32 [%0], {%1,%2,%3,%4,%5,%6,%7,%8};" ::"r"(addr), "r"(r[0]), "r"(r[1]),
+                     "r"(r[2]), "r"(r[3]), "r"(r[4]), "r"(r[5]), "r"(r[6]), "r"(r[7]) : "memory");
+        if constexpr (N == 12)
+            asm volatile("tcgen05.st.sync.aligned.32x32b.x4.b32 [%0], {%1,%2,%3,%4};" ::"r"(addr + 8), "r"(r[8]), "r"(r[9]),
+                         "r"(r[10]), "r"(r[11]) : "memory");
+    }
+    asm volatile("tcgen05.wait::st.sync.aligned;" ::: "memory");
+}
+// a phase's view of one accumulator: `name` is a local array on the device (loaded from tensor memory), the member itself on the host
+#define OO_ACC(name, N, COL) float name[N]; tm_ld<N>(a.tm + (COL), name)
+#define OO_ACC_PUT(name, N, COL) tm_st<N>(a.tm + (COL), name)
+#else
+#define OO_ACC(name, N, COL) float* name = a.name
+#define OO_ACC_PUT(name, N, COL) ((void)0)
+#endif
+
 OO_DEV void acc_zero(TileAcc& a) {
+#ifdef __CUDACC__
+    float z[8] = {0.f, 0.f, 0.f, 0.f, 0.f, 0.f, 0.f, 0.f};
 #pragma unroll
-    for (int i = 0; i < 8; ++i) a.in[i] = a.cat[i] = 0.f;
-#pragma unroll
-    for (int i = 0; i < 4; ++i) a.m1[i] = a.m2[i] = 0.f;
-#pragma unroll
-    for (int i = 0; i < 12; ++i) a.hd[i] = 0.f;
-    a.s0 = a.s1 = a.s2 = a.s3 = 0.f;
-    a.gm[0] = a.gm[1] = a.gm[2] = a.gm[3] = 0.f;
-    a.loss[0] = a.loss[1] = a.loss[2] = a.loss[3] = 0.f;
+    for (int c = 0; c < AC_COLS; c += 8) tm_st<8>(a.tm + c, z);
+#else
+    a = TileAcc{};
+#endif
 }
 
 // everything a tile needs that is uniform across the block
@@ -698,6 +757,7 @@ OO_DEV void tile_phase(int tid, float* __restrict__ sm, const TileCtx& c, TileAc
         // warp r renders ray r: lanes = samples, sums by shuffle; lane 0 (thread 32 r) owns the ray's loss partials
         const int r = tid >> 5, li = tid & 31;
         if (r < RT) {
+            OO_ACC(loss, 4, AC_LOSS);
             float gd = 0.f, go = 0.f, gc0 = 0.f, gc1 = 0.f, gc2 = 0.f, cf = 0.f;
             float depth = 0.f, opac = 0.f, c0 = 0.f, c1 = 0.f, c2 = 0.f, var = 0.f;
 #ifdef __CUDACC__
@@ -739,12 +799,12 @@ OO_DEV void tile_phase(int tid, float* __restrict__ sm, const TileCtx& c, TileAc
                     if (is1 && !(c.flags & 2)) {
                         const float wgt = 1.f / (sqrtf(var) + 1e-4f);           // render_rays.py:95-100, var detached
                         const float dd = depth - rv[V_GTD * RP + r];
-                        a.loss[0] += fabsf(dd) * wgt;
+                        loss[0] += fabsf(dd) * wgt;
                         gd = sgnf_(dd) * wgt * c.inv1;
                         const float e0 = c0 - rv[(V_RGB + 0) * RP + r] / 255.f;   // train.py:373 `/ 255.`
                         const float e1 = c1 - rv[(V_RGB + 1) * RP + r] / 255.f;
                         const float e2 = c2 - rv[(V_RGB + 2) * RP + r] / 255.f;
-                        a.loss[1] += fabsf(e0) + fabsf(e1) + fabsf(e2);              // loss.py:61 sum over channels
+                        loss[1] += fabsf(e0) + fabsf(e1) + fabsf(e2);                // loss.py:61 sum over channels
                         gc0 = sgnf_(e0) * c.cs * c.inv1;
                         gc1 = sgnf_(e1) * c.cs * c.inv1;
                         gc2 = sgnf_(e2) * c.cs * c.inv1;
@@ -752,7 +812,7 @@ OO_DEV void tile_phase(int tid, float* __restrict__ sm, const TileCtx& c, TileAc
                     }
                     if (sem && !(c.flags & 4)) {
                         const float eo = opac - tgt;                                 // loss.py:71
-                        a.loss[2] += fabsf(eo);
+                        loss[2] += fabsf(eo);
                         go = sgnf_(eo) * c.os * c.invs;
                     }
                 }
@@ -764,6 +824,7 @@ OO_DEV void tile_phase(int tid, float* __restrict__ sm, const TileCtx& c, TileAc
                 rv[V_CF * RP + r] = cf;
                 rv[V_BG * RP + r] = 0.f;
             }
+            OO_ACC_PUT(loss, 4, AC_LOSS);
         }
         if (PART) OO_CP_ASYNC_WAIT();      // Y rows issued in phase 0 are complete for this thread; the barrier publishes them
     } else if constexpr (PH == 10) {
@@ -903,6 +964,7 @@ OO_DEV void tile_phase(int tid, float* __restrict__ sm, const TileCtx& c, TileAc
             // warp r: lanes = hidden units, three dot products by shuffle; lane 0 (thread 32 r) owns the ray's loss partial
             const int r = tid >> 5, lj = tid & 31;
             float sv = 0.f, swb = 0.f, sgs = 0.f;
+            float lossf = 0.f;
 #ifdef __CUDACC__
             if (r < RT) {
                 const float sj = sm[SM_ST + lj * RP + r];
@@ -931,7 +993,7 @@ OO_DEV void tile_phase(int tid, float* __restrict__ sm, const TileCtx& c, TileAc
                 const float cosv = xy / (nx * ny);
                 float A = 0.f, B = 0.f;
                 if (cf != 0.f) {
-                    a.loss[3] += 1.f - cosv;
+                    lossf = 1.f - cosv;
                     // d(1-cos)/dx = -y/(nx ny) + [|x|>eps] cos * x / nx^2
                     A = -cf / (nx * ny);
                     B = nxr > 1e-8f ? cf * cosv / (nx * nx) : 0.f;
@@ -939,6 +1001,11 @@ OO_DEV void tile_phase(int tid, float* __restrict__ sm, const TileCtx& c, TileAc
                 rv[V_A * RP + r] = A;
                 rv[V_B * RP + r] = B;
                 rv[V_BG * RP + r] = A * yb + B * xb;       // b_ocl . dL/dx
+            }
+            if (r < RT) {                              // warp-uniform: the accumulator access is a warp-wide operation
+                OO_ACC(loss, 4, AC_LOSS);
+                loss[3] += lossf;
+                OO_ACC_PUT(loss, 4, AC_LOSS);
             }
         }
     } else if constexpr (PH == 13) {
@@ -955,22 +1022,28 @@ OO_DEV void tile_phase(int tid, float* __restrict__ sm, const TileCtx& c, TileAc
                 else c.rayrec[r * RAYREC + REC_S + q - 2] = sm[SM_ST + (q - 2) * RP + r];
             }
             if (tid < 8 * H) {
+                OO_ACC(g_gm, 4, AC_GM);
                 const int k = tid >> 3, j4 = 4 * (tid & 7);
 #pragma unroll
                 for (int r = 0; r < RT; ++r) {
                     const float bs = rv[V_B * RP + r] * sm[SM_ST + k * RP + r];
-                    a.gm[0] += bs * sm[SM_ST + (j4 + 0) * RP + r];
-                    a.gm[1] += bs * sm[SM_ST + (j4 + 1) * RP + r];
-                    a.gm[2] += bs * sm[SM_ST + (j4 + 2) * RP + r];
-                    a.gm[3] += bs * sm[SM_ST + (j4 + 3) * RP + r];
+                    g_gm[0] += bs * sm[SM_ST + (j4 + 0) * RP + r];
+                    g_gm[1] += bs * sm[SM_ST + (j4 + 1) * RP + r];
+                    g_gm[2] += bs * sm[SM_ST + (j4 + 2) * RP + r];
+                    g_gm[3] += bs * sm[SM_ST + (j4 + 3) * RP + r];
                 }
+                OO_ACC_PUT(g_gm, 4, AC_GM);
             }
-            if (tid <= H) {
+            if (tid < 2 * 32) {                        // warps 0 and 1 (thread 32 holds beta): warp-uniform accumulator access
+                OO_ACC(g_mv, 1, AC_MV);
+                if (tid <= H) {
 #pragma unroll
-                for (int r = 0; r < RT; ++r) {
-                    const float bo = rv[V_B * RP + r] * rv[V_OPAC * RP + r];
-                    a.s3 += bo * (tid < H ? sm[SM_ST + tid * RP + r] : rv[V_OPAC * RP + r]);
+                    for (int r = 0; r < RT; ++r) {
+                        const float bo = rv[V_B * RP + r] * rv[V_OPAC * RP + r];
+                        g_mv[0] += bo * (tid < H ? sm[SM_ST + tid * RP + r] : rv[V_OPAC * RP + r]);
+                    }
                 }
+                OO_ACC_PUT(g_mv, 1, AC_MV);
             }
         }
     } else if constexpr (PH == 16) {
@@ -1021,6 +1094,7 @@ OO_DEV void tile_phase(int tid, float* __restrict__ sm, const TileCtx& c, TileAc
     } else if constexpr (PH == 18) {
         // out_color / out_alpha weight gradients (reduce over points) ...
         if (tid < 4 * H) {
+            OO_ACC(g_oc, 1, AC_OC);
             const int o = tid >> 5, j = tid & 31;
             const float* dy = misc + (o < 3 ? (M_DCOL + o) : M_DRAW) * PS;
             const float* x = act + ((o < 3 ? R_HC : R_H4) + j) * PS;
@@ -1030,7 +1104,8 @@ OO_DEV void tile_phase(int tid, float* __restrict__ sm, const TileCtx& c, TileAc
                 const float4 d = ld4(dy + p0), h = ld4(x + p0);
                 s0 += d.x * h.x; s1 += d.y * h.y; s2 += d.z * h.z; s3 += d.w * h.w;
             }
-            a.s0 += (s0 + s1) + (s2 + s3);
+            g_oc[0] += (s0 + s1) + (s2 + s3);
+            OO_ACC_PUT(g_oc, 1, AC_OC);
         }
         // ... and d(hp_pre) = T_p * U_r * [hp > 0] in place
         if (PART) {
@@ -1065,8 +1140,10 @@ OO_DEV void tile_phase(int tid, float* __restrict__ sm, const TileCtx& c, TileAc
         }
     } else if constexpr (PH == 20) {
         // [color_linear ; clip_linear] weight gradient: rows = [d_hc ; d_hp], cols = [h4 ; e2]
-        if (PART) gemm_bwd_w<4, KP_HD / 8>(a.hd, tid, act + R_HC * PS, act + R_H4 * PS);
-        else gemm_bwd_w<2, KP_HD / 8>(a.hd, tid, act + R_HC * PS, act + R_H4 * PS);
+        OO_ACC(w_hd, 12, AC_HD);
+        if (PART) gemm_bwd_w<4, KP_HD / 8>(w_hd, tid, act + R_HC * PS, act + R_H4 * PS);
+        else gemm_bwd_w<2, KP_HD / 8>(w_hd, tid, act + R_HC * PS, act + R_H4 * PS);
+        OO_ACC_PUT(w_hd, 12, AC_HD);
     } else if constexpr (PH == 21) {
         // d[h4 ; e2] = W_cl^T d_hc + W_cp^T d_hp (+ W_a draw on the h4 rows), ReLU mask on the h4 rows; in place
         if (PART)
@@ -1076,22 +1153,30 @@ OO_DEV void tile_phase(int tid, float* __restrict__ sm, const TileCtx& c, TileAc
             gemm_bwd_data<KP_HD, WS_HD, H, 8, 0>(tid, w + W_CL, act + R_HC * PS, nullptr, nullptr,
                                                  act + R_H4 * PS, H, w + W_A, misc + M_DRAW * PS);
     } else if constexpr (PH == 22) {
-        gemm_bwd_w32(a.m2, tid, act + R_H4 * PS, act + R_H3 * PS);
+        OO_ACC(w_m2, 4, AC_M2);
+        gemm_bwd_w32(w_m2, tid, act + R_H4 * PS, act + R_H3 * PS);
+        OO_ACC_PUT(w_m2, 4, AC_M2);
     } else if constexpr (PH == 23) {
         gemm_bwd_data<H, WS_H, H, 8, 0>(tid, w + W_M2, act + R_H4 * PS, nullptr, nullptr, act + R_H3 * PS, H,
                                         nullptr, nullptr);
     } else if constexpr (PH == 24) {
-        gemm_bwd_w<2, KP_CAT / 8>(a.cat, tid, act + R_H3 * PS, act + R_H2 * PS);
+        OO_ACC(w_cat, 8, AC_CAT);
+        gemm_bwd_w<2, KP_CAT / 8>(w_cat, tid, act + R_H3 * PS, act + R_H2 * PS);
+        OO_ACC_PUT(w_cat, 8, AC_CAT);
     } else if constexpr (PH == 25) {
         gemm_bwd_data<H, WS_CAT, H, 8, 0>(tid, w + W_CAT, act + R_H3 * PS, nullptr, nullptr, act + R_H2 * PS, H,
                                           nullptr, nullptr);
     } else if constexpr (PH == 26) {
-        gemm_bwd_w32(a.m1, tid, act + R_H2 * PS, act + R_H1 * PS);
+        OO_ACC(w_m1, 4, AC_M1);
+        gemm_bwd_w32(w_m1, tid, act + R_H2 * PS, act + R_H1 * PS);
+        OO_ACC_PUT(w_m1, 4, AC_M1);
     } else if constexpr (PH == 27) {
         gemm_bwd_data<H, WS_H, H, 8, 0>(tid, w + W_M1, act + R_H2 * PS, nullptr, nullptr, act + R_H1 * PS, H,
                                         nullptr, nullptr);
     } else if constexpr (PH == 28) {
-        gemm_bwd_w<2, KP_IN / 8>(a.in, tid, act + R_H1 * PS, act + R_E1 * PS);
+        OO_ACC(w_in, 8, AC_IN);
+        gemm_bwd_w<2, KP_IN / 8>(w_in, tid, act + R_H1 * PS, act + R_E1 * PS);
+        OO_ACC_PUT(w_in, 8, AC_IN);
     } else if constexpr (PH == 29) {
         // d e1 = W_cat[:, 32:]^T d_h3 + W_in^T d_h1, in place over e1 (no mask)
         gemm_bwd_data<KP_IN, WS_CAT, H, WS_IN, H>(tid, w + W_CAT + H, act + R_H3 * PS, w + W_IN, act + R_H1 * PS,
@@ -1118,7 +1203,9 @@ OO_DEV void tile_phase(int tid, float* __restrict__ sm, const TileCtx& c, TileAc
             act[(R_E1 + 3 + d) * PS + p] = dp;
         }
     } else if constexpr (PH == 31) {
-        if (tid < NDIR * 3) {
+        if (tid < 64) {                                // warps 0, 1: warp-uniform accumulator access
+          OO_ACC(g_pe, 1, AC_PE);
+          if (tid < NDIR * 3) {
             const int d = tid / 3, ch = tid - 3 * d;
             const float* dp = act + (R_E1 + 3 + d) * PS;
             const float* tt = act + (R_T + ch) * PS;
@@ -1128,9 +1215,13 @@ OO_DEV void tile_phase(int tid, float* __restrict__ sm, const TileCtx& c, TileAc
                 const float4 x = ld4(dp + p0), y = ld4(tt + p0);
                 s0 += x.x * y.x; s1 += x.y * y.y; s2 += x.z * y.z; s3 += x.w * y.w;
             }
-            a.s2 += (s0 + s1) + (s2 + s3);
+            g_pe[0] += (s0 + s1) + (s2 + s3);
+          }
+          OO_ACC_PUT(g_pe, 1, AC_PE);
         }
-        if (tid < 6 * H + 4) {
+        if (tid < 7 * H) {                             // warps 0..6: warp-uniform accumulator access
+          OO_ACC(g_b, 1, AC_B);
+          if (tid < 6 * H + 4) {
             const float* row;
             if (tid < 6 * H) {
                 const int l = tid >> 5, j = tid & 31;
@@ -1146,7 +1237,9 @@ OO_DEV void tile_phase(int tid, float* __restrict__ sm, const TileCtx& c, TileAc
                 const float4 x = ld4(row + p0);
                 s0 += x.x; s1 += x.y; s2 += x.z; s3 += x.w;
             }
-            if (PART || tid < 5 * H || tid >= 6 * H) a.s1 += (s0 + s1) + (s2 + s3);
+            if (PART || tid < 5 * H || tid >= 6 * H) g_b[0] += (s0 + s1) + (s2 + s3);
+          }
+          OO_ACC_PUT(g_b, 1, AC_B);
         }
     }
 }
@@ -1170,52 +1263,73 @@ OO_DEV void flush_wfrags(int tid, float* __restrict__ slab, const float* acc, in
 
 template <int STEP, bool PART>
 OO_DEV void tile_flush(int tid, float* __restrict__ sm, float* __restrict__ slab, float* __restrict__ slot_loss,
-                       const TileAcc& a) {
+                       TileAcc& a) {
     if constexpr (STEP == 0) {
-        flush_wfrags<2, KP_IN / 8>(tid, slab, a.in, OFF_IN_W, 0, E1);
-        flush_wfrags<2, KP_CAT / 8>(tid, slab, a.cat, OFF_CAT_W, 0, H + E1);
-        if (tid >= NTHREADS / 2) {                       // second k-half of the 32 x 32 gradients -> scratch (Y area, free here)
+        {
+            OO_ACC(w_in, 8, AC_IN);
+            flush_wfrags<2, KP_IN / 8>(tid, slab, w_in, OFF_IN_W, 0, E1);
+        }
+        {
+            OO_ACC(w_cat, 8, AC_CAT);
+            flush_wfrags<2, KP_CAT / 8>(tid, slab, w_cat, OFF_CAT_W, 0, H + E1);
+        }
+        {
+            OO_ACC(w_m1, 4, AC_M1);
+            OO_ACC(w_m2, 4, AC_M2);
+            if (tid >= NTHREADS / 2) {                   // second k-half of the 32 x 32 gradients -> scratch (Y area, free here)
 #pragma unroll
-            for (int r = 0; r < 4; ++r) {
-                const int e = wfrag32_row(tid, r) * H + wfrag32_col(tid, r);
-                sm[SM_FEAT + e] = a.m1[r];
-                sm[SM_FEAT + H * H + e] = a.m2[r];
+                for (int r = 0; r < 4; ++r) {
+                    const int e = wfrag32_row(tid, r) * H + wfrag32_col(tid, r);
+                    sm[SM_FEAT + e] = w_m1[r];
+                    sm[SM_FEAT + H * H + e] = w_m2[r];
+                }
             }
         }
-        if (PART) flush_wfrags<4, KP_HD / 8>(tid, slab, a.hd, OFF_CL_W, OFF_CP_W, H + E2);
-        else flush_wfrags<2, KP_HD / 8>(tid, slab, a.hd, OFF_CL_W, 0, H + E2);
-        if (tid < 3 * H) slab[OFF_OC_W + tid] = a.s0;
-        else if (tid < 4 * H) slab[OFF_A_W + tid - 3 * H] = a.s0;
+        {
+            OO_ACC(w_hd, 12, AC_HD);
+            if (PART) flush_wfrags<4, KP_HD / 8>(tid, slab, w_hd, OFF_CL_W, OFF_CP_W, H + E2);
+            else flush_wfrags<2, KP_HD / 8>(tid, slab, w_hd, OFF_CL_W, 0, H + E2);
+        }
+        OO_ACC(g_oc, 1, AC_OC);
+        OO_ACC(g_b, 1, AC_B);
+        OO_ACC(g_pe, 1, AC_PE);
+        if (tid < 3 * H) slab[OFF_OC_W + tid] = g_oc[0];
+        else if (tid < 4 * H) slab[OFF_A_W + tid - 3 * H] = g_oc[0];
         if (tid < 6 * H) {
             const int l = tid >> 5, j = tid & 31;
             const int off = l == 0 ? OFF_IN_B : l == 1 ? OFF_M1_B : l == 2 ? OFF_CAT_B : l == 3 ? OFF_M2_B
                                                                       : l == 4 ? OFF_CL_B : OFF_CP_B;
-            if (PART || l < 5) slab[off + j] = a.s1;
+            if (PART || l < 5) slab[off + j] = g_b[0];
         } else if (tid < 6 * H + 3) {
-            slab[OFF_OC_B + tid - 6 * H] = a.s1;
+            slab[OFF_OC_B + tid - 6 * H] = g_b[0];
         } else if (tid == 6 * H + 3) {
-            slab[OFF_A_B] = a.s1;
+            slab[OFF_A_B] = g_b[0];
         }
-        if (tid < NDIR * 3) slab[OFF_PE_B + tid] = a.s2;
+        if (tid < NDIR * 3) slab[OFF_PE_B + tid] = g_pe[0];
         if (PART) {
-            if (tid < 8 * H) st4(slab + SLAB_M + 4 * tid, float4{a.gm[0], a.gm[1], a.gm[2], a.gm[3]});
-            if (tid <= H) slab[SLAB_MV + tid] = a.s3;     // m[0..31], beta at SLAB_MV + 32 == SLAB_BETA
+            OO_ACC(g_gm, 4, AC_GM);
+            OO_ACC(g_mv, 1, AC_MV);
+            if (tid < 8 * H) st4(slab + SLAB_M + 4 * tid, float4{g_gm[0], g_gm[1], g_gm[2], g_gm[3]});
+            if (tid <= H) slab[SLAB_MV + tid] = g_mv[0];     // m[0..31], beta at SLAB_MV + 32 == SLAB_BETA
         }
+        OO_ACC(loss, 4, AC_LOSS);
         if ((tid & 31) == 0 && (tid >> 5) < RT) {       // thread 32 r owns ray slot r (phases 8 and 32)
             float* rvl = sm + SM_RV;
             const int r = tid >> 5;
-            rvl[V_LD * RP + r] = a.loss[0];
-            rvl[V_LC * RP + r] = a.loss[1];
-            rvl[V_LO * RP + r] = a.loss[2];
-            rvl[V_LF * RP + r] = a.loss[3];
+            rvl[V_LD * RP + r] = loss[0];
+            rvl[V_LC * RP + r] = loss[1];
+            rvl[V_LO * RP + r] = loss[2];
+            rvl[V_LF * RP + r] = loss[3];
         }
     } else {
+        OO_ACC(w_m1, 4, AC_M1);
+        OO_ACC(w_m2, 4, AC_M2);
         if (tid < NTHREADS / 2) {
 #pragma unroll
             for (int r = 0; r < 4; ++r) {
                 const int e = wfrag32_row(tid, r) * H + wfrag32_col(tid, r);
-                slab[OFF_M1_W + e] = a.m1[r] + sm[SM_FEAT + e];
-                slab[OFF_M2_W + e] = a.m2[r] + sm[SM_FEAT + H * H + e];
+                slab[OFF_M1_W + e] = w_m1[r] + sm[SM_FEAT + e];
+                slab[OFF_M2_W + e] = w_m2[r] + sm[SM_FEAT + H * H + e];
             }
         }
         if (tid < 4) {

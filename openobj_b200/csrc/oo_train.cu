@@ -72,7 +72,19 @@ __global__ void __launch_bounds__(NTHREADS, 1) k_train(const TrainParams prm) {
     long long* cyc = (prm.phase_cycles != nullptr && blockIdx.x == 0) ? prm.phase_cycles : nullptr;
     const long long t_start = cyc ? clock64() : 0;
     zero_pad_rows(tid, sm);
+    // tensor memory for the weight-gradient accumulators: 16 warps x 64 columns (oo_tile.h, TileAcc); one CTA per SM
+    __shared__ uint32_t tm_base_s;
+    if (tid < 32) {
+        asm volatile("tcgen05.alloc.cta_group::1.sync.aligned.shared::cta.b32 [%0], %1;" ::"r"(
+                         (uint32_t)__cvta_generic_to_shared(&tm_base_s)), "r"((uint32_t)(AC_COLS * NWARPS / 4)) : "memory");
+        asm volatile("tcgen05.relinquish_alloc_permit.cta_group::1.sync.aligned;" ::: "memory");
+    }
+    asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory");
+    __syncthreads();
+    asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
+    const uint32_t tm_base = tm_base_s;
     TileAcc acc;
+    acc.tm = tm_base + ((uint32_t)(32 * ((tid >> 5) & 3)) << 16) + (uint32_t)(AC_COLS * (tid >> 7));
     acc_zero(acc);
     TileCtx c;
     c.flags = flags;
@@ -145,6 +157,11 @@ __global__ void __launch_bounds__(NTHREADS, 1) k_train(const TrainParams prm) {
         cyc[N_TRAIN_PHASES] += clock64() - t_start;     // whole block
         cyc[N_TRAIN_PHASES + 1] += t_end - t_begin;     // tiles processed
     }
+    asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory");
+    __syncthreads();
+    if (tid < 32)
+        asm volatile("tcgen05.dealloc.cta_group::1.sync.aligned.b32 %0, %1;" ::"r"(tm_base), "r"((uint32_t)(AC_COLS * NWARPS / 4))
+                     : "memory");
 }
 
 // ---- per-frame: ray counts per (step, object) and the cross-object zero-mask flags (render_rays.py:88-94)
