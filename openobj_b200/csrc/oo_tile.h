@@ -65,7 +65,7 @@ OO_DEV float warp_sum(float v) {
 // That frees 52 registers per thread for the GEMM loops (128 registers x 512 threads is the whole register file).
 // The host build (CPU tile emulator, tests only) keeps plain arrays.
 constexpr int AC_IN = 0, AC_CAT = 8, AC_HD = 16, AC_M1 = 32, AC_M2 = 36, AC_GM = 40, AC_OC = 44, AC_B = 45, AC_PE = 46,
-              AC_MV = 47, AC_LOSS = 48, AC_COLS = 64;
+              AC_MV = 47, AC_LOSS = 48, AC_TRIG = 52, AC_COLS = 64;
 struct TileAcc {
 #ifdef __CUDACC__
     uint32_t tm;       // tensor-memory address of this warp's column block (lane field = 32 * (warp % 4))
@@ -87,10 +87,12 @@ struct TileAcc {
 #ifdef __CUDACC__
 template <int N>
 OO_DEV void tm_ld(uint32_t addr, float* v) {
-    static_assert(N == 1 || N == 4 || N == 8 || N == 12, "tm_ld sizes");
+    static_assert(N == 1 || N == 2 || N == 4 || N == 8 || N == 12, "tm_ld sizes");
     uint32_t r[12];
     if constexpr (N == 1) {
         asm volatile("tcgen05.ld.sync.aligned.32x32b.x1.b32 {%0}, [%1];" : "=r"(r[0]) : "r"(addr));
+    } else if constexpr (N == 2) {
+        asm volatile("tcgen05.ld.sync.aligned.32x32b.x2.b32 {%0,%1}, [%2];" : "=r"(r[0]), "=r"(r[1]) : "r"(addr));
     } else if constexpr (N == 4) {
         asm volatile("tcgen05.ld.sync.aligned.32x32b.x4.b32 {%0,%1,%2,%3}, [%4];"
                      : "=r"(r[0]), "=r"(r[1]), "=r"(r[2]), "=r"(r[3]) : "r"(addr));
@@ -107,12 +109,14 @@ OO_DEV void tm_ld(uint32_t addr, float* v) {
 }
 template <int N>
 OO_DEV void tm_st(uint32_t addr, const float* v) {
-    static_assert(N == 1 || N == 4 || N == 8 || N == 12, "tm_st sizes");
+    static_assert(N == 1 || N == 2 || N == 4 || N == 8 || N == 12, "tm_st sizes");
     uint32_t r[12];
 #pragma unroll
     for (int i = 0; i < N; ++i) r[i] = __float_as_uint(v[i]);
     if constexpr (N == 1) {
         asm volatile("tcgen05.st.sync.aligned.32x32b.x1.b32 [%0], {%1};" ::"r"(addr), "r"(r[0]) : "memory");
+    } else if constexpr (N == 2) {
+        asm volatile("tcgen05.st.sync.aligned.32x32b.x2.b32 [%0], {%1,%2};" ::"r"(addr), "r"(r[0]), "r"(r[1]) : "memory");
     } else if constexpr (N == 4) {
         asm volatile("tcgen05.st.sync.aligned.32x32b.x4.b32 [%0], {%1,%2,%3,%4};" ::"r"(addr), "r"(r[0]), "r"(r[1]), "r"(r[2]),
                      "r"(r[3]) : "memory");
@@ -694,22 +698,40 @@ OO_DEV void tile_phase(int tid, float* __restrict__ sm, const TileCtx& c, TileAc
         // proj = B t ; e[3 + 21 k + d] = sin(pi * 2^k * proj) (embedding.py:48-53).  The reference's argument for band k
         // is fl(2^k proj * pi_f) = 2^k * fl(proj * pi_f) exactly (power-of-two scaling commutes with rounding), so all
         // six bands follow from one sincosf by angle doubling: s' = 2 s c, c' = (c - s)(c + s)  (norm error only doubles).
-        for (int i = tid; i < NDIR * P; i += NTHREADS) {
-            const int d = i / P, p = i - d * P;
-            const float t0 = act[(R_T + 0) * PS + p], t1 = act[(R_T + 1) * PS + p], t2 = act[(R_T + 2) * PS + p];
-            const float proj = w[W_PE + 3 * d] * t0 + w[W_PE + 3 * d + 1] * t1 + w[W_PE + 3 * d + 2] * t2;
-            float sn, cs;
-            sincosf(proj * PI_F, &sn, &cs);
+        // the band-0 (sin, cos) of this thread's items stay in its tensor-memory lane for the backward encoder (phase 30 walks
+        // the same items with the same thread), which then needs neither the projection nor a second sincosf
+        constexpr int NTRIG = (NDIR * P + NTHREADS - 1) / NTHREADS;
+        static_assert(NTRIG == 5, "the sin/cos stash holds five items per thread");
+        float trig[2 * NTRIG];
 #pragma unroll
-            for (int k = 0; k < NBAND; ++k) {
-                const int row = 3 + NDIR * k + d;
-                if (row < E1) act[(R_E1 + row) * PS + p] = sn;
-                else act[(R_E2 + row - E1) * PS + p] = sn;
-                const float s2 = 2.f * sn * cs, c2 = (cs - sn) * (cs + sn);
-                sn = s2;
-                cs = c2;
+        for (int u = 0; u < NTRIG; ++u) {
+            const int i = tid + NTHREADS * u;
+            trig[u] = trig[NTRIG + u] = 0.f;
+            if (i < NDIR * P) {
+                const int d = i / P, p = i - d * P;
+                const float t0 = act[(R_T + 0) * PS + p], t1 = act[(R_T + 1) * PS + p], t2 = act[(R_T + 2) * PS + p];
+                const float proj = w[W_PE + 3 * d] * t0 + w[W_PE + 3 * d + 1] * t1 + w[W_PE + 3 * d + 2] * t2;
+                float sn, cs;
+                sincosf(proj * PI_F, &sn, &cs);
+                trig[u] = sn;
+                trig[NTRIG + u] = cs;
+#pragma unroll
+                for (int k = 0; k < NBAND; ++k) {
+                    const int row = 3 + NDIR * k + d;
+                    if (row < E1) act[(R_E1 + row) * PS + p] = sn;
+                    else act[(R_E2 + row - E1) * PS + p] = sn;
+                    const float s2 = 2.f * sn * cs, c2 = (cs - sn) * (cs + sn);
+                    sn = s2;
+                    cs = c2;
+                }
             }
         }
+#ifdef __CUDACC__
+        if (c.nrays > 0) {                       // training tiles only (the forward kernels allocate no tensor memory)
+            tm_st<8>(a.tm + AC_TRIG, trig);
+            tm_st<2>(a.tm + AC_TRIG + 8, trig + 8);
+        }
+#endif
     } else if constexpr (PH == 2) {
         gemm_fwd<KP_IN, WS_IN, 2, true>(tid, w + W_IN, w + B_IN, act + R_E1 * PS, act + R_H1 * PS);
     } else if constexpr (PH == 3) {
@@ -1183,12 +1205,25 @@ OO_DEV void tile_phase(int tid, float* __restrict__ sm, const TileCtx& c, TileAc
                                                   act + R_E1 * PS, 0, nullptr, nullptr);
     } else if constexpr (PH == 30) {
         // d proj[d][p] = sum_k d e[3+21k+d][p] * pi 2^k cos(pi 2^k proj); stored over e1 row 3+d
-        for (int i = tid; i < NDIR * P; i += NTHREADS) {
+#ifdef __CUDACC__
+        float trig[10];
+        tm_ld<8>(a.tm + AC_TRIG, trig);
+        tm_ld<2>(a.tm + AC_TRIG + 8, trig + 8);
+#endif
+#pragma unroll
+        for (int u = 0; u < 5; ++u) {
+            const int i = tid + NTHREADS * u;
+            if (i >= NDIR * P) continue;
             const int d = i / P, p = i - d * P;
+            float sn, cs;
+#ifdef __CUDACC__
+            sn = trig[u];
+            cs = trig[5 + u];
+#else
             const float t0 = act[(R_T + 0) * PS + p], t1 = act[(R_T + 1) * PS + p], t2 = act[(R_T + 2) * PS + p];
             const float proj = w[W_PE + 3 * d] * t0 + w[W_PE + 3 * d + 1] * t1 + w[W_PE + 3 * d + 2] * t2;
-            float sn, cs;
             sincosf(proj * PI_F, &sn, &cs);
+#endif
             float band = PI_F, dp = 0.f;
 #pragma unroll
             for (int k = 0; k < NBAND; ++k) {

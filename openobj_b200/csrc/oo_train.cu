@@ -27,9 +27,17 @@ struct TrainParams {
     float* slot_loss;
     float scale, cs, os, fs;
     long long* phase_cycles;   // debug: [N_TRAIN_PHASES + 4] cycle totals of block 0: phases, block, tiles, staging, flush
+    long long* block_times;    // debug: [n_cta][3] = {globaltimer at block start, at block end, tiles} of the last launch
 };
 
 long long* g_phase_cycles = nullptr;
+long long* g_block_times = nullptr;
+
+__device__ __forceinline__ long long global_ns() {
+    long long t;
+    asm volatile("mov.u64 %0, %globaltimer;" : "=l"(t));
+    return t;
+}
 
 template <int PH, int END, bool PART>
 struct Phases {
@@ -69,6 +77,10 @@ __global__ void __launch_bounds__(NTHREADS, 1) k_train(const TrainParams prm) {
     int slot = prm.sched[n_cta + 1 + blockIdx.x];
     const int flags = prm.flags[0];
 
+    if (prm.block_times != nullptr && tid == 0) {
+        prm.block_times[3 * blockIdx.x] = global_ns();
+        prm.block_times[3 * blockIdx.x + 2] = t_end - t_begin;
+    }
     long long* cyc = (prm.phase_cycles != nullptr && blockIdx.x == 0) ? prm.phase_cycles : nullptr;
     const long long t_start = cyc ? clock64() : 0;
     zero_pad_rows(tid, sm);
@@ -159,6 +171,7 @@ __global__ void __launch_bounds__(NTHREADS, 1) k_train(const TrainParams prm) {
     }
     asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory");
     __syncthreads();
+    if (prm.block_times != nullptr && tid == 0) prm.block_times[3 * blockIdx.x + 1] = global_ns();
     if (tid < 32)
         asm volatile("tcgen05.dealloc.cta_group::1.sync.aligned.b32 %0, %1;" ::"r"(tm_base), "r"((uint32_t)(AC_COLS * NWARPS / 4))
                      : "memory");
@@ -759,6 +772,7 @@ int launch_k1(const float* theta, int n_obj, const oo_batch* b, int it, int R, f
     prm.slot_loss = ws->slot_loss;
     prm.scale = scale;
     prm.phase_cycles = g_phase_cycles;
+    prm.block_times = g_block_times;
     prm.cs = 5.f; prm.os = 10.f; prm.fs = 5.f;   // loss.py:6 defaults (the JSON values are never read)
     const size_t smem = (size_t)SM_TOTAL * sizeof(float);
     static bool attr_set = false;
@@ -786,6 +800,11 @@ int launch_k1(const float* theta, int n_obj, const oo_batch* b, int it, int R, f
 }  // namespace
 
 // debug hook (not part of the ABI header): per-phase cycle counters of block 0
+extern "C" int oo_debug_block_times(long long* dev_ptr) {     // [n_cta][3]; nullptr switches it off
+    g_block_times = dev_ptr;
+    return 3;
+}
+
 extern "C" int oo_debug_phase_cycles(long long* dev_ptr) {
     g_phase_cycles = dev_ptr;
     return N_TRAIN_PHASES + 4;
