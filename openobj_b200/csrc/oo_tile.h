@@ -646,11 +646,21 @@ OO_DEV void tile_phase0_pre(int tid, float* __restrict__ sm, const TileCtx& c, f
 // ------------------------------------------------------------------------------------------------
 // phases
 // ------------------------------------------------------------------------------------------------
+#ifdef __CUDACC__
+// device: the eleven small phases between the forward heads and the backward GEMMs are fused into three (40, 41, 42)
+constexpr int N_TRAIN_PHASES = 22;
+#else
 constexpr int N_TRAIN_PHASES = 30;
+#endif
 constexpr int N_FWD_PHASES = 8;    // phases 0..7 are shared with the standalone forward kernel
 // execution order of the training tile (phases 32..35 were split out of their neighbours later)
+#ifdef __CUDACC__
+constexpr int kTrainOrder[N_TRAIN_PHASES] = {0, 1, 2, 3, 4, 5, 6, 40, 41, 42, 20, 21, 22, 23, 24, 25, 26, 27, 28, 29, 30, 31};
+#else
+// host (CPU tile emulator): the unfused formulation, one small phase per step, every thread private within a phase
 constexpr int kTrainOrder[N_TRAIN_PHASES] = {0, 1, 2, 3, 4, 5, 6, 7, 33, 8, 10, 11, 32, 13, 16, 17, 18, 19,
                                              20, 21, 22, 23, 24, 25, 26, 27, 28, 29, 30, 31};
+#endif
 
 template <int PH, bool PART>
 OO_DEV void tile_phase(int tid, float* __restrict__ sm, const TileCtx& c, TileAcc& a) {
@@ -744,6 +754,9 @@ OO_DEV void tile_phase(int tid, float* __restrict__ sm, const TileCtx& c, TileAc
         // [color_linear ; clip_linear] share their input: one GEMM with 64 output rows when the clip head is live
         if (PART) gemm_fwd<KP_HD, WS_HD, 4, true>(tid, w + W_CL, w + B_CL, act + R_H4 * PS, act + R_HC * PS);
         else gemm_fwd<KP_HD, WS_HD, 2, true>(tid, w + W_CL, w + B_CL, act + R_H4 * PS, act + R_HC * PS);
+#ifdef __CUDACC__
+        if (PART) OO_CP_ASYNC_WAIT();      // Y rows issued in phase 1 are complete for this thread; the barrier publishes them
+#endif
     } else if constexpr (PH == 7) {
         // out_alpha (x10, model.py:88) -> occupancy = sigmoid (render_rays.py:13); out_color -> sigmoid (model.py:96)
         for (int i = tid; i < 4 * P; i += NTHREADS) {
@@ -762,6 +775,305 @@ OO_DEV void tile_phase(int tid, float* __restrict__ sm, const TileCtx& c, TileAc
                 misc[(M_COL + ch) * PS + p] = sigmoidf_(r);
             }
         }
+#ifdef __CUDACC__
+    } else if constexpr (PH == 40) {
+        // ---- fused: out_alpha / out_color heads (phase 7) + v = W^T y partials (tensor part of phase 10).  The out_clip
+        // fragments come from L2: they are requested first and the head outputs are computed while they fly.
+        constexpr int CW = C / NWARPS;
+        static_assert(CW == 32, "each warp takes four 8-wide k-steps of gt-feature columns");
+        const int wv = tid >> 5, lane = tid & 31, g = lane >> 2, t = lane & 3;
+        float bw[4][4][2], bq[4][2];
+        if (PART) {
+            const float* wg = c.theta + OFF_OCL_W + (size_t)(wv * CW) * H;
+            const float* bg = c.theta + OFF_OCL_B + wv * CW;
+#pragma unroll
+            for (int ks = 0; ks < 4; ++ks) {
+#pragma unroll
+                for (int nt = 0; nt < 4; ++nt) {
+                    bw[ks][nt][0] = OO_LDG(wg + (8 * ks + t) * H + 8 * nt + g);
+                    bw[ks][nt][1] = OO_LDG(wg + (8 * ks + t + 4) * H + 8 * nt + g);
+                }
+                bq[ks][0] = g == 0 ? OO_LDG(bg + 8 * ks + t) : 0.f;
+                bq[ks][1] = g == 0 ? OO_LDG(bg + 8 * ks + t + 4) : 0.f;
+            }
+        }
+        if (tid < 4 * P) {
+            const int o = tid / P, p = tid - o * P;
+            if (o == 0) {
+                float r = w[B_A];
+#pragma unroll 8
+                for (int j = 0; j < H; ++j) r += w[W_A + j] * act[(R_H4 + j) * PS + p];
+                misc[M_OCC * PS + p] = sigmoidf_(r * 10.f);
+            } else {
+                const int ch = o - 1;
+                float r = w[B_OC + ch];
+#pragma unroll 8
+                for (int j = 0; j < H; ++j) r += w[W_OC + ch * H + j] * act[(R_HC + j) * PS + p];
+                misc[(M_COL + ch) * PS + p] = sigmoidf_(r);
+            }
+        }
+        if (PART) {
+            float* y = sm + SM_FEAT + wv * CW;
+            const bool hi_row = g + 8 < RT;
+            float vacc[5][4];
+#pragma unroll
+            for (int nt = 0; nt < 5; ++nt) vacc[nt][0] = vacc[nt][1] = vacc[nt][2] = vacc[nt][3] = 0.f;
+            float yy0 = 0.f, yy1 = 0.f;
+#pragma unroll
+            for (int ks = 0; ks < 4; ++ks) {
+                const float a0 = y[g * YSTR + 8 * ks + t], a2 = y[g * YSTR + 8 * ks + t + 4];
+                const float a1 = hi_row ? y[(g + 8) * YSTR + 8 * ks + t] : 0.f, a3 = hi_row ? y[(g + 8) * YSTR + 8 * ks + t + 4] : 0.f;
+                yy0 += a0 * a0 + a2 * a2;
+                yy1 += a1 * a1 + a3 * a3;
+                FragA fa;
+                frag_a(fa, a0, a1, a2, a3);
+#pragma unroll
+                for (int nt = 0; nt < 4; ++nt) {
+                    FragB fb;
+                    frag_b(fb, bw[ks][nt][0], bw[ks][nt][1]);
+                    mma3(vacc[nt], fa, fb);
+                }
+                FragB fq;
+                frag_b(fq, bq[ks][0], bq[ks][1]);
+                mma3(vacc[4], fa, fq);
+            }
+            yy0 += __shfl_xor_sync(0xffffffffu, yy0, 1); yy0 += __shfl_xor_sync(0xffffffffu, yy0, 2);
+            yy1 += __shfl_xor_sync(0xffffffffu, yy1, 1); yy1 += __shfl_xor_sync(0xffffffffu, yy1, 2);
+            if (t == 0) {
+                sm[SM_YS + (g * 16 + wv) * 2] = vacc[4][0];
+                sm[SM_YS + (g * 16 + wv) * 2 + 1] = yy0;
+                if (hi_row) {
+                    sm[SM_YS + ((g + 8) * 16 + wv) * 2] = vacc[4][2];
+                    sm[SM_YS + ((g + 8) * 16 + wv) * 2 + 1] = yy1;
+                }
+            }
+            __syncwarp();
+#pragma unroll
+            for (int nt = 0; nt < 4; ++nt) {
+                *reinterpret_cast<float2*>(y + g * YSTR + 8 * nt + 2 * t) = float2{vacc[nt][0], vacc[nt][1]};
+                if (hi_row) *reinterpret_cast<float2*>(y + (g + 8) * YSTR + 8 * nt + 2 * t) = float2{vacc[nt][2], vacc[nt][3]};
+            }
+        }
+    } else if constexpr (PH == 41) {
+        // ---- fused per-ray chain: warp r owns ray r from the termination weights to dL/d(alpha, colour) of its samples
+        // (phases 33, 8, 10 (S), 11, 32, 13 (U, record), 16, 17 of the unfused formulation; same operation order).  Lanes are
+        // samples for the compositing parts and hidden units for the feature parts; everything stays in registers / shuffles,
+        // shared memory only receives what later phases read.
+        const int r = tid >> 5, lane = tid & 31;
+        if (r < RT) {
+            constexpr unsigned FULL = 0xffffffffu;
+            const bool live_ray = r < c.nrays, smp = lane < S, live = live_ray && smp;
+            const int p = r * S + (smp ? lane : 0);
+            // termination: exclusive product of the free probabilities in torch.cumprod's order (render_rays.py:36-43)
+            const float occ = smp ? misc[M_OCC * PS + p] : 0.f;
+            const float fq = 1.f - occ + 1e-10f;
+            float freep = 1.f;
+#pragma unroll
+            for (int q = 0; q < S - 1; ++q) {
+                const float f = __shfl_sync(FULL, fq, q);
+                if (q < lane) freep *= f;
+            }
+            const float fp = live ? freep : 0.f;
+            const float t = live ? occ * freep : 0.f;
+            if (smp) misc[M_TERM * PS + p] = t;
+            // rendered depth / variance / colour / opacity (render_rays.py:56-63)
+            const float zv = live ? misc[M_Z * PS + p] : 0.f;
+            const float k0 = misc[(M_COL + 0) * PS + p], k1 = misc[(M_COL + 1) * PS + p], k2 = misc[(M_COL + 2) * PS + p];
+            const float depth = warp_sum(t * zv), opac = warp_sum(t);
+            const float c0 = warp_sum(t * k0), c1 = warp_sum(t * k1), c2 = warp_sum(t * k2);
+            const float dz = zv - depth;
+            const float var = warp_sum(t * (dz * dz));
+            float gd = 0.f, go = 0.f, gc0 = 0.f, gc1 = 0.f, gc2 = 0.f, cf = 0.f;
+            float l0 = 0.f, l1 = 0.f, l2 = 0.f, l3 = 0.f;
+            if (lane == 0 && live_ray) {                  // loss terms and their derivatives (loss.py:27-75)
+                const int lab = (int)rv[V_LAB * RP + r];
+                const bool is1 = lab == 1, sem = lab != 2;
+                const float tgt = lab != 0 ? 1.f : 0.f;
+                if (is1 && !(c.flags & 2)) {
+                    const float wgt = 1.f / (sqrtf(var) + 1e-4f);           // render_rays.py:95-100, var detached
+                    const float dd = depth - rv[V_GTD * RP + r];
+                    l0 = fabsf(dd) * wgt;
+                    gd = sgnf_(dd) * wgt * c.inv1;
+                    const float e0 = c0 - rv[(V_RGB + 0) * RP + r] / 255.f;   // train.py:373 `/ 255.`
+                    const float e1 = c1 - rv[(V_RGB + 1) * RP + r] / 255.f;
+                    const float e2 = c2 - rv[(V_RGB + 2) * RP + r] / 255.f;
+                    l1 = fabsf(e0) + fabsf(e1) + fabsf(e2);                      // loss.py:61 sum over channels
+                    gc0 = sgnf_(e0) * c.cs * c.inv1;
+                    gc1 = sgnf_(e1) * c.cs * c.inv1;
+                    gc2 = sgnf_(e2) * c.cs * c.inv1;
+                    cf = PART ? c.fs * c.inv1 : 0.f;
+                }
+                if (sem && !(c.flags & 4)) {
+                    const float eo = opac - tgt;                                 // loss.py:71
+                    l2 = fabsf(eo);
+                    go = sgnf_(eo) * c.os * c.invs;
+                }
+            }
+            gd = __shfl_sync(FULL, gd, 0); go = __shfl_sync(FULL, go, 0);
+            gc0 = __shfl_sync(FULL, gc0, 0); gc1 = __shfl_sync(FULL, gc1, 0); gc2 = __shfl_sync(FULL, gc2, 0);
+            float bgv = 0.f;
+            if (PART) {
+                // S_j = sum_i T_i hp_i[j]; v_j = sum of the 16 partial W^T y; gs_j = (G S)_j + opac wb_j
+                float sj = 0.f;
+#pragma unroll
+                for (int q = 0; q < S; ++q) sj += __shfl_sync(FULL, t, q) * act[(R_HP + lane) * PS + r * S + q];
+                sm[SM_ST + lane * RP + r] = sj;
+                float vj = 0.f;
+#pragma unroll
+                for (int wv = 0; wv < NWARPS; ++wv) vj += sm[SM_FEAT + r * YSTR + wv * (C / NWARPS) + lane];
+                float tot = 0.f;
+                if (lane < 2) {                               // totals of y.b (lane 0) and y.y (lane 1)
+                    float s0 = 0.f, s1 = 0.f;
+#pragma unroll
+                    for (int ch = 0; ch < 16; ch += 2) {
+                        s0 += sm[SM_YS + (r * 16 + ch) * 2 + lane];
+                        s1 += sm[SM_YS + (r * 16 + ch + 1) * 2 + lane];
+                    }
+                    tot = s0 + s1;
+                }
+                const float yb = __shfl_sync(FULL, tot, 0), yy = __shfl_sync(FULL, tot, 1);
+                const float wbj = rv[V_WB * RP + lane];
+                float gk[H];
+#pragma unroll
+                for (int k = 0; k < H; ++k) gk[k] = c.derived[DER_G + k * H + lane];      // G is symmetric: coalesced over j
+                float gs = opac * wbj;
+#pragma unroll
+                for (int k = 0; k < H; ++k) gs += gk[k] * __shfl_sync(FULL, sj, k);
+                const float sv = warp_sum(sj * vj), swb = warp_sum(sj * wbj), sgs = warp_sum(sj * gs);
+                float A = 0.f, B = 0.f;
+                if (lane == 0) {
+                    const float bb = rv[V_WB * RP + H];
+                    const float xb = swb + opac * bb;                     // b . x
+                    const float xy = sv + opac * yb, xx = sgs + opac * xb;
+                    const float nxr = sqrtf(fmaxf(xx, 0.f)), nyr = sqrtf(yy);
+                    const float nx = fmaxf(nxr, 1e-8f), ny = fmaxf(nyr, 1e-8f);   // F.cosine_similarity eps clamp
+                    const float cosv = xy / (nx * ny);
+                    if (cf != 0.f) {
+                        l3 = 1.f - cosv;
+                        A = -cf / (nx * ny);                              // d(1-cos)/dx = -y/(nx ny) + [|x|>eps] cos x / nx^2
+                        B = nxr > 1e-8f ? cf * cosv / (nx * nx) : 0.f;
+                    }
+                    bgv = A * yb + B * xb;                                // b_ocl . dL/dx
+                    rv[V_B * RP + r] = B;
+                }
+                A = __shfl_sync(FULL, A, 0); B = __shfl_sync(FULL, B, 0); bgv = __shfl_sync(FULL, bgv, 0);
+                sm[SM_UT + lane * RP + r] = A * vj + B * gs;             // dL/dS
+                if (live_ray) {                                           // per-ray record for K4 (out_clip gradient)
+                    c.rayrec[r * RAYREC + REC_S + lane] = sj;
+                    if (lane < 2) c.rayrec[r * RAYREC + lane] = lane == REC_A ? A : opac;
+                }
+                __syncwarp();
+            }
+            if (lane == 0) rv[V_OPAC * RP + r] = opac;
+            // dL/dT of each sample, then back through the compositing sums and the exclusive product
+            float g = 0.f;
+            if (live) {
+                g = zv * gd + go + k0 * gc0 + k1 * gc1 + k2 * gc2;
+                if (PART) {
+                    float hu = bgv;
+#pragma unroll 8
+                    for (int j = 0; j < H; ++j) hu += act[(R_HP + j) * PS + p] * sm[SM_UT + j * RP + r];
+                    g += hu;
+                }
+            }
+            const float gT = g * t;
+            float suffix = 0.f;
+#pragma unroll
+            for (int q = S - 1; q >= 1; --q) {
+                const float v = __shfl_sync(FULL, gT, q);
+                if (q > lane) suffix += v;
+            }
+            if (smp) {
+                float draw = 0.f, d0 = 0.f, d1 = 0.f, d2 = 0.f;
+                if (live_ray) {
+                    const float docc = g * fp - suffix / (1.f - occ + 1e-10f);
+                    draw = docc * occ * (1.f - occ) * 10.f;
+                    d0 = t * gc0 * k0 * (1.f - k0);
+                    d1 = t * gc1 * k1 * (1.f - k1);
+                    d2 = t * gc2 * k2 * (1.f - k2);
+                }
+                misc[(M_DCOL + 0) * PS + p] = d0;
+                misc[(M_DCOL + 1) * PS + p] = d1;
+                misc[(M_DCOL + 2) * PS + p] = d2;
+                misc[M_DRAW * PS + p] = draw;
+            }
+            OO_ACC(loss, 4, AC_LOSS);
+            loss[0] += l0; loss[1] += l1; loss[2] += l2; loss[3] += l3;      // non-zero in lane 0 only
+            OO_ACC_PUT(loss, 4, AC_LOSS);
+        }
+    } else if constexpr (PH == 42) {
+        // ---- fused: M / m / beta accumulators (phase 13), out_color / out_alpha weight gradients and d(hp_pre) (phase 18),
+        // then (after a block barrier: it overwrites the hc rows the out_color weight gradient reads) d(hc_pre) (phase 19)
+        if (PART) {
+            if (tid < 8 * H) {
+                OO_ACC(g_gm, 4, AC_GM);
+                const int k = tid >> 3, j4 = 4 * (tid & 7);
+#pragma unroll
+                for (int r = 0; r < RT; ++r) {
+                    const float bs = rv[V_B * RP + r] * sm[SM_ST + k * RP + r];
+                    g_gm[0] += bs * sm[SM_ST + (j4 + 0) * RP + r];
+                    g_gm[1] += bs * sm[SM_ST + (j4 + 1) * RP + r];
+                    g_gm[2] += bs * sm[SM_ST + (j4 + 2) * RP + r];
+                    g_gm[3] += bs * sm[SM_ST + (j4 + 3) * RP + r];
+                }
+                OO_ACC_PUT(g_gm, 4, AC_GM);
+            }
+            if (tid < 2 * 32) {
+                OO_ACC(g_mv, 1, AC_MV);
+                if (tid <= H) {
+#pragma unroll
+                    for (int r = 0; r < RT; ++r) {
+                        const float bo = rv[V_B * RP + r] * rv[V_OPAC * RP + r];
+                        g_mv[0] += bo * (tid < H ? sm[SM_ST + tid * RP + r] : rv[V_OPAC * RP + r]);
+                    }
+                }
+                OO_ACC_PUT(g_mv, 1, AC_MV);
+            }
+        }
+        if (tid < 4 * H) {
+            OO_ACC(g_oc, 1, AC_OC);
+            const int o = tid >> 5, j = tid & 31;
+            const float* dy = misc + (o < 3 ? (M_DCOL + o) : M_DRAW) * PS;
+            const float* x = act + ((o < 3 ? R_HC : R_H4) + j) * PS;
+            float s0 = 0.f, s1 = 0.f, s2 = 0.f, s3 = 0.f;      // four independent chains
+#pragma unroll
+            for (int p0 = 0; p0 < P; p0 += 4) {
+                const float4 d = ld4(dy + p0), h = ld4(x + p0);
+                s0 += d.x * h.x; s1 += d.y * h.y; s2 += d.z * h.z; s3 += d.w * h.w;
+            }
+            g_oc[0] += (s0 + s1) + (s2 + s3);
+            OO_ACC_PUT(g_oc, 1, AC_OC);
+        }
+        if (PART) {
+            for (int i = tid; i < H * (P / 4); i += NTHREADS) {      // d(hp_pre) = T_p * U_r * [hp > 0] in place
+                const int j = i / (P / 4), p0 = 4 * (i - j * (P / 4));
+                float* hp = act + (R_HP + j) * PS + p0;
+                const float4 h = ld4(hp), t = ld4(misc + M_TERM * PS + p0);
+                const float* ut = sm + SM_UT + j * RP;
+                float4 o;
+                o.x = h.x > 0.f ? t.x * ut[(p0 + 0) / S] : 0.f;
+                o.y = h.y > 0.f ? t.y * ut[(p0 + 1) / S] : 0.f;
+                o.z = h.z > 0.f ? t.z * ut[(p0 + 2) / S] : 0.f;
+                o.w = h.w > 0.f ? t.w * ut[(p0 + 3) / S] : 0.f;
+                st4(hp, o);
+            }
+        }
+        __syncthreads();       // the out_color weight gradient above read hc; d(hc_pre) now replaces it in place
+        for (int i = tid; i < H * (P / 4); i += NTHREADS) {          // d(hc_pre) = (W_oc^T dcol_pre) * [hc > 0]
+            const int j = i / (P / 4), p0 = 4 * (i - j * (P / 4));
+            float* hc = act + (R_HC + j) * PS + p0;
+            const float4 h = ld4(hc);
+            const float4 d0 = ld4(misc + (M_DCOL + 0) * PS + p0), d1 = ld4(misc + (M_DCOL + 1) * PS + p0),
+                         d2 = ld4(misc + (M_DCOL + 2) * PS + p0);
+            const float w0 = w[W_OC + j], w1 = w[W_OC + H + j], w2 = w[W_OC + 2 * H + j];
+            float4 o;
+            o.x = h.x > 0.f ? w0 * d0.x + w1 * d1.x + w2 * d2.x : 0.f;
+            o.y = h.y > 0.f ? w0 * d0.y + w1 * d1.y + w2 * d2.y : 0.f;
+            o.z = h.z > 0.f ? w0 * d0.z + w1 * d1.z + w2 * d2.z : 0.f;
+            o.w = h.w > 0.f ? w0 * d0.w + w1 * d1.w + w2 * d2.w : 0.f;
+            st4(hc, o);
+        }
+#endif
     } else if constexpr (PH == 33) {
         // per point: exclusive product of the free probabilities in torch.cumprod's order, termination weight
         // (render_rays.py:36-43)

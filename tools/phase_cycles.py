@@ -36,8 +36,9 @@ tiles = c[NP + 1]
 label = {0: "load", 1: "PE fwd", 2: "in", 3: "mid1", 4: "cat", 5: "mid2", 6: "heads", 7: "out", 33: "termination", 8: "ray sums+loss",
          9: "S", 10: "v=W^T y part", 11: "v reduce", 12: "G S", 32: "cos/A/B", 13: "U+rec+M", 16: "g per point",
          17: "bwd composite", 18: "dWoc+dhp", 19: "dhc", 20: "W heads", 21: "D heads", 22: "W m2", 23: "D h3", 24: "W cat",
-         25: "D h2", 26: "W m1", 27: "D h1", 28: "W in", 29: "D e1", 30: "PE bwd", 31: "bias"}
-order = [0, 1, 2, 3, 4, 5, 6, 7, 33, 8, 10, 11, 32, 13, 16, 17, 18, 19, 20, 21, 22, 23, 24, 25, 26, 27, 28, 29, 30, 31]
+         25: "D h2", 26: "W m1", 27: "D h1", 28: "W in", 29: "D e1", 30: "PE bwd", 31: "bias",
+         40: "out + v=W^T y", 41: "ray chain", 42: "M + dWoc + dhp + dhc"}
+order = [0, 1, 2, 3, 4, 5, 6, 40, 41, 42, 20, 21, 22, 23, 24, 25, 26, 27, 28, 29, 30, 31]     # device order (oo_tile.h kTrainOrder)
 if len(sys.argv) > 3:
     order = [int(x) for x in sys.argv[3].split(",")]
 names = ["%d %s" % (o, label.get(o, "?")) for o in order][:NP]
