@@ -28,11 +28,14 @@
 // 16-byte asynchronous global -> shared copy (LDGSTS); completion awaited with OO_CP_ASYNC_WAIT before a barrier
 #define OO_CP_ASYNC16(dst, src)                                                                          \
     asm volatile("cp.async.cg.shared.global [%0], [%1], 16;" ::"r"((unsigned)__cvta_generic_to_shared(dst)), "l"(src))
+#define OO_CP_ASYNC4(dst, src)                                                                           \
+    asm volatile("cp.async.ca.shared.global [%0], [%1], 4;" ::"r"((unsigned)__cvta_generic_to_shared(dst)), "l"(src))
 #define OO_CP_ASYNC_WAIT() asm volatile("cp.async.wait_all;" ::: "memory")
 #else
 #define OO_DEV inline
 #define OO_LDG(p) (*(p))
 #define OO_CP_ASYNC16(dst, src) memcpy((dst), (src), 16)
+#define OO_CP_ASYNC4(dst, src) memcpy((dst), (src), 4)
 #define OO_CP_ASYNC_WAIT() ((void)0)
 #include <string.h>
 struct alignas(16) float4 {
@@ -492,10 +495,13 @@ OO_DEV void gemm_bwd_w32(float* acc, int tid, const float* __restrict__ DY, cons
 // ------------------------------------------------------------------------------------------------
 // staging an object's weights into shared memory (padded rows, zero pad columns)
 // ------------------------------------------------------------------------------------------------
+// every element travels as a 4-byte asynchronous copy (the rows of the reference's tensors are not 16-byte aligned): all
+// of a thread's copies are in flight together instead of one L2 round trip per loop iteration; awaited in stage_weights
 OO_DEV void copy_rows(int tid, float* dst, int ws, const float* __restrict__ src, int rows, int cols, int colsp) {
     for (int i = tid; i < rows * colsp; i += NTHREADS) {
         const int r = i / colsp, c = i - r * colsp;
-        dst[r * ws + c] = c < cols ? OO_LDG(src + r * cols + c) : 0.f;
+        if (c < cols) OO_CP_ASYNC4(dst + r * ws + c, src + r * cols + c);
+        else dst[r * ws + c] = 0.f;
     }
 }
 
@@ -508,20 +514,24 @@ OO_DEV void stage_weights(int tid, float* sm, const float* __restrict__ th) {
     copy_rows(tid, w + W_CL, WS_HD, th + OFF_CL_W, H, H + E2, KP_HD);
     copy_rows(tid, w + W_CP, WS_HD, th + OFF_CP_W, H, H + E2, KP_HD);
     for (int i = tid; i < H; i += NTHREADS) {
-        w[W_A + i] = OO_LDG(th + OFF_A_W + i);
-        w[B_IN + i] = OO_LDG(th + OFF_IN_B + i);
-        w[B_M1 + i] = OO_LDG(th + OFF_M1_B + i);
-        w[B_CAT + i] = OO_LDG(th + OFF_CAT_B + i);
-        w[B_M2 + i] = OO_LDG(th + OFF_M2_B + i);
-        w[B_CL + i] = OO_LDG(th + OFF_CL_B + i);
-        w[B_CP + i] = OO_LDG(th + OFF_CP_B + i);
+        OO_CP_ASYNC4(w + W_A + i, th + OFF_A_W + i);
+        OO_CP_ASYNC4(w + B_IN + i, th + OFF_IN_B + i);
+        OO_CP_ASYNC4(w + B_M1 + i, th + OFF_M1_B + i);
+        OO_CP_ASYNC4(w + B_CAT + i, th + OFF_CAT_B + i);
+        OO_CP_ASYNC4(w + B_M2 + i, th + OFF_M2_B + i);
+        OO_CP_ASYNC4(w + B_CL + i, th + OFF_CL_B + i);
+        OO_CP_ASYNC4(w + B_CP + i, th + OFF_CP_B + i);
     }
-    for (int i = tid; i < 3 * H; i += NTHREADS) w[W_OC + i] = OO_LDG(th + OFF_OC_W + i);
-    for (int i = tid; i < 64; i += NTHREADS) w[W_PE + i] = i < NDIR * 3 ? OO_LDG(th + OFF_PE_B + i) : 0.f;
+    for (int i = tid; i < 3 * H; i += NTHREADS) OO_CP_ASYNC4(w + W_OC + i, th + OFF_OC_W + i);
+    for (int i = tid; i < 64; i += NTHREADS) {
+        if (i < NDIR * 3) OO_CP_ASYNC4(w + W_PE + i, th + OFF_PE_B + i);
+        else w[W_PE + i] = 0.f;
+    }
     if (tid < 4) {
         w[B_A + tid] = tid < 1 ? OO_LDG(th + OFF_A_B) : 0.f;
         w[B_OC + tid] = tid < 3 ? OO_LDG(th + OFF_OC_B + tid) : 0.f;
     }
+    OO_CP_ASYNC_WAIT();        // the caller's block barrier publishes the copies
 }
 
 // Per-object constants of the out_clip layer, computed once per object and step by k_gram (one CTA per object, before
