@@ -874,6 +874,10 @@ static int launch_k4(float* theta, float* am, float* av, int n_obj, const oo_bat
         static size_t attr_smem = 0;
         if (smem > attr_smem) {
             OO_CUDA(cudaFuncSetAttribute(k_update<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+            // same L1 / shared-memory split as k_train (which needs the maximum): no SM reconfiguration between the two
+            // kernels of a step
+            OO_CUDA(cudaFuncSetAttribute(k_update<true>, cudaFuncAttributePreferredSharedMemoryCarveout, cudaSharedmemCarveoutMaxShared));
+            OO_CUDA(cudaFuncSetAttribute(k_update<false>, cudaFuncAttributePreferredSharedMemoryCarveout, cudaSharedmemCarveoutMaxShared));
             attr_smem = smem;
         }
         const float decay = (float)(1.0 - (double)lr * (double)wd);

@@ -36,13 +36,38 @@ class Scene:
         self.batch = None
         # the separate background model (train.py:236-242): one hidden-128 model, not part of the vmap ensemble; it lives
         # on the last rank (the ensemble's round-robin starts at rank 0)
+        self._copy_stream = None
         self.scene_bg, self.bg, self.bg_batch, self.bg_tables = None, None, None, None
         self.bg_rank = world - 1
+
+    # ---- host -> device staging of the NEXT frame on a copy stream (what a DataLoader with pin_memory + non_blocking
+    # copies gives the reference, train.py:158-188): the 76 MB of a Replica frame travel while the current frame trains
+    def stage_frame(self, sample):
+        """Start the H2D copies of `sample` (pinned host tensors) on the copy stream; returns a dict to pass to
+        add_frame.  Tensors already on the device pass through."""
+        if self._copy_stream is None:
+            self._copy_stream = torch.cuda.Stream(device=self.device)
+        out = dict(sample)
+        with torch.cuda.stream(self._copy_stream):
+            for k in ("image", "depth", "obj", "T", "part_feat"):
+                v = sample.get(k)
+                if torch.is_tensor(v) and v.device != self.device:
+                    out[k] = v.to(self.device, non_blocking=True)
+            ev = torch.cuda.Event()
+            ev.record(self._copy_stream)
+        out["_staged"] = ev
+        return out
 
     # ---- train.py:164-256 ---------------------------------------------------------------------------------
     def add_frame(self, sample):
         cfg, dev = self.cfg, self.device
         nb = dict(non_blocking=True)
+        if "_staged" in sample:
+            cur = torch.cuda.current_stream(dev)
+            cur.wait_event(sample["_staged"])
+            for k in ("image", "depth", "obj", "T", "part_feat"):     # allocated on the copy stream, consumed on this one
+                if torch.is_tensor(sample.get(k)) and sample[k].is_cuda:
+                    sample[k].record_stream(cur)
         rgb, depth = sample["image"].to(dev, **nb), sample["depth"].to(dev, **nb)
         inst = sample["obj"].to(dev, **nb)
         twc = sample["T"].to(dev, **nb)
