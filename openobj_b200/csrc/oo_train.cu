@@ -443,7 +443,7 @@ __global__ void k_adamw_flat(float* __restrict__ p, const float* __restrict__ g,
 //   (c) the out_clip constants K1 needs in the NEXT step (k_gram: G = W^T W, wb = W^T b, bb = b.b of the UPDATED layer):
 //       each CTA forms the partial product of its 128 rows, the last CTA of an object to arrive sums the four partials
 //       in a fixed order (deterministic).
-// grid = (4 chunks of 128 out_clip rows, n_obj), 256 threads: thread = (row tid / 2, 16 columns).
+// grid = (4 chunks of 128 out_clip rows, n_obj), 256 threads: thread = a 4 x 4 block of the chunk's [128 x 32] gradient.
 constexpr int UPD_CHUNKS = 4, UPD_ROWS = C / UPD_CHUNKS, UPD_THREADS = 256;
 constexpr int GPART = 1092;                   // 33 x 33 partial Gram matrix, padded
 constexpr int UPD_WN = UPD_ROWS * GS;         // staged updated rows [128][36]
@@ -503,7 +503,7 @@ __global__ void __launch_bounds__(UPD_THREADS, 2) k_update(float* theta, float* 
     float* wn = rec + (size_t)cg.R * RAYREC;
     float* ys = wn + UPD_WN;
     float* gp = ys;                         // reused once the gradient is formed
-    const int c_lo = UPD_ROWS * chunk, cl = tid >> 1, j0 = 16 * (tid & 1), cc = c_lo + cl;
+    const int c_lo = UPD_ROWS * chunk;
     float* th = theta + (size_t)o * PSTRIDE;
     const bool clip_on = PART && scal[GROUP_CLIP * 4] != 0.f;
     const float* src = PART ? cg.rayrec + (size_t)o * cg.R * RAYREC : nullptr;
@@ -629,68 +629,98 @@ __global__ void __launch_bounds__(UPD_THREADS, 2) k_update(float* theta, float* 
             const int i = q / (RAYREC / 4), e = q - i * (RAYREC / 4);
             OO_CP_ASYNC16(rec + i * RAYREC + 4 * e, src + (size_t)act[i] * RAYREC + 4 * e);
         }
-        // moments of this thread's 16 weights (and of the row's bias): in flight during the gather
-        const size_t idx = (size_t)o * PSTRIDE + OFF_OCL_W + cc * H + j0;
-        const size_t ib = (size_t)o * PSTRIDE + OFF_OCL_B + cc;
+        // compute mapping: thread (tr = tid / 8, tc = tid % 8) owns the 4 x 4 block rows 4 tr.., columns 4 tc.. of the chunk's
+        // [128 x 32] gradient (two 128-bit shared loads per 16 FMA).  Its moments travel during the gather.
+        const int tr = tid >> 3, tc = tid & 7;
         float4 m4[4], v4r[4];
+        float mb[4] = {0.f, 0.f, 0.f, 0.f}, vb[4] = {0.f, 0.f, 0.f, 0.f};
 #pragma unroll
-        for (int q4 = 0; q4 < 4; ++q4) {
-            m4[q4] = *reinterpret_cast<const float4*>(am + idx + 4 * q4);
-            v4r[q4] = *reinterpret_cast<const float4*>(av + idx + 4 * q4);
+        for (int r = 0; r < 4; ++r) {
+            const size_t idx = (size_t)o * PSTRIDE + OFF_OCL_W + (size_t)(c_lo + 4 * tr + r) * H + 4 * tc;
+            m4[r] = *reinterpret_cast<const float4*>(am + idx);
+            v4r[r] = *reinterpret_cast<const float4*>(av + idx);
+            if (tc == 0) {
+                const size_t ib = (size_t)o * PSTRIDE + OFF_OCL_B + c_lo + 4 * tr + r;
+                mb[r] = am[ib]; vb[r] = av[ib];
+            }
         }
-        float mb = 0.f, vb = 0.f;
-        if ((tid & 1) == 0) { mb = am[ib]; vb = av[ib]; }
         OO_CP_ASYNC_WAIT();
         __syncthreads();
-        float g[16], gb = 0.f;
+        // records -> B'_i = A_i [opac_i, S_i]: the gradient is then a plain product  g[row][j] = sum_i y_i[row] B'_i[j]
+        for (int q = tid; q < n_act * (H + 1); q += UPD_THREADS) {
+            const int i = q / (H + 1), e = q - i * (H + 1);
+            const float Ai = rec[i * RAYREC + REC_A];
+            if (e < H) rec[i * RAYREC + REC_S + e] *= Ai;
+            else rec[i * RAYREC + 2] = Ai * rec[i * RAYREC + REC_OPAC];
+        }
+        __syncthreads();
+        float g[4][4], gb[4] = {0.f, 0.f, 0.f, 0.f};
 #pragma unroll
-        for (int q = 0; q < 16; ++q) g[q] = 0.f;
-#pragma unroll 2
+        for (int r = 0; r < 4; ++r) g[r][0] = g[r][1] = g[r][2] = g[r][3] = 0.f;
+#pragma unroll 4
         for (int i = 0; i < n_act; ++i) {
-            const float ay = rec[i * RAYREC + REC_A] * ys[i * UPD_ROWS + cl];
-            const float* Sp = rec + i * RAYREC + REC_S + j0;
+            const float4 y4 = *reinterpret_cast<const float4*>(ys + i * UPD_ROWS + 4 * tr);
+            const float4 b4 = *reinterpret_cast<const float4*>(rec + i * RAYREC + REC_S + 4 * tc);
+            const float yv[4] = {y4.x, y4.y, y4.z, y4.w};
 #pragma unroll
-            for (int q4 = 0; q4 < 16; q4 += 4) {
-                const float4 S4 = *reinterpret_cast<const float4*>(Sp + q4);
-                g[q4] += ay * S4.x; g[q4 + 1] += ay * S4.y; g[q4 + 2] += ay * S4.z; g[q4 + 3] += ay * S4.w;
+            for (int r = 0; r < 4; ++r) {
+                g[r][0] += yv[r] * b4.x; g[r][1] += yv[r] * b4.y; g[r][2] += yv[r] * b4.z; g[r][3] += yv[r] * b4.w;
             }
-            gb += ay * rec[i * RAYREC + REC_OPAC];
-        }
-        float wm = 0.f;
-        const float* wrow = wn + cl * GS;
-#pragma unroll 8
-        for (int k = 0; k < H; ++k) {
-            const float wk = wrow[k];
-            const float* M = sh + k * H + j0;
+            if (tc == 0) {
+                const float bo = rec[i * RAYREC + 2];
 #pragma unroll
-            for (int q4 = 0; q4 < 16; q4 += 4) {
-                const float4 M4 = *reinterpret_cast<const float4*>(M + q4);
-                g[q4] += wk * M4.x; g[q4 + 1] += wk * M4.y; g[q4 + 2] += wk * M4.z; g[q4 + 3] += wk * M4.w;
+                for (int r = 0; r < 4; ++r) gb[r] += yv[r] * bo;
             }
-            wm += wk * sh[1024 + k];
         }
-        float bc = wrow[H];
+        // + W M + b m^T  (and W m + b beta for the bias)
+        float wm[4] = {0.f, 0.f, 0.f, 0.f};
+#pragma unroll 2
+        for (int k4 = 0; k4 < H; k4 += 4) {
+            float4 wr4[4];
 #pragma unroll
-        for (int q = 0; q < 16; ++q) g[q] += bc * sh[1024 + j0 + q];
-        gb += wm + bc * sh[1056];
-        __syncthreads();                     // every thread has read its row of wn (and ys) before anything is overwritten
+            for (int r = 0; r < 4; ++r) wr4[r] = *reinterpret_cast<const float4*>(wn + (4 * tr + r) * GS + k4);
+#pragma unroll
+            for (int kk = 0; kk < 4; ++kk) {
+                const float4 M4 = *reinterpret_cast<const float4*>(sh + (k4 + kk) * H + 4 * tc);
+                const float mk = sh[1024 + k4 + kk];
+#pragma unroll
+                for (int r = 0; r < 4; ++r) {
+                    const float wk = kk == 0 ? wr4[r].x : kk == 1 ? wr4[r].y : kk == 2 ? wr4[r].z : wr4[r].w;
+                    g[r][0] += wk * M4.x; g[r][1] += wk * M4.y; g[r][2] += wk * M4.z; g[r][3] += wk * M4.w;
+                    wm[r] += wk * mk;
+                }
+            }
+        }
+        float bcr[4];
+        const float4 mj = *reinterpret_cast<const float4*>(sh + 1024 + 4 * tc);
+#pragma unroll
+        for (int r = 0; r < 4; ++r) {
+            bcr[r] = wn[(4 * tr + r) * GS + H];
+            g[r][0] += bcr[r] * mj.x; g[r][1] += bcr[r] * mj.y; g[r][2] += bcr[r] * mj.z; g[r][3] += bcr[r] * mj.w;
+            gb[r] += wm[r] + bcr[r] * sh[1056];
+        }
+        __syncthreads();                     // every thread has read its rows of wn (and ys) before anything is overwritten
         const float step = scal[GROUP_CLIP * 4 + 1], bc2s = scal[GROUP_CLIP * 4 + 2];
 #pragma unroll
-        for (int q4 = 0; q4 < 4; ++q4) {
-            float4 pw = *reinterpret_cast<const float4*>(wrow + j0 + 4 * q4);
-            adam1(pw.x, m4[q4].x, v4r[q4].x, g[4 * q4], decay, b1, b2, eps, step, bc2s);
-            adam1(pw.y, m4[q4].y, v4r[q4].y, g[4 * q4 + 1], decay, b1, b2, eps, step, bc2s);
-            adam1(pw.z, m4[q4].z, v4r[q4].z, g[4 * q4 + 2], decay, b1, b2, eps, step, bc2s);
-            adam1(pw.w, m4[q4].w, v4r[q4].w, g[4 * q4 + 3], decay, b1, b2, eps, step, bc2s);
-            *reinterpret_cast<float4*>(wn + cl * GS + j0 + 4 * q4) = pw;
-            *reinterpret_cast<float4*>(theta + idx + 4 * q4) = pw;
-            *reinterpret_cast<float4*>(am + idx + 4 * q4) = m4[q4];
-            *reinterpret_cast<float4*>(av + idx + 4 * q4) = v4r[q4];
-        }
-        if ((tid & 1) == 0) {
-            adam1(bc, mb, vb, gb, decay, b1, b2, eps, step, bc2s);
-            wn[cl * GS + H] = bc;
-            theta[ib] = bc; am[ib] = mb; av[ib] = vb;
+        for (int r = 0; r < 4; ++r) {
+            const int row = 4 * tr + r;
+            const size_t idx = (size_t)o * PSTRIDE + OFF_OCL_W + (size_t)(c_lo + row) * H + 4 * tc;
+            float4 pw = *reinterpret_cast<const float4*>(wn + row * GS + 4 * tc);
+            adam1(pw.x, m4[r].x, v4r[r].x, g[r][0], decay, b1, b2, eps, step, bc2s);
+            adam1(pw.y, m4[r].y, v4r[r].y, g[r][1], decay, b1, b2, eps, step, bc2s);
+            adam1(pw.z, m4[r].z, v4r[r].z, g[r][2], decay, b1, b2, eps, step, bc2s);
+            adam1(pw.w, m4[r].w, v4r[r].w, g[r][3], decay, b1, b2, eps, step, bc2s);
+            *reinterpret_cast<float4*>(wn + row * GS + 4 * tc) = pw;
+            *reinterpret_cast<float4*>(theta + idx) = pw;
+            *reinterpret_cast<float4*>(am + idx) = m4[r];
+            *reinterpret_cast<float4*>(av + idx) = v4r[r];
+            if (tc == 0) {
+                const size_t ib = (size_t)o * PSTRIDE + OFF_OCL_B + c_lo + row;
+                float bc = bcr[r];
+                adam1(bc, mb[r], vb[r], gb[r], decay, b1, b2, eps, step, bc2s);
+                wn[row * GS + H] = bc;
+                theta[ib] = bc; am[ib] = mb[r]; av[ib] = vb[r];
+            }
         }
     } else {
         OO_CP_ASYNC_WAIT();
