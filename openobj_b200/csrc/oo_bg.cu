@@ -74,32 +74,61 @@ __device__ __forceinline__ float gemm_epilogue(const GemmOp& g, int i, int j, fl
     return v;
 }
 
+// AC / BC: the contraction index is the contiguous one of A / B (compile-time so that the tile loaders have no
+// run-time index arithmetic).  The next k-tile is fetched into registers while the current one is multiplied.
+template <bool AC, bool BC>
 __global__ void __launch_bounds__(256, 2) k_gemm(const GemmOp g) {
     __shared__ __align__(16) float As[BK][LDA_S];
     __shared__ __align__(16) float Bs[BK][LDB_S];
     const int tid = threadIdx.x, i0 = blockIdx.x * BI, j0 = blockIdx.y * BJ;
     const int c_begin = blockIdx.z * g.chunk, c_end = min(g.K, c_begin + g.chunk);
     const int ty = tid >> 4, tx = tid & 15;
+    constexpr int NA = BI * BK / 256, NB_ = BJ * BK / 256;
+    // this thread's elements of the A / B tiles: (ii, cc) pairs and their global offsets (without the k-tile offset)
+    int a_ii[NA], a_cc[NA], b_jj[NB_], b_cc[NB_];
+    int a_off[NA], b_off[NB_];                    // element offsets fit 32 bits (checked in run_gemm)
+    bool a_ok[NA], b_ok[NB_], b_one[NB_];
+#pragma unroll
+    for (int u = 0; u < NA; ++u) {
+        const int e = tid + 256 * u;
+        a_ii[u] = AC ? e / BK : e % BI;
+        a_cc[u] = AC ? e % BK : e / BI;
+        a_ok[u] = i0 + a_ii[u] < g.I;
+        a_off[u] = (int)((i0 + a_ii[u]) * g.sai + a_cc[u] * g.sac);
+    }
+#pragma unroll
+    for (int u = 0; u < NB_; ++u) {
+        const int e = tid + 256 * u;
+        b_jj[u] = BC ? e / BK : e % BJ;
+        b_cc[u] = BC ? e % BK : e / BJ;
+        const int j = j0 + b_jj[u];
+        b_ok[u] = j < g.J;
+        b_one[u] = j == g.J && g.ones_out != nullptr;
+        b_off[u] = (int)(j * g.sbj + b_cc[u] * g.sbc);
+    }
     float acc[8][4];
 #pragma unroll
     for (int a = 0; a < 8; ++a) acc[a][0] = acc[a][1] = acc[a][2] = acc[a][3] = 0.f;
-    const bool a_c_fast = g.sac == 1, b_c_fast = g.sbc == 1;      // which index is contiguous in memory
+    float ra[NA], rb[NB_];
+    const int sac = (int)g.sac, sbc = (int)g.sbc;
+    auto fetch = [&](int c0) {
+#pragma unroll
+        for (int u = 0; u < NA; ++u)
+            ra[u] = (a_ok[u] && c0 + a_cc[u] < c_end) ? g.A[a_off[u] + c0 * sac] : 0.f;
+#pragma unroll
+        for (int u = 0; u < NB_; ++u) {
+            const bool in = c0 + b_cc[u] < c_end;
+            rb[u] = in ? (b_ok[u] ? g.B[b_off[u] + c0 * sbc] : (b_one[u] ? 1.f : 0.f)) : 0.f;
+        }
+    };
+    fetch(c_begin);
     for (int c0 = c_begin; c0 < c_end; c0 += BK) {
 #pragma unroll
-        for (int u = 0; u < BI * BK / 256; ++u) {
-            const int e = tid + 256 * u;
-            const int ii = a_c_fast ? e / BK : e % BI, cc = a_c_fast ? e % BK : e / BI;
-            const int i = i0 + ii, c = c0 + cc;
-            As[cc][ii] = (i < g.I && c < c_end) ? g.A[i * g.sai + c * g.sac] : 0.f;
-        }
+        for (int u = 0; u < NA; ++u) As[a_cc[u]][a_ii[u]] = ra[u];
 #pragma unroll
-        for (int u = 0; u < BJ * BK / 256; ++u) {
-            const int e = tid + 256 * u;
-            const int jj = b_c_fast ? e / BK : e % BJ, cc = b_c_fast ? e % BK : e / BJ;
-            const int j = j0 + jj, c = c0 + cc;
-            Bs[cc][jj] = c < c_end ? (j < g.J ? g.B[j * g.sbj + c * g.sbc] : (j == g.J && g.ones_out != nullptr ? 1.f : 0.f)) : 0.f;
-        }
+        for (int u = 0; u < NB_; ++u) Bs[b_cc[u]][b_jj[u]] = rb[u];
         __syncthreads();
+        if (c0 + BK < c_end) fetch(c0 + BK);          // in flight during the multiply
 #pragma unroll
         for (int k = 0; k < BK; ++k) {
             const float4 a0 = *reinterpret_cast<const float4*>(&As[k][8 * ty]);
@@ -156,8 +185,15 @@ int run_gemm(GemmOp g, int split, float* part, cudaStream_t st) {
         g.split = (g.K + g.chunk - 1) / g.chunk;
     }
     const int je = g.J + (g.ones_out != nullptr ? 1 : 0);
+    OO_REQUIRE((long long)g.I * (g.sai > 0 ? g.sai : 1) + (long long)g.K * (g.sac > 0 ? g.sac : 1) < (1LL << 31) &&
+                   (long long)je * (g.sbj > 0 ? g.sbj : 1) + (long long)g.K * (g.sbc > 0 ? g.sbc : 1) < (1LL << 31),
+               "oo_bg gemm: operand larger than 2^31 elements");
     const dim3 grid((g.I + BI - 1) / BI, (je + BJ - 1) / BJ, g.split);
-    k_gemm<<<grid, 256, 0, st>>>(g);
+    const bool ac = g.sac == 1, bc = g.sbc == 1;
+    if (ac && bc) k_gemm<true, true><<<grid, 256, 0, st>>>(g);
+    else if (ac) k_gemm<true, false><<<grid, 256, 0, st>>>(g);
+    else if (bc) k_gemm<false, true><<<grid, 256, 0, st>>>(g);
+    else k_gemm<false, false><<<grid, 256, 0, st>>>(g);
     OO_LAUNCH_CHECK();
     if (g.split > 1) {
         k_gemm_reduce<<<(g.I * je + 255) / 256, 256, 0, st>>>(g);
