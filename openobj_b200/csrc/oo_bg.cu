@@ -164,13 +164,19 @@ __global__ void __launch_bounds__(256, 2) k_gemm(const GemmOp g) {
     }
 }
 
-__global__ void k_gemm_reduce(const GemmOp g) {
-    const int e = blockIdx.x * blockDim.x + threadIdx.x, je = gemm_je(g);
-    if (e >= g.I * je) return;
-    const int i = e / je, j = e - i * je;
+// fixed-order reduction of the split partials: eight lanes per output element, lane q sums z = q, q + 8, ... in order and
+// the eight sums are combined by a shuffle tree (deterministic; eight times shorter load chains than one thread per element)
+__global__ void __launch_bounds__(256) k_gemm_reduce(const GemmOp g) {
+    const int je = gemm_je(g), n = g.I * je;
+    const int e = (blockIdx.x * blockDim.x + threadIdx.x) >> 3, q = threadIdx.x & 7;
     float s = 0.f;
-#pragma unroll 8
-    for (int z = 0; z < g.split; ++z) s += g.part[(size_t)z * g.I * je + e];        // fixed order: deterministic
+    if (e < n)
+        for (int z = q; z < g.split; z += 8) s += g.part[(size_t)z * n + e];
+    s += __shfl_xor_sync(0xffffffffu, s, 1);
+    s += __shfl_xor_sync(0xffffffffu, s, 2);
+    s += __shfl_xor_sync(0xffffffffu, s, 4);
+    if (e >= n || q != 0) return;
+    const int i = e / je, j = e - i * je;
     float* dst = gemm_dst(g, i, j);
     const float v = gemm_epilogue(g, i, j, s);
     *dst = g.accumulate ? *dst + v : v;
@@ -196,7 +202,7 @@ int run_gemm(GemmOp g, int split, float* part, cudaStream_t st) {
     else k_gemm<false, false><<<grid, 256, 0, st>>>(g);
     OO_LAUNCH_CHECK();
     if (g.split > 1) {
-        k_gemm_reduce<<<(g.I * je + 255) / 256, 256, 0, st>>>(g);
+        k_gemm_reduce<<<(g.I * je * 8 + 255) / 256, 256, 0, st>>>(g);
         OO_LAUNCH_CHECK();
     }
     return 0;
@@ -281,12 +287,15 @@ __global__ void __launch_bounds__(NDIR * 4) k_embed_bwd(const float* __restrict_
     }
 }
 
-__global__ void k_embed_bwd_reduce(const float* __restrict__ partial, int nblk, float* __restrict__ dB) {
-    const int e = threadIdx.x;
+__global__ void __launch_bounds__(256) k_embed_bwd_reduce(const float* __restrict__ partial, int nblk, float* __restrict__ dB) {
+    // one warp per output element: lane l sums blocks l, l + 32, ... in order, then a shuffle tree (fixed order)
+    const int e = blockIdx.x * 8 + (threadIdx.x >> 5), lane = threadIdx.x & 31;
     if (e >= NDIR * 3) return;
     float s = 0.f;
-    for (int b = 0; b < nblk; ++b) s += partial[(size_t)b * (NDIR * 3) + e];
-    dB[e] = s;
+    for (int b = lane; b < nblk; b += 32) s += partial[(size_t)b * (NDIR * 3) + e];
+#pragma unroll
+    for (int o = 16; o > 0; o >>= 1) s += __shfl_xor_sync(0xffffffffu, s, o);
+    if (lane == 0) dB[e] = s;
 }
 
 // ------------------------------------------------------------------------------------------------
@@ -534,7 +543,7 @@ extern "C" int oo_bg_train_step(float* theta, float* adam_m, float* adam_v, int 
         const int nblk = (M + EB_PTS - 1) / EB_PTS;
         k_embed_bwd<<<nblk, NDIR * 4, 0, st>>>(pcs, th + L.off[T_PE], scale, M, gb, w.emb_part);
         OO_LAUNCH_CHECK();
-        k_embed_bwd_reduce<<<1, 64, 0, st>>>(w.emb_part, nblk, G + L.off[T_PE]);
+        k_embed_bwd_reduce<<<(NDIR * 3 + 7) / 8, 256, 0, st>>>(w.emb_part, nblk, G + L.off[T_PE]);
         OO_LAUNCH_CHECK();
     }
     if (grads_out) return 0;
