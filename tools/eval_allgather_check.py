@@ -1,0 +1,62 @@
+"""2-GPU check of the full-frame evaluation path: objects sharded k % G, per-object K5 renders,
+NCCL all-gather of depth / rgb / mask, replicated K6 merge in global insertion order, winner-only feature exchange.
+Every rank also renders ALL objects alone (singleton process group) and the two results must be identical.
+
+    python -m torch.distributed.run --nproc-per-node 2 --master-addr 127.0.0.1 tools/eval_allgather_check.py"""
+import json
+import os
+import sys
+
+import numpy as np
+import torch
+import torch.distributed as dist
+
+sys.path.insert(0, ".")
+from openobj_b200 import cfg as C, dist as D, eval as E, utils as U, vmap as V
+
+rank, world, local = D.init_from_env()
+torch.cuda.set_device(local)
+dev = torch.device("cuda", local)
+solo = None
+for r in range(world):                       # singleton groups (collective call on every rank)
+    g = dist.new_group(ranks=[r])
+    if r == rank:
+        solo = g
+W, H, N = 240, 136, 5
+cfg = C.room0_config(w=W, h=H)
+cfg.training_device = cfg.data_device = str(dev)
+cfg.fx = cfg.fy = 120.0
+cfg.cx, cfg.cy = (W - 1) / 2.0, (H - 1) / 2.0
+cam = V.cameraInfo(cfg)
+torch.manual_seed(7)                          # same initial weights on every rank
+objs = []
+for k in range(N):
+    o = V.sceneObject(cfg, k + 1, torch.zeros(W, H, 3, dtype=torch.uint8, device=dev), torch.ones(W, H, device=dev),
+                      torch.ones(W, H, dtype=torch.uint8, device=dev), torch.tensor([0, W - 1, 0, H - 1]), torch.eye(4), 0)
+    with torch.no_grad():
+        o.trainer.fc_occ_map.out_alpha.bias.fill_(0.6 + 0.1 * k)
+    bb = U.BoundingBox()
+    bb.R, bb.center, bb.extent = np.eye(3), np.array([-0.6 + 0.3 * k, 0.05 * k, 2.0 + 0.25 * k]), np.array([0.9, 0.8, 0.7])
+    o.bbox3dour = bb
+    objs.append(o)
+jit = torch.rand(W * H, 150, generator=torch.Generator().manual_seed(3)).to(dev)
+real_rand = torch.rand
+torch.rand = lambda *a, **k: jit if a[:2] == (W * H, 150) else real_rand(*a, **k)     # the same jitter rows for every render
+T = np.eye(4)
+is_bg = {0: True}
+ref = E.render_frame(objs, T, cam.rays_dir_cache, is_bg=is_bg, render_feat=True, group=solo)
+mine = [o for k, o in enumerate(objs) if k % world == rank]
+got = E.render_frame(mine, T, cam.rays_dir_cache, is_bg=is_bg, render_feat=True)
+torch.rand = real_rand
+torch.cuda.synchronize()
+ok = dict(depth=bool(torch.equal(ref[0], got[0])), rgb=bool(torch.equal(ref[1], got[1])), winner=bool(torch.equal(ref[2], got[2])),
+          feat=bool(torch.allclose(ref[3], got[3], rtol=0, atol=0)), covered=float((got[2] >= 0).float().mean()),
+          winners=sorted(set(got[2].flatten().tolist())))
+res = [None] * world
+dist.all_gather_object(res, ok)
+if rank == 0:
+    print(json.dumps({"world": world, "ranks": res}))
+    assert all(r["depth"] and r["rgb"] and r["winner"] and r["feat"] for r in res), res
+    assert res[0]["covered"] > 0.05 and len(res[0]["winners"]) >= 3, "the check scene must actually render something"
+dist.barrier()
+dist.destroy_process_group()
