@@ -114,7 +114,8 @@ constexpr int SM_FEAT = SM_UPART + H * RP;           // Y [10][512]: gt part fea
 constexpr int YSTR = C + 4;                          // row stride of Y: YSTR % 32 == 4 -> conflict-free A fragments in phase 10
 constexpr int SM_YS = SM_FEAT + RT * YSTR;              // gt-feature statistics: partials [10][16 warps][2], totals [2][12]
 constexpr int SM_FROW = SM_YS + 352;                 // int [12]: feature-table rows of the tile's rays (phase 0 -> phase 1)
-constexpr int SM_TOTAL = SM_FROW + 12;               // floats
+constexpr int SM_G = SM_FROW + 12;                   // G = W_ocl^T W_ocl [32][32] of the current object (stage_derived)
+constexpr int SM_TOTAL = SM_G + H * H;               // floats
 // ray-value rows
 constexpr int V_DEPTH = 0, V_OPAC = 1, V_COL = 2, V_GD = 5, V_GO = 6, V_GC = 7, V_CF = 10, V_BG = 11,
               V_LD = 12, V_LC = 13, V_LO = 14, V_LF = 15, V_A = 16, V_B = 17, V_ZSRC = 18,
@@ -122,7 +123,11 @@ constexpr int V_DEPTH = 0, V_OPAC = 1, V_COL = 2, V_GD = 5, V_GO = 6, V_GC = 7, 
               V_WB = 24;                               // W_ocl^T b_ocl [32] and b.b [1] of the current object (gram_stage)
 
 static_assert(SM_TOTAL * 4 <= 232448, "tile does not fit in 227 KB of shared memory");
-static_assert(PS % 4 == 0 && SM_W % 4 == 0 && SM_RAY % 4 == 0 && SM_FEAT % 4 == 0, "float4 alignment");
+static_assert(PS % 4 == 0 && SM_W % 4 == 0 && SM_RAY % 4 == 0 && SM_FEAT % 4 == 0 && SM_G % 4 == 0, "float4 alignment");
+// owner threads of the small accumulators, spread so that no warp carries more than one of the side jobs of the fused
+// phase 42: M (256 threads from M_T0), out_color / out_alpha weights (128 threads from OC_T0), m / beta (threads 0..32)
+constexpr int M_T0 = 128, OC_T0 = 384;
+static_assert(OC_T0 + 4 * H <= NTHREADS && M_T0 + 8 * H <= OC_T0, "owner-thread ranges");
 
 // per-object constants derived from the out_clip layer (k_gram): G = W^T W [32][32], wb = W^T b [32], bb = b.b
 constexpr int DER_G = 0, DER_WB = 1024, DER_BB = 1056, DERIVED = 1088;

@@ -597,6 +597,8 @@ OO_DEV void gram_stage(int tid, float* __restrict__ sm, const float* __restrict_
 // W_ocl^T b_ocl and b.b of the object a CTA starts working on: global (k_gram) -> the per-object rows of the ray-value area
 OO_DEV void stage_derived(int tid, float* __restrict__ sm, const float* __restrict__ der) {
     if (tid <= H) sm[SM_RV + V_WB * RP + tid] = OO_LDG(der + DER_WB + tid);      // DER_BB == DER_WB + H
+    if (tid < H * H / 4) OO_CP_ASYNC16(sm + SM_G + 4 * tid, der + DER_G + 4 * tid);
+    OO_CP_ASYNC_WAIT();        // the caller's block barrier publishes the copies
 }
 
 // zero the pad rows of e1 / e2 and the spare rows once per kernel
@@ -945,7 +947,7 @@ OO_DEV void tile_phase(int tid, float* __restrict__ sm, const TileCtx& c, TileAc
                 const float wbj = rv[V_WB * RP + lane];
                 float gk[H];
 #pragma unroll
-                for (int k = 0; k < H; ++k) gk[k] = c.derived[DER_G + k * H + lane];      // G is symmetric: coalesced over j
+                for (int k = 0; k < H; ++k) gk[k] = sm[SM_G + k * H + lane];             // G is symmetric: conflict-free over j
                 float gs = opac * wbj;
 #pragma unroll
                 for (int k = 0; k < H; ++k) gs += gk[k] * __shfl_sync(FULL, sj, k);
@@ -1015,9 +1017,9 @@ OO_DEV void tile_phase(int tid, float* __restrict__ sm, const TileCtx& c, TileAc
         // ---- fused: M / m / beta accumulators (phase 13), out_color / out_alpha weight gradients and d(hp_pre) (phase 18),
         // then (after a block barrier: it overwrites the hc rows the out_color weight gradient reads) d(hc_pre) (phase 19)
         if (PART) {
-            if (tid < 8 * H) {
+            if (tid >= M_T0 && tid < M_T0 + 8 * H) {
                 OO_ACC(g_gm, 4, AC_GM);
-                const int k = tid >> 3, j4 = 4 * (tid & 7);
+                const int k = (tid - M_T0) >> 3, j4 = 4 * ((tid - M_T0) & 7);
 #pragma unroll
                 for (int r = 0; r < RT; ++r) {
                     const float bs = rv[V_B * RP + r] * sm[SM_ST + k * RP + r];
@@ -1040,9 +1042,9 @@ OO_DEV void tile_phase(int tid, float* __restrict__ sm, const TileCtx& c, TileAc
                 OO_ACC_PUT(g_mv, 1, AC_MV);
             }
         }
-        if (tid < 4 * H) {
+        if (tid >= OC_T0 && tid < OC_T0 + 4 * H) {
             OO_ACC(g_oc, 1, AC_OC);
-            const int o = tid >> 5, j = tid & 31;
+            const int o = (tid - OC_T0) >> 5, j = tid & 31;
             const float* dy = misc + (o < 3 ? (M_DCOL + o) : M_DRAW) * PS;
             const float* x = act + ((o < 3 ? R_HC : R_H4) + j) * PS;
             float s0 = 0.f, s1 = 0.f, s2 = 0.f, s3 = 0.f;      // four independent chains
@@ -1365,9 +1367,9 @@ OO_DEV void tile_phase(int tid, float* __restrict__ sm, const TileCtx& c, TileAc
                 if (q < 2) c.rayrec[r * RAYREC + q] = q == REC_A ? rv[V_A * RP + r] : rv[V_OPAC * RP + r];
                 else c.rayrec[r * RAYREC + REC_S + q - 2] = sm[SM_ST + (q - 2) * RP + r];
             }
-            if (tid < 8 * H) {
+            if (tid >= M_T0 && tid < M_T0 + 8 * H) {
                 OO_ACC(g_gm, 4, AC_GM);
-                const int k = tid >> 3, j4 = 4 * (tid & 7);
+                const int k = (tid - M_T0) >> 3, j4 = 4 * ((tid - M_T0) & 7);
 #pragma unroll
                 for (int r = 0; r < RT; ++r) {
                     const float bs = rv[V_B * RP + r] * sm[SM_ST + k * RP + r];
@@ -1437,9 +1439,9 @@ OO_DEV void tile_phase(int tid, float* __restrict__ sm, const TileCtx& c, TileAc
         }
     } else if constexpr (PH == 18) {
         // out_color / out_alpha weight gradients (reduce over points) ...
-        if (tid < 4 * H) {
+        if (tid >= OC_T0 && tid < OC_T0 + 4 * H) {
             OO_ACC(g_oc, 1, AC_OC);
-            const int o = tid >> 5, j = tid & 31;
+            const int o = (tid - OC_T0) >> 5, j = tid & 31;
             const float* dy = misc + (o < 3 ? (M_DCOL + o) : M_DRAW) * PS;
             const float* x = act + ((o < 3 ? R_HC : R_H4) + j) * PS;
             float s0 = 0.f, s1 = 0.f, s2 = 0.f, s3 = 0.f;      // four independent chains
@@ -1650,8 +1652,8 @@ OO_DEV void tile_flush(int tid, float* __restrict__ sm, float* __restrict__ slab
         OO_ACC(g_oc, 1, AC_OC);
         OO_ACC(g_b, 1, AC_B);
         OO_ACC(g_pe, 1, AC_PE);
-        if (tid < 3 * H) slab[OFF_OC_W + tid] = g_oc[0];
-        else if (tid < 4 * H) slab[OFF_A_W + tid - 3 * H] = g_oc[0];
+        if (tid >= OC_T0 && tid < OC_T0 + 3 * H) slab[OFF_OC_W + tid - OC_T0] = g_oc[0];
+        else if (tid >= OC_T0 + 3 * H && tid < OC_T0 + 4 * H) slab[OFF_A_W + tid - OC_T0 - 3 * H] = g_oc[0];
         if (tid < 6 * H) {
             const int l = tid >> 5, j = tid & 31;
             const int off = l == 0 ? OFF_IN_B : l == 1 ? OFF_M1_B : l == 2 ? OFF_CAT_B : l == 3 ? OFF_M2_B
@@ -1666,7 +1668,7 @@ OO_DEV void tile_flush(int tid, float* __restrict__ sm, float* __restrict__ slab
         if (PART) {
             OO_ACC(g_gm, 4, AC_GM);
             OO_ACC(g_mv, 1, AC_MV);
-            if (tid < 8 * H) st4(slab + SLAB_M + 4 * tid, float4{g_gm[0], g_gm[1], g_gm[2], g_gm[3]});
+            if (tid >= M_T0 && tid < M_T0 + 8 * H) st4(slab + SLAB_M + 4 * (tid - M_T0), float4{g_gm[0], g_gm[1], g_gm[2], g_gm[3]});
             if (tid <= H) slab[SLAB_MV + tid] = g_mv[0];     // m[0..31], beta at SLAB_MV + 32 == SLAB_BETA
         }
         OO_ACC(loss, 4, AC_LOSS);
