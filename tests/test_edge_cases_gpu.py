@@ -137,3 +137,41 @@ def test_sampler_invariants_full_frame_size():
     ok = dz[..., 0] > 1e-3
     spread = (dirs - dirs[..., :1, :]).abs().amax(-1)
     assert float(spread[ok].max()) < 2e-3
+
+
+def test_scene_scannet_shape_part_features_off():
+    """BASELINE config 4 shape: 640x480 frames, part_mode off (the shipped ScanNet JSONs): the clip head gets no gradient,
+    so its parameters and moments stay untouched while everything else trains; staged (copy-stream) frames give the
+    same result as frames handed over directly."""
+    from openobj_b200 import cfg as C
+    from openobj_b200.scene import Scene
+    from openobj_b200.synthetic import SyntheticScene
+    from openobj_b200 import layout as Lo
+    res = []
+    for staged in (False, True):
+        torch.manual_seed(11)
+        cfg = C.room0_config()
+        cfg.do_bg = False
+        cfg.part_mode = False
+        cfg.W, cfg.H = 640, 480
+        cfg.fx = cfg.fy = 320.0
+        cfg.cx, cfg.cy = 319.5, 239.5
+        cfg.n_iter_per_frame = 10
+        synth = SyntheticScene(8, W=cfg.W, H=cfg.H, part_mode=False, seed=4, n_distinct=1, pin=True)
+        sc = Scene(cfg, seed=21, max_frames=4)
+        lt = torch.zeros(cfg.n_iter_per_frame, 8, 4, device=DEV)
+        for f in range(2):
+            fr = synth.frame(f)
+            sc.add_frame(sc.stage_frame(fr) if staged else fr)
+            sc.sample()
+            if f == 0:
+                clip0 = [Lo.views(sc.ens.theta)[i].clone() for i in (14, 15, 16, 17)]
+            sc.train(loss_terms=lt)
+        torch.cuda.synchronize()
+        assert bool(torch.isfinite(lt).all()) and float(lt[..., 3].abs().max()) == 0.0      # no feature term
+        for i, c0 in zip((14, 15, 16, 17), clip0):
+            assert torch.equal(Lo.views(sc.ens.theta)[i], c0)                                # clip head untouched (quirk 8)
+            assert float(Lo.views(sc.ens.m)[i].abs().max()) == 0.0
+        assert sc.ens.adam_t.cpu().tolist()[2] == 0 and sc.ens.adam_t.cpu().tolist()[0] == 2 * cfg.n_iter_per_frame
+        res.append((sc.ens.theta.clone(), lt.clone()))
+    assert torch.equal(res[0][0], res[1][0]) and torch.equal(res[0][1], res[1][1])
