@@ -30,6 +30,24 @@ struct TrainParams {
     long long* block_times;    // debug: [n_cta][3] = {globaltimer at block start, at block end, tiles} of the last launch
 };
 
+// Programmatic dependent launch: the two kernels of a step are launched with programmaticStreamSerialization, so the CTAs of
+// the next kernel become resident as soon as SMs free up and run their prologue (everything that does not depend on the
+// previous kernel's output) before pdl_wait(); a kernel releases its own dependents only AFTER its wait, so the chain
+// k_update(i-1) -> k_train(i) -> k_update(i) stays transitively ordered.
+__device__ __forceinline__ void pdl_wait() { asm volatile("griddepcontrol.wait;" ::: "memory"); }
+__device__ __forceinline__ void pdl_release() { asm volatile("griddepcontrol.launch_dependents;" ::: "memory"); }
+
+template <typename... KArgs, typename... Args>
+cudaError_t launch_pdl(void (*kernel)(KArgs...), dim3 grid, dim3 block, size_t smem, cudaStream_t st, Args... args) {
+    cudaLaunchConfig_t cfg = {};
+    cfg.gridDim = grid; cfg.blockDim = block; cfg.dynamicSmemBytes = smem; cfg.stream = st;
+    cudaLaunchAttribute at[1];
+    at[0].id = cudaLaunchAttributeProgrammaticStreamSerialization;
+    at[0].val.programmaticStreamSerializationAllowed = 1;
+    cfg.attrs = at; cfg.numAttrs = 1;
+    return cudaLaunchKernelEx(&cfg, kernel, KArgs(args)...);
+}
+
 long long* g_phase_cycles = nullptr;
 long long* g_block_times = nullptr;
 
@@ -121,6 +139,10 @@ __global__ void __launch_bounds__(NTHREADS, 1) k_train(const TrainParams prm) {
     };
     tile_ptrs(t_begin, c);
     float pre = tile_prefetch<PART>(tid, c);          // this thread's input value of the first tile
+    // everything above touches only this CTA's shared / tensor memory and per-frame constants; the parameters and the
+    // out_clip constants below come from the previous update kernel
+    pdl_wait();
+    pdl_release();
     int cur_obj = -1;
     for (int t = t_begin; t < t_end; ++t) {
         const int obj = t / prm.tiles_per_obj;
@@ -516,13 +538,6 @@ __global__ void __launch_bounds__(UPD_THREADS, 2) k_update(float* theta, float* 
         }
         if (tid < UPD_ROWS) *reinterpret_cast<float4*>(wn + tid * GS + H) = float4{th[OFF_OCL_B + c_lo + tid], 0.f, 0.f, 0.f};
     }
-    if (chunk == 0 && tid < 4 && loss_terms != nullptr) {
-        // per-object loss terms: masked mean = sum / (count + 1e-10)  (render_rays.py:108)
-        float s = 0.f;
-        for (int q = s0; q < s1; ++q) s += slot_loss[4 * q + tid];
-        const int n = counts[2 * o + (tid == 2 ? 1 : 0)];
-        loss_terms[4 * o + tid] = s / ((float)n + 1e-10f);
-    }
     // ---- (b) this CTA's quarter of the tensors whose gradient is the slot sum, and the slot sums of M, m, beta
     {
         constexpr int NV_LO = OFF_OCL_W / 4, NV = NV_LO + (PEND - OFF_PE_B) / 4, PER = (NV + UPD_CHUNKS - 1) / UPD_CHUNKS;
@@ -548,6 +563,17 @@ __global__ void __launch_bounds__(UPD_THREADS, 2) k_update(float* theta, float* 
         }
 #pragma unroll
         for (int u = 0; u < NM; ++u) tm[u] = 0.f;
+        // parameters, moments and the out_clip rows above were last written by the previous update kernel (complete: K1 only
+        // released this launch after its own wait); everything below reads what K1 wrote
+        pdl_wait();
+        pdl_release();
+        if (chunk == 0 && tid < 4 && loss_terms != nullptr) {
+            // per-object loss terms: masked mean = sum / (count + 1e-10)  (render_rays.py:108)
+            float s = 0.f;
+            for (int q = s0; q < s1; ++q) s += slot_loss[4 * q + tid];
+            const int n = counts[2 * o + (tid == 2 ? 1 : 0)];
+            loss_terms[4 * o + tid] = s / ((float)n + 1e-10f);
+        }
         for (int sl = s0; sl < s1; sl += 2) {            // slots summed in order, two per round trip
             const float* sp = slab + (size_t)sl * PSTRIDE;
             const bool two = sl + 1 < s1;
@@ -821,8 +847,8 @@ int launch_k1(const float* theta, int n_obj, const oo_batch* b, int it, int R, f
         k_gram<<<n_obj, NTHREADS, gsmem, st>>>(theta, ws->derived);
         OO_LAUNCH_CHECK();
     }
-    if (b->feat_row != nullptr) k_train<true><<<n_cta, NTHREADS, smem, st>>>(prm);
-    else k_train<false><<<n_cta, NTHREADS, smem, st>>>(prm);
+    if (b->feat_row != nullptr) OO_CUDA(launch_pdl(k_train<true>, dim3(n_cta), dim3(NTHREADS), smem, st, prm));
+    else OO_CUDA(launch_pdl(k_train<false>, dim3(n_cta), dim3(NTHREADS), smem, st, prm));
     OO_LAUNCH_CHECK();
     return 0;
 }
@@ -912,12 +938,16 @@ static int launch_k4(float* theta, float* am, float* av, int n_obj, const oo_bat
         }
         const float decay = (float)(1.0 - (double)lr * (double)wd);
         const dim3 ugrid(UPD_CHUNKS, n_obj);
+        const float* cslab = ws->slab;
+        const float* cslot = ws->slot_loss;
+        float* nullf = nullptr;
+        int* nulli = nullptr;
         if (part)
-            k_update<true><<<ugrid, UPD_THREADS, smem, st>>>(theta, am, av, ws->slab, obj_slot, scal, decay, b1, b2, eps, cg,
-                                                             ws->slot_loss, counts, loss_terms, ws->derived, ws->gram_part, ws->gram_cnt);
+            OO_CUDA(launch_pdl(k_update<true>, ugrid, dim3(UPD_THREADS), smem, st, theta, am, av, cslab, obj_slot, scal, decay, b1,
+                               b2, eps, cg, cslot, counts, loss_terms, ws->derived, ws->gram_part, ws->gram_cnt));
         else
-            k_update<false><<<ugrid, UPD_THREADS, 0, st>>>(theta, am, av, ws->slab, obj_slot, scal, decay, b1, b2, eps, cg,
-                                                            ws->slot_loss, counts, loss_terms, nullptr, nullptr, nullptr);
+            OO_CUDA(launch_pdl(k_update<false>, ugrid, dim3(UPD_THREADS), (size_t)0, st, theta, am, av, cslab, obj_slot, scal, decay,
+                               b1, b2, eps, cg, cslot, counts, loss_terms, nullf, nullf, nulli));
         OO_LAUNCH_CHECK();
         return 0;
     }
