@@ -8,6 +8,7 @@
 #include "oo_common.cuh"
 #include "oo_layout.h"
 
+
 using namespace oo;
 
 namespace {
@@ -37,8 +38,8 @@ enum { T_IN_W, T_IN_B, T_M1_W, T_M1_B, T_CAT_W, T_CAT_B, T_M2_W, T_M2_B, T_A_W, 
        T_CP_W, T_CP_B, T_OCL_W, T_OCL_B, T_PE };
 
 // ------------------------------------------------------------------------------------------------
-// generic FP32 GEMM:  C(i,j) (+)= epilogue( mult * sum_c A(i,c) B(j,c) + bias[j] ),  A(i,c) = A[i*sai + c*sac] etc.
-// CTA tile 128 x 64 x 16, 256 threads, 8 x 4 outputs per thread (32 FFMA per three 128-bit shared loads).
+// generic GEMM at fp32 accuracy:  C(i,j) (+)= epilogue( mult * sum_c A(i,c) B(j,c) + bias[j] ),  A(i,c) = A[i*sai + c*sac] etc.
+// CTA tile 128 x 64 x 16, 256 threads = 8 warps of 32 x 32 outputs on the tensor pipe (3 x TF32 mma.sync per product).
 // split > 1: grid.z chunks of the contraction write raw partial sums to part[z][I][J]; k_gemm_reduce finishes.
 // ------------------------------------------------------------------------------------------------
 struct GemmOp {
@@ -62,7 +63,20 @@ __device__ __forceinline__ float* gemm_dst(const GemmOp& g, int i, int j) {
     return j == g.J ? g.ones_out + i : g.C + i * g.sci + j * g.scj;
 }
 
-constexpr int BI = 128, BJ = 64, BK = 16, LDA_S = BI + 4, LDB_S = BJ + 4;
+// row strides = 8 mod 32 banks: the mma fragment loads (k = lane % 4, row = lane / 4) hit 32 different banks
+constexpr int BI = 128, BJ = 64, BK = 16, LDA_S = BI + 8, LDB_S = BJ + 8;
+
+// mma.sync m16n8k8 TF32 with three-term error compensation (x = hi + lo split in registers when the fragment is loaded;
+// lo*hi + hi*lo + hi*hi, fp32 accumulate): fp32-level agreement, the same arithmetic as the fused object tile (oo_tile.h)
+__device__ __forceinline__ void tf32_split(float x, uint32_t& hi, uint32_t& lo) {
+    hi = __float_as_uint(x) & 0xffffe000u;
+    lo = __float_as_uint(x - __uint_as_float(hi));
+}
+__device__ __forceinline__ void mma_tf32(float (&c)[4], const uint32_t (&a)[4], const uint32_t (&b)[2]) {
+    asm("mma.sync.aligned.m16n8k8.row.col.f32.tf32.tf32.f32 {%0,%1,%2,%3}, {%4,%5,%6,%7}, {%8,%9}, {%0,%1,%2,%3};"
+        : "+f"(c[0]), "+f"(c[1]), "+f"(c[2]), "+f"(c[3])
+        : "r"(a[0]), "r"(a[1]), "r"(a[2]), "r"(a[3]), "r"(b[0]), "r"(b[1]));
+}
 
 __device__ __forceinline__ float gemm_epilogue(const GemmOp& g, int i, int j, float v) {
     v *= g.mult;
@@ -75,14 +89,29 @@ __device__ __forceinline__ float gemm_epilogue(const GemmOp& g, int i, int j, fl
 }
 
 // AC / BC: the contraction index is the contiguous one of A / B (compile-time so that the tile loaders have no
-// run-time index arithmetic).  The next k-tile is fetched into registers while the current one is multiplied.
+// run-time index arithmetic).  The k-tiles arrive through a GEMM_STAGES-deep ring of asynchronous 4-byte copies
+// (cp.async with zero fill outside the operand), so GEMM_STAGES - 1 tiles are in flight while one is multiplied:
+// with K <= 215 per layer the kernel is a chain of memory round trips unless several of them overlap.
+constexpr int GEMM_STAGES = 4;
+constexpr int GEMM_SMEM = GEMM_STAGES * BK * (LDA_S + LDB_S) * (int)sizeof(float);
+static_assert(GEMM_SMEM >= BI * (BJ + 8) * (int)sizeof(float), "the epilogue tile reuses the pipeline stages");
+
+__device__ __forceinline__ void cp_async4(float* dst, const float* src, bool ok) {
+    const uint32_t d = (uint32_t)__cvta_generic_to_shared(dst);
+    const int n = ok ? 4 : 0;                       // src-size 0: nothing is read, the destination is zero-filled
+    asm volatile("cp.async.ca.shared.global [%0], [%1], 4, %2;" ::"r"(d), "l"(src), "r"(n) : "memory");
+}
+__device__ __forceinline__ void cp_async_commit() { asm volatile("cp.async.commit_group;" ::: "memory"); }
+template <int N>
+__device__ __forceinline__ void cp_async_wait() { asm volatile("cp.async.wait_group %0;" ::"n"(N) : "memory"); }
+
 template <bool AC, bool BC>
 __global__ void __launch_bounds__(256, 2) k_gemm(const GemmOp g) {
-    __shared__ __align__(16) float As[BK][LDA_S];
-    __shared__ __align__(16) float Bs[BK][LDB_S];
+    extern __shared__ __align__(16) float gemm_sm[];
+    float (*As)[BK][LDA_S] = reinterpret_cast<float (*)[BK][LDA_S]>(gemm_sm);
+    float (*Bs)[BK][LDB_S] = reinterpret_cast<float (*)[BK][LDB_S]>(gemm_sm + GEMM_STAGES * BK * LDA_S);
     const int tid = threadIdx.x, i0 = blockIdx.x * BI, j0 = blockIdx.y * BJ;
     const int c_begin = blockIdx.z * g.chunk, c_end = min(g.K, c_begin + g.chunk);
-    const int ty = tid >> 4, tx = tid & 15;
     constexpr int NA = BI * BK / 256, NB_ = BJ * BK / 256;
     // this thread's elements of the A / B tiles: (ii, cc) pairs and their global offsets (without the k-tile offset)
     int a_ii[NA], a_cc[NA], b_jj[NB_], b_cc[NB_];
@@ -94,7 +123,7 @@ __global__ void __launch_bounds__(256, 2) k_gemm(const GemmOp g) {
         a_ii[u] = AC ? e / BK : e % BI;
         a_cc[u] = AC ? e % BK : e / BI;
         a_ok[u] = i0 + a_ii[u] < g.I;
-        a_off[u] = (int)((i0 + a_ii[u]) * g.sai + a_cc[u] * g.sac);
+        a_off[u] = a_ok[u] ? (i0 + a_ii[u]) * (int)g.sai + a_cc[u] * (int)g.sac : 0;
     }
 #pragma unroll
     for (int u = 0; u < NB_; ++u) {
@@ -104,63 +133,131 @@ __global__ void __launch_bounds__(256, 2) k_gemm(const GemmOp g) {
         const int j = j0 + b_jj[u];
         b_ok[u] = j < g.J;
         b_one[u] = j == g.J && g.ones_out != nullptr;
-        b_off[u] = (int)(j * g.sbj + b_cc[u] * g.sbc);
+        b_off[u] = b_ok[u] ? j * (int)g.sbj + b_cc[u] * (int)g.sbc : 0;
     }
-    float acc[8][4];
-#pragma unroll
-    for (int a = 0; a < 8; ++a) acc[a][0] = acc[a][1] = acc[a][2] = acc[a][3] = 0.f;
-    float ra[NA], rb[NB_];
     const int sac = (int)g.sac, sbc = (int)g.sbc;
-    auto fetch = [&](int c0) {
+    auto issue = [&](int c0, int st) {              // one commit group per k-tile (empty past the end of the chunk)
+        if (c0 < c_end) {
 #pragma unroll
-        for (int u = 0; u < NA; ++u)
-            ra[u] = (a_ok[u] && c0 + a_cc[u] < c_end) ? g.A[a_off[u] + c0 * sac] : 0.f;
+            for (int u = 0; u < NA; ++u) {
+                const bool ok = a_ok[u] && c0 + a_cc[u] < c_end;
+                cp_async4(&As[st][a_cc[u]][a_ii[u]], ok ? g.A + (a_off[u] + c0 * sac) : g.A, ok);
+            }
 #pragma unroll
-        for (int u = 0; u < NB_; ++u) {
-            const bool in = c0 + b_cc[u] < c_end;
-            rb[u] = in ? (b_ok[u] ? g.B[b_off[u] + c0 * sbc] : (b_one[u] ? 1.f : 0.f)) : 0.f;
+            for (int u = 0; u < NB_; ++u) {
+                const bool in = c0 + b_cc[u] < c_end;
+                if (b_one[u]) Bs[st][b_cc[u]][b_jj[u]] = in ? 1.f : 0.f;
+                else {
+                    const bool ok = b_ok[u] && in;
+                    cp_async4(&Bs[st][b_cc[u]][b_jj[u]], ok ? g.B + (b_off[u] + c0 * sbc) : g.B, ok);
+                }
+            }
         }
+        cp_async_commit();
     };
-    fetch(c_begin);
+    // warp tile 32 x 32 = 2 x 4 mma tiles (4 warps along i, 2 along j); fragment element maps as in oo_tile.h
+    const int lane = tid & 31, fg = lane >> 2, ft = lane & 3;
+    const int wi = 32 * ((tid >> 5) & 3), wj = 32 * (tid >> 7);
+    float acc[2][4][4];
+#pragma unroll
+    for (int mt = 0; mt < 2; ++mt)
+#pragma unroll
+        for (int nt = 0; nt < 4; ++nt) acc[mt][nt][0] = acc[mt][nt][1] = acc[mt][nt][2] = acc[mt][nt][3] = 0.f;
+#pragma unroll 1
+    for (int s = 0; s < GEMM_STAGES - 1; ++s) issue(c_begin + s * BK, s);
+    int st = 0;
     for (int c0 = c_begin; c0 < c_end; c0 += BK) {
+        cp_async_wait<GEMM_STAGES - 2>();           // this thread's copies of tile c0 have landed ...
+        __syncthreads();                            // ... and everybody's; the stage multiplied last iteration is free
+        issue(c0 + (GEMM_STAGES - 1) * BK, st == 0 ? GEMM_STAGES - 1 : st - 1);
 #pragma unroll
-        for (int u = 0; u < NA; ++u) As[a_cc[u]][a_ii[u]] = ra[u];
+        for (int k0 = 0; k0 < BK; k0 += 8) {
+            uint32_t ah[2][4], al[2][4], bh[4][2], bl[4][2];
 #pragma unroll
-        for (int u = 0; u < NB_; ++u) Bs[b_cc[u]][b_jj[u]] = rb[u];
-        __syncthreads();
-        if (c0 + BK < c_end) fetch(c0 + BK);          // in flight during the multiply
-#pragma unroll
-        for (int k = 0; k < BK; ++k) {
-            const float4 a0 = *reinterpret_cast<const float4*>(&As[k][8 * ty]);
-            const float4 a1 = *reinterpret_cast<const float4*>(&As[k][8 * ty + 4]);
-            const float4 b = *reinterpret_cast<const float4*>(&Bs[k][4 * tx]);
-            const float av[8] = {a0.x, a0.y, a0.z, a0.w, a1.x, a1.y, a1.z, a1.w};
-#pragma unroll
-            for (int a = 0; a < 8; ++a) {
-                acc[a][0] = fmaf(av[a], b.x, acc[a][0]);
-                acc[a][1] = fmaf(av[a], b.y, acc[a][1]);
-                acc[a][2] = fmaf(av[a], b.z, acc[a][2]);
-                acc[a][3] = fmaf(av[a], b.w, acc[a][3]);
+            for (int mt = 0; mt < 2; ++mt) {
+                const float* ap = &As[st][k0 + ft][wi + 16 * mt + fg];
+                tf32_split(ap[0], ah[mt][0], al[mt][0]);
+                tf32_split(ap[8], ah[mt][1], al[mt][1]);
+                tf32_split(ap[4 * LDA_S], ah[mt][2], al[mt][2]);
+                tf32_split(ap[4 * LDA_S + 8], ah[mt][3], al[mt][3]);
             }
+#pragma unroll
+            for (int nt = 0; nt < 4; ++nt) {
+                const float* bp = &Bs[st][k0 + ft][wj + 8 * nt + fg];
+                tf32_split(bp[0], bh[nt][0], bl[nt][0]);
+                tf32_split(bp[4 * LDB_S], bh[nt][1], bl[nt][1]);
+            }
+            // term-major order: the eight MMAs of a term are independent, the small terms go first
+#pragma unroll
+            for (int mt = 0; mt < 2; ++mt)
+#pragma unroll
+                for (int nt = 0; nt < 4; ++nt) mma_tf32(acc[mt][nt], al[mt], bh[nt]);
+#pragma unroll
+            for (int mt = 0; mt < 2; ++mt)
+#pragma unroll
+                for (int nt = 0; nt < 4; ++nt) mma_tf32(acc[mt][nt], ah[mt], bl[nt]);
+#pragma unroll
+            for (int mt = 0; mt < 2; ++mt)
+#pragma unroll
+                for (int nt = 0; nt < 4; ++nt) mma_tf32(acc[mt][nt], ah[mt], bh[nt]);
         }
-        __syncthreads();
+        st = st + 1 == GEMM_STAGES ? 0 : st + 1;
     }
+    // Epilogue: accumulators -> shared tile [BI][LDT] -> global.  A thread owns ONE output column (bias, column offset and
+    // mask column are thread constants) and walks down the rows four at a time, all loads of the four (ReLU mask, the old
+    // value when accumulating) before the first store; a warp writes 128 contiguous bytes of a row.  The body is a short
+    // rolled loop on purpose: a fully unrolled per-fragment epilogue was thousands of instructions executed once per warp,
+    // and with K <= 215 that instruction stream, not the tensor pipe, set the kernel time.
+    cp_async_wait<0>();
+    __syncthreads();
+    constexpr int LDT = BJ + 8;
+    float* tile = gemm_sm;
 #pragma unroll
-    for (int a = 0; a < 8; ++a) {
-        const int i = i0 + 8 * ty + a;
-        if (i >= g.I) continue;
+    for (int mt = 0; mt < 2; ++mt)
 #pragma unroll
-        for (int q = 0; q < 4; ++q) {
-            const int j = j0 + 4 * tx + q;
-            if (j >= gemm_je(g)) continue;
-            if (g.split > 1) {
-                g.part[((size_t)blockIdx.z * g.I + i) * gemm_je(g) + j] = acc[a][q];
-            } else {
-                float* dst = gemm_dst(g, i, j);
-                const float v = gemm_epilogue(g, i, j, acc[a][q]);
-                *dst = g.accumulate ? *dst + v : v;
-            }
+        for (int half = 0; half < 2; ++half)
+#pragma unroll
+            for (int nt = 0; nt < 4; ++nt)
+                *reinterpret_cast<float2*>(tile + (wi + 16 * mt + fg + 8 * half) * LDT + wj + 8 * nt + 2 * ft) =
+                    make_float2(acc[mt][nt][2 * half], acc[mt][nt][2 * half + 1]);
+    __syncthreads();
+    const int jl = tid & (BJ - 1), j = j0 + jl, je = gemm_je(g);
+    const int n_rows = min(BI, g.I - i0);
+    if (j >= je) return;
+    const float* tp = tile + jl;
+    int il = tid / BJ;                                          // 0..3; rows il, il + 4, ...
+    if (g.split > 1) {
+        float* dst = g.part + ((size_t)blockIdx.z * g.I + i0 + il) * je + j;
+        for (; il < n_rows; il += 4, dst += 4 * (size_t)je) *dst = tp[il * LDT];
+        return;
+    }
+    const bool ones = j == g.J;                                 // the virtual column: bias gradient of a non-split launch
+    const bool use_mask = g.mask != nullptr && j < g.mask_cols && !ones;
+    const float bias = (g.bias != nullptr && !ones) ? g.bias[j] : 0.f, mult = g.mult, post = g.post;
+    const int act = g.act, accumulate = g.accumulate;
+    const long long dstep = ones ? 4 : 4 * g.sci, mstep = 4 * g.smi;
+    float* dst = ones ? g.ones_out + i0 + il : g.C + (i0 + il) * g.sci + j * g.scj;
+    const float* mp = use_mask ? g.mask + (i0 + il) * g.smi + j * g.smj : nullptr;
+#pragma unroll 1
+    for (; il < n_rows; il += 16) {
+        float mk[4], old[4];
+#pragma unroll
+        for (int u = 0; u < 4; ++u) {
+            const bool ok = il + 4 * u < n_rows;
+            mk[u] = (ok && use_mask) ? mp[u * mstep] : 1.f;
+            old[u] = (ok && accumulate) ? dst[u * dstep] : 0.f;
         }
+#pragma unroll
+        for (int u = 0; u < 4; ++u) {
+            if (il + 4 * u >= n_rows) break;
+            float v = (tp[(il + 4 * u) * LDT] * mult + bias) * post;
+            if (act == 1) v = fmaxf(v, 0.f);
+            else if (act == 2) v = 1.f / (1.f + expf(-v));
+            if (!(mk[u] > 0.f)) v = 0.f;
+            dst[u * dstep] = accumulate ? old[u] + v : v;
+        }
+        dst += 4 * dstep;
+        if (use_mask) mp += 4 * mstep;
     }
 }
 
@@ -194,12 +291,23 @@ int run_gemm(GemmOp g, int split, float* part, cudaStream_t st) {
     OO_REQUIRE((long long)g.I * (g.sai > 0 ? g.sai : 1) + (long long)g.K * (g.sac > 0 ? g.sac : 1) < (1LL << 31) &&
                    (long long)je * (g.sbj > 0 ? g.sbj : 1) + (long long)g.K * (g.sbc > 0 ? g.sbc : 1) < (1LL << 31),
                "oo_bg gemm: operand larger than 2^31 elements");
+    OO_REQUIRE((long long)g.I * (g.sci > 0 ? g.sci : 1) + (long long)je * (g.scj > 0 ? g.scj : 1) < (1LL << 31) &&
+                   (g.mask == nullptr || (long long)g.I * (g.smi > 0 ? g.smi : 1) + (long long)je * (g.smj > 0 ? g.smj : 1) < (1LL << 31)),
+               "oo_bg gemm: output / mask larger than 2^31 elements");
     const dim3 grid((g.I + BI - 1) / BI, (je + BJ - 1) / BJ, g.split);
     const bool ac = g.sac == 1, bc = g.sbc == 1;
-    if (ac && bc) k_gemm<true, true><<<grid, 256, 0, st>>>(g);
-    else if (ac) k_gemm<true, false><<<grid, 256, 0, st>>>(g);
-    else if (bc) k_gemm<false, true><<<grid, 256, 0, st>>>(g);
-    else k_gemm<false, false><<<grid, 256, 0, st>>>(g);
+    static bool attr_set = false;
+    if (!attr_set) {
+        OO_CUDA(cudaFuncSetAttribute(k_gemm<true, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, GEMM_SMEM));
+        OO_CUDA(cudaFuncSetAttribute(k_gemm<true, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, GEMM_SMEM));
+        OO_CUDA(cudaFuncSetAttribute(k_gemm<false, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, GEMM_SMEM));
+        OO_CUDA(cudaFuncSetAttribute(k_gemm<false, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, GEMM_SMEM));
+        attr_set = true;
+    }
+    if (ac && bc) k_gemm<true, true><<<grid, 256, GEMM_SMEM, st>>>(g);
+    else if (ac) k_gemm<true, false><<<grid, 256, GEMM_SMEM, st>>>(g);
+    else if (bc) k_gemm<false, true><<<grid, 256, GEMM_SMEM, st>>>(g);
+    else k_gemm<false, false><<<grid, 256, GEMM_SMEM, st>>>(g);
     OO_LAUNCH_CHECK();
     if (g.split > 1) {
         k_gemm_reduce<<<(g.I * je * 8 + 255) / 256, 256, 0, st>>>(g);
