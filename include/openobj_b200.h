@@ -63,6 +63,27 @@ int oo_param_size(int i);
 int oo_forward(const float* theta, int n_obj, const float* pcs, const float* emb_in, int n_pts, float scale,
                float* alpha, float* color, float* clip, float* emb_out, void* stream);
 
+/* ---- f3: Trainer.eval_points (objnerf/trainer.py:104-128): occupancy = sigmoid(alpha)
+ *      (render_rays.py:6-14), colour and (optionally) the 512-wide part feature of ONE model at n_pts free points
+ *      pts [n_pts][3]; occ [n_pts], color [n_pts][3], clip [n_pts][512] or NULL.  One launch for the whole query
+ *      (the reference walks it in chunks of 300 000 points, trainer.py:104).
+ *      oo_make_grid: the query grid of Trainer.meshing (trainer.py:46-66) = render_rays.make_3D_grid
+ *      (render_rays.py:119-146) with scale and a 3x4 transform, minus obj_center: pts_out [dim^3][3], index
+ *      (i, j, k) -> (i*dim + j)*dim + k as torch.meshgrid(indexing='ij').  t = the dim linspace values (device). */
+typedef struct {
+    int dim;
+    const float* t;          /* [dim] on the device: torch.linspace(occ_range[0], occ_range[1], dim) */
+    float scale[3];
+    float transform[12];     /* rows 0..2 of the 4x4 transform, row-major: [R | trans] */
+    float center[3];         /* obj_center subtracted last (trainer.py:64) */
+} oo_grid;
+int oo_make_grid(const oo_grid* g, float* pts_out, void* stream);
+/* render_rays.occupancy_activation (render_rays.py:6-14): sigmoid(alpha), or 1 - exp(-alpha * distances) when
+ * distances != NULL; n elements. */
+int oo_occupancy_activation(const float* alpha, const float* distances, long long n, float* occ, void* stream);
+int oo_eval_points(const float* theta, const float* pts, long long n_pts, float pe_scale, float* occ, float* color,
+                   float* clip, void* stream);
+
 /* ---- a4-a9: loss.step_batch_loss forward and backward as one pair of HBM-bound kernels
  *      (objnerf/loss.py:5-103, render_rays.py:6-117).  alpha [N][R][S], color [N][R][S][3],
  *      z [N][R][S], gt_depth [N][R], gt_color [N][R][3] float in [0,1], labels [N][R] u8,

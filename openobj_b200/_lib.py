@@ -52,6 +52,12 @@ class AppendArgs(Structure):
                 ("depth_ring", c_void_p), ("t_wc_ring", c_void_p), ("bbox_ring", c_void_p)]
 
 
+class Grid(Structure):
+    """oo_grid (include/openobj_b200.h)."""
+    _fields_ = [("dim", c_int), ("t", c_void_p), ("scale", c_float * 3), ("transform", c_float * 12),
+                ("center", c_float * 3)]
+
+
 class RenderArgs(Structure):
     _fields_ = [("W", c_int), ("H", c_int), ("n_bins", c_int), ("scale", c_float),
                 ("theta1", c_void_p), ("T_wc", c_void_p), ("T_oc", c_void_p), ("half_extent", c_void_p),
@@ -91,6 +97,9 @@ _SIGS = {
     "oo_render_object": ([POINTER(RenderArgs), c_void_p], c_int),
     "oo_zmerge": ([c_void_p, c_void_p, c_void_p, c_void_p, c_int, c_int64, c_void_p, c_void_p, c_void_p, c_void_p],
                   c_int),
+    "oo_make_grid": ([POINTER(Grid), c_void_p, c_void_p], c_int),
+    "oo_eval_points": ([c_void_p, c_void_p, c_int64, c_float, c_void_p, c_void_p, c_void_p, c_void_p], c_int),
+    "oo_occupancy_activation": ([c_void_p, c_void_p, c_int64, c_void_p, c_void_p], c_int),
     "oo_fma_peak": ([c_int, c_int, c_void_p, c_void_p], c_int),
     "oo_bg_param_count": ([c_int], c_int),
     "oo_bg_param_offset": ([c_int, c_int], c_int),

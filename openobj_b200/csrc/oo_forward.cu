@@ -27,7 +27,7 @@ __global__ void __launch_bounds__(NTHREADS, 1) k_forward(const float* __restrict
                                                          const float* __restrict__ emb_in, int n_pts, float scale,
                                                          float* __restrict__ alpha,
                                                          float* __restrict__ color, float* __restrict__ clip,
-                                                         float* __restrict__ emb) {
+                                                         float* __restrict__ emb, float* __restrict__ occ) {
     extern __shared__ __align__(16) float sm[];
     const int tid = threadIdx.x, obj = blockIdx.y;
     const float* th = theta + (size_t)obj * PSTRIDE;
@@ -71,7 +71,10 @@ __global__ void __launch_bounds__(NTHREADS, 1) k_forward(const float* __restrict
             c.pcs = pcs + base * 3;
             FwdPhases<0, N_FWD_PHASES>::run(tid, sm, c, acc);
         }
-        for (int i = tid; i < c.npts; i += NTHREADS) alpha[base + i] = misc[M_DRAW * PS + i];
+        if (alpha != nullptr)
+            for (int i = tid; i < c.npts; i += NTHREADS) alpha[base + i] = misc[M_DRAW * PS + i];
+        if (occ != nullptr)      // render_rays.occupancy_activation without distances: sigmoid(alpha) (render_rays.py:6-14)
+            for (int i = tid; i < c.npts; i += NTHREADS) occ[base + i] = 1.f / (1.f + expf(-misc[M_DRAW * PS + i]));
         for (int i = tid; i < c.npts * 3; i += NTHREADS) {
             const int p = i / 3, ch = i - 3 * p;
             color[base * 3 + i] = misc[(M_COL + ch) * PS + p];
@@ -111,7 +114,71 @@ extern "C" int oo_forward(const float* theta, int n_obj, const float* pcs, const
     int gx = (4 * 148 + n_obj - 1) / n_obj;
     if (gx > n_tiles) gx = n_tiles;
     if (gx < 1) gx = 1;
-    k_forward<<<dim3(gx, n_obj), NTHREADS, smem, (cudaStream_t)stream>>>(theta, pcs, emb_in, n_pts, scale, alpha, color, clip, emb_out);
+    k_forward<<<dim3(gx, n_obj), NTHREADS, smem, (cudaStream_t)stream>>>(theta, pcs, emb_in, n_pts, scale, alpha, color, clip, emb_out,
+                                                                         nullptr);
+    OO_LAUNCH_CHECK();
+    return 0;
+}
+
+// ---- f3: Trainer.eval_points (objnerf/trainer.py:104-128) and the query grid of Trainer.meshing (trainer.py:46-66) ----
+namespace {
+// render_rays.make_3D_grid (render_rays.py:119-146): p = R (t_ijk * scale) + trans, then meshing's `grid_pc -= obj_center`
+// (trainer.py:64); separate roundings in the reference's order: products, ((a + b) + c), + translation, - centre.
+__global__ void k_make_grid(const oo_grid g, float* __restrict__ pts) {
+    const long long n = (long long)g.dim * g.dim * g.dim;
+    for (long long e = (long long)blockIdx.x * blockDim.x + threadIdx.x; e < n; e += (long long)gridDim.x * blockDim.x) {
+        const int k = (int)(e % g.dim), j = (int)((e / g.dim) % g.dim), i = (int)(e / ((long long)g.dim * g.dim));
+        const float x = __fmul_rn(g.t[i], g.scale[0]), y = __fmul_rn(g.t[j], g.scale[1]), z = __fmul_rn(g.t[k], g.scale[2]);
+#pragma unroll
+        for (int r = 0; r < 3; ++r) {
+            const float* T = g.transform + 4 * r;
+            float v = __fadd_rn(__fadd_rn(__fmul_rn(T[0], x), __fmul_rn(T[1], y)), __fmul_rn(T[2], z));
+            v = __fsub_rn(__fadd_rn(v, T[3]), g.center[r]);
+            pts[3 * e + r] = v;
+        }
+    }
+}
+}  // namespace
+
+namespace {
+__global__ void k_occupancy(const float* __restrict__ alpha, const float* __restrict__ dist, long long n, float* __restrict__ occ) {
+    for (long long e = (long long)blockIdx.x * blockDim.x + threadIdx.x; e < n; e += (long long)gridDim.x * blockDim.x)
+        occ[e] = dist != nullptr ? 1.f - expf(-alpha[e] * dist[e]) : 1.f / (1.f + expf(-alpha[e]));
+}
+}  // namespace
+
+extern "C" int oo_occupancy_activation(const float* alpha, const float* distances, long long n, float* occ, void* stream) {
+    OO_REQUIRE(alpha && occ && n > 0, "oo_occupancy_activation: bad argument");
+    const int blocks = (int)((n + 255) / 256 < 148 * 16 ? (n + 255) / 256 : 148 * 16);
+    k_occupancy<<<blocks, 256, 0, (cudaStream_t)stream>>>(alpha, distances, n, occ);
+    OO_LAUNCH_CHECK();
+    return 0;
+}
+
+extern "C" int oo_make_grid(const oo_grid* g, float* pts_out, void* stream) {
+    OO_REQUIRE(g && g->t && pts_out, "oo_make_grid: null argument");
+    OO_REQUIRE(g->dim > 0 && g->dim <= 1024, "oo_make_grid: grid_dim out of range");
+    const long long n = (long long)g->dim * g->dim * g->dim;
+    const int blocks = (int)((n + 255) / 256 < 148 * 16 ? (n + 255) / 256 : 148 * 16);
+    k_make_grid<<<blocks, 256, 0, (cudaStream_t)stream>>>(*g, pts_out);
+    OO_LAUNCH_CHECK();
+    return 0;
+}
+
+extern "C" int oo_eval_points(const float* theta, const float* pts, long long n_pts, float pe_scale, float* occ, float* color,
+                              float* clip, void* stream) {
+    OO_REQUIRE(theta && pts && occ && color, "oo_eval_points: null argument");
+    OO_REQUIRE(n_pts > 0 && n_pts < (1LL << 31) - P, "oo_eval_points: point count out of range");
+    const size_t smem = (size_t)SM_TOTAL * sizeof(float);
+    static bool attr_set = false;
+    if (!attr_set) {
+        OO_CUDA(cudaFuncSetAttribute(k_forward, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+        attr_set = true;
+    }
+    const long long n_tiles = (n_pts + P - 1) / P;
+    const int gx = (int)(n_tiles < 4 * 148 ? n_tiles : 4 * 148);
+    k_forward<<<dim3(gx, 1), NTHREADS, smem, (cudaStream_t)stream>>>(theta, pts, nullptr, (int)n_pts, pe_scale, nullptr, color, clip, nullptr,
+                                                                    occ);
     OO_LAUNCH_CHECK();
     return 0;
 }

@@ -39,6 +39,53 @@ def forward(theta, pcs=None, emb=None, scale=2.0, want_clip=True, want_emb=False
             None if emb_o is None else emb_o.view(lead + [129]))
 
 
+def eval_points(theta, points, scale=2.0, want_clip=True):
+    """Trainer.eval_points for ONE hidden-32 model (trainer.py:104-128): theta [1,PSTRIDE] (or [PSTRIDE]), points [n,3].
+    Returns occ [n] = sigmoid(alpha), color [n,3], clip [n,512] or None -- one launch for the whole query."""
+    _dev(theta)
+    pts = points.reshape(-1, 3).contiguous().float()
+    n = pts.shape[0]
+    f32 = dict(dtype=torch.float32, device=theta.device)
+    occ, color = torch.empty(n, **f32), torch.empty(n, 3, **f32)
+    clip = torch.empty(n, layout.CLIP, **f32) if want_clip else None
+    with _dev(theta):
+        check(lib().oo_eval_points(ptr(theta), ptr(pts), n, float(scale), ptr(occ), ptr(color), ptr(clip), stream()),
+              "oo_eval_points")
+    return occ, color, clip
+
+
+def make_grid(dim, scale, transform, center=None, occ_range=(-1., 1.), device="cuda:0"):
+    """The query grid of Trainer.meshing (trainer.py:46-66) = render_rays.make_3D_grid with scale [3] and transform [4,4],
+    minus `center`; returns [dim^3, 3] on the device ((i, j, k) -> (i*dim + j)*dim + k)."""
+    dev = torch.device(device)
+    t = torch.linspace(occ_range[0], occ_range[1], steps=dim, device=dev)       # the dim knot values (plumbing)
+    g = _lib.Grid()
+    g.dim, g.t = int(dim), ptr(t)
+    sc = [1.0, 1.0, 1.0] if scale is None else [float(v) for v in torch.as_tensor(scale).reshape(-1).tolist()]
+    if len(sc) == 1:
+        sc = sc * 3
+    tr = torch.eye(4) if transform is None else torch.as_tensor(transform).detach().cpu().float()
+    ce = [0.0, 0.0, 0.0] if center is None else [float(v) for v in torch.as_tensor(center).reshape(-1).tolist()]
+    g.scale[:] = sc
+    g.transform[:] = [float(v) for v in tr[:3, :4].reshape(-1).tolist()]
+    g.center[:] = ce
+    out = torch.empty(dim ** 3, 3, dtype=torch.float32, device=dev)
+    with torch.cuda.device(dev):
+        check(lib().oo_make_grid(ctypes.byref(g), ptr(out), stream()), "oo_make_grid")
+    return out
+
+
+def occupancy_activation(alpha, distances=None):
+    """render_rays.occupancy_activation (render_rays.py:6-14) on the device."""
+    _dev(alpha)
+    a = alpha.contiguous().float()
+    d = None if distances is None else distances.expand_as(a).contiguous().float()
+    occ = torch.empty_like(a)
+    with _dev(a):
+        check(lib().oo_occupancy_activation(ptr(a), ptr(d), a.numel(), ptr(occ), stream()), "oo_occupancy_activation")
+    return occ
+
+
 class _StepLoss(torch.autograd.Function):
     """loss.step_batch_loss as one fused forward / backward kernel pair (K3)."""
 

@@ -418,6 +418,48 @@ def gen_bg_step(m):
     return out
 
 
+def gen_eval_grid(m):
+    """Trainer.eval_points on the query grid of Trainer.meshing (trainer.py:46-69,104-128): make_3D_grid with the
+    oriented box's scale / transform minus obj_center, then pe -> fc_occ_map -> occupancy_activation in chunks, for an
+    object model (hidden 32, scale 2, bound_extent 0.9) and the background model (hidden 128, scale 5, 0.995)."""
+    torch.manual_seed(99)
+    out = {}
+    base = small_cfg()
+    ang = 0.4
+    R = np.array([[np.cos(ang), 0, np.sin(ang)], [0, 1, 0], [-np.sin(ang), 0, np.cos(ang)]])
+    center, extent = np.array([0.3, -0.2, 2.5]), np.array([1.6, 1.1, 0.8])
+    obj_center = torch.tensor([0.05, -0.02, 0.1])
+    out.update(obb_R=torch.from_numpy(R), obb_center=torch.from_numpy(center), obb_extent=torch.from_numpy(extent),
+               obj_center=obj_center)
+    for tag, cfg, dim in (("obj", small_cfg(), 12),
+                          ("bg", small_cfg(hidden_feature_size=base.hidden_feature_size_bg, obj_scale=base.bg_scale), 7)):
+        cfg.obj_id = 1 if tag == "obj" else 0
+        tr = m["trainer"].Trainer(cfg)
+        tr.pe.B_layer.weight.data += 0.01 * torch.randn(21, 3)
+        with torch.no_grad():
+            tr.fc_occ_map.out_alpha.bias.fill_(0.02)
+        # the lines of Trainer.meshing that build the query (trainer.py:50-64)
+        scene_scale_np = extent / (2.0 * tr.bound_extent)
+        scene_scale = torch.from_numpy(scene_scale_np).float()
+        transform_np = np.eye(4, dtype=np.float32)
+        transform_np[:3, 3] = center
+        transform_np[:3, :3] = R
+        grid_pc = m["render_rays"].make_3D_grid(occ_range=[-1., 1.], dim=dim, device="cpu", scale=scene_scale,
+                                                transform=torch.from_numpy(transform_np)).view(-1, 3)
+        grid_pc -= obj_center
+        occ, color, clip = tr.eval_points(grid_pc, chunk_size=500)
+        out[tag + "_dim"] = torch.tensor(dim)
+        out[tag + "_bound_extent"] = torch.tensor(tr.bound_extent)
+        out[tag + "_scale"] = torch.tensor(float(cfg.obj_scale))
+        out[tag + "_grid"] = grid_pc.clone()
+        out[tag + "_occ"], out[tag + "_color"] = occ.clone(), color.clone()
+        out[tag + "_clip"] = clip[::7].clone()                      # every 7th point keeps the file small
+        for i, p in enumerate(tr.fc_occ_map.parameters()):
+            out["%s_fc%02d" % (tag, i)] = p.detach().clone()[None]
+        out[tag + "_peB"] = tr.pe.B_layer.weight.detach().clone()[None]
+    return out
+
+
 def save(name, d):
     arrs = {k: (v.numpy() if torch.is_tensor(v) else np.asarray(v)) for k, v in d.items()}
     path = os.path.join(OUT, name)
@@ -428,6 +470,9 @@ def save(name, d):
 def main():
     os.makedirs(OUT, exist_ok=True)
     m = rh.load()
+    if "--only-eval" in sys.argv:               # added after the other files were frozen: do not touch them
+        save("eval_grid.npz", gen_eval_grid(m))
+        return
     if "--only-bg" in sys.argv:                 # added after the other files were frozen: do not touch them
         save("bg_step.npz", gen_bg_step(m))
         return
@@ -436,6 +481,7 @@ def main():
     save("sample_obj.npz", gen_sampling(m, bg=False))
     save("sample_bg.npz", gen_sampling(m, bg=True))
     save("render_obj.npz", gen_render(m))
+    save("eval_grid.npz", gen_eval_grid(m))
     with open(os.path.join(OUT, "keyframe_policy.json"), "w") as f:
         json.dump(gen_keyframe_policy(m), f)
     print("done; torch", torch.__version__)

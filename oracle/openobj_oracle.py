@@ -213,6 +213,41 @@ def step_loss(alpha, color, gt_depth, gt_color, labels, z, gt_feat=None, pred_fe
 
 
 # --------------------------------------------------------------------------
+# evaluation at free points / on the meshing grid (trainer.py:46-69,104-128; render_rays.py:119-146)
+# --------------------------------------------------------------------------
+
+def make_3d_grid(dim, scale=None, transform=None, occ_range=(-1.0, 1.0)):
+    """render_rays.make_3D_grid (render_rays.py:119-146): meshgrid of linspace knots, * scale, rows of the transform
+    applied as (R_r * grid).sum(-1), + translation.  Returns [dim, dim, dim, 3]."""
+    t = torch.linspace(occ_range[0], occ_range[1], steps=dim)                   # :123
+    g = torch.stack(torch.meshgrid(t, t, t, indexing="ij"), dim=3)             # :124-129
+    if scale is not None:
+        g = g * scale                                                           # :131-132
+    if transform is not None:
+        rows = [(transform[r, :3][None, None, None] * g).sum(-1, keepdim=True) for r in range(3)]   # :134-140
+        g = torch.cat(rows, dim=-1) + transform[:3, 3][None, None, None]        # :141-144
+    return g
+
+
+def meshing_grid(obb_R, obb_center, obb_extent, bound_extent, dim, obj_center=None):
+    """The query points of Trainer.meshing (trainer.py:50-64): scale = extent / (2 * bound_extent) in float64 -> float32,
+    float32 4x4 [R | center], make_3D_grid, minus obj_center.  Returns [dim^3, 3]."""
+    scale = (obb_extent.double() / (2.0 * float(bound_extent))).float()
+    tr = torch.eye(4, dtype=torch.float32)
+    tr[:3, 3] = obb_center.float()
+    tr[:3, :3] = obb_R.float()
+    pts = make_3d_grid(dim, scale, tr).reshape(-1, 3)
+    return pts if obj_center is None else pts - obj_center
+
+
+def eval_points(fc1, B1, points, scale=2.0):
+    """Trainer.eval_points (trainer.py:104-128) for one model: fc1 = 18 tensors with a leading 1, B1 [1,21,3],
+    points [n,3].  Returns occ [n] = sigmoid(alpha) (render_rays.py:6-14), color [n,3], clip [n,C]."""
+    alpha, color, clip = ensemble_forward(fc1, B1, points[None], scale)
+    return torch.sigmoid(alpha[0, :, 0]), color[0], clip[0]
+
+
+# --------------------------------------------------------------------------
 # one optimisation step of the ensemble (train.py:394-474) and AdamW (SURVEY A.4)
 # --------------------------------------------------------------------------
 

@@ -243,3 +243,19 @@ def test_bg_three_step_loss_conditioning(bg):
             assert abs(l[2] - ref[2]) <= 1e-3 * ref[2]
             worst = max(worst, abs(l[2] - ref[2]) / ref[2])
     assert worst > 1e-4      # the step-2 loss is NOT determined to 1e-4 by fp32 arithmetic
+
+
+# ---- evaluation on the meshing grid: eval_grid.npz frozen from the reference's Trainer.eval_points ----
+@pytest.mark.parametrize("tag", ["obj", "bg"])
+def test_eval_grid_oracle(tag):
+    d = load("eval_grid.npz")
+    fc = [d["%s_fc%02d" % (tag, i)] for i in range(18)]
+    dim = int(d[tag + "_dim"])
+    pts = oc.meshing_grid(d["obb_R"], d["obb_center"], d["obb_extent"], float(d[tag + "_bound_extent"]), dim, d["obj_center"])
+    assert torch.equal(pts, d[tag + "_grid"])                   # the same torch expressions: bit-identical
+    occ, color, clip = oc.eval_points(fc, d[tag + "_peB"], pts, scale=float(d[tag + "_scale"]))
+    close(occ, d[tag + "_occ"], rtol=1e-5, atol=1e-6)
+    close(color, d[tag + "_color"], rtol=1e-5, atol=1e-6)
+    close(clip[::7], d[tag + "_clip"], rtol=1e-4, atol=1e-5)
+    o = d[tag + "_occ"]
+    assert float((o > 0.5).float().mean()) > 0.1 and float((o < 0.5).float().mean()) > 0.01     # occupied and free points
