@@ -229,10 +229,12 @@ typedef struct oo_sample_args {
     /* torch.linspace(0,1,n+1) tables used by utils.stratified_bins (utils.py:349) for n = S, n_c2s, n_bins.
      * HOST pointers: ATen's vectorised linspace is not a closed formula, so the caller supplies what torch gives. */
     const float* lin_s_host; const float* lin_c2s_host; const float* lin_bins_host;
-    /* rng_mode 1: no tapes; every draw comes from the counter RNG of oo_rng_fill evaluated in-kernel, stream
-     * 8*frame + {0 keyframe, 1 u_w, 2 u_h, 3 r_invalid, 4 r_valid, 5 r_normal (std eps/3), 6 r_other}, element = the
-     * tape index (so the result equals tape mode with tapes produced by oo_rng_fill, row = ray index).
-     * keyframe id f: min(int(u * n_keyframes), n_keyframes-1), the last two forced to `latest` when n_keyframes > 2. */
+    /* rng_mode 1: no tapes; every draw comes from the counter RNG (Philox4x32-10 keyed by seed) evaluated in-kernel.
+     * Keyframe draw of frame slot f: element f of oo_rng_fill stream 8*frame + 0; keyframe id = min(int(u * n_keyframes),
+     * n_keyframes-1), the last two forced to `latest` when n_keyframes > 2.  Everything else of ray r comes from the
+     * ray-blocked stream of oo_rng_fill_rows(frame stream 8*frame + 1, row = r): word 0 = u_w, 1 = u_h, 2 .. 2+n_c2s =
+     * r_valid, and from B0 = 4*ceil((2 + n_c2s)/4): r_invalid (S words) / r_other (n_bins words) / r_normal (Box-Muller
+     * pairs, std eps/3) -- so the result equals tape mode (row = ray index) with tapes cut from oo_rng_fill_rows. */
     int rng_mode; uint64_t seed; uint32_t frame;
     const int32_t* obj_ids;              /* [n_obj] RNG key per object (its instance id: shard independent) */
     const int32_t* n_keyframes;          /* [n_obj] */
@@ -266,6 +268,12 @@ int oo_append_frame(const oo_append_args* a, void* stream);
 /* counter-based uniform / normal tapes keyed by (seed, frame, object id, element) -- shard independent. */
 int oo_rng_fill(uint64_t seed, uint32_t frame, const int32_t* obj_ids, int n_obj, int64_t per_obj,
                 int kind /*0 uniform [0,1), 1 normal(0,std)*/, float std, float* out, void* stream);
+
+/* ray-blocked variant: out [n_obj][n_rows][row_words]; word w of row r = word (w % 4) of
+ * philox(counter = (r, w / 4, object id, frame), key = seed) as a uniform, or (kind 1) the Box-Muller normal of its
+ * pair (w even: cos, w odd: sin) -- what oo_sample_rays draws in rng_mode 1 for ray = row. */
+int oo_rng_fill_rows(uint64_t seed, uint32_t frame, const int32_t* obj_ids, int n_obj, int n_rows, int row_words,
+                     int kind /*0 uniform [0,1), 1 normal(0,std)*/, float std, float* out, void* stream);
 
 /* ---- a19: render_2D_syn for one object over all W*H pixels (vmap.py:604-685, trainer.py:130-198)
  *      and the sequential depth-test merge (train.py:577-594). */

@@ -94,6 +94,7 @@ _SIGS = {
     "oo_sample_rays": ([POINTER(SampleArgs), c_void_p], c_int),
     "oo_append_frame": ([POINTER(AppendArgs), c_void_p], c_int),
     "oo_rng_fill": ([c_uint64, c_uint32, c_void_p, c_int, c_int64, c_int, c_float, c_void_p, c_void_p], c_int),
+    "oo_rng_fill_rows": ([c_uint64, c_uint32, c_void_p, c_int, c_int, c_int, c_int, c_float, c_void_p, c_void_p], c_int),
     "oo_render_object": ([POINTER(RenderArgs), c_void_p], c_int),
     "oo_zmerge": ([c_void_p, c_void_p, c_void_p, c_void_p, c_int, c_int64, c_void_p, c_void_p, c_void_p, c_void_p],
                   c_int),

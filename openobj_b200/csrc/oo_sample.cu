@@ -16,18 +16,6 @@ struct SampleK {
     float lin_s[MAXB], lin_c[MAXB], lin_b[MAXB];
 };
 
-__device__ __forceinline__ void sort_small(float* v, int n) {   // insertion sort, n <= 32 (n_bins = 9)
-    for (int i = 1; i < n; ++i) {
-        const float x = v[i];
-        int j = i - 1;
-        while (j >= 0 && v[j] > x) {
-            v[j + 1] = v[j];
-            --j;
-        }
-        v[j + 1] = x;
-    }
-}
-
 // ---- Philox4x32-10 counter RNG: value i of object id `oid` in frame `frame` depends only on (seed, frame, oid, i)
 __device__ __forceinline__ uint4 philox4x32_10(uint4 ctr, uint2 key) {
 #pragma unroll
@@ -53,17 +41,6 @@ struct Rng {
         return i == 0 ? r.x : i == 1 ? r.y : i == 2 ? r.z : r.w;
     }
     __device__ __forceinline__ float uniform(uint32_t stream, uint64_t e) const { return (float)(word(stream, e) >> 8) * TWO_M24; }
-    __device__ __forceinline__ float normal(uint32_t stream, uint64_t e, float std) const {   // same pairing as k_rng_fill
-        const uint64_t q = e >> 2;
-        const uint4 r = philox4x32_10(make_uint4((uint32_t)q, (uint32_t)(q >> 32), oid, 8u * frame + stream), key);
-        const uint32_t i = (uint32_t)(e & 3);
-        const uint32_t a = i < 2 ? r.x : r.z, b = i < 2 ? r.y : r.w;
-        const float u0 = ((float)(a >> 8) + 1.f) * TWO_M24, u1 = (float)(b >> 8) * TWO_M24;
-        const float rad = sqrtf(-2.f * logf(u0)) * std;
-        float sn, cs;
-        sincospif(2.f * u1, &sn, &cs);
-        return (i & 1) ? rad * sn : rad * cs;
-    }
 };
 
 struct RayPix {
@@ -72,24 +49,11 @@ struct RayPix {
     bool oob;
 };
 
-__device__ __forceinline__ RayPix ray_pixel(const oo_sample_args& a, const Rng& g, int obj, int ray) {
+// pixel of a ray from its two uniforms: separate fp32 mul and add, then truncation -- vmap.py:418-422
+__device__ __forceinline__ RayPix pixel_from_uniforms(const oo_sample_args& a, int obj, int kf, float uw, float uh) {
     RayPix r;
-    const int f = ray / a.n_samples;
-    float uw, uh;
-    if (a.rng_mode) {
-        const int nk = a.n_keyframes[obj];
-        if (nk > 2 && f >= a.n_frames - 2) r.kf = a.latest[2 * obj + (f - (a.n_frames - 2))];       // vmap.py:398-400
-        else r.kf = min((int)(g.uniform(0, (uint64_t)f) * (float)nk), nk - 1);
-        uw = g.uniform(1, (uint64_t)ray);
-        uh = g.uniform(2, (uint64_t)ray);
-    } else {
-        r.kf = (int)a.kf_ids[(size_t)obj * a.n_frames + f];
-        const size_t ui = (size_t)obj * a.n_frames * a.n_samples + ray;
-        uw = a.u_w[ui];
-        uh = a.u_h[ui];
-    }
-    const float* bb = a.bbox[obj] + 4 * r.kf;
-    // separate fp32 mul and add, then truncation -- vmap.py:418-422
+    r.kf = kf;
+    const float* bb = a.bbox[obj] + 4 * kf;
     r.iwf = __fadd_rn(__fmul_rn(uw, __fsub_rn(bb[1], bb[0])), bb[0]);
     r.ihf = __fadd_rn(__fmul_rn(uh, __fsub_rn(bb[3], bb[2])), bb[2]);
     int iw = (int)r.iwf, ih = (int)r.ihf;
@@ -99,10 +63,9 @@ __device__ __forceinline__ RayPix ray_pixel(const oo_sample_args& a, const Rng& 
     return r;
 }
 
-// ---- pass A for one ray: pixel draw, gathers, per-ray outputs, class (0 invalid depth / 1 this object / 2 other)
-__device__ __forceinline__ int sample_ray_a(const oo_sample_args& a, const Rng& g, int obj, int ray, int n_rays, float& d_out,
-                                            int& oob) {
-    const RayPix p = ray_pixel(a, g, obj, ray);
+// ---- pass A for one ray: gathers, per-ray outputs, class (0 invalid depth / 1 this object / 2 other)
+__device__ __forceinline__ int gather_ray(const oo_sample_args& a, int obj, int ray, int n_rays, const RayPix& p, float& d_out,
+                                          int& oob) {
     oob += p.oob;
     const size_t pix = ((size_t)p.kf * a.W + p.iw) * a.H + p.ih;
     const uchar4 c = *reinterpret_cast<const uchar4*>(a.rgbs[obj] + pix * 4);    // vmap.py:424
@@ -125,54 +88,6 @@ __device__ __forceinline__ int sample_ray_a(const oo_sample_args& a, const Rng& 
     return invalid ? 0 : (c.w == 1 ? 1 : 2);
 }
 
-// n consecutive values of one stream starting at element e0, one Philox block per four elements (same values as
-// Rng::uniform / Rng::normal element by element, which recompute the block for every element)
-template <int N>
-__device__ __forceinline__ void uniform_run(const Rng& g, uint32_t stream, uint64_t e0, int n, float* out) {
-    int i = 0;
-#pragma unroll
-    for (int blk = 0; blk < (N + 3) / 4 + 1; ++blk) {
-        const uint64_t q = (e0 >> 2) + blk;
-        const uint4 r = philox4x32_10(make_uint4((uint32_t)q, (uint32_t)(q >> 32), g.oid, 8u * g.frame + stream), g.key);
-        const uint32_t w[4] = {r.x, r.y, r.z, r.w};
-#pragma unroll
-        for (int k = 0; k < 4; ++k) {
-            const long long e = (long long)(4 * q + k) - (long long)e0;
-            if (e >= 0 && e < n) {
-#pragma unroll
-                for (int j = 0; j < N; ++j)
-                    if (j == (int)e) out[j] = (float)(w[k] >> 8) * TWO_M24;
-            }
-        }
-        (void)i;
-    }
-}
-
-template <int N>
-__device__ __forceinline__ void normal_run(const Rng& g, uint32_t stream, uint64_t e0, int n, float std, float* out) {
-#pragma unroll
-    for (int blk = 0; blk < (N + 3) / 4 + 1; ++blk) {
-        const uint64_t q = (e0 >> 2) + blk;
-        if ((long long)(4 * q) - (long long)e0 >= n) break;
-        const uint4 r = philox4x32_10(make_uint4((uint32_t)q, (uint32_t)(q >> 32), g.oid, 8u * g.frame + stream), g.key);
-#pragma unroll
-        for (int half = 0; half < 2; ++half) {                    // elements 4q + 2 half (cos) and 4q + 2 half + 1 (sin)
-            const long long e = (long long)(4 * q + 2 * half) - (long long)e0;
-            if (e + 1 < 0 || e >= n) continue;
-            const uint32_t a = half == 0 ? r.x : r.z, b = half == 0 ? r.y : r.w;
-            const float u0 = ((float)(a >> 8) + 1.f) * TWO_M24, u1 = (float)(b >> 8) * TWO_M24;
-            const float rad = sqrtf(-2.f * logf(u0)) * std;
-            float sn, cs;
-            sincospif(2.f * u1, &sn, &cs);
-#pragma unroll
-            for (int j = 0; j < N; ++j) {
-                if (j == (int)e && e >= 0) out[j] = rad * cs;
-                if (j == (int)e + 1 && e + 1 < n) out[j] = rad * sn;
-            }
-        }
-    }
-}
-
 // ascending sort of n <= N values held in registers: odd-even transposition network (N rounds of compare-exchange)
 template <int N>
 __device__ __forceinline__ void sort_regs(float* v, int n) {
@@ -186,35 +101,24 @@ __device__ __forceinline__ void sort_regs(float* v, int n) {
             }
 }
 
-// ---- pass B for one ray: depth placement along the ray and the sample points.  rk_* = rank of the ray inside its class
-// (tape rows in tape_by_rank mode); max_bound = max sampled depth of the object's batch (vmap.py:489, quirk 6).
-// NC / NB = compile-time upper bounds of n_c2s / n_bins (the shipped configurations 1 + 9 and 5 + 9 get exact
-// instantiations, so every per-ray array lives in registers); zo [S] / po [S][3]: where the ray's depths and points go
-// (global rows, or the CTA's staging tile in the parallel path)
-template <int NC, int NB>
-__device__ __forceinline__ void sample_ray_b(const SampleK& k, const Rng& g, int obj, int ray, int n_rays, int rk_inv, int rk_val,
-                                             int rk_obj, int rk_oth, float max_bound, float* zo, float* po) {
+// ---- pass B for one ray: depth placement along the ray and the sample points.  max_bound = max sampled depth of the
+// object's batch (vmap.py:489, quirk 6).  NC / NB = compile-time upper bounds of n_c2s / n_bins (the shipped configurations
+// 1 + 9 and 5 + 9 get exact instantiations, so every per-ray array lives in registers); zo [S] / po [S][3]: where the ray's
+// depths and points go (global rows, or the CTA's staging tile in the parallel path).  `dr` supplies the ray's random draws
+// (TapeDraws: rows of the caller's tapes; CounterDraws: the counter RNG evaluated here), class by class, so that only the
+// draws the ray's class consumes are produced.
+template <int NC, int NB, class Draws>
+__device__ __forceinline__ void place_ray(const SampleK& k, int obj, int kf, int iw, int ih, float d, int state, float max_bound,
+                                          const Draws& dr, float* zo, float* po) {
     const oo_sample_args& a = k.a;
-    const bool rng = a.rng_mode != 0;
     const int nc = a.n_c2s, nb = a.n_bins, S = nc + nb;
     const float eps = a.eps;
-    const RayPix p = ray_pixel(a, g, obj, ray);
-    const size_t o = (size_t)obj * n_rays + ray;
-    const float d = a.gt_depth[o];
-    const int state = a.labels[o];
     const bool invalid = d <= a.min_bound;
     float zs[NC + NB];
     if (invalid) {
         // stratified_bins(min_bound, max(sampled_depth), S) -- vmap.py:493-498, utils.py:342-379
         float u[NC + NB];
-        if (rng) {
-            uniform_run<NC + NB>(g, 3, (uint64_t)ray * S, S, u);
-        } else {
-            const size_t row = ((size_t)obj * n_rays + (a.tape_by_rank ? rk_inv : ray)) * S;
-#pragma unroll
-            for (int i = 0; i < NC + NB; ++i)
-                if (i < S) u[i] = a.r_invalid[row + i];
-        }
+        dr.invalid(u);
         const float range = __fsub_rn(max_bound, a.min_bound);
         const float blen = __fdiv_rn(range, (float)S);
 #pragma unroll
@@ -223,14 +127,7 @@ __device__ __forceinline__ void sample_ray_b(const SampleK& k, const Rng& g, int
     } else {
         float uc[NC], ub[NB];
         {   // cam -> surface: stratified_bins(min_bound, d - eps, n_c2s) -- vmap.py:506-509
-            if (rng) {
-                uniform_run<NC>(g, 4, (uint64_t)ray * nc, nc, uc);
-            } else {
-                const size_t row = ((size_t)obj * n_rays + (a.tape_by_rank ? rk_val : ray)) * nc;
-#pragma unroll
-                for (int i = 0; i < NC; ++i)
-                    if (i < nc) uc[i] = a.r_valid[row + i];
-            }
+            dr.valid(uc);
             const float range = __fsub_rn(__fsub_rn(d, eps), a.min_bound);
             const float blen = __fdiv_rn(range, (float)nc);
 #pragma unroll
@@ -239,28 +136,14 @@ __device__ __forceinline__ void sample_ray_b(const SampleK& k, const Rng& g, int
         }
         if (state == 1) {
             // normal_bins_sampling: N(0, eps/3) draws sorted ascending, clipped to +-eps, + d -- utils.py:382-397
-            if (rng) {
-                normal_run<NB>(g, 5, (uint64_t)ray * nb, nb, __fdiv_rn(eps, 3.f), ub);
-            } else {
-                const size_t row = ((size_t)obj * n_rays + (a.tape_by_rank ? rk_obj : ray)) * nb;
-#pragma unroll
-                for (int i = 0; i < NB; ++i)
-                    if (i < nb) ub[i] = a.r_normal[row + i];
-            }
+            dr.normal(ub, __fdiv_rn(eps, 3.f));
             sort_regs<NB>(ub, nb);
 #pragma unroll
             for (int i = 0; i < NB; ++i)
                 if (i < nb) ub[i] = __fadd_rn(d, fminf(fmaxf(ub[i], -eps), eps));
         } else {
             // stratified_bins(d - eps, d + other_eps, n_bins) -- vmap.py:538-542
-            if (rng) {
-                uniform_run<NB>(g, 6, (uint64_t)ray * nb, nb, ub);
-            } else {
-                const size_t row = ((size_t)obj * n_rays + (a.tape_by_rank ? rk_oth : ray)) * nb;
-#pragma unroll
-                for (int i = 0; i < NB; ++i)
-                    if (i < nb) ub[i] = a.r_other[row + i];
-            }
+            dr.other(ub);
             const float lo = __fsub_rn(d, eps), hi = __fadd_rn(d, a.other_eps);
             const float range = __fsub_rn(hi, lo);
             const float blen = __fdiv_rn(range, (float)nb);
@@ -279,8 +162,8 @@ __device__ __forceinline__ void sample_ray_b(const SampleK& k, const Rng& g, int
         }
     }
     // rays: dir_W = R dir_C, origin = T[:3,3] (utils.py:324-336); points = o + d*z (vmap.py:548-549)
-    const float* T = a.t_wc[obj] + 16 * p.kf;
-    const float* dc = a.rays_dir + ((size_t)p.iw * a.H + p.ih) * 3;
+    const float* T = a.t_wc[obj] + 16 * kf;
+    const float* dc = a.rays_dir + ((size_t)iw * a.H + ih) * 3;
     const float dx = dc[0], dy = dc[1], dz = dc[2];
     const float wx = T[0] * dx + T[1] * dy + T[2] * dz;
     const float wy = T[4] * dx + T[5] * dy + T[6] * dz;
@@ -297,6 +180,121 @@ __device__ __forceinline__ void sample_ray_b(const SampleK& k, const Rng& g, int
     }
 }
 
+// draws read from the caller's tapes; row = rank of the ray inside its class (tape_by_rank) or the ray index
+template <int NC, int NB>
+struct TapeDraws {
+    const oo_sample_args& a;
+    size_t row_inv, row_val, row_obj, row_oth;
+    __device__ __forceinline__ void invalid(float* u) const {
+        const int S = a.n_c2s + a.n_bins;
+#pragma unroll
+        for (int i = 0; i < NC + NB; ++i)
+            if (i < S) u[i] = a.r_invalid[row_inv * S + i];
+    }
+    __device__ __forceinline__ void valid(float* uc) const {
+#pragma unroll
+        for (int i = 0; i < NC; ++i)
+            if (i < a.n_c2s) uc[i] = a.r_valid[row_val * a.n_c2s + i];
+    }
+    __device__ __forceinline__ void normal(float* ub, float) const {
+#pragma unroll
+        for (int i = 0; i < NB; ++i)
+            if (i < a.n_bins) ub[i] = a.r_normal[row_obj * a.n_bins + i];
+    }
+    __device__ __forceinline__ void other(float* ub) const {
+#pragma unroll
+        for (int i = 0; i < NB; ++i)
+            if (i < a.n_bins) ub[i] = a.r_other[row_oth * a.n_bins + i];
+    }
+};
+
+// ---- the counter RNG's ray-blocked stream (rng_mode 1; oo_rng_fill_rows produces the same values as tapes) ----------
+// Ray r of object `oid` in frame `frame` owns the words w[4 j + c] = word c of philox(counter = (r, j, oid, 8 frame + 1)):
+//   w[0] = u_w, w[1] = u_h, w[2 .. 2 + n_c2s) = cam->surface draws, and from B0 = 4 ceil((2 + n_c2s) / 4) the bin draws:
+//   w[B0 + i] uniform (i < S for an invalid-depth ray, i < n_bins for an other-object ray), or for a this-object ray the
+//   Box-Muller pairs (w[B0 + 2k], w[B0 + 2k + 1]) -> normals 2k (cos) and 2k + 1 (sin).
+// Every ray therefore needs ceil(words / 4) Philox blocks and no word is computed twice; the keyframe draw of frame slot f
+// stays element f of stream 8 frame + 0.
+__host__ __device__ constexpr int ray_b0(int nc) { return 4 * ((2 + nc + 3) / 4); }
+
+__device__ __forceinline__ uint4 ray_block(const Rng& g, uint32_t ray, uint32_t j) {
+    return philox4x32_10(make_uint4(ray, j, g.oid, 8u * g.frame + 1u), g.key);
+}
+__device__ __forceinline__ float u24(uint32_t w) { return (float)(w >> 8) * TWO_M24; }
+__device__ __forceinline__ void box_muller(uint32_t a, uint32_t b, float std, float& n0, float& n1) {   // as k_rng_fill
+    const float u0 = ((float)(a >> 8) + 1.f) * TWO_M24, u1 = (float)(b >> 8) * TWO_M24;
+    const float rad = sqrtf(-2.f * logf(u0)) * std;
+    float sn, cs;
+    sincospif(2.f * u1, &sn, &cs);
+    n0 = rad * cs;
+    n1 = rad * sn;
+}
+
+// EXACT: n_c2s == NC and n_bins == NB, every word index is a compile-time constant after unrolling.  Otherwise the bounds
+// are upper bounds and each word is fetched on its own (one Philox block per word: correct, slow, not a shipped configuration).
+template <int NC, int NB, bool EXACT>
+struct CounterDraws {
+    static constexpr int NP = (NB + 1) / 2;                                     // Box-Muller pairs
+    static constexpr int NWC = 4 * ((NC + 2 + 3) / 4);                          // words of the blocks holding u_w, u_h, r_valid
+    static constexpr int NWB = 4 * (((NC + NB > 2 * NP ? NC + NB : 2 * NP) + 3) / 4);   // words of the bin blocks
+    const oo_sample_args& a;
+    const Rng& g;
+    uint32_t ray;
+    uint32_t wc[EXACT ? NWC : 1], wb[EXACT ? NWB : 1];
+    // EXACT: all blocks of the ray are evaluated once, before the (divergent) class branches of place_ray -- the three
+    // classes read the same bin words, so a warp with mixed classes does not evaluate Philox once per class
+    __device__ __forceinline__ CounterDraws(const oo_sample_args& a_, const Rng& g_, uint32_t ray_) : a(a_), g(g_), ray(ray_) {
+        if (EXACT) {
+#pragma unroll
+            for (int j = 0; j < NWC / 4; ++j) {
+                const uint4 r = ray_block(g, ray, (uint32_t)j);
+                wc[4 * j] = r.x; wc[4 * j + 1] = r.y; wc[4 * j + 2] = r.z; wc[4 * j + 3] = r.w;
+            }
+#pragma unroll
+            for (int j = 0; j < NWB / 4; ++j) {
+                const uint4 r = ray_block(g, ray, (uint32_t)(ray_b0(NC) / 4 + j));
+                wb[4 * j] = r.x; wb[4 * j + 1] = r.y; wb[4 * j + 2] = r.z; wb[4 * j + 3] = r.w;
+            }
+        }
+    }
+    // generic instantiation: word `idx` of the ray on its own
+    __device__ __forceinline__ uint32_t word(int idx) const {
+        const uint4 r = ray_block(g, ray, (uint32_t)(idx >> 2));
+        const int c = idx & 3;
+        return c == 0 ? r.x : c == 1 ? r.y : c == 2 ? r.z : r.w;
+    }
+    __device__ __forceinline__ void invalid(float* u) const {
+        const int nc = EXACT ? NC : a.n_c2s, S = nc + (EXACT ? NB : a.n_bins);
+#pragma unroll
+        for (int i = 0; i < NC + NB; ++i)
+            if (i < S) u[i] = u24(EXACT ? wb[i] : word(ray_b0(nc) + i));
+    }
+    __device__ __forceinline__ void valid(float* uc) const {
+        const int nc = EXACT ? NC : a.n_c2s;
+#pragma unroll
+        for (int i = 0; i < NC; ++i)
+            if (i < nc) uc[i] = u24(EXACT ? wc[i + 2] : word(2 + i));
+    }
+    __device__ __forceinline__ void normal(float* ub, float std) const {
+        const int nc = EXACT ? NC : a.n_c2s, nb = EXACT ? NB : a.n_bins;
+#pragma unroll
+        for (int p = 0; p < NP; ++p)
+            if (2 * p < nb) {
+                float n0, n1;
+                if (EXACT) box_muller(wb[2 * p], wb[2 * p + 1], std, n0, n1);
+                else box_muller(word(ray_b0(nc) + 2 * p), word(ray_b0(nc) + 2 * p + 1), std, n0, n1);
+                ub[2 * p] = n0;
+                if (2 * p + 1 < NB && 2 * p + 1 < nb) ub[2 * p + 1] = n1;
+            }
+    }
+    __device__ __forceinline__ void other(float* ub) const {
+        const int nc = EXACT ? NC : a.n_c2s, nb = EXACT ? NB : a.n_bins;
+#pragma unroll
+        for (int i = 0; i < NB; ++i)
+            if (i < nb) ub[i] = u24(EXACT ? wb[i] : word(ray_b0(nc) + i));
+    }
+};
+
 __device__ __forceinline__ Rng make_rng(const oo_sample_args& a, int obj) {
     Rng g;
     g.key = make_uint2((uint32_t)a.seed, (uint32_t)(a.seed >> 32));
@@ -305,7 +303,7 @@ __device__ __forceinline__ Rng make_rng(const oo_sample_args& a, int obj) {
     return g;
 }
 
-// ---- tape mode (and the general path): one 1024-thread CTA per object, ranks by block scan -------------------------
+// ---- tape mode: one 1024-thread CTA per object, ranks by block scan --------------------------------------------------
 template <int NC, int NB>
 __global__ void __launch_bounds__(NTH, 1) k_sample(const SampleK k) {
     const oo_sample_args& a = k.a;
@@ -317,12 +315,15 @@ __global__ void __launch_bounds__(NTH, 1) k_sample(const SampleK k) {
     __shared__ float sh_max[32];
     __shared__ int sh_oob;
     if (tid == 0) sh_oob = 0;
-    const Rng g = make_rng(a, obj);
     int n_inv = 0, n_obj = 0, n_oth = 0, oob = 0;
     float dmax = -INFINITY;
+    auto pixel_of = [&](int ray) {
+        const size_t ui = (size_t)obj * n_rays + ray;
+        return pixel_from_uniforms(a, obj, (int)a.kf_ids[(size_t)obj * a.n_frames + ray / a.n_samples], a.u_w[ui], a.u_h[ui]);
+    };
     for (int ray = r_begin; ray < r_end; ++ray) {
         float d;
-        const int cls = sample_ray_a(a, g, obj, ray, n_rays, d, oob);
+        const int cls = gather_ray(a, obj, ray, n_rays, pixel_of(ray), d, oob);
         dmax = fmaxf(dmax, d);
         n_inv += cls == 0; n_obj += cls == 1; n_oth += cls == 2;
     }
@@ -364,9 +365,14 @@ __global__ void __launch_bounds__(NTH, 1) k_sample(const SampleK k) {
     for (int ray = r_begin; ray < r_end; ++ray) {
         const size_t orow = (size_t)obj * n_rays + ray;
         const int S = a.n_c2s + a.n_bins;
-        sample_ray_b<NC, NB>(k, g, obj, ray, n_rays, rk_inv, ray - rk_inv, rk_obj, rk_oth, max_bound, a.z + orow * S, a.pcs + orow * S * 3);
-        const float d = a.gt_depth[(size_t)obj * n_rays + ray];
-        const int state = a.labels[(size_t)obj * n_rays + ray];
+        const RayPix p = pixel_of(ray);
+        const float d = a.gt_depth[orow];
+        const int state = a.labels[orow];
+        const size_t base = (size_t)obj * n_rays;
+        const bool by_rank = a.tape_by_rank != 0;
+        const TapeDraws<NC, NB> dr{a, base + (by_rank ? rk_inv : ray), base + (by_rank ? ray - rk_inv : ray),
+                                   base + (by_rank ? rk_obj : ray), base + (by_rank ? rk_oth : ray)};
+        place_ray<NC, NB>(k, obj, p.kf, p.iw, p.ih, d, state, max_bound, dr, a.z + orow * S, a.pcs + orow * S * 3);
         if (d <= a.min_bound) ++rk_inv;
         else if (state == 1) ++rk_obj;
         else ++rk_oth;
@@ -374,15 +380,26 @@ __global__ void __launch_bounds__(NTH, 1) k_sample(const SampleK k) {
 }
 
 // ---- counter-RNG mode: no ranks are needed, so every ray is independent: two fully parallel launches with the batch
-// max depth of each object (non-negative floats order like their bit patterns) exchanged through a tiny global array
-__global__ void __launch_bounds__(256) k_sample_a(const SampleK k, int* __restrict__ max_bits) {
+// max depth of each object (non-negative floats order like their bit patterns) exchanged through a tiny global array.
+// Pass A draws the pixel (keyframe word + block 0 of the ray), gathers, writes the per-ray outputs and leaves the pixel
+// packed in 32 bits (kf | w << 5 | h << 16) for pass B, which only draws the words its class consumes.
+__global__ void __launch_bounds__(256) k_sample_a(const SampleK k, int* __restrict__ max_bits, int* __restrict__ pix_pack) {
     const oo_sample_args& a = k.a;
     const int obj = blockIdx.y, n_rays = a.n_frames * a.n_samples;
     const int ray = blockIdx.x * blockDim.x + threadIdx.x;
     const Rng g = make_rng(a, obj);
     float d = 0.f;
     int oob = 0;
-    if (ray < n_rays) sample_ray_a(a, g, obj, ray, n_rays, d, oob);
+    if (ray < n_rays) {
+        const int f = ray / a.n_samples, nk = a.n_keyframes[obj];
+        int kf;
+        if (nk > 2 && f >= a.n_frames - 2) kf = a.latest[2 * obj + (f - (a.n_frames - 2))];       // vmap.py:398-400
+        else kf = min((int)(g.uniform(0, (uint64_t)f) * (float)nk), nk - 1);
+        const uint4 r0 = ray_block(g, (uint32_t)ray, 0u);
+        const RayPix p = pixel_from_uniforms(a, obj, kf, u24(r0.x), u24(r0.y));
+        gather_ray(a, obj, ray, n_rays, p, d, oob);
+        pix_pack[(size_t)obj * n_rays + ray] = p.kf | (p.iw << 5) | (p.ih << 16);
+    }
     d = fmaxf(d, 0.f);
 #pragma unroll
     for (int o = 16; o > 0; o >>= 1) d = fmaxf(d, __shfl_xor_sync(0xffffffffu, d, o));
@@ -393,8 +410,8 @@ __global__ void __launch_bounds__(256) k_sample_a(const SampleK k, int* __restri
 // One thread places the samples of one ray into the CTA's staging tile (z [256][S], points [256][S][3]); the tile is a
 // contiguous range of the outputs and leaves with 128-bit, fully coalesced stores (a thread writing its own 40 B / 120 B
 // rows directly costs one 32-byte sector per 4-byte store).
-template <int NC, int NB>
-__global__ void __launch_bounds__(256) k_sample_b(const SampleK k, const int* __restrict__ max_bits) {
+template <int NC, int NB, bool EXACT>
+__global__ void __launch_bounds__(256) k_sample_b(const SampleK k, const int* __restrict__ max_bits, const int* __restrict__ pix_pack) {
     extern __shared__ __align__(16) float tile[];
     const oo_sample_args& a = k.a;
     const int obj = blockIdx.y, n_rays = a.n_frames * a.n_samples, S = a.n_c2s + a.n_bins;
@@ -404,8 +421,11 @@ __global__ void __launch_bounds__(256) k_sample_b(const SampleK k, const int* __
     float* pt = tile + (size_t)blockDim.x * S;
     if (ray < n_rays) {
         const Rng g = make_rng(a, obj);
-        sample_ray_b<NC, NB>(k, g, obj, ray, n_rays, 0, 0, 0, 0, __int_as_float(max_bits[obj]), zt + threadIdx.x * S,
-                             pt + threadIdx.x * S * 3);
+        const size_t o = (size_t)obj * n_rays + ray;
+        const int pk = pix_pack[o];
+        const CounterDraws<NC, NB, EXACT> dr(a, g, (uint32_t)ray);
+        place_ray<NC, NB>(k, obj, pk & 31, (pk >> 5) & 2047, pk >> 16, a.gt_depth[o], a.labels[o], __int_as_float(max_bits[obj]), dr,
+                          zt + threadIdx.x * S, pt + threadIdx.x * S * 3);
     }
     __syncthreads();
     const size_t row0 = (size_t)obj * n_rays + ray0;
@@ -420,6 +440,29 @@ __global__ void __launch_bounds__(256) k_sample_b(const SampleK k, const int* __
     } else {
         for (int i = threadIdx.x; i < nz; i += blockDim.x) zg[i] = zt[i];
         for (int i = threadIdx.x; i < np; i += blockDim.x) pg[i] = pt[i];
+    }
+}
+
+// tapes of the ray-blocked stream: out[o][row][w], w < row_words, = word w of row `row` (uniform, or the Box-Muller normal of
+// its pair) -- the values rng_mode 1 draws in-kernel for ray = row
+__global__ void k_rng_fill_rows(uint64_t seed, uint32_t frame, const int32_t* __restrict__ obj_ids, int n_rows, int row_words,
+                                int kind, float std, float* __restrict__ out) {
+    const int o = blockIdx.y, nblk = (row_words + 3) / 4;
+    const uint32_t oid = (uint32_t)obj_ids[o];
+    const long long n = (long long)n_rows * nblk;
+    for (long long e = (long long)blockIdx.x * blockDim.x + threadIdx.x; e < n; e += (long long)gridDim.x * blockDim.x) {
+        const uint32_t row = (uint32_t)(e / nblk), j = (uint32_t)(e % nblk);
+        const uint4 r = philox4x32_10(make_uint4(row, j, oid, frame), make_uint2((uint32_t)seed, (uint32_t)(seed >> 32)));
+        float v[4];
+        if (kind == 0) {
+            v[0] = u24(r.x); v[1] = u24(r.y); v[2] = u24(r.z); v[3] = u24(r.w);
+        } else {
+            box_muller(r.x, r.y, std, v[0], v[1]);
+            box_muller(r.z, r.w, std, v[2], v[3]);
+        }
+        float* dst = out + ((size_t)o * n_rows + row) * row_words + 4 * j;
+        for (int i = 0; i < 4; ++i)
+            if (4 * (int)j + i < row_words) dst[i] = v[i];
     }
 }
 
@@ -529,30 +572,35 @@ extern "C" int oo_sample_rays(const oo_sample_args* a, void* stream) {
     if (a->rng_mode) {
         OO_REQUIRE(a->min_bound >= 0.f, "oo_sample_rays: the parallel path assumes min_bound >= 0");
         // per-object batch-max scratch: one small allocation per process, grown on demand (calls are not re-entrant)
+        OO_REQUIRE(a->W <= 2048 && a->H <= 32768, "oo_sample_rays: the packed pixel needs W <= 2048, H <= 32768");
+        const int n_rays = a->n_frames * a->n_samples;
+        // per-object batch-max + per-ray packed pixel scratch: one allocation per process, grown on demand (calls are not
+        // re-entrant)
         static int* max_bits = nullptr;
-        static int max_cap = 0;
-        if (a->n_obj > max_cap) {
+        static size_t max_cap = 0;
+        const size_t need = (size_t)a->n_obj * (1 + (size_t)n_rays);
+        if (need > max_cap) {
             if (max_bits) OO_CUDA(cudaFree(max_bits));
-            max_cap = a->n_obj < 1024 ? 1024 : 2 * a->n_obj;
+            max_cap = need < (1u << 20) ? (1u << 20) : 2 * need;
             OO_CUDA(cudaMalloc((void**)&max_bits, max_cap * sizeof(int)));
         }
+        int* pix_pack = max_bits + a->n_obj;
         OO_CUDA(cudaMemsetAsync(max_bits, 0, a->n_obj * sizeof(int), (cudaStream_t)stream));
-        const int n_rays = a->n_frames * a->n_samples;
         const dim3 grid((n_rays + 255) / 256, a->n_obj);
-        k_sample_a<<<grid, 256, 0, (cudaStream_t)stream>>>(k, max_bits);
+        k_sample_a<<<grid, 256, 0, (cudaStream_t)stream>>>(k, max_bits, pix_pack);
         OO_LAUNCH_CHECK();
         const size_t tile_bytes = (size_t)256 * S * 4 * sizeof(float);        // z [256][S] + points [256][S][3]; <= 128 KB (S <= 32)
         // one instantiation per launch (exact for the shipped 1 + 9 and 5 + 9 bins, upper bounds otherwise): per-ray arrays in
         // registers and a code size the instruction cache holds
-#define OO_LAUNCH_B(NC_, NB_)                                                                                               \
-        do {                                                                                                                \
-            OO_CUDA(cudaFuncSetAttribute(k_sample_b<NC_, NB_>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)tile_bytes)); \
-            k_sample_b<NC_, NB_><<<grid, 256, tile_bytes, (cudaStream_t)stream>>>(k, max_bits);                              \
+#define OO_LAUNCH_B(NC_, NB_, EX_)                                                                                                \
+        do {                                                                                                                      \
+            OO_CUDA(cudaFuncSetAttribute(k_sample_b<NC_, NB_, EX_>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)tile_bytes)); \
+            k_sample_b<NC_, NB_, EX_><<<grid, 256, tile_bytes, (cudaStream_t)stream>>>(k, max_bits, pix_pack);                     \
         } while (0)
-        if (a->n_c2s == 1 && a->n_bins == 9) OO_LAUNCH_B(1, 9);
-        else if (a->n_c2s == 5 && a->n_bins == 9) OO_LAUNCH_B(5, 9);
-        else if (a->n_c2s <= 8 && a->n_bins <= 12) OO_LAUNCH_B(8, 12);
-        else OO_LAUNCH_B(16, 16);
+        if (a->n_c2s == 1 && a->n_bins == 9) OO_LAUNCH_B(1, 9, true);
+        else if (a->n_c2s == 5 && a->n_bins == 9) OO_LAUNCH_B(5, 9, true);
+        else if (a->n_c2s <= 8 && a->n_bins <= 12) OO_LAUNCH_B(8, 12, false);
+        else OO_LAUNCH_B(16, 16, false);
 #undef OO_LAUNCH_B
         OO_LAUNCH_CHECK();
         return 0;
@@ -561,6 +609,17 @@ extern "C" int oo_sample_rays(const oo_sample_args* a, void* stream) {
     else if (a->n_c2s == 5 && a->n_bins == 9) k_sample<5, 9><<<a->n_obj, NTH, 0, (cudaStream_t)stream>>>(k);
     else if (a->n_c2s <= 8 && a->n_bins <= 12) k_sample<8, 12><<<a->n_obj, NTH, 0, (cudaStream_t)stream>>>(k);
     else k_sample<16, 16><<<a->n_obj, NTH, 0, (cudaStream_t)stream>>>(k);
+    OO_LAUNCH_CHECK();
+    return 0;
+}
+
+extern "C" int oo_rng_fill_rows(uint64_t seed, uint32_t frame, const int32_t* obj_ids, int n_obj, int n_rows, int row_words,
+                                int kind, float std, float* out, void* stream) {
+    OO_REQUIRE(obj_ids && out && n_obj > 0 && n_rows > 0 && row_words > 0 && (kind == 0 || kind == 1), "oo_rng_fill_rows: bad argument");
+    const long long n = (long long)n_rows * ((row_words + 3) / 4);
+    int gx = (int)((n + 255) / 256);
+    if (gx > 148 * 8) gx = 148 * 8;
+    k_rng_fill_rows<<<dim3(gx, n_obj), 256, 0, (cudaStream_t)stream>>>(seed, frame, obj_ids, n_rows, row_words, kind, std, out);
     OO_LAUNCH_CHECK();
     return 0;
 }

@@ -151,6 +151,16 @@ def rng_fill(out, seed, frame, obj_ids, kind="uniform", std=1.0):
     return out
 
 
+def rng_fill_rows(n_obj_rows_words, seed, frame, obj_ids, kind="uniform", std=1.0):
+    """Ray-blocked counter tapes [n_obj, n_rows, row_words] (oo_rng_fill_rows): what K2 draws in-kernel for ray = row."""
+    n, rows, words = n_obj_rows_words
+    out = torch.empty(n, rows, words, dtype=torch.float32, device=obj_ids.device)
+    with _dev(out):
+        check(lib().oo_rng_fill_rows(int(seed), int(frame), ptr(obj_ids), n, rows, words, 0 if kind == "uniform" else 1,
+                                     float(std), ptr(out), stream()), "oo_rng_fill_rows")
+    return out
+
+
 def zmerge(masks, depths, rgbs, is_bg):
     """Sequential strict depth test across objects in order (train.py:577-594).
     masks [K,W,H] u8/bool, depths [K,W,H] f32, rgbs [K,W,H,3] u8, is_bg [K]."""

@@ -68,15 +68,18 @@ def device_tapes(objects, n_frames, n_samples, n_c2s, n_bins, eps, seed, frame, 
     for i, o in enumerate(objects):              # forced latest two keyframes (host bookkeeping, vmap.py:398-400)
         if o.n_keyframes > 2:
             kf[i, -2:] = torch.as_tensor(o.lastest_kf_queue[-2:], device=device)
+    # every other draw of ray r: the ray-blocked stream 8*frame + 1 (include/openobj_b200.h, oo_sample_args.rng_mode)
+    b0 = 4 * ((2 + n_c2s + 3) // 4)
+    words = b0 + 4 * ((max(S, 2 * ((n_bins + 1) // 2)) + 3) // 4)
+    U = ops.rng_fill_rows((n, n_rays, words), seed, 8 * frame + 1, ids)
+    Nn = ops.rng_fill_rows((n, n_rays, words), seed, 8 * frame + 1, ids, "normal", eps / 3.)
     return SampleTapes(
         kf_ids=kf.contiguous(),
-        u_w=ops.rng_fill(torch.empty(n, n_rays, **f32), seed, 8 * frame + 1, ids),
-        u_h=ops.rng_fill(torch.empty(n, n_rays, **f32), seed, 8 * frame + 2, ids),
-        r_invalid=ops.rng_fill(torch.empty(n, n_rays * S, **f32), seed, 8 * frame + 3, ids).view(n, n_rays, S),
-        r_valid=ops.rng_fill(torch.empty(n, n_rays * n_c2s, **f32), seed, 8 * frame + 4, ids).view(n, n_rays, n_c2s),
-        r_normal=ops.rng_fill(torch.empty(n, n_rays * n_bins, **f32), seed, 8 * frame + 5, ids, "normal", eps / 3.).view(
-            n, n_rays, n_bins),
-        r_other=ops.rng_fill(torch.empty(n, n_rays * n_bins, **f32), seed, 8 * frame + 6, ids).view(n, n_rays, n_bins),
+        u_w=U[..., 0].contiguous(), u_h=U[..., 1].contiguous(),
+        r_invalid=U[..., b0:b0 + S].contiguous(),
+        r_valid=U[..., 2:2 + n_c2s].contiguous(),
+        r_normal=Nn[..., b0:b0 + n_bins].contiguous(),
+        r_other=U[..., b0:b0 + n_bins].contiguous(),
         by_rank=False)
 
 

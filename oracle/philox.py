@@ -44,3 +44,27 @@ def normal(seed, frame, oid, n, std):
     out = np.stack([ra * np.cos(2 * np.pi * u1.astype(np.float64)), ra * np.sin(2 * np.pi * u1.astype(np.float64)),
                     rb * np.cos(2 * np.pi * u3.astype(np.float64)), rb * np.sin(2 * np.pi * u3.astype(np.float64))], axis=1)
     return out.reshape(-1)[:n].astype(np.float32)
+
+
+def words_rows(seed, frame, oid, n_rows, row_words):
+    """Ray-blocked stream (oo_rng_fill_rows): word w of row r = word (w % 4) of philox(counter=(r, w // 4, oid, frame))."""
+    nblk = (row_words + 3) // 4
+    rows = np.repeat(np.arange(n_rows, dtype=np.uint32), nblk)
+    blk = np.tile(np.arange(nblk, dtype=np.uint32), n_rows)
+    r = philox4x32_10(rows, blk, np.full(rows.shape, oid, np.uint32), np.full(rows.shape, frame, np.uint32),
+                      seed & 0xFFFFFFFF, (seed >> 32) & 0xFFFFFFFF)
+    return np.stack(r, axis=1).reshape(n_rows, 4 * nblk)
+
+
+def uniform_rows(seed, frame, oid, n_rows, row_words):
+    w = words_rows(seed, frame, oid, n_rows, row_words)
+    return ((w >> np.uint32(8)).astype(np.float32) * np.float32(2.0 ** -24))[:, :row_words]
+
+
+def normal_rows(seed, frame, oid, n_rows, row_words, std):
+    w = words_rows(seed, frame, oid, n_rows, row_words).reshape(n_rows, -1, 2)
+    f = lambda x: (x >> np.uint32(8)).astype(np.float32)
+    u0, u1 = (f(w[..., 0]) + 1) * np.float32(2.0 ** -24), f(w[..., 1]) * np.float32(2.0 ** -24)
+    rad = np.sqrt(-2 * np.log(u0.astype(np.float64))) * std
+    out = np.stack([rad * np.cos(2 * np.pi * u1.astype(np.float64)), rad * np.sin(2 * np.pi * u1.astype(np.float64))], axis=-1)
+    return out.reshape(n_rows, -1)[:, :row_words].astype(np.float32)

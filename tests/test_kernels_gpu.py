@@ -173,6 +173,22 @@ def test_rng_fill_is_philox_and_shard_independent():
     assert abs(float(nrm.std()) - 0.1 / 3) < 2e-3 and 0.0 <= float(out.min()) and float(out.max()) < 1.0
 
 
+def test_rng_fill_rows_is_the_ray_blocked_philox_stream():
+    from openobj_b200 import ops
+    ids = torch.tensor([7, 3], dtype=torch.int32, device=DEV)
+    seed = 0xFEDCBA9876543210
+    for words in (16, 14, 5):
+        out = ops.rng_fill_rows((2, 333, words), seed, 41, ids)
+        for i, oid in enumerate([7, 3]):
+            assert np.array_equal(out[i].cpu().numpy(), philox.uniform_rows(seed, 41, oid, 333, words))
+    nrm = ops.rng_fill_rows((2, 2000, 14), 9, 1, ids, "normal", 0.1 / 3)
+    np.testing.assert_allclose(nrm[0].cpu().numpy(), philox.normal_rows(9, 1, 7, 2000, 14, 0.1 / 3), rtol=2e-5, atol=2e-7)
+    assert abs(float(nrm.std()) - 0.1 / 3) < 2e-3
+    # rows are independent of how many rows / which objects are generated with them
+    one = ops.rng_fill_rows((1, 100, 14), 9, 1, ids[:1], "normal", 0.1 / 3)
+    assert torch.equal(one[0], nrm[0, :100])
+
+
 def test_render_object_vs_reference_golden():
     """render_2D_syn through K5 with the reference's jitter (by rank): mask, depth, rgb (+-1 LSB), feature map."""
     from openobj_b200 import cfg as C, utils as U, vmap as V
