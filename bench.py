@@ -20,9 +20,13 @@ import time
 
 ROOT = os.path.dirname(os.path.abspath(__file__))
 sys.path.insert(0, ROOT)
-# stdout carries exactly ONE JSON line: NCCL's version banner / debug output (printed to stdout when the box sets
-# NCCL_DEBUG) goes to stderr instead
+# stdout carries exactly ONE JSON line.  NCCL prints its version banner with printf on file descriptor 1 (seen on the
+# 2-GPU box even with NCCL_DEBUG_FILE set), so descriptor 1 is pointed at stderr for the whole process and the JSON
+# line goes through a duplicate of the original stdout.
 os.environ.setdefault("NCCL_DEBUG_FILE", "/dev/stderr")
+sys.stdout.flush()
+_JSON_OUT = os.fdopen(os.dup(1), "w")
+os.dup2(2, 1)
 
 ITERS = 100           # iters_per_frame (room_0.json:34)
 R = 120               # n_per_optim (room_0.json:35)
@@ -183,7 +187,7 @@ def run_reference_arm(args):
         "e2e": {"value": r["rays_per_s"], "unit": "rays/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
         "gpu_launches": 0,
     }
-    print(json.dumps(line))
+    print(json.dumps(line), file=_JSON_OUT, flush=True)
     return 0
 
 
@@ -470,7 +474,7 @@ def run_ours(args):
             out["cpu_baseline"] = {"value": cpu["rays_per_s"], "unit": "rays/s", "cores": cpu["cores"], "kind": "port",
                                    "sample": "oracle port (torch-CPU restatement of the reference step) on 8 of the %d objects, "
                                              "%d steps in %.1f s" % (n_obj, cpu["steps_done"], cpu["seconds"])}
-        print(json.dumps(out))
+        print(json.dumps(out), file=_JSON_OUT, flush=True)
     D.barrier()
     if world > 1:
         torch.distributed.destroy_process_group()

@@ -460,6 +460,27 @@ def gen_eval_grid(m):
     return out
 
 
+def gen_checkpoint(m):
+    """A per-object checkpoint written by the reference's sceneObject.save_checkpoints (vmap.py:556-576) and what the
+    reference's Trainer.eval_points returns for it at a few points: the drop-in must load the file and reproduce them."""
+    torch.manual_seed(31)
+    cfg = small_cfg(W=40, H=30)
+    g = torch.Generator().manual_seed(32)
+    rgb, depth, state, bbox, T, part = synth_frame(g, 100, 60, with_part=False)
+    W, H = cfg.W, cfg.H
+    obj = m["vmap"].sceneObject(cfg, 7, rgb[:W, :H].contiguous(), depth[:W, :H].contiguous(), state[:W, :H].contiguous(),
+                                torch.tensor([0, W - 1, 0, H - 1]), T, 0)
+    obj.trainer.pe.B_layer.weight.data += 0.01 * torch.randn(21, 3)
+    obj.clip_feat = torch.randn(512)
+    obj.caption_feat = torch.randn(384)
+    obj.semantic_id = 3
+    obj.bbox3dour = None                       # an open3d / utils.BoundingBox object in a real run: not needed here
+    obj.save_checkpoints(OUT, 42)              # -> tests/golden/obj_7.pth
+    pts = torch.randn(64, 3, generator=g) * 0.8
+    occ, color, clip = obj.trainer.eval_points(pts)
+    return dict(points=pts, occ=occ, color=color, clip=clip[:8], clip_feat=obj.clip_feat, caption_feat=obj.caption_feat)
+
+
 def save(name, d):
     arrs = {k: (v.numpy() if torch.is_tensor(v) else np.asarray(v)) for k, v in d.items()}
     path = os.path.join(OUT, name)
@@ -473,6 +494,9 @@ def main():
     if "--only-eval" in sys.argv:               # added after the other files were frozen: do not touch them
         save("eval_grid.npz", gen_eval_grid(m))
         return
+    if "--only-ckpt" in sys.argv:
+        save("ckpt_expect.npz", gen_checkpoint(m))
+        return
     if "--only-bg" in sys.argv:                 # added after the other files were frozen: do not touch them
         save("bg_step.npz", gen_bg_step(m))
         return
@@ -482,6 +506,7 @@ def main():
     save("sample_bg.npz", gen_sampling(m, bg=True))
     save("render_obj.npz", gen_render(m))
     save("eval_grid.npz", gen_eval_grid(m))
+    save("ckpt_expect.npz", gen_checkpoint(m))
     with open(os.path.join(OUT, "keyframe_policy.json"), "w") as f:
         json.dump(gen_keyframe_policy(m), f)
     print("done; torch", torch.__version__)

@@ -101,3 +101,34 @@ def test_occupancy_activation_with_distances():
     torch.testing.assert_close(ops.occupancy_activation(a.to(DEV)).cpu(), torch.sigmoid(a), rtol=1e-6, atol=1e-7)
     torch.testing.assert_close(ops.occupancy_activation(a.to(DEV), dist.to(DEV)).cpu(),
                                render_rays.occupancy_activation(a, dist), rtol=1e-5, atol=1e-6)
+
+
+def test_reference_checkpoint_loads_and_round_trips(tmp_path):
+    """tests/golden/obj_7.pth was written by the REFERENCE's sceneObject.save_checkpoints
+    (vmap.py:556-576).  Our sceneObject.load_checkpoints reads it, eval_points reproduces what the reference's
+    Trainer.eval_points returned for it, and save_checkpoints writes the same keys / tensors back bit for bit."""
+    from openobj_b200 import cfg as C, vmap as V
+    exp = load("ckpt_expect.npz")
+    cfg = C.room0_config(w=40, h=30)
+    cfg.training_device = cfg.data_device = DEV
+    W, H = cfg.W, cfg.H
+    obj = V.sceneObject(cfg, 1, torch.zeros(W, H, 3, dtype=torch.uint8, device=DEV), torch.ones(W, H, device=DEV),
+                        torch.ones(W, H, dtype=torch.uint8, device=DEV), torch.tensor([0., W - 1, 0., H - 1]),
+                        torch.eye(4, device=DEV), 0)
+    src = os.path.join(GOLDEN, "obj_7.pth")
+    assert obj.load_checkpoints(src) is True
+    assert obj.obj_id == 7 and obj.semantic_id == 3 and obj.bbox_final and obj.trainer.obj_scale == 2.0
+    torch.testing.assert_close(obj.clip_feat, exp["clip_feat"], rtol=0, atol=0)
+    occ, color, clip = obj.trainer.eval_points(exp["points"].to(DEV))
+    torch.testing.assert_close(occ.cpu(), exp["occ"], rtol=1e-4, atol=2.5e-5)
+    torch.testing.assert_close(color.cpu(), exp["color"], rtol=1e-4, atol=1e-5)
+    torch.testing.assert_close(clip.cpu()[:8], exp["clip"], rtol=1e-4, atol=1e-4)
+    obj.save_checkpoints(str(tmp_path), 42)
+    a = torch.load(src, weights_only=False)
+    b = torch.load(os.path.join(str(tmp_path), "obj_7.pth"), weights_only=False)
+    assert list(a.keys()) == list(b.keys()) and b["epoch"] == 42
+    for part in ("FC_state_dict", "PE_state_dict"):
+        assert list(a[part].keys()) == list(b[part].keys())
+        for k in a[part]:
+            assert torch.equal(a[part][k], b[part][k].cpu()), (part, k)
+    assert obj.load_checkpoints(os.path.join(str(tmp_path), "missing.pth")) is None     # "ckpt not exist"

@@ -77,3 +77,19 @@ def test_product_never_imports_oracle():
             if f.endswith((".py", ".cu", ".h", ".cuh")):
                 src = open(os.path.join(dirpath, f)).read()
                 assert "openobj_oracle" not in src and "ref_harness" not in src and "import philox" not in src, f
+
+
+def test_reference_checkpoint_keys_are_the_drop_in_state_dict():
+    """tests/golden/obj_7.pth was written by the reference's sceneObject.save_checkpoints (vmap.py:556-576): its state-dict
+    keys and shapes are exactly what openobj_b200.model.OccupancyMap / embedding.UniDirsEmbed expose (no GPU needed)."""
+    from openobj_b200 import embedding, model
+    ck = torch.load(os.path.join(os.path.dirname(__file__), "golden", "obj_7.pth"), weights_only=False)
+    assert list(ck.keys()) == ["epoch", "FC_state_dict", "PE_state_dict", "obj_id", "bbox", "obj_scale", "clip_feat",
+                               "caption_feat", "semantic_id"]
+    fc = model.OccupancyMap(87, 42, hidden_size=32, clip_size=512)
+    pe = embedding.UniDirsEmbed(max_deg=5, scale=2.0)
+    assert list(ck["FC_state_dict"].keys()) == list(fc.state_dict().keys()) == list(layout.NAMES[:18])
+    assert {k: tuple(v.shape) for k, v in ck["FC_state_dict"].items()} == {k: tuple(v.shape) for k, v in fc.state_dict().items()}
+    assert list(ck["PE_state_dict"].keys()) == list(pe.state_dict().keys())
+    fc.load_state_dict(ck["FC_state_dict"])
+    pe.load_state_dict(ck["PE_state_dict"])
