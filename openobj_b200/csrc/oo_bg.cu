@@ -105,6 +105,24 @@ __device__ __forceinline__ void cp_async_commit() { asm volatile("cp.async.commi
 template <int N>
 __device__ __forceinline__ void cp_async_wait() { asm volatile("cp.async.wait_group %0;" ::"n"(N) : "memory"); }
 
+// Programmatic dependent launch between the GEMM kernels of a step (27 + 9 of its 47 launches): a kernel releases its
+// dependents when its main loop is done, so the next kernel's launch latency, block scheduling and index set-up overlap this
+// kernel's epilogue and tail; every kernel waits (griddepcontrol.wait = the previous grid has completed and its writes are
+// visible) before its first global access.  Kernels launched without the attribute are ordered as usual.
+__device__ __forceinline__ void pdl_wait() { asm volatile("griddepcontrol.wait;" ::: "memory"); }
+__device__ __forceinline__ void pdl_release() { asm volatile("griddepcontrol.launch_dependents;" ::: "memory"); }
+
+template <typename... KArgs, typename... Args>
+cudaError_t launch_pdl(void (*kernel)(KArgs...), dim3 grid, dim3 block, size_t smem, cudaStream_t st, Args... args) {
+    cudaLaunchConfig_t cfg = {};
+    cfg.gridDim = grid; cfg.blockDim = block; cfg.dynamicSmemBytes = smem; cfg.stream = st;
+    cudaLaunchAttribute at[1];
+    at[0].id = cudaLaunchAttributeProgrammaticStreamSerialization;
+    at[0].val.programmaticStreamSerializationAllowed = 1;
+    cfg.attrs = at; cfg.numAttrs = 1;
+    return cudaLaunchKernelEx(&cfg, kernel, KArgs(args)...);
+}
+
 template <bool AC, bool BC>
 __global__ void __launch_bounds__(256, 2) k_gemm(const GemmOp g) {
     extern __shared__ __align__(16) float gemm_sm[];
@@ -163,6 +181,7 @@ __global__ void __launch_bounds__(256, 2) k_gemm(const GemmOp g) {
     for (int mt = 0; mt < 2; ++mt)
 #pragma unroll
         for (int nt = 0; nt < 4; ++nt) acc[mt][nt][0] = acc[mt][nt][1] = acc[mt][nt][2] = acc[mt][nt][3] = 0.f;
+    pdl_wait();
 #pragma unroll 1
     for (int s = 0; s < GEMM_STAGES - 1; ++s) issue(c_begin + s * BK, s);
     int st = 0;
@@ -208,6 +227,7 @@ __global__ void __launch_bounds__(256, 2) k_gemm(const GemmOp g) {
     // value when accumulating) before the first store; a warp writes 128 contiguous bytes of a row.  The body is a short
     // rolled loop on purpose: a fully unrolled per-fragment epilogue was thousands of instructions executed once per warp,
     // and with K <= 215 that instruction stream, not the tensor pipe, set the kernel time.
+    pdl_release();
     cp_async_wait<0>();
     __syncthreads();
     constexpr int LDT = BJ + 8;
@@ -266,6 +286,7 @@ __global__ void __launch_bounds__(256, 2) k_gemm(const GemmOp g) {
 __global__ void __launch_bounds__(256) k_gemm_reduce(const GemmOp g) {
     const int je = gemm_je(g), n = g.I * je;
     const int e = (blockIdx.x * blockDim.x + threadIdx.x) >> 3, q = threadIdx.x & 7;
+    pdl_wait();
     float s = 0.f;
     if (e < n)
         for (int z = q; z < g.split; z += 8) s += g.part[(size_t)z * n + e];
@@ -304,13 +325,13 @@ int run_gemm(GemmOp g, int split, float* part, cudaStream_t st) {
         OO_CUDA(cudaFuncSetAttribute(k_gemm<false, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, GEMM_SMEM));
         attr_set = true;
     }
-    if (ac && bc) k_gemm<true, true><<<grid, 256, GEMM_SMEM, st>>>(g);
-    else if (ac) k_gemm<true, false><<<grid, 256, GEMM_SMEM, st>>>(g);
-    else if (bc) k_gemm<false, true><<<grid, 256, GEMM_SMEM, st>>>(g);
-    else k_gemm<false, false><<<grid, 256, GEMM_SMEM, st>>>(g);
+    if (ac && bc) OO_CUDA(launch_pdl(k_gemm<true, true>, grid, dim3(256), (size_t)GEMM_SMEM, st, g));
+    else if (ac) OO_CUDA(launch_pdl(k_gemm<true, false>, grid, dim3(256), (size_t)GEMM_SMEM, st, g));
+    else if (bc) OO_CUDA(launch_pdl(k_gemm<false, true>, grid, dim3(256), (size_t)GEMM_SMEM, st, g));
+    else OO_CUDA(launch_pdl(k_gemm<false, false>, grid, dim3(256), (size_t)GEMM_SMEM, st, g));
     OO_LAUNCH_CHECK();
     if (g.split > 1) {
-        k_gemm_reduce<<<(g.I * je * 8 + 255) / 256, 256, 0, st>>>(g);
+        OO_CUDA(launch_pdl(k_gemm_reduce, dim3((g.I * je * 8 + 255) / 256), dim3(256), (size_t)0, st, g));
         OO_LAUNCH_CHECK();
     }
     return 0;
