@@ -93,6 +93,7 @@ __device__ __forceinline__ float gemm_epilogue(const GemmOp& g, int i, int j, fl
 // (cp.async with zero fill outside the operand), so GEMM_STAGES - 1 tiles are in flight while one is multiplied:
 // with K <= 215 per layer the kernel is a chain of memory round trips unless several of them overlap.
 constexpr int GEMM_STAGES = 4;
+constexpr int BG_SPLIT_MAX = 320;
 constexpr int GEMM_SMEM = GEMM_STAGES * BK * (LDA_S + LDB_S) * (int)sizeof(float);
 static_assert(GEMM_SMEM >= BI * (BJ + 8) * (int)sizeof(float), "the epilogue tile reuses the pipeline stages");
 
@@ -134,7 +135,7 @@ __global__ void __launch_bounds__(256, 2) k_gemm(const GemmOp g) {
     // this thread's elements of the A / B tiles: (ii, cc) pairs and their global offsets (without the k-tile offset)
     int a_ii[NA], a_cc[NA], b_jj[NB_], b_cc[NB_];
     int a_off[NA], b_off[NB_];                    // element offsets fit 32 bits (checked in run_gemm)
-    bool a_ok[NA], b_ok[NB_], b_one[NB_];
+    bool a_ok[NA], b_ok[NB_];
 #pragma unroll
     for (int u = 0; u < NA; ++u) {
         const int e = tid + 256 * u;
@@ -150,7 +151,6 @@ __global__ void __launch_bounds__(256, 2) k_gemm(const GemmOp g) {
         b_cc[u] = BC ? e % BK : e / BJ;
         const int j = j0 + b_jj[u];
         b_ok[u] = j < g.J;
-        b_one[u] = j == g.J && g.ones_out != nullptr;
         b_off[u] = b_ok[u] ? j * (int)g.sbj + b_cc[u] * (int)g.sbc : 0;
     }
     const int sac = (int)g.sac, sbc = (int)g.sbc;
@@ -163,12 +163,8 @@ __global__ void __launch_bounds__(256, 2) k_gemm(const GemmOp g) {
             }
 #pragma unroll
             for (int u = 0; u < NB_; ++u) {
-                const bool in = c0 + b_cc[u] < c_end;
-                if (b_one[u]) Bs[st][b_cc[u]][b_jj[u]] = in ? 1.f : 0.f;
-                else {
-                    const bool ok = b_ok[u] && in;
-                    cp_async4(&Bs[st][b_cc[u]][b_jj[u]], ok ? g.B + (b_off[u] + c0 * sbc) : g.B, ok);
-                }
+                const bool ok = b_ok[u] && c0 + b_cc[u] < c_end;
+                cp_async4(&Bs[st][b_cc[u]][b_jj[u]], ok ? g.B + (b_off[u] + c0 * sbc) : g.B, ok);
             }
         }
         cp_async_commit();
@@ -181,6 +177,10 @@ __global__ void __launch_bounds__(256, 2) k_gemm(const GemmOp g) {
     for (int mt = 0; mt < 2; ++mt)
 #pragma unroll
         for (int nt = 0; nt < 4; ++nt) acc[mt][nt][0] = acc[mt][nt][1] = acc[mt][nt][2] = acc[mt][nt][3] = 0.f;
+    // ones_out: sum_c A(i, c) (the bias gradient = the product with a virtual column of ones) is accumulated from the
+    // staged A tiles by the CTAs of j-tile 0, thread = row; zero fill makes out-of-range rows / k contribute nothing
+    const bool row_sums = g.ones_out != nullptr && blockIdx.y == 0;
+    float rs = 0.f;
     pdl_wait();
 #pragma unroll 1
     for (int s = 0; s < GEMM_STAGES - 1; ++s) issue(c_begin + s * BK, s);
@@ -189,6 +189,10 @@ __global__ void __launch_bounds__(256, 2) k_gemm(const GemmOp g) {
         cp_async_wait<GEMM_STAGES - 2>();           // this thread's copies of tile c0 have landed ...
         __syncthreads();                            // ... and everybody's; the stage multiplied last iteration is free
         issue(c0 + (GEMM_STAGES - 1) * BK, st == 0 ? GEMM_STAGES - 1 : st - 1);
+        if (row_sums && tid < BI) {
+#pragma unroll
+            for (int k = 0; k < BK; ++k) rs += As[st][k][tid];
+        }
 #pragma unroll
         for (int k0 = 0; k0 < BK; k0 += 8) {
             uint32_t ah[2][4], al[2][4], bh[4][2], bl[4][2];
@@ -243,7 +247,15 @@ __global__ void __launch_bounds__(256, 2) k_gemm(const GemmOp g) {
     __syncthreads();
     const int jl = tid & (BJ - 1), j = j0 + jl, je = gemm_je(g);
     const int n_rows = min(BI, g.I - i0);
-    if (j >= je) return;
+    if (row_sums && tid < n_rows) {                             // column J of the partials / ones_out
+        const int i = i0 + tid;
+        if (g.split > 1) g.part[((size_t)blockIdx.z * g.I + i) * je + g.J] = rs;
+        else {
+            const float v = gemm_epilogue(g, i, g.J, rs);
+            g.ones_out[i] = g.accumulate ? g.ones_out[i] + v : v;
+        }
+    }
+    if (j >= g.J) return;
     const float* tp = tile + jl;
     int il = tid / BJ;                                          // 0..3; rows il, il + 4, ...
     if (g.split > 1) {
@@ -251,12 +263,11 @@ __global__ void __launch_bounds__(256, 2) k_gemm(const GemmOp g) {
         for (; il < n_rows; il += 4, dst += 4 * (size_t)je) *dst = tp[il * LDT];
         return;
     }
-    const bool ones = j == g.J;                                 // the virtual column: bias gradient of a non-split launch
-    const bool use_mask = g.mask != nullptr && j < g.mask_cols && !ones;
-    const float bias = (g.bias != nullptr && !ones) ? g.bias[j] : 0.f, mult = g.mult, post = g.post;
+    const bool use_mask = g.mask != nullptr && j < g.mask_cols;
+    const float bias = g.bias != nullptr ? g.bias[j] : 0.f, mult = g.mult, post = g.post;
     const int act = g.act, accumulate = g.accumulate;
-    const long long dstep = ones ? 4 : 4 * g.sci, mstep = 4 * g.smi;
-    float* dst = ones ? g.ones_out + i0 + il : g.C + (i0 + il) * g.sci + j * g.scj;
+    const long long dstep = 4 * g.sci, mstep = 4 * g.smi;
+    float* dst = g.C + (i0 + il) * g.sci + j * g.scj;
     const float* mp = use_mask ? g.mask + (i0 + il) * g.smi + j * g.smj : nullptr;
 #pragma unroll 1
     for (; il < n_rows; il += 16) {
@@ -300,13 +311,26 @@ __global__ void __launch_bounds__(256) k_gemm_reduce(const GemmOp g) {
     *dst = g.accumulate ? *dst + v : v;
 }
 
+// split > 1 asks for a split contraction (the weight gradients: K = all points); how many chunks is chosen here so that the
+// grid is ONE wave of two CTAs per SM: a CTA's time is its number of k-tiles, whatever share of its tile is real output
 int run_gemm(GemmOp g, int split, float* part, cudaStream_t st) {
-    g.split = split < 1 ? 1 : split;
+    static int n_sm = 0;
+    if (n_sm == 0) {
+        int dev = 0;
+        OO_CUDA(cudaGetDevice(&dev));
+        OO_CUDA(cudaDeviceGetAttribute(&n_sm, cudaDevAttrMultiProcessorCount, dev));
+    }
+    const int tiles = ((g.I + BI - 1) / BI) * ((g.J + BJ - 1) / BJ);
+    g.split = 1;
     g.chunk = g.K;
     g.part = part;
-    if (g.split > 1) {
-        g.chunk = ((g.K + g.split - 1) / g.split + BK - 1) / BK * BK;
+    if (split > 1) {
+        int want = 2 * n_sm / tiles;
+        if (want > BG_SPLIT_MAX) want = BG_SPLIT_MAX;
+        if (want < 1) want = 1;
+        g.chunk = ((g.K + want - 1) / want + BK - 1) / BK * BK;
         g.split = (g.K + g.chunk - 1) / g.chunk;
+        if (g.split < 2) { g.split = 2; g.chunk = ((g.K + 1) / 2 + BK - 1) / BK * BK; g.split = (g.K + g.chunk - 1) / g.chunk; }
     }
     const int je = g.J + (g.ones_out != nullptr ? 1 : 0);
     OO_REQUIRE((long long)g.I * (g.sai > 0 ? g.sai : 1) + (long long)g.K * (g.sac > 0 ? g.sac : 1) < (1LL << 31) &&
@@ -315,7 +339,7 @@ int run_gemm(GemmOp g, int split, float* part, cudaStream_t st) {
     OO_REQUIRE((long long)g.I * (g.sci > 0 ? g.sci : 1) + (long long)je * (g.scj > 0 ? g.scj : 1) < (1LL << 31) &&
                    (g.mask == nullptr || (long long)g.I * (g.smi > 0 ? g.smi : 1) + (long long)je * (g.smj > 0 ? g.smj : 1) < (1LL << 31)),
                "oo_bg gemm: output / mask larger than 2^31 elements");
-    const dim3 grid((g.I + BI - 1) / BI, (je + BJ - 1) / BJ, g.split);
+    const dim3 grid((g.I + BI - 1) / BI, (g.J + BJ - 1) / BJ, g.split);
     const bool ac = g.sac == 1, bc = g.sbc == 1;
     static bool attr_set = false;
     if (!attr_set) {
@@ -466,7 +490,7 @@ struct BgWs {
     long long total;
 };
 
-constexpr int BG_SPLIT = 64;
+constexpr int BG_SPLIT = 64;            // "split the contraction" request of the weight-gradient GEMMs (run_gemm picks the count)
 
 BgWs bg_ws_map(float* base, int h, int n_pts, int n_rays) {
     BgWs w;
@@ -483,7 +507,9 @@ BgWs bg_ws_map(float* base, int h, int n_pts, int n_rays) {
     w.loss_ws = take((long long)n_rays * oo_loss_ws_per_ray() + 8);
     w.ones = take(4);
     const long long maxij = (long long)C * (h + 1) > (long long)h * (h + E1 + 1) ? (long long)C * (h + 1) : (long long)h * (h + E1 + 1);
-    w.part = take((BG_SPLIT + 1) * maxij);
+    // split partials [split][I][J + 1]: split * tiles <= 2 SMs-worth of CTAs (<= 2 * 160 here) of BI x BJ outputs each
+    const long long part_wave = 2LL * 160 * BI * (BJ + 1);
+    w.part = take((BG_SPLIT + 1) * maxij > part_wave ? (BG_SPLIT + 1) * maxij : part_wave);
     w.emb_part = take(((M + EB_PTS - 1) / EB_PTS) * (NDIR * 3));
     w.grads = take(bg_layout(h).total);
     w.total = o;
