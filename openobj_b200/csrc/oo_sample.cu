@@ -88,9 +88,30 @@ __device__ __forceinline__ int gather_ray(const oo_sample_args& a, int obj, int 
     return invalid ? 0 : (c.w == 1 ? 1 : 2);
 }
 
+// the 25-exchange network for 9 inputs (Floyd; checked exhaustively with the 0-1 principle): columns, merge of the three
+// sorted rows of a 3 x 3 arrangement, clean-up
+__device__ __forceinline__ void cmpex(float& a, float& b) {
+    const float lo = fminf(a, b), hi = fmaxf(a, b);
+    a = lo; b = hi;
+}
+__device__ __forceinline__ void sort9(float* v) {
+    cmpex(v[0], v[1]); cmpex(v[3], v[4]); cmpex(v[6], v[7]);
+    cmpex(v[1], v[2]); cmpex(v[4], v[5]); cmpex(v[7], v[8]);
+    cmpex(v[0], v[1]); cmpex(v[3], v[4]); cmpex(v[6], v[7]);
+    cmpex(v[0], v[3]); cmpex(v[3], v[6]); cmpex(v[0], v[3]);
+    cmpex(v[1], v[4]); cmpex(v[4], v[7]); cmpex(v[1], v[4]);
+    cmpex(v[2], v[5]); cmpex(v[5], v[8]); cmpex(v[2], v[5]);
+    cmpex(v[1], v[3]); cmpex(v[5], v[7]); cmpex(v[2], v[6]); cmpex(v[4], v[6]);
+    cmpex(v[2], v[4]); cmpex(v[2], v[3]); cmpex(v[5], v[6]);
+}
+
 // ascending sort of n <= N values held in registers: odd-even transposition network (N rounds of compare-exchange)
 template <int N>
 __device__ __forceinline__ void sort_regs(float* v, int n) {
+    if (N == 9 && n == 9) {
+        sort9(v);
+        return;
+    }
 #pragma unroll
     for (int round = 0; round < N; ++round)
 #pragma unroll
@@ -107,11 +128,11 @@ __device__ __forceinline__ void sort_regs(float* v, int n) {
 // depths and points go (global rows, or the CTA's staging tile in the parallel path).  `dr` supplies the ray's random draws
 // (TapeDraws: rows of the caller's tapes; CounterDraws: the counter RNG evaluated here), class by class, so that only the
 // draws the ray's class consumes are produced.
-template <int NC, int NB, class Draws>
+template <int NC, int NB, bool EXACT, class Draws>
 __device__ __forceinline__ void place_ray(const SampleK& k, int obj, int kf, int iw, int ih, float d, int state, float max_bound,
                                           const Draws& dr, float* zo, float* po) {
     const oo_sample_args& a = k.a;
-    const int nc = a.n_c2s, nb = a.n_bins, S = nc + nb;
+    const int nc = EXACT ? NC : a.n_c2s, nb = EXACT ? NB : a.n_bins, S = nc + nb;   // EXACT: compile-time loop bounds
     const float eps = a.eps;
     const bool invalid = d <= a.min_bound;
     float zs[NC + NB];
@@ -152,12 +173,17 @@ __device__ __forceinline__ void place_ray(const SampleK& k, int obj, int kf, int
                 if (i < nb) ub[i] = __fadd_rn(__fadd_rn(__fmul_rn(range, k.lin_b[i]), lo), __fmul_rn(ub[i], blen));
         }
         // zs = [cam->surface bins, surface bins]: the split point nc is a run-time value only in the generic instantiation
+        if (EXACT) {
 #pragma unroll
-        for (int i = 0; i < NC + NB; ++i) {
-            if (i >= nc && i < S) {
+            for (int j = 0; j < NB; ++j) zs[NC + j] = ub[j];
+        } else {
 #pragma unroll
-                for (int j = 0; j < NB; ++j)
-                    if (j == i - nc) zs[i] = ub[j];
+            for (int i = 0; i < NC + NB; ++i) {
+                if (i >= nc && i < S) {
+#pragma unroll
+                    for (int j = 0; j < NB; ++j)
+                        if (j == i - nc) zs[i] = ub[j];
+                }
             }
         }
     }
@@ -304,7 +330,7 @@ __device__ __forceinline__ Rng make_rng(const oo_sample_args& a, int obj) {
 }
 
 // ---- tape mode: one 1024-thread CTA per object, ranks by block scan --------------------------------------------------
-template <int NC, int NB>
+template <int NC, int NB, bool EXACT>
 __global__ void __launch_bounds__(NTH, 1) k_sample(const SampleK k) {
     const oo_sample_args& a = k.a;
     const int obj = blockIdx.x, tid = threadIdx.x, lane = tid & 31, wv = tid >> 5;
@@ -372,7 +398,7 @@ __global__ void __launch_bounds__(NTH, 1) k_sample(const SampleK k) {
         const bool by_rank = a.tape_by_rank != 0;
         const TapeDraws<NC, NB> dr{a, base + (by_rank ? rk_inv : ray), base + (by_rank ? ray - rk_inv : ray),
                                    base + (by_rank ? rk_obj : ray), base + (by_rank ? rk_oth : ray)};
-        place_ray<NC, NB>(k, obj, p.kf, p.iw, p.ih, d, state, max_bound, dr, a.z + orow * S, a.pcs + orow * S * 3);
+        place_ray<NC, NB, EXACT>(k, obj, p.kf, p.iw, p.ih, d, state, max_bound, dr, a.z + orow * S, a.pcs + orow * S * 3);
         if (d <= a.min_bound) ++rk_inv;
         else if (state == 1) ++rk_obj;
         else ++rk_oth;
@@ -414,7 +440,7 @@ template <int NC, int NB, bool EXACT>
 __global__ void __launch_bounds__(256) k_sample_b(const SampleK k, const int* __restrict__ max_bits, const int* __restrict__ pix_pack) {
     extern __shared__ __align__(16) float tile[];
     const oo_sample_args& a = k.a;
-    const int obj = blockIdx.y, n_rays = a.n_frames * a.n_samples, S = a.n_c2s + a.n_bins;
+    const int obj = blockIdx.y, n_rays = a.n_frames * a.n_samples, S = EXACT ? NC + NB : a.n_c2s + a.n_bins;
     const int ray0 = blockIdx.x * blockDim.x, ray = ray0 + threadIdx.x;
     const int n_here = min((int)blockDim.x, n_rays - ray0);
     float* zt = tile;
@@ -424,8 +450,8 @@ __global__ void __launch_bounds__(256) k_sample_b(const SampleK k, const int* __
         const size_t o = (size_t)obj * n_rays + ray;
         const int pk = pix_pack[o];
         const CounterDraws<NC, NB, EXACT> dr(a, g, (uint32_t)ray);
-        place_ray<NC, NB>(k, obj, pk & 31, (pk >> 5) & 2047, pk >> 16, a.gt_depth[o], a.labels[o], __int_as_float(max_bits[obj]), dr,
-                          zt + threadIdx.x * S, pt + threadIdx.x * S * 3);
+        place_ray<NC, NB, EXACT>(k, obj, pk & 31, (pk >> 5) & 2047, pk >> 16, a.gt_depth[o], a.labels[o],
+                                 __int_as_float(max_bits[obj]), dr, zt + threadIdx.x * S, pt + threadIdx.x * S * 3);
     }
     __syncthreads();
     const size_t row0 = (size_t)obj * n_rays + ray0;
@@ -605,10 +631,10 @@ extern "C" int oo_sample_rays(const oo_sample_args* a, void* stream) {
         OO_LAUNCH_CHECK();
         return 0;
     }
-    if (a->n_c2s == 1 && a->n_bins == 9) k_sample<1, 9><<<a->n_obj, NTH, 0, (cudaStream_t)stream>>>(k);
-    else if (a->n_c2s == 5 && a->n_bins == 9) k_sample<5, 9><<<a->n_obj, NTH, 0, (cudaStream_t)stream>>>(k);
-    else if (a->n_c2s <= 8 && a->n_bins <= 12) k_sample<8, 12><<<a->n_obj, NTH, 0, (cudaStream_t)stream>>>(k);
-    else k_sample<16, 16><<<a->n_obj, NTH, 0, (cudaStream_t)stream>>>(k);
+    if (a->n_c2s == 1 && a->n_bins == 9) k_sample<1, 9, true><<<a->n_obj, NTH, 0, (cudaStream_t)stream>>>(k);
+    else if (a->n_c2s == 5 && a->n_bins == 9) k_sample<5, 9, true><<<a->n_obj, NTH, 0, (cudaStream_t)stream>>>(k);
+    else if (a->n_c2s <= 8 && a->n_bins <= 12) k_sample<8, 12, false><<<a->n_obj, NTH, 0, (cudaStream_t)stream>>>(k);
+    else k_sample<16, 16, false><<<a->n_obj, NTH, 0, (cudaStream_t)stream>>>(k);
     OO_LAUNCH_CHECK();
     return 0;
 }
