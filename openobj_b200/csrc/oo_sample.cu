@@ -269,11 +269,13 @@ struct CounterDraws {
     uint32_t wc[EXACT ? NWC : 1], wb[EXACT ? NWB : 1];
     // EXACT: all blocks of the ray are evaluated once, before the (divergent) class branches of place_ray -- the three
     // classes read the same bin words, so a warp with mixed classes does not evaluate Philox once per class
-    __device__ __forceinline__ CounterDraws(const oo_sample_args& a_, const Rng& g_, uint32_t ray_) : a(a_), g(g_), ray(ray_) {
+    // blk0: block 0 of the ray when the caller has it already (the pixel draw), else nullptr
+    __device__ __forceinline__ CounterDraws(const oo_sample_args& a_, const Rng& g_, uint32_t ray_, const uint4* blk0 = nullptr)
+        : a(a_), g(g_), ray(ray_) {
         if (EXACT) {
 #pragma unroll
             for (int j = 0; j < NWC / 4; ++j) {
-                const uint4 r = ray_block(g, ray, (uint32_t)j);
+                const uint4 r = (j == 0 && blk0 != nullptr) ? *blk0 : ray_block(g, ray, (uint32_t)j);
                 wc[4 * j] = r.x; wc[4 * j + 1] = r.y; wc[4 * j + 2] = r.z; wc[4 * j + 3] = r.w;
             }
 #pragma unroll
@@ -405,14 +407,23 @@ __global__ void __launch_bounds__(NTH, 1) k_sample(const SampleK k) {
     }
 }
 
-// ---- counter-RNG mode: no ranks are needed, so every ray is independent: two fully parallel launches with the batch
-// max depth of each object (non-negative floats order like their bit patterns) exchanged through a tiny global array.
-// Pass A draws the pixel (keyframe word + block 0 of the ray), gathers, writes the per-ray outputs and leaves the pixel
-// packed in 32 bits (kf | w << 5 | h << 16) for pass B, which only draws the words its class consumes.
-__global__ void __launch_bounds__(256) k_sample_a(const SampleK k, int* __restrict__ max_bits, int* __restrict__ pix_pack) {
+// ---- counter-RNG mode: no ranks are needed, so every ray is independent.  ONE pass does everything for the rays with a
+// valid depth: keyframe word + block 0 of the ray -> pixel -> gathers -> per-ray outputs -> the remaining blocks -> sample
+// placement into the CTA's staging tile (z [256][S], points [256][S][3]), which is a contiguous range of the outputs and
+// leaves with 128-bit, fully coalesced stores (a thread writing its own 40 B / 120 B rows directly costs one 32-byte sector
+// per 4-byte store).  Only the invalid-depth rays (a few per cent) need the batch-max depth of their object (vmap.py:489,
+// quirk 6): they are appended to a per-object list and placed by a small second launch once the maximum (non-negative
+// floats order like their bit patterns: atomicMax on the bits) is complete.
+template <int NC, int NB, bool EXACT>
+__global__ void __launch_bounds__(256) k_sample_main(const SampleK k, int* __restrict__ max_bits, int* __restrict__ inv_cnt,
+                                                     int2* __restrict__ inv_list) {
+    extern __shared__ __align__(16) float tile[];
     const oo_sample_args& a = k.a;
-    const int obj = blockIdx.y, n_rays = a.n_frames * a.n_samples;
-    const int ray = blockIdx.x * blockDim.x + threadIdx.x;
+    const int obj = blockIdx.y, n_rays = a.n_frames * a.n_samples, S = EXACT ? NC + NB : a.n_c2s + a.n_bins;
+    const int ray0 = blockIdx.x * blockDim.x, ray = ray0 + threadIdx.x;
+    const int n_here = min((int)blockDim.x, n_rays - ray0);
+    float* zt = tile;
+    float* pt = tile + (size_t)blockDim.x * S;
     const Rng g = make_rng(a, obj);
     float d = 0.f;
     int oob = 0;
@@ -423,36 +434,20 @@ __global__ void __launch_bounds__(256) k_sample_a(const SampleK k, int* __restri
         else kf = min((int)(g.uniform(0, (uint64_t)f) * (float)nk), nk - 1);
         const uint4 r0 = ray_block(g, (uint32_t)ray, 0u);
         const RayPix p = pixel_from_uniforms(a, obj, kf, u24(r0.x), u24(r0.y));
-        gather_ray(a, obj, ray, n_rays, p, d, oob);
-        pix_pack[(size_t)obj * n_rays + ray] = p.kf | (p.iw << 5) | (p.ih << 16);
+        const int cls = gather_ray(a, obj, ray, n_rays, p, d, oob);
+        if (cls == 0) {
+            const int slot = atomicAdd(inv_cnt + obj, 1);
+            inv_list[(size_t)obj * n_rays + slot] = make_int2(ray, p.kf | (p.iw << 5) | (p.ih << 16));
+        } else {
+            const CounterDraws<NC, NB, EXACT> dr(a, g, (uint32_t)ray, &r0);
+            place_ray<NC, NB, EXACT>(k, obj, p.kf, p.iw, p.ih, d, cls, 0.f, dr, zt + threadIdx.x * S, pt + threadIdx.x * S * 3);
+        }
     }
     d = fmaxf(d, 0.f);
 #pragma unroll
     for (int o = 16; o > 0; o >>= 1) d = fmaxf(d, __shfl_xor_sync(0xffffffffu, d, o));
     if ((threadIdx.x & 31) == 0) atomicMax(max_bits + obj, __float_as_int(d));
     if (oob && a.oob_count) atomicAdd(a.oob_count, oob);
-}
-
-// One thread places the samples of one ray into the CTA's staging tile (z [256][S], points [256][S][3]); the tile is a
-// contiguous range of the outputs and leaves with 128-bit, fully coalesced stores (a thread writing its own 40 B / 120 B
-// rows directly costs one 32-byte sector per 4-byte store).
-template <int NC, int NB, bool EXACT>
-__global__ void __launch_bounds__(256) k_sample_b(const SampleK k, const int* __restrict__ max_bits, const int* __restrict__ pix_pack) {
-    extern __shared__ __align__(16) float tile[];
-    const oo_sample_args& a = k.a;
-    const int obj = blockIdx.y, n_rays = a.n_frames * a.n_samples, S = EXACT ? NC + NB : a.n_c2s + a.n_bins;
-    const int ray0 = blockIdx.x * blockDim.x, ray = ray0 + threadIdx.x;
-    const int n_here = min((int)blockDim.x, n_rays - ray0);
-    float* zt = tile;
-    float* pt = tile + (size_t)blockDim.x * S;
-    if (ray < n_rays) {
-        const Rng g = make_rng(a, obj);
-        const size_t o = (size_t)obj * n_rays + ray;
-        const int pk = pix_pack[o];
-        const CounterDraws<NC, NB, EXACT> dr(a, g, (uint32_t)ray);
-        place_ray<NC, NB, EXACT>(k, obj, pk & 31, (pk >> 5) & 2047, pk >> 16, a.gt_depth[o], a.labels[o],
-                                 __int_as_float(max_bits[obj]), dr, zt + threadIdx.x * S, pt + threadIdx.x * S * 3);
-    }
     __syncthreads();
     const size_t row0 = (size_t)obj * n_rays + ray0;
     float* zg = a.z + row0 * S;
@@ -466,6 +461,24 @@ __global__ void __launch_bounds__(256) k_sample_b(const SampleK k, const int* __
     } else {
         for (int i = threadIdx.x; i < nz; i += blockDim.x) zg[i] = zt[i];
         for (int i = threadIdx.x; i < np; i += blockDim.x) pg[i] = pt[i];
+    }
+}
+
+// the invalid-depth rays of every object: stratified bins over [min_bound, batch max] (vmap.py:493-498), rows written in place
+template <int NC, int NB, bool EXACT>
+__global__ void __launch_bounds__(128) k_sample_fix(const SampleK k, const int* __restrict__ max_bits, const int* __restrict__ inv_cnt,
+                                                    const int2* __restrict__ inv_list) {
+    const oo_sample_args& a = k.a;
+    const int obj = blockIdx.y, n_rays = a.n_frames * a.n_samples, S = EXACT ? NC + NB : a.n_c2s + a.n_bins;
+    const int n = inv_cnt[obj];
+    const Rng g = make_rng(a, obj);
+    const float max_bound = __int_as_float(max_bits[obj]);
+    for (int idx = blockIdx.x * blockDim.x + threadIdx.x; idx < n; idx += gridDim.x * blockDim.x) {
+        const int2 e = inv_list[(size_t)obj * n_rays + idx];
+        const size_t o = (size_t)obj * n_rays + e.x;
+        const CounterDraws<NC, NB, EXACT> dr(a, g, (uint32_t)e.x);
+        place_ray<NC, NB, EXACT>(k, obj, e.y & 31, (e.y >> 5) & 2047, e.y >> 16, a.gt_depth[o], 0, max_bound, dr, a.z + o * S,
+                                 a.pcs + o * S * 3);
     }
 }
 
@@ -600,34 +613,36 @@ extern "C" int oo_sample_rays(const oo_sample_args* a, void* stream) {
         // per-object batch-max scratch: one small allocation per process, grown on demand (calls are not re-entrant)
         OO_REQUIRE(a->W <= 2048 && a->H <= 32768, "oo_sample_rays: the packed pixel needs W <= 2048, H <= 32768");
         const int n_rays = a->n_frames * a->n_samples;
-        // per-object batch-max + per-ray packed pixel scratch: one allocation per process, grown on demand (calls are not
-        // re-entrant)
-        static int* max_bits = nullptr;
-        static size_t max_cap = 0;
-        const size_t need = (size_t)a->n_obj * (1 + (size_t)n_rays);
-        if (need > max_cap) {
-            if (max_bits) OO_CUDA(cudaFree(max_bits));
-            max_cap = need < (1u << 20) ? (1u << 20) : 2 * need;
-            OO_CUDA(cudaMalloc((void**)&max_bits, max_cap * sizeof(int)));
+        // scratch: per-object batch max and invalid-ray count, per-object invalid-ray lists; one allocation per process, grown
+        // on demand (calls are not re-entrant)
+        static int* scratch = nullptr;
+        static size_t cap = 0;
+        const size_t need = (size_t)a->n_obj * (2 + 2 * (size_t)n_rays);
+        if (need > cap) {
+            if (scratch) OO_CUDA(cudaFree(scratch));
+            cap = need < (1u << 20) ? (1u << 20) : 2 * need;
+            OO_CUDA(cudaMalloc((void**)&scratch, cap * sizeof(int)));
         }
-        int* pix_pack = max_bits + a->n_obj;
-        OO_CUDA(cudaMemsetAsync(max_bits, 0, a->n_obj * sizeof(int), (cudaStream_t)stream));
+        int* max_bits = scratch;
+        int* inv_cnt = scratch + a->n_obj;
+        int2* inv_list = reinterpret_cast<int2*>(scratch + 2 * (size_t)a->n_obj);
+        OO_CUDA(cudaMemsetAsync(scratch, 0, 2 * (size_t)a->n_obj * sizeof(int), (cudaStream_t)stream));
         const dim3 grid((n_rays + 255) / 256, a->n_obj);
-        k_sample_a<<<grid, 256, 0, (cudaStream_t)stream>>>(k, max_bits, pix_pack);
-        OO_LAUNCH_CHECK();
         const size_t tile_bytes = (size_t)256 * S * 4 * sizeof(float);        // z [256][S] + points [256][S][3]; <= 128 KB (S <= 32)
         // one instantiation per launch (exact for the shipped 1 + 9 and 5 + 9 bins, upper bounds otherwise): per-ray arrays in
         // registers and a code size the instruction cache holds
-#define OO_LAUNCH_B(NC_, NB_, EX_)                                                                                                \
-        do {                                                                                                                      \
-            OO_CUDA(cudaFuncSetAttribute(k_sample_b<NC_, NB_, EX_>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)tile_bytes)); \
-            k_sample_b<NC_, NB_, EX_><<<grid, 256, tile_bytes, (cudaStream_t)stream>>>(k, max_bits, pix_pack);                     \
+#define OO_LAUNCH_S(NC_, NB_, EX_)                                                                                                     \
+        do {                                                                                                                           \
+            OO_CUDA(cudaFuncSetAttribute(k_sample_main<NC_, NB_, EX_>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)tile_bytes)); \
+            k_sample_main<NC_, NB_, EX_><<<grid, 256, tile_bytes, (cudaStream_t)stream>>>(k, max_bits, inv_cnt, inv_list);             \
+            OO_LAUNCH_CHECK();                                                                                                         \
+            k_sample_fix<NC_, NB_, EX_><<<dim3(8, a->n_obj), 128, 0, (cudaStream_t)stream>>>(k, max_bits, inv_cnt, inv_list);          \
         } while (0)
-        if (a->n_c2s == 1 && a->n_bins == 9) OO_LAUNCH_B(1, 9, true);
-        else if (a->n_c2s == 5 && a->n_bins == 9) OO_LAUNCH_B(5, 9, true);
-        else if (a->n_c2s <= 8 && a->n_bins <= 12) OO_LAUNCH_B(8, 12, false);
-        else OO_LAUNCH_B(16, 16, false);
-#undef OO_LAUNCH_B
+        if (a->n_c2s == 1 && a->n_bins == 9) OO_LAUNCH_S(1, 9, true);
+        else if (a->n_c2s == 5 && a->n_bins == 9) OO_LAUNCH_S(5, 9, true);
+        else if (a->n_c2s <= 8 && a->n_bins <= 12) OO_LAUNCH_S(8, 12, false);
+        else OO_LAUNCH_S(16, 16, false);
+#undef OO_LAUNCH_S
         OO_LAUNCH_CHECK();
         return 0;
     }
