@@ -52,12 +52,43 @@ struct RayIn {
     int n_rays_total, S, C;
 };
 
+// Feature rows reach the warp through a per-lane staging ring in shared memory (cp.async, 16 B per lane per row): the
+// S x 512 B of the NEXT 128-column chunk -- of this ray or of the warp's next ray -- are in flight while the current chunk is
+// reduced, so a warp keeps 2 x S x 512 B outstanding without holding a second register copy (a register double buffer
+// spilled at 128 registers).  Every lane reads back only the 16 bytes it copied itself.
 template <int SMAX>
-__global__ void __launch_bounds__(256, SMAX <= 16 ? 2 : 1) k_loss_ray_fwd(RayIn in, float* __restrict__ ws) {
+constexpr int loss_fwd_stage_bytes() { return SMAX <= 16 ? 8 * 2 * (SMAX + 1) * 32 * 16 : 0; }
+
+__device__ __forceinline__ void cp_async16(void* dst, const void* src) {
+    asm volatile("cp.async.cg.shared.global [%0], [%1], 16;" ::"r"((unsigned)__cvta_generic_to_shared(dst)), "l"(src) : "memory");
+}
+
+template <int SMAX>
+__global__ void __launch_bounds__(256, SMAX <= 10 ? 2 : 1) k_loss_ray_fwd(RayIn in, float* __restrict__ ws) {
+    extern __shared__ float4 stage4[];                             // [8 warps][2 buffers][SMAX + 1 rows][32 lanes]
+    constexpr bool STAGE = SMAX <= 16;
     const int lane = threadIdx.x & 31;
+    const int S = in.S, C = in.C, nch = (C + 127) / 128;
+    const int wpg = gridDim.x * (blockDim.x >> 5);
+    const bool feat = in.pred_feat != nullptr;
+    float4* sb = stage4 + (size_t)(threadIdx.x >> 5) * 2 * (SMAX + 1) * 32 + lane;
+    // one commit group per (ray, chunk) job, empty when there is nothing to copy, so that wait_group 1 == "the current one landed"
+    auto issue = [&](int ray, int ch, int b) {
+        const int c4 = ch * 128 + lane * 4;
+        if (ray < in.n_rays_total && c4 < C) {
+            const float* pf = in.pred_feat + (size_t)ray * S * C + c4;
+#pragma unroll
+            for (int i = 0; i < SMAX; ++i)
+                if (i < S) cp_async16(sb + (b * (SMAX + 1) + i) * 32, pf + (size_t)i * C);
+            cp_async16(sb + (b * (SMAX + 1) + SMAX) * 32, in.gt_feat + (size_t)ray * C + c4);
+        }
+        asm volatile("cp.async.commit_group;" ::: "memory");
+    };
+    int buf = 0;
     // persistent warps: the grid is sized to one resident wave and every warp strides over the rays (no partial last wave)
-    for (int ray = blockIdx.x * (blockDim.x >> 5) + (threadIdx.x >> 5); ray < in.n_rays_total; ray += gridDim.x * (blockDim.x >> 5)) {
-    const int S = in.S;
+    int ray = blockIdx.x * (blockDim.x >> 5) + (threadIdx.x >> 5);
+    if (STAGE && feat) issue(ray, 0, 0);
+    for (; ray < in.n_rays_total; ray += wpg) {
     const bool act = lane < S;
     const size_t pi = (size_t)ray * S + lane;
     const float a = act ? in.alpha[pi] : 0.f;
@@ -75,39 +106,54 @@ __global__ void __launch_bounds__(256, SMAX <= 16 ? 2 : 1) k_loss_ray_fwd(RayIn 
     const float opac = warp_sum(T);                                // loss.py:35
     const float r0 = warp_sum(T * c0), r1 = warp_sum(T * c1), r2 = warp_sum(T * c2);   // loss.py:34
     float xy = 0.f, xx = 0.f, yy = 0.f;
-    if (in.pred_feat != nullptr) {                                 // loss.py:82-87
-        const float* pf = in.pred_feat + (size_t)ray * S * in.C;
-        const float* gy = in.gt_feat + (size_t)ray * in.C;
+    if (feat) {                                                    // loss.py:82-87
         float px[SMAX], py[SMAX];
 #pragma unroll
         for (int i = 0; i < SMAX; ++i) px[i] = py[i] = 0.f;
-        for (int c4 = lane * 4; c4 < in.C; c4 += 128) {
-            // all S rows of this column chunk are requested before the first is used (memory-level parallelism: one warp
-            // keeps S x 512 B in flight); accumulation stays in sample order
-            float4 p[SMAX];
+        for (int ch = 0; ch < nch; ++ch) {
+            const int c4 = ch * 128 + lane * 4;
+            float4 p[SMAX], y = {0.f, 0.f, 0.f, 0.f};
+            if (STAGE) {
+                if (ch + 1 < nch) issue(ray, ch + 1, buf ^ 1);
+                else issue(ray + wpg, 0, buf ^ 1);
+                asm volatile("cp.async.wait_group 1;" ::: "memory");
+                if (c4 < C) {
 #pragma unroll
-            for (int i = 0; i < SMAX; ++i)
-                if (i < S) p[i] = *reinterpret_cast<const float4*>(pf + (size_t)i * in.C + c4);
-            float4 x = {0.f, 0.f, 0.f, 0.f};
-#pragma unroll
-            for (int i = 0; i < SMAX; ++i) {
-                if (i < S) {
-                    const float Ti = __shfl_sync(0xffffffffu, T, i);
-                    x.x += Ti * p[i].x; x.y += Ti * p[i].y; x.z += Ti * p[i].z; x.w += Ti * p[i].w;
+                    for (int i = 0; i < SMAX; ++i)
+                        if (i < S) p[i] = sb[(buf * (SMAX + 1) + i) * 32];
+                    y = sb[(buf * (SMAX + 1) + SMAX) * 32];
                 }
-            }
-            const float4 y = *reinterpret_cast<const float4*>(gy + c4);
-            xy += x.x * y.x + x.y * y.y + x.z * y.z + x.w * y.w;
-            xx += x.x * x.x + x.y * x.y + x.z * x.z + x.w * x.w;
-            yy += y.x * y.x + y.y * y.y + y.z * y.z + y.w * y.w;
+                buf ^= 1;
+            } else if (c4 < C) {
+                // all S rows of this column chunk are requested before the first is used
+                const float* pf = in.pred_feat + (size_t)ray * S * C + c4;
 #pragma unroll
-            for (int i = 0; i < SMAX; ++i) {
-                if (i < S) {
-                    px[i] += p[i].x * x.x + p[i].y * x.y + p[i].z * x.z + p[i].w * x.w;
-                    py[i] += p[i].x * y.x + p[i].y * y.y + p[i].z * y.z + p[i].w * y.w;
-                }
+                for (int i = 0; i < SMAX; ++i)
+                    if (i < S) p[i] = *reinterpret_cast<const float4*>(pf + (size_t)i * C);
+                y = *reinterpret_cast<const float4*>(in.gt_feat + (size_t)ray * C + c4);
             }
-            *reinterpret_cast<float4*>(ws + (size_t)ray * WSR + WS_X + c4) = x;
+            if (c4 < C) {
+                // accumulation stays in sample order
+                float4 x = {0.f, 0.f, 0.f, 0.f};
+#pragma unroll
+                for (int i = 0; i < SMAX; ++i) {
+                    if (i < S) {
+                        const float Ti = __shfl_sync(0xffffffffu, T, i);
+                        x.x += Ti * p[i].x; x.y += Ti * p[i].y; x.z += Ti * p[i].z; x.w += Ti * p[i].w;
+                    }
+                }
+                xy += x.x * y.x + x.y * y.y + x.z * y.z + x.w * y.w;
+                xx += x.x * x.x + x.y * x.y + x.z * x.z + x.w * x.w;
+                yy += y.x * y.x + y.y * y.y + y.z * y.z + y.w * y.w;
+#pragma unroll
+                for (int i = 0; i < SMAX; ++i) {
+                    if (i < S) {
+                        px[i] += p[i].x * x.x + p[i].y * x.y + p[i].z * x.z + p[i].w * x.w;
+                        py[i] += p[i].x * y.x + p[i].y * y.y + p[i].z * y.z + p[i].w * y.w;
+                    }
+                }
+                *reinterpret_cast<float4*>(ws + (size_t)ray * WSR + WS_X + c4) = x;
+            }
         }
 #pragma unroll
         for (int i = 0; i < SMAX; ++i) {
@@ -277,11 +323,11 @@ __global__ void __launch_bounds__(256, 4) k_loss_ray_bwd(RayIn in, const float* 
 
 // grid of one resident wave (occupancy x SM count), capped by the work
 template <typename K>
-int wave_blocks(K kernel, int needed) {
+int wave_blocks(K kernel, int needed, size_t smem = 0) {
     int dev = 0, n_sm = 148, occ = 1;
     cudaGetDevice(&dev);
     cudaDeviceGetAttribute(&n_sm, cudaDevAttrMultiProcessorCount, dev);
-    cudaOccupancyMaxActiveBlocksPerMultiprocessor(&occ, kernel, 256, 0);
+    cudaOccupancyMaxActiveBlocksPerMultiprocessor(&occ, kernel, 256, smem);
     const int wave = n_sm * (occ < 1 ? 1 : occ);
     return needed < wave ? needed : wave;
 }
@@ -311,9 +357,18 @@ extern "C" int oo_loss_fwd(const float* alpha, const float* color, const float* 
     RayIn in{alpha, color, z, gt_depth, gt_color, pred_feat, gt_feat, labels, n_obj * n_rays, n_samp, n_feat};
     float* tail = ray_ws + (size_t)n_obj * n_rays * WSR;
     const int fblocks = (in.n_rays_total + 7) / 8;
-    if (n_samp <= 10) k_loss_ray_fwd<10><<<wave_blocks(k_loss_ray_fwd<10>, fblocks), 256, 0, st>>>(in, ray_ws);
-    else if (n_samp <= 16) k_loss_ray_fwd<16><<<wave_blocks(k_loss_ray_fwd<16>, fblocks), 256, 0, st>>>(in, ray_ws);
-    else k_loss_ray_fwd<32><<<wave_blocks(k_loss_ray_fwd<32>, fblocks), 256, 0, st>>>(in, ray_ws);
+    // the staging ring is only needed (and only paid for in occupancy) when features are rendered
+#define OO_LAUNCH_FWD(SM_)                                                                                                   \
+    do {                                                                                                                     \
+        const size_t sm = pred_feat != nullptr ? (size_t)loss_fwd_stage_bytes<SM_>() : 0;                                    \
+        OO_CUDA(cudaFuncSetAttribute(k_loss_ray_fwd<SM_>, cudaFuncAttributeMaxDynamicSharedMemorySize,                       \
+                                     loss_fwd_stage_bytes<SM_>()));                                                          \
+        k_loss_ray_fwd<SM_><<<wave_blocks(k_loss_ray_fwd<SM_>, fblocks, sm), 256, sm, st>>>(in, ray_ws);                     \
+    } while (0)
+    if (n_samp <= 10) OO_LAUNCH_FWD(10);
+    else if (n_samp <= 16) OO_LAUNCH_FWD(16);
+    else OO_LAUNCH_FWD(32);
+#undef OO_LAUNCH_FWD
     OO_LAUNCH_CHECK();
     k_loss_obj_reduce<<<n_obj, 256, 0, st>>>(ray_ws, labels, n_rays, tail);
     OO_LAUNCH_CHECK();
