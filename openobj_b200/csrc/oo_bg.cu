@@ -294,7 +294,20 @@ __global__ void __launch_bounds__(256, 2) k_gemm(const GemmOp g) {
 
 // fixed-order reduction of the split partials: eight lanes per output element, lane q sums z = q, q + 8, ... in order and
 // the eight sums are combined by a shuffle tree (deterministic; eight times shorter load chains than one thread per element)
-__global__ void __launch_bounds__(256) k_gemm_reduce(const GemmOp g) {
+__device__ __forceinline__ void gemm_reduce_body(const GemmOp& g);
+
+__global__ void __launch_bounds__(256) k_gemm_reduce(const GemmOp g) { gemm_reduce_body(g); }
+
+// The weight gradients of a step are only consumed by AdamW at its end, so their split partials stay in separate regions
+// and ONE launch finishes all of them (blockIdx.y = which GEMM) instead of a latency-bound launch after every GEMM.
+constexpr int REDUCE_BATCH_MAX = 9;
+struct ReduceBatch {
+    GemmOp op[REDUCE_BATCH_MAX];
+    int n;
+};
+__global__ void __launch_bounds__(256) k_gemm_reduce_batch(const __grid_constant__ ReduceBatch b) { gemm_reduce_body(b.op[blockIdx.y]); }
+
+__device__ __forceinline__ void gemm_reduce_body(const GemmOp& g) {
     const int je = gemm_je(g), n = g.I * je;
     const int e = (blockIdx.x * blockDim.x + threadIdx.x) >> 3, q = threadIdx.x & 7;
     pdl_wait();
@@ -313,13 +326,14 @@ __global__ void __launch_bounds__(256) k_gemm_reduce(const GemmOp g) {
 
 // split > 1 asks for a split contraction (the weight gradients: K = all points); how many chunks is chosen here so that the
 // grid is ONE wave of two CTAs per SM: a CTA's time is its number of k-tiles, whatever share of its tile is real output
-int run_gemm(GemmOp g, int split, float* part, cudaStream_t st) {
+int run_gemm(GemmOp g, int split, float* part, cudaStream_t st, ReduceBatch* defer = nullptr) {
     static int n_sm = 0;
     if (n_sm == 0) {
         int dev = 0;
         OO_CUDA(cudaGetDevice(&dev));
         OO_CUDA(cudaDeviceGetAttribute(&n_sm, cudaDevAttrMultiProcessorCount, dev));
     }
+    OO_REQUIRE(n_sm <= 160, "oo_bg gemm: the split-partial regions are sized for at most 160 SMs");
     const int tiles = ((g.I + BI - 1) / BI) * ((g.J + BJ - 1) / BJ);
     g.split = 1;
     g.chunk = g.K;
@@ -355,10 +369,36 @@ int run_gemm(GemmOp g, int split, float* part, cudaStream_t st) {
     else OO_CUDA(launch_pdl(k_gemm<false, false>, grid, dim3(256), (size_t)GEMM_SMEM, st, g));
     OO_LAUNCH_CHECK();
     if (g.split > 1) {
-        OO_CUDA(launch_pdl(k_gemm_reduce, dim3((g.I * je * 8 + 255) / 256), dim3(256), (size_t)0, st, g));
-        OO_LAUNCH_CHECK();
+        if (defer != nullptr) {
+            OO_REQUIRE(defer->n < REDUCE_BATCH_MAX, "oo_bg gemm: too many deferred reductions");
+            defer->op[defer->n++] = g;
+        } else {
+            OO_CUDA(launch_pdl(k_gemm_reduce, dim3((g.I * je * 8 + 255) / 256), dim3(256), (size_t)0, st, g));
+            OO_LAUNCH_CHECK();
+        }
     }
     return 0;
+}
+
+int run_reduce_batch(const ReduceBatch& b, cudaStream_t st) {
+    if (b.n == 0) return 0;
+    int gx = 1;
+    for (int i = 0; i < b.n; ++i) {
+        const int blocks = (b.op[i].I * (b.op[i].J + (b.op[i].ones_out != nullptr ? 1 : 0)) * 8 + 255) / 256;
+        gx = blocks > gx ? blocks : gx;
+    }
+    OO_CUDA(launch_pdl(k_gemm_reduce_batch, dim3(gx, b.n), dim3(256), (size_t)0, st, b));
+    OO_LAUNCH_CHECK();
+    return 0;
+}
+
+// floats of split partials run_gemm may write for an I x J weight gradient (+ the bias column): split * tiles <= 2 CTAs per SM
+long long part_floats(int I, int J) {
+    const long long tiles = (long long)((I + BI - 1) / BI) * ((J + BJ - 1) / BJ);
+    long long split = 2 * 160 / tiles;                 // >= what run_gemm picks for any SM count up to 160
+    if (split > BG_SPLIT_MAX) split = BG_SPLIT_MAX;
+    if (split < 2) split = 2;
+    return (split + 1) * (long long)I * (J + 1);
 }
 
 // ------------------------------------------------------------------------------------------------
@@ -485,7 +525,7 @@ struct BgWs {
     float *x1, *xc, *h1, *h3, *xh, *hc, *hp, *alpha, *color, *clip;
     // gradients
     float *d_alpha, *d_color, *d_colpre, *d_clip, *d_hc, *d_hp, *d_xh, *d_h3, *d_xc, *d_h1, *d_x1;
-    float *gt_rgb, *gt_feat, *loss_ws, *ones, *part, *emb_part, *grads;
+    float *gt_rgb, *gt_feat, *loss_ws, *ones, *part[9], *emb_part, *grads;   // part[i]: split partials of weight gradient i
     int ld1, ldc, ldh;
     long long total;
 };
@@ -506,10 +546,10 @@ BgWs bg_ws_map(float* base, int h, int n_pts, int n_rays) {
     w.gt_rgb = take(3LL * n_rays); w.gt_feat = take((long long)C * n_rays);
     w.loss_ws = take((long long)n_rays * oo_loss_ws_per_ray() + 8);
     w.ones = take(4);
-    const long long maxij = (long long)C * (h + 1) > (long long)h * (h + E1 + 1) ? (long long)C * (h + 1) : (long long)h * (h + E1 + 1);
-    // split partials [split][I][J + 1]: split * tiles <= 2 SMs-worth of CTAs (<= 2 * 160 here) of BI x BJ outputs each
-    const long long part_wave = 2LL * 160 * BI * (BJ + 1);
-    w.part = take((BG_SPLIT + 1) * maxij > part_wave ? (BG_SPLIT + 1) * maxij : part_wave);
+    {   // one region per weight-gradient GEMM, in the order oo_bg_train_step runs them (they are reduced together at the end)
+        const int wi[9] = {C, h, 3, h, 1, h, h, h, h}, wj[9] = {h, h + E2, h, h + E2, h, h, h + E1, h, E1};
+        for (int i = 0; i < 9; ++i) w.part[i] = take(part_floats(wi[i], wj[i]));
+    }
     w.emb_part = take(((M + EB_PTS - 1) / EB_PTS) * (NDIR * 3));
     w.grads = take(bg_layout(h).total);
     w.total = o;
@@ -622,36 +662,38 @@ extern "C" int oo_bg_train_step(float* theta, float* adam_m, float* adam_v, int 
                        w.d_alpha, w.d_color, part ? w.d_clip : nullptr, stream));
     const float* th = theta;
     GemmOp g;
+    ReduceBatch pending;                         // split partials of the weight gradients, reduced together before AdamW
+    pending.n = 0;
     OO_CUDA(cudaMemsetAsync(G, 0, sizeof(float) * L.total, st));
     // ---- clip head
     if (part) {
         // d out_clip.weight [C][h] = d_clip^T hp ; bias = column sums ; d hp = (d_clip W_ocl) * [hp > 0]
         g = op(w.d_clip, 1, C, w.hp, 1, h, G + L.off[T_OCL_W], h, 1, C, h, M);
         g.ones_out = G + L.off[T_OCL_B];
-        OO_TRY(run_gemm(g, BG_SPLIT, w.part, st));
+        OO_TRY(run_gemm(g, BG_SPLIT, w.part[0], st, &pending));
         g = op(w.d_clip, C, 1, th + L.off[T_OCL_W], 1, h, w.d_hp, h, 1, M, h, C);
         g.mask = w.hp; g.smi = h; g.smj = 1; g.mask_cols = h;
         OO_TRY(run_gemm(g, 1, nullptr, st));
         g = op(w.d_hp, 1, h, w.xh, 1, w.ldh, G + L.off[T_CP_W], h + E2, 1, h, h + E2, M);
         g.ones_out = G + L.off[T_CP_B];
-        OO_TRY(run_gemm(g, BG_SPLIT, w.part, st));
+        OO_TRY(run_gemm(g, BG_SPLIT, w.part[1], st, &pending));
     }
     // ---- colour head: sigmoid backward, out_color, color_linear
     k_sigmoid_bwd<<<(3 * M + 255) / 256, 256, 0, st>>>(w.d_color, w.color, w.d_colpre, 3 * M);
     OO_LAUNCH_CHECK();
     g = op(w.d_colpre, 1, 3, w.hc, 1, h, G + L.off[T_OC_W], h, 1, 3, h, M);
     g.ones_out = G + L.off[T_OC_B];
-    OO_TRY(run_gemm(g, BG_SPLIT, w.part, st));
+    OO_TRY(run_gemm(g, BG_SPLIT, w.part[2], st, &pending));
     g = op(w.d_colpre, 3, 1, th + L.off[T_OC_W], 1, h, w.d_hc, h, 1, M, h, 3);
     g.mask = w.hc; g.smi = h; g.smj = 1; g.mask_cols = h;
     OO_TRY(run_gemm(g, 1, nullptr, st));
     g = op(w.d_hc, 1, h, w.xh, 1, w.ldh, G + L.off[T_CL_W], h + E2, 1, h, h + E2, M);
     g.ones_out = G + L.off[T_CL_B];
-    OO_TRY(run_gemm(g, BG_SPLIT, w.part, st));
+    OO_TRY(run_gemm(g, BG_SPLIT, w.part[3], st, &pending));
     // ---- alpha head: alpha = 10 * (W_a fc4 + b_a)
     g = op(w.d_alpha, 1, 1, w.xh, 1, w.ldh, G + L.off[T_A_W], h, 1, 1, h, M); g.mult = 10.f;
     g.ones_out = G + L.off[T_A_B];
-    OO_TRY(run_gemm(g, BG_SPLIT, w.part, st));
+    OO_TRY(run_gemm(g, BG_SPLIT, w.part[4], st, &pending));
     // ---- d [fc4, e2] = d_hc W_cl + d_hp W_cp + 10 d_alpha W_a (cols < h).  The ReLU mask of fc4 is a 0/1 factor, so it is
     // applied to every term as it is added: (a + b + c) m == a m + b m + c m exactly, in the same order
     g = op(w.d_hc, h, 1, th + L.off[T_CL_W], 1, h + E2, w.d_xh, w.ldh, 1, M, h + E2, h);
@@ -668,28 +710,28 @@ extern "C" int oo_bg_train_step(float* theta, float* adam_m, float* adam_v, int 
     // ---- mid2: d W = d_fc4^T fc3, d fc3 = (d_fc4 W_m2) * [fc3 > 0]
     g = op(w.d_xh, 1, w.ldh, w.h3, 1, h, G + L.off[T_M2_W], h, 1, h, h, M);
     g.ones_out = G + L.off[T_M2_B];
-    OO_TRY(run_gemm(g, BG_SPLIT, w.part, st));
+    OO_TRY(run_gemm(g, BG_SPLIT, w.part[5], st, &pending));
     g = op(w.d_xh, w.ldh, 1, th + L.off[T_M2_W], 1, h, w.d_h3, h, 1, M, h, h);
     g.mask = w.h3; g.smi = h; g.smj = 1; g.mask_cols = h;
     OO_TRY(run_gemm(g, 1, nullptr, st));
     // ---- cat_layer: d W = d_fc3^T [fc2, e1], d [fc2, e1] = d_fc3 W_cat with the ReLU mask on the fc2 columns
     g = op(w.d_h3, 1, h, w.xc, 1, w.ldc, G + L.off[T_CAT_W], h + E1, 1, h, h + E1, M);
     g.ones_out = G + L.off[T_CAT_B];
-    OO_TRY(run_gemm(g, BG_SPLIT, w.part, st));
+    OO_TRY(run_gemm(g, BG_SPLIT, w.part[6], st, &pending));
     g = op(w.d_h3, h, 1, th + L.off[T_CAT_W], 1, h + E1, w.d_xc, w.ldc, 1, M, h + E1, h);
     g.mask = w.xc; g.smi = w.ldc; g.smj = 1; g.mask_cols = h;
     OO_TRY(run_gemm(g, 1, nullptr, st));
     // ---- mid1
     g = op(w.d_xc, 1, w.ldc, w.h1, 1, h, G + L.off[T_M1_W], h, 1, h, h, M);
     g.ones_out = G + L.off[T_M1_B];
-    OO_TRY(run_gemm(g, BG_SPLIT, w.part, st));
+    OO_TRY(run_gemm(g, BG_SPLIT, w.part[7], st, &pending));
     g = op(w.d_xc, w.ldc, 1, th + L.off[T_M1_W], 1, h, w.d_h1, h, 1, M, h, h);
     g.mask = w.h1; g.smi = h; g.smj = 1; g.mask_cols = h;
     OO_TRY(run_gemm(g, 1, nullptr, st));
     // ---- in_layer
     g = op(w.d_h1, 1, h, w.x1, 1, w.ld1, G + L.off[T_IN_W], E1, 1, h, E1, M);
     g.ones_out = G + L.off[T_IN_B];
-    OO_TRY(run_gemm(g, BG_SPLIT, w.part, st));
+    OO_TRY(run_gemm(g, BG_SPLIT, w.part[8], st, &pending));
     g = op(w.d_h1, h, 1, th + L.off[T_IN_W], 1, E1, w.d_x1, w.ld1, 1, M, E1, h);
     OO_TRY(run_gemm(g, 1, nullptr, st));
     // ---- encoder: B_layer.weight is trainable (embedding.py:43)
@@ -701,6 +743,7 @@ extern "C" int oo_bg_train_step(float* theta, float* adam_m, float* adam_v, int 
         k_embed_bwd_reduce<<<(NDIR * 3 + 7) / 8, 256, 0, st>>>(w.emb_part, nblk, G + L.off[T_PE]);
         OO_LAUNCH_CHECK();
     }
+    OO_TRY(run_reduce_batch(pending, st));
     if (grads_out) return 0;
     // ---- torch.optim.AdamW over the flat block; with part features off the clip head has grad None and is skipped
     // entirely (no decay either; quirk 8) -- its four tensors are contiguous in the layout
