@@ -336,6 +336,53 @@ def test_in_kernel_rng_equals_tape_mode():
             assert b.pix[i, -2 * n_samples, 0].item() == o.lastest_kf_queue[-2] and b.pix[i, -1, 0].item() == o.lastest_kf_queue[-1]
 
 
+@pytest.mark.parametrize("bins", [(5, 9), (3, 7), (9, 13), (2, 9)])
+def test_in_kernel_rng_equals_tape_mode_other_bin_counts(bins):
+    """The background's 5 + 9 bins (exact instantiation) and bin counts that only have the generic instantiations
+    (upper bounds 8 + 12 and 16 + 16, one Philox block per word): counter mode == tape mode cut from oo_rng_fill_rows.
+    One object's newest depth frame is zeroed so that its rays exercise the invalid-depth fix-up launch en masse."""
+    from openobj_b200 import sampler
+    nc, nb = bins
+    cfg, synth, sc = _small_scene()
+    for f in range(5):
+        sc.add_frame(synth.frame(f))
+    objs = list(sc.obj_dict.values())
+    objs[1].depth_batch[:objs[1].n_keyframes].zero_()           # every ray of this object has an invalid depth
+    objs[2].depth_batch[objs[2].n_keyframes - 1].zero_()
+    n_frames, n_samples = 12, 24
+    tapes = sampler.device_tapes(objs, n_frames, n_samples, nc, nb, objs[0].surface_eps, 1234, 9, DEV)
+    rng = sampler.counter_rng(objs, 1234, 9, DEV)
+    args = ([o.rgbs_batch for o in objs], [o.depth_batch for o in objs], [o.t_wc_batch for o in objs], [o.bbox for o in objs])
+    kw = dict(n_c2s=nc, n_bins=nb, want_pix=True)
+    a = sampler.sample(*args, None, sc.cam.rays_dir_cache, tapes, n_frames, n_samples, **kw)
+    b = sampler.sample(*args, None, sc.cam.rays_dir_cache, rng, n_frames, n_samples, **kw)
+    for name in ("gt_rgb", "gt_depth", "valid", "labels", "pcs", "z", "pix"):
+        assert torch.equal(getattr(a, name), getattr(b, name)), name
+    assert int(b.valid[1].sum()) == 0 and 0 < int(b.valid[2].sum()) < n_frames * n_samples
+    assert bool((b.z[1][:, 1:] >= b.z[1][:, :-1]).all())         # stratified bins over [0, batch max] are ordered
+
+
+def test_counter_sampling_does_not_depend_on_the_shard():
+    """An object's samples depend on (seed, frame, object id) only: sampling objects {2, 3, 4} alone (another rank's shard)
+    gives bit-identical rows to sampling all five together."""
+    from openobj_b200 import sampler
+    cfg, synth, sc = _small_scene()
+    for f in range(6):
+        sc.add_frame(synth.frame(f))
+    objs = list(sc.obj_dict.values())
+    n_frames, n_samples = 20, 24
+
+    def run(sub):
+        rng = sampler.counter_rng(sub, 99, 3, DEV)
+        pf = torch.stack([o.part_frame_row() for o in sub]).to(DEV).contiguous()
+        return sampler.sample([o.rgbs_batch for o in sub], [o.depth_batch for o in sub], [o.t_wc_batch for o in sub],
+                              [o.bbox for o in sub], pf, sc.cam.rays_dir_cache, rng, n_frames, n_samples, part_down=5,
+                              part_hw=(sc.pw, sc.ph), want_pix=True)
+    full, part = run(objs), run(objs[2:])
+    for name in ("gt_rgb", "gt_depth", "valid", "labels", "pcs", "z", "feat_row", "pix"):
+        assert torch.equal(getattr(full, name)[2:], getattr(part, name)), name
+
+
 def test_scene_frames_train_and_alias_parameters():
     """End-to-end frames through Scene (append -> sample -> 4 steps): losses finite and falling on a fixed batch, the
     objects' nn.Parameters alias the ensemble buffer (write-back of train.py:478-485 is free), labels consistent."""
