@@ -449,7 +449,7 @@ def run_ours(args):
                                  "peak_source": ("MEASURED_PEAKS.json bf16_tflops (cuBLAS bf16 burst)" if "bf16_tflops" in peaks
                                                  else "fallback 1.59 PFLOP/s"),
                                  "note": "for context only: the path must reproduce fp32 arithmetic, it is not a bf16 GEMM"}},
-            "roofline_sampling": {"kernel": "k_sample_a + k_sample_b (K2, all objects; device time of Scene.sample incl. its small H2D table copies, median of 5 frames)",
+            "roofline_sampling": {"kernel": "k_sample_main + k_sample_fix (K2, all objects; device time of Scene.sample incl. its small H2D table copies, median of 5 frames)",
                                   "bound": "hbm", "achieved": sample_bytes / (t_sample * 1e-3) / 1e9, "peak": hbm_peak,
                                   "unit": "GB/s", "frac": sample_bytes / (t_sample * 1e-3) / 1e9 / hbm_peak, "ms": t_sample,
                                   "bytes_per_launch": sample_bytes, "rays_per_s": rays_frame / (t_sample * 1e-3)},
@@ -467,7 +467,7 @@ def run_ours(args):
                                      "bound": "hbm", "achieved": k3_bytes / (k3_ms * 1e-3) / 1e9, "peak": hbm_peak, "unit": "GB/s",
                                      "frac": k3_bytes / (k3_ms * 1e-3) / 1e9 / hbm_peak, "ms": k3_ms, "bytes_per_launch": k3_bytes}
         out["background"] = {"what": "separate background model (train.py:447-463): hidden %d, %d rays x %d samples per step, "
-                                     "layer-by-layer FP32 GEMM path; NOT part of `value`" % (hb, Rb, Sb),
+                                     "layer-by-layer path, GEMMs as 3xTF32 mma.sync (fp32-level accuracy); NOT part of `value`" % (hb, Rb, Sb),
                              "ms_per_step": bg_ms, "rays_per_s": Rb / (bg_ms * 1e-3), "flop_per_step": bg_flop,
                              "achieved_tflops": bg_flop / (bg_ms * 1e-3) / 1e12, "frac_of_fma_peak": bg_flop / (bg_ms * 1e-3) / 1e12 / peak}
         if cpu is not None:
