@@ -291,6 +291,7 @@ def run_ours(args):
     run_frames(frames_t, steps, host=True)
     e1.record()
     torch.cuda.synchronize(); D.barrier()
+    print("[bench] rank %d: value pass %.1f ms, e2e pass %.1f ms (this rank)" % (rank, ms, e0.elapsed_time(e1)), file=sys.stderr)
     ms_e2e = D.max_over_ranks(e0.elapsed_time(e1), dev)
     rays = n_obj * world * R * steps
     h2d_per_step = synth.frame_bytes() / ITERS

@@ -2,6 +2,7 @@
 ensemble index, NO gradient collectives.  The only data-path exchange is the OR of the per-step zero-mask flags
 (render_rays.py:89-94 couples objects through `(mask_num == 0).any()`), one tiny all-reduce per frame."""
 import os
+import sys
 
 import torch
 import torch.distributed as dist
@@ -12,11 +13,45 @@ def owner_rank(ensemble_index, world):
     return ensemble_index % world
 
 
+def bind_to_gpu_cpus(local):
+    """Pin this process to the CPUs NVML reports as local to GPU `local` (its NUMA node), BEFORE the CUDA context and the
+    pinned host buffers exist: with one process per GPU the per-frame host->device copies (76 MB at Replica size) then come
+    from memory on the GPU's own socket.  Returns the CPU list, or None when NVML gives no usable answer (then nothing is
+    changed)."""
+    try:
+        import pynvml
+        pynvml.nvmlInit()
+        vis = os.environ.get("CUDA_VISIBLE_DEVICES")
+        idx = local
+        if vis:
+            ent = vis.split(",")[local].strip()
+            if ent.isdigit():
+                idx = int(ent)
+            else:
+                return None
+        h = pynvml.nvmlDeviceGetHandleByIndex(idx)
+        n_words = (os.cpu_count() + 63) // 64
+        mask = pynvml.nvmlDeviceGetCpuAffinity(h, n_words)
+        cpus = [64 * i + b for i, m in enumerate(mask) for b in range(64) if (int(m) >> b) & 1]
+        allowed = os.sched_getaffinity(0)
+        cpus = [c for c in cpus if c in allowed]
+        if cpus and len(cpus) < len(allowed):
+            os.sched_setaffinity(0, cpus)
+            return cpus
+    except Exception:
+        pass
+    return None
+
+
 def init_from_env(backend=None):
     """(rank, world, local_rank); initialises torch.distributed when launched under torchrun."""
     world = int(os.environ.get("WORLD_SIZE", "1"))
     rank = int(os.environ.get("RANK", "0"))
     local = int(os.environ.get("LOCAL_RANK", "0"))
+    if world > 1 and torch.cuda.is_available() and os.environ.get("OO_NO_CPU_BIND") != "1":
+        cpus = bind_to_gpu_cpus(local)
+        if cpus is not None:
+            print("[openobj_b200.dist] rank %d bound to %d CPUs local to GPU %d" % (rank, len(cpus), local), file=sys.stderr)
     if world > 1 and not dist.is_initialized():
         os.environ.setdefault("MASTER_ADDR", "127.0.0.1")
         os.environ.setdefault("MASTER_PORT", "29500")
