@@ -275,6 +275,31 @@ int oo_rng_fill(uint64_t seed, uint32_t frame, const int32_t* obj_ids, int n_obj
 int oo_rng_fill_rows(uint64_t seed, uint32_t frame, const int32_t* obj_ids, int n_obj, int n_rows, int row_words,
                      int kind /*0 uniform [0,1), 1 normal(0,std)*/, float std, float* out, void* stream);
 
+/* ---- the stand-alone helpers of the reference surface (utils.{stratified_bins, normal_bins_sampling,
+ *      origin_dirs_W, ray_box_intersection}, Trainer.sample_points_bbox, sceneObject.sample_3d_points).  On the hot path
+ *      they are fused into oo_sample_rays / oo_render_object; these element-wise kernels give hand-composed callers the
+ *      same arithmetic in the reference's operation order.  Random draws are inputs (the host surface draws them where the
+ *      reference calls torch.rand / normal_).  All pointers are device pointers unless marked HOST.
+ *      oo_ray_box: utils.ray_box_intersection (utils.py:309-319); origins / dirs [n][3]; bounds HOST float[3];
+ *                  near / far [n], hit u8 [n] = near <= far && far > 0.
+ *      oo_origin_dirs: utils.origin_dirs_W (utils.py:324-336); t_wc [B][4][4], dirs_c [B][n][3] -> origins [B][3], dirs_w.
+ *      oo_stratified_bins: utils.stratified_bins (utils.py:342-379) given u [n][n_bins] in [0,1) and
+ *                  lin = torch.linspace(0, 1, n_bins + 1) (device); min / max per ray, or NULL -> the scalar.
+ *      oo_normal_bins: utils.normal_bins_sampling (utils.py:382-397) given the normal_(0, delta/3) draws [n][n_bins]:
+ *                  rows sorted ascending, clipped to +-delta, + depth[n].
+ *      oo_ray_points: origins + dirs * z - center (vmap.py:548-551); midpoints = 1: z is replaced by
+ *                  0.5 (z[i+1] + z[i]) first (n_samp - 1 points per ray; trainer.py:175-177), written to z_mid_out if set;
+ *                  center HOST float[3] or NULL. */
+int oo_ray_box(const float* origins, const float* dirs, const float* bounds_min, const float* bounds_max, long long n,
+               float* near_out, float* far_out, uint8_t* hit_out, void* stream);
+int oo_origin_dirs(const float* t_wc, const float* dirs_c, int n_poses, int n_per_pose, float* origins, float* dirs_w,
+                   void* stream);
+int oo_stratified_bins(const float* u, const float* min_depth, const float* max_depth, float min_scalar, float max_scalar,
+                       const float* lin, long long n_rays, int n_bins, float* z, void* stream);
+int oo_normal_bins(const float* draws, const float* depth, long long n_rays, int n_bins, float delta, float* z, void* stream);
+int oo_ray_points(const float* origins, const float* dirs, const float* z, long long n_rays, int n_samp, int midpoints,
+                  const float* center, float* z_mid_out, float* pcs, void* stream);
+
 /* ---- a19: render_2D_syn for one object over all W*H pixels (vmap.py:604-685, trainer.py:130-198)
  *      and the sequential depth-test merge (train.py:577-594). */
 typedef struct oo_render_args {

@@ -101,6 +101,13 @@ _SIGS = {
     "oo_make_grid": ([POINTER(Grid), c_void_p, c_void_p], c_int),
     "oo_eval_points": ([c_void_p, c_void_p, c_int64, c_float, c_void_p, c_void_p, c_void_p, c_void_p], c_int),
     "oo_occupancy_activation": ([c_void_p, c_void_p, c_int64, c_void_p, c_void_p], c_int),
+    "oo_ray_box": ([c_void_p, c_void_p, POINTER(c_float), POINTER(c_float), c_int64, c_void_p, c_void_p, c_void_p, c_void_p],
+                   c_int),
+    "oo_origin_dirs": ([c_void_p, c_void_p, c_int, c_int, c_void_p, c_void_p, c_void_p], c_int),
+    "oo_stratified_bins": ([c_void_p, c_void_p, c_void_p, c_float, c_float, c_void_p, c_int64, c_int, c_void_p, c_void_p], c_int),
+    "oo_normal_bins": ([c_void_p, c_void_p, c_int64, c_int, c_float, c_void_p, c_void_p], c_int),
+    "oo_ray_points": ([c_void_p, c_void_p, c_void_p, c_int64, c_int, c_int, POINTER(c_float), c_void_p, c_void_p, c_void_p],
+                      c_int),
     "oo_fma_peak": ([c_int, c_int, c_void_p, c_void_p], c_int),
     "oo_bg_param_count": ([c_int], c_int),
     "oo_bg_param_offset": ([c_int, c_int], c_int),

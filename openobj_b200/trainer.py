@@ -59,6 +59,40 @@ class Trainer:
             return None
         return occ, color, clip
 
+    def sample_points_bbox(self, bbox, do_eval=True, draws=None):
+        """trainer.py:130-198: rays of `self.T_WC_gt` [B,4,4] / `self.dirs_C_gt` [B,n,3] (or [B,3]) against the oriented box
+        `bbox` (.R, .center, .extent); stratified depths between entry and exit (+0.2), bin midpoints, sample points.
+        Sets .dirs_W .origins .z_vals_cat .z_vals .input_pcs for the rays that hit and returns (hit_mask, near, far), or
+        (None, None, None) when at most one ray hits.  `draws` replaces the torch.rand of stratified_bins."""
+        import numpy as np
+        from . import utils
+        dev = self.dirs_C_gt.device
+        T_wc_all = self.T_WC_gt.to(dev).float()
+        origins, dirs_W = utils.origin_dirs_W(T_wc_all, self.dirs_C_gt)
+        B = T_wc_all.shape[0]
+        dirs_W = dirs_W.reshape(-1, 3)
+        origins = origins[:, None, :].expand(B, dirs_W.shape[0] // B, 3).reshape(-1, 3)
+        n_bins = 150 if do_eval else (60 if self.obj_id == 0 else 20)
+        T_WO = torch.eye(4)                                              # 4x4 host algebra, as the reference (trainer.py:153-160)
+        T_WO[:3, :3] = torch.as_tensor(np.asarray(bbox.R), dtype=torch.float32)
+        T_WO[:3, 3] = torch.as_tensor(np.asarray(bbox.center), dtype=torch.float32)
+        T_OC = torch.inverse(T_WO) @ self.T_WC_gt[0].cpu().to(T_WO.dtype)
+        T_OC_gt = T_OC.float().unsqueeze(0).repeat_interleave(B, dim=0).to(dev)
+        origins_r, dirs_r = utils.origin_dirs_W(T_OC_gt, self.dirs_C_gt)
+        dirs_r = dirs_r.reshape(-1, 3)
+        origins_r = origins_r[:, None, :].expand(B, dirs_r.shape[0] // B, 3).reshape(-1, 3)
+        half = np.asarray(bbox.extent, dtype=np.float64).reshape(-1).astype(np.float32) / 2.0
+        near, far, hit = utils.ray_box_intersection(origins_r, dirs_r, -half, half)
+        if int(hit.sum()) <= 1:
+            return None, None, None
+        near_h = torch.clamp(near[hit], min=0.0)                         # trainer.py:168 (selection / clamp of the bounds)
+        far_h = far[hit] + 0.2                                           # :169 if cam inside bound extend ray a bit
+        n_rays = int(near_h.shape[0])
+        self.dirs_W, self.origins = dirs_W[hit], origins[hit]
+        self.z_vals_cat = utils.stratified_bins(near_h, far_h, n_bins, n_rays, device=dev, draws=draws)
+        self.input_pcs, self.z_vals = utils.ray_points(self.origins, self.dirs_W, self.z_vals_cat, midpoints=True)
+        return hit, near_h, far_h
+
     def _wide_model(self, device):
         from .background import BackgroundModel
         bg = BackgroundModel(hidden=self.hidden_feature_size, device=device, scale=self.obj_scale)

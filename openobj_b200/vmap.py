@@ -175,6 +175,44 @@ class sceneObject:
                 out.valid[0].bool(), out.labels[0], out.pcs[0].view(n_frames, n_samples, S, 3),
                 out.z[0].view(n_frames, n_samples, S), pf)
 
+    def sample_3d_points(self, sampled_rgbs, sampled_depth, origins, dirs_w, sampled_partfeat=None, draws=None):
+        """vmap.py:456-554 on caller-supplied rays (get_training_samples does all of this in one oo_sample_rays launch; this
+        is the reference's stand-alone entry, composed from the same utils helpers in the same order, so it consumes
+        torch's generator exactly like the reference: rand(invalid, S), rand(valid, N), normal_(this-object, M),
+        rand(other, M)).  sampled_rgbs [F,P,4] u8 (rgb + pixel state), sampled_depth [F,P], origins [F,3], dirs_w [F,P,3].
+        `draws` = (invalid, valid, normal, other) tensors replacing those four generator calls (tests).
+        Returns (rgb, depth, valid_depth_mask, obj_labels, input_pcs [F,P,S,3], sampled_z [F,P,S], sampled_partfeat)."""
+        from . import utils
+        dr = draws if draws is not None else (None, None, None, None)
+        nc, nb, eps = self.n_bins_cam2surface, self.n_bins, self.surface_eps
+        dev = sampled_depth.device
+        F_, P_ = sampled_rgbs.shape[0], sampled_rgbs.shape[1]
+        sampled_z = torch.zeros(F_ * P_, nc + nb, dtype=torch.float32, device=dev)
+        d = sampled_depth.reshape(-1).float()
+        invalid = d <= self.min_bound
+        max_bound = torch.max(sampled_depth)
+        n_inv = int(invalid.count_nonzero())
+        if n_inv:
+            sampled_z[invalid, :] = utils.stratified_bins(self.min_bound, max_bound.reshape(1), nc + nb, n_inv, device=dev, draws=dr[0])
+        valid = ~invalid
+        n_val = int(valid.count_nonzero())
+        if n_val:
+            sampled_z[valid, :nc] = utils.stratified_bins(self.min_bound, d[valid] - eps, nc, n_val, device=dev, draws=dr[1])
+            state = sampled_rgbs[..., -1].reshape(-1)
+            obj = (state == self.this_obj) & valid
+            n_obj = int(obj.count_nonzero())
+            if n_obj:
+                sampled_z[obj, nc:] = utils.normal_bins_sampling(d[obj], nb, n_obj, delta=eps, device=dev, draws=dr[2])
+            oth = (state != self.this_obj) & valid
+            n_oth = int(oth.count_nonzero())
+            if n_oth:
+                sampled_z[oth, nc:] = utils.stratified_bins(d[oth] - eps, d[oth] + self.stop_eps, nb, n_oth, device=dev, draws=dr[3])
+        org = origins[:, None, :].expand(F_, P_, 3).reshape(-1, 3)
+        center = None if float(torch.as_tensor(self.obj_center).abs().sum()) == 0.0 else torch.as_tensor(self.obj_center).expand(3)
+        pcs, _ = utils.ray_points(org, dirs_w.reshape(-1, 3), sampled_z, center=center)
+        return (sampled_rgbs[..., :3], sampled_depth, valid, sampled_rgbs[..., -1].reshape(-1), pcs.view(F_, P_, nc + nb, 3),
+                sampled_z.view(F_, P_, nc + nb), sampled_partfeat)
+
     def get_bound(self, intrinsic_open3d=None, final=False):
         if self.bbox_final or self.bbox3dour is not None:
             return self.bbox3d, self.bbox3dour

@@ -481,6 +481,84 @@ def gen_checkpoint(m):
     return dict(points=pts, occ=occ, color=color, clip=clip[:8], clip_feat=obj.clip_feat, caption_feat=obj.caption_feat)
 
 
+def gen_surface(m):
+    """The stand-alone helpers of the surface: utils.{stratified_bins, normal_bins_sampling, origin_dirs_W,
+    ray_box_intersection}, Trainer.sample_points_bbox, sceneObject.sample_3d_points -- run on the CPU reference with every
+    random draw recorded."""
+    torch.manual_seed(55)
+    U = m["utils"]
+    g = torch.Generator().manual_seed(56)
+    out = {}
+    # stratified_bins: per-ray bounds, scalar bounds
+    mn, mx = torch.rand(33, generator=g), 1.0 + 3.0 * torch.rand(33, generator=g)
+    with Tape() as t:
+        z = U.stratified_bins(mn, mx, 7, 33, device="cpu")
+    out.update(sb_min=mn, sb_max=mx, sb_u=t.calls[0][1], sb_z=z)
+    with Tape() as t:
+        z = U.stratified_bins(0.0, 3.5, 10, 20, device="cpu")
+    out.update(sbs_u=t.calls[0][1], sbs_z=z)
+    # normal_bins_sampling
+    dep = 1.0 + 2.0 * torch.rand(25, generator=g)
+    with Tape() as t:
+        z = U.normal_bins_sampling(dep, 9, 25, 0.1, device="cpu")
+    out.update(nb_depth=dep, nb_draws=t.calls[0][1], nb_z=z)
+    # origin_dirs_W, both shapes
+    def rigid(k):
+        q, _ = torch.linalg.qr(torch.randn(3, 3, generator=g))
+        T = torch.eye(4)
+        T[:3, :3], T[:3, 3] = q, torch.randn(3, generator=g)
+        return T
+    T = torch.stack([rigid(k) for k in range(4)])
+    d1, d2 = torch.randn(4, 3, generator=g), torch.randn(4, 17, 3, generator=g)
+    o1, w1 = U.origin_dirs_W(T, d1)
+    o2, w2 = U.origin_dirs_W(T, d2)
+    out.update(od_T=T, od_d1=d1, od_d2=d2, od_o1=o1, od_w1=w1, od_o2=o2, od_w2=w2)
+    # ray_box_intersection
+    ro, rd = torch.randn(60, 3, generator=g) * 2.0, torch.randn(60, 3, generator=g)
+    bmin, bmax = torch.tensor([-0.7, -0.5, -0.9]), torch.tensor([0.8, 0.6, 0.4])
+    near, far, hit = U.ray_box_intersection(ro, rd, bmin, bmax)
+    out.update(rb_o=ro, rb_d=rd, rb_min=bmin, rb_max=bmax, rb_near=near, rb_far=far, rb_hit=hit)
+    # Trainer.sample_points_bbox
+    cfg = small_cfg(W=16, H=12)
+    cfg.fx = cfg.fy = 14.0
+    cfg.cx, cfg.cy = 7.5, 5.5
+    cfg.obj_id = 1
+    tr = m["trainer"].Trainer(cfg)
+    cam = m["vmap"].cameraInfo(cfg)
+    pose = torch.eye(4)
+    pose[:3, 3] = torch.tensor([0.05, -0.02, -0.3])
+    tr.dirs_C_gt = cam.rays_dir_cache.reshape(-1, 3).clone()               # one pose per ray, as render_2D_syn sets them
+    tr.T_WC_gt = pose.unsqueeze(0).repeat_interleave(tr.dirs_C_gt.shape[0], dim=0)   # (vmap.py:618-622)
+    bb = U.BoundingBox()
+    ang = 0.25
+    bb.R = np.array([[np.cos(ang), -np.sin(ang), 0], [np.sin(ang), np.cos(ang), 0], [0, 0, 1]])
+    bb.center, bb.extent = np.array([0.1, 0.0, 2.0]), np.array([1.0, 0.8, 1.2])
+    with Tape() as t:
+        hit, near, far = tr.sample_points_bbox(bb, do_eval=True)
+    assert [k for k, _ in t.calls] == ["rand"]
+    out.update(spb_T=tr.T_WC_gt, spb_dirs=tr.dirs_C_gt, spb_R=torch.from_numpy(bb.R), spb_center=torch.from_numpy(bb.center),
+               spb_extent=torch.from_numpy(bb.extent), spb_u=t.calls[0][1], spb_hit=hit, spb_near=near, spb_far=far,
+               spb_zcat=tr.z_vals_cat, spb_z=tr.z_vals, spb_pcs=tr.input_pcs, spb_dirsW=tr.dirs_W, spb_origins=tr.origins)
+    # sceneObject.sample_3d_points
+    cfg2 = small_cfg(W=40, H=30)
+    rgb, depth, state, bbox, Tp, part = synth_frame(g, 100, 60, with_part=False)
+    obj = m["vmap"].sceneObject(cfg2, 1, rgb[:40, :30].contiguous(), depth[:40, :30].contiguous(), state[:40, :30].contiguous(),
+                                torch.tensor([0, 39, 0, 29]), Tp, 0)
+    F_, P_ = 3, 8
+    srgb = torch.randint(0, 256, (F_, P_, 4), generator=g, dtype=torch.uint8)
+    srgb[..., 3] = torch.randint(0, 3, (F_, P_), generator=g, dtype=torch.uint8)
+    sdep = (1.0 + 2.0 * torch.rand(F_, P_, generator=g)).float()
+    sdep[0, 1] = 0.0
+    sdep[2, 5] = 0.0
+    org, dw = torch.randn(F_, 3, generator=g) * 0.2, torch.randn(F_, P_, 3, generator=g)
+    with Tape() as t:
+        res = obj.sample_3d_points(srgb, sdep, org, dw)
+    assert [k for k, _ in t.calls] == ["rand", "rand", "normal", "rand"]
+    out.update(s3_rgbs=srgb, s3_depth=sdep, s3_origins=org, s3_dirs=dw, s3_u_inv=t.calls[0][1], s3_u_val=t.calls[1][1],
+               s3_n_obj=t.calls[2][1], s3_u_oth=t.calls[3][1], s3_valid=res[2], s3_labels=res[3], s3_pcs=res[4], s3_z=res[5])
+    return out
+
+
 def save(name, d):
     arrs = {k: (v.numpy() if torch.is_tensor(v) else np.asarray(v)) for k, v in d.items()}
     path = os.path.join(OUT, name)
@@ -493,6 +571,9 @@ def main():
     m = rh.load()
     if "--only-eval" in sys.argv:               # added after the other files were frozen: do not touch them
         save("eval_grid.npz", gen_eval_grid(m))
+        return
+    if "--only-surface" in sys.argv:
+        save("surface.npz", gen_surface(m))
         return
     if "--only-ckpt" in sys.argv:
         save("ckpt_expect.npz", gen_checkpoint(m))
@@ -507,6 +588,7 @@ def main():
     save("render_obj.npz", gen_render(m))
     save("eval_grid.npz", gen_eval_grid(m))
     save("ckpt_expect.npz", gen_checkpoint(m))
+    save("surface.npz", gen_surface(m))
     with open(os.path.join(OUT, "keyframe_policy.json"), "w") as f:
         json.dump(gen_keyframe_policy(m), f)
     print("done; torch", torch.__version__)

@@ -314,6 +314,20 @@ def stratified(min_d, max_d, n_bins, u):
     return lower + u * (rng / n_bins)[..., None]
 
 
+def normal_bins(depth, draws, delta):
+    """utils.normal_bins_sampling (utils.py:382-397) with the normal_(0, delta/3) draws [n, n_bins] supplied."""
+    return depth[:, None] + torch.clip(draws.sort().values, -delta, delta)
+
+
+def origin_dirs_w(T_wc, dirs_c):
+    """utils.origin_dirs_W (utils.py:324-336)."""
+    if dirs_c.shape[1] == 3 and dirs_c.dim() == 2:
+        dirs_w = torch.matmul(T_wc[:, :3, :3], dirs_c.unsqueeze(-1)).squeeze(-1)
+    else:
+        dirs_w = (T_wc[:, None, :3, :3] @ dirs_c[..., None]).squeeze(-1)
+    return T_wc[:, :3, -1], dirs_w
+
+
 def sample_object(rgbs, depth, t_wc, bbox, rays_dir, tape: SampleTape, n_c2s=1, n_bins=9,
                   eps=0.1, other_eps=0.05, min_bound=0.0, use_frame=None, stride=10, part_down=5):
     """sceneObject.get_training_samples + sample_3d_points for one object.

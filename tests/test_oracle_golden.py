@@ -259,3 +259,23 @@ def test_eval_grid_oracle(tag):
     close(clip[::7], d[tag + "_clip"], rtol=1e-4, atol=1e-5)
     o = d[tag + "_occ"]
     assert float((o > 0.5).float().mean()) > 0.1 and float((o < 0.5).float().mean()) > 0.01     # occupied and free points
+
+
+# ---- stand-alone surface helpers: surface.npz frozen from the reference's utils / Trainer / sceneObject ----
+def test_surface_helpers_oracle():
+    d = load("surface.npz")
+    assert torch.equal(oc.stratified(d["sb_min"], d["sb_max"], 7, d["sb_u"]), d["sb_z"])
+    assert torch.equal(oc.stratified(0.0, 3.5, 10, d["sbs_u"]), d["sbs_z"])
+    assert torch.equal(oc.normal_bins(d["nb_depth"], d["nb_draws"], 0.1), d["nb_z"])
+    o1, w1 = oc.origin_dirs_w(d["od_T"], d["od_d1"])
+    o2, w2 = oc.origin_dirs_w(d["od_T"], d["od_d2"])
+    close(w1, d["od_w1"], rtol=1e-6, atol=1e-6); close(w2, d["od_w2"], rtol=1e-6, atol=1e-6)
+    assert torch.equal(o1, d["od_o1"]) and torch.equal(o2, d["od_o2"])
+    near, far, hit = oc.ray_box(d["rb_o"], d["rb_d"], d["rb_min"], d["rb_max"])
+    assert torch.equal(near, d["rb_near"]) and torch.equal(far, d["rb_far"]) and torch.equal(hit, d["rb_hit"])
+    # sample_points_bbox: depths between the clipped entry and exit + 0.2, bin midpoints, points
+    zc = oc.stratified(d["spb_near"], d["spb_far"], 150, d["spb_u"])
+    assert torch.equal(zc, d["spb_zcat"])
+    zm = 0.5 * (zc[..., 1:] + zc[..., :-1])
+    assert torch.equal(zm, d["spb_z"])
+    close(d["spb_origins"][:, None, :] + d["spb_dirsW"][:, None, :] * zm[:, :, None], d["spb_pcs"], rtol=0, atol=0)
