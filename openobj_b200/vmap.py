@@ -213,6 +213,9 @@ class sceneObject:
         return (sampled_rgbs[..., :3], sampled_depth, valid, sampled_rgbs[..., -1].reshape(-1), pcs.view(F_, P_, nc + nb, 3),
                 sampled_z.view(F_, P_, nc + nb), sampled_partfeat)
 
+    def set_semantic(self, semantic_id):
+        self.semantic_id = semantic_id            # vmap.py:284-285
+
     def get_bound(self, intrinsic_open3d=None, final=False):
         if self.bbox_final or self.bbox3dour is not None:
             return self.bbox3d, self.bbox3dour
