@@ -299,6 +299,13 @@ int oo_stratified_bins(const float* u, const float* min_depth, const float* max_
 int oo_normal_bins(const float* draws, const float* depth, long long n_rays, int n_bins, float delta, float* z, void* stream);
 int oo_ray_points(const float* origins, const float* dirs, const float* z, long long n_rays, int n_samp, int midpoints,
                   const float* center, float* z_mid_out, float* pcs, void* stream);
+/* render_rays.occupancy_to_termination (render_rays.py:32-54): T_i = occ_i * prod_{j<i} (1 - occ_j + 1e-10) along the
+ * n_samp samples of each ray; render_rays.render (render_rays.py:56-63): out[r][c] = sum_i T[r][i] vals[r][i][c]
+ * (n_chan = 1 for depth / variance, 3 colour, 512 part features).  Forward only: the training path differentiates through
+ * the fused kernels (oo_train_step, oo_loss_fwd / _bwd). */
+int oo_termination(const float* occupancy, long long n_rays, int n_samp, float* termination, void* stream);
+int oo_render_sum(const float* termination, const float* vals, long long n_rays, int n_samp, int n_chan, float* out,
+                  void* stream);
 
 /* ---- a19: render_2D_syn for one object over all W*H pixels (vmap.py:604-685, trainer.py:130-198)
  *      and the sequential depth-test merge (train.py:577-594). */

@@ -108,6 +108,8 @@ _SIGS = {
     "oo_normal_bins": ([c_void_p, c_void_p, c_int64, c_int, c_float, c_void_p, c_void_p], c_int),
     "oo_ray_points": ([c_void_p, c_void_p, c_void_p, c_int64, c_int, c_int, POINTER(c_float), c_void_p, c_void_p, c_void_p],
                       c_int),
+    "oo_termination": ([c_void_p, c_int64, c_int, c_void_p, c_void_p], c_int),
+    "oo_render_sum": ([c_void_p, c_void_p, c_int64, c_int, c_int, c_void_p, c_void_p], c_int),
     "oo_fma_peak": ([c_int, c_int, c_void_p, c_void_p], c_int),
     "oo_bg_param_count": ([c_int], c_int),
     "oo_bg_param_offset": ([c_int, c_int], c_int),

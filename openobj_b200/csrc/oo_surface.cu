@@ -101,6 +101,31 @@ __global__ void k_ray_points(const float* __restrict__ org, const float* __restr
     }
 }
 
+// T[r][i] = occ[r][i] * prod_{j<i} (1 - occ[r][j] + 1e-10), one thread per ray (render_rays.py:32-54)
+__global__ void k_termination(const float* __restrict__ occ, long long n, int S, float* __restrict__ T) {
+    for (long long r = (long long)blockIdx.x * blockDim.x + threadIdx.x; r < n; r += (long long)gridDim.x * blockDim.x) {
+        float p = 1.f;
+        for (int i = 0; i < S; ++i) {
+            const float o = occ[r * S + i];
+            T[r * S + i] = __fmul_rn(o, p);
+            p = __fmul_rn(p, __fadd_rn(__fsub_rn(1.f, o), 1e-10f));
+        }
+    }
+}
+
+// out[r][c] = sum_i T[r][i] * vals[r][i][c] in sample order (render_rays.py:56-63)
+__global__ void k_render_sum(const float* __restrict__ T, const float* __restrict__ vals, long long n, int S, int C,
+                             float* __restrict__ out) {
+    const long long total = n * C;
+    for (long long e = (long long)blockIdx.x * blockDim.x + threadIdx.x; e < total; e += (long long)gridDim.x * blockDim.x) {
+        const long long r = e / C;
+        const int c = (int)(e - r * C);
+        float acc = 0.f;
+        for (int i = 0; i < S; ++i) acc = __fadd_rn(acc, __fmul_rn(T[r * S + i], vals[(r * S + i) * C + c]));
+        out[e] = acc;
+    }
+}
+
 int grid_for(long long n) {
     long long b = (n + 255) / 256;
     return (int)(b < 1 ? 1 : (b > 148 * 16 ? 148 * 16 : b));
@@ -150,6 +175,21 @@ extern "C" int oo_ray_points(const float* origins, const float* dirs, const floa
     const float3 c = center ? make_float3(center[0], center[1], center[2]) : make_float3(0.f, 0.f, 0.f);     // HOST 3-vector
     k_ray_points<<<grid_for(n_rays * n_samp), 256, 0, (cudaStream_t)stream>>>(origins, dirs, z, n_rays, n_samp, midpoints, c,
                                                                             z_mid_out, pcs);
+    OO_LAUNCH_CHECK();
+    return 0;
+}
+
+extern "C" int oo_termination(const float* occupancy, long long n_rays, int n_samp, float* termination, void* stream) {
+    OO_REQUIRE(occupancy && termination && n_rays > 0 && n_samp > 0, "oo_termination: bad argument");
+    k_termination<<<grid_for(n_rays), 256, 0, (cudaStream_t)stream>>>(occupancy, n_rays, n_samp, termination);
+    OO_LAUNCH_CHECK();
+    return 0;
+}
+
+extern "C" int oo_render_sum(const float* termination, const float* vals, long long n_rays, int n_samp, int n_chan, float* out,
+                             void* stream) {
+    OO_REQUIRE(termination && vals && out && n_rays > 0 && n_samp > 0 && n_chan > 0, "oo_render_sum: bad argument");
+    k_render_sum<<<grid_for(n_rays * n_chan), 256, 0, (cudaStream_t)stream>>>(termination, vals, n_rays, n_samp, n_chan, out);
     OO_LAUNCH_CHECK();
     return 0;
 }

@@ -1,11 +1,21 @@
 """Mirror of objnerf/render_rays.py.  The compositing / loss arithmetic of the training path runs in the fused
 kernels (`loss.step_batch_loss` -> K3, `Ensemble` -> K1); the small helpers below keep the reference's names for
-callers that compose them by hand, and are thin tensor expressions with the same semantics (they are not on the
-hot path: train.py reaches them only through loss.step_batch_loss)."""
+callers that compose them by hand (train.py reaches them only through loss.step_batch_loss).  For CUDA tensors that
+do not require grad, occupancy_activation / occupancy_to_termination / render run as kernels of libopenobj_b200.so
+(oo_occupancy_activation, oo_termination, oo_render_sum); the tensor expressions with the same semantics remain for
+hand-composed autograd graphs, which the fused path does not need."""
 import torch
 
 
+def _kernel_ok(*ts):
+    """CUDA float32 tensors outside any autograd graph: the forward-only kernels apply."""
+    return all(torch.is_tensor(t) and t.is_cuda and t.dtype == torch.float32 and not t.requires_grad for t in ts)
+
+
 def occupancy_activation(alpha, distances=None):
+    if _kernel_ok(alpha) and (distances is None or _kernel_ok(distances)):
+        from . import ops
+        return ops.occupancy_activation(alpha, distances)
     if distances is not None:
         return 1.0 - torch.exp(-alpha * distances)
     return torch.sigmoid(alpha)
@@ -20,12 +30,35 @@ def alpha_to_occupancy(depths, dirs, alpha, add_last=False):
 
 
 def occupancy_to_termination(occupancy, is_batch=False):
+    if _kernel_ok(occupancy) and occupancy.dim() >= 1 and occupancy.numel() > 0:
+        from ._lib import check, lib, ptr, stream
+        occ = occupancy.contiguous()
+        out = torch.empty_like(occ)
+        with torch.cuda.device(occ.device):
+            check(lib().oo_termination(ptr(occ), occ.numel() // occ.shape[-1], occ.shape[-1], ptr(out), stream()), "oo_termination")
+        return out
     free = 1. - occupancy + 1e-10
     free = torch.cat([torch.ones_like(occupancy[..., :1]), free[..., :-1]], dim=-1)
     return occupancy * torch.cumprod(free, dim=-1)
 
 
 def render(termination, vals, dim=-1):
+    """render_rays.py:56-63.  The two call forms of loss.py: (T [..,S], vals [..,S], dim=-1) and
+    (T [..,S,1], vals [..,S,C], dim=-2)."""
+    if _kernel_ok(termination, vals) and termination.numel() > 0:
+        form1 = dim in (-1, vals.dim() - 1) and termination.shape == vals.shape
+        form2 = (dim in (-2, vals.dim() - 2) and termination.dim() == vals.dim() and termination.shape[-1] == 1
+                 and termination.shape[:-1] == vals.shape[:-1])
+        if form1 or form2:
+            from ._lib import check, lib, ptr, stream
+            S = vals.shape[-1] if form1 else vals.shape[-2]
+            C = 1 if form1 else vals.shape[-1]
+            lead = list(vals.shape[:-1]) if form1 else list(vals.shape[:-2])
+            T, v = termination.contiguous(), vals.contiguous()
+            out = torch.empty(lead if form1 else lead + [C], dtype=torch.float32, device=v.device)
+            with torch.cuda.device(v.device):
+                check(lib().oo_render_sum(ptr(T), ptr(v), v.numel() // (S * C), S, C, ptr(out), stream()), "oo_render_sum")
+            return out
     return (termination * vals).sum(dim=dim)
 
 

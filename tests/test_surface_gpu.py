@@ -93,3 +93,29 @@ def test_scene_object_sample_3d_points_matches_reference():
     lab1 = (d["s3_rgbs"][..., 3] == 1) & (d["s3_depth"] > 0)
     near_surface = (z2.cpu()[lab1][:, 1:] - d["s3_depth"][lab1][:, None]).abs()
     assert float(near_surface.max()) <= 0.1 + 1e-6
+
+
+def test_render_rays_helpers_kernels_vs_tensor_expressions():
+    """render_rays.occupancy_activation / occupancy_to_termination / render: CUDA tensors outside autograd run as kernels
+    (oo_occupancy_activation, oo_termination, oo_render_sum); the same functions on CPU tensors are the reference's tensor
+    expressions (render_rays.py:6-63).  Both call forms of loss.py (:31-35,82) are covered; a tensor that requires grad
+    keeps the differentiable expression."""
+    from openobj_b200 import render_rays as R
+    g = torch.Generator().manual_seed(11)
+    alpha = torch.randn(6, 50, 10, generator=g) * 3
+    z = torch.sort(torch.rand(6, 50, 10, generator=g) * 4 + 0.3, dim=-1).values
+    color = torch.rand(6, 50, 10, 3, generator=g)
+    feat = torch.randn(6, 50, 10, 64, generator=g)
+    occ_c, occ_g = R.occupancy_activation(alpha), R.occupancy_activation(alpha.to(DEV))
+    torch.testing.assert_close(occ_g.cpu(), occ_c, rtol=1e-6, atol=1e-7)
+    T_c, T_g = R.occupancy_to_termination(occ_c, is_batch=True), R.occupancy_to_termination(occ_c.to(DEV), is_batch=True)
+    torch.testing.assert_close(T_g.cpu(), T_c, rtol=1e-5, atol=1e-7)
+    torch.testing.assert_close(R.render(T_c.to(DEV), z.to(DEV)).cpu(), R.render(T_c, z), rtol=1e-5, atol=1e-6)
+    torch.testing.assert_close(R.render(T_c.to(DEV)[..., None], color.to(DEV), dim=-2).cpu(), R.render(T_c[..., None], color, dim=-2),
+                               rtol=1e-5, atol=1e-6)
+    torch.testing.assert_close(R.render(T_c.to(DEV)[..., None], feat.to(DEV), dim=-2).cpu(), R.render(T_c[..., None], feat, dim=-2),
+                               rtol=1e-5, atol=1e-5)
+    a = alpha.to(DEV).requires_grad_(True)
+    d = R.render(R.occupancy_to_termination(R.occupancy_activation(a)), z.to(DEV)).sum()
+    d.backward()
+    assert a.grad is not None and bool(torch.isfinite(a.grad).all())
