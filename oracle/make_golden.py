@@ -1,6 +1,7 @@
 """Freeze golden vectors from the UNMODIFIED reference (run here, CPU) into tests/golden/.
 
     python oracle/make_golden.py            # needs /root/reference
+    python oracle/make_golden.py --check    # regenerate in memory and compare with the committed files (bit for bit)
 
 TEST INFRASTRUCTURE ONLY.  The reference ships no tests or fixtures (SURVEY.md
 section 4), so these files are the pins for oracle/openobj_oracle.py and, through it, for
@@ -566,9 +567,27 @@ def save(name, d):
     print("wrote", path, "%.1f KB" % (os.path.getsize(path) / 1024))
 
 
+def check(m):
+    """--check: regenerate every fixture in memory and compare it with the committed file (bit for bit)."""
+    gens = [("bg_step.npz", gen_bg_step), ("model_step.npz", gen_model_step), ("sample_obj.npz", lambda mm: gen_sampling(mm, bg=False)),
+            ("sample_bg.npz", lambda mm: gen_sampling(mm, bg=True)), ("render_obj.npz", gen_render), ("eval_grid.npz", gen_eval_grid),
+            ("surface.npz", gen_surface)]
+    bad = 0
+    for name, fn in gens:
+        new = {k: (v.detach().numpy() if torch.is_tensor(v) else np.asarray(v)) for k, v in fn(m).items()}
+        old = np.load(os.path.join(OUT, name))
+        same = sorted(new) == sorted(old.files) and all(
+            new[k].shape == old[k].shape and np.array_equal(new[k], old[k], equal_nan=True) for k in new)
+        print("%-18s %s" % (name, "identical" if same else "DIFFERS"))
+        bad += not same
+    return bad
+
+
 def main():
     os.makedirs(OUT, exist_ok=True)
     m = rh.load()
+    if "--check" in sys.argv:
+        sys.exit(check(m))
     if "--only-eval" in sys.argv:               # added after the other files were frozen: do not touch them
         save("eval_grid.npz", gen_eval_grid(m))
         return
