@@ -1,5 +1,7 @@
 """Philox4x32-10 counter RNG in numpy (Salmon et al., "Parallel random numbers: as easy as 1, 2, 3", SC'11) --
 the published algorithm oo_rng_fill implements.  TEST INFRASTRUCTURE ONLY.
+Pinned: tests/test_philox_cpu.py checks it against the Random123 known-answer vectors of Philox4x32-10; the GPU tests
+check the kernels against it word for word.
 Element i of object `oid` in frame `frame` = word (i % 4) of philox(counter=(i//4 lo, i//4 hi, oid, frame), key=seed)."""
 import numpy as np
 
