@@ -211,6 +211,7 @@ def run_ours(args):
     cfg.part_mode = bool(args.part)
     cfg.do_bg = False
     n_local = args.objects
+    cfg.max_n_models = n_local * world          # trainer.n_models: the global cap on objects (train.py:231-233)
     steps, warmup = args.steps, max(args.warmup, 3)
     frames_w = (warmup + ITERS - 1) // ITERS
     frames_t = (steps + ITERS - 1) // ITERS
@@ -259,7 +260,7 @@ def run_ours(args):
             if host:
                 _ = lt[it - 1].sum().item()        # D2H read of the step result inside the timed region
             f += 1
-            # per step: k_train + k_update; per frame: k_gram (part features on), label counts + adam schedule, append,
+            # per step: k_train + k_update; per frame: k_gram (part features on), label counts + adam schedule, frame store,
             # sampler (two passes)
             launches["n"] += 2 * it + (1 if args.part else 0) + 2 + 1 + 2
 
@@ -354,7 +355,8 @@ def run_ours(args):
         t_sample = sorted(a.elapsed_time(b) for a, b in ev_s)[2]
         rays_frame = n_obj * ITERS * R
         sample_bytes = rays_frame * (180 + 4)
-        append_bytes = n_obj * cfg.W * cfg.H * 8 + cfg.W * cfg.H * 11 + (synth.frame_bytes() - cfg.W * cfg.H * 11) * 2
+        # shared keyframe store: the frame is read (11 B/pixel) and written (12 B/pixel) ONCE, + the part-feature map copy
+        append_bytes = cfg.W * cfg.H * (11 + 12) + (synth.frame_bytes() - cfg.W * cfg.H * 11) * 2
         # ---- K3: standalone loss.step_batch_loss forward + backward at the ensemble's per-step shape [N,120,10(,512)]
         gk = torch.Generator(device=dev).manual_seed(4)
         k3_alpha = torch.randn(n_obj, R, S, generator=gk, device=dev)
@@ -454,7 +456,8 @@ def run_ours(args):
                                   "bound": "hbm", "achieved": sample_bytes / (t_sample * 1e-3) / 1e9, "peak": hbm_peak,
                                   "unit": "GB/s", "frac": sample_bytes / (t_sample * 1e-3) / 1e9 / hbm_peak, "ms": t_sample,
                                   "bytes_per_launch": sample_bytes, "rays_per_s": rays_frame / (t_sample * 1e-3)},
-            "roofline_append": {"kernel": "k_append + part-feature copy (per frame)", "bound": "hbm",
+            "roofline_append": {"kernel": "k_store_frame (one copy of the frame in the shared keyframe store) + part-feature copy + "
+                                          "slot-table upload (per frame, device time of Scene.add_frame)", "bound": "hbm",
                                 "achieved": append_bytes / (t_append * 1e-3) / 1e9, "peak": hbm_peak, "unit": "GB/s",
                                 "frac": append_bytes / (t_append * 1e-3) / 1e9 / hbm_peak, "ms": t_append},
             "roofline_hbm": {"kernel": "K4 = k_clipgrad (out_clip gradient assembly) + k_adamw (slab reduction + AdamW)", "bound": "hbm",

@@ -62,6 +62,23 @@ int oo_param_size(int i);
  *      [n_obj][n_pts][129] the encoder is skipped (OccupancyMap.forward on a given embedding). */
 int oo_forward(const float* theta, int n_obj, const float* pcs, const float* emb_in, int n_pts, float scale,
                float* alpha, float* color, float* clip, float* emb_out, void* stream);
+/* alpha == color == clip == NULL with pcs and emb_out set: the encoder alone (vmap(pe_model), train.py:424). */
+
+/* ---- a10 for hand-composed losses: what autograd's backward (train.py:472) does for
+ *      emb = vmap(pe_model)(pe_param, pe_buffer, pcs); alpha, color, clip = vmap(fc_model)(fc_param, fc_buffer, emb)
+ *      (train.py:424-425) given dL/d(alpha, color, clip) from the caller.
+ *      oo_forward_bwd: emb_in [n_obj][n_pts][129]; d_alpha [n_obj][n_pts] (w.r.t. the x10 output), d_color [n_obj][n_pts][3],
+ *      d_clip [n_obj][n_pts][512] or NULL.  grads_out [n_obj][OO_PSTRIDE]: gradients of the 18 OccupancyMap tensors in
+ *      theta layout (fully written; the B_layer block is zero).  d_emb_out [n_obj][n_pts][129] or NULL: gradient w.r.t. the
+ *      embedding (feeds oo_embed_bwd).  ws: oo_forward_bwd_ws_floats(n_obj, n_pts) floats of caller-owned scratch.
+ *      oo_embed_bwd: backward of UniDirsEmbed.forward (embedding.py:46-55) for the trainable direction matrix:
+ *      d_B [n_obj][21][3] from pcs [n_obj][n_pts][3] and d_emb; ws: oo_embed_bwd_ws_floats floats. */
+int64_t oo_forward_bwd_ws_floats(int n_obj, int n_pts);
+int oo_forward_bwd(const float* theta, int n_obj, const float* emb_in, int n_pts, const float* d_alpha, const float* d_color,
+                   const float* d_clip, float* grads_out, float* d_emb_out, float* ws, void* stream);
+int64_t oo_embed_bwd_ws_floats(int n_obj, int n_pts);
+int oo_embed_bwd(const float* theta, int n_obj, const float* pcs, int n_pts, float scale, const float* d_emb, float* d_B,
+                 float* ws, void* stream);
 
 /* ---- f3: Trainer.eval_points (objnerf/trainer.py:104-128): occupancy = sigmoid(alpha)
  *      (render_rays.py:6-14), colour and (optionally) the 512-wide part feature of ONE model at n_pts free points
@@ -143,10 +160,12 @@ int oo_train_schedule(int n_obj, int rays_per_step, int n_sm, oo_train_ws* ws, v
 
 /* per frame: ray counts + zero-mask flags for every step (render_rays.py:88-94 evaluated up front),
  * then the Adam step/bias-correction schedule (torch.optim.AdamW bookkeeping, train.py:473).
- * Sharded runs all-reduce(OR) ws->flags between the two calls. */
+ * Sharded runs: oo_label_counts also writes flag_bits [iters][2] (one int per zero-mask bit), the caller MAX-all-reduces that
+ * array over the ranks (= the OR the cross-object rule needs) and hands it to oo_adam_schedule as reduced_bits, which
+ * rewrites flags[it] from it.  n_obj == 0 (a rank that owns no object yet) writes all-clear flags. */
 int oo_label_counts(const uint8_t* labels, int n_obj, int rays_per_obj, int rays_per_step, int iters,
-                    int* counts, int* flags, void* stream);
-int oo_adam_schedule(const int* flags, int iters, int part_on, float lr, float beta1, float beta2,
+                    int* counts, int* flags, int* flag_bits, void* stream);
+int oo_adam_schedule(int* flags, const int* reduced_bits, int iters, int part_on, float lr, float beta1, float beta2,
                      int* adam_t, float* adam_scal, void* stream);
 
 /* one optimisation step `it` of the whole ensemble: encode + MLP + compositing + loss + backward (K1),
@@ -188,16 +207,27 @@ int oo_bg_param_size(int hidden, int i);
 /* floats of caller-allocated scratch for n_pts points / n_rays rays */
 int64_t oo_bg_ws_floats(int hidden, int n_pts, int n_rays);
 /* pe -> fc_occ_map forward (train.py:449-450): alpha [n_pts] (x10 applied), color [n_pts][3], clip [n_pts][512] or NULL,
- * emb_out [n_pts][129] or NULL */
-int oo_bg_forward(const float* theta, int hidden, const float* pcs, int n_pts, float scale, float* alpha, float* color,
-                  float* clip, float* emb_out, float* ws, void* stream);
+ * emb_out [n_pts][129] or NULL.  Exactly one of pcs [n_pts][3] / emb_in [n_pts][129] is non-NULL: with emb_in the encoder is
+ * skipped (OccupancyMap.forward on a given embedding, the module-level call form). */
+int oo_bg_forward(const float* theta, int hidden, const float* pcs, const float* emb_in, int n_pts, float scale, float* alpha,
+                  float* color, float* clip, float* emb_out, float* ws, void* stream);
+/* backward of oo_bg_forward for upstream gradients d_alpha [n_pts] (w.r.t. the x10 output), d_color [n_pts][3], d_clip
+ * [n_pts][512] or NULL (what autograd does for `fc_occ_map(pe(x))` of the hidden-128 model, train.py:449-450,472):
+ * grads_out = the flat gradient block (parameter layout; with emb_in the B_layer block stays zero and d_emb_out
+ * [n_pts][129], if set, receives the gradient w.r.t. the embedding). */
+int oo_bg_forward_bwd(const float* theta, int hidden, const float* pcs, const float* emb_in, int n_pts, float scale,
+                      const float* d_alpha, const float* d_color, const float* d_clip, float* grads_out, float* d_emb_out,
+                      float* ws, void* stream);
 /* one optimisation step on rays [n_rays] x samples [n_samp] (train.py:447-474 for the background): forward,
- * step_batch_loss on [1,R,S], backward, AdamW (adam_step = 1-based step count).  feat_row/feat_table NULL = part features
- * off (the clip head then has no gradient and is skipped by the optimiser).  grads_out != NULL: write the flat gradient
- * (parameter layout) and do NOT update.  terms_out [4], loss_out [1], flags_out [1] as oo_loss_fwd. */
+ * step_batch_loss on [1,R,S], backward, AdamW.  adam_t: DEVICE int[3], the Adam step counters of the three parameter groups
+ * (trunk + alpha + PE / colour head / clip head), zero-initialised by the caller and advanced by the call: a group whose
+ * tensors autograd does not reach in this step is skipped entirely, exactly like torch.optim.AdamW skips grad-None tensors --
+ * part features off (the clip head; quirk 8) or an empty label mask in this step's step_batch_loss (render_rays.py:89-94
+ * with N = 1: no label-1 ray -> colour and clip heads, neither mask -> everything).  grads_out != NULL: write the flat
+ * gradient (parameter layout) and do NOT update.  terms_out [4], loss_out [1], flags_out [1] as oo_loss_fwd. */
 int oo_bg_train_step(float* theta, float* adam_m, float* adam_v, int hidden, const float* pcs, const float* z,
                      const float* gt_depth, const uint8_t* gt_rgb, const uint8_t* labels, const int32_t* feat_row,
-                     const float* feat_table, int n_rays, int n_samp, float scale, int adam_step, float lr,
+                     const float* feat_table, int n_rays, int n_samp, float scale, int* adam_t, float lr,
                      float weight_decay, float beta1, float beta2, float eps, float color_scaling, float opacity_scaling,
                      float feat_scaling, float* ws, float* terms_out, float* loss_out, int* flags_out, float* grads_out,
                      void* stream);
@@ -243,28 +273,33 @@ typedef struct oo_sample_args {
     uint8_t* gt_rgb; float* gt_depth; uint8_t* valid; uint8_t* labels;
     float* pcs; float* z; int32_t* feat_row; int64_t* pix;   /* pix [n_obj][n_rays][3] = kf, w, h */
     int* oob_count;                      /* [1] rays whose pixel index had to be clamped (quirk 11) */
+    int kf_cap;                          /* keyframe_buffer_size: row length of part_frame / slot_frame / slot_bbox (<= 32) */
+    /* shared keyframe store (oo_store_frame): when store_rgbi != NULL the per-object ring tables above
+     * (rgbs / depth / t_wc / bbox) are not read.  Ring slot s of object o refers to store frame slot_frame[o][s]; the
+     * per-object pixel state (train.py:203-205) is derived from the instance id: 1 where inst == obj_ids[o], 2 where
+     * inst == -1, else 0 -- so obj_ids is required in this mode, also with tapes. */
+    const int32_t* store_rgbi;           /* [F][W][H][2]: word 0 = r | g << 8 | b << 16, word 1 = instance id */
+    const float*   store_depth;          /* [F][W][H] */
+    const float*   store_twc;            /* [F][16] camera-to-world of each stored frame */
+    const int32_t* slot_frame;           /* [n_obj][kf_cap] */
+    const float*   slot_bbox;            /* [n_obj][kf_cap][4] = w_lo,w_hi,h_lo,h_hi (vmap.py:84-89) */
+    /* rng_mode 1: caller-owned scratch of >= n_obj * (2 + 2 * n_frames * n_samples) int32 (per-object batch maximum,
+     * invalid-depth ray lists); the library allocates nothing. */
+    int32_t* scratch; int64_t scratch_ints;
 } oo_sample_args;
 int oo_sample_rays(const oo_sample_args* a, void* stream);
-/* ---- a12: write one new frame into the keyframe rings of every visible object in ONE launch
- *      (sceneObject.__init__ / append_keyframe slot writes, vmap.py:125-147,186-240; pixel state from the instance
- *      map as train.py:203-205: 1 where inst == id, 2 where inst == -1, else 0).  Slot choice (keyframe policy) stays
- *      on the host.  Tables are device arrays of length n_obj. */
-typedef struct oo_append_args {
-    int W, H, n_obj;
+/* ---- f2: the shared keyframe store.  One new frame -> store slot `slot`, ONE launch and 12 bytes per
+ *      pixel whatever the number of objects that see the frame (replaces the per-object ring copies of
+ *      sceneObject.append_keyframe, vmap.py:186-240, and the per-object state maps of train.py:203-205). */
+typedef struct oo_store_args {
+    int W, H, slot;
     const uint8_t* rgb;                  /* [W][H][3] */
     const float*   depth;                /* [W][H] */
-    const int32_t* inst;                 /* [W][H] */
-    const float*   t_wc;                 /* [16] float32 camera-to-world of this frame */
-    const int32_t* obj_id;               /* instance id of each object to append */
-    const int32_t* slot;                 /* ring slot each object writes */
-    const float*   bbox;                 /* [n_obj][4] = w_lo,w_hi,h_lo,h_hi */
-    uint8_t* const* rgbs;                /* -> u8 [KF][W][H][4] */
-    float* const*   depth_ring;          /* -> f32 [KF][W][H] */
-    float* const*   t_wc_ring;           /* -> f32 [KF][4][4] */
-    float* const*   bbox_ring;           /* -> f32 [KF][4] */
-} oo_append_args;
-int oo_append_frame(const oo_append_args* a, void* stream);
-
+    const int32_t* inst;                 /* [W][H] instance map (-1 unknown, 0 background, k > 0 object) */
+    const float*   t_wc;                 /* DEVICE float[16]: camera-to-world of this frame */
+    int32_t* store_rgbi; float* store_depth; float* store_twc;
+} oo_store_args;
+int oo_store_frame(const oo_store_args* a, void* stream);
 /* counter-based uniform / normal tapes keyed by (seed, frame, object id, element) -- shard independent. */
 int oo_rng_fill(uint64_t seed, uint32_t frame, const int32_t* obj_ids, int n_obj, int64_t per_obj,
                 int kind /*0 uniform [0,1), 1 normal(0,std)*/, float std, float* out, void* stream);

@@ -43,13 +43,14 @@ class SampleArgs(Structure):
                 ("obj_ids", c_void_p), ("n_keyframes", c_void_p), ("latest", c_void_p),
                 ("gt_rgb", c_void_p), ("gt_depth", c_void_p), ("valid", c_void_p), ("labels", c_void_p),
                 ("pcs", c_void_p), ("z", c_void_p), ("feat_row", c_void_p), ("pix", c_void_p),
-                ("oob_count", c_void_p)]
+                ("oob_count", c_void_p), ("kf_cap", c_int),
+                ("store_rgbi", c_void_p), ("store_depth", c_void_p), ("store_twc", c_void_p),
+                ("slot_frame", c_void_p), ("slot_bbox", c_void_p), ("scratch", c_void_p), ("scratch_ints", c_int64)]
 
 
-class AppendArgs(Structure):
-    _fields_ = [("W", c_int), ("H", c_int), ("n_obj", c_int), ("rgb", c_void_p), ("depth", c_void_p), ("inst", c_void_p),
-                ("t_wc", c_void_p), ("obj_id", c_void_p), ("slot", c_void_p), ("bbox", c_void_p), ("rgbs", c_void_p),
-                ("depth_ring", c_void_p), ("t_wc_ring", c_void_p), ("bbox_ring", c_void_p)]
+class StoreArgs(Structure):
+    _fields_ = [("W", c_int), ("H", c_int), ("slot", c_int), ("rgb", c_void_p), ("depth", c_void_p), ("inst", c_void_p),
+                ("t_wc", c_void_p), ("store_rgbi", c_void_p), ("store_depth", c_void_p), ("store_twc", c_void_p)]
 
 
 class Grid(Structure):
@@ -78,8 +79,8 @@ _SIGS = {
     "oo_train_ws_sizes": ([c_int, c_int, c_int, c_int, POINTER(c_int), POINTER(c_int), POINTER(c_int64),
                            POINTER(c_int64)], c_int),
     "oo_train_schedule": ([c_int, c_int, c_int, POINTER(TrainWs), c_void_p], c_int),
-    "oo_label_counts": ([c_void_p, c_int, c_int, c_int, c_int, c_void_p, c_void_p, c_void_p], c_int),
-    "oo_adam_schedule": ([c_void_p, c_int, c_int, c_float, c_float, c_float, c_void_p, c_void_p, c_void_p], c_int),
+    "oo_label_counts": ([c_void_p, c_int, c_int, c_int, c_int, c_void_p, c_void_p, c_void_p, c_void_p], c_int),
+    "oo_adam_schedule": ([c_void_p, c_void_p, c_int, c_int, c_float, c_float, c_float, c_void_p, c_void_p, c_void_p], c_int),
     "oo_train_step": ([c_void_p, c_void_p, c_void_p, c_int, POINTER(Batch), c_int, c_int, c_float, c_float, c_float,
                        c_float, c_float, c_float, POINTER(TrainWs), c_void_p, c_int, c_void_p], c_int),
     "oo_train_grads": ([c_void_p, c_int, POINTER(Batch), c_int, c_int, c_float, POINTER(TrainWs), c_void_p, c_void_p,
@@ -92,7 +93,7 @@ _SIGS = {
     "oo_adamw_flat": ([c_void_p, c_void_p, c_void_p, c_void_p, c_int64, c_int, c_float, c_float, c_float, c_float,
                        c_float, c_void_p], c_int),
     "oo_sample_rays": ([POINTER(SampleArgs), c_void_p], c_int),
-    "oo_append_frame": ([POINTER(AppendArgs), c_void_p], c_int),
+    "oo_store_frame": ([POINTER(StoreArgs), c_void_p], c_int),
     "oo_rng_fill": ([c_uint64, c_uint32, c_void_p, c_int, c_int64, c_int, c_float, c_void_p, c_void_p], c_int),
     "oo_rng_fill_rows": ([c_uint64, c_uint32, c_void_p, c_int, c_int, c_int, c_int, c_float, c_void_p, c_void_p], c_int),
     "oo_render_object": ([POINTER(RenderArgs), c_void_p], c_int),
@@ -115,10 +116,17 @@ _SIGS = {
     "oo_bg_param_offset": ([c_int, c_int], c_int),
     "oo_bg_param_size": ([c_int, c_int], c_int),
     "oo_bg_ws_floats": ([c_int, c_int, c_int], c_int64),
-    "oo_bg_forward": ([c_void_p, c_int, c_void_p, c_int, c_float, c_void_p, c_void_p, c_void_p, c_void_p, c_void_p,
+    "oo_bg_forward": ([c_void_p, c_int, c_void_p, c_void_p, c_int, c_float, c_void_p, c_void_p, c_void_p, c_void_p, c_void_p,
                        c_void_p], c_int),
+    "oo_bg_forward_bwd": ([c_void_p, c_int, c_void_p, c_void_p, c_int, c_float, c_void_p, c_void_p, c_void_p, c_void_p,
+                           c_void_p, c_void_p, c_void_p], c_int),
+    "oo_forward_bwd_ws_floats": ([c_int, c_int], c_int64),
+    "oo_forward_bwd": ([c_void_p, c_int, c_void_p, c_int, c_void_p, c_void_p, c_void_p, c_void_p, c_void_p, c_void_p,
+                        c_void_p], c_int),
+    "oo_embed_bwd_ws_floats": ([c_int, c_int], c_int64),
+    "oo_embed_bwd": ([c_void_p, c_int, c_void_p, c_int, c_float, c_void_p, c_void_p, c_void_p, c_void_p], c_int),
     "oo_bg_train_step": ([c_void_p, c_void_p, c_void_p, c_int, c_void_p, c_void_p, c_void_p, c_void_p, c_void_p, c_void_p,
-                          c_void_p, c_int, c_int, c_float, c_int, c_float, c_float, c_float, c_float, c_float, c_float,
+                          c_void_p, c_int, c_int, c_float, c_void_p, c_float, c_float, c_float, c_float, c_float, c_float,
                           c_float, c_float, c_void_p, c_void_p, c_void_p, c_void_p, c_void_p, c_void_p], c_int),
 }
 

@@ -34,7 +34,7 @@ class BackgroundModel:
         self.theta = torch.zeros(n, **f32)
         self.m = torch.zeros(n, **f32)
         self.v = torch.zeros(n, **f32)
-        self.adam_t = 0
+        self.adam_t = torch.zeros(3, dtype=torch.int32, device=self.device)   # per-group Adam step counters (device)
         self._ws = None
         self._ws_key = None
         self.terms = torch.zeros(4, **f32)
@@ -52,8 +52,10 @@ class BackgroundModel:
         return out
 
     def load(self, tensors):
-        for v, t in zip(self.views(), tensors):
-            v.copy_(t.reshape(v.shape).to(self.device))
+        with torch.no_grad():
+            for v, t in zip(self.views(), tensors):
+                if t is not None:
+                    v.copy_(t.detach().reshape(v.shape).to(self.device))
 
     def adopt(self, fc_occ_map, pe):
         """Copy a reference-surface model in and make its nn.Parameters alias the block (write-back is then free)."""
@@ -64,7 +66,7 @@ class BackgroundModel:
                 p.data = v
 
     def reset_optimizer(self):
-        self.m.zero_(); self.v.zero_(); self.adam_t = 0
+        self.m.zero_(); self.v.zero_(); self.adam_t.zero_()
 
     def _scratch(self, n_pts, n_rays):
         key = (n_pts, n_rays)
@@ -75,20 +77,40 @@ class BackgroundModel:
         return self._ws
 
     # ---- forward (train.py:449-450; also the eval / meshing query path) ------------------------
-    def forward(self, pcs, want_clip=True, want_emb=False):
-        lead = list(pcs.shape[:-1])
-        x = pcs.reshape(-1, 3).contiguous().float()
+    def forward(self, pcs=None, want_clip=True, want_emb=False, emb=None):
+        """pcs [...,3] -> encoder + MLP, or emb [...,129] -> the MLP alone (OccupancyMap.forward on a given embedding)."""
+        src = pcs if emb is None else emb
+        lead = list(src.shape[:-1])
+        x = src.reshape(-1, src.shape[-1]).contiguous().float()
         n = x.shape[0]
         f32 = dict(dtype=torch.float32, device=self.device)
         alpha, color = torch.empty(n, **f32), torch.empty(n, 3, **f32)
         clip = torch.empty(n, 512, **f32) if want_clip else None
-        emb = torch.empty(n, 129, **f32) if want_emb else None
+        emb_o = torch.empty(n, 129, **f32) if want_emb else None
         ws = self._scratch(n, 1)
         with torch.cuda.device(self.device):
-            check(self.L.oo_bg_forward(ptr(self.theta), self.hidden, ptr(x), n, float(self.scale), ptr(alpha), ptr(color),
-                                       ptr(clip), ptr(emb), ptr(ws), stream()), "oo_bg_forward")
+            check(self.L.oo_bg_forward(ptr(self.theta), self.hidden, ptr(x) if emb is None else None,
+                                       ptr(x) if emb is not None else None, n, float(self.scale), ptr(alpha), ptr(color),
+                                       ptr(clip), ptr(emb_o), ptr(ws), stream()), "oo_bg_forward")
         return (alpha.view(lead + [1]), color.view(lead + [3]), None if clip is None else clip.view(lead + [512]),
-                None if emb is None else emb.view(lead + [129]))
+                None if emb_o is None else emb_o.view(lead + [129]))
+
+    def forward_bwd(self, pcs, d_alpha, d_color, d_clip=None, emb=None, want_d_emb=False):
+        """Flat gradient block of all 19 tensors for upstream gradients of forward()'s outputs (what autograd does for
+        `fc_occ_map(pe(x))`, train.py:449-450,472).  With `emb` (the MLP on a given embedding) also returns d_emb if asked."""
+        src = pcs if emb is None else emb
+        x = src.reshape(-1, src.shape[-1]).contiguous().float()
+        n = x.shape[0]
+        g = torch.empty_like(self.theta)
+        ws = self._scratch(n, 1)
+        da, dc = d_alpha.reshape(n).contiguous().float(), d_color.reshape(n, 3).contiguous().float()
+        dcl = None if d_clip is None else d_clip.reshape(n, 512).contiguous().float()
+        d_emb = torch.empty(n, 129, dtype=torch.float32, device=self.device) if (want_d_emb and emb is not None) else None
+        with torch.cuda.device(self.device):
+            check(self.L.oo_bg_forward_bwd(ptr(self.theta), self.hidden, ptr(x) if emb is None else None,
+                                           ptr(x) if emb is not None else None, n, float(self.scale), ptr(da), ptr(dc), ptr(dcl),
+                                           ptr(g), ptr(d_emb), ptr(ws), stream()), "oo_bg_forward_bwd")
+        return (g, d_emb) if emb is not None else g
 
     # ---- training (train.py:447-474) ------------------------------------------------------------
     def _step(self, pcs, z, gt_depth, gt_rgb8, labels, feat_row, feat_table, grads_out):
@@ -98,7 +120,7 @@ class BackgroundModel:
         with torch.cuda.device(self.device):
             check(self.L.oo_bg_train_step(ptr(self.theta), ptr(self.m), ptr(self.v), self.hidden, ptr(pcs), ptr(z),
                                           ptr(gt_depth), ptr(gt_rgb8), ptr(labels), ptr(feat_row), ptr(feat_table), r, s,
-                                          float(self.scale), int(self.adam_t + 1), self.lr, self.wd, b1, b2, self.eps,
+                                          float(self.scale), ptr(self.adam_t), self.lr, self.wd, b1, b2, self.eps,
                                           self.cs, self.os, self.fs, ptr(ws), ptr(self.terms), ptr(self.loss),
                                           ptr(self.flags), ptr(grads_out), stream()), "oo_bg_train_step")
 
@@ -112,7 +134,6 @@ class BackgroundModel:
     def train_step(self, pcs, z, gt_depth, gt_rgb8, labels, feat_row=None, feat_table=None):
         """pcs [R,S,3], z [R,S], gt_depth [R], gt_rgb8 [R,3] u8, labels [R] u8, feat_row [R] int32 rows of feat_table."""
         self._step(pcs, z, gt_depth, gt_rgb8, labels, feat_row, feat_table, None)
-        self.adam_t += 1
 
     def train_frame(self, batch, iters=100, loss_out=None):
         """`iters` steps over a pre-sampled frame batch (ensemble.FrameBatch with N = 1): step `it` uses rays

@@ -327,12 +327,14 @@ __device__ __forceinline__ void gemm_reduce_body(const GemmOp& g) {
 // split > 1 asks for a split contraction (the weight gradients: K = all points); how many chunks is chosen here so that the
 // grid is ONE wave of two CTAs per SM: a CTA's time is its number of k-tiles, whatever share of its tile is real output
 int run_gemm(GemmOp g, int split, float* part, cudaStream_t st, ReduceBatch* defer = nullptr) {
-    static int n_sm = 0;
-    if (n_sm == 0) {
-        int dev = 0;
+    static PerDevice n_sm_d;
+    if (n_sm_d.cur() == 0) {
+        int dev = 0, n = 0;
         OO_CUDA(cudaGetDevice(&dev));
-        OO_CUDA(cudaDeviceGetAttribute(&n_sm, cudaDevAttrMultiProcessorCount, dev));
+        OO_CUDA(cudaDeviceGetAttribute(&n, cudaDevAttrMultiProcessorCount, dev));
+        n_sm_d.cur() = (size_t)n;
     }
+    const int n_sm = (int)n_sm_d.cur();
     OO_REQUIRE(n_sm <= 160, "oo_bg gemm: the split-partial regions are sized for at most 160 SMs");
     const int tiles = ((g.I + BI - 1) / BI) * ((g.J + BJ - 1) / BJ);
     g.split = 1;
@@ -355,13 +357,13 @@ int run_gemm(GemmOp g, int split, float* part, cudaStream_t st, ReduceBatch* def
                "oo_bg gemm: output / mask larger than 2^31 elements");
     const dim3 grid((g.I + BI - 1) / BI, (g.J + BJ - 1) / BJ, g.split);
     const bool ac = g.sac == 1, bc = g.sbc == 1;
-    static bool attr_set = false;
-    if (!attr_set) {
+    static PerDevice attr_set;
+    if (!attr_set.cur()) {
         OO_CUDA(cudaFuncSetAttribute(k_gemm<true, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, GEMM_SMEM));
         OO_CUDA(cudaFuncSetAttribute(k_gemm<true, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, GEMM_SMEM));
         OO_CUDA(cudaFuncSetAttribute(k_gemm<false, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, GEMM_SMEM));
         OO_CUDA(cudaFuncSetAttribute(k_gemm<false, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, GEMM_SMEM));
-        attr_set = true;
+        attr_set.cur() = 1;
     }
     if (ac && bc) OO_CUDA(launch_pdl(k_gemm<true, true>, grid, dim3(256), (size_t)GEMM_SMEM, st, g));
     else if (ac) OO_CUDA(launch_pdl(k_gemm<true, false>, grid, dim3(256), (size_t)GEMM_SMEM, st, g));
@@ -447,6 +449,22 @@ __global__ void k_embed_fwd(const float* __restrict__ pcs, const float* __restri
     }
 }
 
+// OccupancyMap.forward on a caller-supplied embedding [M][129] (the module-level call form fc_occ_map(pe(x)), train.py:449-450):
+// the embedding goes to the three places that consume it; its gradient is gathered back from them
+__global__ void k_embed_scatter(const float* __restrict__ emb, int n_pts, const EmbedBufs b) {
+    const size_t e = (size_t)blockIdx.x * blockDim.x + threadIdx.x;
+    if (e >= (size_t)n_pts * EMB) return;
+    const size_t p = e / EMB;
+    emb_store(b, p, (int)(e - p * EMB), emb[e]);
+}
+__global__ void k_embed_gather_grad(const EmbedBufs g, int n_pts, float* __restrict__ d_emb) {
+    const size_t e = (size_t)blockIdx.x * blockDim.x + threadIdx.x;
+    if (e >= (size_t)n_pts * EMB) return;
+    const size_t p = e / EMB;
+    const int idx = (int)(e - p * EMB);
+    d_emb[e] = idx < E1 ? g.x1[p * g.ld1 + idx] + g.xc[p * g.ldc + g.h + idx] : g.xh[p * g.ldh + g.h + idx - E1];
+}
+
 // d B[d][ch] = sum_p t[p][ch] * sum_k de[3+21k+d][p] * pi 2^k cos(pi 2^k proj): per-block partials [nblk][63], then a
 // fixed-order reduction
 constexpr int EB_PTS = 32;        // points per block
@@ -525,7 +543,7 @@ struct BgWs {
     float *x1, *xc, *h1, *h3, *xh, *hc, *hp, *alpha, *color, *clip;
     // gradients
     float *d_alpha, *d_color, *d_colpre, *d_clip, *d_hc, *d_hp, *d_xh, *d_h3, *d_xc, *d_h1, *d_x1;
-    float *gt_rgb, *gt_feat, *loss_ws, *ones, *part[9], *emb_part, *grads;   // part[i]: split partials of weight gradient i
+    float *gt_rgb, *gt_feat, *loss_ws, *ones, *adam_scal, *part[9], *emb_part, *grads;   // part[i]: split partials of weight gradient i
     int ld1, ldc, ldh;
     long long total;
 };
@@ -546,6 +564,7 @@ BgWs bg_ws_map(float* base, int h, int n_pts, int n_rays) {
     w.gt_rgb = take(3LL * n_rays); w.gt_feat = take((long long)C * n_rays);
     w.loss_ws = take((long long)n_rays * oo_loss_ws_per_ray() + 8);
     w.ones = take(4);
+    w.adam_scal = take(12);
     {   // one region per weight-gradient GEMM, in the order oo_bg_train_step runs them (they are reduced together at the end)
         const int wi[9] = {C, h, 3, h, 1, h, h, h, h}, wj[9] = {h, h + E2, h, h + E2, h, h, h + E1, h, E1};
         for (int i = 0; i < 9; ++i) w.part[i] = take(part_floats(wi[i], wj[i]));
@@ -572,9 +591,10 @@ GemmOp op(const float* A, long long sai, long long sac, const float* B, long lon
 // forward of the whole model into the workspace (model.py:61-103); returns with ws.alpha (x10 applied), ws.color
 // (after sigmoid) and, if want_clip, ws.clip filled
 int bg_forward(const float* th, const BgLayout& L, int h, const float* pcs, int M, float scale, const BgWs& w, bool want_clip,
-               float* emb_out, cudaStream_t st) {
+               float* emb_out, cudaStream_t st, const float* emb_in = nullptr) {
     const EmbedBufs eb = {w.x1, w.xc, w.xh, w.ld1, w.ldc, w.ldh, h};
-    k_embed_fwd<<<(unsigned)(((size_t)M * 24 + 255) / 256), 256, 0, st>>>(pcs, th + L.off[T_PE], scale, M, eb, emb_out);
+    if (emb_in != nullptr) k_embed_scatter<<<(unsigned)(((size_t)M * EMB + 255) / 256), 256, 0, st>>>(emb_in, M, eb);
+    else k_embed_fwd<<<(unsigned)(((size_t)M * 24 + 255) / 256), 256, 0, st>>>(pcs, th + L.off[T_PE], scale, M, eb, emb_out);
     OO_LAUNCH_CHECK();
     GemmOp g;
     // fc1 = relu(in_layer(e1))
@@ -607,59 +627,11 @@ int bg_forward(const float* th, const BgLayout& L, int h, const float* pcs, int 
     return 0;
 }
 
-}  // namespace
 
-extern "C" int oo_bg_param_count(int hidden) { return hidden > 0 ? bg_layout(hidden).total : -1; }
-extern "C" int oo_bg_param_offset(int hidden, int i) { return (hidden > 0 && i >= 0 && i < NT) ? bg_layout(hidden).off[i] : -1; }
-extern "C" int oo_bg_param_size(int hidden, int i) { return (hidden > 0 && i >= 0 && i < NT) ? bg_layout(hidden).size[i] : -1; }
-extern "C" int64_t oo_bg_ws_floats(int hidden, int n_pts, int n_rays) {
-    if (hidden <= 0 || n_pts <= 0 || n_rays <= 0) return -1;
-    return bg_ws_map(nullptr, hidden, n_pts, n_rays).total;
-}
-
-extern "C" int oo_bg_forward(const float* theta, int hidden, const float* pcs, int n_pts, float scale, float* alpha,
-                             float* color, float* clip, float* emb_out, float* ws, void* stream) {
-    OO_REQUIRE(theta && pcs && ws && alpha && color, "oo_bg_forward: null argument");
-    OO_REQUIRE(hidden > 0 && hidden % 4 == 0 && n_pts > 0, "oo_bg_forward: hidden must be a positive multiple of 4");
-    cudaStream_t st = (cudaStream_t)stream;
-    const BgLayout L = bg_layout(hidden);
-    const BgWs w = bg_ws_map(ws, hidden, n_pts, 1);
-    OO_TRY(bg_forward(theta, L, hidden, pcs, n_pts, scale, w, clip != nullptr, emb_out, st));
-    OO_CUDA(cudaMemcpyAsync(alpha, w.alpha, sizeof(float) * n_pts, cudaMemcpyDeviceToDevice, st));
-    OO_CUDA(cudaMemcpyAsync(color, w.color, sizeof(float) * 3 * n_pts, cudaMemcpyDeviceToDevice, st));
-    if (clip) OO_CUDA(cudaMemcpyAsync(clip, w.clip, sizeof(float) * C * (size_t)n_pts, cudaMemcpyDeviceToDevice, st));
-    return 0;
-}
-
-extern "C" int oo_bg_train_step(float* theta, float* adam_m, float* adam_v, int hidden, const float* pcs, const float* z,
-                                const float* gt_depth, const uint8_t* gt_rgb, const uint8_t* labels, const int32_t* feat_row,
-                                const float* feat_table, int n_rays, int n_samp, float scale, int adam_step, float lr,
-                                float weight_decay, float beta1, float beta2, float eps, float color_scaling,
-                                float opacity_scaling, float feat_scaling, float* ws, float* terms_out, float* loss_out,
-                                int* flags_out, float* grads_out, void* stream) {
-    OO_REQUIRE(theta && pcs && z && gt_depth && gt_rgb && labels && ws && terms_out && loss_out && flags_out,
-               "oo_bg_train_step: null argument");
-    OO_REQUIRE(hidden > 0 && hidden % 4 == 0 && n_rays > 0 && n_samp > 0 && n_samp <= 32, "oo_bg_train_step: bad shape");
-    OO_REQUIRE(grads_out || (adam_m && adam_v && adam_step >= 1), "oo_bg_train_step: optimiser state missing");
-    OO_REQUIRE((feat_row == nullptr) == (feat_table == nullptr), "oo_bg_train_step: feat_row and feat_table go together");
-    cudaStream_t st = (cudaStream_t)stream;
-    const int h = hidden, M = n_rays * n_samp;
-    const bool part = feat_row != nullptr;
-    const BgLayout L = bg_layout(h);
-    const BgWs w = bg_ws_map(ws, h, M, n_rays);
-    float* G = grads_out ? grads_out : w.grads;
-    k_fill<<<1, 32, 0, st>>>(w.ones, 1.f, 4);
-    OO_LAUNCH_CHECK();
-    k_gt_prepare<<<n_rays, 128, 0, st>>>(gt_rgb, feat_row, feat_table, n_rays, w.gt_rgb, w.gt_feat);
-    OO_LAUNCH_CHECK();
-    OO_TRY(bg_forward(theta, L, h, pcs, M, scale, w, part, nullptr, st));
-    // ---- loss.step_batch_loss on [1, R, S] (train.py:452-462) and its gradient w.r.t. alpha / colour / clip (K3)
-    OO_TRY(oo_loss_fwd(w.alpha, w.color, z, gt_depth, w.gt_rgb, labels, part ? w.clip : nullptr, part ? w.gt_feat : nullptr, 1,
-                       n_rays, n_samp, part ? C : 0, color_scaling, opacity_scaling, feat_scaling, terms_out, loss_out,
-                       flags_out, w.loss_ws, stream));
-    OO_TRY(oo_loss_bwd(w.alpha, w.color, z, gt_depth, w.gt_rgb, labels, part ? w.clip : nullptr, part ? w.gt_feat : nullptr, 1,
-                       n_rays, n_samp, part ? C : 0, color_scaling, opacity_scaling, feat_scaling, 1.f, flags_out, w.loss_ws,
-                       w.d_alpha, w.d_color, part ? w.d_clip : nullptr, stream));
+// backward of the whole model given dL/d(alpha, colour, clip) in w.d_alpha / w.d_color / w.d_clip and the forward activations
+// of bg_forward in `w`: all 19 gradients into G (flat parameter layout)
+int bg_backward(const float* theta, const BgLayout& L, int h, const float* pcs, int M, float scale, const BgWs& w, bool part,
+                float* G, cudaStream_t st, float* d_emb_out = nullptr) {
     const float* th = theta;
     GemmOp g;
     ReduceBatch pending;                         // split partials of the weight gradients, reduced together before AdamW
@@ -734,8 +706,15 @@ extern "C" int oo_bg_train_step(float* theta, float* adam_m, float* adam_v, int 
     OO_TRY(run_gemm(g, BG_SPLIT, w.part[8], st, &pending));
     g = op(w.d_h1, h, 1, th + L.off[T_IN_W], 1, E1, w.d_x1, w.ld1, 1, M, E1, h);
     OO_TRY(run_gemm(g, 1, nullptr, st));
-    // ---- encoder: B_layer.weight is trainable (embedding.py:43)
-    {
+    // ---- encoder: B_layer.weight is trainable (embedding.py:43); on a caller-supplied embedding its gradient
+    // goes back to the caller instead
+    if (pcs == nullptr) {
+        const EmbedBufs gb = {w.d_x1, w.d_xc, w.d_xh, w.ld1, w.ldc, w.ldh, h};
+        if (d_emb_out != nullptr) {
+            k_embed_gather_grad<<<(unsigned)(((size_t)M * EMB + 255) / 256), 256, 0, st>>>(gb, M, d_emb_out);
+            OO_LAUNCH_CHECK();
+        }
+    } else {
         const EmbedBufs gb = {w.d_x1, w.d_xc, w.d_xh, w.ld1, w.ldc, w.ldh, h};
         const int nblk = (M + EB_PTS - 1) / EB_PTS;
         k_embed_bwd<<<nblk, NDIR * 4, 0, st>>>(pcs, th + L.off[T_PE], scale, M, gb, w.emb_part);
@@ -744,16 +723,127 @@ extern "C" int oo_bg_train_step(float* theta, float* adam_m, float* adam_v, int 
         OO_LAUNCH_CHECK();
     }
     OO_TRY(run_reduce_batch(pending, st));
-    if (grads_out) return 0;
-    // ---- torch.optim.AdamW over the flat block; with part features off the clip head has grad None and is skipped
-    // entirely (no decay either; quirk 8) -- its four tensors are contiguous in the layout
-    if (part) {
-        OO_TRY(oo_adamw_flat(theta, G, adam_m, adam_v, L.total, adam_step, lr, weight_decay, beta1, beta2, eps, stream));
+    return 0;
+}
+
+// ---- torch.optim.AdamW bookkeeping of the background model on the device (train.py:473): which parameter groups
+// autograd reaches in this step follows from the zero-mask flags of its own step_batch_loss call (render_rays.py:89-94 with
+// N = 1: a term whose mask is empty is a constant zero, so the tensors only it reaches have grad None and are skipped --
+// no decay, no step count).  Groups: 0 trunk + alpha + PE, 1 colour head, 2 clip head (as the ensemble, oo_layout.h).
+__global__ void k_bg_adam_sched(const int* __restrict__ flags, int part_on, double lr, double b1, double b2, int* __restrict__ adam_t,
+                                float* __restrict__ scal) {
+    const int g = threadIdx.x;
+    if (g >= 3) return;
+    const int f = flags[0];
+    const bool obj_terms = !(f & OO_FLAG_NO_OBJ), op_term = !(f & OO_FLAG_NO_SEM);
+    const bool active = g == 0 ? (obj_terms || op_term) : g == 1 ? obj_terms : (obj_terms && part_on != 0);
+    float* s = scal + 4 * g;
+    if (active) {
+        const int t = adam_t[g] + 1;
+        adam_t[g] = t;
+        const double bc1 = 1.0 - pow(b1, (double)t), bc2 = 1.0 - pow(b2, (double)t);
+        s[0] = 1.f; s[1] = (float)(lr / bc1); s[2] = (float)sqrt(bc2); s[3] = (float)t;
     } else {
-        const int a = L.off[T_CP_W], b = L.off[T_PE];
-        OO_TRY(oo_adamw_flat(theta, G, adam_m, adam_v, a, adam_step, lr, weight_decay, beta1, beta2, eps, stream));
-        OO_TRY(oo_adamw_flat(theta + b, G + b, adam_m + b, adam_v + b, L.total - b, adam_step, lr, weight_decay, beta1, beta2,
-                             eps, stream));
+        s[0] = s[1] = s[2] = s[3] = 0.f;
     }
+}
+
+__global__ void k_bg_adamw(float* __restrict__ p, const float* __restrict__ g, float* __restrict__ m, float* __restrict__ v, int n,
+                           int off_color, int off_clip, int off_pe, const float* __restrict__ scal, float decay, float b1, float b2,
+                           float eps) {
+    for (int i = blockIdx.x * blockDim.x + threadIdx.x; i < n; i += gridDim.x * blockDim.x) {
+        const int grp = i < off_color ? 0 : i < off_clip ? 1 : i < off_pe ? 2 : 0;
+        if (scal[4 * grp] == 0.f) continue;
+        const float step = scal[4 * grp + 1], bc2s = scal[4 * grp + 2];
+        float P = p[i] * decay;
+        const float G = g[i];
+        const float Mn = m[i] + (G - m[i]) * (1.f - b1);
+        const float Vn = v[i] * b2 + ((1.f - b2) * G) * G;
+        P = P - step * (Mn / (sqrtf(Vn) / bc2s + eps));
+        p[i] = P; m[i] = Mn; v[i] = Vn;
+    }
+}
+}  // namespace
+
+extern "C" int oo_bg_param_count(int hidden) { return hidden > 0 ? bg_layout(hidden).total : -1; }
+extern "C" int oo_bg_param_offset(int hidden, int i) { return (hidden > 0 && i >= 0 && i < NT) ? bg_layout(hidden).off[i] : -1; }
+extern "C" int oo_bg_param_size(int hidden, int i) { return (hidden > 0 && i >= 0 && i < NT) ? bg_layout(hidden).size[i] : -1; }
+extern "C" int64_t oo_bg_ws_floats(int hidden, int n_pts, int n_rays) {
+    if (hidden <= 0 || n_pts <= 0 || n_rays <= 0) return -1;
+    return bg_ws_map(nullptr, hidden, n_pts, n_rays).total;
+}
+
+extern "C" int oo_bg_forward(const float* theta, int hidden, const float* pcs, const float* emb_in, int n_pts, float scale,
+                             float* alpha, float* color, float* clip, float* emb_out, float* ws, void* stream) {
+    OO_REQUIRE(theta && ws && alpha && color, "oo_bg_forward: null argument");
+    OO_REQUIRE((pcs != nullptr) != (emb_in != nullptr), "oo_bg_forward: give exactly one of pcs / emb_in");
+    OO_REQUIRE(hidden > 0 && hidden % 4 == 0 && n_pts > 0, "oo_bg_forward: hidden must be a positive multiple of 4");
+    cudaStream_t st = (cudaStream_t)stream;
+    const BgLayout L = bg_layout(hidden);
+    const BgWs w = bg_ws_map(ws, hidden, n_pts, 1);
+    OO_TRY(bg_forward(theta, L, hidden, pcs, n_pts, scale, w, clip != nullptr, emb_out, st, emb_in));
+    OO_CUDA(cudaMemcpyAsync(alpha, w.alpha, sizeof(float) * n_pts, cudaMemcpyDeviceToDevice, st));
+    OO_CUDA(cudaMemcpyAsync(color, w.color, sizeof(float) * 3 * n_pts, cudaMemcpyDeviceToDevice, st));
+    if (clip) OO_CUDA(cudaMemcpyAsync(clip, w.clip, sizeof(float) * C * (size_t)n_pts, cudaMemcpyDeviceToDevice, st));
+    return 0;
+}
+
+extern "C" int oo_bg_forward_bwd(const float* theta, int hidden, const float* pcs, const float* emb_in, int n_pts, float scale,
+                                 const float* d_alpha, const float* d_color, const float* d_clip, float* grads_out,
+                                 float* d_emb_out, float* ws, void* stream) {
+    OO_REQUIRE(theta && d_alpha && d_color && grads_out && ws, "oo_bg_forward_bwd: null argument");
+    OO_REQUIRE((pcs != nullptr) != (emb_in != nullptr), "oo_bg_forward_bwd: give exactly one of pcs / emb_in");
+    OO_REQUIRE(hidden > 0 && hidden % 4 == 0 && n_pts > 0, "oo_bg_forward_bwd: hidden must be a positive multiple of 4");
+    cudaStream_t st = (cudaStream_t)stream;
+    const BgLayout L = bg_layout(hidden);
+    BgWs w = bg_ws_map(ws, hidden, n_pts, 1);
+    k_fill<<<1, 32, 0, st>>>(w.ones, 1.f, 4);
+    OO_LAUNCH_CHECK();
+    OO_TRY(bg_forward(theta, L, hidden, pcs, n_pts, scale, w, false, nullptr, st, emb_in));
+    // the caller's upstream gradients take the place of the loss kernel's outputs (read-only in bg_backward)
+    w.d_alpha = const_cast<float*>(d_alpha);
+    w.d_color = const_cast<float*>(d_color);
+    w.d_clip = const_cast<float*>(d_clip);
+    return bg_backward(theta, L, hidden, pcs, n_pts, scale, w, d_clip != nullptr, grads_out, st, d_emb_out);
+}
+
+extern "C" int oo_bg_train_step(float* theta, float* adam_m, float* adam_v, int hidden, const float* pcs, const float* z,
+                                const float* gt_depth, const uint8_t* gt_rgb, const uint8_t* labels, const int32_t* feat_row,
+                                const float* feat_table, int n_rays, int n_samp, float scale, int* adam_t, float lr,
+                                float weight_decay, float beta1, float beta2, float eps, float color_scaling,
+                                float opacity_scaling, float feat_scaling, float* ws, float* terms_out, float* loss_out,
+                                int* flags_out, float* grads_out, void* stream) {
+    OO_REQUIRE(theta && pcs && z && gt_depth && gt_rgb && labels && ws && terms_out && loss_out && flags_out,
+               "oo_bg_train_step: null argument");
+    OO_REQUIRE(hidden > 0 && hidden % 4 == 0 && n_rays > 0 && n_samp > 0 && n_samp <= 32, "oo_bg_train_step: bad shape");
+    OO_REQUIRE(grads_out || (adam_m && adam_v && adam_t), "oo_bg_train_step: optimiser state missing");
+    OO_REQUIRE((feat_row == nullptr) == (feat_table == nullptr), "oo_bg_train_step: feat_row and feat_table go together");
+    cudaStream_t st = (cudaStream_t)stream;
+    const int h = hidden, M = n_rays * n_samp;
+    const bool part = feat_row != nullptr;
+    const BgLayout L = bg_layout(h);
+    const BgWs w = bg_ws_map(ws, h, M, n_rays);
+    float* G = grads_out ? grads_out : w.grads;
+    k_fill<<<1, 32, 0, st>>>(w.ones, 1.f, 4);
+    OO_LAUNCH_CHECK();
+    k_gt_prepare<<<n_rays, 128, 0, st>>>(gt_rgb, feat_row, feat_table, n_rays, w.gt_rgb, w.gt_feat);
+    OO_LAUNCH_CHECK();
+    OO_TRY(bg_forward(theta, L, h, pcs, M, scale, w, part, nullptr, st));
+    // ---- loss.step_batch_loss on [1, R, S] (train.py:452-462) and its gradient w.r.t. alpha / colour / clip (K3)
+    OO_TRY(oo_loss_fwd(w.alpha, w.color, z, gt_depth, w.gt_rgb, labels, part ? w.clip : nullptr, part ? w.gt_feat : nullptr, 1,
+                       n_rays, n_samp, part ? C : 0, color_scaling, opacity_scaling, feat_scaling, terms_out, loss_out,
+                       flags_out, w.loss_ws, stream));
+    OO_TRY(oo_loss_bwd(w.alpha, w.color, z, gt_depth, w.gt_rgb, labels, part ? w.clip : nullptr, part ? w.gt_feat : nullptr, 1,
+                       n_rays, n_samp, part ? C : 0, color_scaling, opacity_scaling, feat_scaling, 1.f, flags_out, w.loss_ws,
+                       w.d_alpha, w.d_color, part ? w.d_clip : nullptr, stream));
+    OO_TRY(bg_backward(theta, L, h, pcs, M, scale, w, part, G, st));
+    if (grads_out) return 0;
+    // ---- torch.optim.AdamW over the flat block, per parameter group: a group autograd does not reach in this step (part
+    // features off: the clip head, quirk 8; an empty label mask: see k_bg_adam_sched) is skipped entirely
+    k_bg_adam_sched<<<1, 32, 0, st>>>(flags_out, part ? 1 : 0, (double)lr, (double)beta1, (double)beta2, adam_t, w.adam_scal);
+    OO_LAUNCH_CHECK();
+    k_bg_adamw<<<148 * 4, 256, 0, st>>>(theta, G, adam_m, adam_v, L.total, L.off[T_CL_W], L.off[T_CP_W], L.off[T_PE], w.adam_scal,
+                                        (float)(1.0 - (double)lr * (double)weight_decay), beta1, beta2, eps);
+    OO_LAUNCH_CHECK();
     return 0;
 }

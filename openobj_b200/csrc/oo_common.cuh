@@ -8,6 +8,17 @@
 namespace oo {
 std::string& last_error();
 int fail(int code, const char* fmt, ...);
+
+// Function attributes (cudaFuncSetAttribute) and SM counts belong to a device, not to the process: one value per device
+// ordinal, addressed by the calling thread's current device.
+struct PerDevice {
+    size_t v[64] = {};
+    size_t& cur() {
+        int d = 0;
+        cudaGetDevice(&d);
+        return v[d & 63];
+    }
+};
 }  // namespace oo
 
 #define OO_CUDA(expr)                                                                          \

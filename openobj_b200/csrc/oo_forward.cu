@@ -69,16 +69,18 @@ __global__ void __launch_bounds__(NTHREADS, 1) k_forward(const float* __restrict
             FwdPhases<2, N_FWD_PHASES>::run(tid, sm, c, acc);
         } else {
             c.pcs = pcs + base * 3;
-            FwdPhases<0, N_FWD_PHASES>::run(tid, sm, c, acc);
+            if (color == nullptr) FwdPhases<0, 2>::run(tid, sm, c, acc);      // encoder only (vmap(pe_model) on its own)
+            else FwdPhases<0, N_FWD_PHASES>::run(tid, sm, c, acc);
         }
         if (alpha != nullptr)
             for (int i = tid; i < c.npts; i += NTHREADS) alpha[base + i] = misc[M_DRAW * PS + i];
         if (occ != nullptr)      // render_rays.occupancy_activation without distances: sigmoid(alpha) (render_rays.py:6-14)
             for (int i = tid; i < c.npts; i += NTHREADS) occ[base + i] = 1.f / (1.f + expf(-misc[M_DRAW * PS + i]));
-        for (int i = tid; i < c.npts * 3; i += NTHREADS) {
-            const int p = i / 3, ch = i - 3 * p;
-            color[base * 3 + i] = misc[(M_COL + ch) * PS + p];
-        }
+        if (color != nullptr)
+            for (int i = tid; i < c.npts * 3; i += NTHREADS) {
+                const int p = i / 3, ch = i - 3 * p;
+                color[base * 3 + i] = misc[(M_COL + ch) * PS + p];
+            }
         if (emb != nullptr) {
             for (int i = tid; i < c.npts * EMB; i += NTHREADS) {
                 const int p = i / EMB, e = i - p * EMB;
@@ -101,14 +103,16 @@ __global__ void __launch_bounds__(NTHREADS, 1) k_forward(const float* __restrict
 
 extern "C" int oo_forward(const float* theta, int n_obj, const float* pcs, const float* emb_in, int n_pts, float scale,
                           float* alpha, float* color, float* clip, float* emb_out, void* stream) {
-    OO_REQUIRE(theta && alpha && color, "oo_forward: null argument");
+    OO_REQUIRE(theta, "oo_forward: null argument");
+    OO_REQUIRE((alpha && color) || (!alpha && !color && !clip && emb_out && pcs),
+               "oo_forward: alpha and color go together; without them only the encoder runs (pcs -> emb_out)");
     OO_REQUIRE((pcs != nullptr) != (emb_in != nullptr), "oo_forward: give exactly one of pcs / emb_in");
     OO_REQUIRE(n_obj > 0 && n_pts > 0, "oo_forward: empty input");
     const size_t smem = (size_t)SM_TOTAL * sizeof(float);
-    static bool attr_set = false;
-    if (!attr_set) {
+    static PerDevice attr_set;
+    if (!attr_set.cur()) {
         OO_CUDA(cudaFuncSetAttribute(k_forward, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
-        attr_set = true;
+        attr_set.cur() = 1;
     }
     const int n_tiles = (n_pts + P - 1) / P;
     int gx = (4 * 148 + n_obj - 1) / n_obj;
@@ -170,10 +174,10 @@ extern "C" int oo_eval_points(const float* theta, const float* pts, long long n_
     OO_REQUIRE(theta && pts && occ && color, "oo_eval_points: null argument");
     OO_REQUIRE(n_pts > 0 && n_pts < (1LL << 31) - P, "oo_eval_points: point count out of range");
     const size_t smem = (size_t)SM_TOTAL * sizeof(float);
-    static bool attr_set = false;
-    if (!attr_set) {
+    static PerDevice attr_set;
+    if (!attr_set.cur()) {
         OO_CUDA(cudaFuncSetAttribute(k_forward, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
-        attr_set = true;
+        attr_set.cur() = 1;
     }
     const long long n_tiles = (n_pts + P - 1) / P;
     const int gx = (int)(n_tiles < 4 * 148 ? n_tiles : 4 * 148);

@@ -344,10 +344,10 @@ extern "C" int oo_render_object(const oo_render_args* a, void* stream) {
     k_compact<<<1, 1024, 0, st>>>(k);
     OO_LAUNCH_CHECK();
     const size_t smem = (size_t)SM_TOTAL * sizeof(float);
-    static bool attr_set = false;
-    if (!attr_set) {
+    static PerDevice attr_set;
+    if (!attr_set.cur()) {
         OO_CUDA(cudaFuncSetAttribute(k_render, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
-        attr_set = true;
+        attr_set.cur() = 1;
     }
     int dev = 0, n_sm = 148;
     OO_CUDA(cudaGetDevice(&dev));

@@ -53,7 +53,7 @@ struct RayPix {
 __device__ __forceinline__ RayPix pixel_from_uniforms(const oo_sample_args& a, int obj, int kf, float uw, float uh) {
     RayPix r;
     r.kf = kf;
-    const float* bb = a.bbox[obj] + 4 * kf;
+    const float* bb = a.store_rgbi != nullptr ? a.slot_bbox + ((size_t)obj * a.kf_cap + kf) * 4 : a.bbox[obj] + 4 * kf;
     r.iwf = __fadd_rn(__fmul_rn(uw, __fsub_rn(bb[1], bb[0])), bb[0]);
     r.ihf = __fadd_rn(__fmul_rn(uh, __fsub_rn(bb[3], bb[2])), bb[2]);
     int iw = (int)r.iwf, ih = (int)r.ihf;
@@ -67,9 +67,21 @@ __device__ __forceinline__ RayPix pixel_from_uniforms(const oo_sample_args& a, i
 __device__ __forceinline__ int gather_ray(const oo_sample_args& a, int obj, int ray, int n_rays, const RayPix& p, float& d_out,
                                           int& oob) {
     oob += p.oob;
-    const size_t pix = ((size_t)p.kf * a.W + p.iw) * a.H + p.ih;
-    const uchar4 c = *reinterpret_cast<const uchar4*>(a.rgbs[obj] + pix * 4);    // vmap.py:424
-    const float d = a.depth[obj][pix];                                          // vmap.py:425
+    uchar4 c;
+    float d;
+    if (a.store_rgbi != nullptr) {
+        // shared keyframe store: one copy of the frame for all objects; the per-object pixel state of train.py:203-205
+        // (1 where inst == id, 2 where inst == -1, else 0) is derived here from the instance map
+        const size_t pix = ((size_t)a.slot_frame[(size_t)obj * a.kf_cap + p.kf] * a.W + p.iw) * a.H + p.ih;
+        const int2 v = reinterpret_cast<const int2*>(a.store_rgbi)[pix];
+        c = make_uchar4((unsigned char)(v.x & 255), (unsigned char)((v.x >> 8) & 255), (unsigned char)((v.x >> 16) & 255),
+                        (unsigned char)(v.y == a.obj_ids[obj] ? 1 : (v.y == -1 ? 2 : 0)));
+        d = a.store_depth[pix];
+    } else {
+        const size_t pix = ((size_t)p.kf * a.W + p.iw) * a.H + p.ih;
+        c = *reinterpret_cast<const uchar4*>(a.rgbs[obj] + pix * 4);              // vmap.py:424
+        d = a.depth[obj][pix];                                                    // vmap.py:425
+    }
     const size_t o = (size_t)obj * n_rays + ray;
     a.gt_rgb[o * 3 + 0] = c.x; a.gt_rgb[o * 3 + 1] = c.y; a.gt_rgb[o * 3 + 2] = c.z;
     a.gt_depth[o] = d;
@@ -82,7 +94,7 @@ __device__ __forceinline__ int gather_ray(const oo_sample_args& a, int obj, int 
     if (a.feat_row) {                                                           // vmap.py:437-452
         const int pw = min(max((int)floorf(__fdiv_rn(p.iwf, (float)a.part_down)), 0), a.pw - 1);
         const int ph = min(max((int)floorf(__fdiv_rn(p.ihf, (float)a.part_down)), 0), a.ph - 1);
-        a.feat_row[o] = (a.part_frame[obj * 20 + p.kf] * a.pw + pw) * a.ph + ph;
+        a.feat_row[o] = (a.part_frame[(size_t)obj * a.kf_cap + p.kf] * a.pw + pw) * a.ph + ph;
     }
     d_out = d;
     return invalid ? 0 : (c.w == 1 ? 1 : 2);
@@ -188,7 +200,8 @@ __device__ __forceinline__ void place_ray(const SampleK& k, int obj, int kf, int
         }
     }
     // rays: dir_W = R dir_C, origin = T[:3,3] (utils.py:324-336); points = o + d*z (vmap.py:548-549)
-    const float* T = a.t_wc[obj] + 16 * kf;
+    const float* T = a.store_rgbi != nullptr ? a.store_twc + 16 * (size_t)a.slot_frame[(size_t)obj * a.kf_cap + kf]
+                                             : a.t_wc[obj] + 16 * kf;
     const float* dc = a.rays_dir + ((size_t)iw * a.H + ih) * 3;
     const float dx = dc[0], dy = dc[1], dz = dc[2];
     const float wx = T[0] * dx + T[1] * dy + T[2] * dz;
@@ -533,55 +546,45 @@ __global__ void k_rng_fill(uint64_t seed, uint32_t frame, const int32_t* __restr
     }
 }
 
-// ---- keyframe ring append for all visible objects: one thread per pixel, loop over objects -----------------
-constexpr int APPEND_MAX = 256;
-__global__ void __launch_bounds__(256) k_append(const oo_append_args a) {
-    __shared__ int s_id[APPEND_MAX];
-    __shared__ uint8_t* s_rgbs[APPEND_MAX];
-    __shared__ float* s_depth[APPEND_MAX];
-    const int n_pix = a.W * a.H;
-    for (int o0 = 0; o0 < a.n_obj; o0 += APPEND_MAX) {
-        const int n = min(APPEND_MAX, a.n_obj - o0);
-        __syncthreads();
-        for (int i = threadIdx.x; i < n; i += blockDim.x) {
-            const size_t off = (size_t)a.slot[o0 + i] * n_pix;
-            s_id[i] = a.obj_id[o0 + i];
-            s_rgbs[i] = a.rgbs[o0 + i] + off * 4;
-            s_depth[i] = a.depth_ring[o0 + i] + off;
-        }
-        __syncthreads();
-        for (int pix = blockIdx.x * blockDim.x + threadIdx.x; pix < n_pix; pix += gridDim.x * blockDim.x) {
-            const uint8_t r = a.rgb[3 * (size_t)pix], g = a.rgb[3 * (size_t)pix + 1], b = a.rgb[3 * (size_t)pix + 2];
-            const float d = a.depth[pix];
-            const int id = a.inst[pix];
-            const uint8_t unk = id == -1 ? 2 : 0;
-            for (int i = 0; i < n; ++i) {
-                const uchar4 v = make_uchar4(r, g, b, id == s_id[i] ? 1 : unk);          // train.py:203-205
-                reinterpret_cast<uchar4*>(s_rgbs[i])[pix] = v;
-                s_depth[i][pix] = d;
-            }
+// ---- shared keyframe store: ONE copy of the new frame, whatever the number of objects that see it.
+// A pixel becomes {r | g << 8 | b << 16, instance id} (8 bytes: one load in K2 gives colour and pixel state) + depth.
+__global__ void __launch_bounds__(256) k_store_frame(const oo_store_args a) {
+    const size_t n_pix = (size_t)a.W * a.H;
+    int2* dst = reinterpret_cast<int2*>(a.store_rgbi) + (size_t)a.slot * n_pix;
+    float* dd = a.store_depth + (size_t)a.slot * n_pix;
+    const size_t n4 = n_pix / 4;
+    const bool vec = ((reinterpret_cast<uintptr_t>(a.rgb) | reinterpret_cast<uintptr_t>(a.depth) | reinterpret_cast<uintptr_t>(a.inst)) & 15) == 0;
+    if (vec) {
+        for (size_t q = (size_t)blockIdx.x * blockDim.x + threadIdx.x; q < n4; q += (size_t)gridDim.x * blockDim.x) {
+            const uint32_t* rp = reinterpret_cast<const uint32_t*>(a.rgb) + 3 * q;         // 4 pixels = 12 bytes
+            const uint32_t w0 = rp[0], w1 = rp[1], w2 = rp[2];
+            const float4 d4 = reinterpret_cast<const float4*>(a.depth)[q];
+            const int4 i4 = reinterpret_cast<const int4*>(a.inst)[q];
+            const int c0 = (int)(w0 & 0xffffffu), c1 = (int)((w0 >> 24) | ((w1 & 0xffffu) << 8)),
+                      c2 = (int)((w1 >> 16) | ((w2 & 0xffu) << 16)), c3 = (int)(w2 >> 8);
+            reinterpret_cast<int4*>(dst)[2 * q] = make_int4(c0, i4.x, c1, i4.y);
+            reinterpret_cast<int4*>(dst)[2 * q + 1] = make_int4(c2, i4.z, c3, i4.w);
+            reinterpret_cast<float4*>(dd)[q] = d4;
         }
     }
-    if (blockIdx.x == 0) {
-        for (int i = threadIdx.x; i < a.n_obj * 20; i += blockDim.x) {
-            const int o = i / 20, q = i - 20 * o;
-            if (q < 16) a.t_wc_ring[o][16 * a.slot[o] + q] = a.t_wc[q];
-            else a.bbox_ring[o][4 * a.slot[o] + q - 16] = a.bbox[4 * o + q - 16];
-        }
+    for (size_t pix = (vec ? 4 * n4 : 0) + (size_t)blockIdx.x * blockDim.x + threadIdx.x; pix < n_pix; pix += (size_t)gridDim.x * blockDim.x) {
+        const int c = (int)a.rgb[3 * pix] | ((int)a.rgb[3 * pix + 1] << 8) | ((int)a.rgb[3 * pix + 2] << 16);
+        dst[pix] = make_int2(c, a.inst[pix]);
+        dd[pix] = a.depth[pix];
     }
+    if (blockIdx.x == 0 && threadIdx.x < 16) a.store_twc[16 * (size_t)a.slot + threadIdx.x] = a.t_wc[threadIdx.x];
 }
 
 }  // namespace
 
-extern "C" int oo_append_frame(const oo_append_args* a, void* stream) {
-    OO_REQUIRE(a && a->rgb && a->depth && a->inst && a->t_wc, "oo_append_frame: null frame");
-    if (a->n_obj == 0) return 0;
-    OO_REQUIRE(a->n_obj > 0 && a->obj_id && a->slot && a->bbox && a->rgbs && a->depth_ring && a->t_wc_ring && a->bbox_ring,
-               "oo_append_frame: null table");
-    const int n_pix = a->W * a->H;
-    int blocks = (n_pix + 255) / 256;
+extern "C" int oo_store_frame(const oo_store_args* a, void* stream) {
+    OO_REQUIRE(a && a->rgb && a->depth && a->inst && a->t_wc && a->store_rgbi && a->store_depth && a->store_twc,
+               "oo_store_frame: null argument");
+    OO_REQUIRE(a->W > 0 && a->H > 0 && a->slot >= 0, "oo_store_frame: bad shape / slot");
+    const size_t n4 = ((size_t)a->W * a->H + 3) / 4;
+    int blocks = (int)((n4 + 255) / 256);
     if (blocks > 148 * 8) blocks = 148 * 8;
-    k_append<<<blocks, 256, 0, (cudaStream_t)stream>>>(*a);
+    k_store_frame<<<blocks, 256, 0, (cudaStream_t)stream>>>(*a);
     OO_LAUNCH_CHECK();
     return 0;
 }
@@ -591,7 +594,13 @@ extern "C" int oo_sample_rays(const oo_sample_args* a, void* stream) {
     OO_REQUIRE(a->n_obj > 0 && a->n_frames > 0 && a->n_samples > 0, "oo_sample_rays: empty request");
     const int S = a->n_c2s + a->n_bins;
     OO_REQUIRE(a->n_c2s >= 1 && a->n_bins >= 1 && a->n_c2s <= 16 && a->n_bins <= 16, "oo_sample_rays: need 1 <= n_c2s, n_bins <= 16");
-    OO_REQUIRE(a->rgbs && a->depth && a->t_wc && a->bbox && a->rays_dir, "oo_sample_rays: null input");
+    OO_REQUIRE(a->rays_dir, "oo_sample_rays: null input");
+    OO_REQUIRE(a->kf_cap >= 1 && a->kf_cap <= 32, "oo_sample_rays: kf_cap (keyframe_buffer_size) must be in [1, 32]");
+    if (a->store_rgbi != nullptr)
+        OO_REQUIRE(a->store_depth && a->store_twc && a->slot_frame && a->slot_bbox && a->obj_ids,
+                   "oo_sample_rays: the shared keyframe store needs store_depth / store_twc / slot_frame / slot_bbox / obj_ids");
+    else
+        OO_REQUIRE(a->rgbs && a->depth && a->t_wc && a->bbox, "oo_sample_rays: null keyframe ring table");
     if (a->rng_mode) {
         OO_REQUIRE(a->obj_ids && a->n_keyframes && a->latest, "oo_sample_rays: rng_mode needs obj_ids / n_keyframes / latest");
         OO_REQUIRE(!a->tape_by_rank, "oo_sample_rays: the counter RNG is indexed by ray, not by rank");
@@ -610,19 +619,12 @@ extern "C" int oo_sample_rays(const oo_sample_args* a, void* stream) {
     for (int i = 0; i <= a->n_bins; ++i) k.lin_b[i] = a->lin_bins_host[i];
     if (a->rng_mode) {
         OO_REQUIRE(a->min_bound >= 0.f, "oo_sample_rays: the parallel path assumes min_bound >= 0");
-        // per-object batch-max scratch: one small allocation per process, grown on demand (calls are not re-entrant)
         OO_REQUIRE(a->W <= 2048 && a->H <= 32768, "oo_sample_rays: the packed pixel needs W <= 2048, H <= 32768");
         const int n_rays = a->n_frames * a->n_samples;
-        // scratch: per-object batch max and invalid-ray count, per-object invalid-ray lists; one allocation per process, grown
-        // on demand (calls are not re-entrant)
-        static int* scratch = nullptr;
-        static size_t cap = 0;
+        // caller-owned scratch: per-object batch max and invalid-ray count, then the per-object invalid-ray lists
         const size_t need = (size_t)a->n_obj * (2 + 2 * (size_t)n_rays);
-        if (need > cap) {
-            if (scratch) OO_CUDA(cudaFree(scratch));
-            cap = need < (1u << 20) ? (1u << 20) : 2 * need;
-            OO_CUDA(cudaMalloc((void**)&scratch, cap * sizeof(int)));
-        }
+        OO_REQUIRE(a->scratch && (size_t)a->scratch_ints >= need, "oo_sample_rays: rng_mode 1 needs scratch of n_obj * (2 + 2 n_rays) ints");
+        int* scratch = a->scratch;
         int* max_bits = scratch;
         int* inv_cnt = scratch + a->n_obj;
         int2* inv_list = reinterpret_cast<int2*>(scratch + 2 * (size_t)a->n_obj);

@@ -169,6 +169,11 @@ struct TileCtx {
     float scale;               // UniDirsEmbed scale
     float inv1, invs;          // 1/(n(label==1)+1e-10), 1/(n(label!=2)+1e-10) of this object in this step
     float cs, os, fs;          // colour / opacity / feature scaling (loss.py:6)
+    // general-upstream backward (oo_forward_bwd: the autograd surface of vmap(fc_model)), first point of the tile:
+    const float* up_alpha;     // [npts]      dL/d alpha (alpha = 10 x out_alpha's output, model.py:88)
+    const float* up_color;     // [npts][3]   dL/d color (after the sigmoid)
+    const float* up_hp;        // [npts][32]  dL/d hp = d_clip W_ocl (k_clip_dhp), or nullptr
+    float* hp_out;             // [npts][32]  clip_linear's output (post-ReLU) for the out_clip weight gradient, or nullptr
 };
 
 // ------------------------------------------------------------------------------------------------
@@ -1071,6 +1076,60 @@ OO_DEV void tile_phase(int tid, float* __restrict__ sm, const TileCtx& c, TileAc
             }
         }
         __syncthreads();       // the out_color weight gradient above read hc; d(hc_pre) now replaces it in place
+        for (int i = tid; i < H * (P / 4); i += NTHREADS) {          // d(hc_pre) = (W_oc^T dcol_pre) * [hc > 0]
+            const int j = i / (P / 4), p0 = 4 * (i - j * (P / 4));
+            float* hc = act + (R_HC + j) * PS + p0;
+            const float4 h = ld4(hc);
+            const float4 d0 = ld4(misc + (M_DCOL + 0) * PS + p0), d1 = ld4(misc + (M_DCOL + 1) * PS + p0),
+                         d2 = ld4(misc + (M_DCOL + 2) * PS + p0);
+            const float w0 = w[W_OC + j], w1 = w[W_OC + H + j], w2 = w[W_OC + 2 * H + j];
+            float4 o;
+            o.x = h.x > 0.f ? w0 * d0.x + w1 * d1.x + w2 * d2.x : 0.f;
+            o.y = h.y > 0.f ? w0 * d0.y + w1 * d1.y + w2 * d2.y : 0.f;
+            o.z = h.z > 0.f ? w0 * d0.z + w1 * d1.z + w2 * d2.z : 0.f;
+            o.w = h.w > 0.f ? w0 * d0.w + w1 * d1.w + w2 * d2.w : 0.f;
+            st4(hc, o);
+        }
+    } else if constexpr (PH == 43) {
+        // ---- general upstream (oo_forward_bwd), after forward phases 2..7: gradients w.r.t. the raw head outputs.
+        //   d raw_alpha = 10 d_alpha (model.py:88);  d col_pre = d_color * col (1 - col) (model.py:96);
+        //   d hp_pre = (d_clip W_ocl) * [hp > 0], the product having been formed by k_clip_dhp; hp itself leaves for the
+        //   out_clip weight gradient (k_clip_dw) before it is overwritten.  Points beyond npts contribute nothing.
+        for (int p = tid; p < P; p += NTHREADS) {
+            const bool in = p < c.npts;
+            misc[M_DRAW * PS + p] = in ? 10.f * OO_LDG(c.up_alpha + p) : 0.f;
+#pragma unroll
+            for (int ch = 0; ch < 3; ++ch) {
+                const float k = misc[(M_COL + ch) * PS + p];
+                misc[(M_DCOL + ch) * PS + p] = in ? OO_LDG(c.up_color + 3 * p + ch) * k * (1.f - k) : 0.f;
+            }
+        }
+        for (int i = tid; i < P * H; i += NTHREADS) {
+            const int p = i / H, j = i - p * H;
+            float* hp = act + (R_HP + j) * PS + p;
+            const float h = *hp;
+            const bool in = p < c.npts;
+            if (in && c.hp_out != nullptr) c.hp_out[i] = h;
+            *hp = (in && c.up_hp != nullptr && h > 0.f) ? OO_LDG(c.up_hp + i) : 0.f;
+        }
+    } else if constexpr (PH == 44) {
+        // ---- out_color / out_alpha weight gradients, then (after a block barrier) d(hc_pre) in place: phase 42 without the
+        // compositing-specific parts
+        if (tid >= OC_T0 && tid < OC_T0 + 4 * H) {
+            OO_ACC(g_oc, 1, AC_OC);
+            const int o = (tid - OC_T0) >> 5, j = tid & 31;
+            const float* dy = misc + (o < 3 ? (M_DCOL + o) : M_DRAW) * PS;
+            const float* x = act + ((o < 3 ? R_HC : R_H4) + j) * PS;
+            float s0 = 0.f, s1 = 0.f, s2 = 0.f, s3 = 0.f;
+#pragma unroll
+            for (int p0 = 0; p0 < P; p0 += 4) {
+                const float4 d = ld4(dy + p0), h = ld4(x + p0);
+                s0 += d.x * h.x; s1 += d.y * h.y; s2 += d.z * h.z; s3 += d.w * h.w;
+            }
+            g_oc[0] += (s0 + s1) + (s2 + s3);
+            OO_ACC_PUT(g_oc, 1, AC_OC);
+        }
+        __syncthreads();
         for (int i = tid; i < H * (P / 4); i += NTHREADS) {          // d(hc_pre) = (W_oc^T dcol_pre) * [hc > 0]
             const int j = i / (P / 4), p0 = 4 * (i - j * (P / 4));
             float* hc = act + (R_HC + j) * PS + p0;

@@ -201,7 +201,7 @@ __global__ void __launch_bounds__(NTHREADS, 1) k_train(const TrainParams prm) {
 
 // ---- per-frame: ray counts per (step, object) and the cross-object zero-mask flags (render_rays.py:88-94)
 __global__ void k_label_counts(const uint8_t* __restrict__ labels, int n_obj, int rays_per_obj, int R,
-                               int* __restrict__ counts, int* __restrict__ flags) {
+                               int* __restrict__ counts, int* __restrict__ flags, int* __restrict__ flag_bits) {
     const int it = blockIdx.x;
     int f = 0;
     for (int o = 0; o < n_obj; ++o) {
@@ -221,19 +221,29 @@ __global__ void k_label_counts(const uint8_t* __restrict__ labels, int n_obj, in
         if (n1 == 0) f |= OO_FLAG_NO_OBJ;
         if (ns == 0) f |= OO_FLAG_NO_SEM;
     }
-    if (threadIdx.x == 0) flags[it] = f;
+    if (threadIdx.x == 0) {
+        flags[it] = f;
+        if (flag_bits != nullptr) {           // one int per bit: a MAX all-reduce over ranks is then the OR the rule needs
+            flag_bits[2 * it] = (f & OO_FLAG_NO_OBJ) ? 1 : 0;
+            flag_bits[2 * it + 1] = (f & OO_FLAG_NO_SEM) ? 1 : 0;
+        }
+    }
 }
 
 // ---- per-frame: which parameter groups autograd reaches in each step, their Adam step numbers and bias
 // corrections (torch.optim.AdamW: tensors whose grad is None are skipped entirely)
-__global__ void k_adam_schedule(const int* __restrict__ flags, int iters, int part_on, double lr, double b1, double b2,
-                                int* __restrict__ adam_t, float* __restrict__ scal) {
+__global__ void k_adam_schedule(int* __restrict__ flags, const int* __restrict__ reduced_bits, int iters, int part_on, double lr,
+                                double b1, double b2, int* __restrict__ adam_t, float* __restrict__ scal) {
     // one thread per step; the step number of a group = its counter + number of active steps up to and including `it`
     __shared__ int s_act[3][1024];
     const int it = threadIdx.x;
     bool active[3] = {false, false, false};
     if (it < iters) {
-        const int f = flags[it];
+        int f = flags[it];
+        if (reduced_bits != nullptr) {        // sharded run: the zero-mask bits OR-ed over all ranks replace the local ones
+            f = (reduced_bits[2 * it] ? OO_FLAG_NO_OBJ : 0) | (reduced_bits[2 * it + 1] ? OO_FLAG_NO_SEM : 0);
+            flags[it] = f;
+        }
         const bool obj_terms = !(f & OO_FLAG_NO_OBJ), op_term = !(f & OO_FLAG_NO_SEM);
         active[0] = obj_terms || op_term;
         active[1] = obj_terms;
@@ -383,16 +393,19 @@ __global__ void __launch_bounds__(256) k_adamw(float* __restrict__ theta, float*
                                                const float* __restrict__ scal, float decay, float b1, float b2, float eps,
                                                const float* __restrict__ clip_grad, const float* __restrict__ slot_loss,
                                                const int* __restrict__ counts, float* __restrict__ loss_terms,
-                                               float* __restrict__ grads_out) {
+                                               float* __restrict__ grads_out, int* __restrict__ step_flags) {
     const int o = blockIdx.y;
     const int i = 4 * (blockIdx.x * 256 + threadIdx.x);
     const int s0 = obj_slot[o], s1 = obj_slot[o + 1];
-    if (blockIdx.x == 0 && threadIdx.x < 4 && loss_terms != nullptr) {
-        // per-object loss terms: masked mean = sum / (count + 1e-10)  (render_rays.py:108)
+    if (blockIdx.x == 0 && threadIdx.x < 4) {
+        // per-object loss terms: masked mean = sum / (count + 1e-10)  (render_rays.py:108); a term above 1e5 is where the
+        // reference prints "loss explode" and exits (render_rays.py:109-111): bit OO_FLAG_EXPLODE of this step's flags
         float s = 0.f;
         for (int q = s0; q < s1; ++q) s += slot_loss[4 * q + threadIdx.x];
         const int n = counts[2 * o + (threadIdx.x == 2 ? 1 : 0)];
-        loss_terms[4 * o + threadIdx.x] = s / ((float)n + 1e-10f);
+        const float term = s / ((float)n + 1e-10f);
+        if (loss_terms != nullptr) loss_terms[4 * o + threadIdx.x] = term;
+        if (term > 100000.f) atomicOr(step_flags, OO_FLAG_EXPLODE);
     }
     if (i >= PEND) return;
     const int grp = group_of_offset(i);
@@ -512,7 +525,7 @@ __global__ void __launch_bounds__(UPD_THREADS, 2) k_update(float* theta, float* 
                                                            float decay, float b1, float b2, float eps, const ClipGrad cg,
                                                            const float* __restrict__ slot_loss, const int* __restrict__ counts,
                                                            float* __restrict__ loss_terms, float* __restrict__ derived,
-                                                           float* gram_part, int* gram_cnt) {
+                                                           float* gram_part, int* gram_cnt, int* __restrict__ step_flags) {
     extern __shared__ __align__(16) float sh[];   // [1088] M, m, beta | act [Rp] | frow [Rp] | rec [R][36] | wn [128][36] | ys [R][128]
     __shared__ int s_warp[UPD_THREADS / 32];
     __shared__ int s_last;
@@ -567,12 +580,16 @@ __global__ void __launch_bounds__(UPD_THREADS, 2) k_update(float* theta, float* 
         // released this launch after its own wait); everything below reads what K1 wrote
         pdl_wait();
         pdl_release();
-        if (chunk == 0 && tid < 4 && loss_terms != nullptr) {
-            // per-object loss terms: masked mean = sum / (count + 1e-10)  (render_rays.py:108)
+        if (chunk == 0 && tid < 4) {
+            // per-object loss terms: masked mean = sum / (count + 1e-10)  (render_rays.py:108); a term above 1e5 is where the
+            // reference prints "loss explode" and exits (render_rays.py:109-111): bit OO_FLAG_EXPLODE of this step's flags
+            // (k_train of this step has read its zero-mask bits already; the host looks at the flags once per frame)
             float s = 0.f;
             for (int q = s0; q < s1; ++q) s += slot_loss[4 * q + tid];
             const int n = counts[2 * o + (tid == 2 ? 1 : 0)];
-            loss_terms[4 * o + tid] = s / ((float)n + 1e-10f);
+            const float term = s / ((float)n + 1e-10f);
+            if (loss_terms != nullptr) loss_terms[4 * o + tid] = term;
+            if (term > 100000.f) atomicOr(step_flags, OO_FLAG_EXPLODE);
         }
         for (int sl = s0; sl < s1; sl += 2) {            // slots summed in order, two per round trip
             const float* sp = slab + (size_t)sl * PSTRIDE;
@@ -831,18 +848,18 @@ int launch_k1(const float* theta, int n_obj, const oo_batch* b, int it, int R, f
     prm.block_times = g_block_times;
     prm.cs = 5.f; prm.os = 10.f; prm.fs = 5.f;   // loss.py:6 defaults (the JSON values are never read)
     const size_t smem = (size_t)SM_TOTAL * sizeof(float);
-    static bool attr_set = false;
-    if (!attr_set) {
+    static PerDevice attr_set;
+    if (!attr_set.cur()) {
         OO_CUDA(cudaFuncSetAttribute(k_train<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
         OO_CUDA(cudaFuncSetAttribute(k_train<false>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
-        attr_set = true;
+        attr_set.cur() = 1;
     }
     if (b->feat_row != nullptr && gram) {
         const size_t gsmem = (size_t)(SM_GPART + NGG * 36 * 36) * sizeof(float);
-        static bool gattr = false;
-        if (!gattr) {
+        static PerDevice gattr;
+        if (!gattr.cur()) {
             OO_CUDA(cudaFuncSetAttribute(k_gram, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)gsmem));
-            gattr = true;
+            gattr.cur() = 1;
         }
         k_gram<<<n_obj, NTHREADS, gsmem, st>>>(theta, ws->derived);
         OO_LAUNCH_CHECK();
@@ -887,20 +904,21 @@ extern "C" int oo_train_schedule(int n_obj, int rays_per_step, int n_sm, oo_trai
 }
 
 extern "C" int oo_label_counts(const uint8_t* labels, int n_obj, int rays_per_obj, int rays_per_step, int iters,
-                               int* counts, int* flags, void* stream) {
-    OO_REQUIRE(labels && counts && flags && iters > 0, "oo_label_counts: null argument");
-    OO_REQUIRE((long long)iters * rays_per_step <= rays_per_obj, "oo_label_counts: iters*rays_per_step > rays_per_obj");
-    k_label_counts<<<iters, 128, 0, (cudaStream_t)stream>>>(labels, n_obj, rays_per_obj, rays_per_step, counts, flags);
+                               int* counts, int* flags, int* flag_bits, void* stream) {
+    OO_REQUIRE(counts && flags && iters > 0 && n_obj >= 0, "oo_label_counts: null argument");
+    OO_REQUIRE(n_obj == 0 || labels, "oo_label_counts: null labels");
+    OO_REQUIRE(n_obj == 0 || (long long)iters * rays_per_step <= rays_per_obj, "oo_label_counts: iters*rays_per_step > rays_per_obj");
+    k_label_counts<<<iters, 128, 0, (cudaStream_t)stream>>>(labels, n_obj, rays_per_obj, rays_per_step, counts, flags, flag_bits);
     OO_LAUNCH_CHECK();
     return 0;
 }
 
-extern "C" int oo_adam_schedule(const int* flags, int iters, int part_on, float lr, float beta1, float beta2,
+extern "C" int oo_adam_schedule(int* flags, const int* reduced_bits, int iters, int part_on, float lr, float beta1, float beta2,
                                 int* adam_t, float* adam_scal, void* stream) {
     OO_REQUIRE(flags && adam_t && adam_scal, "oo_adam_schedule: null argument");
     OO_REQUIRE(iters >= 1 && iters <= 1024, "oo_adam_schedule: iters must be in [1, 1024]");
-    k_adam_schedule<<<1, 1024, 0, (cudaStream_t)stream>>>(flags, iters, part_on, (double)lr, (double)beta1, (double)beta2,
-                                                        adam_t, adam_scal);
+    k_adam_schedule<<<1, 1024, 0, (cudaStream_t)stream>>>(flags, reduced_bits, iters, part_on, (double)lr, (double)beta1,
+                                                        (double)beta2, adam_t, adam_scal);
     OO_LAUNCH_CHECK();
     return 0;
 }
@@ -927,14 +945,15 @@ static int launch_k4(float* theta, float* am, float* av, int n_obj, const oo_bat
         }
         const size_t smem = update_smem_floats(R, part) * sizeof(float);
         OO_REQUIRE(smem <= 112 * 1024, "oo_train: rays_per_step too large for the update kernel's staging buffer");
-        static size_t attr_smem = 0;
-        if (smem > attr_smem) {
+        static PerDevice attr_smem_d;
+        size_t& attr_smem = attr_smem_d.cur();
+        if (smem > attr_smem || attr_smem == 0) {
             OO_CUDA(cudaFuncSetAttribute(k_update<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
             // same L1 / shared-memory split as k_train (which needs the maximum): no SM reconfiguration between the two
             // kernels of a step
             OO_CUDA(cudaFuncSetAttribute(k_update<true>, cudaFuncAttributePreferredSharedMemoryCarveout, cudaSharedmemCarveoutMaxShared));
             OO_CUDA(cudaFuncSetAttribute(k_update<false>, cudaFuncAttributePreferredSharedMemoryCarveout, cudaSharedmemCarveoutMaxShared));
-            attr_smem = smem;
+            attr_smem = smem > 0 ? smem : 1;
         }
         const float decay = (float)(1.0 - (double)lr * (double)wd);
         const dim3 ugrid(UPD_CHUNKS, n_obj);
@@ -944,10 +963,10 @@ static int launch_k4(float* theta, float* am, float* av, int n_obj, const oo_bat
         int* nulli = nullptr;
         if (part)
             OO_CUDA(launch_pdl(k_update<true>, ugrid, dim3(UPD_THREADS), smem, st, theta, am, av, cslab, obj_slot, scal, decay, b1,
-                               b2, eps, cg, cslot, counts, loss_terms, ws->derived, ws->gram_part, ws->gram_cnt));
+                               b2, eps, cg, cslot, counts, loss_terms, ws->derived, ws->gram_part, ws->gram_cnt, ws->flags + it));
         else
             OO_CUDA(launch_pdl(k_update<false>, ugrid, dim3(UPD_THREADS), (size_t)0, st, theta, am, av, cslab, obj_slot, scal, decay,
-                               b1, b2, eps, cg, cslot, counts, loss_terms, nullf, nullf, nulli));
+                               b1, b2, eps, cg, cslot, counts, loss_terms, nullf, nullf, nulli, ws->flags + it));
         OO_LAUNCH_CHECK();
         return 0;
     }
@@ -960,7 +979,8 @@ static int launch_k4(float* theta, float* am, float* av, int n_obj, const oo_bat
         cg.R = R;
         const size_t smem = (size_t)(DERIVED + ((R + 3) & ~3) + (size_t)R * RAYREC + (size_t)R * 128) * sizeof(float);
         OO_REQUIRE(smem <= 200 * 1024, "oo_train: rays_per_step too large for the out_clip gradient kernel's staging buffer");
-        static size_t attr_smem = 0;
+        static PerDevice attr_smem_d;
+        size_t& attr_smem = attr_smem_d.cur();
         if (smem > attr_smem) {
             OO_CUDA(cudaFuncSetAttribute(k_clipgrad, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
             attr_smem = smem;
@@ -971,11 +991,11 @@ static int launch_k4(float* theta, float* am, float* av, int n_obj, const oo_bat
     const float* cgrad = part ? ws->clip_grad : nullptr;
     if (grads_out) {
         k_adamw<false><<<grid, 256, 0, st>>>(theta, nullptr, nullptr, ws->slab, obj_slot, scal, 0.f, 0.f, 0.f, 0.f, cgrad,
-                                             ws->slot_loss, counts, loss_terms, grads_out);
+                                             ws->slot_loss, counts, loss_terms, grads_out, ws->flags + it);
     } else {
         const float decay = (float)(1.0 - (double)lr * (double)wd);
         k_adamw<true><<<grid, 256, 0, st>>>(theta, am, av, ws->slab, obj_slot, scal, decay, b1, b2, eps, cgrad, ws->slot_loss,
-                                            counts, loss_terms, nullptr);
+                                            counts, loss_terms, nullptr, ws->flags + it);
     }
     OO_LAUNCH_CHECK();
     return 0;

@@ -13,6 +13,34 @@ def owner_rank(ensemble_index, world):
     return ensemble_index % world
 
 
+class ShardBook:
+    """Which objects exist and who owns them: every rank sees every frame's instance ids (train.py:191) and runs this same
+    bookkeeping, so all ranks agree on the ensemble index k of an object (order of first appearance, ties by ascending id),
+    on its owner k mod G, on the global "models full" cap (train.py:231-233) and on WHEN a new object appeared anywhere --
+    the event at which the reference restacks all models and Adam's state restarts for everybody (train.py:272-276)."""
+
+    def __init__(self, rank=0, world=1, cap=100):
+        self.rank, self.world, self.cap = int(rank), int(world), int(cap)
+        self.global_index = {}            # obj id -> k
+        self.local_index = {}             # obj id -> position among this rank's objects
+
+    def full(self):
+        return len(self.global_index) >= self.cap
+
+    def see(self, obj_id):
+        """-> (k, local index or None, new) ; None when the object is dropped because the model table is full."""
+        k = self.global_index.get(obj_id)
+        new = k is None
+        if new:
+            if self.full():
+                return None
+            k = len(self.global_index)
+            self.global_index[obj_id] = k
+            if owner_rank(k, self.world) == self.rank:
+                self.local_index[obj_id] = len(self.local_index)
+        return k, self.local_index.get(obj_id), new
+
+
 def bind_to_gpu_cpus(local):
     """Pin this process to the CPUs NVML reports as local to GPU `local` (its NUMA node), BEFORE the CUDA context and the
     pinned host buffers exist: with one process per GPU the per-frame host->device copies (76 MB at Replica size) then come
@@ -60,14 +88,13 @@ def init_from_env(backend=None):
 
 
 def make_flag_allreduce(group=None):
-    """OR-reduce OO_FLAG_* bit masks across ranks.  NCCL has no bitwise reduction: MAX over the two bits separately."""
+    """OR of the zero-mask bits across ranks: the caller hands an int32 tensor [iters, 2] holding ONE int per bit
+    (oo_label_counts' flag_bits), so a single MAX all-reduce is the OR (NCCL has no bitwise reduction)."""
     if not dist.is_initialized() or dist.get_world_size(group) == 1:
         return None
 
-    def allreduce(flags):
-        bits = torch.stack([(flags >> 1) & 1, (flags >> 2) & 1], dim=1).contiguous()
+    def allreduce(bits):
         dist.all_reduce(bits, op=dist.ReduceOp.MAX, group=group)
-        flags.copy_((bits[:, 0] << 1) | (bits[:, 1] << 2))
     return allreduce
 
 

@@ -26,10 +26,20 @@ class UniDirsEmbed(torch.nn.Module):
         self.register_buffer("scale", self.tensor_scale, persistent=True)
 
     def forward(self, x):
+        """embedding.py:46-55: x [...,3] -> [...,129]; differentiable w.r.t. B_layer.weight (oo_embed_bwd)."""
         if self.min_deg != 0 or self.n_freqs != 6:
             raise NotImplementedError("the CUDA encoder is built for n_unidir_funcs=5 (6 bands), as every shipped config uses")
-        theta = torch.zeros(1, layout.PSTRIDE, dtype=torch.float32, device=x.device)
-        layout.views(theta)[18].copy_(self.B_layer.weight.detach()[None])
-        with torch.no_grad():
-            _, _, _, emb = ops.forward(theta, pcs=x.detach()[None], scale=float(self.scale), want_clip=False, want_emb=True)
-        return emb[0]
+        if not x.is_cuda:
+            raise RuntimeError("openobj_b200.embedding.UniDirsEmbed needs CUDA tensors (no CPU fallback)")
+        B = self.B_layer.weight[None]
+        theta = ops._as_theta([B], 18)
+        return ops.embed_autograd(x[None], theta, self._scale_value(), B)[0]
+
+    def _scale_value(self):
+        """The `scale` buffer as a Python float (it is persistent: a checkpoint may have replaced it); read back from the
+        device only when the buffer changed."""
+        key = (self.scale.data_ptr(), self.scale._version)
+        if getattr(self, "_scale_key", None) != key:
+            object.__setattr__(self, "_scale_key", key)
+            object.__setattr__(self, "_scale_float", float(self.scale))
+        return self._scale_float

@@ -89,6 +89,10 @@ class Ensemble:
             self._sched = torch.zeros(sched_i.value, **i32)
             self.counts = torch.zeros(self.iters, self.n_obj, 2, **i32)
             self.flags = torch.zeros(self.iters, **i32)
+            self.flag_bits = torch.zeros(self.iters, 2, **i32)      # one int per zero-mask bit: what a sharded run all-reduces
+            self._explode_host = torch.zeros(1, dtype=torch.int32).pin_memory()
+            self._explode_dev = torch.zeros(1, **i32)
+            self._explode_event = None
             self._adam_scal = torch.zeros(self.iters, 3, 4, **f32)
             self.adam_t = torch.zeros(3, **i32)
             self._gram_part = torch.zeros(self.n_obj, 4, 1092, **f32)             # OO_GRAM_PART_FLOATS
@@ -107,12 +111,6 @@ class Ensemble:
     def load_stacked(self, tensors):
         for v, t in zip(self.stacked(), tensors):
             v.copy_(t.to(self.device))
-        self.params_changed()
-
-    def params_changed(self):
-        """Kept for callers that write theta from outside: nothing derived from the parameters is cached any more
-        (K1 recomputes the out_clip constants when it starts an object)."""
-        return None
 
     def reset_optimizer(self):
         """Adam moments and step counters restart whenever the ensemble is rebuilt."""
@@ -121,18 +119,48 @@ class Ensemble:
         self.adam_t.zero_()
 
     # ---- per frame --------------------------------------------------------------------------
+    def _iters(self, iters):
+        iters = int(iters or self.iters)
+        if not 1 <= iters <= self.iters:
+            raise ValueError("iters=%d outside [1, iters_per_frame=%d]: the per-step tables are sized by the constructor" % (iters, self.iters))
+        return iters
+
     def prepare_frame(self, batch: FrameBatch, iters=None, flag_allreduce=None):
-        """Ray counts + zero-mask flags for every step, then the Adam schedule.  `flag_allreduce(flags)` lets a
-        sharded run OR the flags across ranks (the one cross-object coupling, render_rays.py:89-94)."""
-        iters = iters or self.iters
+        """Ray counts + zero-mask flags for every step, then the Adam schedule.  `flag_allreduce(bits)` lets a sharded run
+        OR the zero-mask bits across ranks (the one cross-object coupling, render_rays.py:89-94): it receives the int32
+        tensor [iters, 2] (one int per bit) and MAX-all-reduces it in place."""
+        iters = self._iters(iters)
         part_on = batch.feat_row is not None
+        self.check_explode()                      # of the previous frame: one look per frame (SURVEY section 5)
         with torch.cuda.device(self.device):
+            bits = self.flag_bits[:iters] if flag_allreduce is not None else None
             check(self.L.oo_label_counts(ptr(batch.labels), self.n_obj, batch.rays_per_obj, self.R, iters,
-                                         ptr(self.counts), ptr(self.flags), stream()), "oo_label_counts")
+                                         ptr(self.counts), ptr(self.flags), ptr(bits), stream()), "oo_label_counts")
             if flag_allreduce is not None:
-                flag_allreduce(self.flags[:iters])
-            check(self.L.oo_adam_schedule(ptr(self.flags), iters, int(part_on), self.lr, self.betas[0], self.betas[1],
+                flag_allreduce(bits)
+            check(self.L.oo_adam_schedule(ptr(self.flags), ptr(bits), iters, int(part_on), self.lr, self.betas[0], self.betas[1],
                                           ptr(self.adam_t), ptr(self._adam_scal), stream()), "oo_adam_schedule")
+
+    # ---- the reference's `loss > 1e5 -> print, exit(-1)` guard (render_rays.py:109-111): the update kernel raises bit
+    # OO_FLAG_EXPLODE of a step's flags; the host looks once per frame, without stalling the stream
+    def _post_explode(self, iters):
+        with torch.cuda.device(self.device):
+            torch.amax(self.flags[:iters] & 1, dim=0, keepdim=True, out=self._explode_dev)
+            self._explode_host.copy_(self._explode_dev, non_blocking=True)
+            self._explode_event = torch.cuda.Event()
+            self._explode_event.record()
+
+    def check_explode(self, wait=False):
+        """Raises FloatingPointError if a per-object loss term of an already finished frame exceeded 1e5."""
+        ev = self._explode_event
+        if ev is None:
+            return
+        if wait:
+            ev.synchronize()
+        if ev.query():
+            self._explode_event = None
+            if int(self._explode_host[0]) != 0:
+                raise FloatingPointError("loss explode (a per-object loss term > 1e5, render_rays.py:109-111)")
 
     def grads(self, batch: FrameBatch, it=0):
         """Gradients of the step loss w.r.t. theta (no update) + per-object loss terms [N,4]."""
@@ -154,7 +182,7 @@ class Ensemble:
     def train_frame(self, batch: FrameBatch, iters=None, loss_terms=None, prepare=True, flag_allreduce=None):
         """`iters` optimisation steps over the pre-sampled batch (train.py:394-474).
         loss_terms: optional [iters,N,4] output (depth, colour, opacity, feature per object)."""
-        iters = iters or self.iters
+        iters = self._iters(iters)
         if prepare:
             self.prepare_frame(batch, iters, flag_allreduce)
         b = batch.to_c()
@@ -162,6 +190,7 @@ class Ensemble:
             check(self.L.oo_train_frame(ptr(self.theta), ptr(self.m), ptr(self.v), self.n_obj, ctypes.byref(b), iters,
                                         self.R, self.scale, self.lr, self.wd, self.betas[0], self.betas[1], self.eps,
                                         ctypes.byref(self.ws), ptr(loss_terms), self.n_sm, stream()), "oo_train_frame")
+        self._post_explode(iters)
 
     def k1(self, batch_c, it, refresh_derived=True):
         """K1 alone (fused encode/MLP/composite/loss/backward into the slabs).  refresh_derived=False skips the

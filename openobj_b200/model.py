@@ -1,7 +1,9 @@
 """Mirror of objnerf/model.py: `OccupancyMap` keeps the reference's constructor, sub-module names (hence state-dict
 keys: in_layer.0.weight, mid1.0.0.weight, ...) and forward signature; forward() runs the CUDA tile on the given
-embedding.  Module-level forward is inference-only (no autograd through the kernel); training goes through
-`openobj_b200.ensemble.Ensemble` (fused forward + loss + backward + AdamW)."""
+embedding and is differentiable w.r.t. the module's parameters and the embedding (oo_forward_bwd), so
+`alpha, color, clip = fc_occ_map(pe(x)); loss.backward(); optimiser.step()` (train.py:449-474) works on it.  Hidden width 32
+(every object model) runs the fused tile; other widths (the hidden-128 background model) the layer-by-layer kernels.
+The fast path for training many objects is `openobj_b200.ensemble.Ensemble` (fused forward + loss + backward + AdamW)."""
 import torch
 
 from . import layout, ops
@@ -50,9 +52,27 @@ class OccupancyMap(torch.nn.Module):
         return theta
 
     def forward(self, x, noise_std=None, do_alpha=True, do_color=True, do_cat=True, do_clip=True):
-        if not self._supported() or noise_std is not None or not do_cat:
-            raise NotImplementedError("CUDA OccupancyMap supports hidden=32, clip=512, e1/e2=87/42, do_cat=True, "
-                                      "noise_std=None (the configuration every shipped object model uses)")
-        with torch.no_grad():
-            a, c, f, _ = ops.forward(self.packed(x.device), emb=x.detach()[None], want_clip=bool(do_clip))
-        return (a[0] if do_alpha else None, c[0] if do_color else None, f[0] if do_clip else None)
+        """model.py:61-103 on an embedding x [...,129]; returns (alpha [...,1], color [...,3], clip [...,512])."""
+        if noise_std is not None or not do_cat:
+            raise NotImplementedError("CUDA OccupancyMap: noise_std / do_cat=False are never used by the reference's callers")
+        if not (self.clip_size == layout.CLIP and self.embedding_size1 == layout.E1 and self.embedding_size2 == layout.E2
+                and self.do_color and self.do_clip and len(self.mid1) == 1 and len(self.mid2) == 1):
+            raise NotImplementedError("CUDA OccupancyMap supports clip=512, e1/e2=87/42, one hidden block (every shipped config)")
+        if not x.is_cuda:
+            raise RuntimeError("openobj_b200.model.OccupancyMap needs CUDA tensors (no CPU fallback)")
+        params = list(self.parameters())
+        want_clip = bool(do_clip)
+        if self.hidden_size == layout.HIDDEN:
+            stacked = [p[None] for p in params]
+            theta = ops._as_theta(stacked, 0)
+            out = ops.fc_autograd(x[None], theta, want_clip, stacked)
+            a, c = out[0][0], out[1][0]
+            f = out[2][0] if want_clip else None
+        else:
+            from .background import BackgroundModel
+            if getattr(self, "_wide", None) is None or self._wide.device != x.device:
+                object.__setattr__(self, "_wide", BackgroundModel(hidden=self.hidden_size, device=x.device))
+            out = ops.wide_autograd(x, self._wide, want_clip, params)
+            a, c = out[0], out[1]
+            f = out[2] if want_clip else None
+        return (a if do_alpha else None, c if do_color else None, f)

@@ -39,6 +39,155 @@ def forward(theta, pcs=None, emb=None, scale=2.0, want_clip=True, want_emb=False
             None if emb_o is None else emb_o.view(lead + [129]))
 
 
+def embed(theta, pcs, scale=2.0):
+    """vmap(pe_model) on its own: theta [N,PSTRIDE] (only the B_layer block is read), pcs [N,...,3] -> emb [N,...,129]."""
+    _dev(theta)
+    n = theta.shape[0]
+    lead = list(pcs.shape[:-1])
+    x = pcs.reshape(n, -1, 3).contiguous().float()
+    m = x.shape[1]
+    emb = torch.empty(n, m, 129, dtype=torch.float32, device=theta.device)
+    with _dev(theta):
+        check(lib().oo_forward(ptr(theta), n, ptr(x), None, m, float(scale), None, None, None, ptr(emb), stream()), "oo_forward")
+    return emb.view(lead + [129])
+
+
+# ---- the autograd surface of the reference's call form (train.py:424-425, backward at :472) ----------------------------
+def _as_theta(params, first, fallback_theta=None):
+    """A [N,PSTRIDE] block holding `params` (stacked tensors first .. first+len-1 of the layout).  When they already are
+    the strided views of one such block (what update_vmap hands out) that block is used in place; otherwise they are
+    packed into a fresh one."""
+    n = params[0].shape[0]
+    base = params[0].data_ptr() - 4 * layout.OFFSETS[first]
+    aliased = all(p.is_cuda and p.dtype == torch.float32 and p.data_ptr() == base + 4 * layout.OFFSETS[first + i]
+                  and (n == 1 or p.stride(0) == layout.PSTRIDE) and p[0].is_contiguous() for i, p in enumerate(params))
+    if aliased and fallback_theta is not None and fallback_theta.data_ptr() == base and fallback_theta.shape[0] == n:
+        return fallback_theta
+    theta = torch.zeros(n, layout.PSTRIDE, dtype=torch.float32, device=params[0].device)
+    with torch.no_grad():
+        for v, p in zip(layout.views(theta)[first:first + len(params)], params):
+            v.copy_(p)
+    return theta
+
+
+class _EmbedFn(torch.autograd.Function):
+    """emb = vmap(pe_model)(pe_param, pe_buffer, pcs) with the gradient of the trainable direction matrix."""
+
+    @staticmethod
+    def forward(ctx, pcs, theta, scale, B):
+        ctx.set_materialize_grads(False)
+        emb = embed(theta, pcs, scale)
+        ctx.save_for_backward(pcs, theta)
+        ctx.scale = float(scale)
+        return emb
+
+    @staticmethod
+    def backward(ctx, d_emb):
+        if d_emb is None:
+            return None, None, None, None
+        pcs, theta = ctx.saved_tensors
+        n = theta.shape[0]
+        x = pcs.reshape(n, -1, 3).contiguous().float()
+        m = x.shape[1]
+        de = d_emb.reshape(n, m, 129).contiguous().float()
+        L = lib()
+        d_B = torch.empty(n, 21, 3, dtype=torch.float32, device=theta.device)
+        ws = torch.empty(L.oo_embed_bwd_ws_floats(n, m), dtype=torch.float32, device=theta.device)
+        with _dev(theta):
+            check(L.oo_embed_bwd(ptr(theta), n, ptr(x), m, ctx.scale, ptr(de), ptr(d_B), ptr(ws), stream()), "oo_embed_bwd")
+        return None, None, None, d_B
+
+
+class _FcFn(torch.autograd.Function):
+    """alpha, color, clip = vmap(fc_model)(fc_param, fc_buffer, emb) with gradients of the 18 stacked tensors and of emb."""
+
+    @staticmethod
+    def forward(ctx, emb, theta, want_clip, *params):
+        ctx.set_materialize_grads(False)          # an output no loss term uses must leave its tensors with grad None
+        a, c, f, _ = forward(theta, emb=emb, want_clip=want_clip)
+        ctx.save_for_backward(emb, theta)
+        ctx.want_clip = want_clip
+        if f is None:
+            return a, c
+        return a, c, f
+
+    @staticmethod
+    def backward(ctx, d_alpha, d_color, d_clip=None):
+        emb, theta = ctx.saved_tensors
+        n = theta.shape[0]
+        e = emb.reshape(n, -1, 129).contiguous().float()
+        m = e.shape[1]
+        dev = theta.device
+        da = (torch.zeros(n, m, device=dev) if d_alpha is None else d_alpha.reshape(n, m).contiguous().float())
+        dc = (torch.zeros(n, m, 3, device=dev) if d_color is None else d_color.reshape(n, m, 3).contiguous().float())
+        dcl = None if (d_clip is None or not ctx.want_clip) else d_clip.reshape(n, m, layout.CLIP).contiguous().float()
+        L = lib()
+        grads = torch.empty(n, layout.PSTRIDE, dtype=torch.float32, device=dev)
+        d_emb = torch.empty(n, m, 129, dtype=torch.float32, device=dev) if ctx.needs_input_grad[0] else None
+        ws = torch.empty(L.oo_forward_bwd_ws_floats(n, m), dtype=torch.float32, device=dev)
+        with _dev(theta):
+            check(L.oo_forward_bwd(ptr(theta), n, ptr(e), m, ptr(da), ptr(dc), ptr(dcl), ptr(grads), ptr(d_emb), ptr(ws),
+                                   stream()), "oo_forward_bwd")
+        gv = layout.views(grads)[:18]
+        # autograd leaves tensors no loss term reaches with grad None (the optimiser then skips them: quirk 8)
+        if d_color is None:
+            gv[10:14] = [None] * 4
+        if dcl is None:
+            gv[14:18] = [None] * 4
+        if d_alpha is None and d_color is None and dcl is None:
+            gv = [None] * 18
+        return (None if d_emb is None else d_emb.view(emb.shape), None, None) + tuple(gv)
+
+
+def embed_autograd(pcs, theta, scale, B):
+    return _EmbedFn.apply(pcs, theta, scale, B)
+
+
+def fc_autograd(emb, theta, want_clip, params):
+    return _FcFn.apply(emb, theta, want_clip, *params)
+
+
+class _WideFn(torch.autograd.Function):
+    """OccupancyMap.forward of a model of another hidden width (the hidden-128 background model called as
+    `fc_occ_map(pe(x))`, train.py:449-450) through the layer-by-layer kernels of oo_bg."""
+
+    @staticmethod
+    def forward(ctx, emb, model, want_clip, *params):
+        ctx.set_materialize_grads(False)
+        model.load(list(params) + [None])
+        a, c, f, _ = model.forward(emb=emb, want_clip=want_clip)
+        ctx.model, ctx.want_clip = model, want_clip
+        ctx.save_for_backward(emb, *params)
+        if f is None:
+            return a, c
+        return a, c, f
+
+    @staticmethod
+    def backward(ctx, d_alpha, d_color, d_clip=None):
+        emb = ctx.saved_tensors[0]
+        params = ctx.saved_tensors[1:]
+        model = ctx.model
+        model.load(list(params) + [None])              # the scratch model may have served another call in between
+        n = emb.reshape(-1, 129).shape[0]
+        dev = emb.device
+        da = torch.zeros(n, device=dev) if d_alpha is None else d_alpha
+        dc = torch.zeros(n, 3, device=dev) if d_color is None else d_color
+        dcl = d_clip if ctx.want_clip else None
+        g, d_emb = model.forward_bwd(None, da, dc, dcl, emb=emb, want_d_emb=ctx.needs_input_grad[0])
+        gv = [v.clone() for v in model.views(g)[:18]]
+        if d_color is None:
+            gv[10:14] = [None] * 4
+        if dcl is None:
+            gv[14:18] = [None] * 4
+        if d_alpha is None and d_color is None and dcl is None:
+            gv = [None] * 18
+        return (None if d_emb is None else d_emb.view(emb.shape), None, None) + tuple(gv)
+
+
+def wide_autograd(emb, model, want_clip, params):
+    return _WideFn.apply(emb, model, want_clip, *params)
+
+
 def eval_points(theta, points, scale=2.0, want_clip=True):
     """Trainer.eval_points for ONE hidden-32 model (trainer.py:104-128): theta [1,PSTRIDE] (or [PSTRIDE]), points [n,3].
     Returns occ [n] = sigmoid(alpha), color [n,3], clip [n,512] or None -- one launch for the whole query."""
@@ -119,6 +268,13 @@ class _StepLoss(torch.autograd.Function):
     def backward(ctx, g_loss, _g_terms, _g_flags):
         alpha_c, color_c, z, gt_depth, gt_color, labels, pred_feat, gt_feat, flags, ws = ctx.saved_tensors
         n, r, s, cf, cs, os_, fs, a_shape, c_shape = ctx.dims
+        # reduce_batch_loss returns constant zeros for a term with an empty mask (render_rays.py:89-94): the inputs only such
+        # terms reach get no gradient at all (None), which is what lets the optimiser skip their tensors.  The reference pays
+        # the same host sync here (`.any()` in a Python `if`).
+        f = int(flags.item())
+        no_obj, no_sem = bool(f & 2), bool(f & 4)
+        if no_obj and no_sem:
+            return (None,) * 11
         d_alpha = torch.empty_like(alpha_c)
         d_color = torch.empty_like(color_c)
         d_pred = torch.empty_like(pred_feat) if pred_feat is not None else None
@@ -126,7 +282,8 @@ class _StepLoss(torch.autograd.Function):
             check(lib().oo_loss_bwd(ptr(alpha_c), ptr(color_c), ptr(z), ptr(gt_depth), ptr(gt_color), ptr(labels),
                                     ptr(pred_feat), ptr(gt_feat), n, r, s, cf, cs, os_, fs, float(g_loss), ptr(flags),
                                     ptr(ws), ptr(d_alpha), ptr(d_color), ptr(d_pred), stream()), "oo_loss_bwd")
-        return (d_alpha.view(a_shape), d_color.view(c_shape), None, None, None, None, d_pred, None, None, None, None)
+        return (d_alpha.view(a_shape), None if no_obj else d_color.view(c_shape), None, None, None, None,
+                None if no_obj else d_pred, None, None, None, None)
 
 
 def step_loss(alpha, color, gt_depth, gt_color, labels, z, pred_feat=None, gt_feat=None,

@@ -7,9 +7,28 @@ from typing import Optional
 import torch
 
 from . import ops
-from ._lib import AppendArgs, SampleArgs, check, lib, ptr, stream
+from ._lib import SampleArgs, check, lib, ptr, stream
 
-KF_MAX = 20
+_LIN = {}
+_SCRATCH = {}
+
+
+def _lin_tables(S, n_c2s, n_bins):
+    key = (S, n_c2s, n_bins)
+    if key not in _LIN:
+        _LIN[key] = [torch_linspace01(S), torch_linspace01(n_c2s), torch_linspace01(n_bins)]
+    return _LIN[key]
+
+
+def _scratch(dev, n_ints):
+    """Caller-owned scratch of the counter-RNG path (per-object batch maximum + invalid-depth ray lists), one per device and
+    stream; the library allocates nothing."""
+    key = (str(dev), torch.cuda.current_stream(dev).cuda_stream)
+    t = _SCRATCH.get(key)
+    if t is None or t.numel() < n_ints:
+        t = torch.empty(max(int(n_ints), 1 << 20), dtype=torch.int32, device=dev)
+        _SCRATCH[key] = t
+    return t
 
 
 def torch_linspace01(n):
@@ -106,11 +125,13 @@ class RingTables:
 
 def sample(rgbs, depth, t_wc, bbox, part_frame, rays_dir, tapes, n_frames, n_samples, n_c2s=1, n_bins=9,
            eps=0.1, other_eps=0.05, min_bound=0.0, part_down=0, part_hw=(0, 0), want_pix=False, out: SampleOut = None,
-           tables: RingTables = None):
-    """rgbs/depth/t_wc/bbox: lists (one per object) of the keyframe ring tensors in the reference layout
-    (u8 [KF,W,H,4], f32 [KF,W,H], f32 [KF,4,4], f32 [KF,4]), or `tables`; part_frame int32 [n_obj,20] or None;
-    tapes: SampleTapes (explicit draws) or CounterRng (draws generated in the kernel)."""
-    n = tables.n if tables is not None else len(rgbs)
+           tables: RingTables = None, store=None, slot_frame=None, slot_bbox=None, kf_cap=20, obj_ids=None):
+    """Keyframes come either from private per-object rings -- rgbs/depth/t_wc/bbox: lists (one per object) of the ring tensors
+    in the reference layout (u8 [KF,W,H,4], f32 [KF,W,H], f32 [KF,4,4], f32 [KF,4]), or `tables` -- or from a shared
+    `store` (framestore.FrameStore) with slot_frame int32 [n_obj,kf_cap] and slot_bbox f32 [n_obj,kf_cap,4] on the device.
+    part_frame int32 [n_obj,kf_cap] or None; tapes: SampleTapes (explicit draws) or CounterRng (draws generated in the
+    kernel); obj_ids int32 [n_obj] (device): needed with a store and tapes (the pixel state is derived from the id)."""
+    n = slot_frame.shape[0] if store is not None else (tables.n if tables is not None else len(rgbs))
     dev = rays_dir.device
     W, H = rays_dir.shape[:2]
     n_rays = n_frames * n_samples
@@ -123,27 +144,38 @@ def sample(rgbs, depth, t_wc, bbox, part_frame, rays_dir, tapes, n_frames, n_sam
                         torch.empty(n, n_rays, dtype=torch.int32, device=dev) if part_frame is not None else None,
                         torch.empty(n, n_rays, 3, dtype=torch.int64, device=dev) if want_pix else None,
                         torch.zeros(1, dtype=torch.int32, device=dev))
-    tabs = ([tables.rgbs, tables.depth, tables.t_wc, tables.bbox] if tables is not None
-            else [_ptr_table(x, dev) for x in (rgbs, depth, t_wc, bbox)])
-    lin = [torch_linspace01(S), torch_linspace01(n_c2s), torch_linspace01(n_bins)]
+    lin = _lin_tables(S, n_c2s, n_bins)
     a = SampleArgs()
     a.n_obj, a.n_frames, a.n_samples = n, n_frames, n_samples
     a.W, a.H, a.n_c2s, a.n_bins = W, H, n_c2s, n_bins
     a.eps, a.other_eps, a.min_bound = eps, other_eps, min_bound
     a.part_down, a.pw, a.ph = int(part_down), int(part_hw[0]), int(part_hw[1])
-    a.rgbs, a.depth, a.t_wc, a.bbox = [ptr(t) for t in tabs]
+    a.kf_cap = int(kf_cap)
+    if store is not None:
+        assert slot_frame.shape == (n, kf_cap) and slot_bbox.shape == (n, kf_cap, 4)
+        a.store_rgbi, a.store_depth, a.store_twc = ptr(store.rgbi), ptr(store.depth), ptr(store.t_wc)
+        a.slot_frame, a.slot_bbox = ptr(slot_frame), ptr(slot_bbox)
+    else:
+        tabs = ([tables.rgbs, tables.depth, tables.t_wc, tables.bbox] if tables is not None
+                else [_ptr_table(x, dev) for x in (rgbs, depth, t_wc, bbox)])
+        a.rgbs, a.depth, a.t_wc, a.bbox = [ptr(t) for t in tabs]
+    assert part_frame is None or tuple(part_frame.shape) == (n, kf_cap), "part_frame must be [n_obj, kf_cap]"
     a.part_frame = ptr(part_frame)
     a.rays_dir = ptr(rays_dir)
     if isinstance(tapes, CounterRng):
         a.rng_mode, a.seed, a.frame = 1, int(tapes.seed), int(tapes.frame)
         a.obj_ids, a.n_keyframes, a.latest = ptr(tapes.obj_ids), ptr(tapes.n_keyframes), ptr(tapes.latest)
         a.tape_by_rank = 0
+        need = n * (2 + 2 * n_rays)
+        scr = _scratch(dev, need)
+        a.scratch, a.scratch_ints = ptr(scr), scr.numel()
     else:
         a.rng_mode = 0
         a.kf_ids, a.u_w, a.u_h = ptr(tapes.kf_ids), ptr(tapes.u_w), ptr(tapes.u_h)
         a.r_invalid, a.r_valid, a.r_normal, a.r_other = (ptr(tapes.r_invalid), ptr(tapes.r_valid), ptr(tapes.r_normal),
                                                          ptr(tapes.r_other))
         a.tape_by_rank = int(tapes.by_rank)
+        a.obj_ids = ptr(obj_ids)
     a.lin_s_host, a.lin_c2s_host, a.lin_bins_host = [ctypes.c_void_p(t.data_ptr()) for t in lin]
     a.gt_rgb, a.gt_depth, a.valid, a.labels = ptr(out.gt_rgb), ptr(out.gt_depth), ptr(out.valid), ptr(out.labels)
     a.pcs, a.z, a.feat_row, a.pix, a.oob_count = ptr(out.pcs), ptr(out.z), ptr(out.feat_row), ptr(out.pix), ptr(out.oob)
@@ -160,25 +192,3 @@ def counter_rng(objects, seed, frame, device):
     pack = torch.cat([ids, nkf, latest.reshape(-1)]).to(device, non_blocking=True)     # one H2D copy
     n = len(objects)
     return CounterRng(seed, frame, pack[:n], pack[n:2 * n], pack[2 * n:].view(n, 2))
-
-
-def append_frame(rgb, depth, inst, t_wc, objects, slots, bboxes):
-    """One launch writes the new frame into ring slot slots[i] of objects[i] (rgb + per-object pixel state, depth,
-    pose, bbox).  rgb u8 [W,H,3], depth f32 [W,H], inst int32 [W,H], t_wc f32 [4,4] on the device; bboxes: list of
-    4-vectors (host)."""
-    dev = rgb.device
-    n = len(objects)
-    if n == 0:
-        return
-    W, H = depth.shape
-    ints = torch.tensor([[o.obj_id for o in objects], slots], dtype=torch.int32).to(dev, non_blocking=True)
-    bb = torch.stack([torch.as_tensor(b, dtype=torch.float32) for b in bboxes]).to(dev, non_blocking=True).contiguous()
-    tab = RingTables(objects, dev)
-    t = t_wc.to(torch.float32).contiguous()
-    a = AppendArgs()
-    a.W, a.H, a.n_obj = W, H, n
-    a.rgb, a.depth, a.inst, a.t_wc = ptr(rgb), ptr(depth), ptr(inst), ptr(t)
-    a.obj_id, a.slot, a.bbox = ptr(ints[0]), ptr(ints[1]), ptr(bb)
-    a.rgbs, a.depth_ring, a.t_wc_ring, a.bbox_ring = ptr(tab.rgbs), ptr(tab.depth), ptr(tab.t_wc), ptr(tab.bbox)
-    with torch.cuda.device(dev):
-        check(lib().oo_append_frame(ctypes.byref(a), stream()), "oo_append_frame")

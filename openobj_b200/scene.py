@@ -1,43 +1,120 @@
-"""Per-frame driver of the accelerated path: the body of objnerf/train.py:158-485 for the vmap strategy, with the
-Python object loop replaced by three batched launches per frame (append is still per object in round 1):
+"""Per-frame driver of the accelerated path: the body of objnerf/train.py:158-485 for the vmap strategy.
 
-    add_frame   (train.py:164-256)  H2D, per-object pixel state, keyframe rings, new objects -> ensemble rebuild
+    add_frame   (train.py:164-276)  one launch stores the frame ONCE in the shared keyframe store (framestore.py); the
+                                    keyframe policy of every visible local object updates a slot table (host integers);
+                                    new objects -> ensemble rebuild; one small H2D copy carries all per-frame tables
     sample      (train.py:300-388)  K2 for all local objects in one launch, no [N,12000,512] feature copy
-    train       (train.py:394-474)  100 x (K1 + K4)
+    train       (train.py:394-474)  iters x (K1 + K4)
     write-back  (train.py:478-485)  not needed: every object's nn.Parameters are views of the ensemble buffer
 
-Objects are sharded by ensemble index k (order of first appearance): rank = k % world; ranks share
-nothing but the per-step zero-mask flags, OR-reduced once per frame."""
+Objects are sharded by ensemble index k (order of first appearance): rank = k % world.  Ranks share two things
+only: (1) the per-step zero-mask bits, OR-reduced once per frame; (2) the fact that ANY new object restarts Adam's moments
+and step counts for every object (the reference restacks all models into fresh tensors on update_vmap, train.py:272-276) --
+every rank sees every frame's object ids, so each applies that reset locally without communication."""
+import numpy as np
 import torch
 
-from . import layout, sampler, vmap
+from . import sampler, vmap
 from .background import BackgroundModel
+from .dist import ShardBook
 from .ensemble import Ensemble, FrameBatch
+from .framestore import FrameStore
+
+
+class _Tables:
+    """Per-object integer / float tables K2 reads (slot -> store frame, slot bbox, slot part-feature frame, keyframe count,
+    latest two keyframes, object id) + the new frame's pose: ONE pinned block, ONE async H2D copy per frame.  A ring of
+    staging blocks lets the host run ahead of the device."""
+    N_STAGE = 4
+
+    def __init__(self, cap, kf, device):
+        self.cap, self.kf, self.device = cap, kf, device
+        per = kf * 6 + 4                              # slot_frame kf, bbox 4 kf, part_frame kf, n_kf 1, latest 2, obj_id 1
+        self.words = cap * per + 16
+        self.master = np.zeros(self.words, dtype=np.int32)
+        o = 0
+        def take(n, shape, dtype=np.int32):
+            nonlocal o
+            v = self.master[o:o + n].view(dtype).reshape(shape)
+            o += n
+            return v
+        self.slot_frame = take(cap * kf, (cap, kf)); self.slot_frame[:] = -1
+        self.slot_bbox = take(cap * kf * 4, (cap, kf, 4), np.float32)
+        self.part_frame = take(cap * kf, (cap, kf))
+        self.n_kf = take(cap, (cap,))
+        self.latest = take(cap * 2, (cap, 2))
+        self.obj_id = take(cap, (cap,))
+        self.t_wc = take(16, (16,), np.float32)
+        self.stage = [torch.zeros(self.words, dtype=torch.int32).pin_memory() for _ in range(self.N_STAGE)]
+        self.stage_np = [s.numpy() for s in self.stage]
+        self.events = [None] * self.N_STAGE
+        self.k = 0
+        self.dev = torch.zeros(self.words, dtype=torch.int32, device=device)
+        d, o = self.dev, 0
+        def dtake(n, shape, dtype=torch.int32):
+            nonlocal o
+            v = d[o:o + n].view(dtype).view(shape)
+            o += n
+            return v
+        self.d_slot_frame = dtake(cap * kf, (cap, kf))
+        self.d_slot_bbox = dtake(cap * kf * 4, (cap, kf, 4), torch.float32)
+        self.d_part_frame = dtake(cap * kf, (cap, kf))
+        self.d_n_kf = dtake(cap, (cap,))
+        self.d_latest = dtake(cap * 2, (cap, 2))
+        self.d_obj_id = dtake(cap, (cap,))
+        self.d_t_wc = dtake(16, (16,), torch.float32)
+
+    def upload(self):
+        k = self.k
+        self.k = (k + 1) % self.N_STAGE
+        if self.events[k] is not None:
+            self.events[k].synchronize()           # the copy that last read this staging block has run
+        self.stage_np[k][:] = self.master
+        self.dev.copy_(self.stage[k], non_blocking=True)
+        ev = torch.cuda.Event()
+        ev.record()
+        self.events[k] = ev
 
 
 class Scene:
-    def __init__(self, cfg, rank=0, world=1, seed=0, max_frames=64, n_sm=None, flag_allreduce=None):
+    def __init__(self, cfg, rank=0, world=1, seed=0, max_frames=64, n_sm=None, flag_allreduce=None, store_capacity=32,
+                 init_seed=None):
+        """init_seed: None = new objects draw their initial weights from torch's global generator in creation order, exactly
+        like the reference (trainer.py:43, model.py:4-6).  A sharded run (world > 1) defaults to init_seed = seed: every
+        object's initial weights are then drawn from a generator keyed by (init_seed, object id), so they do not depend on
+        which rank creates the object or on how many ranks there are."""
         self.cfg, self.rank, self.world, self.seed = cfg, rank, world, seed
+        self.init_seed = init_seed if init_seed is not None else (seed if world > 1 else None)
         self.device = torch.device(cfg.training_device)
         self.cam = vmap.cameraInfo(cfg)
         self.obj_dict = {}            # local objects, insertion order == local ensemble index
-        self.global_index = {}        # obj id -> global ensemble index k (all ranks agree)
+        self.book = ShardBook(rank, world, cfg.max_n_models)
+        self.global_index = self.book.global_index        # obj id -> global ensemble index k (all ranks agree)
         self.ens = None
         self.n_sm = n_sm
         self.flag_allreduce = flag_allreduce
         self.frames_seen = 0
         self.part_mode = cfg.part_mode
         self.part_table = None
+        self.pw = self.ph = 0
         if self.part_mode:
             self.pw, self.ph = cfg.W // cfg.part_down, cfg.H // cfg.part_down
             self.part_table = torch.empty(max_frames, self.pw, self.ph, cfg.clip_point_feature_size,
                                           dtype=torch.float32, device=self.device)
+        self.kf = cfg.keyframe_buffer_size
+        self.store = FrameStore(cfg.W, cfg.H, self.device, capacity=store_capacity)
+        self.tab = _Tables(max((int(cfg.max_n_models) + world - 1) // world, 1), self.kf, self.device)
+        self._objs = []
+        self.tab_bg = None
         self._stale = False
         self.batch = None
+        self.sample_out = None
+        self._copy_stream = None
+        self._sorted_ids = (None, None)
+        self._empty_bits = None
         # the separate background model (train.py:236-242): one hidden-128 model, not part of the vmap ensemble; it lives
         # on the last rank (the ensemble's round-robin starts at rank 0)
-        self._copy_stream = None
-        self.scene_bg, self.bg, self.bg_batch, self.bg_tables = None, None, None, None
+        self.scene_bg, self.bg, self.bg_batch, self.bg_sample_out = None, None, None, None
         self.bg_rank = world - 1
 
     # ---- host -> device staging of the NEXT frame on a copy stream (what a DataLoader with pin_memory + non_blocking
@@ -49,7 +126,7 @@ class Scene:
             self._copy_stream = torch.cuda.Stream(device=self.device)
         out = dict(sample)
         with torch.cuda.stream(self._copy_stream):
-            for k in ("image", "depth", "obj", "T", "part_feat"):
+            for k in ("image", "depth", "obj", "part_feat"):
                 v = sample.get(k)
                 if torch.is_tensor(v) and v.device != self.device:
                     out[k] = v.to(self.device, non_blocking=True)
@@ -58,68 +135,117 @@ class Scene:
         out["_staged"] = ev
         return out
 
-    # ---- train.py:164-256 ---------------------------------------------------------------------------------
+    def _ids_of(self, bbox_dict):
+        """Sorted instance ids of a frame (torch.unique order, train.py:191); cached while the same dict object comes back."""
+        if self._sorted_ids[0] is not bbox_dict:
+            self._sorted_ids = (bbox_dict, sorted(int(k) for k in bbox_dict.keys()))
+        return self._sorted_ids[1]
+
+    def _place(self, tab, i, o, slot, store_slot, bbox, frame_id):
+        """Ring slot `slot` of local object i now holds store frame `store_slot`."""
+        old = int(tab.slot_frame[i, slot])
+        if old >= 0:
+            self.store.release(old)
+        self.store.acquire(store_slot)
+        tab.slot_frame[i, slot] = store_slot
+        tab.slot_bbox[i, slot] = bbox
+        if self.part_mode:
+            tab.part_frame[i, slot] = int(frame_id / o.stride)             # (use_frame / stride).long(), vmap.py:438-440
+        tab.n_kf[i] = o.ring.n_keyframes
+        lat = o.ring.latest
+        if len(lat) >= 2:
+            tab.latest[i, 0], tab.latest[i, 1] = lat[-2], lat[-1]
+
+    # ---- train.py:164-276 ---------------------------------------------------------------------------------
     def add_frame(self, sample):
         cfg, dev = self.cfg, self.device
         nb = dict(non_blocking=True)
         if "_staged" in sample:
             cur = torch.cuda.current_stream(dev)
             cur.wait_event(sample["_staged"])
-            for k in ("image", "depth", "obj", "T", "part_feat"):     # allocated on the copy stream, consumed on this one
+            for k in ("image", "depth", "obj", "part_feat"):     # allocated on the copy stream, consumed on this one
                 if torch.is_tensor(sample.get(k)) and sample[k].is_cuda:
                     sample[k].record_stream(cur)
         rgb, depth = sample["image"].to(dev, **nb), sample["depth"].to(dev, **nb)
         inst = sample["obj"].to(dev, **nb)
-        twc = sample["T"].to(dev, **nb)
         frame_id = sample.get("frame_id", self.frames_seen)
         if self.part_mode:
             if self.frames_seen >= self.part_table.shape[0]:
                 raise RuntimeError("part-feature table full: raise max_frames")
             self.part_table[self.frames_seen].copy_(sample["part_feat"], non_blocking=True)   # train.py:183-188
-        twc32 = twc.to(torch.float32)
-        objs, slots, bboxes = [], [], []
-        for obj_id in sorted(int(k) for k in sample["bbox_dict"].keys()):                 # torch.unique order (train.py:191)
+        twc = sample["T"]
+        twc32 = (twc.detach().cpu() if torch.is_tensor(twc) else torch.as_tensor(np.asarray(twc))).to(torch.float32).reshape(16)
+        bd = sample["bbox_dict"]
+        obj_clip, obj_cap = sample.get("obj_clip"), sample.get("obj_cap")
+        placed = []                   # (tab, local index, object, ring slot, bbox)
+        new_global = False
+        for obj_id in self._ids_of(bd):
             if obj_id == -1:
                 continue
             if cfg.do_bg and obj_id == 0:
                 # the separate background model is not part of the vmap ensemble (train.py:236-242)
                 if self.rank != self.bg_rank:
                     continue
-                bbox = sample["bbox_dict"][obj_id]
                 if self.scene_bg is None:
-                    self.scene_bg = vmap.sceneObject(cfg, 0, rgb, depth, None, bbox, twc, frame_id, defer_write=True)
+                    if self.book.full():
+                        continue       # "models full" is tested before the background branch (train.py:231-236)
+                    self.scene_bg = vmap.sceneObject(cfg, 0, rgb, depth, None, bd[obj_id], twc32.view(4, 4), frame_id, shared=True,
+                                                     clip_feat=_first(obj_clip, obj_id), caption_feat=_get(obj_cap, obj_id))
                     self.bg = BackgroundModel(hidden=cfg.hidden_feature_size_bg, device=self.device,
                                               rays_per_step=cfg.n_per_optim_bg,
                                               n_samp=self.scene_bg.n_bins_cam2surface + self.scene_bg.n_bins,
                                               lr=cfg.learning_rate, weight_decay=cfg.weight_decay, scale=cfg.bg_scale)
                     self.bg.adopt(self.scene_bg.trainer.fc_occ_map, self.scene_bg.trainer.pe)
-                    self.bg_tables = sampler.RingTables([self.scene_bg], self.device)
+                    self.tab_bg = _Tables(1, self.kf, self.device)
+                    self.tab_bg.obj_id[0] = 0
                     slot = 0
                 else:
-                    slot = self.scene_bg.push_slot(frame_id)
-                objs.append(self.scene_bg); slots.append(slot); bboxes.append(bbox)
+                    slot = self.scene_bg.push_slot(frame_id, _first(obj_clip, obj_id), _get(obj_cap, obj_id))
+                placed.append((self.tab_bg, 0, self.scene_bg, slot, bd[obj_id]))
                 continue
-            if obj_id not in self.global_index:
-                if len(self.global_index) >= cfg.max_n_models * self.world:
-                    continue           # "models full" (train.py:231-233)
-                self.global_index[obj_id] = len(self.global_index)
-            if self.global_index[obj_id] % self.world != self.rank:
-                continue
-            bbox = sample["bbox_dict"][obj_id]
-            if obj_id in self.obj_dict:
-                o = self.obj_dict[obj_id]
-                slot = o.push_slot(frame_id)
-            else:
-                o = vmap.sceneObject(cfg, obj_id, rgb, depth, None, bbox, twc, frame_id, defer_write=True)
+            seen = self.book.see(obj_id)
+            if seen is None:
+                continue               # "models full" (train.py:231-233): the cap is global, whatever the number of ranks
+            k, i, new = seen
+            new_global |= new
+            if i is None:
+                continue               # another rank's object
+            if new:
+                o = self._new_object(obj_id, rgb, depth, bd[obj_id], twc32, frame_id, obj_clip, obj_cap)
+                assert i == len(self.obj_dict)
                 self.obj_dict[obj_id] = o
+                self.tab.obj_id[i] = obj_id
                 slot = 0
                 self._stale = True
-            objs.append(o); slots.append(slot); bboxes.append(bbox)
-        # pixel state (train.py:203-205) + ring writes of every visible object in ONE launch
-        sampler.append_frame(rgb, depth, inst, twc32, objs, slots, bboxes)
+            else:
+                o = self._objs[i]
+                slot = o.push_slot(frame_id, _first(obj_clip, obj_id), _get(obj_cap, obj_id))
+            placed.append((self.tab, i, o, slot, bd[obj_id]))
+        self._objs = list(self.obj_dict.values())
+        # ---- the frame itself: ONE copy in the shared store (12 bytes per pixel whatever the number of objects)
+        self.tab.t_wc[:] = twc32.numpy()
+        g = self.store.alloc() if placed else -1
+        for tab, i, o, slot, bbox in placed:
+            self._place(tab, i, o, slot, g, np.asarray(bbox, dtype=np.float32), frame_id)
+        self.tab.upload()                                          # slot tables + the pose the store kernel reads
+        if self.tab_bg is not None:
+            self.tab_bg.upload()
+        if placed:
+            self.store.write(g, rgb, depth, inst, self.tab.d_t_wc)
         self.frames_seen += 1
         if self._stale:
             self._rebuild_ensemble()
+        elif new_global and self.ens is not None:
+            self.ens.reset_optimizer()     # another rank's new object: the reference restacks everything (quirk 7)
+
+    def _new_object(self, obj_id, rgb, depth, bbox, twc32, frame_id, obj_clip, obj_cap):
+        mk = lambda: vmap.sceneObject(self.cfg, obj_id, rgb, depth, None, bbox, twc32.view(4, 4), frame_id, shared=True,   # noqa: E731
+                                      clip_feat=_first(obj_clip, obj_id), caption_feat=_get(obj_cap, obj_id))
+        if self.init_seed is None:
+            return mk()
+        with torch.random.fork_rng(devices=[self.device]):
+            torch.manual_seed((int(self.init_seed) * 1000003 + int(obj_id)) % (2 ** 63 - 1))
+            return mk()
 
     # ---- utils.update_vmap (train.py:272-276): restack, Adam state restarts ---------------------------------
     def _rebuild_ensemble(self):
@@ -134,48 +260,37 @@ class Scene:
                 for v, p in zip(views, ps):
                     v[k].copy_(p.detach())
                     p.data = v[k]      # the module now aliases the ensemble buffer: write-back (train.py:478-485) is free
-        new.params_changed()
         new.reset_optimizer()
+        if self.ens is not None:
+            self.ens.check_explode(wait=True)
         self.ens = new
-        self.tables = sampler.RingTables(objs, self.device)
         self._stale = False
 
     # ---- train.py:300-388 -----------------------------------------------------------------------------------
+    def _sample(self, tab, n, obj0, n_frames, n_samples, out):
+        cfg = self.cfg
+        rng = sampler.CounterRng(self.seed, self.frames_seen, tab.d_obj_id[:n], tab.d_n_kf[:n], tab.d_latest[:n])
+        return sampler.sample(None, None, None, None, tab.d_part_frame[:n] if self.part_mode else None, self.cam.rays_dir_cache,
+                              rng, n_frames, n_samples, obj0.n_bins_cam2surface, obj0.n_bins, obj0.surface_eps, obj0.stop_eps,
+                              obj0.min_bound, cfg.part_down if self.part_mode else 0, (self.pw, self.ph), out=out,
+                              store=self.store, slot_frame=tab.d_slot_frame[:n], slot_bbox=tab.d_slot_bbox[:n], kf_cap=self.kf)
+
     def sample(self):
         cfg = self.cfg
-        objs = list(self.obj_dict.values())
-        n_frames = cfg.n_iter_per_frame * cfg.win_size
-        n_samples = cfg.n_samples_per_frame
-        o0 = objs[0]
-        rng = sampler.counter_rng(objs, self.seed, self.frames_seen, self.device)
-        part_frame = None
-        if self.part_mode:
-            import numpy as np
-            pf = np.stack([(o.use_frame / o.stride).astype(np.int64) for o in objs]).astype(np.int32)   # vmap.py:438-440
-            part_frame = torch.from_numpy(pf).to(self.device, non_blocking=True)
-        out = sampler.sample(None, None, None, None, part_frame, self.cam.rays_dir_cache, rng, n_frames, n_samples,
-                             o0.n_bins_cam2surface, o0.n_bins, o0.surface_eps, o0.stop_eps, o0.min_bound,
-                             cfg.part_down if self.part_mode else 0, (self.pw, self.ph) if self.part_mode else (0, 0),
-                             out=getattr(self, "sample_out", None) if getattr(self, "_out_n", -1) == len(objs) else None,
-                             tables=self.tables)
-        self._out_n = len(objs)
+        objs = self._objs if self.obj_dict else []
         table = self.part_table.view(-1, self.part_table.shape[-1]) if self.part_mode else None
-        self.batch = FrameBatch(out.pcs, out.z, out.gt_depth, out.gt_rgb, out.labels, out.feat_row, table)
-        self.sample_out = out
+        if objs:
+            out = self.sample_out if (self.sample_out is not None and self.sample_out.labels.shape[0] == len(objs)) else None
+            out = self._sample(self.tab, len(objs), objs[0], cfg.n_iter_per_frame * cfg.win_size, cfg.n_samples_per_frame, out)
+            self.sample_out = out
+            self.batch = FrameBatch(out.pcs, out.z, out.gt_depth, out.gt_rgb, out.labels, out.feat_row, table)
+        else:
+            self.batch = None                       # this rank owns no object (yet)
         if self.scene_bg is not None:
             # train.py:300-315: the background draws n_iter_per_frame * win_size_bg keyframes x n_samples_per_frame_bg
             # pixels with 5 + 9 samples per ray
-            b = self.scene_bg
-            rng_bg = sampler.counter_rng([b], self.seed, self.frames_seen, self.device)
-            pf_bg = None
-            if self.part_mode:
-                import numpy as np
-                pf_bg = torch.from_numpy((b.use_frame / b.stride).astype(np.int64).astype(np.int32)[None]).to(self.device, non_blocking=True)
-            ob = sampler.sample(None, None, None, None, pf_bg, self.cam.rays_dir_cache, rng_bg,
-                                cfg.n_iter_per_frame * cfg.win_size_bg, cfg.n_samples_per_frame_bg, b.n_bins_cam2surface,
-                                b.n_bins, b.surface_eps, b.stop_eps, b.min_bound, cfg.part_down if self.part_mode else 0,
-                                (self.pw, self.ph) if self.part_mode else (0, 0), out=getattr(self, "bg_sample_out", None),
-                                tables=self.bg_tables)
+            ob = self._sample(self.tab_bg, 1, self.scene_bg, cfg.n_iter_per_frame * cfg.win_size_bg, cfg.n_samples_per_frame_bg,
+                              self.bg_sample_out)
             self.bg_sample_out = ob
             self.bg_batch = FrameBatch(ob.pcs, ob.z, ob.gt_depth, ob.gt_rgb, ob.labels, ob.feat_row, table)
         return self.batch
@@ -185,11 +300,37 @@ class Scene:
         """loss_terms [iters, N, 4] (optional) receives the ensemble's per-object terms; bg_loss [iters] the background's
         scalar loss of each step (the reference adds it to the same scalar, train.py:463: the two problems share no
         tensor, so they are trained as two independent launch sequences)."""
-        self.ens.train_frame(self.batch, iters=iters, loss_terms=loss_terms, flag_allreduce=self.flag_allreduce)
+        iters = int(iters or self.cfg.n_iter_per_frame)
+        if self.batch is not None:
+            self.ens.train_frame(self.batch, iters=iters, loss_terms=loss_terms, flag_allreduce=self.flag_allreduce)
+        elif self.flag_allreduce is not None:
+            # no local object: still join this frame's all-reduce of the zero-mask bits, with nothing to report
+            if self._empty_bits is None or self._empty_bits.shape[0] < iters:
+                self._empty_bits = torch.zeros(max(iters, self.cfg.n_iter_per_frame), 2, dtype=torch.int32, device=self.device)
+            self._empty_bits.zero_()
+            self.flag_allreduce(self._empty_bits[:iters])
         if self.bg is not None and self.bg_batch is not None:
-            self.bg.train_frame(self.bg_batch, iters=iters or self.cfg.n_iter_per_frame, loss_out=bg_loss)
+            self.bg.train_frame(self.bg_batch, iters=iters, loss_out=bg_loss)
 
     def step_frame(self, sample, iters=None, loss_terms=None):
         self.add_frame(sample)
         self.sample()
         self.train(iters, loss_terms)
+
+    def finish(self):
+        """End of the run: look at the last frame's explode flag."""
+        if self.ens is not None:
+            self.ens.check_explode(wait=True)
+
+
+def _first(d, k):
+    """obj_clip[obj_id][0] (train.py:221), tolerant of frames that carry no semantic features."""
+    if d is None or k not in d:
+        return None
+    return d[k][0]
+
+
+def _get(d, k):
+    if d is None or k not in d:
+        return None
+    return d[k]

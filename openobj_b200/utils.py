@@ -10,7 +10,6 @@ import numpy as np
 import torch
 
 from . import layout, ops
-from .ensemble import Ensemble
 
 
 class performance_measure:
@@ -48,55 +47,58 @@ def enlarge_bbox(bbox, scale, w, h):
 
 
 class EnsembleFn:
-    """What update_vmap returns as `fmodel`: calling convention fmodel(params, buffers, x) on ONE object's slice is
-    what functorch would vmap; `vmap(fmodel)` below maps it over the stacked dimension in one kernel launch."""
+    """What update_vmap returns as `fmodel` (functorch's FunctionalModuleWithBuffers in the reference): `vmap(fmodel)` maps it
+    over the stacked dimension in one kernel launch.  Holds the stacked parameter block the views in `params` alias."""
 
-    def __init__(self, ensemble, kind):
-        self.ensemble, self.kind = ensemble, kind
-
-
-_current = {}
+    def __init__(self, kind, theta, scale):
+        self.kind, self.theta, self.scale = kind, theta, scale
 
 
-def update_vmap(models, optimiser=None, rays_per_step=120, iters_per_frame=100):
-    """utils.py:55-62: stack N modules.  Called once with the OccupancyMap list and once with the UniDirsEmbed list
-    (train.py:274-275); both calls address the same Ensemble (one theta buffer).  Adam state restarts (quirk 7)."""
+def update_vmap(models, optimiser=None):
+    """utils.py:55-62: stack N modules into `(fmodel, params, buffers)`; params require grad and join `optimiser` as a NEW
+    parameter group (so Adam's moments and step counts restart, quirk 7).  Called once with the OccupancyMap list and once
+    with the UniDirsEmbed list (train.py:274-275).  The stacked tensors are strided views of one block theta[N, PSTRIDE]
+    per call; `vmap(fmodel)(params, buffers, x)` is differentiable (oo_forward / oo_forward_bwd / oo_embed_bwd), so the
+    reference's loop body -- step_batch_loss, backward, optimiser.step -- runs unchanged on top of it."""
     n = len(models)
     dev = next(models[0].parameters()).device
+    if dev.type != "cuda":
+        raise RuntimeError("openobj_b200.utils.update_vmap: the models must live on a CUDA device (no CPU fallback)")
     is_pe = hasattr(models[0], "B_layer")
-    ens = _current.get("ens")
-    if ens is None or ens.n_obj != n or (not is_pe and _current.get("fc_done")) or (is_pe and _current.get("pe_done")):
-        scale = float(models[0].scale) if is_pe else 2.0
-        ens = Ensemble(n, device=dev, rays_per_step=rays_per_step, iters_per_frame=iters_per_frame, scale=scale)
-        _current.update(ens=ens, fc_done=False, pe_done=False)
-    views = ens.stacked()
+    theta = torch.zeros(n, layout.PSTRIDE, dtype=torch.float32, device=dev)
+    views = layout.views(theta)
     with torch.no_grad():
         if is_pe:
             views[18].copy_(torch.stack([m.B_layer.weight.detach() for m in models]))
-            ens.scale = float(models[0].scale)
-            _current["pe_done"] = True
             params = (views[18],)
             buffers = (torch.stack([m.frequency_bands for m in models]), torch.stack([m.scale for m in models]))
+            scale = float(models[0].tensor_scale)
         else:
+            for m in models:
+                if not m._supported():
+                    raise NotImplementedError("update_vmap stacks the shipped object model (hidden 32, clip 512); other widths "
+                                              "are single models (OccupancyMap.forward)")
             for i in range(18):
                 views[i].copy_(torch.stack([list(m.parameters())[i].detach() for m in models]))
-            _current["fc_done"] = True
-            params, buffers = tuple(views[:18]), ()
-    ens.params_changed()
-    ens.reset_optimizer()
-    return EnsembleFn(ens, "pe" if is_pe else "fc"), params, buffers
+            params, buffers, scale = tuple(views[:18]), (), None
+    [p.requires_grad_() for p in params]
+    if optimiser is not None:
+        optimiser.add_param_group({"params": params})          # utils.py:61
+    return EnsembleFn("pe" if is_pe else "fc", theta, scale), params, buffers
 
 
 def vmap(fmodel):
     """Call form of train.py:424-425: vmap(pe_model)(pe_param, pe_buffer, pcs) -> embedding [N,...,129];
-    vmap(fc_model)(fc_param, fc_buffer, embedding) -> (alpha, color, clip)."""
-    ens = fmodel.ensemble
+    vmap(fc_model)(fc_param, fc_buffer, embedding) -> (alpha, color, clip).  Differentiable w.r.t. the stacked parameters
+    (and the embedding)."""
 
     def run(params, buffers, x):
+        params = tuple(params)
         if fmodel.kind == "pe":
-            return ops.forward(ens.theta, pcs=x, scale=ens.scale, want_clip=False, want_emb=True)[3]
-        a, c, f, _ = ops.forward(ens.theta, emb=x, scale=ens.scale)
-        return a, c, f
+            theta = ops._as_theta(params, 18, fmodel.theta)
+            return ops.embed_autograd(x, theta, fmodel.scale, params[0])
+        theta = ops._as_theta(params, 0, fmodel.theta)
+        return ops.fc_autograd(x, theta, True, params)
     return run
 
 

@@ -61,11 +61,13 @@ class KeyframeRing:
 
 class sceneObject:
     def __init__(self, cfg, obj_id, rgb, depth, mask, bbox_2d, t_wc, live_frame_id, clip_feat=None, caption_feat=None,
-                 defer_write=False):
-        """`defer_write=True` (used by scene.Scene): allocate the rings but let the batched oo_append_frame launch write
-        slot 0 together with every other object's slot of this frame."""
-        assert rgb.shape[:2] == depth.shape and bbox_2d.shape == (4,) and t_wc.shape == (4, 4)
-        assert defer_write or rgb.shape[:2] == mask.shape
+                 shared=False):
+        """`shared=True` (used by scene.Scene): the object owns NO pixel rings -- its keyframes are slots of the scene's shared
+        frame store (framestore.FrameStore, SURVEY 8f rank 2) and its pixel state is derived from the stored instance map;
+        only the keyframe policy (self.ring) and the semantic features live here."""
+        assert rgb.shape[:2] == depth.shape and tuple(bbox_2d.shape) == (4,) and tuple(t_wc.shape) == (4, 4)
+        assert shared or rgb.shape[:2] == mask.shape
+        defer_write = shared
         self.do_bg, self.obj_id = cfg.do_bg, obj_id
         self.data_device, self.training_device = cfg.data_device, cfg.training_device
         self.part_mode, self.stride = cfg.part_mode, cfg.stride
@@ -83,11 +85,15 @@ class sceneObject:
         self.feat_cnt, self.clip_feat, self.caption_feat = 1, clip_feat, caption_feat
         self.eps_fine_vis, self.n_bins_fine_vis = cfg.eps_fine_vis, cfg.n_bins_fine_vis
         dev, K, W, H = self.data_device, self.keyframe_buffer_size, self.frames_width, self.frames_height
-        self.bbox = torch.empty(K, 4, device=dev)                       # [w_lo, w_hi, h_lo, h_hi] per slot
         self.rgb_idx, self.state_idx = slice(0, 3), slice(3, 4)
-        self.rgbs_batch = torch.empty(K, W, H, 4, dtype=torch.uint8, device=dev)   # rgb + pixel state
-        self.depth_batch = torch.empty(K, W, H, dtype=torch.float32, device=dev)
-        self.t_wc_batch = torch.empty(K, 4, 4, dtype=torch.float32, device=dev)
+        self.shared = bool(shared)
+        if shared:
+            self.bbox = self.rgbs_batch = self.depth_batch = self.t_wc_batch = None
+        else:
+            self.bbox = torch.empty(K, 4, device=dev)                       # [w_lo, w_hi, h_lo, h_hi] per slot
+            self.rgbs_batch = torch.empty(K, W, H, 4, dtype=torch.uint8, device=dev)   # rgb + pixel state
+            self.depth_batch = torch.empty(K, W, H, dtype=torch.float32, device=dev)
+            self.t_wc_batch = torch.empty(K, 4, 4, dtype=torch.float32, device=dev)
         if self.part_mode:
             self.part_down = cfg.part_down
             self.use_frame = np.zeros(K)
@@ -130,12 +136,16 @@ class sceneObject:
             self.caption_feat = np.vstack((self.caption_feat, caption_feat))
             self.feat_cnt += 1
 
-    def push_slot(self, frame_id):
-        """Keyframe policy only (vmap.py:166-257): returns the slot the caller must write (scene.Scene batches the
-        writes of all objects into one oo_append_frame launch)."""
+    def push_slot(self, frame_id, clip_feat=None, caption_feat=None):
+        """Keyframe policy + semantic-feature accumulation of append_keyframe (vmap.py:166-257) without any pixel copy:
+        returns the ring slot the new frame takes (scene.Scene points that slot at the shared frame store)."""
         s = self.ring.push(frame_id)
         if self.part_mode:
             self.use_frame[s] = frame_id
+        if clip_feat is not None and self.clip_feat is not None:
+            self.clip_feat = np.vstack((self.clip_feat, clip_feat))        # vmap.py:241-246
+            self.caption_feat = np.vstack((self.caption_feat, caption_feat))
+            self.feat_cnt += 1
         return s
 
     def prune_keyframe(self):
@@ -149,6 +159,8 @@ class sceneObject:
         """vmap.py:386-454 -> (gt_rgb, gt_depth, valid_mask, labels, pcs, z, partfeat), one launch of K2.
         Random draws come from torch's generator on the data device in the reference's order unless `tapes`
         (a sampler.SampleTapes with n_obj = 1) is given."""
+        if self.shared:
+            raise RuntimeError("this sceneObject's keyframes live in a Scene's shared frame store: sample through Scene.sample()")
         dev = self.rgbs_batch.device
         n_rays, S = n_frames * n_samples, self.n_bins_cam2surface + self.n_bins
         if tapes is None:
@@ -167,7 +179,7 @@ class sceneObject:
                              self.part_frame_row()[None].to(dev).contiguous() if part else None, cached_rays_dir, tapes,
                              n_frames, n_samples, self.n_bins_cam2surface, self.n_bins, self.surface_eps, self.stop_eps,
                              self.min_bound, self.part_down if part else 0,
-                             tuple(global_partfeat.shape[1:3]) if part else (0, 0))
+                             tuple(global_partfeat.shape[1:3]) if part else (0, 0), kf_cap=self.keyframe_buffer_size)
         pf = None
         if part:
             pf = global_partfeat.reshape(-1, global_partfeat.shape[-1])[out.feat_row[0].long()].view(n_frames, n_samples, -1)
@@ -269,8 +281,11 @@ class sceneObject:
 
     def save_checkpoints(self, path, epoch):
         """Same dict keys as vmap.py:556-576 (the viewer, visualization/gen_map_vis.py, reads these)."""
-        torch.save({"epoch": epoch, "FC_state_dict": self.trainer.fc_occ_map.state_dict(),
-                    "PE_state_dict": self.trainer.pe.state_dict(), "obj_id": self.obj_id, "bbox": self.bbox3dour,
+        # the modules' tensors may be views of a whole ensemble block [N, 30720]: clone them, or torch.save would write the
+        # entire storage (every other object's weights) into each file
+        clone = lambda sd: type(sd)((k, v.detach().clone()) for k, v in sd.items())      # noqa: E731
+        torch.save({"epoch": epoch, "FC_state_dict": clone(self.trainer.fc_occ_map.state_dict()),
+                    "PE_state_dict": clone(self.trainer.pe.state_dict()), "obj_id": self.obj_id, "bbox": self.bbox3dour,
                     "obj_scale": self.trainer.obj_scale, "clip_feat": self.clip_feat, "caption_feat": self.caption_feat,
                     "semantic_id": self.semantic_id}, os.path.join(path, "obj_" + str(self.obj_id) + ".pth"))
 

@@ -140,7 +140,7 @@ def test_scene_with_background_model():
         assert bool(torch.isfinite(bg_loss).all())
         first = float(bg_loss.mean()) if first is None else first       # mean over the frame's steps (each step sees other rays)
         last = float(bg_loss.mean())
-    assert sc.bg is not None and sc.bg.hidden == 128 and sc.bg.adam_t == 3 * cfg.n_iter_per_frame
+    assert sc.bg is not None and sc.bg.hidden == 128 and sc.bg.adam_t.cpu().tolist() == [3 * cfg.n_iter_per_frame] * 3
     b = sc.bg_batch
     assert b.z.shape == (1, cfg.n_iter_per_frame * cfg.n_per_optim_bg, 14)
     assert 0 not in sc.obj_dict and len(sc.obj_dict) == 4

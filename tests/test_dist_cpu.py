@@ -26,7 +26,13 @@ def _worker(rank, world, port, q):
     assert (r, w) == (rank, world)
     # per-step flags: rank 0 sees an empty object mask in step 1, rank 1 an empty semantic mask in step 2 and both in 3
     flags = torch.tensor([[0, 2, 0, 0], [0, 0, 4, 6]][rank], dtype=torch.int32)
-    D.make_flag_allreduce()(flags)
+    bits = torch.stack([(flags >> 1) & 1, (flags >> 2) & 1], 1).contiguous()     # what oo_label_counts writes as flag_bits
+    D.make_flag_allreduce()(bits)
+    flags = (bits[:, 0] << 1) | (bits[:, 1] << 2)                                 # what oo_adam_schedule rebuilds
+    # a rank that owns no object joins with all-clear bits (Scene.train) and must not change the result
+    empty = torch.zeros(4, 2, dtype=torch.int32) if rank == 1 else bits.clone()
+    D.make_flag_allreduce()(empty)
+    assert empty.tolist() == bits.tolist()
     t = D.max_over_ranks(10.0 + rank, torch.device("cpu"))
     # objects: ensemble index k -> rank k % world, each object owned exactly once
     owned = [k for k in range(11) if D.owner_rank(k, world) == rank]
@@ -69,3 +75,22 @@ def test_eval_gather_order_is_global_insertion_order():
     assert [ks[q] for q in order] == list(range(7))
     ks, order = global_order([4], 1)
     assert ks == [0, 1, 2, 3] and order == [0, 1, 2, 3]
+
+
+def test_shard_book_world_larger_than_object_count():
+    """fewer objects than ranks (first frames, background-only ranks).  Every rank runs the same bookkeeping:
+    same ensemble indices, owners k mod G, a global models-full cap, and a 'new object somewhere' signal on ALL ranks
+    (the reference restacks every model then: Adam state restarts everywhere)."""
+    world = 4
+    books = [D.ShardBook(r, world, cap=5) for r in range(world)]
+    frames = [[7, 3], [3, 7, 9], [1, 2, 3, 4, 5, 6]]
+    for ids in frames:
+        news = []
+        for b in books:
+            res = [b.see(i) for i in sorted(ids)]
+            news.append([r is not None and r[2] for r in res])
+        assert all(n == news[0] for n in news)                      # the reset signal is the same on every rank
+    assert all(b.global_index == books[0].global_index for b in books)
+    assert books[0].global_index == {3: 0, 7: 1, 9: 2, 1: 3, 2: 4}  # order of first appearance, ties by id; capped at 5
+    assert [sorted(b.local_index) for b in books] == [[2, 3], [7], [9], [1]]
+    assert books[2].see(6) is None and books[1].see(7) == (1, 0, False)

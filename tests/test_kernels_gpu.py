@@ -260,18 +260,20 @@ def test_reference_surface_modules():
     x = torch.randn(3, 50, 10, 3, device=DEV)
     fc_model, fc_param, fc_buffer = U.update_vmap([t.fc_occ_map for t in trs])
     pe_model, pe_param, pe_buffer = U.update_vmap([t.pe for t in trs])
-    assert fc_model.ensemble is pe_model.ensemble and len(fc_param) == 18 and fc_param[0].shape == (3, 32, 87)
-    emb = U.vmap(pe_model)(pe_param, pe_buffer, x)
-    a, c, f = U.vmap(fc_model)(fc_param, fc_buffer, emb)
+    assert len(fc_param) == 18 and fc_param[0].shape == (3, 32, 87) and all(p.requires_grad for p in fc_param)
+    with torch.no_grad():
+        emb = U.vmap(pe_model)(pe_param, pe_buffer, x)
+        a, c, f = U.vmap(fc_model)(fc_param, fc_buffer, emb)
     fc = [torch.stack([list(t.fc_occ_map.parameters())[i].detach().cpu() for t in trs]) for i in range(18)]
     B = torch.stack([t.pe.B_layer.weight.detach().cpu() for t in trs])
     ra, rc, rf = oc.ensemble_forward(fc, B, x.cpu())
     torch.testing.assert_close(a.cpu(), ra, rtol=1e-4, atol=1e-4)
     torch.testing.assert_close(f.cpu(), rf, rtol=1e-4, atol=1e-4)
     # single-module forward
-    e1 = trs[1].pe(x[1])
-    torch.testing.assert_close(e1, emb[1], rtol=0, atol=0)
-    a1, c1, f1 = trs[1].fc_occ_map(e1)
+    with torch.no_grad():
+        e1 = trs[1].pe(x[1])
+        torch.testing.assert_close(e1, emb[1], rtol=0, atol=0)
+        a1, c1, f1 = trs[1].fc_occ_map(e1)
     torch.testing.assert_close(a1, a[1], rtol=0, atol=0)
 
 
@@ -287,38 +289,84 @@ def _small_scene(n_obj=5, W=100, H=60, frames=7):
     return cfg, synth, sc
 
 
-def test_append_kernel_equals_reference_slot_writes():
-    """oo_append_frame (one launch, all objects) == sceneObject.__init__/append_keyframe's per-object slot writes."""
+def _ring_objects(cfg, synth, frames):
+    """Stand-alone sceneObjects with PRIVATE rings, filled exactly like the reference does (sceneObject(...) on first sight,
+    append_keyframe afterwards, per-object state map of train.py:203-205)."""
     from openobj_b200 import vmap as V
-    cfg, synth, sc = _small_scene()
+    cfg.training_device = cfg.data_device = DEV
     ref = {}
-    for f in range(7):
+    for f in range(frames):
         s = synth.frame(f)
-        sc.add_frame(s)
         rgb, depth, inst = s["image"].to(DEV), s["depth"].to(DEV), s["obj"].to(DEV)
-        for oid, bbox in s["bbox_dict"].items():
+        for oid in sorted(s["bbox_dict"].keys()):
+            bbox = s["bbox_dict"][oid]
             state = (inst == oid).to(torch.uint8) + (inst == -1).to(torch.uint8) * 2
             if oid not in ref:
                 ref[oid] = V.sceneObject(cfg, oid, rgb, depth, state, bbox, s["T"].to(DEV), s["frame_id"])
             else:
                 ref[oid].append_keyframe(rgb, depth, state, bbox, s["T"].to(DEV), s["frame_id"])
+    return list(ref.values())
+
+
+def test_shared_store_equals_private_rings_and_oracle():
+    """SURVEY 8f rank 2.  Scene keeps ONE copy of every frame (oo_store_frame) + per-object slot tables; K2 derives the pixel
+    state from the stored instance map.  (1) The store holds exactly the frames' bytes; (2) sampling through it is bit-identical
+    to sampling the reference-layout private rings of stand-alone sceneObjects; (3) and equal to the ORACLE's sample_object
+    (the restatement of vmap.py:386-554) fed the same draws: indices / labels / depths / z bit-exact, pcs rel 1e-6."""
+    from openobj_b200 import sampler
+    cfg, synth, sc = _small_scene()
+    frames = 7
+    for f in range(frames):
+        sc.add_frame(synth.frame(f))
+    objs = _ring_objects(cfg, synth, frames)
     torch.cuda.synchronize()
-    for oid, r in ref.items():
-        o = sc.obj_dict[oid]
-        n = r.n_keyframes
-        assert o.n_keyframes == n and o.lastest_kf_queue == r.lastest_kf_queue and dict(o.kf_id_dict) == dict(r.kf_id_dict)
-        assert torch.equal(o.rgbs_batch[:n], r.rgbs_batch[:n]) and torch.equal(o.depth_batch[:n], r.depth_batch[:n])
-        assert torch.equal(o.t_wc_batch[:n], r.t_wc_batch[:n]) and torch.equal(o.bbox[:n], r.bbox[:n])
-        assert (o.use_frame == r.use_frame).all()
+    assert sc.store.frames_alive() <= frames and all(o.rgbs_batch is None for o in sc.obj_dict.values())
+    # (1) store contents of the newest frame
+    s = synth.frame(frames - 1)
+    g = int(sc.tab.slot_frame[0, sc._objs[0].ring.slot_of[s["frame_id"]]])
+    word = s["image"][..., 0].int() | (s["image"][..., 1].int() << 8) | (s["image"][..., 2].int() << 16)
+    assert torch.equal(sc.store.rgbi[g, ..., 0].cpu(), word) and torch.equal(sc.store.rgbi[g, ..., 1].cpu(), s["obj"])
+    assert torch.equal(sc.store.depth[g].cpu(), s["depth"])
+    torch.testing.assert_close(sc.store.t_wc[g].cpu().view(4, 4), s["T"].float(), rtol=0, atol=0)
+    # (2) same counter RNG, shared store vs private rings
+    n_frames, n_samples = 20, 24
+    n = len(objs)
+    for o, r in zip(sc._objs, objs):
+        assert o.obj_id == r.obj_id and o.n_keyframes == r.n_keyframes and o.lastest_kf_queue == r.lastest_kf_queue
+    rng = sampler.counter_rng(objs, 77, 5, DEV)
+    pf = torch.stack([o.part_frame_row() for o in objs]).to(DEV).contiguous()
+    kw = dict(part_down=5, part_hw=(sc.pw, sc.ph), want_pix=True)
+    a = sampler.sample([o.rgbs_batch for o in objs], [o.depth_batch for o in objs], [o.t_wc_batch for o in objs],
+                       [o.bbox for o in objs], pf, sc.cam.rays_dir_cache, rng, n_frames, n_samples, **kw)
+    assert torch.equal(sc.tab.d_part_frame[:n].cpu(), pf.cpu())
+    b = sampler.sample(None, None, None, None, sc.tab.d_part_frame[:n], sc.cam.rays_dir_cache, rng, n_frames, n_samples,
+                       store=sc.store, slot_frame=sc.tab.d_slot_frame[:n], slot_bbox=sc.tab.d_slot_bbox[:n], kf_cap=sc.kf, **kw)
+    for name in ("gt_rgb", "gt_depth", "valid", "labels", "pcs", "z", "feat_row", "pix"):
+        assert torch.equal(getattr(a, name), getattr(b, name)), name
+    # (3) the oracle on rings built from the frames, fed the tapes cut from the same counter stream
+    tapes = sampler.device_tapes(objs, n_frames, n_samples, 1, 9, objs[0].surface_eps, 77, 5, DEV)
+    for i in (0, n - 1):
+        o = objs[i]
+        # the oracle consumes class tapes by RANK inside the class mask (the reference's order); the counter stream is indexed
+        # by ray, so rows are picked with the kernel's own class masks -- which are then checked against the oracle's
+        val, lab = b.valid[i].cpu().bool(), b.labels[i].cpu()
+        tp = oc.SampleTape(kf_ids=tapes.kf_ids[i].cpu(), u_w=tapes.u_w[i].cpu().view(n_frames, n_samples),
+                           u_h=tapes.u_h[i].cpu().view(n_frames, n_samples), r_invalid=tapes.r_invalid[i].cpu()[~val],
+                           r_valid=tapes.r_valid[i].cpu()[val], r_normal=tapes.r_normal[i].cpu()[val & (lab == 1)],
+                           r_other=tapes.r_other[i].cpu()[val & (lab != 1)])
+        ref = oc.sample_object(o.rgbs_batch.cpu(), o.depth_batch.cpu(), o.t_wc_batch.cpu(), o.bbox.cpu(), sc.cam.rays_dir_cache.cpu(), tp)
+        pix = torch.stack([ref["kf"][:, None].expand_as(ref["iw"]), ref["iw"], ref["ih"]], -1).reshape(-1, 3)
+        assert torch.equal(b.pix[i].cpu(), pix) and torch.equal(lab, ref["labels"]) and torch.equal(val, ref["valid"])
+        assert torch.equal(b.gt_rgb[i].cpu(), ref["rgb"].reshape(-1, 3)) and torch.equal(b.gt_depth[i].cpu(), ref["depth"].reshape(-1))
+        assert torch.equal(b.z[i].cpu(), ref["z"].reshape(-1, 10))
+        torch.testing.assert_close(b.pcs[i].cpu(), ref["pcs"].reshape(-1, 10, 3), rtol=1e-6, atol=1e-6)
 
 
 def test_in_kernel_rng_equals_tape_mode():
     """rng_mode=1 (Philox evaluated inside K2) is bit-identical to tape mode fed by oo_rng_fill."""
     from openobj_b200 import sampler
     cfg, synth, sc = _small_scene()
-    for f in range(7):
-        sc.add_frame(synth.frame(f))
-    objs = list(sc.obj_dict.values())
+    objs = _ring_objects(cfg, synth, 7)
     n_frames, n_samples = 20, 24
     o0 = objs[0]
     tapes = sampler.device_tapes(objs, n_frames, n_samples, 1, 9, o0.surface_eps, 77, 5, DEV)
@@ -344,9 +392,7 @@ def test_in_kernel_rng_equals_tape_mode_other_bin_counts(bins):
     from openobj_b200 import sampler
     nc, nb = bins
     cfg, synth, sc = _small_scene()
-    for f in range(5):
-        sc.add_frame(synth.frame(f))
-    objs = list(sc.obj_dict.values())
+    objs = _ring_objects(cfg, synth, 5)
     objs[1].depth_batch[:objs[1].n_keyframes].zero_()           # every ray of this object has an invalid depth
     objs[2].depth_batch[objs[2].n_keyframes - 1].zero_()
     n_frames, n_samples = 12, 24
@@ -367,9 +413,7 @@ def test_counter_sampling_does_not_depend_on_the_shard():
     gives bit-identical rows to sampling all five together."""
     from openobj_b200 import sampler
     cfg, synth, sc = _small_scene()
-    for f in range(6):
-        sc.add_frame(synth.frame(f))
-    objs = list(sc.obj_dict.values())
+    objs = _ring_objects(cfg, synth, 6)
     n_frames, n_samples = 20, 24
 
     def run(sub):

@@ -25,26 +25,115 @@ def make_batch(ms, labels=None, feat=True, dev="cuda:0"):
                                  lab.to(dev), ms["gt_feat"].to(dev) if feat else None)
 
 
-def check_grads(got_theta_grads, ref_grads, tol=1e-4, ref_grads_alt=None):
+def _grads_with_relu_flips(fc1, B1, pcs1, z1, gt_depth1, rgb1, labels1, gt_feat1, inv_counts, flags, flips):
+    """float64 gradients of ONE object's loss with the ReLU decision of the listed (layer, point, unit) entries inverted.
+    inv_counts / flags: the per-object normalisers and the cross-object zero-mask bits of the full batch (the object is
+    evaluated alone here)."""
+    fc = [p.detach().clone().requires_grad_(True) for p in fc1]
+    B = B1.detach().clone().requires_grad_(True)
+    (W_in, b_in, W_m1, b_m1, W_cat, b_cat, W_m2, b_m2, W_a, b_a, W_cl, b_cl, W_oc, b_oc, W_cp, b_cp, W_ocp, b_ocp) = fc
+    emb = oc.pe_forward(pcs1, B, 2.0)
+    x = emb.reshape(1, -1, emb.shape[-1])
+    xa, xb = x[..., :87], x[..., 87:]
+    pres = []
+
+    def act(pre, li):
+        pres.append(pre.detach())
+        m = pre.detach() > 0
+        for (l, p, j) in flips:
+            if l == li:
+                m[0, p, j] = ~m[0, p, j]
+        return pre * m
+
+    h1 = act(oc._lin(xa, W_in, b_in), 0)
+    h2 = act(oc._lin(h1, W_m1, b_m1), 1)
+    h3 = act(oc._lin(torch.cat((h2, xa), -1), W_cat, b_cat), 2)
+    h4 = act(oc._lin(h3, W_m2, b_m2), 3)
+    alpha = oc._lin(h4, W_a, b_a) * 10.0
+    hx = torch.cat((h4, xb), -1)
+    color = torch.sigmoid(oc._lin(act(oc._lin(hx, W_cl, b_cl), 4), W_oc, b_oc))
+    clip = oc._lin(act(oc._lin(hx, W_cp, b_cp), 5), W_ocp, b_ocp)
+    R, S = z1.shape[1], z1.shape[2]
+    # the object's share of loss.step_batch_loss with the batch's normalisers (sums are per object: loss.py:101)
+    lab = labels1[0]
+    m1, ms = (lab == 1).double(), (lab != 2).double()
+    occ, T = oc.termination(alpha.reshape(1, R, S))
+    d = (T * z1).sum(-1)[0]
+    var = (T * (z1 - d[None, :, None]) ** 2).sum(-1)[0].detach()
+    col = (T[..., None] * color.reshape(1, R, S, 3)).sum(-2)[0]
+    opac = T.sum(-1)[0]
+    loss = 0.0
+    if not flags & 2:
+        loss = loss + ((d - gt_depth1[0]).abs() * m1 / (var.sqrt() + 1e-4)).sum() * inv_counts[0]
+        loss = loss + 5.0 * ((col - rgb1[0]).abs().sum(-1) * m1).sum() * inv_counts[0]
+        if gt_feat1 is not None:
+            rf = (T[..., None] * clip.reshape(1, R, S, -1)).sum(-2)[0]
+            loss = loss + 5.0 * ((1.0 - oc.cosine(rf, gt_feat1[0])) * m1).sum() * inv_counts[0]
+    if not flags & 4:
+        loss = loss + 10.0 * ((opac - (lab != 0).double()).abs() * ms).sum() * inv_counts[1]
+    grads = torch.autograd.grad(loss, fc + [B], allow_unused=True)
+    return list(grads), pres
+
+
+def relu_flip_explainer(fc, B, pcs, z, gt_depth, rgb01, labels, gt_feat, rel=2e-5, max_candidates=6):
+    """For check_grads: explain(k, got) -> True iff the kernel's gradients of object k equal the float64 gradients once the
+    ReLU decision of ONE or TWO hidden units whose pre-activation is within rounding of zero (|pre| < rel * rms of its layer)
+    is inverted.  That is the only legitimate way two correct fp32 evaluations can differ by more than rounding here: a ReLU
+    whose argument is at rounding level switches a whole row contribution (1 / 1200 of the points) on or off."""
+    d = lambda t: None if t is None else t.double()
+    n1 = (labels == 1).sum(1).double()
+    ns = (labels != 2).sum(1).double()
+    flags = (2 if bool((n1 == 0).any()) else 0) | (4 if bool((ns == 0).any()) else 0)
+
+    def explain(k, got_k, tol):
+        sl = slice(k, k + 1)
+        args = ([d(p[sl]) for p in fc], d(B[sl]), d(pcs[sl]), d(z[sl]), d(gt_depth[sl]), d(rgb01[sl]), labels[sl],
+                d(gt_feat[sl]) if gt_feat is not None else None, (1.0 / (n1[k] + 1e-10), 1.0 / (ns[k] + 1e-10)), flags)
+        _, pres = _grads_with_relu_flips(*args, flips=[])
+        cand = []
+        for li, pre in enumerate(pres):
+            rms = float(pre.pow(2).mean().sqrt())
+            idx = (pre.abs() < rel * rms).nonzero()
+            cand += [(li, int(p), int(j)) for _, p, j in idx.tolist()]
+        cand = cand[:max_candidates]
+        trials = [[c] for c in cand] + [[a, b] for i, a in enumerate(cand) for b in cand[i + 1:]]
+        for flips in trials:
+            g, _ = _grads_with_relu_flips(*args, flips=flips)
+            ok = True
+            for gk, rk in zip(got_k, g):
+                rk = torch.zeros_like(gk) if rk is None else rk[0].float()
+                if float((gk - rk).abs().max()) > tol * float(rk.abs().max()) + 1e-7:
+                    ok = False
+                    break
+            if ok:
+                return True
+        return False
+    return explain
+
+
+def check_grads(got_theta_grads, ref_grads, tol=1e-4, ref_grads_alt=None, explain=None):
     """Per object and tensor: max |error| <= tol * max |reference|.
 
-    Two evaluations of the same algorithm serve as references: the oracle in float64 and (ref_grads_alt) in float32.
-    Neither alone is a fair judge: the fp32 autograd of the oracle is ~5e-4 (clip head up to 5e-2) away from fp64 on
-    saturated inputs, while fp64 takes the other side of a ReLU / |.| kink about once per 3 object-steps, which changes
-    a row of a weight gradient by ~1/sqrt(1200) of its size (profiles/r1b_grad_diag.txt: on such an object the kernel
-    and the fp32 oracle agree to 1e-6 and both differ from fp64 by 6e-2).  An object passes if the kernel is within
-    `tol` of EITHER reference; all objects but max(1, 5 %) must pass."""
+    Two evaluations of the same algorithm serve as references: the oracle in float64 and (ref_grads_alt) in float32; an
+    object passes if the kernel is within `tol` of EITHER.  An object that matches neither must be EXPLAINED: `explain`
+    (relu_flip_explainer) has to reproduce the kernel's gradients of that object -- all 19 tensors, to `tol` -- from the
+    float64 evaluation by inverting the ReLU decision of hidden units whose pre-activation is at rounding level.  No
+    unexplained deviation is accepted, whatever its size."""
     alt = ref_grads_alt or [None] * len(ref_grads)
-    for name, g, r, ra in zip(layout.NAMES, layout.views(got_theta_grads.cpu()), ref_grads, alt):
+    views = layout.views(got_theta_grads.cpu())
+    n = views[0].shape[0]
+    failing = {}
+    for name, g, r, ra in zip(layout.NAMES, views, ref_grads, alt):
         r = torch.zeros_like(g) if r is None else r.float()
-        n = g.shape[0]
         scale = r.reshape(n, -1).abs().max(1).values
         err = (g - r).reshape(n, -1).abs().max(1).values
         if ra is not None:
             err = torch.minimum(err, (g - ra.float()).reshape(n, -1).abs().max(1).values)
-        ok = (err <= tol * scale + 1e-7)
-        n_out = int((~ok).sum())
-        assert n_out <= max(1, n // 20) and bool((err <= 0.2 * scale + 1e-7).all()), (name, (err / (scale + 1e-12)).tolist())
+        for k in (~(err <= tol * scale + 1e-7)).nonzero().flatten().tolist():
+            failing.setdefault(k, []).append((name, float(err[k] / (scale[k] + 1e-12))))
+    for k, what in failing.items():
+        assert explain is not None and explain(k, [v[k] for v in views], tol), ("unexplained gradient deviation", k, what)
+    return sorted(failing)
 
 
 def grads64(fc, B, pcs, z, gt_depth, rgb01, labels, gt_feat):
@@ -68,10 +157,11 @@ def test_golden_step_grads_and_loss(mode, n_sm):
     total = float(ens.total_loss(terms.cpu()))
     assert abs(total - float(ms["loss_" + mode])) <= 1e-4 * abs(float(ms["loss_" + mode])) + 1e-6   # rel 1e-4 on losses
     ref = [ms["g_%s%02d" % (mode, i)] if ("g_%s%02d" % (mode, i)) in ms else None for i in range(19)]
-    check_grads(g, ref, tol=2e-4)     # reference's own fp32 autograd (frozen golden)
-    rt, rg = grads64(fc, ms["peB"], ms["pcs"], ms["z"], ms["gt_depth"], ms["gt_rgb8"] / 255., labels,
-                     ms["gt_feat"] if mode != "off" else None)
-    check_grads(g, rg)                # same algorithm in float64
+    gt_feat = ms["gt_feat"] if mode != "off" else None
+    ex = relu_flip_explainer(fc, ms["peB"], ms["pcs"], ms["z"], ms["gt_depth"], ms["gt_rgb8"] / 255., labels, gt_feat)
+    rt, rg = grads64(fc, ms["peB"], ms["pcs"], ms["z"], ms["gt_depth"], ms["gt_rgb8"] / 255., labels, gt_feat)
+    # the reference's own fp32 autograd (frozen golden, 2e-4: its noise against float64) or the same algorithm in float64
+    check_grads(g, rg, tol=2e-4, ref_grads_alt=ref, explain=ex)
     assert int(ens.flags[0]) == (2 if mode == "zm" else 0)
 
 
@@ -131,12 +221,9 @@ def test_room0_shape_steps_match_oracle(N, feat):
     from openobj_b200.ensemble import Ensemble, FrameBatch
     R, I = 120, 3
     pcs, z, gt_depth, rgb8, labels, gt_feat = synth_batch(N, R * I, seed=N, feat=feat)
+    # the reference's init distributions as they are (mean |alpha| ~ 4, max ~ 35); saturated out_alpha layers are the subject
+    # of tests/test_parity_r2_gpu.py::test_reference_init_and_saturated_alpha_measured_tolerance
     fc, B = oc.init_params(N, generator=torch.Generator().manual_seed(100 + N))
-    # keep sigmoid(alpha) away from saturation: the reference forms the free probability as 1 - occ in fp32
-    # (render_rays.py:38), so with |alpha| ~ 15 one ulp of occ moves T, var and the depth weight by ~10 % and no two
-    # fp32 implementations (nor the reference on CPU vs CUDA) agree to 1e-4; see DESIGN.md "conditioning".
-    fc[8] *= 0.3
-    fc[9] *= 0.3
     ens = Ensemble(N, rays_per_step=R, iters_per_frame=I)
     ens.load_stacked(fc + [B])
     dev = "cuda:0"
@@ -152,7 +239,8 @@ def test_room0_shape_steps_match_oracle(N, feat):
     torch.testing.assert_close(terms.cpu(), ref_t, rtol=1e-4, atol=1e-6)
     _, rg32 = oc.train_step_grads(fc, B, pcs[:, sl], z[:, sl], gt_depth[:, sl], rgb8[:, sl] / 255., labels[:, sl],
                                   gt_feat[:, sl] if feat else None)
-    check_grads(g, rg, ref_grads_alt=rg32)
+    check_grads(g, rg, ref_grads_alt=rg32, explain=relu_flip_explainer(
+        fc, B, pcs[:, sl], z[:, sl], gt_depth[:, sl], rgb8[:, sl] / 255., labels[:, sl], gt_feat[:, sl] if feat else None))
     # three optimisation steps
     ens.reset_optimizer()
     lt = torch.zeros(I, N, 4, device=dev)
