@@ -19,7 +19,7 @@ def _batch(N, RAYS, seed, feat):
 def _ensemble(N, R, I, seed):
     from openobj_b200.ensemble import Ensemble
     fc, B = oc.init_params(N, generator=torch.Generator().manual_seed(seed))
-    fc[8] *= 0.3
+    fc[8] *= 0.3       # out of saturation: see the conditioning note in tests/test_train_gpu.py::test_room0_shape_steps_match_oracle
     fc[9] *= 0.3
     ens = Ensemble(N, rays_per_step=R, iters_per_frame=I)
     ens.load_stacked(fc + [B])
@@ -31,7 +31,7 @@ def test_ragged_and_extreme_shapes(N, R, feat):
     """rays per step not a multiple of the 10-ray tile, one object, 200 objects (more tiles than CTAs): losses rel 1e-4
     against the oracle; gradients against its float64 / float32 evaluations."""
     from openobj_b200.ensemble import FrameBatch
-    from test_train_gpu import check_grads, grads64
+    from test_train_gpu import check_grads, grads64, relu_flip_explainer
     pcs, z, gt_depth, rgb8, labels, gt_feat = _batch(N, R, seed=N * 1000 + R, feat=feat)
     labels[:, 0], labels[:, -1] = 1, 0
     ens, fc, B = _ensemble(N, R, 1, seed=N + R)
@@ -42,11 +42,9 @@ def test_ragged_and_extreme_shapes(N, R, feat):
     rt, rg = grads64(fc, B, pcs, z, gt_depth, rgb8 / 255., labels, gt_feat)
     ref_t = torch.stack([rt.depth, rt.color, rt.opacity, rt.feat], 1).float()
     torch.testing.assert_close(terms.cpu(), ref_t, rtol=1e-4, atol=1e-6)
-    if N <= 5:
-        _, rg32 = oc.train_step_grads(fc, B, pcs, z, gt_depth, rgb8 / 255., labels, gt_feat)
-        check_grads(g, rg, ref_grads_alt=rg32)
-    else:
-        check_grads(g, rg)
+    _, rg32 = oc.train_step_grads(fc, B, pcs, z, gt_depth, rgb8 / 255., labels, gt_feat)
+    check_grads(g, rg, ref_grads_alt=rg32,
+                explain=relu_flip_explainer(fc, B, pcs, z, gt_depth, rgb8 / 255., labels, gt_feat))
     if not feat:       # clip head: no gradient at all (quirk 8)
         for i in (14, 15, 16, 17):
             assert float(layout.views(g)[i].abs().max()) == 0.0
