@@ -168,22 +168,69 @@ def cpu_reference_run(n_obj, part, steps, warmup, time_budget_s):
     return dict(rays_per_s=n_obj * R * done / dt, steps_done=done, seconds=dt, cores=cores, ms_per_step=1e3 * dt / done)
 
 
+def reference_loop_run(n_obj, part, steps, warmup, W, H, device="cpu", max_seconds=150.0):
+    """The reference's own loop (UNMODIFIED reference modules from oracle/_ref or /root/reference through
+    oracle/ref_loop.py: frame ingestion, per-object sampling, vmap forward, step_batch_loss, backward, AdamW, write-back) on
+    synthetic frames of the bench's shape.  Returns None when the reference modules are not available (then the oracle port
+    is the CPU arm)."""
+    import torch
+    sys.path.insert(0, os.path.join(ROOT, "oracle"))
+    import ref_harness
+    if not ref_harness.available():
+        return None
+    import warnings
+    warnings.filterwarnings("ignore")
+    import ref_loop
+    from openobj_b200.synthetic import SyntheticScene
+    if device == "cpu":
+        torch.set_num_threads(os.cpu_count() or 1)
+    synth = SyntheticScene(n_obj, W=W, H=H, part_mode=bool(part), seed=0, n_distinct=2)
+    r = ref_loop.timed_run(n_obj, device, bool(part), steps, warmup, synth, fill_frames=2, iters_per_frame=ITERS,
+                           max_seconds=max_seconds)
+    r["kind"] = "reference"
+    return r
+
+
+def config_shape(args):
+    """(W, H, part_mode, total objects or None = args.objects per GPU) of BASELINE.json's configs."""
+    if args.config == 3:
+        return 1200, 680, 1, 100
+    if args.config == 4:
+        return 640, 480, 0, 200
+    return 1200, 680, int(args.part), None
+
+
 def run_reference_arm(args):
     rank = int(os.environ.get("RANK", "0"))
     if rank != 0:
         return 0
-    n_obj = 8     # bounded sample: 8 of the 60 objects per step (objects are independent; rays/s per core is the same)
-    r = cpu_reference_run(n_obj, bool(args.part), args.steps, min(args.warmup, 3), time_budget_s=150.0)
+    W, H, part, total = config_shape(args)
+    n_obj = total or args.objects
+    warm = min(args.warmup, 3)
+    r = reference_loop_run(n_obj, part, args.steps, warm, W, H, device=args.device)
+    if r is None:
+        n_port = 8
+        r = cpu_reference_run(n_port, bool(part), args.steps, warm, time_budget_s=150.0)
+        r.update(kind="port", n_obj=n_port)
+        sample = ("oracle port (torch-CPU restatement of the reference step: vmap forward, step_batch_loss, autograd backward, "
+                  "AdamW; no sampling) on %d of the %d objects per step, %d steps (time-bounded); the reference modules "
+                  "(oracle/_ref) were not found" % (n_port, n_obj, r["steps_done"]))
+    else:
+        sample = ("UNMODIFIED reference modules (objnerf/{vmap,utils,trainer,model,embedding,render_rays,loss,cfg}.py via "
+                  "oracle/ref_loop.py) on %s: all %d objects, %dx%d frames, part_mode=%d; per frame: ingestion into the "
+                  "per-object keyframe rings + per-object sampling + %d steps of vmap forward / step_batch_loss / backward / "
+                  "AdamW + write-back; %d steps in %.1f s" % (args.device, r["n_obj"], W, H, part, min(ITERS, args.steps),
+                                                              r["steps_done"], r["seconds"]))
     line = {
         "metric": "training rays/sec for N-object ensemble", "value": r["rays_per_s"], "unit": "rays/s", "n_gpus": args.gpus,
-        "steps": r["steps_done"], "warmup": min(args.warmup, 3), "ms_per_step": r["ms_per_step"], "higher_is_better": True,
-        "scaling": "weak", "vs_baseline": None, "dtype": "f32", "data": "synthetic", "impl": "reference",
-        "config": {"workload": "Replica room_0 shape, %d objects x 120 rays x 10 samples per step, part_mode=%d"
-                               % (args.objects, args.part)},
-        "cpu_baseline": {"value": r["rays_per_s"], "unit": "rays/s", "cores": r["cores"], "kind": "port",
-                         "sample": "oracle port (torch-CPU restatement of the reference step: vmap forward, step_batch_loss, "
-                                   "autograd backward, AdamW) on %d of the %d objects per step, %d steps (time-bounded)"
-                                   % (n_obj, args.objects, r["steps_done"])},
+        "steps": r["steps_done"], "warmup": warm, "ms_per_step": r["ms_per_step"], "higher_is_better": True,
+        "scaling": "weak" if total is None else "strong", "vs_baseline": None, "dtype": "f32", "data": "synthetic",
+        "impl": "reference",
+        "config": {"workload": "BASELINE configs[%d]: %dx%d frames, %d objects x 120 rays x 10 samples per step, part_mode=%d, "
+                               "%d steps per frame; per-frame ingestion + sampling inside the timed region"
+                               % (args.config - 1, W, H, n_obj, part, ITERS),
+                   "device": args.device},
+        "cpu_baseline": {"value": r["rays_per_s"], "unit": "rays/s", "cores": r["cores"], "kind": r["kind"], "sample": sample},
         "e2e": {"value": r["rays_per_s"], "unit": "rays/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
         "gpu_launches": 0,
     }
@@ -206,19 +253,24 @@ def run_ours(args):
         raise _lib.OOError("bench.py needs a CUDA device: the product path has no CPU fallback")
     torch.cuda.set_device(local)
     dev = torch.device("cuda", local)
+    W_, H_, part_, total_ = config_shape(args)
     cfg = C.room0_config()
     cfg.training_device = cfg.data_device = str(dev)
-    cfg.part_mode = bool(args.part)
+    cfg.part_mode = bool(part_)
     cfg.do_bg = False
-    n_local = args.objects
-    cfg.max_n_models = n_local * world          # trainer.n_models: the global cap on objects (train.py:231-233)
+    if (W_, H_) != (cfg.W, cfg.H):              # ScanNet shape (configs/ScanNet/scene0011_01.json:56-57)
+        cfg.W, cfg.H = W_, H_
+        cfg.fx = cfg.fy = 0.5 * W_
+        cfg.cx, cfg.cy = 0.5 * W_ - 0.5, 0.5 * H_ - 0.5
+    n_total = total_ if total_ is not None else args.objects * world
+    cfg.max_n_models = n_total                  # trainer.n_models: the global cap on objects (train.py:231-233)
     steps, warmup = args.steps, max(args.warmup, 3)
     frames_w = (warmup + ITERS - 1) // ITERS
     frames_t = (steps + ITERS - 1) // ITERS
     fill = args.fill_frames
     n_frames_total = fill + 2 * (frames_w + frames_t) + 12
     # every rank sees the same frames; object ids are spread so that rank r owns ids with (index % world == r)
-    synth = SyntheticScene(n_local * world, W=cfg.W, H=cfg.H, part_mode=cfg.part_mode, seed=0, pin=True, n_distinct=2)
+    synth = SyntheticScene(n_total, W=cfg.W, H=cfg.H, part_mode=cfg.part_mode, seed=0, pin=True, n_distinct=2)
     scene = Scene(cfg, rank=rank, world=world, seed=1234, max_frames=n_frames_total, flag_allreduce=D.make_flag_allreduce())
 
     def iters_of(frame_idx, n_frames, total):
@@ -294,7 +346,8 @@ def run_ours(args):
     torch.cuda.synchronize(); D.barrier()
     print("[bench] rank %d: value pass %.1f ms, e2e pass %.1f ms (this rank)" % (rank, ms, e0.elapsed_time(e1)), file=sys.stderr)
     ms_e2e = D.max_over_ranks(e0.elapsed_time(e1), dev)
-    rays = n_obj * world * R * steps
+    n_all = int(D.sum_over_ranks(n_obj, dev))
+    rays = n_all * R * steps
     h2d_per_step = synth.frame_bytes() / ITERS
     d2h_per_step = 4.0 / ITERS
 
@@ -424,15 +477,28 @@ def run_ours(args):
         bg_mac_pt = 63 + hb * 87 + hb * hb + hb * (hb + 87) + hb * hb + hb + hb * (hb + 42) + 3 * hb + (
             (hb * (hb + 42) + 512 * hb) if cfg.part_mode else 0)
         bg_flop = 2 * 3 * bg_mac_pt * Rb * Sb
-        cpu = cpu_reference_run(8, cfg.part_mode, steps=10 ** 6, warmup=1, time_budget_s=15.0) if not args.no_cpu else None
+        # ---- the reference beside it: (i) its own CPU path on this box's host cores, a bounded sample (one frame: ingestion +
+        # sampling + 20 steps, all objects); (ii) informative, the real bar of SURVEY 8d: the same unmodified modules as eager
+        # PyTorch + functorch.vmap on this same GPU
+        cpu = eager = None
+        if not args.no_cpu:
+            cpu = reference_loop_run(n_obj, cfg.part_mode, 20, 3, cfg.W, cfg.H, device="cpu", max_seconds=60.0)
+            if cpu is None:
+                cpu = cpu_reference_run(8, cfg.part_mode, steps=10 ** 6, warmup=1, time_budget_s=15.0)
+                cpu.update(kind="port", n_obj=8)
+            else:
+                torch.cuda.empty_cache()
+                eager = reference_loop_run(n_obj, cfg.part_mode, 40, 5, cfg.W, cfg.H, device=str(dev), max_seconds=60.0)
+                torch.cuda.empty_cache()
         out = {
             "metric": "training rays/sec for N-object ensemble", "value": rays / (ms * 1e-3), "unit": "rays/s",
             "n_gpus": world, "steps": steps, "warmup": warmup, "ms_per_step": ms / steps, "higher_is_better": True,
-            "scaling": "weak", "vs_baseline": None, "dtype": "f32", "data": "synthetic",
-            "config": {"workload": "BASELINE configs[1]: Replica room_0 shape (1200x680), %d objects per GPU x 120 rays x 10 "
-                                   "samples per step, part_mode=%d, 100 steps per frame; per-frame append + sampling of all "
-                                   "objects inside the timed region" % (n_obj, int(cfg.part_mode)),
-                       "objects_per_gpu": n_obj, "rays_per_step_per_object": R, "iters_per_frame": ITERS,
+            "scaling": "weak" if total_ is None else "strong", "vs_baseline": None, "dtype": "f32", "data": "synthetic",
+            "config": {"workload": "BASELINE configs[%d]: %dx%d frames, %d objects in total (%d on rank 0) x 120 rays x 10 "
+                                   "samples per step, part_mode=%d, 100 steps per frame; per-frame ingestion (shared keyframe "
+                                   "store) + sampling of all objects inside the timed region"
+                                   % (args.config - 1, cfg.W, cfg.H, n_all, n_obj, int(cfg.part_mode)),
+                       "objects_total": n_all, "objects_per_gpu": n_obj, "rays_per_step_per_object": R, "iters_per_frame": ITERS,
                        "l2": "inputs larger than L2: %.0f MB sampled batch per frame + part-feature table" %
                              (n_obj * ITERS * R * 181 / 1e6),
                        "parallelism": "objects sharded by ensemble index, rank = k mod %d; no gradient collectives" % world},
@@ -475,9 +541,20 @@ def run_ours(args):
                              "ms_per_step": bg_ms, "rays_per_s": Rb / (bg_ms * 1e-3), "flop_per_step": bg_flop,
                              "achieved_tflops": bg_flop / (bg_ms * 1e-3) / 1e12, "frac_of_fma_peak": bg_flop / (bg_ms * 1e-3) / 1e12 / peak}
         if cpu is not None:
-            out["cpu_baseline"] = {"value": cpu["rays_per_s"], "unit": "rays/s", "cores": cpu["cores"], "kind": "port",
-                                   "sample": "oracle port (torch-CPU restatement of the reference step) on 8 of the %d objects, "
-                                             "%d steps in %.1f s" % (n_obj, cpu["steps_done"], cpu["seconds"])}
+            what = ("UNMODIFIED reference modules (oracle/ref_loop.py) on the host cores: all %d objects, one frame = ingestion "
+                    "into the per-object rings + per-object sampling + %d steps + write-back, %.1f s"
+                    % (cpu["n_obj"], cpu["steps_done"], cpu["seconds"])) if cpu["kind"] == "reference" else (
+                    "oracle port (torch-CPU restatement of the reference step, no sampling) on 8 of the %d objects, %d steps in "
+                    "%.1f s" % (n_obj, cpu["steps_done"], cpu["seconds"]))
+            out["cpu_baseline"] = {"value": cpu["rays_per_s"], "unit": "rays/s", "cores": cpu["cores"], "kind": cpu["kind"],
+                                   "sample": what}
+        if eager is not None:
+            out["gpu_eager_reference"] = {
+                "what": "informative (SURVEY 8d-ii, 'the real bar'): the same unmodified reference modules as eager PyTorch + "
+                        "functorch.vmap on this same B200 (data_device = training_device = cuda), all %d objects, per-frame "
+                        "ingestion + sampling + steps; NOT the driver's reference arm" % eager["n_obj"],
+                "value": eager["rays_per_s"], "unit": "rays/s", "ms_per_step": eager["ms_per_step"], "steps": eager["steps_done"],
+                "speedup_of_value": rays / (ms * 1e-3) / eager["rays_per_s"] if world == 1 else None}
         print(json.dumps(out), file=_JSON_OUT, flush=True)
     D.barrier()
     if world > 1:
@@ -494,7 +571,12 @@ def main():
     ap.add_argument("--objects", type=int, default=60, help="objects per GPU")
     ap.add_argument("--part", type=int, default=1, help="part-level feature head on (room_0.json part_mode)")
     ap.add_argument("--fill-frames", type=int, default=20, help="untimed frames that fill the keyframe rings (SURVEY 8d)")
-    ap.add_argument("--no-cpu", action="store_true", help="skip the CPU baseline leg")
+    ap.add_argument("--no-cpu", action="store_true", help="skip the CPU baseline / GPU-eager reference legs")
+    ap.add_argument("--config", type=int, default=2, choices=[2, 3, 4],
+                    help="BASELINE.json configs (1-based): 2 = room_0 shape, --objects per GPU (weak scaling; the headline); "
+                         "3 = 100 objects in total, CLIP + part heads (strong scaling); 4 = ScanNet shape 640x480, 200 objects, "
+                         "part features off (strong scaling)")
+    ap.add_argument("--device", default="cpu", help="--impl reference only: cpu (the driver's arm) or cuda:0 (eager reference)")
     args = ap.parse_args()
     if args.impl == "reference":
         return run_reference_arm(args)

@@ -4,7 +4,8 @@ TEST INFRASTRUCTURE ONLY.  Nothing under ``openobj_b200/`` may import this file.
 It is used (a) by ``oracle/make_golden.py`` to freeze golden vectors into
 ``tests/golden/`` and (b) by ``tests/test_oracle_vs_reference.py`` to pin the
 restatement in ``oracle/openobj_oracle.py`` against the real code whenever
-``/root/reference`` is present (it is NOT present on the GPU box).
+``/root/reference`` is present, and (c) by ``oracle/ref_loop.py`` for bench.py's reference arm; on the GPU box, where
+/root/reference does not exist, the modules come from ``oracle/_ref`` (byte-identical files, see oracle/build_ref.py).
 
 The reference imports visualisation / geometry packages that are not installed in
 this image and are not on the hot path:
@@ -19,7 +20,10 @@ import sys
 import types
 import warnings
 
-REF_ROOT = os.environ.get("OPENOBJ_REFERENCE", "/root/reference")
+_HERE = os.path.dirname(os.path.abspath(__file__))
+# /root/reference in the build container; on the GPU box the byte-identical files oracle/build_ref.py placed in oracle/_ref/
+REF_ROOT = os.environ.get("OPENOBJ_REFERENCE") or (
+    "/root/reference" if os.path.isfile("/root/reference/objnerf/vmap.py") else os.path.join(_HERE, "_ref"))
 REF_OBJNERF = os.path.join(REF_ROOT, "objnerf")
 
 
