@@ -26,7 +26,8 @@ struct TrainParams {
     float* slab;
     float* slot_loss;
     float scale, cs, os, fs;
-    long long* phase_cycles;   // debug: [N_TRAIN_PHASES + 4] cycle totals of block 0: phases, block, tiles, staging, flush
+    long long* phase_cycles;   // debug: [N_TRAIN_PHASES + 8] cycle totals of block 0: phases, block, tiles, staging, flush,
+                               // prologue (start -> past the dependency wait), wait (inside griddepcontrol.wait), tail
     long long* block_times;    // debug: [n_cta][3] = {globaltimer at block start, at block end, tiles} of the last launch
 };
 
@@ -101,6 +102,7 @@ __global__ void __launch_bounds__(NTHREADS, 1) k_train(const TrainParams prm) {
     }
     long long* cyc = (prm.phase_cycles != nullptr && blockIdx.x == 0) ? prm.phase_cycles : nullptr;
     const long long t_start = cyc ? clock64() : 0;
+    const long long ns_start = cyc ? global_ns() : 0;
     zero_pad_rows(tid, sm);
     // tensor memory for the weight-gradient accumulators: 16 warps x 64 columns (oo_tile.h, TileAcc); one CTA per SM
     __shared__ uint32_t tm_base_s;
@@ -141,8 +143,14 @@ __global__ void __launch_bounds__(NTHREADS, 1) k_train(const TrainParams prm) {
     float pre = tile_prefetch<PART>(tid, c);          // this thread's input value of the first tile
     // everything above touches only this CTA's shared / tensor memory and per-frame constants; the parameters and the
     // out_clip constants below come from the previous update kernel
+    const long long t_w0 = cyc ? clock64() : 0;
     pdl_wait();
     pdl_release();
+    if (cyc && tid == 0) {
+        const long long now = clock64();
+        cyc[N_TRAIN_PHASES + 4] += t_w0 - t_start;
+        cyc[N_TRAIN_PHASES + 5] += now - t_w0;
+    }
     int cur_obj = -1;
     for (int t = t_begin; t < t_end; ++t) {
         const int obj = t / prm.tiles_per_obj;
@@ -187,16 +195,20 @@ __global__ void __launch_bounds__(NTHREADS, 1) k_train(const TrainParams prm) {
             if (cyc && tid == 0) cyc[N_TRAIN_PHASES + 3] += clock64() - tf0;
         }
     }
-    if (cyc && tid == 0) {
-        cyc[N_TRAIN_PHASES] += clock64() - t_start;     // whole block
-        cyc[N_TRAIN_PHASES + 1] += t_end - t_begin;     // tiles processed
-    }
+    const long long t_tail = cyc ? clock64() : 0;
     asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory");
     __syncthreads();
     if (prm.block_times != nullptr && tid == 0) prm.block_times[3 * blockIdx.x + 1] = global_ns();
     if (tid < 32)
         asm volatile("tcgen05.dealloc.cta_group::1.sync.aligned.b32 %0, %1;" ::"r"(tm_base), "r"((uint32_t)(AC_COLS * NWARPS / 4))
                      : "memory");
+    if (cyc && tid == 0) {
+        const long long now = clock64();
+        cyc[N_TRAIN_PHASES] += now - t_start;           // whole block
+        cyc[N_TRAIN_PHASES + 1] += t_end - t_begin;     // tiles processed
+        cyc[N_TRAIN_PHASES + 6] += now - t_tail;
+        cyc[N_TRAIN_PHASES + 7] += global_ns() - ns_start;     // the same interval in nanoseconds: cycles / ns = SM clock
+    }
 }
 
 // ---- per-frame: ray counts per (step, object) and the cross-object zero-mask flags (render_rays.py:88-94)
@@ -880,7 +892,7 @@ extern "C" int oo_debug_block_times(long long* dev_ptr) {     // [n_cta][3]; nul
 
 extern "C" int oo_debug_phase_cycles(long long* dev_ptr) {
     g_phase_cycles = dev_ptr;
-    return N_TRAIN_PHASES + 4;
+    return N_TRAIN_PHASES + 8;
 }
 
 extern "C" int oo_train_ws_sizes(int n_obj, int rays_per_step, int iters, int n_sm, int* n_cta, int* n_slots,

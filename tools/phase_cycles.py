@@ -27,11 +27,19 @@ L.oo_debug_phase_cycles.argtypes = [ctypes.c_void_p]
 n = L.oo_debug_phase_cycles(None)
 cyc = torch.zeros(n, dtype=torch.int64, device=dev)
 L.oo_debug_phase_cycles(ctypes.c_void_p(cyc.data_ptr()))
-ens.train_frame(batch)
+separate = len(sys.argv) > 4 and sys.argv[4] == "separate"
+if separate:       # K1 and K4 launched apart with an event between them: no programmatic overlap, block 0's total is its own time
+    bc = batch.to_c()
+    ens.prepare_frame(batch)
+    ev = torch.cuda.Event()
+    for it in range(I):
+        ens.k1(bc, it, refresh_derived=(it == 0)); ev.record(); ens.k4(bc, it); ev.record()
+else:
+    ens.train_frame(batch)
 torch.cuda.synchronize()
 L.oo_debug_phase_cycles(None)
 c = cyc.cpu().tolist()
-NP = n - 4
+NP = n - 8
 tiles = c[NP + 1]
 label = {0: "load", 1: "PE fwd", 2: "in", 3: "mid1", 4: "cat", 5: "mid2", 6: "heads", 7: "out", 33: "termination", 8: "ray sums+loss",
          9: "S", 10: "v=W^T y part", 11: "v reduce", 12: "G S", 32: "cos/A/B", 13: "U+rec+M", 16: "g per point",
@@ -44,5 +52,9 @@ if len(sys.argv) > 3:
 names = ["%d %s" % (o, label.get(o, "?")) for o in order][:NP]
 tot = sum(c[:NP])
 print("tiles", tiles, "block cycles/tile %.0f, phases sum/tile %.0f, staging/tile %.0f, flush/tile %.0f" % (c[NP] / tiles, tot / tiles, c[NP + 2] / tiles, c[NP + 3] / tiles))
+print("per launch (block 0): block %.0f = phases %.0f + staging %.0f + flush %.0f + prologue %.0f + dependency wait %.0f + tail %.0f + other %.0f cycles"
+      % (c[NP] / I, tot / I, c[NP + 2] / I, c[NP + 3] / I, c[NP + 4] / I, c[NP + 5] / I, c[NP + 6] / I,
+         (c[NP] - tot - c[NP + 2] - c[NP + 3] - c[NP + 4] - c[NP + 5] - c[NP + 6]) / I))
+print("block 0: %.1f us per launch by globaltimer -> SM clock during the kernel %.0f MHz" % (c[NP + 7] / I / 1e3, 1e3 * c[NP] / max(c[NP + 7], 1)))
 for nme, v in zip(names, c[:NP]):
     print("%-14s %8.0f cyc/tile  %5.1f%%" % (nme, v / tiles, 100.0 * v / tot))
