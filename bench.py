@@ -300,6 +300,7 @@ def run_ours(args):
         staged = scene.stage_frame(synth.frame(f)) if host else None
         for j in range(n_frames):
             it = iters_of(j, n_frames, total_steps)
+            t0 = time.perf_counter()
             if host:
                 cur = staged
                 scene.add_frame(cur)
@@ -307,8 +308,14 @@ def run_ours(args):
                     staged = scene.stage_frame(synth.frame(f + 1))
             else:
                 scene.add_frame(frames[j])
+            t1 = time.perf_counter()
             scene.sample()
+            t2 = time.perf_counter()
             scene.train(iters=it, loss_terms=lt)
+            if args.trace:
+                t3 = time.perf_counter()
+                print("[trace] rank %d frame %d host ms: add_frame %.3f sample %.3f train(enqueue %d steps) %.3f"
+                      % (rank, j, 1e3 * (t1 - t0), 1e3 * (t2 - t1), it, 1e3 * (t3 - t2)), file=sys.stderr)
             if host:
                 _ = lt[it - 1].sum().item()        # D2H read of the step result inside the timed region
             f += 1
@@ -328,11 +335,29 @@ def run_ours(args):
     torch.cuda.synchronize(); D.barrier()
     e0, e1 = cuda_timer()
     launches["n"] = 0
-    with ClockSampler(local) as clk:
-        e0.record()
-        run_frames(frames_t, steps, host=False, frames=dev_frames)
-        e1.record()
-        torch.cuda.synchronize()
+    marks = []
+    if args.trace:           # device-side timeline of the per-frame work (events on the stream, read after the pass)
+        def mark(name):
+            ev = torch.cuda.Event(enable_timing=True)
+            ev.record()
+            marks.append((name, ev))
+        scene.ens.mark = mark
+    # the clock sampler (NVML initialisation, a thread start: milliseconds, different on every rank) is brought up BEFORE the
+    # barrier: whatever sits between the barrier and e0 becomes start skew between the ranks, and the first rank to reach the
+    # per-frame all-reduce then waits for the last one inside its own timed region
+    clk = ClockSampler(local)
+    clk.__enter__()
+    time.sleep(0.02)
+    torch.cuda.synchronize(); D.barrier()
+    e0.record()
+    run_frames(frames_t, steps, host=False, frames=dev_frames)
+    e1.record()
+    torch.cuda.synchronize()
+    clk.__exit__()
+    if args.trace:
+        scene.ens.mark = None
+        print("[trace] rank %d device ms since start: %s | end %.3f" % (
+            rank, " ".join("%s %.3f" % (n, e0.elapsed_time(ev)) for n, ev in marks[:6]), e0.elapsed_time(e1)), file=sys.stderr)
     del dev_frames
     D.barrier()
     ms = D.max_over_ranks(e0.elapsed_time(e1), dev)
@@ -576,6 +601,7 @@ def main():
                     help="BASELINE.json configs (1-based): 2 = room_0 shape, --objects per GPU (weak scaling; the headline); "
                          "3 = 100 objects in total, CLIP + part heads (strong scaling); 4 = ScanNet shape 640x480, 200 objects, "
                          "part features off (strong scaling)")
+    ap.add_argument("--trace", action="store_true", help="per-rank host timings of every frame (stderr)")
     ap.add_argument("--device", default="cpu", help="--impl reference only: cpu (the driver's arm) or cuda:0 (eager reference)")
     args = ap.parse_args()
     if args.impl == "reference":

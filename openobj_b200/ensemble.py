@@ -132,14 +132,18 @@ class Ensemble:
         iters = self._iters(iters)
         part_on = batch.feat_row is not None
         self.check_explode()                      # of the previous frame: one look per frame
+        mark = getattr(self, "mark", None) or (lambda name: None)
         with torch.cuda.device(self.device):
             bits = self.flag_bits[:iters] if flag_allreduce is not None else None
             check(self.L.oo_label_counts(ptr(batch.labels), self.n_obj, batch.rays_per_obj, self.R, iters,
                                          ptr(self.counts), ptr(self.flags), ptr(bits), stream()), "oo_label_counts")
+            mark("label_counts")
             if flag_allreduce is not None:
                 flag_allreduce(bits)
+                mark("flag_allreduce")
             check(self.L.oo_adam_schedule(ptr(self.flags), ptr(bits), iters, int(part_on), self.lr, self.betas[0], self.betas[1],
                                           ptr(self.adam_t), ptr(self._adam_scal), stream()), "oo_adam_schedule")
+            mark("adam_schedule")
 
     # ---- the reference's `loss > 1e5 -> print, exit(-1)` guard (render_rays.py:109-111): the update kernel raises bit
     # OO_FLAG_EXPLODE of a step's flags; the host looks once per frame, without stalling the stream

@@ -5,6 +5,7 @@ per-object pixel state of train.py:203-205 is derived in the sampling kernel fro
 O(frames alive), not O(objects): a frame is dropped when the last ring slot referring to it is overwritten."""
 import ctypes
 
+import numpy as np
 import torch
 
 from ._lib import StoreArgs, check, lib, ptr, stream
@@ -15,7 +16,7 @@ class FrameStore:
         self.W, self.H, self.device = int(W), int(H), torch.device(device)
         self.capacity = 0
         self.rgbi = self.depth = self.t_wc = None
-        self.refs, self.free = [], []
+        self.refs, self.free = np.zeros(0, dtype=np.int64), []
         self._grow(int(capacity))
 
     # ---- storage ---------------------------------------------------------------------------------------------------------
@@ -29,7 +30,7 @@ class FrameStore:
             depth[:self.capacity].copy_(self.depth)
             t_wc[:self.capacity].copy_(self.t_wc)
         self.free = list(range(capacity - 1, self.capacity - 1, -1)) + self.free
-        self.refs += [0] * (capacity - self.capacity)
+        self.refs = np.concatenate([self.refs, np.zeros(capacity - self.capacity, dtype=np.int64)])
         self.rgbi, self.depth, self.t_wc, self.capacity = rgbi, depth, t_wc, capacity
 
     def bytes_per_frame(self):
@@ -55,8 +56,19 @@ class FrameStore:
         with torch.cuda.device(self.device):
             check(lib().oo_store_frame(ctypes.byref(a), stream()), "oo_store_frame")
 
-    def acquire(self, slot):
-        self.refs[slot] += 1
+    def acquire(self, slot, n=1):
+        self.refs[slot] += n
+
+    def release_many(self, slots):
+        """Drop one reference per entry of `slots` (int array, -1 = nothing)."""
+        slots = slots[slots >= 0]
+        if slots.size == 0:
+            return
+        np.subtract.at(self.refs, slots, 1)
+        for s in np.unique(slots).tolist():
+            if self.refs[s] <= 0:
+                self.refs[s] = 0
+                self.free.append(s)
 
     def release(self, slot):
         """Drop one reference; a slot nobody refers to goes back to the free list.  (Stream order makes the reuse safe: the

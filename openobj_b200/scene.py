@@ -111,6 +111,7 @@ class Scene:
         self.sample_out = None
         self._copy_stream = None
         self._sorted_ids = (None, None)
+        self._vis_cache = (None, None, None)
         self._empty_bits = None
         # the separate background model (train.py:236-242): one hidden-128 model, not part of the vmap ensemble; it lives
         # on the last rank (the ensemble's round-robin starts at rank 0)
@@ -141,20 +142,22 @@ class Scene:
             self._sorted_ids = (bbox_dict, sorted(int(k) for k in bbox_dict.keys()))
         return self._sorted_ids[1]
 
-    def _place(self, tab, i, o, slot, store_slot, bbox, frame_id):
-        """Ring slot `slot` of local object i now holds store frame `store_slot`."""
-        old = int(tab.slot_frame[i, slot])
-        if old >= 0:
-            self.store.release(old)
-        self.store.acquire(store_slot)
-        tab.slot_frame[i, slot] = store_slot
-        tab.slot_bbox[i, slot] = bbox
+    def _place_all(self, tab, placed, store_slot, frame_id):
+        """Ring slot `slot` of local object i now holds store frame `store_slot`, for every (i, object, slot, bbox) of this
+        frame at once (numpy fancy indexing: the per-object Python work is the keyframe policy alone)."""
+        ii = np.fromiter((p[0] for p in placed), dtype=np.int64, count=len(placed))
+        ss = np.fromiter((p[2] for p in placed), dtype=np.int64, count=len(placed))
+        self.store.release_many(tab.slot_frame[ii, ss].astype(np.int64))
+        self.store.acquire(store_slot, len(placed))
+        tab.slot_frame[ii, ss] = store_slot
+        tab.slot_bbox[ii, ss] = np.stack([np.asarray(p[3], dtype=np.float32) for p in placed])
         if self.part_mode:
-            tab.part_frame[i, slot] = int(frame_id / o.stride)             # (use_frame / stride).long(), vmap.py:438-440
-        tab.n_kf[i] = o.ring.n_keyframes
-        lat = o.ring.latest
-        if len(lat) >= 2:
-            tab.latest[i, 0], tab.latest[i, 1] = lat[-2], lat[-1]
+            tab.part_frame[ii, ss] = int(frame_id / placed[0][1].stride)      # (use_frame / stride).long(), vmap.py:438-440
+        tab.n_kf[ii] = np.fromiter((p[1].ring.n_keyframes for p in placed), dtype=np.int32, count=len(placed))
+        for i, o, _, _ in placed:
+            lat = o.ring.latest
+            if len(lat) >= 2:
+                tab.latest[i, 0], tab.latest[i, 1] = lat[-2], lat[-1]
 
     # ---- train.py:164-276 ---------------------------------------------------------------------------------
     def add_frame(self, sample):
@@ -179,7 +182,13 @@ class Scene:
         obj_clip, obj_cap = sample.get("obj_clip"), sample.get("obj_cap")
         placed = []                   # (tab, local index, object, ring slot, bbox)
         new_global = False
-        for obj_id in self._ids_of(bd):
+        ids = self._ids_of(bd)
+        # frames usually come with the same objects as the one before: once every id of this dict is known, only the ids this
+        # rank owns (and the background) are walked
+        key = (id(bd), len(bd), len(self.book.global_index))
+        if self._vis_cache[0] == key and self._vis_cache[1] is bd:
+            ids = self._vis_cache[2]
+        for obj_id in ids:
             if obj_id == -1:
                 continue
             if cfg.do_bg and obj_id == 0:
@@ -222,11 +231,16 @@ class Scene:
                 slot = o.push_slot(frame_id, _first(obj_clip, obj_id), _get(obj_cap, obj_id))
             placed.append((self.tab, i, o, slot, bd[obj_id]))
         self._objs = list(self.obj_dict.values())
+        if not new_global:
+            mine = [i for i in self._ids_of(bd) if i in self.book.local_index or (cfg.do_bg and i == 0)]
+            self._vis_cache = ((id(bd), len(bd), len(self.book.global_index)), bd, mine)
         # ---- the frame itself: ONE copy in the shared store (12 bytes per pixel whatever the number of objects)
         self.tab.t_wc[:] = twc32.numpy()
         g = self.store.alloc() if placed else -1
-        for tab, i, o, slot, bbox in placed:
-            self._place(tab, i, o, slot, g, np.asarray(bbox, dtype=np.float32), frame_id)
+        for tab in (self.tab, self.tab_bg):
+            mine = [(i, o, slot, bbox) for t, i, o, slot, bbox in placed if t is tab]
+            if mine:
+                self._place_all(tab, mine, g, frame_id)
         self.tab.upload()                                          # slot tables + the pose the store kernel reads
         if self.tab_bg is not None:
             self.tab_bg.upload()
