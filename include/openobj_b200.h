@@ -101,6 +101,14 @@ int oo_occupancy_activation(const float* alpha, const float* distances, long lon
 int oo_eval_points(const float* theta, const float* pts, long long n_pts, float pe_scale, float* occ, float* color,
                    float* clip, void* stream);
 
+/* Blackwell-native variant of oo_eval_points without the part-feature output: tcgen05.mma kind::tf32 with three-term error
+ * compensation (fp32-level accuracy), accumulators and the chained activations in tensor memory, the object's pre-split
+ * weights resident in shared memory; a tile = 128 points = the 128 TMEM lanes (csrc/oo_forward_tc.cu).  occ = sigmoid(alpha)
+ * and / or alpha (the x10 output) [n_pts], either may be NULL; color [n_pts][3].  err_flag: device int[1], zeroed by the
+ * caller, set to 1 if a tensor-core completion did not arrive within the (bounded) wait. */
+int oo_eval_points_tc(const float* theta, const float* pts, long long n_pts, float pe_scale, float* occ, float* alpha,
+                      float* color, int* err_flag, void* stream);
+
 /* ---- a4-a9: loss.step_batch_loss forward and backward as one pair of HBM-bound kernels
  *      (objnerf/loss.py:5-103, render_rays.py:6-117).  alpha [N][R][S], color [N][R][S][3],
  *      z [N][R][S], gt_depth [N][R], gt_color [N][R][3] float in [0,1], labels [N][R] u8,

@@ -101,6 +101,7 @@ _SIGS = {
                   c_int),
     "oo_make_grid": ([POINTER(Grid), c_void_p, c_void_p], c_int),
     "oo_eval_points": ([c_void_p, c_void_p, c_int64, c_float, c_void_p, c_void_p, c_void_p, c_void_p], c_int),
+    "oo_eval_points_tc": ([c_void_p, c_void_p, c_int64, c_float, c_void_p, c_void_p, c_void_p, c_void_p, c_void_p], c_int),
     "oo_occupancy_activation": ([c_void_p, c_void_p, c_int64, c_void_p, c_void_p], c_int),
     "oo_ray_box": ([c_void_p, c_void_p, POINTER(c_float), POINTER(c_float), c_int64, c_void_p, c_void_p, c_void_p, c_void_p],
                    c_int),

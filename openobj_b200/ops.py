@@ -188,10 +188,41 @@ def wide_autograd(emb, model, want_clip, params):
     return _WideFn.apply(emb, model, want_clip, *params)
 
 
-def eval_points(theta, points, scale=2.0, want_clip=True):
-    """Trainer.eval_points for ONE hidden-32 model (trainer.py:104-128): theta [1,PSTRIDE] (or [PSTRIDE]), points [n,3].
-    Returns occ [n] = sigmoid(alpha), color [n,3], clip [n,512] or None -- one launch for the whole query."""
+_TC_ERR = {}
+
+
+def eval_points_tc(theta, points, scale=2.0, want_alpha=False):
+    """The tcgen05 / TMEM forward (oo_eval_points_tc): occ [n] (or alpha when want_alpha), color [n,3].  The kernel's error
+    flag (a tensor-core completion that never arrived) is checked by check_tc()."""
     _dev(theta)
+    pts = points.reshape(-1, 3).contiguous().float()
+    n = pts.shape[0]
+    f32 = dict(dtype=torch.float32, device=theta.device)
+    out, color = torch.empty(n, **f32), torch.empty(n, 3, **f32)
+    err = _TC_ERR.get(theta.device)
+    if err is None:
+        err = _TC_ERR[theta.device] = torch.zeros(1, dtype=torch.int32, device=theta.device)
+    with _dev(theta):
+        check(lib().oo_eval_points_tc(ptr(theta), ptr(pts), n, float(scale), None if want_alpha else ptr(out),
+                                      ptr(out) if want_alpha else None, ptr(color), ptr(err), stream()), "oo_eval_points_tc")
+    return out, color
+
+
+def check_tc(device):
+    """Raises if a tcgen05 kernel reported a missed tensor-core completion (synchronises)."""
+    err = _TC_ERR.get(torch.device(device))
+    if err is not None and int(err.item()) != 0:
+        raise _lib.OOError("oo_eval_points_tc: a tcgen05.mma completion did not arrive (results are invalid)")
+
+
+def eval_points(theta, points, scale=2.0, want_clip=True, tensor_core=True):
+    """Trainer.eval_points for ONE hidden-32 model (trainer.py:104-128): theta [1,PSTRIDE] (or [PSTRIDE]), points [n,3].
+    Returns occ [n] = sigmoid(alpha), color [n,3], clip [n,512] or None -- one launch for the whole query.  Without the part
+    feature (what Trainer.meshing uses) the query runs on the tcgen05 / TMEM kernel."""
+    _dev(theta)
+    if not want_clip and tensor_core:
+        occ, color = eval_points_tc(theta, points, scale)
+        return occ, color, None
     pts = points.reshape(-1, 3).contiguous().float()
     n = pts.shape[0]
     f32 = dict(dtype=torch.float32, device=theta.device)

@@ -57,6 +57,8 @@ class Trainer:
         if float(occ.max()) == 0:
             print("no occ")
             return None
+        if self.hidden_feature_size == layout.HIDDEN and not want_clip:
+            ops.check_tc(pts.device)
         return occ, color, clip
 
     def sample_points_bbox(self, bbox, do_eval=True, draws=None):
