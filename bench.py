@@ -587,6 +587,118 @@ def run_ours(args):
     return 0
 
 
+# ------------------------------------------------------------------------------------------------------------
+# BASELINE config 5: render-only evaluation (full-frame RGB / depth / part-feature maps of every object, all-gather, z-merge)
+# ------------------------------------------------------------------------------------------------------------
+def run_eval(args):
+    import numpy as np
+    import torch
+    from openobj_b200 import _lib, cfg as C, dist as D, eval as E, utils as U, vmap as V
+    from openobj_b200.synthetic import object_layout
+    rank, world, local = D.init_from_env()
+    if not torch.cuda.is_available():
+        raise _lib.OOError("bench.py needs a CUDA device: the product path has no CPU fallback")
+    torch.cuda.set_device(local)
+    dev = torch.device("cuda", local)
+    cfg = C.room0_config()
+    cfg.training_device = cfg.data_device = str(dev)
+    W, H = cfg.W, cfg.H
+    n_total = args.objects
+    cam = V.cameraInfo(cfg)
+    boxes = object_layout(n_total, W, H, np.random.default_rng(0))
+    torch.manual_seed(0)
+    blank = (torch.zeros(W, H, 3, dtype=torch.uint8, device=dev), torch.ones(W, H, device=dev))
+    mine = []
+    for k, (x0, y0, x1, y1) in enumerate(boxes):
+        if k % world != rank:
+            torch.manual_seed(1000 + k)
+            continue
+        torch.manual_seed(1000 + k)
+        o = V.sceneObject(cfg, k + 1, blank[0], blank[1], None, torch.tensor([x0, x1, y0, y1]), torch.eye(4), 0, shared=True)
+        with torch.no_grad():
+            o.trainer.fc_occ_map.out_alpha.bias.fill_(0.8)          # opaque enough for the opacity >= 0.9 test (vmap.py:665)
+        z = 2.0 + 0.02 * (k % 50)
+        bb = U.BoundingBox()
+        bb.R = np.eye(3)
+        bb.center = np.array([((x0 + x1) / 2 - cfg.cx) / cfg.fx * z, ((y0 + y1) / 2 - cfg.cy) / cfg.fy * z, z])
+        bb.extent = np.array([(x1 - x0) / cfg.fx * z, (y1 - y0) / cfg.fy * z, 0.6])
+        o.bbox3dour = bb
+        mine.append(o)
+    steps, warmup = args.steps, max(min(args.warmup, 10), 3)
+
+    def pose(f):
+        T = np.eye(4)
+        T[:3, 3] = [0.01 * np.sin(0.3 * f), 0.01 * np.cos(0.2 * f), -0.002 * (f % 10)]
+        return T
+
+    stats = {}
+    hits = torch.zeros(1, dtype=torch.int64, device=dev)
+    for f in range(warmup):
+        E.render_frame(mine, pose(f), cam.rays_dir_cache, is_bg={0: True}, render_feat=True, stats=stats)
+    torch.cuda.synchronize(); D.barrier()
+    e0, e1 = cuda_timer()
+    clk = ClockSampler(local)
+    clk.__enter__()
+    time.sleep(0.02)
+    torch.cuda.synchronize(); D.barrier()
+    e0.record()
+    for f in range(steps):
+        depth, rgb, winner, feat = E.render_frame(mine, pose(warmup + f), cam.rays_dir_cache, is_bg={0: True}, render_feat=True,
+                                                  stats=stats)
+    e1.record()
+    torch.cuda.synchronize()
+    clk.__exit__()
+    D.barrier()
+    ms = D.max_over_ranks(e0.elapsed_time(e1), dev)
+    # per-kernel view on rank 0: K5 alone over this rank's objects, one frame
+    recs = []
+    jit = torch.rand(W * H, 150, device=dev)
+    ek0, ek1 = cuda_timer()
+    ek0.record()
+    for o in mine:
+        recs.append(o._render(pose(0), cam.rays_dir_cache, jitter=jit, jitter_by_pixel=True, want_rec=True))
+    ek1.record()
+    torch.cuda.synchronize()
+    k5_ms = ek0.elapsed_time(ek1)
+    n_hit_local = sum(int(r["n_hit"].item()) for r in recs)
+    n_hit_all = int(D.sum_over_ranks(n_hit_local, dev))
+    covered = float((winner >= 0).float().mean())
+    if rank == 0:
+        mac_pt = MAC_PER_POINT - 63 + 63 + MAC_CLIP_POINT                  # PE + trunk + colour head + clip_linear per sample point
+        k5_flop = 2.0 * mac_pt * 149 * n_hit_local
+        peaks = {}
+        try:
+            peaks = json.load(open(os.path.join(ROOT, "MEASURED_PEAKS.json")))
+        except OSError:
+            pass
+        from openobj_b200 import ops
+        peak = ops.fma_peak_tflops()
+        out = {
+            "metric": "full-frame eval frames/sec (every object rendered over all pixels: depth, RGB, 512-d part feature; "
+                      "all-gather; depth-test merge)", "value": steps / (ms * 1e-3), "unit": "frames/s", "n_gpus": world,
+            "steps": steps, "warmup": warmup, "ms_per_step": ms / steps, "higher_is_better": True, "scaling": "strong",
+            "vs_baseline": None, "dtype": "f32", "data": "synthetic",
+            "config": {"workload": "BASELINE configs[4]: render-only eval, %dx%d frames, %d objects in total (%d on rank 0), 149 "
+                                   "samples per ray, render_part on; one step = one pose" % (W, H, n_total, len(mine)),
+                       "objects_total": n_total, "hit_rays_per_frame": n_hit_all, "pixels_covered": covered,
+                       "parallelism": "objects sharded by ensemble index, rank = k mod %d; one all_gather_into_tensor of 8 B per "
+                                      "pixel and object + winner-only feature rows" % world},
+            "object_rays_per_s": n_hit_all * steps / (ms * 1e-3),
+            "clocks": clk.summary(),
+            "interconnect": stats,
+            "roofline": {"kernel": "k_render (K5: 149 samples per hit ray through the fused forward tile + compositing), this rank's "
+                                   "%d objects of one frame" % len(mine), "bound": "fma", "achieved": k5_flop / (k5_ms * 1e-3) / 1e12,
+                         "peak": peak, "unit": "TFLOP/s", "frac": k5_flop / (k5_ms * 1e-3) / 1e12 / peak, "traffic": None,
+                         "ms": k5_ms, "flop": k5_flop},
+            "gpu_launches": steps * (len(mine) * 4 + 2 + len(mine)),
+        }
+        print(json.dumps(out), file=_JSON_OUT, flush=True)
+    D.barrier()
+    if world > 1:
+        torch.distributed.destroy_process_group()
+    return 0
+
+
 def main():
     ap = argparse.ArgumentParser()
     ap.add_argument("--gpus", type=int, default=1)
@@ -597,15 +709,18 @@ def main():
     ap.add_argument("--part", type=int, default=1, help="part-level feature head on (room_0.json part_mode)")
     ap.add_argument("--fill-frames", type=int, default=20, help="untimed frames that fill the keyframe rings (SURVEY 8d)")
     ap.add_argument("--no-cpu", action="store_true", help="skip the CPU baseline / GPU-eager reference legs")
-    ap.add_argument("--config", type=int, default=2, choices=[2, 3, 4],
+    ap.add_argument("--config", type=int, default=2, choices=[2, 3, 4, 5],
                     help="BASELINE.json configs (1-based): 2 = room_0 shape, --objects per GPU (weak scaling; the headline); "
                          "3 = 100 objects in total, CLIP + part heads (strong scaling); 4 = ScanNet shape 640x480, 200 objects, "
-                         "part features off (strong scaling)")
+                         "part features off (strong scaling); 5 = render-only eval: --objects objects in total, one step = one "
+                         "pose (full-frame depth / RGB / part-feature maps, all-gather, z-merge)")
     ap.add_argument("--trace", action="store_true", help="per-rank host timings of every frame (stderr)")
     ap.add_argument("--device", default="cpu", help="--impl reference only: cpu (the driver's arm) or cuda:0 (eager reference)")
     args = ap.parse_args()
     if args.impl == "reference":
         return run_reference_arm(args)
+    if args.config == 5:
+        return run_eval(args)
     return run_ours(args)
 
 

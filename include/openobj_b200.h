@@ -366,8 +366,27 @@ typedef struct oo_render_args {
     uint8_t* mask; float* depth; uint8_t* rgb; float* feat;  /* [W][H], [W][H], [W][H][3], [W][H][512] or NULL */
     float* opacity;                      /* [W][H] or NULL */
     int* n_hit;                          /* [1] */
+    /* compact per-hit records for the winner-only feature path (both or neither): ray_rec [W*H][OO_RENDER_REC] = {S[32] =
+     * sum_i T_i hp_i (clip_linear activations composited), opacity, 0, 0, 0} of hit j (rank among the rays that intersect the
+     * box), hit_pix [W*H] = pixel index of hit j.  Use with feat == NULL, then oo_winner_features after the merge. */
+    float* ray_rec; int32_t* hit_pix;
+    /* feat == NULL runs on the tcgen05 / TMEM kernel (csrc/oo_forward_tc.cu) unless force_mma_sync != 0 (the mma.sync tile
+     * kernel, kept for the dense-feature output and as the comparison arm); tc_err: device int[1] or NULL, set to 1 if a
+     * tensor-core completion did not arrive within the bounded wait. */
+    int force_mma_sync; int* tc_err;
 } oo_render_args;
+#define OO_RENDER_REC 36
 int oo_render_object(const oo_render_args* a, void* stream);
+/* the depth-test merge over per-object pointers (device arrays of n_obj pointers to [n_pix] / [n_pix][3] maps, in global
+ * insertion order): what a sharded run uses on the all-gathered buffer without re-packing it */
+int oo_zmerge_ptr(const uint8_t* const* masks, const float* const* depths, const uint8_t* const* rgbs, const uint8_t* is_bg,
+                  int n_obj, int64_t n_pix, float* depth_out, uint8_t* rgb_out, int32_t* winner_out, void* stream);
+/* part features of the pixels object k_global won (winner [n_pix] from the merge): rows [<= cap_rows][512] = W_ocl S +
+ * b_ocl opacity, row_pix = their pixels, n_rows [1] = running count (zeroed by the caller; rows beyond cap_rows are counted
+ * but not written).  The 512-wide layer runs once per WON pixel instead of once per hit of every object
+ * (vmap.py:660-670 with render_part, train.py:577-594). */
+int oo_winner_features(const float* theta1, const float* ray_rec, const int32_t* hit_pix, const int* n_hit, const int32_t* winner,
+                       int k_global, int64_t cap_rows, float* rows, int32_t* row_pix, int* n_rows, void* stream);
 int oo_zmerge(const uint8_t* masks, const float* depths, const uint8_t* rgbs, const uint8_t* is_bg, int n_obj,
               int64_t n_pix, float* depth_out, uint8_t* rgb_out, int32_t* winner_out, void* stream);
 

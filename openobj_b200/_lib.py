@@ -64,7 +64,8 @@ class RenderArgs(Structure):
                 ("theta1", c_void_p), ("T_wc", c_void_p), ("T_oc", c_void_p), ("half_extent", c_void_p),
                 ("rays_dir", c_void_p), ("jitter", c_void_p), ("jitter_by_rank", c_int), ("lin_host", c_void_p),
                 ("mask", c_void_p), ("depth", c_void_p), ("rgb", c_void_p), ("feat", c_void_p),
-                ("opacity", c_void_p), ("n_hit", c_void_p)]
+                ("opacity", c_void_p), ("n_hit", c_void_p), ("ray_rec", c_void_p), ("hit_pix", c_void_p),
+                ("force_mma_sync", c_int), ("tc_err", c_void_p)]
 
 
 _SIGS = {
@@ -99,6 +100,9 @@ _SIGS = {
     "oo_render_object": ([POINTER(RenderArgs), c_void_p], c_int),
     "oo_zmerge": ([c_void_p, c_void_p, c_void_p, c_void_p, c_int, c_int64, c_void_p, c_void_p, c_void_p, c_void_p],
                   c_int),
+    "oo_zmerge_ptr": ([c_void_p, c_void_p, c_void_p, c_void_p, c_int, c_int64, c_void_p, c_void_p, c_void_p, c_void_p], c_int),
+    "oo_winner_features": ([c_void_p, c_void_p, c_void_p, c_void_p, c_void_p, c_int, c_int64, c_void_p, c_void_p, c_void_p,
+                            c_void_p], c_int),
     "oo_make_grid": ([POINTER(Grid), c_void_p, c_void_p], c_int),
     "oo_eval_points": ([c_void_p, c_void_p, c_int64, c_float, c_void_p, c_void_p, c_void_p, c_void_p], c_int),
     "oo_eval_points_tc": ([c_void_p, c_void_p, c_int64, c_float, c_void_p, c_void_p, c_void_p, c_void_p, c_void_p], c_int),

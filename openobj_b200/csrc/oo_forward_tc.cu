@@ -1,22 +1,25 @@
-// Blackwell-native forward of one hidden-32 OccupancyMap + UniDirsEmbed at free query points -- the compute of
-// Trainer.eval_points / the meshing grid (objnerf/trainer.py:46-69,104-128; embedding.py:46-55; model.py:61-103;
-// render_rays.py:6-14) -- on the 5th-generation tensor cores: tcgen05.mma kind::tf32, accumulators AND the A operands in
-// tensor memory, the object's weights pre-split and resident in shared memory.
+// Blackwell-native forward of one hidden-32 OccupancyMap + UniDirsEmbed on the 5th-generation tensor cores: tcgen05.mma
+// kind::tf32, accumulators AND the A operands in tensor memory, the object's weights pre-split and resident in shared memory.
+// Two entry points share the kernel:
+//   * oo_eval_points_tc : Trainer.eval_points / the meshing grid (objnerf/trainer.py:46-69,104-128) at free query points;
+//   * oo_render_object (feat == NULL) : render_2D_syn (vmap.py:604-685, trainer.py:130-198) -- the 149 midpoints of every hit
+//     ray through the network, occupancy -> termination compositing along the ray (render_rays.py:32-63), masked depth / rgb
+//     maps and the compact per-hit record {S = sum_i T_i hp_i, opacity} the winner-only feature path consumes.
 //
-//   * one CTA per SM, 128 threads, a tile = 128 query points = the 128 lanes of tensor memory: thread p owns point p;
-//   * the layers are chained through TMEM: an MMA leaves D[point][unit] (fp32) in TMEM, the owning thread reads its row with
-//     tcgen05.ld, applies bias + ReLU, splits the result into (hi, lo) TF32 halves and writes them back with tcgen05.st as
-//     the A operand [point][k] of the next layer -- activations never touch shared memory;
-//   * fp32-level accuracy with TF32 inputs by three-term error compensation, exactly like the mma.sync path of the training
+//   - one CTA per SM, 512 threads, a tile = 128 points = the 128 lanes of tensor memory; FOUR threads share a point (warp w:
+//     lane quarter w % 4, sub-thread w / 4): they split the encoder by projection direction and every epilogue by column;
+//   - the layers are chained through TMEM: an MMA leaves D[point][unit] (fp32) in TMEM, a thread reads its columns of its
+//     point's row with tcgen05.ld, applies bias + ReLU, splits the result into (hi, lo) TF32 halves and writes them back with
+//     tcgen05.st as the A operand [point][k] of the next layer -- hidden activations never touch shared memory;
+//   - fp32-level accuracy with TF32 inputs by three-term error compensation, exactly like the mma.sync path of the training
 //     tile (oo_tile.h): x = hi + lo, a.b ~ lo_a hi_b + hi_a lo_b + hi_a hi_b accumulated in fp32 -> 3 tcgen05.mma per
 //     8-wide k-step.  The weights are constant per object, so their (hi, lo) copies are formed ONCE when the CTA starts and
 //     stay in shared memory in the canonical K-major core-matrix layout the MMA's shared-memory descriptor addresses
-//     ([k / 4][32 rows][4]: 8 rows x 16 bytes per core matrix, SBO = 128 B between 8-row groups, LBO = 512 B between 16-byte
+//     ([k / 4][rows][4]: 8 rows x 16 bytes per core matrix, SBO = 128 B between 8-row groups, LBO = rows x 16 B between 16-byte
 //     k-chunks); nothing is re-split per tile;
-//   * the encoder and the two tiny output layers (out_alpha 32 -> 1, out_color 32 -> 3) run in registers of the owning
-//     thread in the operation order of the training tile (phase 1 / phase 7 of oo_tile.h).
-//
-// Per 128 points: 132 tcgen05.mma (M128 N32 K8) = 4.3 M tensor MACs for 1.43 M algorithmic MACs.
+//   - the two tiny output layers (out_alpha 32 -> 1, out_color 32 -> 3) are dot products in registers, partial sums of the
+//     four sub-threads combined through shared memory in a fixed order.
+// Per 128 points: 132 tcgen05.mma M128 N32 K8 (eval) or 102 x N32 + 30 x N64 (render, with clip_linear).
 #include "../../include/openobj_b200.h"
 #include "oo_common.cuh"
 #include "oo_tile.h"
@@ -25,70 +28,75 @@ using namespace oo;
 
 namespace {
 
-constexpr int TC_M = 128, TC_THREADS = 128;
+constexpr int TC_M = 128, TC_THREADS = 512;
 // tensor-memory columns (32-bit each, 128 lanes)
 constexpr int C_E1H = 0, C_E1L = 88, C_E2H = 176, C_E2L = 224, C_HAH = 272, C_HAL = 304, C_HBH = 336, C_HBL = 368, C_D = 400;
 constexpr int TC_COLS = 512;
-// shared memory (floats): weight blocks in canonical layout (hi copies, then lo copies), small vectors, the mbarrier
-constexpr int K_IN = 88, K_H = 32, K_CATB = 88, K_CLB = 48;
+constexpr int E_COLS = 136;                          // 88 columns of e1 (87 values + a zero) + 48 of e2 (42 + six zeros)
+// shared memory (floats): weight blocks in canonical layout (hi copies, then lo copies)
+constexpr int K_IN = 88, K_H = 32, K_CATB = 88, K_HDB = 48, N_HD = 64;
 constexpr int WB_IN = 0, WB_M1 = WB_IN + H * K_IN, WB_CATA = WB_M1 + H * K_H, WB_CATB = WB_CATA + H * K_H,
-              WB_M2 = WB_CATB + H * K_CATB, WB_CLA = WB_M2 + H * K_H, WB_CLB = WB_CLA + H * K_H, WB_TOTAL = WB_CLB + H * K_CLB;
-constexpr int SB_BIAS = 2 * WB_TOTAL;                 // in, m1, cat, m2, cl: 5 x 32
-constexpr int SB_WA = SB_BIAS + 5 * H;                // out_alpha.weight [32], bias at +32
+              WB_M2 = WB_CATB + H * K_CATB, WB_HDA = WB_M2 + H * K_H, WB_HDB = WB_HDA + N_HD * K_H,
+              WB_TOTAL = WB_HDB + N_HD * K_HDB;
+constexpr int SB_BIAS = 2 * WB_TOTAL;                 // in, m1, cat, m2 (4 x 32), heads (64: color_linear, clip_linear)
+constexpr int SB_WA = SB_BIAS + 4 * H + N_HD;         // out_alpha.weight [32], bias at +32
 constexpr int SB_WOC = SB_WA + 36;                    // out_color.weight [3][32], bias at +96
 constexpr int SB_PE = SB_WOC + 100;                   // B_layer.weight [21][3]
-constexpr int SB_BAR = SB_PE + 64;                    // mbarrier (8 bytes, 8-byte aligned: SB_BAR is even)
-constexpr int SB_FLOATS = SB_BAR + 4;
-// at least half of the SM's shared memory is requested so that two CTAs can never share an SM: each allocates all 512
-// tensor-memory columns, and a second CTA would wait for them forever
-constexpr size_t TC_SMEM = 120 * 1024;
-static_assert(SB_FLOATS * 4 <= TC_SMEM && SB_BAR % 2 == 0, "shared-memory map");
+constexpr int SB_BAR = SB_PE + 64;                    // mbarrier (8 bytes; SB_BAR is even)
+constexpr int SB_PT = SB_BAR + 4;                     // per point: t0, t1, t2, z  [4][128]
+constexpr int SB_STG = SB_PT + 4 * TC_M;              // encoder staging [136][128]; later the per-point results (see R_*)
+// per-point results, aliasing the staging area once the embedding is in tensor memory
+constexpr int R_APART = 0;                            // [4][128]    partial out_alpha dot products of the four sub-threads
+constexpr int R_CPART = R_APART + 4 * TC_M;           // [4][3][128] partial out_color dot products
+constexpr int R_OCC = R_CPART + 12 * TC_M;            // [128] occupancy
+constexpr int R_COL = R_OCC + TC_M;                   // [3][128] colour
+constexpr int R_T = R_COL + 3 * TC_M;                 // [128] termination weights
+constexpr int R_HP = R_T + TC_M;                      // [32][128] clip_linear activations
+constexpr int R_END = R_HP + H * TC_M;
+static_assert(R_END <= E_COLS * TC_M, "per-point results must fit in the staging area");
+constexpr int SB_OPEN = SB_STG + E_COLS * TC_M;       // [2][40] open-ray accumulators {depth, opac, c0, c1, c2, carry, -, -, S[32]}
+constexpr int SB_FLOATS = SB_OPEN + 80;
+constexpr size_t TC_SMEM = (size_t)SB_FLOATS * 4;
+// more than half of the SM's shared memory: two CTAs can never share an SM (each allocates all 512 tensor-memory columns; a
+// second CTA would wait for them forever)
+static_assert(TC_SMEM > 116 * 1024 && TC_SMEM <= 227 * 1024 && SB_BAR % 2 == 0, "shared-memory map");
 
 // instruction descriptor of tcgen05.mma kind::tf32: D fp32 (bits 4-5 = 1), A and B TF32 (bits 7-9 / 10-12 = 2), both K-major,
 // N >> 3 at bit 17, M >> 4 at bit 24
-constexpr uint32_t IDESC = (1u << 4) | (2u << 7) | (2u << 10) | ((uint32_t)(H >> 3) << 17) | ((uint32_t)(TC_M >> 4) << 24);
-
-__device__ __forceinline__ uint64_t smem_desc(uint32_t byte_addr) {
-    // K-major, no swizzle: start >> 4 | LBO (512 B, next 16-byte k-chunk) >> 4 at bit 16 | SBO (128 B, next 8 rows) >> 4 at
-    // bit 32 | descriptor version 1 (sm_100) at bit 46
-    return (uint64_t)((byte_addr & 0x3FFFFu) >> 4) | ((uint64_t)(512u >> 4) << 16) | ((uint64_t)(128u >> 4) << 32) | (1ull << 46);
+__host__ __device__ constexpr uint32_t idesc(int n) {
+    return (1u << 4) | (2u << 7) | (2u << 10) | ((uint32_t)(n >> 3) << 17) | ((uint32_t)(TC_M >> 4) << 24);
 }
 
-__device__ __forceinline__ void umma_ts(uint32_t d_tmem, uint32_t a_tmem, uint64_t b_desc, uint32_t accumulate) {
+__device__ __forceinline__ uint64_t smem_desc(uint32_t byte_addr, uint32_t lbo_bytes) {
+    // K-major, no swizzle: start >> 4 | LBO (next 16-byte k-chunk) >> 4 at bit 16 | SBO (128 B, next 8 rows) >> 4 at bit 32 |
+    // descriptor version 1 (sm_100) at bit 46
+    return (uint64_t)((byte_addr & 0x3FFFFu) >> 4) | ((uint64_t)(lbo_bytes >> 4) << 16) | ((uint64_t)(128u >> 4) << 32) | (1ull << 46);
+}
+
+__device__ __forceinline__ void umma_ts(uint32_t d_tmem, uint32_t a_tmem, uint64_t b_desc, uint32_t id, uint32_t accumulate) {
     asm volatile("{\n\t.reg .pred p;\n\tsetp.ne.b32 p, %4, 0;\n\t"
                  "tcgen05.mma.cta_group::1.kind::tf32 [%0], [%1], %2, %3, p;\n\t}\n"
-                 ::"r"(d_tmem), "r"(a_tmem), "l"(b_desc), "r"(IDESC), "r"(accumulate) : "memory");
+                 ::"r"(d_tmem), "r"(a_tmem), "l"(b_desc), "r"(id), "r"(accumulate) : "memory");
 }
 
-// D (+)= A [128 x K] * W^T with A's (hi, lo) halves in TMEM columns a_hi / a_lo and W's in the shared blocks w_hi / w_lo
-__device__ __forceinline__ void layer_mma(uint32_t tm, int a_hi, int a_lo, uint32_t w_hi, uint32_t w_lo, int K, bool first) {
+// D (+)= A [128 x K] * W^T with A's (hi, lo) halves in TMEM columns a_hi / a_lo and W's [n rows] x K in the shared blocks
+// w_hi / w_lo (rows_blk = rows the block was staged with: its k-chunk stride is rows_blk x 16 bytes)
+__device__ __forceinline__ void layer_mma(uint32_t tm, int a_hi, int a_lo, uint32_t w_hi, uint32_t w_lo, int K, int n, int rows_blk,
+                                          bool first) {
+    const uint32_t lbo = (uint32_t)rows_blk * 16u, id = idesc(n);
     for (int s = 0; s < K / 8; ++s) {
-        const uint64_t bh = smem_desc(w_hi + (uint32_t)(2 * s) * 512u), bl = smem_desc(w_lo + (uint32_t)(2 * s) * 512u);
-        umma_ts(tm + C_D, tm + a_lo + 8 * s, bh, (first && s == 0) ? 0u : 1u);      // small terms first
-        umma_ts(tm + C_D, tm + a_hi + 8 * s, bl, 1u);
-        umma_ts(tm + C_D, tm + a_hi + 8 * s, bh, 1u);
+        const uint64_t bh = smem_desc(w_hi + (uint32_t)(2 * s) * lbo, lbo), bl = smem_desc(w_lo + (uint32_t)(2 * s) * lbo, lbo);
+        umma_ts(tm + C_D, tm + a_lo + 8 * s, bh, id, (first && s == 0) ? 0u : 1u);      // small terms first
+        umma_ts(tm + C_D, tm + a_hi + 8 * s, bl, id, 1u);
+        umma_ts(tm + C_D, tm + a_hi + 8 * s, bh, id, 1u);
     }
 }
 
-// tcgen05.st / tcgen05.ld of 8 / 32 consecutive columns of this thread's lane WITHOUT the completion wait: a layer's stores
-// are awaited once (publish_tmem), its 32 accumulator columns arrive with one load and one wait
+// tcgen05.st of 8 consecutive columns of this thread's lane; stores are awaited once per layer (publish_tmem)
 __device__ __forceinline__ void tm_st8_nw(uint32_t addr, const float* v) {
     asm volatile("tcgen05.st.sync.aligned.32x32b.x8.b32 [%0], {%1,%2,%3,%4,%5,%6,%7,%8};" ::"r"(addr), "r"(__float_as_uint(v[0])),
                  "r"(__float_as_uint(v[1])), "r"(__float_as_uint(v[2])), "r"(__float_as_uint(v[3])), "r"(__float_as_uint(v[4])),
                  "r"(__float_as_uint(v[5])), "r"(__float_as_uint(v[6])), "r"(__float_as_uint(v[7])) : "memory");
-}
-__device__ __forceinline__ void tm_ld32(uint32_t addr, float* v) {
-    uint32_t r[32];
-    asm volatile("tcgen05.ld.sync.aligned.32x32b.x32.b32 {%0,%1,%2,%3,%4,%5,%6,%7,%8,%9,%10,%11,%12,%13,%14,%15,%16,%17,%18,%19,%20,%21,"
-                 "%22,%23,%24,%25,%26,%27,%28,%29,%30,%31}, [%32];"
-                 : "=r"(r[0]), "=r"(r[1]), "=r"(r[2]), "=r"(r[3]), "=r"(r[4]), "=r"(r[5]), "=r"(r[6]), "=r"(r[7]), "=r"(r[8]), "=r"(r[9]),
-                   "=r"(r[10]), "=r"(r[11]), "=r"(r[12]), "=r"(r[13]), "=r"(r[14]), "=r"(r[15]), "=r"(r[16]), "=r"(r[17]), "=r"(r[18]),
-                   "=r"(r[19]), "=r"(r[20]), "=r"(r[21]), "=r"(r[22]), "=r"(r[23]), "=r"(r[24]), "=r"(r[25]), "=r"(r[26]), "=r"(r[27]),
-                   "=r"(r[28]), "=r"(r[29]), "=r"(r[30]), "=r"(r[31])
-                 : "r"(addr));
-    asm volatile("tcgen05.wait::ld.sync.aligned;" ::: "memory");
-#pragma unroll
-    for (int i = 0; i < 32; ++i) v[i] = __uint_as_float(r[i]);
 }
 
 __device__ __forceinline__ void split(float x, float& hi, float& lo) {
@@ -96,34 +104,33 @@ __device__ __forceinline__ void split(float x, float& hi, float& lo) {
     lo = x - hi;
 }
 
-// one weight matrix [32][K_real] (row-major in theta, `ld` floats per row, columns col0 ..) -> canonical (hi, lo) blocks
-__device__ void stage_block(int tid, float* sm, int blk, const float* __restrict__ W, int ld, int col0, int k_real, int K) {
-    for (int i = tid; i < H * K; i += TC_THREADS) {
+// one weight matrix [rows][k_real] (row-major in theta, `ld` floats per row, columns col0 ..) -> rows row0 .. of a canonical
+// (hi, lo) block staged for rows_blk rows
+__device__ void stage_block(int tid, float* sm, int blk, const float* __restrict__ W, int ld, int col0, int k_real, int K, int rows,
+                            int row0, int rows_blk) {
+    for (int i = tid; i < rows * K; i += TC_THREADS) {
         const int j = i / K, k = i - j * K;
         const float v = k < k_real ? W[j * ld + col0 + k] : 0.f;
         float hi, lo;
         split(v, hi, lo);
-        const int e = (k >> 2) * (H * 4) + j * 4 + (k & 3);
+        const int e = (k >> 2) * (rows_blk * 4) + (row0 + j) * 4 + (k & 3);
         sm[blk + e] = hi;
         sm[WB_TOTAL + blk + e] = lo;
     }
 }
 
-// bias + ReLU on the 32 accumulator columns of this thread's point, result into v; then (hi, lo) -> TMEM columns
-__device__ __forceinline__ void epilogue(uint32_t tm_lane, const float* __restrict__ bias, float* v) {
-    tm_ld32(tm_lane + C_D, v);
+// 8 accumulator columns c0 .. c0+7 of this thread's point: bias + ReLU into v
+__device__ __forceinline__ void epilogue8(uint32_t tm_lane, int c0, const float* __restrict__ bias, float* v) {
+    tm_ld<8>(tm_lane + C_D + c0, v);
 #pragma unroll
-    for (int j = 0; j < H; ++j) v[j] = fmaxf(v[j] + bias[j], 0.f);
+    for (int j = 0; j < 8; ++j) v[j] = fmaxf(v[j] + bias[c0 + j], 0.f);
 }
-__device__ __forceinline__ void put_split(uint32_t tm_lane, int col_hi, int col_lo, const float* v) {
+__device__ __forceinline__ void put_split8(uint32_t tm_lane, int col_hi, int col_lo, const float* v) {
+    float hi[8], lo[8];
 #pragma unroll
-    for (int q = 0; q < H; q += 8) {
-        float hi[8], lo[8];
-#pragma unroll
-        for (int i = 0; i < 8; ++i) split(v[q + i], hi[i], lo[i]);
-        tm_st8_nw(tm_lane + col_hi + q, hi);
-        tm_st8_nw(tm_lane + col_lo + q, lo);
-    }
+    for (int i = 0; i < 8; ++i) split(v[i], hi[i], lo[i]);
+    tm_st8_nw(tm_lane + col_hi, hi);
+    tm_st8_nw(tm_lane + col_lo, lo);
 }
 
 // wait for phase `parity` of the mbarrier; bounded (a descriptor mistake must end as an error code, not as a hung GPU)
@@ -145,34 +152,75 @@ __device__ __forceinline__ void publish_tmem() {
     __syncthreads();
     asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
 }
+__device__ __forceinline__ void commit(uint32_t bar) {
+    asm volatile("tcgen05.commit.cta_group::1.mbarrier::arrive::one.shared::cluster.b64 [%0];" ::"r"(bar) : "memory");
+}
+__device__ __forceinline__ float wsum32(float v) {
+#pragma unroll
+    for (int o = 16; o > 0; o >>= 1) v += __shfl_xor_sync(0xffffffffu, v, o);
+    return v;
+}
 
-__global__ void __launch_bounds__(TC_THREADS, 1) k_forward_tc(const float* __restrict__ theta, const float* __restrict__ pts,
-                                                              long long n_pts, float scale, float* __restrict__ occ,
-                                                              float* __restrict__ alpha_out, float* __restrict__ color,
-                                                              int* __restrict__ err) {
+struct TcArgs {
+    const float* theta;
+    float scale;
+    int* err;
+    // eval-points mode
+    const float* pts; long long n_pts; float* occ; float* alpha; float* color;
+    // render mode: hit rays [j0, j1) of this CTA x (n_bins - 1) samples
+    int n_bins;
+    const int* n_hit; const int* list; const float* near_; const float* far_; const float* lin; const float* jitter;
+    int jitter_by_rank;
+    const float* rays_dir; const float* T_wc;
+    uint8_t* mask; float* depth_out; uint8_t* rgb; float* opacity; float* ray_rec;
+};
+
+template <bool RENDER>
+__global__ void __launch_bounds__(TC_THREADS, 1) k_forward_tc(const TcArgs a) {
     extern __shared__ __align__(128) float sm[];
     __shared__ uint32_t tm_base_s;
-    const int tid = threadIdx.x, warp = tid >> 5;
+    const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
+    const int sub = warp >> 2, p = 32 * (warp & 3) + lane;             // four threads (sub 0..3) share point p
+    const float* theta = a.theta;
+    long long q_begin = 0, q_end = 0;                                   // this CTA's range of points
+    int nmid = 1;
+    if (RENDER) {
+        const int n_hit = a.n_hit[0];
+        if (n_hit <= 1) return;                                         // trainer.py:167 "<= 1 -> miss"
+        nmid = a.n_bins - 1;
+        const int j0 = (int)(((long long)n_hit * blockIdx.x) / gridDim.x), j1 = (int)(((long long)n_hit * (blockIdx.x + 1)) / gridDim.x);
+        if (j0 >= j1) return;
+        q_begin = (long long)j0 * nmid; q_end = (long long)j1 * nmid;
+    } else {
+        const long long n_tiles = (a.n_pts + TC_M - 1) / TC_M;
+        const long long t0 = n_tiles * blockIdx.x / gridDim.x, t1 = n_tiles * (blockIdx.x + 1) / gridDim.x;
+        if (t0 >= t1) return;
+        q_begin = t0 * TC_M; q_end = t1 * TC_M < a.n_pts ? t1 * TC_M : a.n_pts;
+    }
     // ---- once per CTA: the object's weights as canonical (hi, lo) blocks, small vectors, TMEM, the mbarrier
-    stage_block(tid, sm, WB_IN, theta + OFF_IN_W, E1, 0, E1, K_IN);
-    stage_block(tid, sm, WB_M1, theta + OFF_M1_W, H, 0, H, K_H);
-    stage_block(tid, sm, WB_CATA, theta + OFF_CAT_W, H + E1, 0, H, K_H);
-    stage_block(tid, sm, WB_CATB, theta + OFF_CAT_W, H + E1, H, E1, K_CATB);
-    stage_block(tid, sm, WB_M2, theta + OFF_M2_W, H, 0, H, K_H);
-    stage_block(tid, sm, WB_CLA, theta + OFF_CL_W, H + E2, 0, H, K_H);
-    stage_block(tid, sm, WB_CLB, theta + OFF_CL_W, H + E2, H, E2, K_CLB);
+    stage_block(tid, sm, WB_IN, theta + OFF_IN_W, E1, 0, E1, K_IN, H, 0, H);
+    stage_block(tid, sm, WB_M1, theta + OFF_M1_W, H, 0, H, K_H, H, 0, H);
+    stage_block(tid, sm, WB_CATA, theta + OFF_CAT_W, H + E1, 0, H, K_H, H, 0, H);
+    stage_block(tid, sm, WB_CATB, theta + OFF_CAT_W, H + E1, H, E1, K_CATB, H, 0, H);
+    stage_block(tid, sm, WB_M2, theta + OFF_M2_W, H, 0, H, K_H, H, 0, H);
+    stage_block(tid, sm, WB_HDA, theta + OFF_CL_W, H + E2, 0, H, K_H, H, 0, N_HD);          // color_linear rows 0..31
+    stage_block(tid, sm, WB_HDA, theta + OFF_CP_W, H + E2, 0, H, K_H, H, H, N_HD);          // clip_linear  rows 32..63
+    stage_block(tid, sm, WB_HDB, theta + OFF_CL_W, H + E2, H, E2, K_HDB, H, 0, N_HD);
+    stage_block(tid, sm, WB_HDB, theta + OFF_CP_W, H + E2, H, E2, K_HDB, H, H, N_HD);
     if (tid < H) {
         sm[SB_BIAS + tid] = theta[OFF_IN_B + tid];
         sm[SB_BIAS + H + tid] = theta[OFF_M1_B + tid];
         sm[SB_BIAS + 2 * H + tid] = theta[OFF_CAT_B + tid];
         sm[SB_BIAS + 3 * H + tid] = theta[OFF_M2_B + tid];
         sm[SB_BIAS + 4 * H + tid] = theta[OFF_CL_B + tid];
+        sm[SB_BIAS + 5 * H + tid] = theta[OFF_CP_B + tid];
         sm[SB_WA + tid] = theta[OFF_A_W + tid];
     }
     if (tid < 3 * H) sm[SB_WOC + tid] = theta[OFF_OC_W + tid];
     if (tid < 3) sm[SB_WOC + 3 * H + tid] = theta[OFF_OC_B + tid];
     if (tid == 0) sm[SB_WA + H] = theta[OFF_A_B];
     if (tid < NDIR * 3) sm[SB_PE + tid] = theta[OFF_PE_B + tid];
+    if (tid < 80) sm[SB_OPEN + tid] = (tid == 5 || tid == 45) ? 1.f : 0.f;      // carry (free-probability product) starts at 1
     const uint32_t bar = (uint32_t)__cvta_generic_to_shared(sm + SB_BAR);
     if (tid == 0) {
         asm volatile("mbarrier.init.shared::cta.b64 [%0], 1;" ::"r"(bar) : "memory");
@@ -193,119 +241,164 @@ __global__ void __launch_bounds__(TC_THREADS, 1) k_forward_tc(const float* __res
     uint32_t phase = 0;
     bool ok = true;
     const float* bias = sm + SB_BIAS;
+    float* pt = sm + SB_PT;
+    float* stg = sm + SB_STG;
+    float* open = sm + SB_OPEN;
+    int cur = 0;                                                        // which open-ray slot continues from the previous tile
+    const float* Tw = a.T_wc;
 
-    const long long n_tiles = (n_pts + TC_M - 1) / TC_M;
-    for (long long tile = blockIdx.x; tile < n_tiles; tile += gridDim.x) {
-        const long long p = tile * TC_M + tid;
-        const bool live = p < n_pts;
-        // ---- encoder (embedding.py:46-55; arithmetic of oo_tile.h phase 0 / 1): e = [t, sin(pi 2^k B t)] -> (hi, lo) A operands
-        float t0 = 0.f, t1 = 0.f, t2 = 0.f;
-        if (live) {
-            t0 = pts[3 * p] / scale; t1 = pts[3 * p + 1] / scale; t2 = pts[3 * p + 2] / scale;
-        }
-        {
-            float sn[NDIR], cs[NDIR];
-#pragma unroll
-            for (int d = 0; d < NDIR; ++d) {
-                const float proj = sm[SB_PE + 3 * d] * t0 + sm[SB_PE + 3 * d + 1] * t1 + sm[SB_PE + 3 * d + 2] * t2;
-                sincosf(proj * PI_F, &sn[d], &cs[d]);
-            }
-            float hi[8], lo[8];
-            // columns 0 .. 135: the 88 columns of e1 (87 values + one zero), then the 48 columns of e2 (42 values + six zeros);
-            // value q of e1 is t (q < 3) or band (q - 3) / 21 of direction (q - 3) % 21; e2 continues with bands 4 and 5
-#pragma unroll
-            for (int q = 0; q < 136; ++q) {
-                const int row = q < 88 ? q : q - 1;            // embedding row of this column (column 87 is e1's zero pad)
-                float v = 0.f;
-                if (q < 3) v = q == 0 ? t0 : q == 1 ? t1 : t2;
-                else if (q != 87 && row < EMB) {
-                    const int d = (row - 3) % NDIR;
-                    v = sn[d];
-                    const float s2 = 2.f * sn[d] * cs[d], c2 = (cs[d] - sn[d]) * (cs[d] + sn[d]);   // next band of this direction
-                    sn[d] = s2; cs[d] = c2;
+    for (long long q0 = q_begin; q0 < q_end; q0 += TC_M) {
+        const int npts = (int)((q_end - q0) < TC_M ? (q_end - q0) : TC_M);
+        // ---- (0) the tile's points: scaled coordinates t = x / scale (embedding.py:47) and, when rendering, the sample depth
+        if (tid < TC_M) {
+            float t0 = 0.f, t1 = 0.f, t2 = 0.f, zm = 0.f;
+            if (tid < npts) {
+                if (RENDER) {
+                    // midpoints of the jittered stratified bins (trainer.py:174-178, utils.py:342-379), points = o + d z
+                    const long long q = q0 + tid;
+                    const int j = (int)(q / nmid), kk = (int)(q - (long long)j * nmid);
+                    const int pix = a.list[j];
+                    const float near = a.near_[pix], far = a.far_[pix];
+                    const float range = __fsub_rn(far, near), blen = __fdiv_rn(range, (float)a.n_bins);
+                    const float* u = a.jitter + (size_t)(a.jitter_by_rank ? j : pix) * a.n_bins;
+                    const float za = __fadd_rn(__fadd_rn(__fmul_rn(range, a.lin[kk]), near), __fmul_rn(u[kk], blen));
+                    const float zb = __fadd_rn(__fadd_rn(__fmul_rn(range, a.lin[kk + 1]), near), __fmul_rn(u[kk + 1], blen));
+                    zm = __fmul_rn(0.5f, __fadd_rn(zb, za));
+                    const float* dc = a.rays_dir + (size_t)pix * 3;
+                    const float dx = dc[0], dy = dc[1], dz = dc[2];
+                    const float wx = Tw[0] * dx + Tw[1] * dy + Tw[2] * dz, wy = Tw[4] * dx + Tw[5] * dy + Tw[6] * dz,
+                                wz = Tw[8] * dx + Tw[9] * dy + Tw[10] * dz;
+                    t0 = (Tw[3] + wx * zm) / a.scale; t1 = (Tw[7] + wy * zm) / a.scale; t2 = (Tw[11] + wz * zm) / a.scale;
+                } else {
+                    const float* x = a.pts + 3 * (q0 + tid);
+                    t0 = x[0] / a.scale; t1 = x[1] / a.scale; t2 = x[2] / a.scale;
                 }
-                split(v, hi[q & 7], lo[q & 7]);
-                if ((q & 7) == 7) {
-                    const int c0 = q - 7;
-                    if (c0 < 88) {
-                        tm_st8_nw(tm_lane + C_E1H + c0, hi);
-                        tm_st8_nw(tm_lane + C_E1L + c0, lo);
-                    } else {
-                        tm_st8_nw(tm_lane + C_E2H + c0 - 88, hi);
-                        tm_st8_nw(tm_lane + C_E2L + c0 - 88, lo);
+            }
+            pt[tid] = t0; pt[TC_M + tid] = t1; pt[2 * TC_M + tid] = t2; pt[3 * TC_M + tid] = zm;
+        }
+        __syncthreads();
+        // ---- (1) encoder (embedding.py:46-55; arithmetic of oo_tile.h phase 1): sub-thread s takes directions s, s + 4, ...;
+        // value (band k, direction d) -> staging column 3 + 21 k + d (+ 1 past e1's zero pad)
+        {
+            const float t0 = pt[p], t1 = pt[TC_M + p], t2 = pt[2 * TC_M + p];
+            if (sub == 0) {
+                stg[0 * TC_M + p] = t0; stg[1 * TC_M + p] = t1; stg[2 * TC_M + p] = t2;
+            } else if (sub == 1) {
+                stg[87 * TC_M + p] = 0.f;
+#pragma unroll
+                for (int c = 130; c < E_COLS; ++c) stg[c * TC_M + p] = 0.f;
+            }
+#pragma unroll
+            for (int u = 0; u < 6; ++u) {
+                const int d = sub + 4 * u;
+                if (d < NDIR) {
+                    const float proj = sm[SB_PE + 3 * d] * t0 + sm[SB_PE + 3 * d + 1] * t1 + sm[SB_PE + 3 * d + 2] * t2;
+                    float sn, cs;
+                    sincosf(proj * PI_F, &sn, &cs);
+#pragma unroll
+                    for (int k = 0; k < NBAND; ++k) {
+                        const int row = 3 + NDIR * k + d;
+                        stg[(row < E1 ? row : row + 1) * TC_M + p] = sn;
+                        const float s2 = 2.f * sn * cs, c2 = (cs - sn) * (cs + sn);
+                        sn = s2; cs = c2;
                     }
                 }
             }
         }
-        float v[H];
+        __syncthreads();
+        // ---- (2) staging -> (hi, lo) A operands in tensor memory, 8 columns at a time (sub-thread s: groups s, s + 4, ...)
+#pragma unroll
+        for (int u = 0; u < 5; ++u) {
+            const int g = sub + 4 * u;
+            if (g < E_COLS / 8) {
+                float e8[8];
+#pragma unroll
+                for (int i = 0; i < 8; ++i) e8[i] = stg[(8 * g + i) * TC_M + p];
+                if (8 * g < 88) put_split8(tm_lane, C_E1H + 8 * g, C_E1L + 8 * g, e8);
+                else put_split8(tm_lane, C_E2H + 8 * g - 88, C_E2L + 8 * g - 88, e8);
+            }
+        }
+        float v[16];
         // ---- in_layer: relu(W_in e1 + b) -> HA
         publish_tmem();
         if (tid == 0) {
-            layer_mma(tm, C_E1H, C_E1L, w_hi + WB_IN * 4u, w_lo + WB_IN * 4u, K_IN, true);
-            asm volatile("tcgen05.commit.cta_group::1.mbarrier::arrive::one.shared::cluster.b64 [%0];" ::"r"(bar) : "memory");
+            layer_mma(tm, C_E1H, C_E1L, w_hi + WB_IN * 4u, w_lo + WB_IN * 4u, K_IN, H, H, true);
+            commit(bar);
         }
         ok &= mbar_wait(bar, phase); phase ^= 1;
         asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
-        epilogue(tm_lane, bias, v);
-        put_split(tm_lane, C_HAH, C_HAL, v);
+        epilogue8(tm_lane, 8 * sub, bias, v);
+        put_split8(tm_lane, C_HAH + 8 * sub, C_HAL + 8 * sub, v);
         // ---- mid1 -> HB (fc2)
         publish_tmem();
         if (tid == 0) {
-            layer_mma(tm, C_HAH, C_HAL, w_hi + WB_M1 * 4u, w_lo + WB_M1 * 4u, K_H, true);
-            asm volatile("tcgen05.commit.cta_group::1.mbarrier::arrive::one.shared::cluster.b64 [%0];" ::"r"(bar) : "memory");
+            layer_mma(tm, C_HAH, C_HAL, w_hi + WB_M1 * 4u, w_lo + WB_M1 * 4u, K_H, H, H, true);
+            commit(bar);
         }
         ok &= mbar_wait(bar, phase); phase ^= 1;
         asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
-        epilogue(tm_lane, bias + H, v);
-        put_split(tm_lane, C_HBH, C_HBL, v);
+        epilogue8(tm_lane, 8 * sub, bias + H, v);
+        put_split8(tm_lane, C_HBH + 8 * sub, C_HBL + 8 * sub, v);
         // ---- cat_layer on [fc2, e1] -> HA (fc3)
         publish_tmem();
         if (tid == 0) {
-            layer_mma(tm, C_HBH, C_HBL, w_hi + WB_CATA * 4u, w_lo + WB_CATA * 4u, K_H, true);
-            layer_mma(tm, C_E1H, C_E1L, w_hi + WB_CATB * 4u, w_lo + WB_CATB * 4u, K_CATB, false);
-            asm volatile("tcgen05.commit.cta_group::1.mbarrier::arrive::one.shared::cluster.b64 [%0];" ::"r"(bar) : "memory");
+            layer_mma(tm, C_HBH, C_HBL, w_hi + WB_CATA * 4u, w_lo + WB_CATA * 4u, K_H, H, H, true);
+            layer_mma(tm, C_E1H, C_E1L, w_hi + WB_CATB * 4u, w_lo + WB_CATB * 4u, K_CATB, H, H, false);
+            commit(bar);
         }
         ok &= mbar_wait(bar, phase); phase ^= 1;
         asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
-        epilogue(tm_lane, bias + 2 * H, v);
-        put_split(tm_lane, C_HAH, C_HAL, v);
-        // ---- mid2 -> HB (fc4); out_alpha (x10, model.py:88) in registers
+        epilogue8(tm_lane, 8 * sub, bias + 2 * H, v);
+        put_split8(tm_lane, C_HAH + 8 * sub, C_HAL + 8 * sub, v);
+        // ---- mid2 -> HB (fc4); this sub-thread's share of out_alpha (model.py:86-88)
         publish_tmem();
         if (tid == 0) {
-            layer_mma(tm, C_HAH, C_HAL, w_hi + WB_M2 * 4u, w_lo + WB_M2 * 4u, K_H, true);
-            asm volatile("tcgen05.commit.cta_group::1.mbarrier::arrive::one.shared::cluster.b64 [%0];" ::"r"(bar) : "memory");
+            layer_mma(tm, C_HAH, C_HAL, w_hi + WB_M2 * 4u, w_lo + WB_M2 * 4u, K_H, H, H, true);
+            commit(bar);
         }
         ok &= mbar_wait(bar, phase); phase ^= 1;
         asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
-        epilogue(tm_lane, bias + 3 * H, v);
-        put_split(tm_lane, C_HBH, C_HBL, v);
+        epilogue8(tm_lane, 8 * sub, bias + 3 * H, v);
+        put_split8(tm_lane, C_HBH + 8 * sub, C_HBL + 8 * sub, v);
         {
-            float r = sm[SB_WA + H];
+            float r = 0.f;
 #pragma unroll
-            for (int j = 0; j < H; ++j) r += sm[SB_WA + j] * v[j];
-            const float a = r * 10.f;
-            if (live) {
-                if (alpha_out != nullptr) alpha_out[p] = a;
-                if (occ != nullptr) occ[p] = 1.f / (1.f + expf(-a));            // render_rays.py:13 without distances
-            }
+            for (int j = 0; j < 8; ++j) r += sm[SB_WA + 8 * sub + j] * v[j];
+            stg[R_APART + sub * TC_M + p] = r;
         }
-        // ---- color_linear on [fc4, e2], out_color + sigmoid (model.py:94-96) in registers
+        // ---- heads on [fc4, e2]: color_linear (and clip_linear when rendering) in one MMA group
         publish_tmem();
         if (tid == 0) {
-            layer_mma(tm, C_HBH, C_HBL, w_hi + WB_CLA * 4u, w_lo + WB_CLA * 4u, K_H, true);
-            layer_mma(tm, C_E2H, C_E2L, w_hi + WB_CLB * 4u, w_lo + WB_CLB * 4u, K_CLB, false);
-            asm volatile("tcgen05.commit.cta_group::1.mbarrier::arrive::one.shared::cluster.b64 [%0];" ::"r"(bar) : "memory");
+            layer_mma(tm, C_HBH, C_HBL, w_hi + WB_HDA * 4u, w_lo + WB_HDA * 4u, K_H, RENDER ? N_HD : H, N_HD, true);
+            layer_mma(tm, C_E2H, C_E2L, w_hi + WB_HDB * 4u, w_lo + WB_HDB * 4u, K_HDB, RENDER ? N_HD : H, N_HD, false);
+            commit(bar);
         }
         ok &= mbar_wait(bar, phase); phase ^= 1;
         asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
-        epilogue(tm_lane, bias + 4 * H, v);
-        if (live) {
+        if (RENDER) {
+            // sub-threads 0, 1: columns 0..31 = color_linear; 2, 3: columns 32..63 = clip_linear (kept per point for S)
+            epilogue8(tm_lane, 16 * sub, bias + 4 * H, v);
+            epilogue8(tm_lane, 16 * sub + 8, bias + 4 * H, v + 8);
+            if (sub < 2) {
+#pragma unroll
+                for (int ch = 0; ch < 3; ++ch) {
+                    float r = 0.f;
+#pragma unroll
+                    for (int j = 0; j < 16; ++j) r += sm[SB_WOC + ch * H + 16 * sub + j] * v[j];
+                    stg[R_CPART + (sub * 3 + ch) * TC_M + p] = r;
+                }
+            } else {
+#pragma unroll
+                for (int j = 0; j < 16; ++j) stg[R_HP + (16 * (sub - 2) + j) * TC_M + p] = v[j];
+            }
+        } else {
+            epilogue8(tm_lane, 8 * sub, bias + 4 * H, v);
 #pragma unroll
             for (int ch = 0; ch < 3; ++ch) {
-                float r = sm[SB_WOC + 3 * H + ch];
+                float r = 0.f;
 #pragma unroll
-                for (int j = 0; j < H; ++j) r += sm[SB_WOC + ch * H + j] * v[j];
-                color[3 * p + ch] = sigmoidf_(r);
+                for (int j = 0; j < 8; ++j) r += sm[SB_WOC + ch * H + 8 * sub + j] * v[j];
+                stg[R_CPART + (sub * 3 + ch) * TC_M + p] = r;
             }
         }
         // the accumulator columns are re-used by the next tile's first MMA: every thread is past its loads here.  A missed
@@ -314,12 +407,115 @@ __global__ void __launch_bounds__(TC_THREADS, 1) k_forward_tc(const float* __res
         ok = __syncthreads_and(ok ? 1 : 0) != 0;
         asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
         if (!ok) break;
+        // ---- out_alpha (x10) -> occupancy (render_rays.py:13), out_color -> sigmoid (model.py:96): partial sums in a fixed order
+        if (tid < TC_M) {
+            const float ra = sm[SB_WA + H] + ((stg[R_APART + tid] + stg[R_APART + TC_M + tid]) +
+                                              (stg[R_APART + 2 * TC_M + tid] + stg[R_APART + 3 * TC_M + tid]));
+            const float al = ra * 10.f, oc_ = 1.f / (1.f + expf(-al));
+            float col[3];
+#pragma unroll
+            for (int ch = 0; ch < 3; ++ch) {
+                float r = sm[SB_WOC + 3 * H + ch];
+                if (RENDER) r += stg[R_CPART + ch * TC_M + tid] + stg[R_CPART + (3 + ch) * TC_M + tid];
+                else r += (stg[R_CPART + ch * TC_M + tid] + stg[R_CPART + (3 + ch) * TC_M + tid]) +
+                          (stg[R_CPART + (6 + ch) * TC_M + tid] + stg[R_CPART + (9 + ch) * TC_M + tid]);
+                col[ch] = sigmoidf_(r);
+            }
+            if (RENDER) {
+                stg[R_OCC + tid] = oc_;
+                stg[R_COL + tid] = col[0]; stg[R_COL + TC_M + tid] = col[1]; stg[R_COL + 2 * TC_M + tid] = col[2];
+            } else if (tid < npts) {
+                const long long gq = q0 + tid;
+                if (a.alpha != nullptr) a.alpha[gq] = al;
+                if (a.occ != nullptr) a.occ[gq] = oc_;
+                a.color[3 * gq] = col[0]; a.color[3 * gq + 1] = col[1]; a.color[3 * gq + 2] = col[2];
+            }
+        }
+        __syncthreads();
+        if (RENDER) {
+            // ---- compositing: the tile holds the tail of the open ray (segment A) and maybe the head of the next (B)
+            const int jA = (int)(q0 / nmid);
+            const int kA = (int)(q0 - (long long)jA * nmid);
+            const int lenA = npts < nmid - kA ? npts : nmid - kA;
+            const int lenB = npts - lenA;                                // < nmid because nmid > 128
+            if (warp < 2) {
+                const int pa = warp == 0 ? 0 : lenA, len = warp == 0 ? lenA : lenB;
+                float* acc_o = open + (warp == 0 ? cur : cur ^ 1) * 40;
+                if (len > 0) {
+                    float carry = acc_o[5];
+                    float sd = 0.f, so = 0.f, s0 = 0.f, s1 = 0.f, s2 = 0.f;
+                    for (int b0 = 0; b0 < len; b0 += 32) {
+                        const int pp = pa + b0 + lane;
+                        const bool in = b0 + lane < len;
+                        const float o = in ? stg[R_OCC + pp] : 0.f;
+                        float inc = in ? (1.f - o + 1e-10f) : 1.f;                      // render_rays.py:41
+#pragma unroll
+                        for (int s = 1; s < 32; s <<= 1) {
+                            const float t = __shfl_up_sync(0xffffffffu, inc, s);
+                            if (lane >= s) inc *= t;
+                        }
+                        float ex = __shfl_up_sync(0xffffffffu, inc, 1);
+                        if (lane == 0) ex = 1.f;
+                        const float T = o * carry * ex;                                  // render_rays.py:43
+                        carry *= __shfl_sync(0xffffffffu, inc, 31);
+                        if (in) {
+                            stg[R_T + pp] = T;
+                            sd += T * pt[3 * TC_M + pp];
+                            so += T;
+                            s0 += T * stg[R_COL + pp];
+                            s1 += T * stg[R_COL + TC_M + pp];
+                            s2 += T * stg[R_COL + 2 * TC_M + pp];
+                        }
+                    }
+                    sd = wsum32(sd); so = wsum32(so); s0 = wsum32(s0); s1 = wsum32(s1); s2 = wsum32(s2);
+                    __syncwarp();
+                    float sj = 0.f;                                       // S[j] += sum_p T_p hp[j][p]  (lane = hidden unit)
+                    for (int pp = pa; pp < pa + len; ++pp) sj += stg[R_T + pp] * stg[R_HP + lane * TC_M + pp];
+                    acc_o[8 + lane] += sj;
+                    if (lane == 0) {
+                        acc_o[0] += sd; acc_o[1] += so; acc_o[2] += s0; acc_o[3] += s1; acc_o[4] += s2; acc_o[5] = carry;
+                    }
+                }
+            }
+            __syncthreads();
+            // ---- a ray that ended in this tile: mask test (vmap.py:665,672), outputs, compact record; its slot is reset
+            if (lenA > 0 && kA + lenA == nmid) {
+                const float* acc_o = open + cur * 40;
+                const int pix = a.list[jA];
+                const float d = acc_o[0], op = acc_o[1];
+                const bool bad = d < a.near_[pix] || d > a.far_[pix] || op < 0.9f;
+                if (tid < OO_RENDER_REC && a.ray_rec != nullptr)
+                    a.ray_rec[(size_t)jA * OO_RENDER_REC + tid] = tid < H ? acc_o[8 + tid] : (tid == H ? op : 0.f);
+                if (tid == 0) {
+                    a.mask[pix] = bad ? 0 : 1;
+                    a.depth_out[pix] = bad ? 0.f : d;
+#pragma unroll
+                    for (int ch = 0; ch < 3; ++ch) {
+                        const float vv = __fmul_rn(acc_o[2 + ch], 255.f);                            // vmap.py:671
+                        a.rgb[(size_t)pix * 3 + ch] = bad ? 0 : (uint8_t)(int)vv;
+                    }
+                    if (a.opacity) a.opacity[pix] = op;
+                }
+                __syncthreads();
+                if (tid < 40) open[cur * 40 + tid] = tid == 5 ? 1.f : 0.f;
+                cur ^= 1;                                               // segment B (if any) is now the open ray
+                __syncthreads();
+            }
+        }
     }
-    if (!ok && tid == 0 && err != nullptr) atomicExch(err, 1);
+    if (!ok && tid == 0 && a.err != nullptr) atomicExch(a.err, 1);
     asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory");
     __syncthreads();
     if (warp == 0)
         asm volatile("tcgen05.dealloc.cta_group::1.sync.aligned.b32 %0, %1;" ::"r"(tm), "r"((uint32_t)TC_COLS) : "memory");
+}
+
+int n_sm_of_current_device(int* out) {
+    int dev = 0, n = 148;
+    OO_CUDA(cudaGetDevice(&dev));
+    OO_CUDA(cudaDeviceGetAttribute(&n, cudaDevAttrMultiProcessorCount, dev));
+    *out = n;
+    return 0;
 }
 
 }  // namespace
@@ -332,15 +528,41 @@ extern "C" int oo_eval_points_tc(const float* theta, const float* pts, long long
     OO_REQUIRE(n_pts > 0, "oo_eval_points_tc: empty query");
     static PerDevice attr_set;
     if (!attr_set.cur()) {
-        OO_CUDA(cudaFuncSetAttribute(k_forward_tc, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)TC_SMEM));
+        OO_CUDA(cudaFuncSetAttribute(k_forward_tc<false>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)TC_SMEM));
         attr_set.cur() = 1;
     }
-    int dev = 0, n_sm = 148;
-    OO_CUDA(cudaGetDevice(&dev));
-    OO_CUDA(cudaDeviceGetAttribute(&n_sm, cudaDevAttrMultiProcessorCount, dev));
+    int n_sm = 148;
+    if (int rc = n_sm_of_current_device(&n_sm)) return rc;
     const long long n_tiles = (n_pts + TC_M - 1) / TC_M;
     const int grid = (int)(n_tiles < n_sm ? n_tiles : n_sm);
-    k_forward_tc<<<grid, TC_THREADS, TC_SMEM, (cudaStream_t)stream>>>(theta, pts, n_pts, pe_scale, occ, alpha, color, err_flag);
+    TcArgs a = {};
+    a.theta = theta; a.scale = pe_scale; a.err = err_flag;
+    a.pts = pts; a.n_pts = n_pts; a.occ = occ; a.alpha = alpha; a.color = color;
+    k_forward_tc<false><<<grid, TC_THREADS, TC_SMEM, (cudaStream_t)stream>>>(a);
     OO_LAUNCH_CHECK();
     return 0;
 }
+
+// K5 on the tensor cores: called by oo_render_object (oo_render.cu) when no dense feature map is requested.
+namespace oo {
+int render_tc_launch(const oo_render_args* ra, const int* list, const float* near_, const float* far_, const float* lin,
+                     cudaStream_t st) {
+    OO_REQUIRE(ra->n_bins - 1 > TC_M, "oo_render_object: the tensor-core path needs more than %d samples per ray", TC_M);
+    static PerDevice attr_set;
+    if (!attr_set.cur()) {
+        OO_CUDA(cudaFuncSetAttribute(k_forward_tc<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)TC_SMEM));
+        attr_set.cur() = 1;
+    }
+    int n_sm = 148;
+    if (int rc = n_sm_of_current_device(&n_sm)) return rc;
+    TcArgs a = {};
+    a.theta = ra->theta1; a.scale = ra->scale; a.err = ra->tc_err;
+    a.n_bins = ra->n_bins;
+    a.n_hit = ra->n_hit; a.list = list; a.near_ = near_; a.far_ = far_; a.lin = lin; a.jitter = ra->jitter;
+    a.jitter_by_rank = ra->jitter_by_rank; a.rays_dir = ra->rays_dir; a.T_wc = ra->T_wc;
+    a.mask = ra->mask; a.depth_out = ra->depth; a.rgb = ra->rgb; a.opacity = ra->opacity; a.ray_rec = ra->ray_rec;
+    k_forward_tc<true><<<n_sm, TC_THREADS, TC_SMEM, st>>>(a);
+    OO_LAUNCH_CHECK();
+    return 0;
+}
+}  // namespace oo

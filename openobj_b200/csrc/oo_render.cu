@@ -11,6 +11,12 @@
 
 using namespace oo;
 
+namespace oo {
+// K5 on the tensor cores (oo_forward_tc.cu): tcgen05.mma / TMEM forward + compositing, used when no dense feature map is asked for
+int render_tc_launch(const oo_render_args* ra, const int* list, const float* near_, const float* far_, const float* lin,
+                     cudaStream_t st);
+}  // namespace oo
+
 namespace {
 
 constexpr int MAXBINS = 160;
@@ -85,7 +91,7 @@ __global__ void __launch_bounds__(1024, 1) k_compact(RenderK k) {
 // shared-memory extras of the render kernel live in the per-ray region of the training tile (unused here)
 constexpr int SM_OPEN = SM_UT;            // [2][40]: open-ray accumulators {depth, opac, c0, c1, c2, carry, -, -, S[32]}
 constexpr int SM_FIN = SM_RV;             // finished batch: rows V_DEPTH.. (see below) [NRV][12]
-constexpr int F_DEPTH = 0, F_OPAC = 1, F_C0 = 2, F_NEAR = 5, F_FAR = 6, F_PIX = 7;
+constexpr int F_DEPTH = 0, F_OPAC = 1, F_C0 = 2, F_NEAR = 5, F_FAR = 6, F_PIX = 7, F_J = 8;
 
 template <int PH, int END>
 struct RPhases {
@@ -137,6 +143,15 @@ __device__ void emit_batch(int tid, float* sm, const RenderK& k, const float* th
                 const size_t pix = (size_t)__float_as_int(fin[F_PIX * RP + r]);
                 k.a.feat[pix * C + c0] = bad ? 0.f : f[r];
             }
+        }
+    }
+    if (k.a.ray_rec != nullptr) {
+        // compact per-hit record {S[32] = sum_i T_i hp_i, opacity, -, -, -}: the 512-wide out_clip layer is applied later, and
+        // only for the pixels this object wins in the depth-test merge (oo_winner_features)
+        for (int i = tid; i < n_fin * OO_RENDER_REC; i += NTHREADS) {
+            const int r = i / OO_RENDER_REC, e = i - r * OO_RENDER_REC;
+            const size_t j = (size_t)__float_as_int(fin[F_J * RP + r]);
+            k.a.ray_rec[j * OO_RENDER_REC + e] = e < H ? sm[SM_ST + e * RP + r] : (e == H ? fin[F_OPAC * RP + r] : 0.f);
         }
     }
     if (tid < n_fin) {
@@ -271,6 +286,7 @@ __global__ void __launch_bounds__(NTHREADS, 1) k_render(const RenderK k) {
                 fin[F_NEAR * RP + n_fin] = k.near_[pix];
                 fin[F_FAR * RP + n_fin] = k.far_[pix];
                 fin[F_PIX * RP + n_fin] = __int_as_float(pix);
+                fin[F_J * RP + n_fin] = __int_as_float(jA);
             }
             __syncthreads();
             if (tid < 40) open[cur * 40 + tid] = tid == 5 ? 1.f : 0.f;   // reset the slot for a later ray
@@ -310,7 +326,90 @@ __global__ void k_zmerge(const uint8_t* __restrict__ masks, const float* __restr
     winner[i] = win;
 }
 
+// the same merge over per-object POINTERS (objects of different ranks sit in different places of an all-gathered buffer):
+// object q of the global insertion order has mask / depth / rgb maps at masks[q] / depths[q] / rgbs[q]
+__global__ void k_zmerge_ptr(const uint8_t* const* __restrict__ masks, const float* const* __restrict__ depths,
+                             const uint8_t* const* __restrict__ rgbs, const uint8_t* __restrict__ is_bg, int n_obj, int64_t n_pix,
+                             float* __restrict__ depth_out, uint8_t* __restrict__ rgb_out, int32_t* __restrict__ winner) {
+    const int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+    if (i >= n_pix) return;
+    float dbuf = 100.f;                                                 // train.py:562
+    int win = -1;
+    uint8_t r = 0, g = 0, b = 0;
+    for (int o = 0; o < n_obj; ++o) {
+        if (!masks[o][i]) continue;
+        const float d = depths[o][i];
+        if (dbuf > d) {                                                 // train.py:582 strict test
+            const uint8_t* c = rgbs[o] + i * 3;
+            r = c[0]; g = c[1]; b = c[2];
+            win = o;
+            if (!is_bg[o]) dbuf = d;                                    // train.py:593-594
+        }
+    }
+    depth_out[i] = dbuf;
+    rgb_out[i * 3] = r; rgb_out[i * 3 + 1] = g; rgb_out[i * 3 + 2] = b;
+    winner[i] = win;
+}
+
+// Part features of the pixels ONE object won in the merge: feat = W_ocl S + b_ocl * opacity (the legal restructure of
+// out_clip is linear and only consumed through the compositing sum) for the hits whose pixel has winner == k.
+// One warp per hit: lanes = 16 output channels each; rows are appended to a compact list (the order of the list is not
+// deterministic, its content is: every row carries its pixel).
+__global__ void __launch_bounds__(256) k_winner_features(const float* __restrict__ theta1, const float* __restrict__ ray_rec,
+                                                         const int32_t* __restrict__ hit_pix, const int* __restrict__ n_hit,
+                                                         const int32_t* __restrict__ winner, int k_global, int64_t cap,
+                                                         float* __restrict__ rows, int32_t* __restrict__ row_pix,
+                                                         int* __restrict__ n_rows) {
+    __shared__ float S[8][OO_RENDER_REC];
+    const int wv = threadIdx.x >> 5, lane = threadIdx.x & 31;
+    const int n = n_hit[0];
+    for (int j = blockIdx.x * 8 + wv; j < n; j += gridDim.x * 8) {
+        const int pix = hit_pix[j];
+        if (winner[pix] != k_global) continue;                          // warp-uniform
+        int slot = 0;
+        if (lane == 0) slot = atomicAdd(n_rows, 1);
+        slot = __shfl_sync(0xffffffffu, slot, 0);
+        if (slot >= cap) continue;
+        for (int e = lane; e < OO_RENDER_REC; e += 32) S[wv][e] = ray_rec[(size_t)j * OO_RENDER_REC + e];
+        __syncwarp();
+        const float op = S[wv][H];
+        for (int c = lane; c < C; c += 32) {
+            float f = theta1[OFF_OCL_B + c] * op;
+            const float4* w = reinterpret_cast<const float4*>(theta1 + OFF_OCL_W + c * H);
+#pragma unroll
+            for (int j4 = 0; j4 < H / 4; ++j4) {
+                const float4 a = w[j4];
+                f += a.x * S[wv][4 * j4] + a.y * S[wv][4 * j4 + 1] + a.z * S[wv][4 * j4 + 2] + a.w * S[wv][4 * j4 + 3];
+            }
+            rows[(size_t)slot * C + c] = f;
+        }
+        if (lane == 0) row_pix[slot] = pix;
+        __syncwarp();
+    }
+}
+
 }  // namespace
+
+extern "C" int oo_zmerge_ptr(const uint8_t* const* masks, const float* const* depths, const uint8_t* const* rgbs,
+                             const uint8_t* is_bg, int n_obj, int64_t n_pix, float* depth_out, uint8_t* rgb_out,
+                             int32_t* winner_out, void* stream) {
+    OO_REQUIRE(masks && depths && rgbs && is_bg && depth_out && rgb_out && winner_out, "oo_zmerge_ptr: null argument");
+    OO_REQUIRE(n_obj >= 0 && n_pix > 0, "oo_zmerge_ptr: bad size");
+    k_zmerge_ptr<<<(unsigned)((n_pix + 255) / 256), 256, 0, (cudaStream_t)stream>>>(masks, depths, rgbs, is_bg, n_obj, n_pix,
+                                                                                    depth_out, rgb_out, winner_out);
+    OO_LAUNCH_CHECK();
+    return 0;
+}
+
+extern "C" int oo_winner_features(const float* theta1, const float* ray_rec, const int32_t* hit_pix, const int* n_hit,
+                                  const int32_t* winner, int k_global, int64_t cap_rows, float* rows, int32_t* row_pix,
+                                  int* n_rows, void* stream) {
+    OO_REQUIRE(theta1 && ray_rec && hit_pix && n_hit && winner && rows && row_pix && n_rows, "oo_winner_features: null argument");
+    k_winner_features<<<148 * 4, 256, 0, (cudaStream_t)stream>>>(theta1, ray_rec, hit_pix, n_hit, winner, k_global, cap_rows, rows,
+                                                                 row_pix, n_rows);
+    OO_LAUNCH_CHECK();
+    return 0;
+}
 
 // scratch for the render call is carved from one cudaMallocAsync allocation on `stream`
 extern "C" int oo_render_object(const oo_render_args* a, void* stream) {
@@ -319,6 +418,7 @@ extern "C" int oo_render_object(const oo_render_args* a, void* stream) {
     OO_REQUIRE(a->mask && a->depth && a->rgb && a->n_hit, "oo_render_object: null output");
     OO_REQUIRE(a->n_bins > P + 1 && a->n_bins <= MAXBINS, "oo_render_object: need %d < n_bins <= %d", P + 1, MAXBINS);
     OO_REQUIRE(a->lin_host != nullptr, "oo_render_object: null linspace table");
+    OO_REQUIRE((a->ray_rec == nullptr) == (a->hit_pix == nullptr), "oo_render_object: ray_rec and hit_pix go together");
     cudaStream_t st = (cudaStream_t)stream;
     RenderK k;
     k.a = *a;
@@ -343,6 +443,13 @@ extern "C" int oo_render_object(const oo_render_args* a, void* stream) {
     OO_LAUNCH_CHECK();
     k_compact<<<1, 1024, 0, st>>>(k);
     OO_LAUNCH_CHECK();
+    if (a->hit_pix != nullptr) OO_CUDA(cudaMemcpyAsync(a->hit_pix, k.list, n * sizeof(int), cudaMemcpyDeviceToDevice, st));
+    if (a->feat == nullptr && !a->force_mma_sync) {
+        // no dense [W][H][512] map wanted (the winner-only feature path, or no features at all): the tcgen05 / TMEM kernel
+        if (int rc = render_tc_launch(a, k.list, k.near_, k.far_, k.lin, st)) return rc;
+        OO_CUDA(cudaFreeAsync(scratch, st));
+        return 0;
+    }
     const size_t smem = (size_t)SM_TOTAL * sizeof(float);
     static PerDevice attr_set;
     if (!attr_set.cur()) {

@@ -234,11 +234,12 @@ class sceneObject:
         raise NotImplementedError("3-D bounds come from open3d/trimesh in the reference (vmap.py:285-379); outside the "
                                   "accelerated path -- set .bbox3dour (center, R, extent) from the host pipeline")
 
-    def render_2D_syn(self, T_WC, intrinsic_open3d, cached_rays_dir, T_WO=None, chunk_size=1000, do_fine=True,
-                      obj_mask=None, render_part=False, jitter=None, dense=False):
-        """vmap.py:604-685 over every pixel, as one K5 launch.  Returns (obj_mask [W,H] bool, depth[n], rgb[n,3] u8,
-        feat[n,512] or None) compressed by the mask like the reference; `dense=True` returns device maps instead."""
-        _, bb = self.get_bound(intrinsic_open3d, final=True)
+    def _render(self, T_WC, cached_rays_dir, jitter=None, render_part=False, out=None, want_rec=False, theta=None,
+                jitter_by_pixel=False, tensor_core=True):
+        """One K5 launch over every pixel.  out = (mask u8 [W,H], depth f32 [W,H], rgb u8 [W,H,3]) views to write into (e.g. a
+        rank's all-gather send buffer) or None; want_rec: compact per-hit records for the winner-only feature path instead of
+        a dense [W,H,512] map.  Returns dict(mask, depth, rgb, feat, rec, hit_pix, n_hit)."""
+        _, bb = self.get_bound(None, final=True)
         dev = torch.device(self.training_device)
         W, H = cached_rays_dir.shape[:2]
         T_wc = torch.as_tensor(np.asarray(T_WC), dtype=torch.float32)
@@ -248,16 +249,21 @@ class sceneObject:
         T_oc = torch.inverse(T_wo) @ T_wc                                  # trainer.py:157-160 (4x4 host algebra)
         half = torch.as_tensor(np.asarray(bb.extent), dtype=torch.float32) / 2.0
         n_bins = 150
-        by_rank = jitter is not None
+        by_rank = jitter is not None and not jitter_by_pixel        # an explicit tape holds the reference's rows: by hit rank
         if jitter is None:
             jitter = torch.rand(W * H, n_bins, device=dev)
         lin = sampler.torch_linspace01(n_bins)
-        theta = self.trainer.packed(dev)
+        theta = self.trainer.packed(dev) if theta is None else theta
         f32 = dict(dtype=torch.float32, device=dev)
-        mask = torch.empty(W, H, dtype=torch.uint8, device=dev)
-        depth = torch.empty(W, H, **f32)
-        rgb = torch.empty(W, H, 3, dtype=torch.uint8, device=dev)
-        feat = torch.empty(W, H, layout.CLIP, **f32) if render_part else None
+        if out is None:
+            mask = torch.empty(W, H, dtype=torch.uint8, device=dev)
+            depth = torch.empty(W, H, **f32)
+            rgb = torch.empty(W, H, 3, dtype=torch.uint8, device=dev)
+        else:
+            mask, depth, rgb = out
+        feat = torch.empty(W, H, layout.CLIP, **f32) if (render_part and not want_rec) else None
+        rec = torch.empty(W * H, 36, **f32) if want_rec else None
+        hit_pix = torch.empty(W * H, dtype=torch.int32, device=dev) if want_rec else None
         n_hit = torch.zeros(1, dtype=torch.int32, device=dev)
         keep = [T_wc.to(dev), T_oc.to(dev).contiguous(), half.to(dev), cached_rays_dir.to(dev).contiguous(),
                 jitter.to(dev).contiguous()]
@@ -267,8 +273,24 @@ class sceneObject:
         a.jitter_by_rank = int(by_rank)
         a.lin_host = ctypes.c_void_p(lin.data_ptr())
         a.mask, a.depth, a.rgb, a.feat, a.opacity, a.n_hit = ptr(mask), ptr(depth), ptr(rgb), ptr(feat), None, ptr(n_hit)
+        a.ray_rec, a.hit_pix = ptr(rec), ptr(hit_pix)
+        from . import ops
+        err = ops._TC_ERR.get(dev)
+        if err is None:
+            err = ops._TC_ERR[dev] = torch.zeros(1, dtype=torch.int32, device=dev)
+        a.force_mma_sync, a.tc_err = int(not tensor_core), ptr(err)
         with torch.cuda.device(dev):
             check(lib().oo_render_object(ctypes.byref(a), stream()), "oo_render_object")
+        return dict(mask=mask, depth=depth, rgb=rgb, feat=feat, rec=rec, hit_pix=hit_pix, n_hit=n_hit, theta=theta)
+
+    def render_2D_syn(self, T_WC, intrinsic_open3d, cached_rays_dir, T_WO=None, chunk_size=1000, do_fine=True,
+                      obj_mask=None, render_part=False, jitter=None, dense=False):
+        """vmap.py:604-685 over every pixel, as one K5 launch.  Returns (obj_mask [W,H] bool, depth[n], rgb[n,3] u8,
+        feat[n,512] or None) compressed by the mask like the reference; `dense=True` returns device maps instead.
+        `jitter` [>= n_hit, 150] replaces the reference's torch.rand(n_hit, 150) (rows by hit rank)."""
+        r = self._render(T_WC, cached_rays_dir, jitter=jitter, render_part=render_part)
+        mask, depth, rgb, feat, n_hit = r["mask"], r["depth"], r["rgb"], r["feat"], r["n_hit"]
+        dev = mask.device
         if dense:
             return mask.bool(), depth, rgb, feat
         if int(n_hit.item()) <= 1:

@@ -501,9 +501,19 @@ def test_eval_render_frame_single_rank_matches_oracle_merge():
     real_rand = torch.rand
     torch.rand = lambda *a, **k: jit.to(DEV) if a[:2] == (W * H, 150) else real_rand(*a, **k)
     try:
-        depth, rgb, win, _ = E.render_frame(objs, d["T_wc"].numpy(), rays, is_bg=[True, False, False])
+        depth, rgb, win, feat = E.render_frame(objs, d["T_wc"].numpy(), rays, is_bg=[True, False, False], render_feat=True)
+        # winner-only feature path (36 floats per hit + out_clip after the merge) == the dense per-object feature maps of
+        # render_2D_syn(render_part=True) selected by the winner
+        dense = [o.render_2D_syn(d["T_wc"].numpy(), None, rays, render_part=True, dense=True, jitter=None) for o in objs]
     finally:
         torch.rand = real_rand
+    expect = torch.zeros_like(feat)
+    for k, (m_k, _, _, f_k) in enumerate(dense):
+        sel = win == k
+        assert bool(m_k[sel].all())
+        expect[sel] = f_k[sel]
+    torch.testing.assert_close(feat, expect, rtol=1e-5, atol=1e-5)
+    assert float(feat[win < 0].abs().max()) == 0.0 and float(feat.abs().max()) > 0
     agree = (win.cpu() == rw)
     assert float(agree.float().mean()) > 0.995          # a borderline opacity / depth test may flip a pixel
     np.testing.assert_allclose(depth.cpu()[agree].numpy(), rd[agree].numpy(), rtol=1e-4, atol=1e-5)
