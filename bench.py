@@ -650,17 +650,11 @@ def run_eval(args):
     clk.__exit__()
     D.barrier()
     ms = D.max_over_ranks(e0.elapsed_time(e1), dev)
-    # per-kernel view on rank 0: K5 alone over this rank's objects, one frame
-    recs = []
-    jit = torch.rand(W * H, 150, device=dev)
-    ek0, ek1 = cuda_timer()
-    ek0.record()
-    for o in mine:
-        recs.append(o._render(pose(0), cam.rays_dir_cache, jitter=jit, jitter_by_pixel=True, want_rec=True))
-    ek1.record()
-    torch.cuda.synchronize()
-    k5_ms = ek0.elapsed_time(ek1)
-    n_hit_local = sum(int(r["n_hit"].item()) for r in recs)
+    # per-kernel view: K5 (hit lists + the tcgen05 render launch) of this rank's objects, one frame, CUDA events inside render_frame
+    st2 = {"time_kernels": True}
+    E.render_frame(mine, pose(0), cam.rays_dir_cache, is_bg={0: True}, render_feat=True, stats=st2)
+    k5_ms = st2.get("k5_ms", float("nan"))
+    n_hit_local = st2.get("hit_rays_local", 0)
     n_hit_all = int(D.sum_over_ranks(n_hit_local, dev))
     covered = float((winner >= 0).float().mean())
     if rank == 0:
@@ -686,11 +680,12 @@ def run_eval(args):
             "object_rays_per_s": n_hit_all * steps / (ms * 1e-3),
             "clocks": clk.summary(),
             "interconnect": stats,
-            "roofline": {"kernel": "k_render (K5: 149 samples per hit ray through the fused forward tile + compositing), this rank's "
-                                   "%d objects of one frame" % len(mine), "bound": "fma", "achieved": k5_flop / (k5_ms * 1e-3) / 1e12,
+            "roofline": {"kernel": "oo_render_frame = k_hit_count / _scan / _fill + k_forward_tc<render> (K5 on tcgen05 / TMEM: 149 samples "
+                                   "per hit ray, 3xTF32 tcgen05.mma, compositing), this rank's %d objects of one frame, one launch"
+                                   % len(mine), "bound": "fma", "achieved": k5_flop / (k5_ms * 1e-3) / 1e12,
                          "peak": peak, "unit": "TFLOP/s", "frac": k5_flop / (k5_ms * 1e-3) / 1e12 / peak, "traffic": None,
                          "ms": k5_ms, "flop": k5_flop},
-            "gpu_launches": steps * (len(mine) * 4 + 2 + len(mine)),
+            "gpu_launches": steps * (4 + 1 + 1),       # hit count / scan / fill, render, merge, winner features
         }
         print(json.dumps(out), file=_JSON_OUT, flush=True)
     D.barrier()

@@ -377,6 +377,34 @@ typedef struct oo_render_args {
 } oo_render_args;
 #define OO_RENDER_REC 36
 int oo_render_object(const oo_render_args* a, void* stream);
+/* ---- a19 for ALL objects a rank owns, one call per frame (BASELINE config 5): the hit lists of every object are built in three
+ *      parallel passes (slab test per (object, pixel); pixels in increasing order inside an object's list, the reference's rank
+ *      order, trainer.py:166-176), then ONE launch of the tcgen05 / TMEM kernel walks the pooled hits: a CTA takes an equal share
+ *      of the pool and re-stages the weights when its share crosses into the next object.  Jitter rows are taken by pixel.
+ *      Outputs: dense per-object maps mask / depth / rgb [n_obj][W*H](x3), ZERO-INITIALISED BY THE CALLER (only hit pixels are
+ *      written); obj_start [n_obj + 1] (device) = prefix of the hit counts; hit_pix [pool_rows] pooled pixel ids; ray_rec
+ *      [pool_rows][OO_RENDER_REC] pooled per-hit records (or NULL).  If obj_start[n_obj] > pool_rows the excess hits are not
+ *      rendered: the caller checks and re-runs with a larger pool.  scratch: >= n_obj * ceil(W*H / 256) + 1 int32. */
+typedef struct oo_render_frame_args {
+    int W, H, n_bins, n_obj;
+    float scale;
+    const float* const* theta;           /* DEVICE array of n_obj device pointers to parameter blocks */
+    const float* T_wc;                   /* [16] */
+    const float* T_oc;                   /* [n_obj][16] = inv(T_WO) @ T_WC per object (trainer.py:157-160) */
+    const float* half_extent;            /* [n_obj][3] */
+    const float* rays_dir;               /* [W][H][3] */
+    const float* jitter;                 /* [W*H][n_bins], rows by pixel */
+    const float* lin;                    /* DEVICE: torch.linspace(0, 1, n_bins + 1) */
+    uint8_t* mask; float* depth; uint8_t* rgb;
+    int32_t* obj_start; int32_t* hit_pix; float* ray_rec; int64_t pool_rows;
+    int32_t* scratch; int64_t scratch_ints;
+    int* tc_err;
+} oo_render_frame_args;
+int oo_render_frame(const oo_render_frame_args* f, void* stream);
+/* winner-only features over the pooled hits of oo_render_frame: k_of [n_obj] = global ensemble index of each local object */
+int oo_winner_features_frame(const float* const* theta, const float* ray_rec, const int32_t* hit_pix, const int* obj_start,
+                             int n_obj, const int32_t* k_of, const int32_t* winner, int64_t pool_rows, int64_t cap_rows,
+                             float* rows, int32_t* row_pix, int* n_rows, void* stream);
 /* the depth-test merge over per-object pointers (device arrays of n_obj pointers to [n_pix] / [n_pix][3] maps, in global
  * insertion order): what a sharded run uses on the all-gathered buffer without re-packing it */
 int oo_zmerge_ptr(const uint8_t* const* masks, const float* const* depths, const uint8_t* const* rgbs, const uint8_t* is_bg,

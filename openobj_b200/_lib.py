@@ -68,6 +68,14 @@ class RenderArgs(Structure):
                 ("force_mma_sync", c_int), ("tc_err", c_void_p)]
 
 
+class RenderFrameArgs(Structure):
+    _fields_ = [("W", c_int), ("H", c_int), ("n_bins", c_int), ("n_obj", c_int), ("scale", c_float),
+                ("theta", c_void_p), ("T_wc", c_void_p), ("T_oc", c_void_p), ("half_extent", c_void_p), ("rays_dir", c_void_p),
+                ("jitter", c_void_p), ("lin", c_void_p), ("mask", c_void_p), ("depth", c_void_p), ("rgb", c_void_p),
+                ("obj_start", c_void_p), ("hit_pix", c_void_p), ("ray_rec", c_void_p), ("pool_rows", c_int64),
+                ("scratch", c_void_p), ("scratch_ints", c_int64), ("tc_err", c_void_p)]
+
+
 _SIGS = {
     "oo_version": ([], c_int),
     "oo_last_error": ([], c_char_p),
@@ -100,6 +108,9 @@ _SIGS = {
     "oo_render_object": ([POINTER(RenderArgs), c_void_p], c_int),
     "oo_zmerge": ([c_void_p, c_void_p, c_void_p, c_void_p, c_int, c_int64, c_void_p, c_void_p, c_void_p, c_void_p],
                   c_int),
+    "oo_render_frame": ([POINTER(RenderFrameArgs), c_void_p], c_int),
+    "oo_winner_features_frame": ([c_void_p, c_void_p, c_void_p, c_void_p, c_int, c_void_p, c_void_p, c_int64, c_int64, c_void_p,
+                                  c_void_p, c_void_p, c_void_p], c_int),
     "oo_zmerge_ptr": ([c_void_p, c_void_p, c_void_p, c_void_p, c_int, c_int64, c_void_p, c_void_p, c_void_p, c_void_p], c_int),
     "oo_winner_features": ([c_void_p, c_void_p, c_void_p, c_void_p, c_void_p, c_int, c_int64, c_void_p, c_void_p, c_void_p,
                             c_void_p], c_int),

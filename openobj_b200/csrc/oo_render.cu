@@ -13,8 +13,7 @@ using namespace oo;
 
 namespace oo {
 // K5 on the tensor cores (oo_forward_tc.cu): tcgen05.mma / TMEM forward + compositing, used when no dense feature map is asked for
-int render_tc_launch(const oo_render_args* ra, const int* list, const float* near_, const float* far_, const float* lin,
-                     cudaStream_t st);
+int render_tc_launch(const oo_render_args* ra, const int* list, int* obj_start2, const float* lin, cudaStream_t st);
 }  // namespace oo
 
 namespace {
@@ -390,6 +389,63 @@ __global__ void __launch_bounds__(256) k_winner_features(const float* __restrict
 
 }  // namespace
 
+namespace {
+// the same for ALL local objects in one launch over the pooled hits of oo_render_frame: hit g belongs to the object o with
+// obj_start[o] <= g < obj_start[o + 1] (binary search), whose global ensemble index is k_of[o]
+__global__ void __launch_bounds__(256) k_winner_features_pool(const float* const* __restrict__ theta, const float* __restrict__ ray_rec,
+                                                              const int32_t* __restrict__ hit_pix, const int* __restrict__ obj_start,
+                                                              int n_obj, const int32_t* __restrict__ k_of,
+                                                              const int32_t* __restrict__ winner, int64_t pool_rows, int64_t cap,
+                                                              float* __restrict__ rows, int32_t* __restrict__ row_pix,
+                                                              int* __restrict__ n_rows) {
+    __shared__ float S[8][OO_RENDER_REC];
+    const int wv = threadIdx.x >> 5, lane = threadIdx.x & 31;
+    long long n = obj_start[n_obj];
+    if (n > pool_rows) n = pool_rows;
+    for (long long g = (long long)blockIdx.x * 8 + wv; g < n; g += (long long)gridDim.x * 8) {
+        int lo = 0, hi = n_obj - 1;
+        while (lo < hi) {
+            const int mid = (lo + hi + 1) >> 1;
+            if ((long long)obj_start[mid] <= g) lo = mid; else hi = mid - 1;
+        }
+        const int pix = hit_pix[g];
+        if (winner[pix] != k_of[lo]) continue;                          // warp-uniform
+        int slot = 0;
+        if (lane == 0) slot = atomicAdd(n_rows, 1);
+        slot = __shfl_sync(0xffffffffu, slot, 0);
+        if (slot >= cap) continue;
+        for (int e = lane; e < OO_RENDER_REC; e += 32) S[wv][e] = ray_rec[(size_t)g * OO_RENDER_REC + e];
+        __syncwarp();
+        const float* th = theta[lo];
+        const float op = S[wv][H];
+        for (int c = lane; c < C; c += 32) {
+            float f = th[OFF_OCL_B + c] * op;
+            const float4* w = reinterpret_cast<const float4*>(th + OFF_OCL_W + c * H);
+#pragma unroll
+            for (int j4 = 0; j4 < H / 4; ++j4) {
+                const float4 a = w[j4];
+                f += a.x * S[wv][4 * j4] + a.y * S[wv][4 * j4 + 1] + a.z * S[wv][4 * j4 + 2] + a.w * S[wv][4 * j4 + 3];
+            }
+            rows[(size_t)slot * C + c] = f;
+        }
+        if (lane == 0) row_pix[slot] = pix;
+        __syncwarp();
+    }
+}
+
+}  // namespace
+
+extern "C" int oo_winner_features_frame(const float* const* theta, const float* ray_rec, const int32_t* hit_pix, const int* obj_start,
+                                        int n_obj, const int32_t* k_of, const int32_t* winner, int64_t pool_rows, int64_t cap_rows,
+                                        float* rows, int32_t* row_pix, int* n_rows, void* stream) {
+    OO_REQUIRE(theta && ray_rec && hit_pix && obj_start && k_of && winner && rows && row_pix && n_rows && n_obj >= 1,
+               "oo_winner_features_frame: null argument");
+    k_winner_features_pool<<<148 * 4, 256, 0, (cudaStream_t)stream>>>(theta, ray_rec, hit_pix, obj_start, n_obj, k_of, winner, pool_rows,
+                                                                      cap_rows, rows, row_pix, n_rows);
+    OO_LAUNCH_CHECK();
+    return 0;
+}
+
 extern "C" int oo_zmerge_ptr(const uint8_t* const* masks, const float* const* depths, const uint8_t* const* rgbs,
                              const uint8_t* is_bg, int n_obj, int64_t n_pix, float* depth_out, uint8_t* rgb_out,
                              int32_t* winner_out, void* stream) {
@@ -424,7 +480,7 @@ extern "C" int oo_render_object(const oo_render_args* a, void* stream) {
     k.a = *a;
     k.n_pix = a->W * a->H;
     const size_t n = (size_t)k.n_pix;
-    const size_t bytes = n * (1 + 4 + 4 + 4) + MAXBINS * 4 + 256;
+    const size_t bytes = n * (1 + 4 + 4 + 4) + MAXBINS * 4 + 256 + 64;
     char* scratch = nullptr;
     OO_CUDA(cudaMallocAsync((void**)&scratch, bytes, st));
     k.near_ = (float*)scratch;
@@ -446,7 +502,7 @@ extern "C" int oo_render_object(const oo_render_args* a, void* stream) {
     if (a->hit_pix != nullptr) OO_CUDA(cudaMemcpyAsync(a->hit_pix, k.list, n * sizeof(int), cudaMemcpyDeviceToDevice, st));
     if (a->feat == nullptr && !a->force_mma_sync) {
         // no dense [W][H][512] map wanted (the winner-only feature path, or no features at all): the tcgen05 / TMEM kernel
-        if (int rc = render_tc_launch(a, k.list, k.near_, k.far_, k.lin, st)) return rc;
+        if (int rc = render_tc_launch(a, k.list, reinterpret_cast<int*>(k.hit + ((n + 15) & ~(size_t)15)), k.lin, st)) return rc;
         OO_CUDA(cudaFreeAsync(scratch, st));
         return 0;
     }

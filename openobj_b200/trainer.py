@@ -32,6 +32,15 @@ class Trainer:
         layout.views(theta)[18].copy_(self.pe.B_layer.weight.detach()[None])
         return theta
 
+    def packed_cached(self, device=None):
+        """packed(), re-used while no parameter has been written (tensor version counters): full-frame evaluation renders the
+        same trained weights for every pose."""
+        ps = list(self.fc_occ_map.parameters()) + [self.pe.B_layer.weight]
+        key = (str(device), tuple((p.data_ptr(), p._version) for p in ps))
+        if getattr(self, "_packed_key", None) != key:
+            self._packed_key, self._packed = key, self.packed(device)
+        return self._packed
+
     # ---- evaluation at free points / on the meshing grid (trainer.py:46-128; SURVEY 8f rank 3) ----------------
     def eval_points(self, points, chunk_size=300000, want_clip=True):
         """trainer.py:104-128: occupancy, colour and part feature at `points` [n,3]; None when nothing is occupied.
