@@ -49,9 +49,13 @@ mine = [o for k, o in enumerate(objs) if k % world == rank]
 got = E.render_frame(mine, T, cam.rays_dir_cache, is_bg=is_bg, render_feat=True)
 torch.rand = real_rand
 torch.cuda.synchronize()
-ok = dict(depth=bool(torch.equal(ref[0], got[0])), rgb=bool(torch.equal(ref[1], got[1])), winner=bool(torch.equal(ref[2], got[2])),
-          feat=bool(torch.allclose(ref[3], got[3], rtol=0, atol=0)), covered=float((got[2] >= 0).float().mean()),
-          winners=sorted(set(got[2].flatten().tolist())))
+# winner map and 8-bit colours must be identical; depth / features agree to fp32 rounding: one launch renders all of a rank's
+# objects over a POOLED hit list, so where a ray's 149 samples are cut into 128-point tiles -- hence the association of its
+# termination product and sums -- depends on which objects share the rank
+ok = dict(depth=bool(torch.allclose(ref[0], got[0], rtol=1e-5, atol=1e-6)), rgb=bool(torch.equal(ref[1], got[1])),
+          winner=bool(torch.equal(ref[2], got[2])), feat=bool(torch.allclose(ref[3], got[3], rtol=1e-4, atol=1e-5)),
+          depth_max_abs_diff=float((ref[0] - got[0]).abs().max()), feat_max_abs_diff=float((ref[3] - got[3]).abs().max()),
+          covered=float((got[2] >= 0).float().mean()), winners=sorted(set(got[2].flatten().tolist())))
 res = [None] * world
 dist.all_gather_object(res, ok)
 if rank == 0:
