@@ -112,6 +112,7 @@ class Scene:
         self._copy_stream = None
         self._sorted_ids = (None, None)
         self._vis_cache = (None, None, None)
+        self._bbox_cache = {}
         self._empty_bits = None
         # the separate background model (train.py:236-242): one hidden-128 model, not part of the vmap ensemble; it lives
         # on the last rank (the ensemble's round-robin starts at rank 0)
@@ -150,7 +151,7 @@ class Scene:
         self.store.release_many(tab.slot_frame[ii, ss].astype(np.int64))
         self.store.acquire(store_slot, len(placed))
         tab.slot_frame[ii, ss] = store_slot
-        tab.slot_bbox[ii, ss] = np.stack([np.asarray(p[3], dtype=np.float32) for p in placed])
+        tab.slot_bbox[ii, ss] = np.stack([self._bbox_np(p[1].obj_id, p[3]) for p in placed])
         if self.part_mode:
             tab.part_frame[ii, ss] = int(frame_id / placed[0][1].stride)      # (use_frame / stride).long(), vmap.py:438-440
         tab.n_kf[ii] = np.fromiter((p[1].ring.n_keyframes for p in placed), dtype=np.int32, count=len(placed))
@@ -158,6 +159,13 @@ class Scene:
             lat = o.ring.latest
             if len(lat) >= 2:
                 tab.latest[i, 0], tab.latest[i, 1] = lat[-2], lat[-1]
+
+    def _bbox_np(self, obj_id, bbox):
+        """float32 [4] of a frame's 2-D box; a box object that comes back unchanged (same tensor) is converted once."""
+        c = self._bbox_cache.get(obj_id)
+        if c is None or c[0] is not bbox:
+            c = self._bbox_cache[obj_id] = (bbox, np.asarray(bbox, dtype=np.float32))
+        return c[1]
 
     # ---- train.py:164-276 ---------------------------------------------------------------------------------
     def add_frame(self, sample):
