@@ -6,7 +6,11 @@
 // oo_composite.cu) in between.  Hidden width is a run-time argument (any multiple of 4).
 #include "../../include/openobj_b200.h"
 #include "oo_common.cuh"
+#include "oo_gemm.h"
 #include "oo_layout.h"
+
+#include <stdlib.h>
+#include <string.h>
 
 
 using namespace oo;
@@ -42,22 +46,6 @@ enum { T_IN_W, T_IN_B, T_M1_W, T_M1_B, T_CAT_W, T_CAT_B, T_M2_W, T_M2_B, T_A_W, 
 // CTA tile 128 x 64 x 16, 256 threads = 8 warps of 32 x 32 outputs on the tensor pipe (3 x TF32 mma.sync per product).
 // split > 1: grid.z chunks of the contraction write raw partial sums to part[z][I][J]; k_gemm_reduce finishes.
 // ------------------------------------------------------------------------------------------------
-struct GemmOp {
-    const float* A; long long sai, sac;
-    const float* B; long long sbj, sbc;
-    float* C; long long sci, scj;
-    int I, J, K;
-    const float* bias;          // [J] or null
-    float mult, post;           // v = (mult * acc + bias) * post
-    int act;                    // 0 none, 1 relu, 2 sigmoid
-    const float* mask; long long smi, smj; int mask_cols;   // C(i,j) = 0 where j < mask_cols and mask(i,j) <= 0
-    int accumulate;             // C += result
-    int split, chunk;           // contraction chunks (chunk is a multiple of BK)
-    float* part;
-    float* ones_out;            // non-null: one more virtual column j == J with B(J, c) = 1, written to ones_out[i]
-                                // (the bias gradient = column sums rides along with the weight gradient)
-};
-
 __device__ __forceinline__ int gemm_je(const GemmOp& g) { return g.J + (g.ones_out != nullptr ? 1 : 0); }
 __device__ __forceinline__ float* gemm_dst(const GemmOp& g, int i, int j) {
     return j == g.J ? g.ones_out + i : g.C + i * g.sci + j * g.scj;
@@ -336,17 +324,21 @@ int run_gemm(GemmOp g, int split, float* part, cudaStream_t st, ReduceBatch* def
     }
     const int n_sm = (int)n_sm_d.cur();
     OO_REQUIRE(n_sm <= 160, "oo_bg gemm: the split-partial regions are sized for at most 160 SMs");
-    const int tiles = ((g.I + BI - 1) / BI) * ((g.J + BJ - 1) / BJ);
+    // engine: tcgen05 (default) or the round-1 mma.sync kernel (OO_BG_GEMM=mma, kept for A/B runs and as the documented baseline)
+    static const bool tc_on = []() { const char* e = getenv("OO_BG_GEMM"); return !(e != nullptr && strcmp(e, "mma") == 0); }();
+    const bool use_tc = tc_on && gemm_tc_supported(g);     // operand layouts the tcgen05 engine cannot stage go to mma.sync
+    const int tiles = use_tc ? ((g.I + TG_BI - 1) / TG_BI) * ((g.J + TG_BJ - 1) / TG_BJ) : ((g.I + BI - 1) / BI) * ((g.J + BJ - 1) / BJ);
+    const int kq = use_tc ? TG_KC : BK;          // contraction granularity of a chunk
     g.split = 1;
-    g.chunk = g.K;
+    g.chunk = use_tc ? (g.K + kq - 1) / kq * kq : g.K;
     g.part = part;
     if (split > 1) {
-        int want = 2 * n_sm / tiles;
+        int want = (use_tc ? n_sm : 2 * n_sm) / tiles;       // one wave: 1 CTA per SM (tcgen05: 198 KB of staging) or 2 (mma.sync)
         if (want > BG_SPLIT_MAX) want = BG_SPLIT_MAX;
         if (want < 1) want = 1;
-        g.chunk = ((g.K + want - 1) / want + BK - 1) / BK * BK;
+        g.chunk = ((g.K + want - 1) / want + kq - 1) / kq * kq;
         g.split = (g.K + g.chunk - 1) / g.chunk;
-        if (g.split < 2) { g.split = 2; g.chunk = ((g.K + 1) / 2 + BK - 1) / BK * BK; g.split = (g.K + g.chunk - 1) / g.chunk; }
+        if (g.split < 2) { g.split = 2; g.chunk = ((g.K + 1) / 2 + kq - 1) / kq * kq; g.split = (g.K + g.chunk - 1) / g.chunk; }
     }
     const int je = g.J + (g.ones_out != nullptr ? 1 : 0);
     OO_REQUIRE((long long)g.I * (g.sai > 0 ? g.sai : 1) + (long long)g.K * (g.sac > 0 ? g.sac : 1) < (1LL << 31) &&
@@ -355,6 +347,9 @@ int run_gemm(GemmOp g, int split, float* part, cudaStream_t st, ReduceBatch* def
     OO_REQUIRE((long long)g.I * (g.sci > 0 ? g.sci : 1) + (long long)je * (g.scj > 0 ? g.scj : 1) < (1LL << 31) &&
                    (g.mask == nullptr || (long long)g.I * (g.smi > 0 ? g.smi : 1) + (long long)je * (g.smj > 0 ? g.smj : 1) < (1LL << 31)),
                "oo_bg gemm: output / mask larger than 2^31 elements");
+    if (use_tc) {
+        if (int rc = run_gemm_tc(g, st)) return rc;
+    } else {
     const dim3 grid((g.I + BI - 1) / BI, (g.J + BJ - 1) / BJ, g.split);
     const bool ac = g.sac == 1, bc = g.sbc == 1;
     static PerDevice attr_set;
@@ -370,6 +365,7 @@ int run_gemm(GemmOp g, int split, float* part, cudaStream_t st, ReduceBatch* def
     else if (bc) OO_CUDA(launch_pdl(k_gemm<false, true>, grid, dim3(256), (size_t)GEMM_SMEM, st, g));
     else OO_CUDA(launch_pdl(k_gemm<false, false>, grid, dim3(256), (size_t)GEMM_SMEM, st, g));
     OO_LAUNCH_CHECK();
+    }
     if (g.split > 1) {
         if (defer != nullptr) {
             OO_REQUIRE(defer->n < REDUCE_BATCH_MAX, "oo_bg gemm: too many deferred reductions");
@@ -397,7 +393,9 @@ int run_reduce_batch(const ReduceBatch& b, cudaStream_t st) {
 // floats of split partials run_gemm may write for an I x J weight gradient (+ the bias column): split * tiles <= 2 CTAs per SM
 long long part_floats(int I, int J) {
     const long long tiles = (long long)((I + BI - 1) / BI) * ((J + BJ - 1) / BJ);
-    long long split = 2 * 160 / tiles;                 // >= what run_gemm picks for any SM count up to 160
+    const long long tiles_tc = (long long)((I + TG_BI - 1) / TG_BI) * ((J + TG_BJ - 1) / TG_BJ);
+    long long split = 2 * 160 / tiles;                 // >= what run_gemm picks for any SM count up to 160 (mma.sync engine)
+    if (160 / tiles_tc > split) split = 160 / tiles_tc;    // tcgen05 engine: one CTA per SM
     if (split > BG_SPLIT_MAX) split = BG_SPLIT_MAX;
     if (split < 2) split = 2;
     return (split + 1) * (long long)I * (J + 1);
@@ -544,6 +542,7 @@ struct BgWs {
     // gradients
     float *d_alpha, *d_color, *d_colpre, *d_clip, *d_hc, *d_hp, *d_xh, *d_h3, *d_xc, *d_h1, *d_x1;
     float *gt_rgb, *gt_feat, *loss_ws, *ones, *adam_scal, *part[9], *emb_part, *grads;   // part[i]: split partials of weight gradient i
+    float *wp_in, *wp_cat, *wp_cl, *wp_cp;   // in_layer / cat_layer / color_linear / clip_linear weights with rows padded to ld1 / ldc / ldh
     int ld1, ldc, ldh;
     long long total;
 };
@@ -571,8 +570,25 @@ BgWs bg_ws_map(float* base, int h, int n_pts, int n_rays) {
     }
     w.emb_part = take(((M + EB_PTS - 1) / EB_PTS) * (NDIR * 3));
     w.grads = take(bg_layout(h).total);
+    w.wp_in = take((long long)h * w.ld1); w.wp_cat = take((long long)h * w.ldc);
+    w.wp_cl = take((long long)h * w.ldh); w.wp_cp = take((long long)h * w.ldh);
     w.total = o;
     return w;
+}
+
+// The four weight matrices whose rows are not multiples of 4 floats (in 87, cat h + 87, heads h + 42) get a zero-padded,
+// 16-byte aligned copy per step: the tcgen05 engine stages aligned rows with 16-byte asynchronous copies (forward: weights are
+// the contraction-contiguous B operand) and 128-bit loads (backward-data: row-contiguous B operand).
+__global__ void k_pack_weights(const float* __restrict__ th, int h, int o_in, int o_cat, int o_cl, int o_cp, float* __restrict__ p_in,
+                               float* __restrict__ p_cat, float* __restrict__ p_cl, float* __restrict__ p_cp, int ld1, int ldc, int ldh) {
+    const int which = blockIdx.y;
+    const float* src = th + (which == 0 ? o_in : which == 1 ? o_cat : which == 2 ? o_cl : o_cp);
+    float* dst = which == 0 ? p_in : which == 1 ? p_cat : which == 2 ? p_cl : p_cp;
+    const int cols = which == 0 ? E1 : which == 1 ? h + E1 : h + E2, ld = which == 0 ? ld1 : which == 1 ? ldc : ldh;
+    for (int e = blockIdx.x * blockDim.x + threadIdx.x; e < h * ld; e += gridDim.x * blockDim.x) {
+        const int r = e / ld, c = e - r * ld;
+        dst[e] = c < cols ? src[r * cols + c] : 0.f;
+    }
 }
 
 GemmOp op(const float* A, long long sai, long long sac, const float* B, long long sbj, long long sbc, float* Cp, long long sci,
@@ -596,15 +612,18 @@ int bg_forward(const float* th, const BgLayout& L, int h, const float* pcs, int 
     if (emb_in != nullptr) k_embed_scatter<<<(unsigned)(((size_t)M * EMB + 255) / 256), 256, 0, st>>>(emb_in, M, eb);
     else k_embed_fwd<<<(unsigned)(((size_t)M * 24 + 255) / 256), 256, 0, st>>>(pcs, th + L.off[T_PE], scale, M, eb, emb_out);
     OO_LAUNCH_CHECK();
+    k_pack_weights<<<dim3(16, 4), 256, 0, st>>>(th, h, L.off[T_IN_W], L.off[T_CAT_W], L.off[T_CL_W], L.off[T_CP_W], w.wp_in, w.wp_cat,
+                                               w.wp_cl, w.wp_cp, w.ld1, w.ldc, w.ldh);
+    OO_LAUNCH_CHECK();
     GemmOp g;
     // fc1 = relu(in_layer(e1))
-    g = op(w.x1, w.ld1, 1, th + L.off[T_IN_W], E1, 1, w.h1, h, 1, M, h, E1); g.bias = th + L.off[T_IN_B]; g.act = 1;
+    g = op(w.x1, w.ld1, 1, w.wp_in, w.ld1, 1, w.h1, h, 1, M, h, E1); g.bias = th + L.off[T_IN_B]; g.act = 1;
     OO_TRY(run_gemm(g, 1, nullptr, st));
     // fc2 = relu(mid1(fc1)) -> cols 0..h-1 of the cat input
     g = op(w.h1, h, 1, th + L.off[T_M1_W], h, 1, w.xc, w.ldc, 1, M, h, h); g.bias = th + L.off[T_M1_B]; g.act = 1;
     OO_TRY(run_gemm(g, 1, nullptr, st));
     // fc3 = relu(cat_layer([fc2, e1]))
-    g = op(w.xc, w.ldc, 1, th + L.off[T_CAT_W], h + E1, 1, w.h3, h, 1, M, h, h + E1); g.bias = th + L.off[T_CAT_B]; g.act = 1;
+    g = op(w.xc, w.ldc, 1, w.wp_cat, w.ldc, 1, w.h3, h, 1, M, h, h + E1); g.bias = th + L.off[T_CAT_B]; g.act = 1;
     OO_TRY(run_gemm(g, 1, nullptr, st));
     // fc4 = relu(mid2(fc3)) -> cols 0..h-1 of the head input
     g = op(w.h3, h, 1, th + L.off[T_M2_W], h, 1, w.xh, w.ldh, 1, M, h, h); g.bias = th + L.off[T_M2_B]; g.act = 1;
@@ -613,12 +632,12 @@ int bg_forward(const float* th, const BgLayout& L, int h, const float* pcs, int 
     g = op(w.xh, w.ldh, 1, th + L.off[T_A_W], h, 1, w.alpha, 1, 1, M, 1, h); g.bias = th + L.off[T_A_B]; g.post = 10.f;
     OO_TRY(run_gemm(g, 1, nullptr, st));
     // color = sigmoid(out_color(relu(color_linear([fc4, e2]))))
-    g = op(w.xh, w.ldh, 1, th + L.off[T_CL_W], h + E2, 1, w.hc, h, 1, M, h, h + E2); g.bias = th + L.off[T_CL_B]; g.act = 1;
+    g = op(w.xh, w.ldh, 1, w.wp_cl, w.ldh, 1, w.hc, h, 1, M, h, h + E2); g.bias = th + L.off[T_CL_B]; g.act = 1;
     OO_TRY(run_gemm(g, 1, nullptr, st));
     g = op(w.hc, h, 1, th + L.off[T_OC_W], h, 1, w.color, 3, 1, M, 3, h); g.bias = th + L.off[T_OC_B]; g.act = 2;
     OO_TRY(run_gemm(g, 1, nullptr, st));
     // clip = out_clip(relu(clip_linear([fc4, e2])))
-    g = op(w.xh, w.ldh, 1, th + L.off[T_CP_W], h + E2, 1, w.hp, h, 1, M, h, h + E2); g.bias = th + L.off[T_CP_B]; g.act = 1;
+    g = op(w.xh, w.ldh, 1, w.wp_cp, w.ldh, 1, w.hp, h, 1, M, h, h + E2); g.bias = th + L.off[T_CP_B]; g.act = 1;
     OO_TRY(run_gemm(g, 1, nullptr, st));
     if (want_clip) {
         g = op(w.hp, h, 1, th + L.off[T_OCL_W], h, 1, w.clip, C, 1, M, C, h); g.bias = th + L.off[T_OCL_B];
@@ -668,11 +687,11 @@ int bg_backward(const float* theta, const BgLayout& L, int h, const float* pcs, 
     OO_TRY(run_gemm(g, BG_SPLIT, w.part[4], st, &pending));
     // ---- d [fc4, e2] = d_hc W_cl + d_hp W_cp + 10 d_alpha W_a (cols < h).  The ReLU mask of fc4 is a 0/1 factor, so it is
     // applied to every term as it is added: (a + b + c) m == a m + b m + c m exactly, in the same order
-    g = op(w.d_hc, h, 1, th + L.off[T_CL_W], 1, h + E2, w.d_xh, w.ldh, 1, M, h + E2, h);
+    g = op(w.d_hc, h, 1, w.wp_cl, 1, w.ldh, w.d_xh, w.ldh, 1, M, h + E2, h);
     g.mask = w.xh; g.smi = w.ldh; g.smj = 1; g.mask_cols = h;
     OO_TRY(run_gemm(g, 1, nullptr, st));
     if (part) {
-        g = op(w.d_hp, h, 1, th + L.off[T_CP_W], 1, h + E2, w.d_xh, w.ldh, 1, M, h + E2, h); g.accumulate = 1;
+        g = op(w.d_hp, h, 1, w.wp_cp, 1, w.ldh, w.d_xh, w.ldh, 1, M, h + E2, h); g.accumulate = 1;
         g.mask = w.xh; g.smi = w.ldh; g.smj = 1; g.mask_cols = h;
         OO_TRY(run_gemm(g, 1, nullptr, st));
     }
@@ -690,7 +709,7 @@ int bg_backward(const float* theta, const BgLayout& L, int h, const float* pcs, 
     g = op(w.d_h3, 1, h, w.xc, 1, w.ldc, G + L.off[T_CAT_W], h + E1, 1, h, h + E1, M);
     g.ones_out = G + L.off[T_CAT_B];
     OO_TRY(run_gemm(g, BG_SPLIT, w.part[6], st, &pending));
-    g = op(w.d_h3, h, 1, th + L.off[T_CAT_W], 1, h + E1, w.d_xc, w.ldc, 1, M, h + E1, h);
+    g = op(w.d_h3, h, 1, w.wp_cat, 1, w.ldc, w.d_xc, w.ldc, 1, M, h + E1, h);
     g.mask = w.xc; g.smi = w.ldc; g.smj = 1; g.mask_cols = h;
     OO_TRY(run_gemm(g, 1, nullptr, st));
     // ---- mid1
@@ -704,7 +723,7 @@ int bg_backward(const float* theta, const BgLayout& L, int h, const float* pcs, 
     g = op(w.d_h1, 1, h, w.x1, 1, w.ld1, G + L.off[T_IN_W], E1, 1, h, E1, M);
     g.ones_out = G + L.off[T_IN_B];
     OO_TRY(run_gemm(g, BG_SPLIT, w.part[8], st, &pending));
-    g = op(w.d_h1, h, 1, th + L.off[T_IN_W], 1, E1, w.d_x1, w.ld1, 1, M, E1, h);
+    g = op(w.d_h1, h, 1, w.wp_in, 1, w.ld1, w.d_x1, w.ld1, 1, M, E1, h);
     OO_TRY(run_gemm(g, 1, nullptr, st));
     // ---- encoder: B_layer.weight is trainable (embedding.py:43); on a caller-supplied embedding its gradient
     // goes back to the caller instead
