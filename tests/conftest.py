@@ -17,8 +17,13 @@ def pytest_configure(config):
 
 
 def pytest_collection_modifyitems(config, items):
-    # `-m gpu` on a box without a GPU must fail loudly rather than silently pass.
-    pass
+    # `-m gpu` on a box without a GPU must fail loudly rather than silently pass: the kernels are the product and there is
+    # no CPU fallback behind them.
+    expr = (config.getoption("-m") or "").strip()
+    if expr == "gpu" and any(it.get_closest_marker("gpu") for it in items):
+        import torch
+        if not torch.cuda.is_available():
+            raise pytest.UsageError("`-m gpu` selected but no CUDA device is visible: the GPU tests cannot run here")
 
 
 @pytest.fixture(scope="session")
