@@ -104,6 +104,7 @@ class Scene:
         self.kf = cfg.keyframe_buffer_size
         self.store = FrameStore(cfg.W, cfg.H, self.device, capacity=store_capacity)
         self.tab = _Tables(max((int(cfg.max_n_models) + world - 1) // world, 1), self.kf, self.device)
+        self.bank = vmap.RingBank(self.tab.cap, self.kf)      # keyframe policy of every local object, as arrays
         self._objs = []
         self.tab_bg = None
         self._stale = False
@@ -111,8 +112,10 @@ class Scene:
         self.sample_out = None
         self._copy_stream = None
         self._sorted_ids = (None, None)
-        self._vis_cache = (None, None, None)
+        self._vis_cache = (None, None, None, None)
         self._bbox_cache = {}
+        self._sample_cache = {}
+        self._staged_pending, self._part_event = 0, None
         self._empty_bits = None
         # the separate background model (train.py:236-242): one hidden-128 model, not part of the vmap ensemble; it lives
         # on the last rank (the ensemble's round-robin starts at rank 0)
@@ -123,19 +126,40 @@ class Scene:
     # copies gives the reference, train.py:158-188): the 76 MB of a Replica frame travel while the current frame trains
     def stage_frame(self, sample):
         """Start the H2D copies of `sample` (pinned host tensors) on the copy stream; returns a dict to pass to
-        add_frame.  Tensors already on the device pass through."""
+        add_frame.  Tensors already on the device pass through.  The small tensors ingestion and sampling need (image, depth,
+        instance map: 9.8 MB at Replica size) go first and get their own event; the part features (66.8 MB), which only the
+        training kernels read, follow STRAIGHT into their slot of the resident part-feature table with a second event, so
+        the frame store write, K2 and the per-frame bookkeeping run while they are still on the wire."""
         if self._copy_stream is None:
             self._copy_stream = torch.cuda.Stream(device=self.device)
         out = dict(sample)
         with torch.cuda.stream(self._copy_stream):
-            for k in ("image", "depth", "obj", "part_feat"):
+            for k in ("image", "depth", "obj"):
                 v = sample.get(k)
                 if torch.is_tensor(v) and v.device != self.device:
                     out[k] = v.to(self.device, non_blocking=True)
             ev = torch.cuda.Event()
             ev.record(self._copy_stream)
-        out["_staged"] = ev
+            out["_staged"] = ev
+            pf = sample.get("part_feat")
+            if self.part_mode and torch.is_tensor(pf):
+                slot = self.frames_seen + self._staged_pending
+                if slot >= self.part_table.shape[0]:
+                    raise RuntimeError("part-feature table full: raise max_frames")
+                # nothing reads this slot yet: rows of the table are only reached through keyframes already ingested
+                self.part_table[slot].copy_(pf, non_blocking=True)           # train.py:183-188, without a staging copy
+                ev2 = torch.cuda.Event()
+                ev2.record(self._copy_stream)
+                out["_part_slot"], out["_part_event"] = slot, ev2
+                out.pop("part_feat", None)
+        self._staged_pending += 1
         return out
+
+    def _wait_part_features(self):
+        """Training kernels gather rows of the part-feature table: the newest frame's rows must have landed."""
+        if self._part_event is not None:
+            torch.cuda.current_stream(self.device).wait_event(self._part_event)
+            self._part_event = None
 
     def _ids_of(self, bbox_dict):
         """Sorted instance ids of a frame (torch.unique order, train.py:191); cached while the same dict object comes back."""
@@ -160,6 +184,19 @@ class Scene:
             if len(lat) >= 2:
                 tab.latest[i, 0], tab.latest[i, 1] = lat[-2], lat[-1]
 
+    def _place_bank(self, tab, ii, ss, boxes, store_slot, frame_id):
+        """_place_all for objects whose rings live in self.bank: no per-object Python at all."""
+        self.store.release_many(tab.slot_frame[ii, ss].astype(np.int64))
+        self.store.acquire(store_slot, int(ii.size))
+        tab.slot_frame[ii, ss] = store_slot
+        tab.slot_bbox[ii, ss] = boxes
+        if self.part_mode:
+            self.bank.use_frame[ii, ss] = frame_id
+            tab.part_frame[ii, ss] = int(frame_id / self.cfg.stride)      # (use_frame / stride).long(), vmap.py:438-440
+        tab.n_kf[ii] = self.bank.n_kf[ii]
+        two = self.bank.lat_len[ii] >= 2
+        tab.latest[ii[two]] = self.bank.lat[ii[two]]
+
     def _bbox_np(self, obj_id, bbox):
         """float32 [4] of a frame's 2-D box; a box object that comes back unchanged (same tensor) is converted once."""
         c = self._bbox_cache.get(obj_id)
@@ -177,24 +214,32 @@ class Scene:
             for k in ("image", "depth", "obj", "part_feat"):     # allocated on the copy stream, consumed on this one
                 if torch.is_tensor(sample.get(k)) and sample[k].is_cuda:
                     sample[k].record_stream(cur)
+            self._staged_pending -= 1
         rgb, depth = sample["image"].to(dev, **nb), sample["depth"].to(dev, **nb)
         inst = sample["obj"].to(dev, **nb)
         frame_id = sample.get("frame_id", self.frames_seen)
         if self.part_mode:
             if self.frames_seen >= self.part_table.shape[0]:
                 raise RuntimeError("part-feature table full: raise max_frames")
-            self.part_table[self.frames_seen].copy_(sample["part_feat"], non_blocking=True)   # train.py:183-188
+            if "_part_slot" in sample:           # stage_frame sent the features straight to their slot
+                assert sample["_part_slot"] == self.frames_seen, "staged frames must be added in the order they were staged"
+                self._part_event = sample["_part_event"]
+            else:
+                self._wait_part_features()
+                self.part_table[self.frames_seen].copy_(sample["part_feat"], non_blocking=True)   # train.py:183-188
         twc = sample["T"]
         twc32 = (twc.detach().cpu() if torch.is_tensor(twc) else torch.as_tensor(np.asarray(twc))).to(torch.float32).reshape(16)
         bd = sample["bbox_dict"]
         obj_clip, obj_cap = sample.get("obj_clip"), sample.get("obj_cap")
-        placed = []                   # (tab, local index, object, ring slot, bbox)
+        placed = []                   # new objects and the background: (tab, local index, object, ring slot, bbox)
+        old_idx, old_ids = [], []     # local objects seen before: their keyframe policy runs as arrays (vmap.RingBank)
         new_global = False
         ids = self._ids_of(bd)
         # frames usually come with the same objects as the one before: once every id of this dict is known, only the ids this
-        # rank owns (and the background) are walked
+        # rank owns (and the background) are walked, and their local indices / boxes are cached with them
         key = (id(bd), len(bd), len(self.book.global_index))
-        if self._vis_cache[0] == key and self._vis_cache[1] is bd:
+        cached = self._vis_cache[0] == key and self._vis_cache[1] is bd
+        if cached:
             ids = self._vis_cache[2]
         for obj_id in ids:
             if obj_id == -1:
@@ -220,6 +265,8 @@ class Scene:
                     slot = self.scene_bg.push_slot(frame_id, _first(obj_clip, obj_id), _get(obj_cap, obj_id))
                 placed.append((self.tab_bg, 0, self.scene_bg, slot, bd[obj_id]))
                 continue
+            if cached and self._vis_cache[3] is not None:
+                break                  # every other cached id is a known local object: taken from the cache below
             seen = self.book.see(obj_id)
             if seen is None:
                 continue               # "models full" (train.py:231-233): the cap is global, whatever the number of ranks
@@ -228,23 +275,43 @@ class Scene:
             if i is None:
                 continue               # another rank's object
             if new:
-                o = self._new_object(obj_id, rgb, depth, bd[obj_id], twc32, frame_id, obj_clip, obj_cap)
+                o = self._new_object(obj_id, rgb, depth, bd[obj_id], twc32, frame_id, obj_clip, obj_cap, i)
                 assert i == len(self.obj_dict)
                 self.obj_dict[obj_id] = o
                 self.tab.obj_id[i] = obj_id
-                slot = 0
                 self._stale = True
+                placed.append((self.tab, i, o, 0, bd[obj_id]))
             else:
-                o = self._objs[i]
-                slot = o.push_slot(frame_id, _first(obj_clip, obj_id), _get(obj_cap, obj_id))
-            placed.append((self.tab, i, o, slot, bd[obj_id]))
+                old_idx.append(i)
+                old_ids.append(obj_id)
         self._objs = list(self.obj_dict.values())
+        box_ids = None
+        if cached and self._vis_cache[3] is not None:
+            old_arr, old_ids, old_box, box_ids = self._vis_cache[3]
+            now_ids = tuple(id(bd[i]) for i in old_ids)
+            if now_ids != box_ids:         # same dict, boxes replaced in place: convert them again
+                old_box, box_ids = np.stack([self._bbox_np(i, bd[i]) for i in old_ids]), now_ids
+        else:
+            old_arr = np.asarray(old_idx, dtype=np.int64)
+            old_box = (np.stack([self._bbox_np(i, bd[i]) for i in old_ids]) if old_ids else np.zeros((0, 4), np.float32))
         if not new_global:
             mine = [i for i in self._ids_of(bd) if i in self.book.local_index or (cfg.do_bg and i == 0)]
-            self._vis_cache = ((id(bd), len(bd), len(self.book.global_index)), bd, mine)
+            # the background id (0) sorts first, so the walk above handles it before it reaches the cached local objects
+            fast = not placed or all(p[0] is self.tab_bg for p in placed)
+            if fast and box_ids is None:
+                box_ids = tuple(id(bd[i]) for i in old_ids)
+            self._vis_cache = ((id(bd), len(bd), len(self.book.global_index)), bd, mine,
+                               (old_arr, old_ids, old_box, box_ids) if fast else None)
+        # ---- keyframe policy of the known local objects (vmap.py:166-257), all at once
+        old_slots = self.bank.push_many(old_arr, frame_id) if old_arr.size else np.zeros(0, np.int64)
+        if old_arr.size and (obj_clip is not None or obj_cap is not None):
+            for i, obj_id in zip(old_arr.tolist(), old_ids):           # semantic features of append_keyframe (vmap.py:241-246)
+                self._objs[i].add_semantic(_first(obj_clip, obj_id), _get(obj_cap, obj_id))
         # ---- the frame itself: ONE copy in the shared store (12 bytes per pixel whatever the number of objects)
         self.tab.t_wc[:] = twc32.numpy()
-        g = self.store.alloc() if placed else -1
+        g = self.store.alloc() if (placed or old_arr.size) else -1
+        if old_arr.size:
+            self._place_bank(self.tab, old_arr, old_slots, old_box, g, frame_id)
         for tab in (self.tab, self.tab_bg):
             mine = [(i, o, slot, bbox) for t, i, o, slot, bbox in placed if t is tab]
             if mine:
@@ -252,7 +319,7 @@ class Scene:
         self.tab.upload()                                          # slot tables + the pose the store kernel reads
         if self.tab_bg is not None:
             self.tab_bg.upload()
-        if placed:
+        if g >= 0:
             self.store.write(g, rgb, depth, inst, self.tab.d_t_wc)
         self.frames_seen += 1
         if self._stale:
@@ -260,9 +327,10 @@ class Scene:
         elif new_global and self.ens is not None:
             self.ens.reset_optimizer()     # another rank's new object: the reference restacks everything (quirk 7)
 
-    def _new_object(self, obj_id, rgb, depth, bbox, twc32, frame_id, obj_clip, obj_cap):
+    def _new_object(self, obj_id, rgb, depth, bbox, twc32, frame_id, obj_clip, obj_cap, index):
         mk = lambda: vmap.sceneObject(self.cfg, obj_id, rgb, depth, None, bbox, twc32.view(4, 4), frame_id, shared=True,   # noqa: E731
-                                      clip_feat=_first(obj_clip, obj_id), caption_feat=_get(obj_cap, obj_id))
+                                      clip_feat=_first(obj_clip, obj_id), caption_feat=_get(obj_cap, obj_id),
+                                      bank=self.bank, bank_index=index)
         if self.init_seed is None:
             return mk()
         with torch.random.fork_rng(devices=[self.device]):
@@ -291,11 +359,13 @@ class Scene:
     # ---- train.py:300-388 -----------------------------------------------------------------------------------
     def _sample(self, tab, n, obj0, n_frames, n_samples, out):
         cfg = self.cfg
+        cache = self._sample_cache.setdefault(id(tab), {})
         rng = sampler.CounterRng(self.seed, self.frames_seen, tab.d_obj_id[:n], tab.d_n_kf[:n], tab.d_latest[:n])
         return sampler.sample(None, None, None, None, tab.d_part_frame[:n] if self.part_mode else None, self.cam.rays_dir_cache,
                               rng, n_frames, n_samples, obj0.n_bins_cam2surface, obj0.n_bins, obj0.surface_eps, obj0.stop_eps,
                               obj0.min_bound, cfg.part_down if self.part_mode else 0, (self.pw, self.ph), out=out,
-                              store=self.store, slot_frame=tab.d_slot_frame[:n], slot_bbox=tab.d_slot_bbox[:n], kf_cap=self.kf)
+                              store=self.store, slot_frame=tab.d_slot_frame[:n], slot_bbox=tab.d_slot_bbox[:n], kf_cap=self.kf,
+                              cache=cache)
 
     def sample(self):
         cfg = self.cfg
@@ -323,6 +393,7 @@ class Scene:
         scalar loss of each step (the reference adds it to the same scalar, train.py:463: the two problems share no
         tensor, so they are trained as two independent launch sequences)."""
         iters = int(iters or self.cfg.n_iter_per_frame)
+        self._wait_part_features()
         if self.batch is not None:
             self.ens.train_frame(self.batch, iters=iters, loss_terms=loss_terms, flag_allreduce=self.flag_allreduce)
         elif self.flag_allreduce is not None:

@@ -59,9 +59,145 @@ class KeyframeRing:
         return slot
 
 
+class RingBank:
+    """The keyframe policy of MANY objects as arrays (scene.Scene): the same decisions as one KeyframeRing per object
+    (vmap.py:166-257), taken for all objects a frame shows in a handful of numpy operations instead of a Python loop -- the
+    per-frame host work ahead of the first kernel is what a short training window pays for.  The insertion-ordered
+    frame-id -> slot dictionary of the reference (`kf_id_dict`, whose ORDER the pruning draw depends on) is kept as two arrays
+    per object: the frame id held by each slot and a stamp of when the slot was last (re)keyed; the dictionary's order is the
+    order of the stamps.  Rings whose buffer is full (pruning with Python's `random.choice`) are stepped one by one, in the
+    order given, so the draws are consumed exactly as by per-object rings.  `ring(i)` is a KeyframeRing-compatible view."""
+
+    def __init__(self, cap, buffer_size):
+        self.cap, self.K = int(cap), int(buffer_size)
+        n, K = self.cap, self.K
+        self.frame_cnt = np.zeros(n, dtype=np.int64)
+        self.n_kf = np.zeros(n, dtype=np.int32)
+        self.step = np.ones(n, dtype=np.float64)
+        self.full = np.zeros(n, dtype=bool)
+        self.kf_ptr = np.full(n, -1, dtype=np.int32)           # -1 = None
+        self.lat = np.zeros((n, 2), dtype=np.int32)
+        self.lat_len = np.zeros(n, dtype=np.int32)
+        self.fid = np.full((n, K), -1, dtype=np.int64)         # frame id held by each slot
+        self.stamp = np.full((n, K), -1, dtype=np.int64)       # when the slot was last (re)keyed; -1 = never
+        self.use_frame = np.zeros((n, K))                      # sceneObject.use_frame rows (float64 like the reference)
+        self.clock = 0
+
+    def add(self, i, first_frame_id, keyframe_step):
+        self.frame_cnt[i], self.n_kf[i], self.step[i], self.full[i], self.kf_ptr[i] = 0, 1, keyframe_step, False, -1
+        self.lat_len[i] = 0
+        self.fid[i], self.stamp[i] = -1, -1
+        self.fid[i, 0], self.stamp[i, 0] = first_frame_id, self._tick()
+        return BankRing(self, i)
+
+    def _tick(self):
+        self.clock += 1
+        return self.clock
+
+    def _append_latest(self, i, slot):
+        if self.lat_len[i] < 2:
+            self.lat[i, self.lat_len[i]] = slot
+            self.lat_len[i] += 1
+        else:
+            self.lat[i, 0], self.lat[i, 1] = self.lat[i, 1], slot
+
+    def ordered_items(self, i):
+        """[(frame id, slot)] in the reference dictionary's order."""
+        used = np.nonzero(self.stamp[i] >= 0)[0]
+        order = used[np.argsort(self.stamp[i, used], kind="stable")]
+        return [(int(self.fid[i, s]), int(s)) for s in order]
+
+    def push_one(self, i, frame_id):
+        """KeyframeRing.push for ring i (the general path: full buffers prune with random.choice)."""
+        K = self.K
+        nk, cnt = int(self.n_kf[i]), int(self.frame_cnt[i])
+        is_kf = (cnt % float(self.step[i]) == 0) or nk == 1
+        if nk == K - 1:
+            self.full[i] = True
+            if self.kf_ptr[i] < 0:
+                self.kf_ptr[i] = nk
+            slot = int(self.kf_ptr[i])
+            self.fid[i, slot], self.stamp[i, slot] = frame_id, self._tick()
+            if is_kf:
+                self._append_latest(i, slot)
+                _, ptr_ = random.choice(self.ordered_items(i)[:-2])
+                self.kf_ptr[i] = ptr_
+        elif not is_kf:
+            slot = nk - 1
+            self.fid[i, slot], self.stamp[i, slot] = frame_id, self._tick()
+        else:
+            slot = nk
+            self.fid[i, slot], self.stamp[i, slot] = frame_id, self._tick()
+            self._append_latest(i, slot)
+            self.n_kf[i] = nk + 1
+        self.frame_cnt[i] = cnt + 1
+        return slot
+
+    def push_many(self, ii, frame_id):
+        """One new frame for the rings `ii` (int array, in the order the reference would visit them) -> their slots."""
+        ii = np.asarray(ii, dtype=np.int64)
+        K = self.K
+        nk, cnt = self.n_kf[ii].astype(np.int64), self.frame_cnt[ii]
+        is_kf = (np.mod(cnt.astype(np.float64), self.step[ii]) == 0) | (nk == 1)
+        fullm = nk == K - 1
+        t = self._tick()
+        # ---- rings with room: a keyframe takes the next slot, any other frame overwrites the newest one
+        slots = np.where(is_kf, nk, nk - 1)
+        # ---- full rings: the frame goes to the slot the last pruning draw freed (the first time: the one spare slot)
+        if fullm.any():
+            f = ii[fullm]
+            self.full[f] = True
+            first = self.kf_ptr[f] < 0
+            self.kf_ptr[f[first]] = K - 1
+            slots[fullm] = self.kf_ptr[f]
+        self.fid[ii, slots], self.stamp[ii, slots] = frame_id, t
+        ik, sk = ii[is_kf], slots[is_kf]
+        if ik.size:                                           # keyframes enter the latest-two queue
+            two = self.lat_len[ik] >= 2
+            i2, s2 = ik[two], sk[two]
+            self.lat[i2, 0] = self.lat[i2, 1]
+            self.lat[i2, 1] = s2
+            i1, s1 = ik[~two], sk[~two]
+            self.lat[i1, self.lat_len[i1]] = s1
+            self.lat_len[i1] += 1
+            grow = is_kf & ~fullm
+            self.n_kf[ii[grow]] += 1
+        prune = is_kf & fullm
+        if prune.any():
+            # random.choice(list(kf_id_dict.items())[:-2]) (vmap.py:256): every slot of a full ring is keyed, the dictionary's
+            # order is the stamps' order; choice(seq) is seq[randbelow(len(seq))], so a range of the same length consumes the
+            # generator identically -- one draw per ring, in the order given
+            rows = ii[prune]
+            order = np.argsort(self.stamp[rows], axis=1, kind="stable")[:, :K - 2]
+            n = range(K - 2)
+            js = np.fromiter((random.choice(n) for _ in range(rows.size)), dtype=np.int64, count=rows.size)
+            self.kf_ptr[rows] = order[np.arange(rows.size), js]
+        self.frame_cnt[ii] += 1
+        return slots
+
+
+class BankRing:
+    """KeyframeRing's attributes and push() for ring i of a RingBank."""
+
+    def __init__(self, bank, i):
+        self.bank, self.i = bank, int(i)
+        self.buffer_size = bank.K
+
+    keyframe_step = property(lambda self: float(self.bank.step[self.i]))
+    n_keyframes = property(lambda self: int(self.bank.n_kf[self.i]))
+    kf_pointer = property(lambda self: None if self.bank.kf_ptr[self.i] < 0 else int(self.bank.kf_ptr[self.i]))
+    kf_buffer_full = property(lambda self: bool(self.bank.full[self.i]))
+    frame_cnt = property(lambda self: int(self.bank.frame_cnt[self.i]))
+    latest = property(lambda self: [int(v) for v in self.bank.lat[self.i, :self.bank.lat_len[self.i]]])
+    slot_of = property(lambda self: dict(self.bank.ordered_items(self.i)))
+
+    def push(self, frame_id):
+        return self.bank.push_one(self.i, frame_id)
+
+
 class sceneObject:
     def __init__(self, cfg, obj_id, rgb, depth, mask, bbox_2d, t_wc, live_frame_id, clip_feat=None, caption_feat=None,
-                 shared=False):
+                 shared=False, bank=None, bank_index=None):
         """`shared=True` (used by scene.Scene): the object owns NO pixel rings -- its keyframes are slots of the scene's shared
         frame store (framestore.FrameStore, SURVEY 8f rank 2) and its pixel state is derived from the stored instance map;
         only the keyframe policy (self.ring) and the semantic features live here."""
@@ -81,7 +217,10 @@ class sceneObject:
         self.n_bins, self.n_unidir_funcs = cfg.n_bins, cfg.n_unidir_funcs
         self.surface_eps, self.stop_eps = cfg.surface_eps, cfg.stop_eps
         self.keyframe_buffer_size = cfg.keyframe_buffer_size
-        self.ring = KeyframeRing(live_frame_id, self.keyframe_buffer_size, self.keyframe_step)
+        # bank: the scene keeps every object's keyframe policy in one RingBank (arrays); this object's ring is a view of it
+        self.ring = (bank.add(bank_index, live_frame_id, self.keyframe_step) if bank is not None
+                     else KeyframeRing(live_frame_id, self.keyframe_buffer_size, self.keyframe_step))
+        self._bank_row = bank.use_frame[bank_index] if bank is not None else None
         self.feat_cnt, self.clip_feat, self.caption_feat = 1, clip_feat, caption_feat
         self.eps_fine_vis, self.n_bins_fine_vis = cfg.eps_fine_vis, cfg.n_bins_fine_vis
         dev, K, W, H = self.data_device, self.keyframe_buffer_size, self.frames_width, self.frames_height
@@ -96,7 +235,8 @@ class sceneObject:
             self.t_wc_batch = torch.empty(K, 4, 4, dtype=torch.float32, device=dev)
         if self.part_mode:
             self.part_down = cfg.part_down
-            self.use_frame = np.zeros(K)
+            self.use_frame = self._bank_row if self._bank_row is not None else np.zeros(K)
+            self.use_frame[:] = 0
         self.other_obj, self.this_obj, self.unknown_obj = 0, 1, 2
         self.semantic_id = None
         if defer_write:
@@ -147,6 +287,13 @@ class sceneObject:
             self.caption_feat = np.vstack((self.caption_feat, caption_feat))
             self.feat_cnt += 1
         return s
+
+    def add_semantic(self, clip_feat, caption_feat):
+        """The semantic-feature accumulation of append_keyframe (vmap.py:241-246) on its own."""
+        if clip_feat is not None and self.clip_feat is not None:
+            self.clip_feat = np.vstack((self.clip_feat, clip_feat))
+            self.caption_feat = np.vstack((self.caption_feat, caption_feat))
+            self.feat_cnt += 1
 
     def prune_keyframe(self):
         return random.choice(list(self.ring.slot_of.items())[:-2])

@@ -173,3 +173,39 @@ def test_scene_scannet_shape_part_features_off():
         assert sc.ens.adam_t.cpu().tolist()[2] == 0 and sc.ens.adam_t.cpu().tolist()[0] == 2 * cfg.n_iter_per_frame
         res.append((sc.ens.theta.clone(), lt.clone()))
     assert torch.equal(res[0][0], res[1][0]) and torch.equal(res[0][1], res[1][1])
+
+
+def test_staged_frames_with_part_features_equal_direct_frames():
+    """Scene.stage_frame sends the part features of the NEXT frame straight into their slot of the resident table on the copy
+    stream (their own event, awaited by the training kernels only): pipelined staging must give bit-identical parameters and
+    loss terms to frames handed over directly, with part features on."""
+    from openobj_b200 import cfg as C
+    from openobj_b200.scene import Scene
+    from openobj_b200.synthetic import SyntheticScene
+    res = []
+    for staged in (False, True):
+        torch.manual_seed(5)
+        cfg = C.room0_config()
+        cfg.do_bg = False
+        cfg.part_mode = True
+        cfg.W, cfg.H = 320, 240
+        cfg.fx = cfg.fy = 160.0
+        cfg.cx, cfg.cy = 159.5, 119.5
+        cfg.n_iter_per_frame = 6
+        synth = SyntheticScene(5, W=cfg.W, H=cfg.H, part_mode=True, seed=9, n_distinct=2, pin=True)
+        sc = Scene(cfg, seed=3, max_frames=6)
+        lt = torch.zeros(cfg.n_iter_per_frame, 5, 4, device=DEV)
+        terms = []
+        nxt = sc.stage_frame(synth.frame(0)) if staged else synth.frame(0)
+        for f in range(4):
+            sc.add_frame(nxt)
+            if f + 1 < 4:                      # the next frame's copies are in flight while this one samples and trains
+                nxt = sc.stage_frame(synth.frame(f + 1)) if staged else synth.frame(f + 1)
+            sc.sample()
+            sc.train(loss_terms=lt)
+            terms.append(lt.clone())
+        torch.cuda.synchronize()
+        assert bool(torch.isfinite(torch.stack(terms)).all()) and float(torch.stack(terms)[..., 3].abs().max()) > 0.0
+        res.append((sc.ens.theta.clone(), torch.stack(terms), sc.part_table[:4].clone()))
+    assert torch.equal(res[0][2], res[1][2])
+    assert torch.equal(res[0][0], res[1][0]) and torch.equal(res[0][1], res[1][1])

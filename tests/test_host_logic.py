@@ -5,6 +5,7 @@ import os
 import random
 import re
 
+import numpy as np
 import pytest
 import torch
 
@@ -93,3 +94,54 @@ def test_reference_checkpoint_keys_are_the_drop_in_state_dict():
     assert list(ck["PE_state_dict"].keys()) == list(pe.state_dict().keys())
     fc.load_state_dict(ck["FC_state_dict"])
     pe.load_state_dict(ck["PE_state_dict"])
+
+
+def test_ring_bank_matches_reference_trace():
+    """The array form of the keyframe policy (vmap.RingBank, what scene.Scene runs) against the reference's 140-frame trace."""
+    from openobj_b200.vmap import RingBank
+    t = json.load(open(os.path.join(ROOT, "tests", "golden", "keyframe_policy.json")))
+    random.seed(t["seed"])
+    bank = RingBank(3, t["buffer"])
+    ring = bank.add(1, 0, t["keyframe_step"])
+    for n, rec in enumerate(t["trace"][1:]):
+        s = int(bank.push_many(np.array([1]), rec["frame"])[0]) if n % 2 else ring.push(rec["frame"])
+        assert ring.n_keyframes == rec["n_keyframes"] and ring.kf_pointer == rec["kf_pointer"]
+        assert ring.latest == rec["latest"] and ring.frame_cnt == rec["frame_cnt"]
+        assert [[k, v] for k, v in ring.slot_of.items()] == rec["kf_id_dict"]
+        assert 0 <= s < t["buffer"]
+
+
+def test_ring_bank_equals_per_object_rings():
+    """RingBank.push_many == one KeyframeRing per object on random schedules: objects appearing at different frames, dropping
+    out of view, different keyframe steps, small buffers so that most rings are full and prune with random.choice -- the
+    draws must be consumed in the same order."""
+    from openobj_b200.vmap import KeyframeRing, RingBank
+    for seed in range(24):
+        K = [4, 6, 20][seed % 3]
+        n_obj, n_frames = 7, 150
+        steps = [[2.5, 5.0, 1.0, 2.0][(seed + o) % 4] for o in range(n_obj)]
+        rs = np.random.RandomState(seed)
+        first, present = rs.randint(0, 10, n_obj), rs.rand(n_frames, n_obj) < 0.85
+        state = lambda r, o, s: (o, s, r.n_keyframes, r.kf_pointer, r.kf_buffer_full, r.frame_cnt, list(r.latest), list(r.slot_of.items()))   # noqa: E731
+        random.seed(seed)
+        rings, ref = {}, []
+        for f in range(n_frames):
+            for o in range(n_obj):
+                if f < first[o] or not present[f, o]:
+                    continue
+                if o not in rings:
+                    rings[o], s = KeyframeRing(f * 10, K, steps[o]), 0
+                else:
+                    s = rings[o].push(f * 10)
+                ref.append(state(rings[o], o, s))
+        random.seed(seed)
+        bank, have, out = RingBank(n_obj, K), {}, []
+        for f in range(n_frames):
+            vis = [o for o in range(n_obj) if f >= first[o] and present[f, o]]
+            old = [o for o in vis if o in have]
+            slots = dict(zip(old, bank.push_many(np.array(old), f * 10).tolist())) if old else {}
+            for o in vis:
+                if o not in have:
+                    have[o], slots[o] = bank.add(o, f * 10, steps[o]), 0
+            out += [state(have[o], o, slots[o]) for o in vis]
+        assert ref == out, (seed, K)
