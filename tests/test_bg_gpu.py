@@ -148,3 +148,42 @@ def test_scene_with_background_model():
     p0 = next(sc.scene_bg.trainer.fc_occ_map.parameters())
     assert p0.data_ptr() == sc.bg.views()[0].data_ptr()
     assert last < first, (first, last)
+
+
+@pytest.mark.parametrize("hidden,R,S,part", [(64, 37, 14, True), (256, 53, 14, True), (32, 41, 10, False), (128, 129, 6, True)])
+def test_bg_other_widths_and_ragged_sizes_against_oracle(hidden, R, S, part):
+    """The layer-by-layer path is generic in the hidden width (model.OccupancyMap routes every width but 32 to it; the
+    reference's default is 256) and in the point count: ragged sizes put partial 128-row tiles, column tails (87 / h + 87 / h +
+    42 wide weights), split contractions that end inside a 16-wide chunk and both GEMM engines (tcgen05 where the operand
+    layouts allow, mma.sync for the 1- and 3-wide ones) on the path.  Loss and all 19 gradients against the float64 oracle."""
+    g = torch.Generator().manual_seed(100 + hidden + R)
+    fc, B = oc.init_params(1, hidden=hidden, generator=g)
+    fc[8] *= 0.3
+    fc[9] *= 0.3
+    z = torch.sort(0.5 + 5.0 * torch.rand(R, S, generator=g), dim=-1).values
+    d = torch.nn.functional.normalize(torch.randn(R, 1, 3, generator=g), dim=-1)
+    pcs = (torch.randn(R, 1, 3, generator=g) * 0.3 + d * z[..., None]).float()
+    gt_depth = z[:, S // 2].clone()
+    rgb8 = torch.randint(0, 256, (R, 3), generator=g, dtype=torch.uint8)
+    labels = torch.randint(0, 3, (R,), generator=g, dtype=torch.uint8)
+    labels[0], labels[1] = 1, 0
+    table = torch.randn(64, 512, generator=g) if part else None
+    rows = torch.randint(0, 64, (R,), generator=g, dtype=torch.int32) if part else None
+    from openobj_b200.background import BackgroundModel
+    model = BackgroundModel(hidden=hidden, device=DEV, rays_per_step=R, n_samp=S)
+    model.load([p[0] for p in fc] + [B[0]])
+    gr, loss, terms = model.grads(pcs.to(DEV), z.to(DEV), gt_depth.to(DEV), rgb8.to(DEV), labels.to(DEV),
+                                  rows.to(DEV) if part else None, table.to(DEV) if part else None)
+    f64 = [p.double() for p in fc]
+    feat = table[rows.long()][None].double() if part else None
+    t64, g64 = oc.train_step_grads(f64, B.double(), pcs[None].double(), z[None].double(), gt_depth[None].double(),
+                                   (rgb8 / 255.)[None].double(), labels[None], feat, scale=5.0)
+    ref = float(t64.total)
+    assert abs(float(loss) - ref) <= 1e-4 * abs(ref) + 1e-6, (float(loss), ref)
+    for i, v in enumerate(model.views(gr)):
+        if g64[i] is None:
+            assert float(v.abs().max()) == 0.0, i            # part features off: the clip head gets no gradient
+            continue
+        r = g64[i][0].float()
+        err, sc = float((v.cpu() - r).abs().max()), float(r.abs().max()) + 1e-12
+        assert err <= 1e-4 * sc + 1e-7, (hidden, i, err, sc)
