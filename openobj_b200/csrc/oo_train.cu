@@ -212,28 +212,34 @@ __global__ void __launch_bounds__(NTHREADS, 1) k_train(const TrainParams prm) {
 }
 
 // ---- per-frame: ray counts per (step, object) and the cross-object zero-mask flags (render_rays.py:88-94)
-__global__ void k_label_counts(const uint8_t* __restrict__ labels, int n_obj, int rays_per_obj, int R,
-                               int* __restrict__ counts, int* __restrict__ flags, int* __restrict__ flag_bits) {
-    const int it = blockIdx.x;
+__global__ void __launch_bounds__(256) k_label_counts(const uint8_t* __restrict__ labels, int n_obj, int rays_per_obj, int R,
+                                                      int* __restrict__ counts, int* __restrict__ flags, int* __restrict__ flag_bits) {
+    // one block per step; a warp takes objects w, w + 8, ... and counts its R labels with ballots (no block barrier per object:
+    // the first version walked the objects one after the other with two __syncthreads_count each, 38 us per frame at N = 60)
+    __shared__ int s_f[8];
+    const int it = blockIdx.x, lane = threadIdx.x & 31, wv = threadIdx.x >> 5;
     int f = 0;
-    for (int o = 0; o < n_obj; ++o) {
+    for (int o = wv; o < n_obj; o += 8) {
+        const uint8_t* lab = labels + (size_t)o * rays_per_obj + (size_t)it * R;
         int n1 = 0, ns = 0;
-        for (int r0 = 0; r0 < R; r0 += blockDim.x) {
-            const int r = r0 + threadIdx.x;
-            int lab = 2;
-            bool in = r < R;
-            if (in) lab = labels[(size_t)o * rays_per_obj + (size_t)it * R + r];
-            n1 += __syncthreads_count(in && lab == 1);
-            ns += __syncthreads_count(in && lab != 2);
+        for (int r0 = 0; r0 < R; r0 += 32) {
+            const int r = r0 + lane;
+            const int l = r < R ? lab[r] : 2;
+            n1 += __popc(__ballot_sync(0xffffffffu, r < R && l == 1));
+            ns += __popc(__ballot_sync(0xffffffffu, r < R && l != 2));
         }
-        if (threadIdx.x == 0) {
+        if (lane == 0) {
             counts[((size_t)it * n_obj + o) * 2 + 0] = n1;
             counts[((size_t)it * n_obj + o) * 2 + 1] = ns;
         }
         if (n1 == 0) f |= OO_FLAG_NO_OBJ;
         if (ns == 0) f |= OO_FLAG_NO_SEM;
     }
+    if (lane == 0) s_f[wv] = f;
+    __syncthreads();
     if (threadIdx.x == 0) {
+        f = 0;
+        for (int w = 0; w < 8; ++w) f |= s_f[w];
         flags[it] = f;
         if (flag_bits != nullptr) {           // one int per bit: a MAX all-reduce over ranks is then the OR the rule needs
             flag_bits[2 * it] = (f & OO_FLAG_NO_OBJ) ? 1 : 0;
@@ -920,7 +926,7 @@ extern "C" int oo_label_counts(const uint8_t* labels, int n_obj, int rays_per_ob
     OO_REQUIRE(counts && flags && iters > 0 && n_obj >= 0, "oo_label_counts: null argument");
     OO_REQUIRE(n_obj == 0 || labels, "oo_label_counts: null labels");
     OO_REQUIRE(n_obj == 0 || (long long)iters * rays_per_step <= rays_per_obj, "oo_label_counts: iters*rays_per_step > rays_per_obj");
-    k_label_counts<<<iters, 128, 0, (cudaStream_t)stream>>>(labels, n_obj, rays_per_obj, rays_per_step, counts, flags, flag_bits);
+    k_label_counts<<<iters, 256, 0, (cudaStream_t)stream>>>(labels, n_obj, rays_per_obj, rays_per_step, counts, flags, flag_bits);
     OO_LAUNCH_CHECK();
     return 0;
 }
