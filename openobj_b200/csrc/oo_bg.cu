@@ -1,9 +1,12 @@
 // a17: the background model (objnerf/train.py:300-315,379-388,447-463; vmap.py:43-47): ONE OccupancyMap of hidden
 // width 128 + UniDirsEmbed(scale 5) trained on 1200 rays x 14 samples per step beside the object ensemble.
-// M = 16 800 points with K <= 215 are ordinary GEMMs, so this path is layer by layer: an FP32 shared-memory-tiled
-// GEMM with fused bias / activation / ReLU-mask epilogues (forward, backward-data, split-M backward-weight with a
-// fixed-order reduction), the encoder forward / backward, and the standalone compositing + loss kernels (K3,
-// oo_composite.cu) in between.  Hidden width is a run-time argument (any multiple of 4).
+// M = 16 800 points with K <= 215 are ordinary GEMMs, so this path is layer by layer: a generic GEMM descriptor (oo_gemm.h)
+// with fused bias / activation / ReLU-mask epilogues (forward, backward-data, split-contraction backward-weight with a
+// fixed-order reduction) on one of two engines -- k_gemm_tc (oo_gemm_tc.cu: tcgen05.mma kind::tf32 x3, accumulators in tensor
+// memory; the default wherever the operand layouts can be staged) or k_gemm below (mma.sync 3xTF32; the 1- and 3-wide
+// operands of the alpha / colour outputs, and everything with OO_BG_GEMM=mma) -- the encoder forward / backward, and the
+// standalone compositing + loss kernels (K3, oo_composite.cu) in between.  Hidden width is a run-time argument (any multiple
+// of 4; tests run 32, 64, 128, 256).
 #include "../../include/openobj_b200.h"
 #include "oo_common.cuh"
 #include "oo_gemm.h"
@@ -14,6 +17,21 @@
 
 
 using namespace oo;
+
+namespace oo {
+// oo_bg_clip.cu: the part-feature term of the background step without [points x 512] tensors
+int bg_clip_render(const float* alpha, const float* hp, int n_rays, int S, int h, int hs, float* Sx, cudaStream_t st);
+int bg_clip_loss(const float* X, const float* gt_feat, const uint8_t* labels, const int* flags, const float* tail, int n_rays, int C,
+                 float fs, float* d_x, float* lf, float* terms, float* loss, cudaStream_t st);
+int bg_clip_bwd(const float* alpha, const float* hp, const float* dSx, int n_rays, int S, int h, int hs, float* hu, float* d_hp,
+                cudaStream_t st);
+int bg_clip_scatter(const float* dWb, int C, int h, int hs, float* gW, float* gb, cudaStream_t st);
+// oo_composite.cu: oo_loss_bwd with an extra per-sample dL/dT input
+int loss_bwd_hu(const float* alpha, const float* color, const float* z, const float* gt_depth, const float* gt_color,
+                const uint8_t* labels, const float* pred_feat, const float* gt_feat, int n_obj, int n_rays, int n_samp, int n_feat,
+                float cs, float os, float fs, float grad_loss, const int* flags, const float* ray_ws, float* d_alpha, float* d_color,
+                float* d_pred_feat, const float* hu_extra, void* stream);
+}  // namespace oo
 
 namespace {
 
@@ -543,6 +561,9 @@ struct BgWs {
     float *d_alpha, *d_color, *d_colpre, *d_clip, *d_hc, *d_hp, *d_xh, *d_h3, *d_xc, *d_h1, *d_x1;
     float *gt_rgb, *gt_feat, *loss_ws, *ones, *adam_scal, *part[9], *emb_part, *grads;   // part[i]: split partials of weight gradient i
     float *wp_in, *wp_cat, *wp_cl, *wp_cp;   // in_layer / cat_layer / color_linear / clip_linear weights with rows padded to ld1 / ldc / ldh
+    // factored clip head (oo_bg_clip.cu): [W_ocl | b_ocl | 0] rows of hs = h + 4, per-ray tensors, split partials
+    float *wb_ocl, *Sx, *X, *d_x, *dSx, *hu, *lf, *dWb, *part_ds, *part_wb;
+    int hs;
     int ld1, ldc, ldh;
     long long total;
 };
@@ -572,6 +593,10 @@ BgWs bg_ws_map(float* base, int h, int n_pts, int n_rays) {
     w.grads = take(bg_layout(h).total);
     w.wp_in = take((long long)h * w.ld1); w.wp_cat = take((long long)h * w.ldc);
     w.wp_cl = take((long long)h * w.ldh); w.wp_cp = take((long long)h * w.ldh);
+    w.hs = h + 4;
+    w.wb_ocl = take((long long)C * w.hs); w.Sx = take((long long)n_rays * w.hs); w.X = take((long long)n_rays * C);
+    w.d_x = take((long long)n_rays * C); w.dSx = take((long long)n_rays * w.hs); w.hu = take(M); w.lf = take(n_rays);
+    w.dWb = take((long long)C * w.hs); w.part_ds = take(part_floats(n_rays, w.hs)); w.part_wb = take(part_floats(C, w.hs));
     w.total = o;
     return w;
 }
@@ -580,8 +605,16 @@ BgWs bg_ws_map(float* base, int h, int n_pts, int n_rays) {
 // 16-byte aligned copy per step: the tcgen05 engine stages aligned rows with 16-byte asynchronous copies (forward: weights are
 // the contraction-contiguous B operand) and 128-bit loads (backward-data: row-contiguous B operand).
 __global__ void k_pack_weights(const float* __restrict__ th, int h, int o_in, int o_cat, int o_cl, int o_cp, float* __restrict__ p_in,
-                               float* __restrict__ p_cat, float* __restrict__ p_cl, float* __restrict__ p_cp, int ld1, int ldc, int ldh) {
+                               float* __restrict__ p_cat, float* __restrict__ p_cl, float* __restrict__ p_cp, int ld1, int ldc, int ldh,
+                               int o_ocl_w, int o_ocl_b, float* __restrict__ p_wb, int hs) {
     const int which = blockIdx.y;
+    if (which == 4) {                     // [W_ocl | b_ocl | 0 0 0]: the factored clip head's one operand (oo_bg_clip.cu)
+        for (int e = blockIdx.x * blockDim.x + threadIdx.x; e < C * hs; e += gridDim.x * blockDim.x) {
+            const int r = e / hs, c = e - r * hs;
+            p_wb[e] = c < h ? th[o_ocl_w + r * h + c] : c == h ? th[o_ocl_b + r] : 0.f;
+        }
+        return;
+    }
     const float* src = th + (which == 0 ? o_in : which == 1 ? o_cat : which == 2 ? o_cl : o_cp);
     float* dst = which == 0 ? p_in : which == 1 ? p_cat : which == 2 ? p_cl : p_cp;
     const int cols = which == 0 ? E1 : which == 1 ? h + E1 : h + E2, ld = which == 0 ? ld1 : which == 1 ? ldc : ldh;
@@ -612,8 +645,8 @@ int bg_forward(const float* th, const BgLayout& L, int h, const float* pcs, int 
     if (emb_in != nullptr) k_embed_scatter<<<(unsigned)(((size_t)M * EMB + 255) / 256), 256, 0, st>>>(emb_in, M, eb);
     else k_embed_fwd<<<(unsigned)(((size_t)M * 24 + 255) / 256), 256, 0, st>>>(pcs, th + L.off[T_PE], scale, M, eb, emb_out);
     OO_LAUNCH_CHECK();
-    k_pack_weights<<<dim3(16, 4), 256, 0, st>>>(th, h, L.off[T_IN_W], L.off[T_CAT_W], L.off[T_CL_W], L.off[T_CP_W], w.wp_in, w.wp_cat,
-                                               w.wp_cl, w.wp_cp, w.ld1, w.ldc, w.ldh);
+    k_pack_weights<<<dim3(16, 5), 256, 0, st>>>(th, h, L.off[T_IN_W], L.off[T_CAT_W], L.off[T_CL_W], L.off[T_CP_W], w.wp_in, w.wp_cat,
+                                               w.wp_cl, w.wp_cp, w.ld1, w.ldc, w.ldh, L.off[T_OCL_W], L.off[T_OCL_B], w.wb_ocl, w.hs);
     OO_LAUNCH_CHECK();
     GemmOp g;
     // fc1 = relu(in_layer(e1))
@@ -650,14 +683,21 @@ int bg_forward(const float* th, const BgLayout& L, int h, const float* pcs, int 
 // backward of the whole model given dL/d(alpha, colour, clip) in w.d_alpha / w.d_color / w.d_clip and the forward activations
 // of bg_forward in `w`: all 19 gradients into G (flat parameter layout)
 int bg_backward(const float* theta, const BgLayout& L, int h, const float* pcs, int M, float scale, const BgWs& w, bool part,
-                float* G, cudaStream_t st, float* d_emb_out = nullptr) {
+                float* G, cudaStream_t st, float* d_emb_out = nullptr, int factored_rays = 0) {
     const float* th = theta;
     GemmOp g;
     ReduceBatch pending;                         // split partials of the weight gradients, reduced together before AdamW
     pending.n = 0;
     OO_CUDA(cudaMemsetAsync(G, 0, sizeof(float) * L.total, st));
     // ---- clip head
-    if (part) {
+    if (part && factored_rays > 0) {
+        // factored clip head (oo_bg_clip.cu): d hp is already in w.d_hp; [dW | db | 0] = d_x^T [S | opac | 0] over the RAYS
+        g = op(w.d_x, 1, C, w.Sx, 1, w.hs, w.dWb, w.hs, 1, C, w.hs, factored_rays);
+        OO_TRY(run_gemm(g, BG_SPLIT, w.part_wb, st, &pending));
+        g = op(w.d_hp, 1, h, w.xh, 1, w.ldh, G + L.off[T_CP_W], h + E2, 1, h, h + E2, M);
+        g.ones_out = G + L.off[T_CP_B];
+        OO_TRY(run_gemm(g, BG_SPLIT, w.part[1], st, &pending));
+    } else if (part) {
         // d out_clip.weight [C][h] = d_clip^T hp ; bias = column sums ; d hp = (d_clip W_ocl) * [hp > 0]
         g = op(w.d_clip, 1, C, w.hp, 1, h, G + L.off[T_OCL_W], h, 1, C, h, M);
         g.ones_out = G + L.off[T_OCL_B];
@@ -742,6 +782,8 @@ int bg_backward(const float* theta, const BgLayout& L, int h, const float* pcs, 
         OO_LAUNCH_CHECK();
     }
     OO_TRY(run_reduce_batch(pending, st));
+    if (part && factored_rays > 0)
+        OO_TRY(bg_clip_scatter(w.dWb, C, h, w.hs, G + L.off[T_OCL_W], G + L.off[T_OCL_B], st));
     return 0;
 }
 
@@ -847,7 +889,27 @@ extern "C" int oo_bg_train_step(float* theta, float* adam_m, float* adam_v, int 
     OO_LAUNCH_CHECK();
     k_gt_prepare<<<n_rays, 128, 0, st>>>(gt_rgb, feat_row, feat_table, n_rays, w.gt_rgb, w.gt_feat);
     OO_LAUNCH_CHECK();
-    OO_TRY(bg_forward(theta, L, h, pcs, M, scale, w, part, nullptr, st));
+    // part features: the clip head is applied per RAY to S_r = sum_i T_i hp_i (oo_bg_clip.cu) unless OO_BG_CLIP=dense asks for
+    // the [points x 512] formulation (kept for A/B runs and for hidden widths the factored kernels do not cover)
+    static const bool dense_env = []() { const char* e = getenv("OO_BG_CLIP"); return e != nullptr && strcmp(e, "dense") == 0; }();
+    const bool factored = part && !dense_env && h <= 256;
+    OO_TRY(bg_forward(theta, L, h, pcs, M, scale, w, part && !factored, nullptr, st));
+    if (factored) {
+        OO_TRY(bg_clip_render(w.alpha, w.hp, n_rays, n_samp, h, w.hs, w.Sx, st));
+        GemmOp g = op(w.Sx, w.hs, 1, w.wb_ocl, w.hs, 1, w.X, C, 1, n_rays, C, w.hs);          // x_r = W S_r + b opac_r
+        OO_TRY(run_gemm(g, 1, nullptr, st));
+        // ---- depth / colour / opacity terms of loss.step_batch_loss on [1, R, S] (K3 without features), then the feature term
+        OO_TRY(oo_loss_fwd(w.alpha, w.color, z, gt_depth, w.gt_rgb, labels, nullptr, nullptr, 1, n_rays, n_samp, 0, color_scaling,
+                           opacity_scaling, feat_scaling, terms_out, loss_out, flags_out, w.loss_ws, stream));
+        const float* tail = w.loss_ws + (size_t)n_rays * oo_loss_ws_per_ray();
+        OO_TRY(bg_clip_loss(w.X, w.gt_feat, labels, flags_out, tail, n_rays, C, feat_scaling, w.d_x, w.lf, terms_out, loss_out, st));
+        g = op(w.d_x, C, 1, w.wb_ocl, 1, w.hs, w.dSx, w.hs, 1, n_rays, w.hs, C);               // [dS | d opac] = d_x [W | b]
+        OO_TRY(run_gemm(g, BG_SPLIT, w.part_ds, st));
+        OO_TRY(bg_clip_bwd(w.alpha, w.hp, w.dSx, n_rays, n_samp, h, w.hs, w.hu, w.d_hp, st));
+        OO_TRY(loss_bwd_hu(w.alpha, w.color, z, gt_depth, w.gt_rgb, labels, nullptr, nullptr, 1, n_rays, n_samp, 0, color_scaling,
+                           opacity_scaling, feat_scaling, 1.f, flags_out, w.loss_ws, w.d_alpha, w.d_color, nullptr, w.hu, stream));
+        OO_TRY(bg_backward(theta, L, h, pcs, M, scale, w, part, G, st, nullptr, n_rays));
+    } else {
     // ---- loss.step_batch_loss on [1, R, S] (train.py:452-462) and its gradient w.r.t. alpha / colour / clip (K3)
     OO_TRY(oo_loss_fwd(w.alpha, w.color, z, gt_depth, w.gt_rgb, labels, part ? w.clip : nullptr, part ? w.gt_feat : nullptr, 1,
                        n_rays, n_samp, part ? C : 0, color_scaling, opacity_scaling, feat_scaling, terms_out, loss_out,
@@ -856,6 +918,7 @@ extern "C" int oo_bg_train_step(float* theta, float* adam_m, float* adam_v, int 
                        n_rays, n_samp, part ? C : 0, color_scaling, opacity_scaling, feat_scaling, 1.f, flags_out, w.loss_ws,
                        w.d_alpha, w.d_color, part ? w.d_clip : nullptr, stream));
     OO_TRY(bg_backward(theta, L, h, pcs, M, scale, w, part, G, st));
+    }
     if (grads_out) return 0;
     // ---- torch.optim.AdamW over the flat block, per parameter group: a group autograd does not reach in this step (part
     // features off: the clip head, quirk 8; an empty label mask: see k_bg_adam_sched) is skipped entirely

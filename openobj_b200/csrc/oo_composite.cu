@@ -251,7 +251,8 @@ template <int SMAX>
 __global__ void __launch_bounds__(256, 4) k_loss_ray_bwd(RayIn in, const float* __restrict__ ws, const float* __restrict__ tail,
                                                       const int* __restrict__ flags, int n_rays, float cs, float os,
                                                       float fs, float gl, float* __restrict__ d_alpha,
-                                                      float* __restrict__ d_color, float* __restrict__ d_pred) {
+                                                      float* __restrict__ d_color, float* __restrict__ d_pred,
+                                                      const float* __restrict__ hu_extra) {
     const int lane = threadIdx.x & 31;
     for (int ray = blockIdx.x * (blockDim.x >> 5) + (threadIdx.x >> 5); ray < in.n_rays_total; ray += gridDim.x * (blockDim.x >> 5)) {
     const int S = in.S, obj = ray / n_rays;
@@ -309,6 +310,8 @@ __global__ void __launch_bounds__(256, 4) k_loss_ray_bwd(RayIn in, const float* 
             }
         }
     }
+    // hu_extra: dL/dT contributions formed outside (the background's factored clip head, oo_bg_clip.cu)
+    if (hu_extra != nullptr && act) hu += hu_extra[pi];
     const float g = zv * gd + go + c0 * gc0 + c1 * gc1 + c2 * gc2 + hu;    // dL/dT_lane
     const float suffix = warp_excl_suffix_sum(act ? g * T : 0.f, lane);
     if (act) {
@@ -377,11 +380,13 @@ extern "C" int oo_loss_fwd(const float* alpha, const float* color, const float* 
     return 0;
 }
 
-extern "C" int oo_loss_bwd(const float* alpha, const float* color, const float* z, const float* gt_depth,
+// oo_loss_bwd with an extra per-sample dL/dT input (nullptr = none); internal: the C ABI entry below passes nullptr
+namespace oo {
+int loss_bwd_hu(const float* alpha, const float* color, const float* z, const float* gt_depth,
                            const float* gt_color, const uint8_t* labels, const float* pred_feat, const float* gt_feat,
                            int n_obj, int n_rays, int n_samp, int n_feat, float cs, float os, float fs, float grad_loss,
                            const int* flags, const float* ray_ws, float* d_alpha, float* d_color, float* d_pred_feat,
-                           void* stream) {
+                           const float* hu_extra, void* stream) {
     if (int rc = check_loss_args(alpha, color, z, gt_depth, gt_color, labels, pred_feat, gt_feat, n_obj, n_rays, n_samp,
                                  n_feat))
         return rc;
@@ -393,13 +398,23 @@ extern "C" int oo_loss_bwd(const float* alpha, const float* color, const float* 
     const int blocks = (in.n_rays_total + 7) / 8;
     if (n_samp <= 10)
         k_loss_ray_bwd<10><<<wave_blocks(k_loss_ray_bwd<10>, blocks), 256, 0, st>>>(in, ray_ws, tail, flags, n_rays, cs, os, fs, grad_loss, d_alpha, d_color,
-                                                   d_pred_feat);
+                                                   d_pred_feat, hu_extra);
     else if (n_samp <= 16)
         k_loss_ray_bwd<16><<<wave_blocks(k_loss_ray_bwd<16>, blocks), 256, 0, st>>>(in, ray_ws, tail, flags, n_rays, cs, os, fs, grad_loss, d_alpha, d_color,
-                                                   d_pred_feat);
+                                                   d_pred_feat, hu_extra);
     else
         k_loss_ray_bwd<32><<<wave_blocks(k_loss_ray_bwd<32>, blocks), 256, 0, st>>>(in, ray_ws, tail, flags, n_rays, cs, os, fs, grad_loss, d_alpha, d_color,
-                                                   d_pred_feat);
+                                                   d_pred_feat, hu_extra);
     OO_LAUNCH_CHECK();
     return 0;
+}
+}  // namespace oo
+
+extern "C" int oo_loss_bwd(const float* alpha, const float* color, const float* z, const float* gt_depth,
+                           const float* gt_color, const uint8_t* labels, const float* pred_feat, const float* gt_feat,
+                           int n_obj, int n_rays, int n_samp, int n_feat, float cs, float os, float fs, float grad_loss,
+                           const int* flags, const float* ray_ws, float* d_alpha, float* d_color, float* d_pred_feat,
+                           void* stream) {
+    return oo::loss_bwd_hu(alpha, color, z, gt_depth, gt_color, labels, pred_feat, gt_feat, n_obj, n_rays, n_samp, n_feat, cs, os, fs,
+                           grad_loss, flags, ray_ws, d_alpha, d_color, d_pred_feat, nullptr, stream);
 }
