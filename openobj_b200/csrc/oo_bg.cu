@@ -365,8 +365,14 @@ int run_gemm(GemmOp g, int split, float* part, cudaStream_t st, ReduceBatch* def
     OO_REQUIRE((long long)g.I * (g.sci > 0 ? g.sci : 1) + (long long)je * (g.scj > 0 ? g.scj : 1) < (1LL << 31) &&
                    (g.mask == nullptr || (long long)g.I * (g.smi > 0 ? g.smi : 1) + (long long)je * (g.smj > 0 ? g.smj : 1) < (1LL << 31)),
                "oo_bg gemm: output / mask larger than 2^31 elements");
+    const bool split_path = g.split > 1;          // partials in `part`: a reduction launch must follow, however few they are
     if (use_tc) {
-        if (int rc = run_gemm_tc(g, st)) return rc;
+        // split CTAs of one output tile form clusters of TG_CLUSTER and reduce through distributed shared memory first
+        static const int cl_env = []() { const char* e = getenv("OO_GEMM_TC_CLUSTER"); return e ? atoi(e) : TG_CLUSTER; }();
+        const int cl = g.split > 1 && cl_env > 1 ? cl_env : 1;
+        g.split = (g.split + cl - 1) / cl * cl;              // padding CTAs have an empty contraction range: zero tiles
+        if (int rc = run_gemm_tc(g, st, cl)) return rc;
+        g.split /= cl;                                       // partials the reduction will read
     } else {
     const dim3 grid((g.I + BI - 1) / BI, (g.J + BJ - 1) / BJ, g.split);
     const bool ac = g.sac == 1, bc = g.sbc == 1;
@@ -384,7 +390,7 @@ int run_gemm(GemmOp g, int split, float* part, cudaStream_t st, ReduceBatch* def
     else OO_CUDA(launch_pdl(k_gemm<false, false>, grid, dim3(256), (size_t)GEMM_SMEM, st, g));
     OO_LAUNCH_CHECK();
     }
-    if (g.split > 1) {
+    if (split_path) {
         if (defer != nullptr) {
             OO_REQUIRE(defer->n < REDUCE_BATCH_MAX, "oo_bg gemm: too many deferred reductions");
             defer->op[defer->n++] = g;

@@ -27,8 +27,11 @@ struct GemmOp {
 
 constexpr int TG_BI = 128, TG_BJ = 256, TG_KC = 16;      // tcgen05 engine: CTA tile 128 x (<= 256), k-chunks of 16
 
-// launches k_gemm_tc for `g` (split / chunk / part already chosen by the caller; chunk % TG_KC == 0)
-int run_gemm_tc(const GemmOp& g, cudaStream_t st);
+// launches k_gemm_tc for `g` (split / chunk / part already chosen by the caller; chunk % TG_KC == 0).  cluster_z > 1: the
+// split CTAs run as thread-block clusters of that size and add their tiles through distributed shared memory before writing:
+// part then holds g.split / cluster_z partials (g.split must be a multiple of cluster_z).
+int run_gemm_tc(const GemmOp& g, cudaStream_t st, int cluster_z = 1);
+constexpr int TG_CLUSTER = 4;
 // can the tcgen05 engine stage both operands of `g` (alignment / stride rules in oo_gemm_tc.cu)?
 bool gemm_tc_supported(const GemmOp& g);
 

@@ -208,7 +208,7 @@ __device__ __noinline__ void ep2_vec(const GemmOp& g, const float* __restrict__ 
 }
 
 template <bool AV, bool BV>
-__global__ void __launch_bounds__(TG_BLOCK, 1) k_gemm_tc(const GemmOp g, int tm_cols, int dbg) {
+__global__ void __launch_bounds__(TG_BLOCK, 1) k_gemm_tc(const GemmOp g, int tm_cols, int cl, int dbg) {
     extern __shared__ __align__(128) float sm[];
     __shared__ uint32_t tm_base_s;
     __shared__ __align__(8) uint64_t bars[2 * TG_STAGES];             // full[s] (producers -> MMA warp), empty[s] (MMAs done)
@@ -425,7 +425,7 @@ __global__ void __launch_bounds__(TG_BLOCK, 1) k_gemm_tc(const GemmOp g, int tm_
         __syncthreads();
         if (tid < TG_BI && i0 + tid < g.I) {
             const int i = i0 + tid;
-            if (g.split > 1) g.part[((size_t)blockIdx.z * g.I + i) * je + g.J] = rs_sm[tid];
+            if (g.split > 1) { if (cl <= 1) g.part[((size_t)blockIdx.z * g.I + i) * je + g.J] = rs_sm[tid]; }
             else g.ones_out[i] = epilogue1(g, rs_sm[tid], 0.f, 1.f, g.accumulate ? g.ones_out[i] : 0.f);
         }
     }
@@ -457,6 +457,59 @@ __global__ void __launch_bounds__(TG_BLOCK, 1) k_gemm_tc(const GemmOp g, int tm_
     __syncthreads();
     if (warp == 0)
         asm volatile("tcgen05.dealloc.cta_group::1.sync.aligned.b32 %0, %1;" ::"r"(tm), "r"((uint32_t)tm_cols) : "memory");
+
+    // ---- split partials, cluster form: the `cl` CTAs of a thread-block cluster hold consecutive contraction chunks of the SAME
+    // output tile; they add their tiles through distributed shared memory in a fixed order (rank 0, 1, ..) before anything goes
+    // to global memory -- CTA rank q sums rows [128 q / cl, 128 (q + 1) / cl) -- so the fixed-order reduction launch that
+    // follows reads cl x fewer partials (132 -> 33 per weight gradient)
+    if (g.split > 1 && cl > 1) {
+        uint32_t rank;
+        asm volatile("mov.u32 %0, %%cluster_ctarank;" : "=r"(rank));
+        asm volatile("barrier.cluster.arrive.release.aligned;\n\tbarrier.cluster.wait.acquire.aligned;" ::: "memory");
+        const int rows_per = TG_BI / cl, r_lo = (int)rank * rows_per;
+        const int n_cols_c = min(nj, g.J - j0);
+        const uint32_t t_base = sm_base, rs_base = (uint32_t)__cvta_generic_to_shared(&rs_sm[0]);
+        const size_t zc = blockIdx.z / cl;
+        // items = (row, 4-column group): the cl remote 128-bit loads of an item are issued together, summed in rank order
+        const int nq4 = (n_cols_c + 3) >> 2, n_items = rows_per * nq4;
+        for (int e = tid; e < n_items; e += TG_BLOCK) {
+            const int r = r_lo + e / nq4, c = 4 * (e % nq4);
+            if (i0 + r >= g.I) continue;
+            float4 x[8];
+#pragma unroll
+            for (int q = 0; q < 8; ++q) {
+                if (q < cl) {
+                    uint32_t ra;
+                    asm("mapa.shared::cluster.u32 %0, %1, %2;" : "=r"(ra) : "r"(t_base + (uint32_t)(r * ldt + c) * 4u), "r"(q));
+                    asm volatile("ld.shared::cluster.v4.f32 {%0,%1,%2,%3}, [%4];" : "=f"(x[q].x), "=f"(x[q].y), "=f"(x[q].z), "=f"(x[q].w) : "r"(ra));
+                }
+            }
+            float4 v = x[0];
+#pragma unroll
+            for (int q = 1; q < 8; ++q)
+                if (q < cl) { v.x += x[q].x; v.y += x[q].y; v.z += x[q].z; v.w += x[q].w; }
+            float* dst = g.part + (zc * g.I + i0 + r) * je + j0 + c;
+            dst[0] = v.x;
+            if (c + 1 < n_cols_c) dst[1] = v.y;
+            if (c + 2 < n_cols_c) dst[2] = v.z;
+            if (c + 3 < n_cols_c) dst[3] = v.w;
+        }
+        if (row_sums && tid < rows_per && i0 + r_lo + tid < g.I) {
+            const int r = r_lo + tid;
+            float v = 0.f;
+            for (int q = 0; q < cl; ++q) {
+                uint32_t ra;
+                float x;
+                asm("mapa.shared::cluster.u32 %0, %1, %2;" : "=r"(ra) : "r"(rs_base + (uint32_t)r * 4u), "r"(q));
+                asm volatile("ld.shared::cluster.f32 %0, [%1];" : "=f"(x) : "r"(ra));
+                v += x;
+            }
+            g.part[(zc * g.I + i0 + r) * je + g.J] = v;
+        }
+        // nobody leaves while its tile may still be read by the others
+        asm volatile("barrier.cluster.arrive.release.aligned;\n\tbarrier.cluster.wait.acquire.aligned;" ::: "memory");
+        return;
+    }
 
     // ---- epilogue, part 2: a warp per row, lanes along the columns (contiguous in C when scj == 1)
     if (warp >= TG_THREADS / 32) return;
@@ -497,13 +550,18 @@ __global__ void __launch_bounds__(TG_BLOCK, 1) k_gemm_tc(const GemmOp g, int tm_
 }
 
 template <typename... KArgs, typename... Args>
-cudaError_t launch_pdl(void (*kernel)(KArgs...), dim3 grid, dim3 block, size_t smem, cudaStream_t st, Args... args) {
+cudaError_t launch_pdl(void (*kernel)(KArgs...), dim3 grid, dim3 block, size_t smem, cudaStream_t st, int cluster_z, Args... args) {
     cudaLaunchConfig_t cfg = {};
     cfg.gridDim = grid; cfg.blockDim = block; cfg.dynamicSmemBytes = smem; cfg.stream = st;
-    cudaLaunchAttribute at[1];
+    cudaLaunchAttribute at[2];
     at[0].id = cudaLaunchAttributeProgrammaticStreamSerialization;
     at[0].val.programmaticStreamSerializationAllowed = 1;
     cfg.attrs = at; cfg.numAttrs = 1;
+    if (cluster_z > 1) {                        // thread-block cluster along the split dimension (distributed shared memory)
+        at[1].id = cudaLaunchAttributeClusterDimension;
+        at[1].val.clusterDim.x = 1; at[1].val.clusterDim.y = 1; at[1].val.clusterDim.z = (unsigned)cluster_z;
+        cfg.numAttrs = 2;
+    }
     return cudaLaunchKernelEx(&cfg, kernel, KArgs(args)...);
 }
 
@@ -522,7 +580,7 @@ bool gemm_tc_supported(const GemmOp& g) {
     return (op_v(g.A, g.sai, g.sac) || op_r(g.A, g.sai, g.sac, g.I)) && (op_v(g.B, g.sbj, g.sbc) || op_r(g.B, g.sbj, g.sbc, g.J));
 }
 
-int run_gemm_tc(const GemmOp& g, cudaStream_t st) {
+int run_gemm_tc(const GemmOp& g, cudaStream_t st, int cluster_z) {
     OO_REQUIRE(g.chunk > 0 && g.chunk % TG_KC == 0, "oo_bg gemm (tcgen05): chunk must be a multiple of %d", TG_KC);
     OO_REQUIRE(gemm_tc_supported(g), "oo_bg gemm (tcgen05): operand layout not supported");
     const int nj_max = g.J >= TG_BJ ? TG_BJ : (g.J + 15) & ~15;
@@ -546,12 +604,13 @@ int run_gemm_tc(const GemmOp& g, cudaStream_t st) {
         attr_set.cur() = 1;
     }
     static const int dbg = []() { const char* e = getenv("OO_GEMM_TC_DEBUG"); return e ? atoi(e) : 0; }();   // profiling experiments
+    OO_REQUIRE(cluster_z >= 1 && cluster_z <= 8 && g.split % cluster_z == 0 && TG_BI % cluster_z == 0, "oo_bg gemm (tcgen05): split %d is not a multiple of the cluster size %d", g.split, cluster_z);
     const dim3 grid((g.I + TG_BI - 1) / TG_BI, (g.J + TG_BJ - 1) / TG_BJ, g.split);
     const bool av = op_v(g.A, g.sai, g.sac), bv = op_v(g.B, g.sbj, g.sbc);
-    if (av && bv) OO_CUDA(launch_pdl(k_gemm_tc<true, true>, grid, dim3(TG_BLOCK), smem, st, g, tm_cols, dbg));
-    else if (av) OO_CUDA(launch_pdl(k_gemm_tc<true, false>, grid, dim3(TG_BLOCK), smem, st, g, tm_cols, dbg));
-    else if (bv) OO_CUDA(launch_pdl(k_gemm_tc<false, true>, grid, dim3(TG_BLOCK), smem, st, g, tm_cols, dbg));
-    else OO_CUDA(launch_pdl(k_gemm_tc<false, false>, grid, dim3(TG_BLOCK), smem, st, g, tm_cols, dbg));
+    if (av && bv) OO_CUDA(launch_pdl(k_gemm_tc<true, true>, grid, dim3(TG_BLOCK), smem, st, cluster_z, g, tm_cols, cluster_z, dbg));
+    else if (av) OO_CUDA(launch_pdl(k_gemm_tc<true, false>, grid, dim3(TG_BLOCK), smem, st, cluster_z, g, tm_cols, cluster_z, dbg));
+    else if (bv) OO_CUDA(launch_pdl(k_gemm_tc<false, true>, grid, dim3(TG_BLOCK), smem, st, cluster_z, g, tm_cols, cluster_z, dbg));
+    else OO_CUDA(launch_pdl(k_gemm_tc<false, false>, grid, dim3(TG_BLOCK), smem, st, cluster_z, g, tm_cols, cluster_z, dbg));
     OO_LAUNCH_CHECK();
     return 0;
 }
