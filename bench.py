@@ -257,7 +257,8 @@ def run_ours(args):
     cfg = C.room0_config()
     cfg.training_device = cfg.data_device = str(dev)
     cfg.part_mode = bool(part_)
-    cfg.do_bg = False
+    cfg.do_bg = bool(args.bg)               # --bg 1: the reference's real loop (room_0.json do_bg: 1) -- the hidden-128 background
+                                            # model trains beside the ensemble every step (train.py:447-463); informative
     if (W_, H_) != (cfg.W, cfg.H):              # ScanNet shape (configs/ScanNet/scene0011_01.json:56-57)
         cfg.W, cfg.H = W_, H_
         cfg.fx = cfg.fy = 0.5 * W_
@@ -270,7 +271,7 @@ def run_ours(args):
     fill = args.fill_frames
     n_frames_total = fill + 2 * (frames_w + frames_t) + 12
     # every rank sees the same frames; object ids are spread so that rank r owns ids with (index % world == r)
-    synth = SyntheticScene(n_total, W=cfg.W, H=cfg.H, part_mode=cfg.part_mode, seed=0, pin=True, n_distinct=2)
+    synth = SyntheticScene(n_total, W=cfg.W, H=cfg.H, part_mode=cfg.part_mode, seed=0, pin=True, n_distinct=2, with_bg=cfg.do_bg)
     scene = Scene(cfg, rank=rank, world=world, seed=1234, max_frames=n_frames_total, flag_allreduce=D.make_flag_allreduce())
 
     def iters_of(frame_idx, n_frames, total):
@@ -322,6 +323,8 @@ def run_ours(args):
             # per step: k_train + k_update; per frame: k_gram (part features on), label counts + adam schedule, frame store,
             # sampler (two passes)
             launches["n"] += 2 * it + (1 if args.part else 0) + 2 + 1 + 2
+            if args.bg and scene.bg is not None:
+                launches["n"] += 47 * it + 2          # the background step (41-47 launches) + its sampling passes
 
     def resident(n_frames):
         """device copies of the next n_frames frames, made BEFORE the timed region"""
@@ -521,8 +524,10 @@ def run_ours(args):
             "scaling": "weak" if total_ is None else "strong", "vs_baseline": None, "dtype": "f32", "data": "synthetic",
             "config": {"workload": "BASELINE configs[%d]: %dx%d frames, %d objects in total (%d on rank 0) x 120 rays x 10 "
                                    "samples per step, part_mode=%d, 100 steps per frame; per-frame ingestion (shared keyframe "
-                                   "store) + sampling of all objects inside the timed region"
-                                   % (args.config - 1, cfg.W, cfg.H, n_all, n_obj, int(cfg.part_mode)),
+                                   "store) + sampling of all objects inside the timed region%s"
+                                   % (args.config - 1, cfg.W, cfg.H, n_all, n_obj, int(cfg.part_mode),
+                                      "; do_bg=1: the background model (hidden 128, 1200 rays x 14 samples) also trains every step, "
+                                      "on the last rank, its rays NOT counted in `value`" if cfg.do_bg else ""),
                        "objects_total": n_all, "objects_per_gpu": n_obj, "rays_per_step_per_object": R, "iters_per_frame": ITERS,
                        "l2": "inputs larger than L2: %.0f MB sampled batch per frame + part-feature table" %
                              (n_obj * ITERS * R * 181 / 1e6),
@@ -562,7 +567,8 @@ def run_ours(args):
                                      "bound": "hbm", "achieved": k3_bytes / (k3_ms * 1e-3) / 1e9, "peak": hbm_peak, "unit": "GB/s",
                                      "frac": k3_bytes / (k3_ms * 1e-3) / 1e9 / hbm_peak, "ms": k3_ms, "bytes_per_launch": k3_bytes}
         out["background"] = {"what": "separate background model (train.py:447-463): hidden %d, %d rays x %d samples per step, "
-                                     "layer-by-layer path, GEMMs as 3xTF32 mma.sync (fp32-level accuracy); NOT part of `value`" % (hb, Rb, Sb),
+                                     "layer-by-layer path, GEMMs as 3xTF32 tcgen05.mma (accumulators in tensor memory, fp32-level accuracy), clip head "
+                                     "applied per ray; NOT part of `value`" % (hb, Rb, Sb),
                              "ms_per_step": bg_ms, "rays_per_s": Rb / (bg_ms * 1e-3), "flop_per_step": bg_flop,
                              "achieved_tflops": bg_flop / (bg_ms * 1e-3) / 1e12, "frac_of_fma_peak": bg_flop / (bg_ms * 1e-3) / 1e12 / peak}
         if cpu is not None:
@@ -703,6 +709,7 @@ def main():
     ap.add_argument("--objects", type=int, default=60, help="objects per GPU")
     ap.add_argument("--part", type=int, default=1, help="part-level feature head on (room_0.json part_mode)")
     ap.add_argument("--fill-frames", type=int, default=20, help="untimed frames that fill the keyframe rings (SURVEY 8d)")
+    ap.add_argument("--bg", type=int, default=0, help="1 = also train the separate background model every step (room_0.json do_bg)")
     ap.add_argument("--no-cpu", action="store_true", help="skip the CPU baseline / GPU-eager reference legs")
     ap.add_argument("--config", type=int, default=2, choices=[2, 3, 4, 5],
                     help="BASELINE.json configs (1-based): 2 = room_0 shape, --objects per GPU (weak scaling; the headline); "

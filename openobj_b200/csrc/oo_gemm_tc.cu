@@ -363,7 +363,7 @@ __global__ void __launch_bounds__(TG_BLOCK, 1) k_gemm_tc(const GemmOp g, int tm_
                     for (int u = 0; u < NPA; ++u) {
                         if (row_sums) rs4[u] += (xa[u].x + xa[u].y) + (xa[u].z + xa[u].w);
                         const float4 l = split4(xa[u]);
-                        *reinterpret_cast<float4*>(a_hi + a_off[u]) = xa[u];
+                        if (dbg != 6) *reinterpret_cast<float4*>(a_hi + a_off[u]) = xa[u];
                         *reinterpret_cast<float4*>(a_lo + a_off[u]) = l;
                     }
                 }
@@ -372,7 +372,7 @@ __global__ void __launch_bounds__(TG_BLOCK, 1) k_gemm_tc(const GemmOp g, int tm_
                     for (int u = 0; u < NPB; ++u) {
                         if (!b_has[u]) continue;
                         const float4 l = split4(xb[u]);
-                        *reinterpret_cast<float4*>(b_hi + b_off[u]) = xb[u];
+                        if (dbg != 6) *reinterpret_cast<float4*>(b_hi + b_off[u]) = xb[u];
                         *reinterpret_cast<float4*>(b_lo + b_off[u]) = l;
                     }
                 }
