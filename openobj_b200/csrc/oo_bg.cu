@@ -492,32 +492,40 @@ __global__ void k_embed_gather_grad(const EmbedBufs g, int n_pts, float* __restr
 constexpr int EB_PTS = 32;        // points per block
 __global__ void __launch_bounds__(NDIR * 4) k_embed_bwd(const float* __restrict__ pcs, const float* __restrict__ Bm, float scale,
                                                          int n_pts, const EmbedBufs g, float* __restrict__ partial) {
-    // thread = (direction d, point lane q of 4); each walks EB_PTS / 4 points
-    const int d = threadIdx.x >> 2, q = threadIdx.x & 3;
+    // thread = (point lane q of 4, direction d) with d fastest: the 21 directions of a band are 84 contiguous bytes of a row.
+    // cos(2^k theta) for the six bands from ONE sincosf by angle doubling (as the fused tile, oo_tile.h phase 30: the reference's
+    // argument for band k is exactly 2^k times that of band 0); each thread walks EB_PTS / 4 points
+    __shared__ float sh[4][NDIR * 3];
+    const int d = threadIdx.x % NDIR, q = threadIdx.x / NDIR;
     const float b0 = Bm[3 * d], b1 = Bm[3 * d + 1], b2 = Bm[3 * d + 2];
     float s0 = 0.f, s1 = 0.f, s2 = 0.f;
     const int p_end = min(n_pts, (int)(blockIdx.x + 1) * EB_PTS);
     for (int p = blockIdx.x * EB_PTS + q; p < p_end; p += 4) {
         const float t0 = pcs[3 * (size_t)p] / scale, t1 = pcs[3 * (size_t)p + 1] / scale, t2 = pcs[3 * (size_t)p + 2] / scale;
-        const float arg = (b0 * t0 + b1 * t1 + b2 * t2) * PI_F;
-        float band = 1.f, dp = 0.f;
+        float sn, cs;
+        sincosf((b0 * t0 + b1 * t1 + b2 * t2) * PI_F, &sn, &cs);
+        float de[NBAND];
+#pragma unroll
+        for (int k = 0; k < NBAND; ++k) {                       // all loads before the dependent chain
+            const int idx = 3 + NDIR * k + d;
+            de[k] = idx < E1 ? g.x1[(size_t)p * g.ld1 + idx] + g.xc[(size_t)p * g.ldc + g.h + idx]
+                             : g.xh[(size_t)p * g.ldh + g.h + idx - E1];
+        }
+        float band = PI_F, dp = 0.f;
 #pragma unroll
         for (int k = 0; k < NBAND; ++k) {
-            const int idx = 3 + NDIR * k + d;
-            const float de = idx < E1 ? g.x1[(size_t)p * g.ld1 + idx] + g.xc[(size_t)p * g.ldc + g.h + idx]
-                                      : g.xh[(size_t)p * g.ldh + g.h + idx - E1];
-            dp += de * (cosf(arg * band) * (PI_F * band));
+            dp += de[k] * (cs * band);
+            const float s2_ = 2.f * sn * cs, c2_ = (cs - sn) * (cs + sn);
+            sn = s2_; cs = c2_;
             band *= 2.f;
         }
         s0 += dp * t0; s1 += dp * t1; s2 += dp * t2;
     }
-    s0 += __shfl_xor_sync(0xffffffffu, s0, 1); s0 += __shfl_xor_sync(0xffffffffu, s0, 2);
-    s1 += __shfl_xor_sync(0xffffffffu, s1, 1); s1 += __shfl_xor_sync(0xffffffffu, s1, 2);
-    s2 += __shfl_xor_sync(0xffffffffu, s2, 1); s2 += __shfl_xor_sync(0xffffffffu, s2, 2);
-    if (q == 0) {
-        float* o = partial + (size_t)blockIdx.x * (NDIR * 3) + 3 * d;
-        o[0] = s0; o[1] = s1; o[2] = s2;
-    }
+    sh[q][3 * d] = s0; sh[q][3 * d + 1] = s1; sh[q][3 * d + 2] = s2;
+    __syncthreads();
+    if (threadIdx.x < NDIR * 3)
+        partial[(size_t)blockIdx.x * (NDIR * 3) + threadIdx.x] =
+            (sh[0][threadIdx.x] + sh[1][threadIdx.x]) + (sh[2][threadIdx.x] + sh[3][threadIdx.x]);
 }
 
 __global__ void __launch_bounds__(256) k_embed_bwd_reduce(const float* __restrict__ partial, int nblk, float* __restrict__ dB) {
