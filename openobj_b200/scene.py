@@ -111,7 +111,7 @@ class Scene:
         self.batch = None
         self.sample_out = None
         self._copy_stream = None
-        self._sorted_ids = (None, None)
+        self._sorted_ids = (None, None, None)
         self._vis_cache = (None, None, None, None)
         self._bbox_cache = {}
         self._sample_cache = {}
@@ -162,9 +162,12 @@ class Scene:
             self._part_event = None
 
     def _ids_of(self, bbox_dict):
-        """Sorted instance ids of a frame (torch.unique order, train.py:191); cached while the same dict object comes back."""
-        if self._sorted_ids[0] is not bbox_dict:
-            self._sorted_ids = (bbox_dict, sorted(int(k) for k in bbox_dict.keys()))
+        """Sorted instance ids of a frame (torch.unique order, train.py:191); cached while the same dict object comes back with
+        the same keys (a dict mutated in place -- other ids, same length -- is noticed: its key tuple is compared)."""
+        keys = tuple(bbox_dict.keys())
+        if self._sorted_ids[0] is not bbox_dict or self._sorted_ids[2] != keys:
+            self._sorted_ids = (bbox_dict, sorted(int(k) for k in keys), keys)
+            self._vis_cache = (None, None, None, None)
         return self._sorted_ids[1]
 
     def _place_all(self, tab, placed, store_slot, frame_id):
