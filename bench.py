@@ -368,6 +368,7 @@ def run_ours(args):
     # ---- end-to-end pass: host (pinned) frame -> H2D -> append -> sample -> train -> D2H loss
     run_frames(1, min(warmup, ITERS), host=True)
     torch.cuda.synchronize(); D.barrier()
+    h2d0 = scene.h2d_bytes
     e0.record()
     run_frames(frames_t, steps, host=True)
     e1.record()
@@ -376,8 +377,10 @@ def run_ours(args):
     ms_e2e = D.max_over_ranks(e0.elapsed_time(e1), dev)
     n_all = int(D.sum_over_ranks(n_obj, dev))
     rays = n_all * R * steps
-    h2d_per_step = synth.frame_bytes() / ITERS
-    d2h_per_step = 4.0 / ITERS
+    # bytes Scene.stage_frame actually moved during the timed e2e pass (a sharded rank gathers only its objects' part-feature
+    # rows) + the poses; per step of this window
+    h2d_per_step = (scene.h2d_bytes - h2d0 + 128 * frames_t) / steps
+    d2h_per_step = 4.0 * frames_t / steps
 
     out = None
     if rank == 0:

@@ -308,6 +308,12 @@ typedef struct oo_store_args {
     int32_t* store_rgbi; float* store_depth; float* store_twc;
 } oo_store_args;
 int oo_store_frame(const oo_store_args* a, void* stream);
+/* Part-feature cells of a frame, only inside the given boxes (train.py:183-188 copies the whole [W/5][H/5][512] tensor; a rank of
+ * a sharded run only ever gathers rows inside its own objects' boxes, vmap.py:437-452).  src_host: the frame's tensor in PINNED
+ * host memory (read by the kernel over the host link), dst: the same-shaped slot of the resident table on the device,
+ * boxes: HOST int32 [n_boxes][4] = w_lo, w_hi, h_lo, h_hi in cells, inclusive; at most 192 boxes per call. */
+int oo_gather_part_rows(const float* src_host, float* dst, int pw, int ph, int n_feat, const int32_t* boxes, int n_boxes,
+                        void* stream);
 /* counter-based uniform / normal tapes keyed by (seed, frame, object id, element) -- shard independent. */
 int oo_rng_fill(uint64_t seed, uint32_t frame, const int32_t* obj_ids, int n_obj, int64_t per_obj,
                 int kind /*0 uniform [0,1), 1 normal(0,std)*/, float std, float* out, void* stream);

@@ -103,6 +103,7 @@ _SIGS = {
                        c_float, c_void_p], c_int),
     "oo_sample_rays": ([POINTER(SampleArgs), c_void_p], c_int),
     "oo_store_frame": ([POINTER(StoreArgs), c_void_p], c_int),
+    "oo_gather_part_rows": ([c_void_p, c_void_p, c_int, c_int, c_int, c_void_p, c_int, c_void_p], c_int),
     "oo_rng_fill": ([c_uint64, c_uint32, c_void_p, c_int, c_int64, c_int, c_float, c_void_p, c_void_p], c_int),
     "oo_rng_fill_rows": ([c_uint64, c_uint32, c_void_p, c_int, c_int, c_int, c_int, c_float, c_void_p, c_void_p], c_int),
     "oo_render_object": ([POINTER(RenderArgs), c_void_p], c_int),

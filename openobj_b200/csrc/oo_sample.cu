@@ -589,6 +589,41 @@ extern "C" int oo_store_frame(const oo_store_args* a, void* stream) {
     return 0;
 }
 
+// ---- part-feature rows of a frame, only where this rank's objects can sample them.  src is the frame's [pw][ph][C] tensor in
+// PINNED HOST memory (device-addressable under unified addressing): the kernel reads the cells of each box straight over the
+// host link and writes them to the same cells of the resident table slot -- a rank of a sharded run moves the boxes' worth
+// of the 66.8 MB, not all of it.  Boxes may overlap (a cell is then written twice with the same values).
+namespace {
+constexpr int GATHER_MAX_BOXES = 192;
+struct GatherBoxes { int n, pw, ph, c4; int box[GATHER_MAX_BOXES][4]; };
+__global__ void __launch_bounds__(128) k_gather_part(const float4* __restrict__ src, float4* __restrict__ dst, const GatherBoxes b) {
+    const int w0 = b.box[blockIdx.x][0], w1 = b.box[blockIdx.x][1], h0 = b.box[blockIdx.x][2], h1 = b.box[blockIdx.x][3];
+    const int nh = h1 - h0 + 1, cells = (w1 - w0 + 1) * nh;
+    for (int c = blockIdx.y; c < cells; c += gridDim.y) {
+        const size_t cell = (size_t)(w0 + c / nh) * b.ph + (h0 + c % nh);
+        for (int q = threadIdx.x; q < b.c4; q += blockDim.x) dst[cell * b.c4 + q] = src[cell * b.c4 + q];
+    }
+}
+}  // namespace
+
+extern "C" int oo_gather_part_rows(const float* src_host, float* dst, int pw, int ph, int n_feat, const int32_t* boxes, int n_boxes,
+                                   void* stream) {
+    OO_REQUIRE(src_host && dst && boxes, "oo_gather_part_rows: null argument");
+    OO_REQUIRE(pw > 0 && ph > 0 && n_feat > 0 && (n_feat & 3) == 0, "oo_gather_part_rows: bad shape");
+    OO_REQUIRE(n_boxes >= 1 && n_boxes <= GATHER_MAX_BOXES, "oo_gather_part_rows: 1 .. %d boxes per call", GATHER_MAX_BOXES);
+    GatherBoxes b;
+    b.n = n_boxes; b.pw = pw; b.ph = ph; b.c4 = n_feat / 4;
+    for (int i = 0; i < n_boxes; ++i) {
+        for (int k = 0; k < 4; ++k) b.box[i][k] = boxes[4 * i + k];
+        OO_REQUIRE(0 <= b.box[i][0] && b.box[i][0] <= b.box[i][1] && b.box[i][1] < pw && 0 <= b.box[i][2] && b.box[i][2] <= b.box[i][3] &&
+                       b.box[i][3] < ph, "oo_gather_part_rows: box %d outside the [%d x %d] cell grid", i, pw, ph);
+    }
+    k_gather_part<<<dim3(n_boxes, 16), 128, 0, (cudaStream_t)stream>>>(reinterpret_cast<const float4*>(src_host),
+                                                                      reinterpret_cast<float4*>(dst), b);
+    OO_LAUNCH_CHECK();
+    return 0;
+}
+
 extern "C" int oo_sample_rays(const oo_sample_args* a, void* stream) {
     OO_REQUIRE(a, "oo_sample_rays: null args");
     OO_REQUIRE(a->n_obj > 0 && a->n_frames > 0 && a->n_samples > 0, "oo_sample_rays: empty request");

@@ -11,6 +11,8 @@ Objects are sharded by ensemble index k (order of first appearance): rank = k % 
 only: (1) the per-step zero-mask bits, OR-reduced once per frame; (2) the fact that ANY new object restarts Adam's moments
 and step counts for every object (the reference restacks all models into fresh tensors on update_vmap, train.py:272-276) --
 every rank sees every frame's object ids, so each applies that reset locally without communication."""
+import ctypes
+
 import numpy as np
 import torch
 
@@ -19,6 +21,7 @@ from .background import BackgroundModel
 from .dist import ShardBook
 from .ensemble import Ensemble, FrameBatch
 from .framestore import FrameStore
+from ._lib import check, lib, ptr
 
 
 class _Tables:
@@ -116,6 +119,9 @@ class Scene:
         self._bbox_cache = {}
         self._sample_cache = {}
         self._staged_pending, self._part_event = 0, None
+        self.h2d_bytes = 0                # bytes stage_frame has moved host -> device so far
+        self._host_keep = []
+        self.gather_fraction = 0.6        # stage_frame gathers part-feature rows per box when the boxes cover less than this
         self._empty_bits = None
         # the separate background model (train.py:236-242): one hidden-128 model, not part of the vmap ensemble; it lives
         # on the last rank (the ensemble's round-robin starts at rank 0)
@@ -138,6 +144,7 @@ class Scene:
                 v = sample.get(k)
                 if torch.is_tensor(v) and v.device != self.device:
                     out[k] = v.to(self.device, non_blocking=True)
+                    self.h2d_bytes += v.numel() * v.element_size()
             ev = torch.cuda.Event()
             ev.record(self._copy_stream)
             out["_staged"] = ev
@@ -147,13 +154,59 @@ class Scene:
                 if slot >= self.part_table.shape[0]:
                     raise RuntimeError("part-feature table full: raise max_frames")
                 # nothing reads this slot yet: rows of the table are only reached through keyframes already ingested
-                self.part_table[slot].copy_(pf, non_blocking=True)           # train.py:183-188, without a staging copy
+                boxes = self._part_boxes(sample["bbox_dict"], pf) if self._staged_pending == 0 else None
+                if boxes is not None:
+                    # a rank of a sharded run only ever gathers feature rows inside its own objects' boxes (vmap.py:437-452):
+                    # the kernel reads those cells straight from the pinned host tensor instead of moving all 66.8 MB
+                    check(lib().oo_gather_part_rows(ctypes.c_void_p(pf.data_ptr()), ptr(self.part_table[slot]), self.pw, self.ph,
+                                                    self.part_table.shape[-1], ctypes.c_void_p(boxes.ctypes.data), int(boxes.shape[0]),
+                                                    ctypes.c_void_p(self._copy_stream.cuda_stream)), "oo_gather_part_rows")
+                    self.h2d_bytes += int(((boxes[:, 1] - boxes[:, 0] + 1) * (boxes[:, 3] - boxes[:, 2] + 1)).sum()) * self.part_table.shape[-1] * 4
+                else:
+                    self.part_table[slot].copy_(pf, non_blocking=True)       # train.py:183-188, without a staging copy
+                    self.h2d_bytes += pf.numel() * pf.element_size()
                 ev2 = torch.cuda.Event()
                 ev2.record(self._copy_stream)
                 out["_part_slot"], out["_part_event"] = slot, ev2
+                # the gather kernel reads the host tensor itself: it must outlive the kernel, whatever the caller does with it
+                self._host_keep = [(e, t) for e, t in self._host_keep if not e.query()] + [(ev2, pf)]
                 out.pop("part_feat", None)
         self._staged_pending += 1
         return out
+
+    def _part_boxes(self, bd, pf):
+        """int32 [n, 4] cell boxes (w_lo, w_hi, h_lo, h_hi, inclusive) of the part-feature rows this rank can sample from the
+        frame with boxes `bd`, or None when moving the whole tensor is the better (or the only correct) choice: the background
+        model samples everywhere; objects first seen in this frame are assigned with ShardBook's rule (ascending id, next
+        ensemble index) without touching the book; K2 clamps pixel / 5 to the grid (oo_sample.cu gather_ray)."""
+        if not (pf.device.type == "cpu" and pf.is_pinned() and pf.is_contiguous() and pf.dtype == torch.float32):
+            return None
+        if self.cfg.do_bg and self.rank == self.bg_rank:
+            return None
+        gi, k_next, mine = self.book.global_index, len(self.book.global_index), []
+        for i in self._ids_of(bd):
+            if i == -1 or (self.cfg.do_bg and i == 0):
+                continue
+            k = gi.get(i)
+            if k is None:
+                if k_next >= self.book.cap:
+                    continue
+                k, k_next = k_next, k_next + 1
+            if k % self.world == self.rank:
+                mine.append(i)
+        if not mine or len(mine) > 192:
+            return None
+        bb = np.stack([self._bbox_np(i, bd[i]) for i in mine]).astype(np.float64)
+        pd = float(self.cfg.part_down)
+        box = np.empty((len(mine), 4), dtype=np.int32)
+        box[:, 0] = np.clip(np.floor(bb[:, 0] / pd), 0, self.pw - 1)
+        box[:, 1] = np.clip(np.floor(bb[:, 1] / pd), 0, self.pw - 1)
+        box[:, 2] = np.clip(np.floor(bb[:, 2] / pd), 0, self.ph - 1)
+        box[:, 3] = np.clip(np.floor(bb[:, 3] / pd), 0, self.ph - 1)
+        cells = int(((box[:, 1] - box[:, 0] + 1) * (box[:, 3] - box[:, 2] + 1)).sum())
+        if cells > self.gather_fraction * self.pw * self.ph:
+            return None                   # the boxes cover most of the frame (single-GPU runs): one DMA of everything is cheaper
+        return np.ascontiguousarray(box)
 
     def _wait_part_features(self):
         """Training kernels gather rows of the part-feature table: the newest frame's rows must have landed."""

@@ -209,3 +209,46 @@ def test_staged_frames_with_part_features_equal_direct_frames():
         res.append((sc.ens.theta.clone(), torch.stack(terms), sc.part_table[:4].clone()))
     assert torch.equal(res[0][2], res[1][2])
     assert torch.equal(res[0][0], res[1][0]) and torch.equal(res[0][1], res[1][1])
+
+
+@pytest.mark.parametrize("rank", [0, 1])
+def test_sharded_staging_gathers_only_local_part_rows(rank):
+    """A rank of a sharded run stages the part features of a frame by reading ONLY the cells inside its own objects' boxes from
+    the pinned host tensor (oo_gather_part_rows), objects first seen in that frame included: parameters and loss terms must be
+    bit-identical to the same rank fed whole frames directly."""
+    from openobj_b200 import cfg as C
+    from openobj_b200.scene import Scene
+    from openobj_b200.synthetic import SyntheticScene
+    res = []
+    for staged in (False, True):
+        torch.manual_seed(5)
+        cfg = C.room0_config()
+        cfg.do_bg = False
+        cfg.part_mode = True
+        cfg.W, cfg.H = 320, 240
+        cfg.fx = cfg.fy = 160.0
+        cfg.cx, cfg.cy = 159.5, 119.5
+        cfg.n_iter_per_frame = 5
+        cfg.max_n_models = 6
+        synth = SyntheticScene(6, W=cfg.W, H=cfg.H, part_mode=True, seed=9, n_distinct=2, pin=True)
+        sc = Scene(cfg, rank=rank, world=2, seed=3, max_frames=6)
+        sc.gather_fraction = 2.0                    # always gather (the default only does when the boxes cover < 60 % of the frame)
+        n_loc = 3
+        lt = torch.zeros(cfg.n_iter_per_frame, n_loc, 4, device=DEV)
+        terms = []
+        nxt = sc.stage_frame(synth.frame(0)) if staged else synth.frame(0)
+        for f in range(3):
+            sc.add_frame(nxt)
+            if f + 1 < 3:
+                nxt = sc.stage_frame(synth.frame(f + 1)) if staged else synth.frame(f + 1)
+            sc.sample()
+            sc.train(loss_terms=lt)
+            terms.append(lt.clone())
+        torch.cuda.synchronize()
+        assert len(sc.obj_dict) == n_loc and bool(torch.isfinite(torch.stack(terms)).all())
+        assert float(torch.stack(terms)[..., 3].abs().max()) > 0.0
+        if staged:
+            full = 3 * (synth.frame_bytes() - 128)
+            assert 0 < sc.h2d_bytes < full            # fewer bytes than three whole frames crossed the host link
+        res.append((sc.ens.theta.clone(), torch.stack(terms)))
+    assert torch.equal(res[0][0], res[1][0]) and torch.equal(res[0][1], res[1][1])
